@@ -1,0 +1,223 @@
+/*
+ * sarpro_gpu.h — C ABI of libsarpro_gpu.so: the B200 (sm_100a) implementation of SARPRO's
+ * per-pixel raster hot path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * The reference (bogwi/sarpro, Rust) has no FFI/plugin interface for this path; the seam is the
+ * set of pure functions in src/core/processing (pipeline, autoscale, ops, resize, padding, synthetic_rgb).  Each entry point below names the reference
+ * function (file:line, relative to the reference root) whose body it replaces.  The Rust-side
+ * binding (`sarpro-gpu-sys`) a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions (mirroring the reference):
+ *   - inputs are borrowed, outputs are caller-allocated; the library never frees caller memory;
+ *   - every call is synchronous and returns 0 on success or a negative sarpro_status;
+ *     sarpro_last_error(ctx) then holds the message the Rust side wraps in Error::External(String)
+ *     (src/error.rs:43-47).  No exception or abort crosses the boundary;
+ *   - a sarpro_ctx is single-threaded (the reference calls this path from one thread at a time);
+ *     distinct contexts may be used concurrently;
+ *   - enum discriminants equal the Rust declaration order;
+ *   - pointers are HOST pointers unless the parameter is named *_dev or the descriptor says
+ *     SARPRO_LOC_DEVICE.  Pinned host memory (sarpro_host_alloc) makes the copies asynchronous.
+ *   - there is NO CPU fallback: without a CUDA device sarpro_ctx_create fails with
+ *     SARPRO_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef SARPRO_GPU_H
+#define SARPRO_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SARPRO_GPU_ABI_VERSION 1
+
+/* ---- enums (discriminants = Rust declaration order) ------------------------------------ */
+/* AutoscaleStrategy, src/types.rs:115-123 */
+typedef enum sarpro_strategy {
+    SARPRO_STRATEGY_STANDARD = 0, SARPRO_STRATEGY_ROBUST = 1, SARPRO_STRATEGY_ADAPTIVE = 2,
+    SARPRO_STRATEGY_EQUALIZED = 3, SARPRO_STRATEGY_CLAHE = 4, SARPRO_STRATEGY_TAMED = 5,
+    SARPRO_STRATEGY_DEFAULT = 6
+} sarpro_strategy;
+/* BitDepth, src/types.rs:170-173 */
+typedef enum sarpro_bit_depth { SARPRO_U8 = 0, SARPRO_U16 = 1 } sarpro_bit_depth;
+/* PolarizationOperation, src/types.rs:8-14 */
+typedef enum sarpro_pol_operation {
+    SARPRO_OP_SUM = 0, SARPRO_OP_DIFF = 1, SARPRO_OP_RATIO = 2, SARPRO_OP_NDIFF = 3, SARPRO_OP_LOGRATIO = 4,
+    SARPRO_OP_NONE = -1
+} sarpro_pol_operation;
+/* SyntheticRgbMode, src/types.rs:177-182 (all four alias Default, synthetic_rgb.rs:72-79) */
+typedef enum sarpro_synrgb_mode {
+    SARPRO_SYNRGB_DEFAULT = 0, SARPRO_SYNRGB_RGB_RATIO = 1, SARPRO_SYNRGB_SAR_URBAN = 2, SARPRO_SYNRGB_ENHANCED = 3
+} sarpro_synrgb_mode;
+/* OutputFormat, src/types.rs:162-165 (JPEG forces U8, save.rs:121,321) */
+typedef enum sarpro_output_format { SARPRO_FORMAT_TIFF = 0, SARPRO_FORMAT_JPEG = 1 } sarpro_output_format;
+
+typedef enum sarpro_dtype { SARPRO_DT_F32 = 0, SARPRO_DT_U16 = 1 } sarpro_dtype;
+typedef enum sarpro_location { SARPRO_LOC_HOST = 0, SARPRO_LOC_DEVICE = 1 } sarpro_location;
+
+typedef enum sarpro_status {
+    SARPRO_OK = 0,
+    SARPRO_ERR_INVALID_ARGUMENT = -1,
+    SARPRO_ERR_NO_DEVICE = -2,      /* no CUDA device / driver: the library has no CPU path */
+    SARPRO_ERR_CUDA = -3,
+    SARPRO_ERR_OUT_OF_MEMORY = -4,
+    SARPRO_ERR_U16_REQUIRED = -5,   /* "U16 data required for U16 bit depth" resize.rs:162,221 padding.rs:36 */
+    SARPRO_ERR_TOO_LARGE = -6,
+    SARPRO_ERR_COMM = -7,
+    SARPRO_ERR_INTERNAL = -8
+} sarpro_status;
+
+/* ---- plain structs --------------------------------------------------------------------- */
+/* HistogramStats (autoscale.rs:7-24) + the chosen window, so the host can emit the reference's
+ * info!/debug! lines (autoscale.rs:398-401, 431-434, 485-488, 566-569). */
+typedef struct sarpro_stats {
+    uint64_t valid_count;
+    double min_db, max_db, mean_db, std_db, median_db;
+    double p01, p02, p05, p10, p25, p75, p90, p95, p98, p99;
+    double low_clip, high_clip, gamma;
+} sarpro_stats;
+
+/* tuple returned by resize_image_data_with_meta, resize.rs:99-110 */
+typedef struct sarpro_resize_meta {
+    uint64_t cols, rows;
+    double scale_x, scale_y;
+    uint64_t pad_left, pad_top;
+} sarpro_resize_meta;
+
+/* One input band: a row-major rows x cols raster (Array2<f32> at the reference boundary,
+ * gdal.rs:123-131; or the raw u16 DN the f32 was read from). */
+typedef struct sarpro_band {
+    const void* data;
+    int32_t dtype;     /* sarpro_dtype */
+    int32_t location;  /* sarpro_location */
+    uint64_t rows, cols;
+} sarpro_band;
+
+/* One output raster, caller-allocated. channels: 1 (gray) or 3 (interleaved RGB). */
+typedef struct sarpro_image {
+    void* data;              /* u8 or u16 samples */
+    int32_t location;        /* sarpro_location */
+    int32_t bit_depth;       /* sarpro_bit_depth of `data` */
+    uint64_t capacity_bytes; /* size of the caller's buffer; checked */
+    uint64_t cols, rows;     /* filled by the library */
+    int32_t channels;        /* filled by the library */
+    int32_t reserved;
+    sarpro_resize_meta meta; /* filled by the library */
+} sarpro_image;
+
+/* Time spent on the device for the last pipeline call (CUDA events on the ctx stream). */
+typedef struct sarpro_timing {
+    float total_ms;      /* first kernel/copy -> last kernel/copy on the ctx stream */
+    float h2d_ms, d2h_ms;
+    float kernel_ms;     /* total_ms minus copies when they are serialised */
+    uint32_t kernel_launches;
+    uint32_t host_syncs; /* planner round trips */
+    uint64_t h2d_bytes, d2h_bytes;
+} sarpro_timing;
+
+typedef struct sarpro_ctx sarpro_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int sarpro_abi_version(void);
+/* Creates a context on CUDA device `device_id`. Fails (SARPRO_ERR_NO_DEVICE) without a GPU. */
+int sarpro_ctx_create(sarpro_ctx** out, int device_id);
+void sarpro_ctx_destroy(sarpro_ctx* ctx);
+/* Message for the last failing call on ctx (ctx==NULL: last sarpro_ctx_create failure on this thread). */
+const char* sarpro_last_error(const sarpro_ctx* ctx);
+/* Run the context on a caller-owned CUDA stream (cudaStream_t) instead of its own. */
+int sarpro_ctx_set_stream(sarpro_ctx* ctx, void* cuda_stream);
+int sarpro_ctx_synchronize(sarpro_ctx* ctx);
+int sarpro_last_timing(const sarpro_ctx* ctx, sarpro_timing* out);
+/* Pinned host memory for inputs/outputs (optional; pageable pointers also work). */
+int sarpro_host_alloc(void** out, size_t bytes);
+void sarpro_host_free(void* p);
+int sarpro_host_register(void* p, size_t bytes);
+void sarpro_host_unregister(void* p);
+
+/* ---- stage level: 1:1 with the reference functions ------------------------------------- */
+/* ops.rs:4-44  sum_arrays / difference_arrays / ratio_arrays / normalized_diff_arrays / log_ratio_arrays */
+int sarpro_pol_op(sarpro_ctx* ctx, int op, const float* a, const float* b, size_t rows, size_t cols, float* out);
+
+/* pipeline.rs:42-66  process_scalar_data_pipeline (dB + mask + autoscale dispatch + bit depth,
+ * autoscale.rs:662-704). The f64 dB plane and mask are not materialised (callers only use .dim(),
+ * save.rs:53,122,201,329). out_u8 is filled for U8, out_u16 for U16; the other may be NULL. */
+int sarpro_process_scalar_data_pipeline(sarpro_ctx* ctx, const float* v, size_t rows, size_t cols, int bit_depth,
+                                        int strategy, uint8_t* out_u8, uint16_t* out_u16, sarpro_stats* stats);
+/* Same result as casting the u16 DN raster to f32 first (gdal.rs:123) and calling the above. */
+int sarpro_process_dn_pipeline(sarpro_ctx* ctx, const uint16_t* dn, size_t rows, size_t cols, int bit_depth,
+                               int strategy, uint8_t* out_u8, uint16_t* out_u16, sarpro_stats* stats);
+/* pipeline.rs:8-40  process_scalar_data_inplace (only for callers that really want the planes) */
+int sarpro_process_scalar_data_inplace(sarpro_ctx* ctx, const float* v, size_t rows, size_t cols, double* db,
+                                       uint8_t* valid_mask);
+/* autoscale.rs:710-742  autoscale_db_image_tamed_synrgb_u8 (takes the linear band, not the dB plane) */
+int sarpro_autoscale_tamed_synrgb_u8(sarpro_ctx* ctx, const float* v, size_t rows, size_t cols, int is_copol,
+                                     uint8_t* out);
+/* autoscale.rs:348-364  scale_u16_to_u8 */
+int sarpro_scale_u16_to_u8(sarpro_ctx* ctx, const uint16_t* data, size_t n, uint8_t* out);
+
+/* resize.rs:6-30 calculate_resize_dimensions + the control flow of resize.rs:112-236 + padding.rs:12
+ * (pure host arithmetic; no context needed): dims of the buffer resize_image_data_with_meta returns. */
+int sarpro_resize_output_dims(size_t cols, size_t rows, int has_target, size_t target, int pad, size_t* out_cols,
+                              size_t* out_rows);
+/* resize.rs:91-236 resize_image_data_with_meta (Lanczos3 of resize.rs:32-89 + padding.rs:5-49).
+ * u8_data is used for U8, u16_data for U16 (NULL -> SARPRO_ERR_U16_REQUIRED). */
+int sarpro_resize_image_data_with_meta(sarpro_ctx* ctx, const uint8_t* u8_data, const uint16_t* u16_data,
+                                       size_t cols, size_t rows, int has_target, size_t target, int bit_depth,
+                                       int pad, uint8_t* out_u8, uint16_t* out_u16, sarpro_resize_meta* meta);
+/* padding.rs:5-49 add_padding_to_square */
+int sarpro_add_padding_to_square(sarpro_ctx* ctx, const uint8_t* u8_data, const uint16_t* u16_data, size_t cols,
+                                 size_t rows, int bit_depth, uint8_t* out_u8, uint16_t* out_u16);
+/* synthetic_rgb.rs:182-197 create_synthetic_rgb_by_mode_and_strategy (-> :10-67 or :88-178) */
+int sarpro_create_synthetic_rgb_by_mode_and_strategy(sarpro_ctx* ctx, int mode, int strategy, const uint8_t* band1,
+                                                     const uint8_t* band2, size_t n, uint8_t* rgb);
+
+/* ---- fused pipelines: what save.rs / api/mod.rs run per product; data stays in HBM ------ */
+/* Single band (optionally a polarization op of two bands, sentinel1.rs:1497-1579 -> ops.rs):
+ * save.rs:49-65 / 119-134 and api/mod.rs:84-130, 250-281, 284-369.
+ * b is ignored when op == SARPRO_OP_NONE. JPEG forces U8. */
+int sarpro_pipeline_single(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, int op, int format,
+                           int bit_depth, int strategy, int has_target, size_t target, int pad, sarpro_image* out,
+                           sarpro_stats* stats);
+/* Two-band TIFF: save.rs:199-316, api/mod.rs:133-200 (independent statistics per band). */
+int sarpro_pipeline_multiband_tiff(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_band* b2, int bit_depth,
+                                   int strategy, int has_target, size_t target, int pad, sarpro_image* out1,
+                                   sarpro_image* out2, sarpro_stats* stats2 /* [2] or NULL */);
+/* Synthetic-RGB JPEG: save.rs:317-368 (tamed_band_step != 0: band-specific Tamed autoscale of
+ * save.rs:324-328,347-351) or api/mod.rs:203-247 (tamed_band_step == 0). out is interleaved RGB u8. */
+int sarpro_pipeline_synrgb(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_band* b2, int strategy, int mode,
+                           int has_target, size_t target, int pad, int tamed_band_step, sarpro_image* out,
+                           sarpro_stats* stats2 /* [2] or NULL */);
+
+/* ---- multi-GPU: one process per GPU, a scene row-band-sharded across ranks --------------- */
+/* The library dlopen()s libnccl.so.2 and runs its own small collectives (DN-histogram and CLAHE
+ * tile-histogram all-reduce, min/max all-reduce, gather of the resized rows) on the ctx stream.
+ * The host only ships the 128-byte ncclUniqueId between ranks (any transport). */
+int sarpro_comm_unique_id(void* out128);
+int sarpro_comm_init(sarpro_ctx* ctx, const void* unique_id128, int rank, int world);
+int sarpro_comm_destroy(sarpro_ctx* ctx);
+/* Row band [*r0,*r1) owned by `rank`; with clahe != 0 the edges are aligned to the CLAHE tile
+ * height ceil(rows/8) (autoscale.rs:235). Pure host arithmetic. */
+int sarpro_shard_rows(size_t rows, int world, int rank, int clahe, size_t* r0, size_t* r1);
+/* Source rows [*h0,*h1) a rank must hold to produce its share of a resize to `target` (its own
+ * band plus the vertical Lanczos halo). Pure host arithmetic. */
+int sarpro_shard_halo_rows(size_t rows, size_t cols, int has_target, size_t target, int world, int rank, int clahe,
+                           size_t* h0, size_t* h1);
+/* Sharded synthetic-RGB pipeline. b1/b2 describe THIS rank's rows [h0,h1) of the scene
+ * (rows field = h1-h0); scene_rows is the full height. The full output lands on rank 0. */
+int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_band* b2, size_t scene_rows,
+                                   int strategy, int mode, int has_target, size_t target, int pad,
+                                   int tamed_band_step, sarpro_image* out);
+
+/* ---- host-only planner entry points (pure CPU; used by tests and by multi-rank hosts) ---- */
+/* Statistics + window + DN->sample LUT from a 65,536-bin DN histogram, i.e. what
+ * compute_histogram_stats (autoscale.rs:35-160) + autoscale_db_image[_advanced] (:368-659) +
+ * scale_u16_to_u8 (:348-364) yield for a u16 raster with that histogram. lut16 has 65536 entries.
+ * For CLAHE the LUT holds the 256-bin index of autoscale.rs:263 (the blend needs pixel positions). */
+int sarpro_plan_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int strategy, sarpro_stats* stats,
+                                  uint16_t* lut16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SARPRO_GPU_H */

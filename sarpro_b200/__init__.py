@@ -1,0 +1,16 @@
+"""sarpro_b200 — B200 (sm_100a) implementation of SARPRO's per-pixel raster hot path.
+
+The compute lives in libsarpro_gpu.so (sarpro_b200/csrc, C ABI in include/sarpro_gpu.h); this package
+is the ctypes binding plus a host-side mirror of the reference's function names. There is no CPU or
+pure-Python path: importing works anywhere, using it needs the built library and a B200.
+"""
+from . import _ffi
+from ._ffi import (ADAPTIVE, CLAHE, DEFAULT, EQUALIZED, JPEG, OP_DIFF, OP_LOGRATIO, OP_NDIFF, OP_NONE, OP_RATIO,
+                   OP_SUM, ROBUST, STANDARD, STRATEGY_NAMES, TAMED, TIFF, U8, U16)
+from .api import Context, ProcessedImage, SarproError, plan_from_dn_histogram, shard_rows
+
+__all__ = [
+    "Context", "ProcessedImage", "SarproError", "plan_from_dn_histogram", "shard_rows", "_ffi",
+    "STANDARD", "ROBUST", "ADAPTIVE", "EQUALIZED", "CLAHE", "TAMED", "DEFAULT", "STRATEGY_NAMES",
+    "U8", "U16", "TIFF", "JPEG", "OP_NONE", "OP_SUM", "OP_DIFF", "OP_RATIO", "OP_NDIFF", "OP_LOGRATIO",
+]

@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's function surface for the raster path, over the C ABI.
+
+Names, argument meaning and error behaviour follow src/core/processing/*.rs and the buffer variants
+of src/api/mod.rs (cited per function), so parity tests read like tests of the reference itself.
+Arrays are numpy (host) or torch CUDA tensors (device-resident; used by bench.py's kernel-only leg).
+Nothing here computes pixels: every function is one call into libsarpro_gpu.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _ffi as F
+from ._ffi import (ADAPTIVE, CLAHE, DEFAULT, EQUALIZED, JPEG, OP_DIFF, OP_LOGRATIO, OP_NDIFF, OP_NONE, OP_RATIO,  # noqa: F401
+                   OP_SUM, ROBUST, STANDARD, TAMED, TIFF, U8, U16)
+
+
+class SarproError(RuntimeError):
+    """Error::External(String) of the reference (src/error.rs:43-47) plus the status code."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _host(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+@dataclass
+class ProcessedImage:
+    """api/mod.rs:51-62 (metadata omitted: SAFE metadata never enters the raster path)."""
+    width: int
+    height: int
+    bit_depth: int
+    format: int
+    gray: np.ndarray | None = None
+    gray16: np.ndarray | None = None
+    rgb: np.ndarray | None = None
+    gray_band2: np.ndarray | None = None
+    gray16_band2: np.ndarray | None = None
+    scale_x: float = 1.0
+    scale_y: float = 1.0
+    pad_left: int = 0
+    pad_top: int = 0
+    stats: list = field(default_factory=list)
+
+
+class Context:
+    """Owns one sarpro_ctx (one GPU, one stream). Not thread-safe, like a reference call chain."""
+
+    def __init__(self, device: int = 0):
+        self._lib = F.lib()
+        h = C.c_void_p()
+        rc = self._lib.sarpro_ctx_create(C.byref(h), int(device))
+        if rc != F.OK:
+            raise SarproError(rc, (self._lib.sarpro_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sarpro_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != F.OK:
+            raise SarproError(rc, (self._lib.sarpro_last_error(self._h) or b"").decode())
+
+    def timing(self) -> F.Timing:
+        t = F.Timing()
+        self._check(self._lib.sarpro_last_timing(self._h, C.byref(t)))
+        return t
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self._lib.sarpro_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def _band(self, a):
+        """sarpro_band for a numpy array (host) or torch CUDA tensor (device). Keeps `a` alive via the return."""
+        if _is_torch(a):
+            import torch
+            if not a.is_cuda or not a.is_contiguous():
+                raise ValueError("device bands must be contiguous CUDA tensors")
+            if a.dtype == torch.float32:
+                dt = F.DT_F32
+            elif a.dtype in (torch.uint16, torch.int16):
+                dt = F.DT_U16
+            else:
+                raise ValueError(f"unsupported band dtype {a.dtype}")
+            rows, cols = a.shape
+            return F.Band(a.data_ptr(), dt, F.LOC_DEVICE, rows, cols), a
+        if a.dtype == np.uint16:
+            a = _host(a, np.uint16)
+            dt = F.DT_U16
+        else:
+            a = _host(a, np.float32)
+            dt = F.DT_F32
+        rows, cols = a.shape
+        return F.Band(a.ctypes.data, dt, F.LOC_HOST, rows, cols), a
+
+    @staticmethod
+    def resize_output_dims(cols, rows, target, pad):
+        oc, orr = C.c_size_t(), C.c_size_t()
+        F.lib().sarpro_resize_output_dims(cols, rows, int(target is not None), int(target or 0), int(bool(pad)),
+                                          C.byref(oc), C.byref(orr))
+        return oc.value, orr.value
+
+    def _image(self, cols, rows, channels, bit_depth, out=None):
+        dt = np.uint8 if bit_depth == U8 else np.uint16
+        shape = (rows, cols) if channels == 1 else (rows, cols, channels)
+        if out is None:
+            out = np.empty(shape, dt)
+            img = F.Image(out.ctypes.data, F.LOC_HOST, bit_depth, out.nbytes, 0, 0, 0, 0, F.ResizeMeta())
+        elif _is_torch(out):
+            img = F.Image(out.data_ptr(), F.LOC_DEVICE, bit_depth, out.numel() * out.element_size(), 0, 0, 0, 0, F.ResizeMeta())
+        else:
+            img = F.Image(out.ctypes.data, F.LOC_HOST, bit_depth, out.nbytes, 0, 0, 0, 0, F.ResizeMeta())
+        return img, out
+
+    # -- stage level (src/core/processing) ------------------------------------------------------
+    def process_scalar_data_pipeline(self, processed, bit_depth, strategy):
+        """pipeline.rs:42-66. Returns (scaled_u8 | None, scaled_u16 | None, stats).
+        The (db_data, valid_mask) members of the reference's tuple are not materialised
+        (see process_scalar_data_inplace)."""
+        if processed.dtype == np.uint16:
+            v = _host(processed, np.uint16)
+            fn = self._lib.sarpro_process_dn_pipeline
+        else:
+            v = _host(processed, np.float32)
+            fn = self._lib.sarpro_process_scalar_data_pipeline
+        rows, cols = v.shape
+        u8 = np.empty(v.shape, np.uint8) if bit_depth == U8 else None
+        u16 = np.empty(v.shape, np.uint16) if bit_depth == U16 else None
+        st = F.Stats()
+        self._check(fn(self._h, _ptr(v), rows, cols, bit_depth, strategy, _ptr(u8), _ptr(u16), C.byref(st)))
+        return u8, u16, st
+
+    def process_scalar_data_inplace(self, processed):
+        """pipeline.rs:8-40 -> (db f64, valid_mask u8)."""
+        v = _host(processed, np.float32)
+        rows, cols = v.shape
+        db = np.empty(v.shape, np.float64)
+        mask = np.empty(v.shape, np.uint8)
+        self._check(self._lib.sarpro_process_scalar_data_inplace(self._h, _ptr(v), rows, cols, _ptr(db), _ptr(mask)))
+        return db, mask
+
+    def autoscale_db_image_tamed_synrgb_u8(self, processed, is_copol):
+        """autoscale.rs:710-742 (takes the linear band the dB plane came from)."""
+        v = _host(processed, np.float32)
+        rows, cols = v.shape
+        out = np.empty(v.shape, np.uint8)
+        self._check(self._lib.sarpro_autoscale_tamed_synrgb_u8(self._h, _ptr(v), rows, cols, int(bool(is_copol)), _ptr(out)))
+        return out
+
+    def scale_u16_to_u8(self, data):
+        """autoscale.rs:348-364"""
+        d = _host(data, np.uint16)
+        out = np.empty(d.shape, np.uint8)
+        self._check(self._lib.sarpro_scale_u16_to_u8(self._h, _ptr(d), d.size, _ptr(out)))
+        return out
+
+    def _pol(self, op, a, b):
+        a = _host(a, np.float32)
+        b = _host(b, np.float32)
+        if a.shape != b.shape:
+            raise ValueError("shape mismatch")
+        rows, cols = a.shape
+        out = np.empty(a.shape, np.float32)
+        self._check(self._lib.sarpro_pol_op(self._h, op, _ptr(a), _ptr(b), rows, cols, _ptr(out)))
+        return out
+
+    def sum_arrays(self, a, b):              # ops.rs:4
+        return self._pol(OP_SUM, a, b)
+
+    def difference_arrays(self, a, b):       # ops.rs:7
+        return self._pol(OP_DIFF, a, b)
+
+    def ratio_arrays(self, a, b):            # ops.rs:10-20
+        return self._pol(OP_RATIO, a, b)
+
+    def normalized_diff_arrays(self, a, b):  # ops.rs:22-33
+        return self._pol(OP_NDIFF, a, b)
+
+    def log_ratio_arrays(self, a, b):        # ops.rs:35-44
+        return self._pol(OP_LOGRATIO, a, b)
+
+    @staticmethod
+    def calculate_resize_dimensions(original_cols, original_rows, target_size):
+        """resize.rs:6-30 (through the same C entry the pipelines use)."""
+        if target_size > max(original_cols, original_rows):
+            return original_cols, original_rows
+        return Context.resize_output_dims(original_cols, original_rows, target_size, False)
+
+    def resize_image_data_with_meta(self, data, target_size, bit_depth, pad):
+        """resize.rs:91-236. `data` is the u8 plane (U8) or the u16 plane (U16); None for U16 raises
+        the reference's "U16 data required for U16 bit depth"."""
+        if data is None:
+            if bit_depth == U16:
+                meta = F.ResizeMeta()
+                self._check(self._lib.sarpro_resize_image_data_with_meta(
+                    self._h, None, None, 0, 0, int(target_size is not None), int(target_size or 0), U16, int(bool(pad)),
+                    None, None, C.byref(meta)))
+            raise ValueError("data is None")
+        dt = np.uint8 if bit_depth == U8 else np.uint16
+        d = _host(data, dt)
+        rows, cols = d.shape
+        oc, orr = self.resize_output_dims(cols, rows, target_size, pad)
+        out = np.empty((orr, oc), dt)
+        meta = F.ResizeMeta()
+        self._check(self._lib.sarpro_resize_image_data_with_meta(
+            self._h, _ptr(d) if bit_depth == U8 else None, _ptr(d) if bit_depth == U16 else None, cols, rows,
+            int(target_size is not None), int(target_size or 0), bit_depth, int(bool(pad)),
+            _ptr(out) if bit_depth == U8 else None, _ptr(out) if bit_depth == U16 else None, C.byref(meta)))
+        return out, meta
+
+    def resize_image_data(self, data, target_size, bit_depth, pad):
+        """resize.rs:238-257"""
+        out, meta = self.resize_image_data_with_meta(data, target_size, bit_depth, pad)
+        return meta.cols, meta.rows, out
+
+    def add_padding_to_square(self, data, bit_depth):
+        """padding.rs:5-49"""
+        if data is None and bit_depth == U16:
+            self._check(self._lib.sarpro_add_padding_to_square(self._h, None, None, 0, 0, U16, None, None))
+        dt = np.uint8 if bit_depth == U8 else np.uint16
+        d = _host(data, dt)
+        rows, cols = d.shape
+        m = max(rows, cols)
+        out = np.empty((m, m), dt)
+        self._check(self._lib.sarpro_add_padding_to_square(
+            self._h, _ptr(d) if bit_depth == U8 else None, _ptr(d) if bit_depth == U16 else None, cols, rows, bit_depth,
+            _ptr(out) if bit_depth == U8 else None, _ptr(out) if bit_depth == U16 else None))
+        return out
+
+    def create_synthetic_rgb_by_mode_and_strategy(self, mode, strategy, band1_data, band2_data):
+        """synthetic_rgb.rs:182-197"""
+        b1 = _host(band1_data, np.uint8)
+        b2 = _host(band2_data, np.uint8)
+        if b1.shape != b2.shape:
+            raise ValueError("shape mismatch")
+        rgb = np.empty(b1.shape + (3,), np.uint8)
+        self._check(self._lib.sarpro_create_synthetic_rgb_by_mode_and_strategy(
+            self._h, mode, strategy, _ptr(b1), _ptr(b2), b1.size, _ptr(rgb)))
+        return rgb
+
+    # -- fused pipelines (save.rs / api/mod.rs call orders) ---------------------------------------
+    def process_single(self, band, fmt, bit_depth, strategy, target_size=None, pad=False, op=OP_NONE, band2=None,
+                       out=None) -> ProcessedImage:
+        """save.rs:49-65/119-134; api/mod.rs:84-130, 250-281, 284-369 (op: sentinel1.rs:1497-1579)."""
+        ba, keep_a = self._band(band)
+        bb, keep_b = (self._band(band2) if band2 is not None else (None, None))
+        if fmt == JPEG:
+            bit_depth = U8
+        rows, cols = keep_a.shape
+        oc, orr = self.resize_output_dims(cols, rows, target_size, pad)
+        img, out = self._image(oc, orr, 1, bit_depth, out)
+        st = F.Stats()
+        self._check(self._lib.sarpro_pipeline_single(
+            self._h, C.byref(ba), C.byref(bb) if bb is not None else None, op, fmt, bit_depth, strategy,
+            int(target_size is not None), int(target_size or 0), int(bool(pad)), C.byref(img), C.byref(st)))
+        del keep_b
+        return ProcessedImage(img.cols, img.rows, bit_depth, fmt,
+                              gray=out if bit_depth == U8 else None, gray16=out if bit_depth == U16 else None,
+                              scale_x=img.meta.scale_x, scale_y=img.meta.scale_y, pad_left=img.meta.pad_left,
+                              pad_top=img.meta.pad_top, stats=[st])
+
+    def process_multiband_tiff(self, band1, band2, bit_depth, strategy, target_size=None, pad=False) -> ProcessedImage:
+        """save.rs:199-316; api/mod.rs:133-200."""
+        b1, k1 = self._band(band1)
+        b2, k2 = self._band(band2)
+        rows, cols = k1.shape
+        oc, orr = self.resize_output_dims(cols, rows, target_size, pad)
+        i1, o1 = self._image(oc, orr, 1, bit_depth)
+        i2, o2 = self._image(oc, orr, 1, bit_depth)
+        st = (F.Stats * 2)()
+        self._check(self._lib.sarpro_pipeline_multiband_tiff(
+            self._h, C.byref(b1), C.byref(b2), bit_depth, strategy, int(target_size is not None), int(target_size or 0),
+            int(bool(pad)), C.byref(i1), C.byref(i2), st))
+        del k2
+        u8 = bit_depth == U8
+        return ProcessedImage(i1.cols, i1.rows, bit_depth, TIFF, gray=o1 if u8 else None, gray16=None if u8 else o1,
+                              gray_band2=o2 if u8 else None, gray16_band2=None if u8 else o2,
+                              scale_x=i1.meta.scale_x, scale_y=i1.meta.scale_y, pad_left=i1.meta.pad_left,
+                              pad_top=i1.meta.pad_top, stats=[st[0], st[1]])
+
+    def process_synrgb_jpeg(self, band1, band2, strategy, target_size=None, pad=False, mode=F.SYNRGB_DEFAULT,
+                            tamed_band_step=True, out=None) -> ProcessedImage:
+        """save.rs:317-368 (tamed_band_step=True) / api/mod.rs:203-247 (False)."""
+        b1, k1 = self._band(band1)
+        b2, k2 = self._band(band2)
+        rows, cols = k1.shape
+        oc, orr = self.resize_output_dims(cols, rows, target_size, pad)
+        img, out = self._image(oc, orr, 3, U8, out)
+        st = (F.Stats * 2)()
+        self._check(self._lib.sarpro_pipeline_synrgb(
+            self._h, C.byref(b1), C.byref(b2), strategy, mode, int(target_size is not None), int(target_size or 0),
+            int(bool(pad)), int(bool(tamed_band_step)), C.byref(img), st))
+        del k2
+        return ProcessedImage(img.cols, img.rows, U8, JPEG, rgb=out, scale_x=img.meta.scale_x, scale_y=img.meta.scale_y,
+                              pad_left=img.meta.pad_left, pad_top=img.meta.pad_top, stats=[st[0], st[1]])
+
+
+def plan_from_dn_histogram(hist65536, bit_depth, strategy):
+    """Host-only planner entry (no GPU needed): stats + DN->sample LUT from a DN histogram."""
+    h = np.ascontiguousarray(hist65536, dtype=np.uint64)
+    assert h.size == 65536
+    lut = np.zeros(65536, np.uint16)
+    st = F.Stats()
+    rc = F.lib().sarpro_plan_from_dn_histogram(h.ctypes.data, bit_depth, strategy, C.byref(st), lut.ctypes.data)
+    if rc != F.OK:
+        raise SarproError(rc, "sarpro_plan_from_dn_histogram failed")
+    return st, lut
+
+
+def shard_rows(rows, world, rank, clahe):
+    r0, r1 = C.c_size_t(), C.c_size_t()
+    rc = F.lib().sarpro_shard_rows(rows, world, rank, int(bool(clahe)), C.byref(r0), C.byref(r1))
+    if rc != F.OK:
+        raise SarproError(rc, "sarpro_shard_rows: invalid argument")
+    return r0.value, r1.value

@@ -1,0 +1,976 @@
+// api.cu — sarpro_ctx and the C ABI of include/sarpro_gpu.h.
+//
+// Orchestration of the device passes in the order of the reference's callers
+// (save.rs:49-65,119-134,199-316,317-368; api/mod.rs:84-369). Data layout in HBM per band:
+//   dn        [rows][cols] u16      the raster (uploaded, or the caller's device pointer)
+//   tile_hist [tiles][65536] u32    per-CLAHE-tile DN counts (tiles = 64 for CLAHE, else 1)
+//   total     [65536] u32           DN histogram -> host planner (256 KB D2H)
+//   lut       [65536] u16           DN -> final sample or CLAHE bin (128 KB H2D)
+//   tile256 / cdf / cdf32           CLAHE per-tile 256-bin histograms and CDFs
+//   temp      [rows][out_cols]      horizontally resized samples
+//   small     [out_rows][out_cols]  resized (+ padded) band
+// There is no CPU fallback: every entry point needs a live context on a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ctx.h"
+
+using namespace sarpro;
+
+namespace {
+thread_local std::string g_create_error;
+} // namespace
+
+namespace sarpro {
+
+int fail(sarpro_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = (bytes + 255) & ~size_t(255);
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// smallest f32 whose dB exceeds -50 (pipeline.rs:19-22), found with the host libm
+float compute_valid_thresh() {
+    auto valid = [](float v) { return 10.0 * std::log10(std::fmax((double)v, 1e-10)) > -50.0; };
+    uint32_t lo = 0, hi;
+    float one = 1.0f;
+    std::memcpy(&hi, &one, 4); // valid(1.0) is true, valid(0) false
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        float f;
+        std::memcpy(&f, &mid, 4);
+        if (valid(f)) hi = mid; else lo = mid;
+    }
+    float f;
+    std::memcpy(&f, &hi, 4);
+    return f;
+}
+
+int upload_rgb_luts(sarpro_ctx* ctx) {
+    std::vector<uint8_t> all((size_t)kSynRgbSets * kSynRgbSetBytes, 0);
+    auto build = [&](uint32_t set) {
+        SynRgbLut l;
+        if (set == kSynRgbDefaultSet) build_synrgb_default_lut(&l);
+        else build_synrgb_suppressed_lut((int)set, &l);
+        uint8_t* dst = all.data() + (size_t)set * kSynRgbSetBytes;
+        std::memcpy(dst, l.r, 256);
+        std::memcpy(dst + 256, l.g, 256);
+        std::memcpy(dst + 512, l.b.data(), 65536);
+    };
+    std::vector<std::thread> th;
+    const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&, t] { for (uint32_t s = t; s < kSynRgbSets; s += nt) build(s); });
+    for (auto& t : th) t.join();
+    RC(reserve(ctx, ctx->rgb_luts, all.size()));
+    CU(cudaMemcpyAsync(ctx->rgb_luts.p, all.data(), all.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- histogram work units ---------------------------------------------------------------------
+// local rows [0, rows) are scene rows [row_off, row_off+rows); tiles follow the scene geometry.
+int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uint64_t scene_rows, uint64_t row_off) {
+    std::vector<HistUnit> units;
+    const uint64_t target_px = 192 * 1024;
+    if (!clahe) {
+        uint64_t chunk = std::max<uint64_t>(1, target_px / std::max<uint64_t>(cols, 1));
+        for (uint64_t r = 0; r < rows; r += chunk)
+            units.push_back(HistUnit{(uint32_t)r, (uint32_t)std::min(rows, r + chunk), 0u, (uint32_t)cols, 0u, 0u});
+        ctx->n_tiles = 1;
+    } else {
+        const ClaheGeom g = clahe_geometry(scene_rows, cols);
+        for (uint64_t ty = 0; ty < kClaheTiles; ++ty) {
+            const uint64_t gr0 = ty * g.tile_h, gr1 = std::min((ty + 1) * g.tile_h, scene_rows);
+            // intersect with the local band
+            const uint64_t a = std::max(gr0, row_off), b = std::min(gr1, row_off + rows);
+            if (a >= b) continue;
+            for (uint64_t tx = 0; tx < kClaheTiles; ++tx) {
+                const uint64_t c0 = tx * g.tile_w, c1 = std::min((tx + 1) * g.tile_w, cols);
+                if (c0 >= c1) continue;
+                const uint64_t chunk = std::max<uint64_t>(1, target_px / (c1 - c0));
+                for (uint64_t r = a; r < b; r += chunk)
+                    units.push_back(HistUnit{(uint32_t)(r - row_off), (uint32_t)(std::min(b, r + chunk) - row_off),
+                                             (uint32_t)c0, (uint32_t)c1, (uint32_t)(ty * kClaheTiles + tx), 0u});
+            }
+        }
+        ctx->n_tiles = kClaheTiles * kClaheTiles;
+    }
+    ctx->n_units = (uint32_t)units.size();
+    if (!units.empty()) {
+        RC(reserve(ctx, ctx->units, units.size() * sizeof(HistUnit)));
+        CU(cudaMemcpyAsync(ctx->units.p, units.data(), units.size() * sizeof(HistUnit), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream)); // `units` is a pageable temporary
+    }
+    if (clahe) {
+        const ClaheGeom g = clahe_geometry(scene_rows, cols);
+        uint64_t px[kClaheTiles * kClaheTiles];
+        for (uint64_t ty = 0; ty < kClaheTiles; ++ty)
+            for (uint64_t tx = 0; tx < kClaheTiles; ++tx) {
+                const uint64_t r0 = ty * g.tile_h, r1 = std::min((ty + 1) * g.tile_h, scene_rows);
+                const uint64_t c0 = tx * g.tile_w, c1 = std::min((tx + 1) * g.tile_w, cols);
+                // tiles beyond the raster hold no pixel and are never sampled (autoscale.rs:308-318)
+                px[ty * kClaheTiles + tx] = (r1 > r0 ? r1 - r0 : 0) * (c1 > c0 ? c1 - c0 : 0);
+            }
+        RC(reserve(ctx, ctx->tile_px, sizeof(px)));
+        CU(cudaMemcpyAsync(ctx->tile_px.p, px, sizeof(px), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        // bilinear geometry per column / row
+        RC(reserve(ctx, ctx->col_dx, cols * 8));
+        RC(reserve(ctx, ctx->col_omdx, cols * 8));
+        RC(reserve(ctx, ctx->col_t, cols * 2));
+        RC(reserve(ctx, ctx->row_dy, rows * 8));
+        RC(reserve(ctx, ctx->row_omdy, rows * 8));
+        RC(reserve(ctx, ctx->row_t, rows * 2));
+        KL(launch_clahe_axis((uint32_t)cols, 0, (uint32_t)g.tile_w, kClaheTiles, (double*)ctx->col_dx.p,
+                             (double*)ctx->col_omdx.p, (uint16_t*)ctx->col_t.p, ctx->stream));
+        KL(launch_clahe_axis((uint32_t)rows, (uint32_t)row_off, (uint32_t)g.tile_h, kClaheTiles, (double*)ctx->row_dy.p,
+                             (double*)ctx->row_omdy.p, (uint16_t*)ctx->row_t.p, ctx->stream));
+    }
+    return 0;
+}
+
+ClaheDev clahe_dev(sarpro_ctx* ctx, int b) {
+    ClaheDev cl;
+    cl.cdf = (const double*)ctx->band[b].cdf.p;
+    cl.cdf32 = (const float*)ctx->band[b].cdf32.p;
+    cl.col_dx = (const double*)ctx->col_dx.p;
+    cl.col_omdx = (const double*)ctx->col_omdx.p;
+    cl.col_t = (const uint16_t*)ctx->col_t.p;
+    cl.row_dy = (const double*)ctx->row_dy.p;
+    cl.row_omdy = (const double*)ctx->row_omdy.p;
+    cl.row_t = (const uint16_t*)ctx->row_t.p;
+    cl.tiles_x = kClaheTiles;
+    return cl;
+}
+
+// ---- Lanczos axis plans ---------------------------------------------------------------------------
+int upload_vec(sarpro_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    RC(reserve(ctx, b, std::max<size_t>(bytes, 16)));
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res) {
+    const AxisKey key{in, out, wide ? 1 : 0, horiz ? 1 : 0, horiz ? src_kind : 0};
+    auto it = ctx->axes.find(key);
+    if (it != ctx->axes.end()) { *res = it->second; return 0; }
+    if (ctx->axes.size() > 64) { // bounded cache
+        for (auto& kv : ctx->axes) {
+            release(kv.second->start); release(kv.second->size); release(kv.second->coef);
+            release(kv.second->packed); release(kv.second->strips);
+            delete kv.second;
+        }
+        ctx->axes.clear();
+    }
+    AxisPlan* ap = new AxisPlan();
+    build_lanczos3_axis(in, out, wide, &ap->h);
+    const ResampleAxis& h = ap->h;
+    std::vector<uint32_t> packed;
+    if (horiz && !wide) {
+        ap->pairs = ((h.window + 3 + 3) / 4) * 2; // taps = 2*pairs, multiple of 4, >= window + 3
+        packed.assign((size_t)out * ap->pairs, 0);
+        for (uint32_t ox = 0; ox < out; ++ox) {
+            const uint32_t shift = h.start[ox] & 3u;
+            for (uint32_t k = 0; k < h.size[ox]; ++k) {
+                const uint32_t j = k + shift;
+                const uint32_t c = (uint32_t)(uint16_t)(int16_t)h.coef[(size_t)ox * h.window + k];
+                packed[(size_t)ox * ap->pairs + (j >> 1)] |= (j & 1) ? (c << 16) : c;
+            }
+        }
+    }
+    int rc = upload_vec(ctx, ap->start, h.start.data(), h.start.size() * 4);
+    if (!rc) rc = upload_vec(ctx, ap->size, h.size.data(), h.size.size() * 4);
+    if (!rc) rc = upload_vec(ctx, ap->coef, h.coef.data(), h.coef.size() * 4);
+    if (!rc) rc = upload_vec(ctx, ap->packed, packed.data(), packed.size() * 4);
+    if (!rc && horiz) {
+        std::vector<HStrip> strips;
+        cudaError_t e = hresize_build_strips(h.start.data(), h.size.data(), out, in, h.window, ap->pairs, wide ? 1 : 0,
+                                             src_kind, &ap->oxb, &strips, &ap->rbw, &ap->smem);
+        if (e != cudaSuccess) rc = fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "resize %u -> %u needs more shared memory than an SM has", in, out);
+        else {
+            ap->n_strips = (uint32_t)strips.size();
+            rc = upload_vec(ctx, ap->strips, strips.data(), strips.size() * sizeof(HStrip));
+            ap->has_strips = true;
+        }
+    }
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream); // host vectors are temporaries
+        if (e != cudaSuccess) rc = fail(ctx, SARPRO_ERR_CUDA, "CUDA error %s", cudaGetErrorName(e));
+    }
+    if (rc) { delete ap; return rc; }
+    ctx->axes[key] = ap;
+    *res = ap;
+    return 0;
+}
+
+// ---- one band through the device passes -----------------------------------------------------------
+struct BandJob {
+    const uint16_t* dn = nullptr; // device
+    uint64_t rows = 0, cols = 0;
+    int strategy = 0, bit_depth = 0;
+    PlanKind kind = PlanKind::Autoscale;
+};
+
+OutGeom out_geometry(size_t cols, size_t rows, bool has_target, size_t target, bool pad) {
+    OutGeom g;
+    resize_output_dims(cols, rows, has_target, target, pad, &g.rc, &g.rr, &g.oc, &g.orr);
+    g.resize = has_target && std::max(cols, rows) != target; // resize.rs:115-116
+    g.pad = pad;
+    g.pad_left = pad ? (g.oc - g.rc) / 2 : 0;
+    g.pad_top = pad ? (g.orr - g.rr) / 2 : 0;
+    g.meta.cols = g.oc;
+    g.meta.rows = g.orr;
+    g.meta.scale_x = g.resize ? (double)g.rc / (double)cols : 1.0; // resize.rs:169-170
+    g.meta.scale_y = g.resize ? (double)g.rr / (double)rows : 1.0;
+    g.meta.pad_left = g.pad_left;
+    g.meta.pad_top = g.pad_top;
+    return g;
+}
+
+bool uses_clahe(const BandJob& j) { return j.kind == PlanKind::Autoscale && j.strategy == SARPRO_STRATEGY_CLAHE; }
+
+// Pass A for `nb` bands of identical geometry, then one planner round trip for all of them.
+int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
+    const uint64_t rows = jobs[0].rows, cols = jobs[0].cols;
+    bool any_clahe = false;
+    for (int b = 0; b < nb; ++b) any_clahe |= uses_clahe(jobs[b]);
+    if (ctx->units_rows != rows || ctx->units_cols != cols || ctx->units_clahe != (int)any_clahe) {
+        RC(prepare_units(ctx, rows, cols, any_clahe, rows, 0));
+        ctx->units_rows = rows;
+        ctx->units_cols = cols;
+        ctx->units_clahe = any_clahe;
+    }
+    for (int b = 0; b < nb; ++b) {
+        BandWs& w = ctx->band[b];
+        RC(reserve(ctx, w.tile_hist, (size_t)ctx->n_tiles * kDnBins * 4));
+        RC(reserve(ctx, w.total, kDnBins * 4));
+        RC(reserve(ctx, w.lut, kDnBins * 2));
+        RC(reserve(ctx, w.scalars, 64));
+        CU(cudaMemsetAsync(w.tile_hist.p, 0, (size_t)ctx->n_tiles * kDnBins * 4, ctx->stream));
+        const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0u};
+        std::memcpy(ctx->h_scalars + 8 * b, init, sizeof(init));
+        CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        KL(launch_dn_hist(jobs[b].dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
+                          ctx->sm_count, ctx->hist_variant, ctx->stream));
+        KL(launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
+                             (uint32_t*)w.scalars.p + 2, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->timing.host_syncs++;
+    for (int b = 0; b < nb; ++b) {
+        BandWs& w = ctx->band[b];
+        std::vector<uint64_t> h64(kDnBins);
+        const uint32_t* h32 = ctx->h_hist + (size_t)b * kDnBins;
+        for (int i = 0; i < kDnBins; ++i) h64[i] = h32[i];
+        plan_from_dn_histogram(h64.data(), jobs[b].bit_depth, jobs[b].strategy, jobs[b].kind, &w.plan);
+        std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+        CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return 0;
+}
+
+// CLAHE tile CDFs for band b (after the LUT is on the device)
+int run_clahe_stats(sarpro_ctx* ctx, int b) {
+    BandWs& w = ctx->band[b];
+    RC(reserve(ctx, w.tile256, (size_t)ctx->n_tiles * 256 * 4));
+    RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
+    RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
+    CU(cudaMemsetAsync(w.tile256.p, 0, (size_t)ctx->n_tiles * 256 * 4, ctx->stream));
+    KL(launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles, w.plan.max_present_dn,
+                            (uint32_t*)w.tile256.p, ctx->stream));
+    KL(launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles, (double*)w.cdf.p,
+                        (float*)w.cdf32.p, ctx->stream));
+    return 0;
+}
+
+// Reads back the CLAHE sample min/max of band b and returns whether scale_u16_to_u8 is the identity.
+int clahe_minmax(sarpro_ctx* ctx, int b, uint32_t* mn, uint32_t* mx) {
+    BandWs& w = ctx->band[b];
+    CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b, w.scalars.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->timing.host_syncs++;
+    *mn = ctx->h_scalars[8 * b];
+    *mx = ctx->h_scalars[8 * b + 1];
+    if (*mn == 0xffffffffu) { *mn = 0; *mx = 0; }
+    return 0;
+}
+int upload_remap(sarpro_ctx* ctx, int b, uint32_t mn, uint32_t mx) {
+    BandWs& w = ctx->band[b];
+    RC(reserve(ctx, w.remap, 256));
+    make_u16_to_u8_remap((uint16_t)mn, (uint16_t)mx, 256, ctx->h_remap + 256 * b);
+    CU(cudaMemcpyAsync(w.remap.p, ctx->h_remap + 256 * b, 256, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+int reset_minmax(sarpro_ctx* ctx, int b) {
+    BandWs& w = ctx->band[b];
+    const uint32_t init[2] = {0xffffffffu, 0u};
+    std::memcpy(ctx->h_scalars + 8 * b + 4, init, sizeof(init));
+    CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b + 4, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// Pass B, full resolution: dst is a device buffer of rows*cols samples of the job's bit depth.
+int run_pass_b_full(sarpro_ctx* ctx, int b, const BandJob& j, void* dst) {
+    BandWs& w = ctx->band[b];
+    const uint64_t n = j.rows * j.cols;
+    const bool out8 = j.kind != PlanKind::Autoscale || j.bit_depth == SARPRO_U8;
+    if (!w.plan.any_valid) { // all-zero output (autoscale.rs:376-378, 466-468, 716-718)
+        CU(cudaMemsetAsync(dst, 0, n * (out8 ? 1 : 2), ctx->stream));
+        return 0;
+    }
+    if (!uses_clahe(j)) {
+        KL(launch_apply_lut(j.dn, n, (const uint16_t*)w.lut.p, out8 ? (uint8_t*)dst : nullptr,
+                            out8 ? nullptr : (uint16_t*)dst, ctx->sm_count, ctx->stream));
+        return 0;
+    }
+    RC(run_clahe_stats(ctx, b));
+    KL(launch_apply_clahe(j.dn, (uint32_t)j.rows, (uint32_t)j.cols, (const uint16_t*)w.lut.p, clahe_dev(ctx, b),
+                          out8 ? 255 : 65535, out8 ? (uint8_t*)dst : nullptr, out8 ? nullptr : (uint16_t*)dst,
+                          (uint32_t*)w.scalars.p, ctx->sm_count, ctx->stream));
+    if (out8) { // scale_u16_to_u8 over the blended samples (autoscale.rs:691-693)
+        uint32_t mn, mx;
+        RC(clahe_minmax(ctx, b, &mn, &mx));
+        if (!(mn == 0 && mx == 255)) {
+            RC(upload_remap(ctx, b, mn, mx));
+            KL(launch_remap_u8((uint8_t*)dst, n, (const uint8_t*)w.remap.p, ctx->sm_count, ctx->stream));
+        }
+    }
+    return 0;
+}
+
+// Pass B fused with the Lanczos resize: writes the resized band into `canvas` (pitch g.oc) at the pad offset.
+int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& g, void* canvas) {
+    BandWs& w = ctx->band[b];
+    const bool out8 = j.kind != PlanKind::Autoscale || j.bit_depth == SARPRO_U8;
+    const int pix16 = out8 ? 0 : 1;
+    const size_t esz = out8 ? 1 : 2;
+    if (g.pad || !w.plan.any_valid) CU(cudaMemsetAsync(canvas, 0, g.oc * g.orr * esz, ctx->stream));
+    if (g.rc == 0 || g.rr == 0) return 0;
+    if (!w.plan.any_valid) return 0; // resize of an all-zero raster is all zero
+    const bool clahe = uses_clahe(j);
+    const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
+    AxisPlan *ah, *av;
+    RC(get_axis(ctx, (uint32_t)j.cols, (uint32_t)g.rc, pix16, true, src_kind, &ah));
+    RC(get_axis(ctx, (uint32_t)j.rows, (uint32_t)g.rr, pix16, false, 0, &av));
+    RC(reserve(ctx, w.temp, (size_t)j.rows * g.rc * esz));
+    if (clahe) RC(run_clahe_stats(ctx, b));
+    HResizeArgs a{};
+    a.src = j.dn;
+    a.src_rows = (uint32_t)j.rows;
+    a.src_cols = (uint32_t)j.cols;
+    a.lut = (const uint16_t*)w.lut.p;
+    a.remap = nullptr;
+    if (clahe) a.clahe = clahe_dev(ctx, b);
+    a.minmax = clahe ? (uint32_t*)w.scalars.p : nullptr;
+    a.row0 = 0;
+    a.n_rows = (uint32_t)j.rows;
+    a.temp = w.temp.p;
+    a.ax = ah->dev();
+    auto run = [&]() -> int {
+        KL(launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw,
+                                  ah->smem, ctx->sm_count, ctx->stream));
+        unsigned char* dst = (unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz;
+        KL(launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream));
+        return 0;
+    };
+    RC(run());
+    if (clahe && out8) {
+        // scale_u16_to_u8 is the identity when the blended samples span exactly [0,255]; the first run
+        // assumed so. Verify, and redo the pass with the remap table in the (rare) other case.
+        uint32_t mn, mx;
+        RC(clahe_minmax(ctx, b, &mn, &mx));
+        if (!(mn == 0 && mx == 255)) {
+            RC(upload_remap(ctx, b, mn, mx));
+            a.remap = (const uint8_t*)w.remap.p;
+            a.minmax = nullptr;
+            RC(run());
+        }
+    }
+    return 0;
+}
+
+// ---- inputs ----------------------------------------------------------------------------------------
+// Brings band `in` (optionally op(in, in2)) to a u16 DN raster on the device. Returns SARPRO_ERR_INTERNAL + flag
+// when the samples are not u16-valued (general f32 path).
+int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band* in2, int op, const uint16_t** dn_out,
+               bool* integral) {
+    BandWs& w = ctx->band[b];
+    const uint64_t n = in->rows * in->cols;
+    *integral = true;
+    if (in->dtype == SARPRO_DT_U16 && op < 0) {
+        if (in->location == SARPRO_LOC_DEVICE) { *dn_out = (const uint16_t*)in->data; return 0; }
+        RC(reserve(ctx, w.dn, n * 2));
+        CU(cudaMemcpyAsync(w.dn.p, in->data, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += n * 2;
+        *dn_out = (const uint16_t*)w.dn.p;
+        return 0;
+    }
+    if (in->dtype != SARPRO_DT_F32 || (op >= 0 && in2->dtype != SARPRO_DT_F32))
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "polarization ops take f32 bands (ops.rs:4-44)");
+    const float* fa = (const float*)in->data;
+    const float* fb = op >= 0 ? (const float*)in2->data : nullptr;
+    if (in->location == SARPRO_LOC_HOST) {
+        RC(reserve(ctx, w.f32a, n * 4));
+        CU(cudaMemcpyAsync(w.f32a.p, in->data, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += n * 4;
+        fa = (const float*)w.f32a.p;
+    }
+    if (op >= 0 && in2->location == SARPRO_LOC_HOST) {
+        RC(reserve(ctx, w.f32b, n * 4));
+        CU(cudaMemcpyAsync(w.f32b.p, in2->data, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += n * 4;
+        fb = (const float*)w.f32b.p;
+    }
+    RC(reserve(ctx, w.dn, n * 2));
+    RC(reserve(ctx, w.scalars, 64));
+    CU(cudaMemsetAsync((uint32_t*)w.scalars.p + 3, 0, 4, ctx->stream));
+    KL(launch_f32_to_dn(fa, fb, op, n, ctx->valid_thresh, (uint16_t*)w.dn.p, (uint32_t*)w.scalars.p + 3, ctx->sm_count,
+                        ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b + 3, (uint32_t*)w.scalars.p + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->timing.host_syncs++;
+    *integral = ctx->h_scalars[8 * b + 3] == 0;
+    *dn_out = (const uint16_t*)w.dn.p;
+    return 0;
+}
+
+int check_band(sarpro_ctx* ctx, const sarpro_band* b) {
+    if (!b) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "band descriptor is NULL");
+    if (b->rows * b->cols > 0 && !b->data) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "band data is NULL");
+    if (b->rows >= (1ull << 31) || b->cols >= (1ull << 31) || b->rows * b->cols >= (1ull << 32))
+        return fail(ctx, SARPRO_ERR_TOO_LARGE, "raster %llux%llu exceeds 2^32 samples", (unsigned long long)b->rows,
+                    (unsigned long long)b->cols);
+    return 0;
+}
+
+int begin_call(sarpro_ctx* ctx) {
+    if (!ctx) return SARPRO_ERR_INVALID_ARGUMENT;
+    ctx->err.clear();
+    CU(cudaSetDevice(ctx->device));
+    std::memset(&ctx->timing, 0, sizeof(ctx->timing));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    return 0;
+}
+int end_call(sarpro_ctx* ctx) {
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->timing.total_ms = ms;
+    return 0;
+}
+
+int deliver(sarpro_ctx* ctx, const void* dev_src, size_t bytes, sarpro_image* out) {
+    if (!out->data && bytes) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "output buffer is NULL");
+    if (out->capacity_bytes < bytes)
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "output buffer holds %llu bytes, %llu needed",
+                    (unsigned long long)out->capacity_bytes, (unsigned long long)bytes);
+    if (!bytes) return 0;
+    if (out->location == SARPRO_LOC_DEVICE) {
+        if (out->data != dev_src) CU(cudaMemcpyAsync(out->data, dev_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        CU(cudaMemcpyAsync(out->data, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->timing.d2h_bytes += bytes;
+    }
+    return 0;
+}
+
+void fill_image(sarpro_image* out, const OutGeom& g, int channels, int bit_depth) {
+    out->cols = g.oc;
+    out->rows = g.orr;
+    out->channels = channels;
+    out->bit_depth = bit_depth;
+    out->meta = g.meta;
+}
+
+} // namespace sarpro
+
+namespace sarpro {
+int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const float* b_dev, int op, uint64_t rows,
+                       uint64_t cols, int bit_depth, int strategy, PlanKind kind, bool has_target, size_t target,
+                       bool pad, void* canvas_dev, sarpro_stats* stats);
+}
+
+namespace {
+
+// Produces one processed band (autoscale [+resize+pad]) into a device canvas owned by the ctx.
+// Returns the canvas pointer through *canvas. `slot` selects the workspace.
+int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_band* const* ins2, const int* ops, int nb,
+                  const int* strategies, const int* bit_depths, const PlanKind* kinds, bool has_target, size_t target,
+                  bool pad, void** canvases, OutGeom* geom, sarpro_stats* stats) {
+    const uint64_t rows = ins[0]->rows, cols = ins[0]->cols;
+    *geom = out_geometry(cols, rows, has_target, target, pad);
+    BandJob jobs[2];
+    bool integral[2] = {true, true};
+    for (int b = 0; b < nb; ++b) {
+        RC(check_band(ctx, ins[b]));
+        if (ops[b] >= 0) RC(check_band(ctx, ins2[b]));
+        if (ins[b]->rows != rows || ins[b]->cols != cols || (ops[b] >= 0 && (ins2[b]->rows != rows || ins2[b]->cols != cols)))
+            return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "bands differ in shape");
+        jobs[b].rows = rows;
+        jobs[b].cols = cols;
+        jobs[b].strategy = strategies[b];
+        jobs[b].bit_depth = bit_depths[b];
+        jobs[b].kind = kinds[b];
+    }
+    const size_t n_out = geom->oc * geom->orr;
+    if (rows * cols == 0) {
+        for (int b = 0; b < nb; ++b) {
+            const bool out8 = kinds[b] != PlanKind::Autoscale || bit_depths[b] == SARPRO_U8;
+            RC(reserve(ctx, ctx->band[b].small, std::max<size_t>(n_out * (out8 ? 1 : 2), 16)));
+            canvases[b] = ctx->band[b].small.p;
+            if (stats) std::memset(&stats[b], 0, sizeof(sarpro_stats));
+        }
+        return 0;
+    }
+    for (int b = 0; b < nb; ++b) RC(stage_band(ctx, b, ins[b], ins2[b], ops[b], &jobs[b].dn, &integral[b]));
+    // u16-valued rasters share one pass A + planner round trip
+    BandJob dnjobs[2];
+    int dnidx[2], ndn = 0;
+    for (int b = 0; b < nb; ++b)
+        if (integral[b]) { dnjobs[ndn] = jobs[b]; dnidx[ndn] = b; ndn++; }
+    if (ndn == nb && ndn > 0) {
+        RC(run_pass_a_and_plan(ctx, jobs, nb));
+    } else {
+        for (int k = 0; k < ndn; ++k) {
+            // mixed case: plan band by band in its own slot
+            if (dnidx[k] != 0) std::swap(ctx->band[0], ctx->band[dnidx[k]]);
+            int rc = run_pass_a_and_plan(ctx, &dnjobs[k], 1);
+            if (dnidx[k] != 0) std::swap(ctx->band[0], ctx->band[dnidx[k]]);
+            RC(rc);
+        }
+    }
+    for (int b = 0; b < nb; ++b) {
+        BandWs& w = ctx->band[b];
+        const bool out8 = kinds[b] != PlanKind::Autoscale || bit_depths[b] == SARPRO_U8;
+        const size_t esz = out8 ? 1 : 2;
+        RC(reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)));
+        canvases[b] = w.small.p;
+        if (!integral[b]) {
+            const float* fa = ins[b]->location == SARPRO_LOC_HOST ? (const float*)w.f32a.p : (const float*)ins[b]->data;
+            const float* fb = ops[b] >= 0 ? (ins2[b]->location == SARPRO_LOC_HOST ? (const float*)w.f32b.p : (const float*)ins2[b]->data) : nullptr;
+            RC(f32_general_single(ctx, b, fa, fb, ops[b], rows, cols, bit_depths[b], strategies[b], kinds[b], has_target,
+                                  target, pad, w.small.p, stats ? &stats[b] : nullptr));
+            continue;
+        }
+        if (stats) stats[b] = w.plan.stats;
+        if (!geom->resize && !geom->pad) {
+            RC(run_pass_b_full(ctx, b, jobs[b], w.small.p));
+        } else if (!geom->resize) { // pad only: full-res apply, then copy into the zeroed canvas
+            RC(reserve(ctx, w.full, rows * cols * esz));
+            RC(run_pass_b_full(ctx, b, jobs[b], w.full.p));
+            CU(cudaMemsetAsync(w.small.p, 0, n_out * esz, ctx->stream));
+            CU(cudaMemcpy2DAsync((unsigned char*)w.small.p + (geom->pad_top * geom->oc + geom->pad_left) * esz,
+                                 geom->oc * esz, w.full.p, cols * esz, cols * esz, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            RC(run_pass_b_resized(ctx, b, jobs[b], *geom, w.small.p));
+        }
+    }
+    return 0;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int sarpro_abi_version(void) { return SARPRO_GPU_ABI_VERSION; }
+
+const char* sarpro_last_error(const sarpro_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
+    if (!out) return SARPRO_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, SARPRO_ERR_NO_DEVICE, "no CUDA device available (%s); libsarpro_gpu has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_id < 0 || device_id >= n) return fail(nullptr, SARPRO_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device_id, n);
+    sarpro_ctx* ctx = new sarpro_ctx();
+    ctx->device = device_id;
+    auto bail = [&](const char* what, cudaError_t err) {
+        fail(nullptr, SARPRO_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(err));
+        delete ctx;
+        return SARPRO_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        fail(nullptr, SARPRO_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device_id, prop.major, prop.minor);
+        delete ctx;
+        return SARPRO_ERR_NO_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_hist, 2 * kDnBins * 4)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_lut, 2 * kDnBins * 2)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_scalars, 2 * 8 * 4)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_remap, 2 * 256)) != cudaSuccess) return bail("cudaMallocHost", e);
+    ctx->valid_thresh = compute_valid_thresh();
+    dn_db_table();
+    if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
+    int rc = upload_rgb_luts(ctx);
+    if (rc) {
+        g_create_error = ctx->err;
+        sarpro_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return SARPRO_OK;
+}
+
+void sarpro_ctx_destroy(sarpro_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& w : ctx->band)
+        for (DevBuf* b : {&w.dn, &w.f32a, &w.f32b, &w.tile_hist, &w.total, &w.lut, &w.tile256, &w.cdf, &w.cdf32, &w.remap,
+                          &w.temp, &w.small, &w.full, &w.scalars})
+            release(*b);
+    for (DevBuf* b : {&ctx->units, &ctx->tile_px, &ctx->col_dx, &ctx->col_omdx, &ctx->col_t, &ctx->row_dy, &ctx->row_omdy,
+                      &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts})
+        release(*b);
+    for (auto& kv : ctx->axes) {
+        release(kv.second->start); release(kv.second->size); release(kv.second->coef);
+        release(kv.second->packed); release(kv.second->strips);
+        delete kv.second;
+    }
+    if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
+    if (ctx->h_lut) cudaFreeHost(ctx->h_lut);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->h_remap) cudaFreeHost(ctx->h_remap);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int sarpro_ctx_set_stream(sarpro_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return SARPRO_ERR_INVALID_ARGUMENT;
+    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return SARPRO_OK;
+}
+int sarpro_ctx_synchronize(sarpro_ctx* ctx) {
+    if (!ctx) return SARPRO_ERR_INVALID_ARGUMENT;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SARPRO_OK;
+}
+int sarpro_last_timing(const sarpro_ctx* ctx, sarpro_timing* out) {
+    if (!ctx || !out) return SARPRO_ERR_INVALID_ARGUMENT;
+    *out = ctx->timing;
+    return SARPRO_OK;
+}
+int sarpro_host_alloc(void** out, size_t bytes) {
+    if (!out) return SARPRO_ERR_INVALID_ARGUMENT;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? SARPRO_OK : SARPRO_ERR_OUT_OF_MEMORY;
+}
+void sarpro_host_free(void* p) { if (p) cudaFreeHost(p); }
+int sarpro_host_register(void* p, size_t bytes) {
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? SARPRO_OK : SARPRO_ERR_CUDA;
+}
+void sarpro_host_unregister(void* p) { if (p) cudaHostUnregister(p); }
+
+int sarpro_resize_output_dims(size_t cols, size_t rows, int has_target, size_t target, int pad, size_t* out_cols,
+                              size_t* out_rows) {
+    if (!out_cols || !out_rows) return SARPRO_ERR_INVALID_ARGUMENT;
+    size_t rc, rr;
+    resize_output_dims(cols, rows, has_target != 0, target, pad != 0, &rc, &rr, out_cols, out_rows);
+    return SARPRO_OK;
+}
+
+int sarpro_plan_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int strategy, sarpro_stats* stats,
+                                  uint16_t* lut16) {
+    if (!hist65536) return SARPRO_ERR_INVALID_ARGUMENT;
+    BandPlan p;
+    plan_from_dn_histogram(hist65536, bit_depth, strategy, PlanKind::Autoscale, &p);
+    if (stats) *stats = p.stats;
+    if (lut16) std::memcpy(lut16, p.lut.data(), kDnBins * 2);
+    return SARPRO_OK;
+}
+
+// ---- fused pipelines ---------------------------------------------------------------------------------
+int sarpro_pipeline_single(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, int op, int format, int bit_depth,
+                           int strategy, int has_target, size_t target, int pad, sarpro_image* out, sarpro_stats* stats) {
+    RC(begin_call(ctx));
+    if (!a || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (format == SARPRO_FORMAT_JPEG) bit_depth = SARPRO_U8; // save.rs:121
+    const sarpro_band* ins[1] = {a};
+    const sarpro_band* ins2[1] = {b};
+    const int ops[1] = {op};
+    const int strategies[1] = {strategy}, depths[1] = {bit_depth};
+    const PlanKind kinds[1] = {PlanKind::Autoscale};
+    void* canvas[1];
+    OutGeom g;
+    RC(produce_bands(ctx, ins, ins2, ops, 1, strategies, depths, kinds, has_target != 0, target, pad != 0, canvas, &g, stats));
+    fill_image(out, g, 1, bit_depth);
+    RC(deliver(ctx, canvas[0], g.oc * g.orr * (bit_depth == SARPRO_U8 ? 1 : 2), out));
+    return end_call(ctx);
+}
+
+int sarpro_pipeline_multiband_tiff(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_band* b2, int bit_depth,
+                                   int strategy, int has_target, size_t target, int pad, sarpro_image* out1,
+                                   sarpro_image* out2, sarpro_stats* stats2) {
+    RC(begin_call(ctx));
+    if (!b1 || !b2 || !out1 || !out2) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    const sarpro_band* ins[2] = {b1, b2};
+    const sarpro_band* ins2[2] = {nullptr, nullptr};
+    const int ops[2] = {-1, -1};
+    const int strategies[2] = {strategy, strategy}, depths[2] = {bit_depth, bit_depth};
+    const PlanKind kinds[2] = {PlanKind::Autoscale, PlanKind::Autoscale};
+    void* canvas[2];
+    OutGeom g;
+    RC(produce_bands(ctx, ins, ins2, ops, 2, strategies, depths, kinds, has_target != 0, target, pad != 0, canvas, &g, stats2));
+    const size_t bytes = g.oc * g.orr * (bit_depth == SARPRO_U8 ? 1 : 2);
+    fill_image(out1, g, 1, bit_depth);
+    fill_image(out2, g, 1, bit_depth);
+    RC(deliver(ctx, canvas[0], bytes, out1));
+    RC(deliver(ctx, canvas[1], bytes, out2));
+    return end_call(ctx);
+}
+
+int sarpro_pipeline_synrgb(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_band* b2, int strategy, int mode,
+                           int has_target, size_t target, int pad, int tamed_band_step, sarpro_image* out,
+                           sarpro_stats* stats2) {
+    (void)mode; // all four SyntheticRgbMode values alias Default (synthetic_rgb.rs:72-79)
+    RC(begin_call(ctx));
+    if (!b1 || !b2 || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    const sarpro_band* ins[2] = {b1, b2};
+    const sarpro_band* ins2[2] = {nullptr, nullptr};
+    const int ops[2] = {-1, -1};
+    const int strategies[2] = {strategy, strategy}, depths[2] = {SARPRO_U8, SARPRO_U8}; // save.rs:321
+    PlanKind kinds[2] = {PlanKind::Autoscale, PlanKind::Autoscale};
+    if (tamed_band_step && strategy == SARPRO_STRATEGY_TAMED) { // save.rs:324-328, 347-351
+        kinds[0] = PlanKind::TamedSynRgbCopol;
+        kinds[1] = PlanKind::TamedSynRgbCross;
+    }
+    void* canvas[2];
+    OutGeom g;
+    RC(produce_bands(ctx, ins, ins2, ops, 2, strategies, depths, kinds, has_target != 0, target, pad != 0, canvas, &g, stats2));
+    const size_t n = g.oc * g.orr;
+    RC(reserve(ctx, ctx->rgb, std::max<size_t>(n * 3, 16)));
+    const bool suppressed = strategy == SARPRO_STRATEGY_TAMED || strategy == SARPRO_STRATEGY_CLAHE; // synthetic_rgb.rs:189-195
+    if (n) {
+        if (suppressed) {
+            RC(reserve(ctx, ctx->hist256, 256 * 4));
+            RC(reserve(ctx, ctx->rgbsel, 16));
+            CU(cudaMemsetAsync(ctx->hist256.p, 0, 256 * 4, ctx->stream));
+            KL(launch_hist256_pair((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (uint32_t*)ctx->hist256.p, ctx->stream));
+            KL(launch_synrgb_floor((const uint32_t*)ctx->hist256.p, n, (uint32_t*)ctx->rgbsel.p, ctx->stream));
+            KL(launch_synrgb((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (const uint8_t*)ctx->rgb_luts.p,
+                             (const uint32_t*)ctx->rgbsel.p, 0, 1, (uint8_t*)ctx->rgb.p, ctx->stream));
+        } else {
+            KL(launch_synrgb((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (const uint8_t*)ctx->rgb_luts.p, nullptr,
+                             kSynRgbDefaultSet, 0, (uint8_t*)ctx->rgb.p, ctx->stream));
+        }
+    }
+    fill_image(out, g, 3, SARPRO_U8);
+    RC(deliver(ctx, ctx->rgb.p, n * 3, out));
+    return end_call(ctx);
+}
+
+// ---- stage level ---------------------------------------------------------------------------------------
+static int stage_pipeline(sarpro_ctx* ctx, const void* data, int dtype, size_t rows, size_t cols, int bit_depth,
+                          int strategy, PlanKind kind, uint8_t* out_u8, uint16_t* out_u16, sarpro_stats* stats) {
+    RC(begin_call(ctx));
+    sarpro_band band{data, dtype, SARPRO_LOC_HOST, rows, cols};
+    const sarpro_band* ins[1] = {&band};
+    const sarpro_band* ins2[1] = {nullptr};
+    const int ops[1] = {-1};
+    const int strategies[1] = {strategy}, depths[1] = {bit_depth};
+    const PlanKind kinds[1] = {kind};
+    void* canvas[1];
+    OutGeom g;
+    RC(produce_bands(ctx, ins, ins2, ops, 1, strategies, depths, kinds, false, 0, false, canvas, &g, stats));
+    const bool out8 = kind != PlanKind::Autoscale || bit_depth == SARPRO_U8;
+    void* dst = out8 ? (void*)out_u8 : (void*)out_u16;
+    const size_t bytes = rows * cols * (out8 ? 1 : 2);
+    if (bytes) {
+        if (!dst) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "output pointer for the requested bit depth is NULL");
+        CU(cudaMemcpyAsync(dst, canvas[0], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->timing.d2h_bytes += bytes;
+    }
+    return end_call(ctx);
+}
+
+int sarpro_process_scalar_data_pipeline(sarpro_ctx* ctx, const float* v, size_t rows, size_t cols, int bit_depth,
+                                        int strategy, uint8_t* out_u8, uint16_t* out_u16, sarpro_stats* stats) {
+    return stage_pipeline(ctx, v, SARPRO_DT_F32, rows, cols, bit_depth, strategy, PlanKind::Autoscale, out_u8, out_u16, stats);
+}
+int sarpro_process_dn_pipeline(sarpro_ctx* ctx, const uint16_t* dn, size_t rows, size_t cols, int bit_depth, int strategy,
+                               uint8_t* out_u8, uint16_t* out_u16, sarpro_stats* stats) {
+    return stage_pipeline(ctx, dn, SARPRO_DT_U16, rows, cols, bit_depth, strategy, PlanKind::Autoscale, out_u8, out_u16, stats);
+}
+int sarpro_autoscale_tamed_synrgb_u8(sarpro_ctx* ctx, const float* v, size_t rows, size_t cols, int is_copol, uint8_t* out) {
+    return stage_pipeline(ctx, v, SARPRO_DT_F32, rows, cols, SARPRO_U8, SARPRO_STRATEGY_TAMED,
+                          is_copol ? PlanKind::TamedSynRgbCopol : PlanKind::TamedSynRgbCross, out, nullptr, nullptr);
+}
+
+int sarpro_scale_u16_to_u8(sarpro_ctx* ctx, const uint16_t* data, size_t n, uint8_t* out) {
+    RC(begin_call(ctx));
+    if (n == 0) return end_call(ctx);
+    if (!data || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    BandWs& w = ctx->band[0];
+    RC(reserve(ctx, w.dn, n * 2));
+    RC(reserve(ctx, w.small, n));
+    RC(reserve(ctx, w.scalars, 64));
+    CU(cudaMemcpyAsync(w.dn.p, data, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    RC(reset_minmax(ctx, 0));
+    KL(launch_minmax_u16((const uint16_t*)w.dn.p, n, (uint32_t*)w.scalars.p, ctx->sm_count, ctx->stream));
+    KL(launch_scale_u16_to_u8((const uint16_t*)w.dn.p, n, (const uint32_t*)w.scalars.p, (uint8_t*)w.small.p, ctx->sm_count, ctx->stream));
+    CU(cudaMemcpyAsync(out, w.small.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx);
+}
+
+int sarpro_pol_op(sarpro_ctx* ctx, int op, const float* a, const float* b, size_t rows, size_t cols, float* out) {
+    RC(begin_call(ctx));
+    const size_t n = rows * cols;
+    if (n == 0) return end_call(ctx);
+    if (!a || !b || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (op < 0 || op > 4) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "unknown polarization operation %d", op);
+    BandWs& w = ctx->band[0];
+    RC(reserve(ctx, w.f32a, n * 4));
+    RC(reserve(ctx, w.f32b, n * 4));
+    RC(reserve(ctx, w.full, n * 4));
+    CU(cudaMemcpyAsync(w.f32a.p, a, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(w.f32b.p, b, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    KL(launch_pol_op((const float*)w.f32a.p, (const float*)w.f32b.p, op, n, (float*)w.full.p, ctx->sm_count, ctx->stream));
+    CU(cudaMemcpyAsync(out, w.full.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx);
+}
+
+int sarpro_add_padding_to_square(sarpro_ctx* ctx, const uint8_t* u8_data, const uint16_t* u16_data, size_t cols,
+                                 size_t rows, int bit_depth, uint8_t* out_u8, uint16_t* out_u16) {
+    RC(begin_call(ctx));
+    const void* src = bit_depth == SARPRO_U8 ? (const void*)u8_data : (const void*)u16_data;
+    void* dst = bit_depth == SARPRO_U8 ? (void*)out_u8 : (void*)out_u16;
+    if (bit_depth == SARPRO_U16 && !u16_data) return fail(ctx, SARPRO_ERR_U16_REQUIRED, "U16 data required for U16 bit depth");
+    const size_t esz = bit_depth == SARPRO_U8 ? 1 : 2;
+    const size_t m = std::max(cols, rows), n = m * m;
+    if (n == 0) return end_call(ctx);
+    if (!src || !dst) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    BandWs& w = ctx->band[0];
+    RC(reserve(ctx, w.full, std::max<size_t>(rows * cols * esz, 16)));
+    RC(reserve(ctx, w.small, n * esz));
+    CU(cudaMemcpyAsync(w.full.p, src, rows * cols * esz, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(w.small.p, 0, n * esz, ctx->stream));
+    const size_t pl = (m - cols) / 2, pt = (m - rows) / 2; // padding.rs:13-14
+    if (rows && cols)
+        CU(cudaMemcpy2DAsync((unsigned char*)w.small.p + (pt * m + pl) * esz, m * esz, w.full.p, cols * esz, cols * esz, rows,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dst, w.small.p, n * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx);
+}
+
+int sarpro_resize_image_data_with_meta(sarpro_ctx* ctx, const uint8_t* u8_data, const uint16_t* u16_data, size_t cols,
+                                       size_t rows, int has_target, size_t target, int bit_depth, int pad,
+                                       uint8_t* out_u8, uint16_t* out_u16, sarpro_resize_meta* meta) {
+    RC(begin_call(ctx));
+    const int pix16 = bit_depth == SARPRO_U16;
+    const size_t esz = pix16 ? 2 : 1;
+    const OutGeom g = out_geometry(cols, rows, has_target != 0, target, pad != 0);
+    if (meta) *meta = g.meta;
+    const void* src = pix16 ? (const void*)u16_data : (const void*)u8_data;
+    void* dst = pix16 ? (void*)out_u16 : (void*)out_u8;
+    if (pix16 && !u16_data) return fail(ctx, SARPRO_ERR_U16_REQUIRED, "U16 data required for U16 bit depth");
+    const size_t n_out = g.oc * g.orr;
+    if (n_out == 0) return end_call(ctx);
+    if (!dst || (rows != 0 && cols != 0 && !src)) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (rows >= (1ull << 31) || cols >= (1ull << 31)) return fail(ctx, SARPRO_ERR_TOO_LARGE, "raster too large");
+    BandWs& w = ctx->band[0];
+    RC(reserve(ctx, w.full, std::max<size_t>(rows * cols * esz, 16)));
+    RC(reserve(ctx, w.small, n_out * esz));
+    CU(cudaMemcpyAsync(w.full.p, src, rows * cols * esz, cudaMemcpyHostToDevice, ctx->stream));
+    if (g.pad) CU(cudaMemsetAsync(w.small.p, 0, n_out * esz, ctx->stream));
+    unsigned char* region = (unsigned char*)w.small.p + (g.pad_top * g.oc + g.pad_left) * esz;
+    if (!g.resize) {
+        if (rows && cols)
+            CU(cudaMemcpy2DAsync(region, g.oc * esz, w.full.p, cols * esz, cols * esz, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else if (g.rc && g.rr) {
+        AxisPlan *ah, *av;
+        RC(get_axis(ctx, (uint32_t)cols, (uint32_t)g.rc, pix16, true, HSRC_IMAGE, &ah));
+        RC(get_axis(ctx, (uint32_t)rows, (uint32_t)g.rr, pix16, false, 0, &av));
+        RC(reserve(ctx, w.temp, rows * g.rc * esz));
+        HResizeArgs a{};
+        a.src = w.full.p;
+        a.src_rows = (uint32_t)rows;
+        a.src_cols = (uint32_t)cols;
+        a.row0 = 0;
+        a.n_rows = (uint32_t)rows;
+        a.temp = w.temp.p;
+        a.ax = ah->dev();
+        KL(launch_hresize_planned(a, HSRC_IMAGE, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem,
+                                  ctx->sm_count, ctx->stream));
+        KL(launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, region, (uint32_t)g.oc, 0, pix16, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(dst, w.small.p, n_out * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx);
+}
+
+int sarpro_create_synthetic_rgb_by_mode_and_strategy(sarpro_ctx* ctx, int mode, int strategy, const uint8_t* band1,
+                                                     const uint8_t* band2, size_t n, uint8_t* rgb) {
+    (void)mode;
+    RC(begin_call(ctx));
+    if (n == 0) return end_call(ctx);
+    if (!band1 || !band2 || !rgb) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    RC(reserve(ctx, ctx->band[0].small, n));
+    RC(reserve(ctx, ctx->band[1].small, n));
+    RC(reserve(ctx, ctx->rgb, n * 3));
+    CU(cudaMemcpyAsync(ctx->band[0].small.p, band1, n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->band[1].small.p, band2, n, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* d1 = (const uint8_t*)ctx->band[0].small.p;
+    const uint8_t* d2 = (const uint8_t*)ctx->band[1].small.p;
+    if (strategy == SARPRO_STRATEGY_TAMED || strategy == SARPRO_STRATEGY_CLAHE) {
+        RC(reserve(ctx, ctx->hist256, 256 * 4));
+        RC(reserve(ctx, ctx->rgbsel, 16));
+        CU(cudaMemsetAsync(ctx->hist256.p, 0, 256 * 4, ctx->stream));
+        KL(launch_hist256_pair(d1, d2, n, (uint32_t*)ctx->hist256.p, ctx->stream));
+        KL(launch_synrgb_floor((const uint32_t*)ctx->hist256.p, n, (uint32_t*)ctx->rgbsel.p, ctx->stream));
+        KL(launch_synrgb(d1, d2, n, (const uint8_t*)ctx->rgb_luts.p, (const uint32_t*)ctx->rgbsel.p, 0, 1, (uint8_t*)ctx->rgb.p, ctx->stream));
+    } else {
+        KL(launch_synrgb(d1, d2, n, (const uint8_t*)ctx->rgb_luts.p, nullptr, kSynRgbDefaultSet, 0, (uint8_t*)ctx->rgb.p, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(rgb, ctx->rgb.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx);
+}
+
+} // extern "C"

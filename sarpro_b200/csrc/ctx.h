@@ -1,0 +1,130 @@
+// ctx.h — internal definition of sarpro_ctx and helpers shared by api.cu / api_f32.cu / comm.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/sarpro_gpu.h"
+#include "kernels.h"
+#include "plan.h"
+
+namespace sarpro {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct AxisPlan {
+    ResampleAxis h; // host copy
+    DevBuf start, size, coef, packed, strips;
+    uint32_t pairs = 0, oxb = 0, rbw = 0, smem = 0, n_strips = 0;
+    bool has_strips = false;
+    AxisDev dev() const {
+        AxisDev d;
+        d.start = (const uint32_t*)start.p;
+        d.size = (const uint32_t*)size.p;
+        d.coef = (const int32_t*)coef.p;
+        d.packed = (const uint32_t*)packed.p;
+        d.window = h.window;
+        d.pairs = pairs;
+        d.out_size = h.out_size;
+        d.in_size = h.in_size;
+        d.precision = h.precision;
+        return d;
+    }
+};
+
+struct AxisKey {
+    uint32_t in, out;
+    int wide, horiz, src_kind;
+    bool operator<(const AxisKey& o) const {
+        return std::tie(in, out, wide, horiz, src_kind) < std::tie(o.in, o.out, o.wide, o.horiz, o.src_kind);
+    }
+};
+
+struct BandWs {
+    DevBuf dn;         // uploaded / converted raster
+    DevBuf f32a, f32b; // f32 staging
+    DevBuf tile_hist, total, lut, tile256, cdf, cdf32, remap;
+    DevBuf temp, small, full;
+    DevBuf scalars; // [0..1] minmax, [2] max_dn, [3] flag
+    DevBuf edges, hist4096, f32scan; // general f32 path
+    BandPlan plan;
+};
+
+constexpr uint32_t kSynRgbSets = 42; // 0..40 suppressed by floor_with_cushion, 41 default
+constexpr uint32_t kSynRgbDefaultSet = 41;
+
+struct OutGeom {
+    bool resize = false, pad = false;
+    size_t rc = 0, rr = 0;  // resized dims
+    size_t oc = 0, orr = 0; // output dims (after pad)
+    size_t pad_left = 0, pad_top = 0;
+    sarpro_resize_meta meta{};
+};
+OutGeom out_geometry(size_t cols, size_t rows, bool has_target, size_t target, bool pad);
+
+struct CommState; // comm.cu
+
+} // namespace sarpro
+
+struct sarpro_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    std::string err;
+    sarpro::BandWs band[2];
+    sarpro::DevBuf units, tile_px, col_dx, col_omdx, col_t, row_dy, row_omdy, row_t, rgb, hist256, rgbsel, rgb_luts;
+    // geometry caches
+    uint64_t units_rows = 0, units_cols = 0, units_scene_rows = 0, units_row_off = 0;
+    int units_clahe = -1;
+    uint32_t n_units = 0, n_tiles = 0;
+    std::map<sarpro::AxisKey, sarpro::AxisPlan*> axes;
+    // pinned staging
+    uint32_t* h_hist = nullptr;    // [2][65536]
+    uint16_t* h_lut = nullptr;     // [2][65536]
+    uint32_t* h_scalars = nullptr; // [2][8]
+    uint8_t* h_remap = nullptr;    // [2][256]
+    // timing
+    cudaEvent_t ev[6] = {};
+    sarpro_timing timing{};
+    int hist_variant = 0;
+    float valid_thresh = 0.f;
+    sarpro::CommState* comm = nullptr;
+};
+
+namespace sarpro {
+
+int fail(sarpro_ctx* c, int code, const char* fmt, ...);
+int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes);
+void release(DevBuf& b);
+int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res);
+int begin_call(sarpro_ctx* ctx);
+int end_call(sarpro_ctx* ctx);
+
+#define CU(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return sarpro::fail(ctx, e__ == cudaErrorMemoryAllocation ? SARPRO_ERR_OUT_OF_MEMORY : SARPRO_ERR_CUDA, \
+                                "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), __FILE__, __LINE__,    \
+                                cudaGetErrorString(e__));                                                    \
+    } while (0)
+#define KL(call)                       \
+    do {                               \
+        CU(call);                      \
+        ctx->timing.kernel_launches++; \
+    } while (0)
+#define RC(call)               \
+    do {                       \
+        int rc__ = (call);     \
+        if (rc__) return rc__; \
+    } while (0)
+
+} // namespace sarpro

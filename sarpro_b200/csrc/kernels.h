@@ -1,0 +1,155 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (definitions in kernels_*.cu).
+// All launchers are asynchronous on `stream` and return the cudaError_t of the launch.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace sarpro {
+
+// ---- work decomposition -----------------------------------------------------------------
+// A histogram work unit: rows [r0,r1) x cols [c0,c1) of the local raster, all inside one tile.
+struct HistUnit {
+    uint32_t r0, r1, c0, c1;
+    uint32_t tile; // index into the per-tile histogram array
+    uint32_t pad;
+};
+
+// ---- pass A: DN histograms ----------------------------------------------------------------
+// tile_hist: [n_tiles][65536] u32, zeroed by the caller. Counts every pixel of every unit.
+cudaError_t launch_dn_hist(const uint16_t* dn, uint64_t cols, const HistUnit* units_dev, uint32_t n_units,
+                           uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream);
+// total[dn] = sum_t tile_hist[t][dn]; max_dn[0] = highest DN with a non-zero total (atomicMax).
+cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint32_t* total, uint32_t* max_dn,
+                              cudaStream_t stream);
+
+// ---- CLAHE tile statistics ------------------------------------------------------------------
+// tile256[t][bin] = sum over dn>=1 of tile_hist[t][dn] where lut[dn] == bin (autoscale.rs:259-269)
+cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut, uint32_t n_tiles, uint32_t max_dn,
+                                 uint32_t* tile256, cudaStream_t stream);
+// clip / redistribute / CDF per tile (autoscale.rs:271-302). tile_px[t] = tile_rows*tile_cols.
+cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, uint32_t n_tiles, double* cdf,
+                             float* cdf32, cudaStream_t stream);
+// per-row / per-column bilinear geometry (autoscale.rs:308-318): t01 = t0 | t1 << 8
+cudaError_t launch_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles, double* d,
+                              double* omd, uint16_t* t01, cudaStream_t stream);
+
+struct ClaheDev {
+    const double* cdf;      // [64][256]
+    const float* cdf32;     // [64][256]
+    const double* col_dx;   // [cols]
+    const double* col_omdx; // [cols]
+    const uint16_t* col_t;  // [cols]
+    const double* row_dy;   // [local rows]
+    const double* row_omdy;
+    const uint16_t* row_t;
+    int tiles_x;
+};
+
+// ---- pass B: full-resolution apply ----------------------------------------------------------
+// out[i] = lut[dn[i]] (u8 or u16 samples). lut has 65536 u16 entries.
+cudaError_t launch_apply_lut(const uint16_t* dn, uint64_t n, const uint16_t* lut, uint8_t* out_u8, uint16_t* out_u16,
+                             int sm_count, cudaStream_t stream);
+// CLAHE apply: bin = lut[dn]; v = blend; out = trunc(clamp(v) * max_val); invalid (dn == 0) -> 0.
+// minmax[0] = min, minmax[1] = max over all written samples (atomicMin/Max; init {65535, 0}).
+cudaError_t launch_apply_clahe(const uint16_t* dn, uint32_t rows, uint32_t cols, const uint16_t* lut, ClaheDev cl,
+                               int max_val, uint8_t* out_u8, uint16_t* out_u16, uint32_t* minmax, int sm_count,
+                               cudaStream_t stream);
+// in-place u8 remap through a 256-entry table
+cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, int sm_count, cudaStream_t stream);
+// min/max of a u16 array + u16 -> u8 remap (scale_u16_to_u8, autoscale.rs:348-364)
+cudaError_t launch_minmax_u16(const uint16_t* data, uint64_t n, uint32_t* minmax, int sm_count, cudaStream_t stream);
+cudaError_t launch_scale_u16_to_u8(const uint16_t* data, uint64_t n, const uint32_t* minmax, uint8_t* out, int sm_count,
+                                   cudaStream_t stream);
+
+// ---- resize -------------------------------------------------------------------------------
+// Device-side description of one Lanczos axis (built by plan.cpp, uploaded by the context).
+struct AxisDev {
+    const uint32_t* start; // [out]
+    const uint32_t* size;  // [out]
+    const int32_t* coef;   // [out][window]  (plain, one i32 per tap)
+    const uint32_t* packed; // u8 horizontal only: [out][pairs] two i16 taps per word, tap 0 at source (start & ~3)
+    uint32_t window, pairs, out_size, in_size;
+    int precision;
+};
+
+enum HSrcKind { HSRC_IMAGE = 0, HSRC_DN_LUT = 1, HSRC_DN_CLAHE = 2 };
+
+struct HResizeArgs {
+    // source
+    const void* src;       // u8/u16 image (HSRC_IMAGE) or u16 DN raster
+    uint32_t src_rows;     // rows available in src (local)
+    uint32_t src_cols;
+    const uint16_t* lut;   // HSRC_DN_*
+    const uint8_t* remap;  // HSRC_DN_CLAHE u8: 256-entry post-blend remap (scale_u16_to_u8) or nullptr
+    ClaheDev clahe;        // HSRC_DN_CLAHE
+    uint32_t* minmax;      // HSRC_DN_CLAHE: min/max of the blended samples (before remap)
+    // rows to produce: temp row i <- source row (row0 + i), i < n_rows
+    uint32_t row0, n_rows;
+    void* temp;            // [n_rows][out_cols] same pixel type
+    AxisDev ax;
+};
+// One CTA of the horizontal pass owns a strip of output columns; the strip's source span is staged per row.
+struct HStrip {
+    uint32_t sc0;  // first staged source column (multiple of 8)
+    uint32_t nvec; // staged 8-sample vectors per row
+};
+} // namespace sarpro
+#include <vector>
+namespace sarpro {
+// Strip table + launch geometry for an axis (host arrays). pix16: u16 pixels. Returns the block width
+// (output columns per CTA), the shared row-buffer pitch in bytes and the dynamic shared memory size.
+cudaError_t hresize_build_strips(const uint32_t* start_h, const uint32_t* size_h, uint32_t out_size, uint32_t in_size,
+                                 uint32_t window, uint32_t pairs, int pix16, int src_kind, uint32_t* oxb_out,
+                                 std::vector<HStrip>* strips, uint32_t* rbw_out, uint32_t* smem_out);
+// pix16 == 0: u8 pixels (i16 taps / i32 accumulate); 1: u16 pixels (i32 taps / i64 accumulate)
+cudaError_t launch_hresize_planned(const HResizeArgs& a, int src_kind, int pix16, const HStrip* strips_dev,
+                                   uint32_t n_strips, uint32_t oxb, uint32_t rbw, uint32_t smem, int sm_count,
+                                   cudaStream_t stream);
+// vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
+cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
+                           void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream);
+
+// ---- small-image stages ---------------------------------------------------------------------
+// dst (dcols x drows) zero-filled, src (scols x srows) copied at (pad_left, pad_top). elem = 1 or 2 bytes.
+cudaError_t launch_pad(const void* src, uint32_t scols, uint32_t srows, void* dst, uint32_t dcols, uint32_t drows,
+                       uint32_t pad_left, uint32_t pad_top, int elem, cudaStream_t stream);
+cudaError_t launch_hist256_pair(const uint8_t* b1, const uint8_t* b2, uint64_t n, uint32_t* hist256,
+                                cudaStream_t stream);
+// suppressed-floor selection on the device: floor_idx[0] = floor_with_cushion (synthetic_rgb.rs:99-113)
+cudaError_t launch_synrgb_floor(const uint32_t* hist256, uint64_t n_per_band, uint32_t* floor_idx, cudaStream_t stream);
+// lut_sets: [41] sets of (r[256], g[256], b[65536]); set index = floor (suppressed) or a fixed index (default)
+constexpr size_t kSynRgbSetBytes = 256 + 256 + 65536;
+cudaError_t launch_synrgb(const uint8_t* b1, const uint8_t* b2, uint64_t n, const uint8_t* lut_sets,
+                          const uint32_t* set_idx_dev, uint32_t fixed_set, int suppressed, uint8_t* rgb,
+                          cudaStream_t stream);
+
+// ---- f32 rasters (API boundary Array2<f32>; polarization ops) --------------------------------
+// f32 -> u16 when every sample is an integer in [0,65535] (a u16 raster read as f32, gdal.rs:123);
+// flag[0] is set non-zero when any sample is not. op != -1 fuses the polarization op (ops.rs:4-44).
+cudaError_t launch_f32_to_dn(const float* a, const float* b, int op, uint64_t n, float valid_thresh, uint16_t* dn,
+                             uint32_t* flag, int sm_count, cudaStream_t stream);
+cudaError_t launch_pol_op(const float* a, const float* b, int op, uint64_t n, float* out, int sm_count,
+                          cudaStream_t stream);
+// generic path: order-preserving key of every sample's f32 value -> min/max over valid samples.
+// valid <=> v >= valid_thresh (host-derived bit pattern of the smallest f32 with dB > -50)
+struct F32Scan {
+    uint32_t min_key, max_key; // ordered-uint keys of min / max valid value
+    unsigned long long valid_count;
+};
+cudaError_t launch_f32_scan(const float* a, const float* b, int op, uint64_t n, float valid_thresh, F32Scan* out,
+                            int sm_count, cudaStream_t stream);
+// 4096-bin histogram (autoscale.rs:108-117) by searching host-built f32 bin-edge thresholds:
+// idx(v) = number of edges e_k (k = 1..4095) with v >= e_k.
+cudaError_t launch_f32_hist4096(const float* a, const float* b, int op, uint64_t n, float valid_thresh,
+                                const float* edges4096, unsigned long long* hist4096, int sm_count,
+                                cudaStream_t stream);
+// quantisation by thresholds: out = number of level edges q_k (k = 1..n_levels-1) with v >= q_k; invalid -> 0.
+cudaError_t launch_f32_quantize(const float* a, const float* b, int op, uint64_t n, float valid_thresh,
+                                const float* level_edges, uint32_t n_levels, uint8_t* out_u8, uint16_t* out_u16,
+                                int sm_count, cudaStream_t stream);
+// dB plane + mask (pipeline.rs:8-40) for callers that want them (device log10; see DESIGN.md tolerance)
+cudaError_t launch_db_mask(const float* v, uint64_t n, double* db, uint8_t* mask, int sm_count, cudaStream_t stream);
+
+} // namespace sarpro

@@ -1,0 +1,441 @@
+// kernels_dn.cu — the u16-DN passes of the raster path for sm_100a.
+//
+// Design: for a u16 raster every per-pixel quantity of the reference's path
+// (dB pipeline.rs:19-20, validity :22, 4096-bin stat histogram autoscale.rs:108-117, clip/gamma/
+// quantise :437-446 / :647-655, scale_u16_to_u8 :348-364, CLAHE bin :263) is a pure function of the
+// DN, so pass A only counts DNs (per CLAHE tile) and pass B is "load DN, look up, consume".
+// No transcendental runs on the device; the host planner (plan.cpp) evaluates them once per
+// distinct DN with the same libm the reference uses.
+//
+// All kernels are HBM-streaming: 128-bit coalesced loads, shared-memory privatised histograms /
+// tables, grids sized to a multiple of the SM count.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sarpro {
+
+// =============================================================================================
+// Pass A — per-tile DN histogram.  2 B/px read; one shared-memory atomic per non-zero pixel.
+// =============================================================================================
+// Shared layout: NCOPY = 1 << LOGC interleaved sub-histograms, word (dn << LOGC) | (lane & (NCOPY-1)).
+// With NCOPY = 32 every lane owns a bank (no conflicts); smaller NCOPY trades conflicts for range.
+// DN 0 (black fill, long runs of identical values) is counted in a register; DN >= HOT (rare bright
+// targets) goes straight to the L2-resident tile histogram.
+template <int HOT, int LOGC>
+__global__ void __launch_bounds__(512) k_dn_hist(const uint16_t* __restrict__ dn, uint64_t cols,
+                                                 const HistUnit* __restrict__ units, uint32_t n_units,
+                                                 uint32_t* __restrict__ tile_hist) {
+    extern __shared__ uint32_t sh[];
+    constexpr uint32_t NCOPY = 1u << LOGC;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t mycopy = lane & (NCOPY - 1);
+    for (uint32_t i = tid; i < (uint32_t)HOT * NCOPY; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+
+    // 16-byte aligned view of the raster: element e of `dn` is element e + eoff of `dn_al`.
+    const uint16_t* dn_al = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(dn) & ~uintptr_t(15));
+    const uint64_t eoff = (uint64_t)(dn - dn_al);
+
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const HistUnit un = units[u];
+        uint32_t* __restrict__ gh = tile_hist + (size_t)un.tile * 65536u;
+        unsigned zeros = 0;
+        const uint32_t seg = un.c1 - un.c0;
+
+        auto add = [&](uint32_t d) {
+            if (d == 0) zeros++;
+            else if (d < (uint32_t)HOT) atomicAdd(&sh[(d << LOGC) | mycopy], 1u);
+            else atomicAdd(&gh[d], 1u);
+        };
+        auto consume = [&](const uint4& q, uint64_t vb, uint64_t e0, uint64_t e1) {
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            if (vb >= e0 && vb + 8 <= e1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { add(w[k] & 0xffffu); add(w[k] >> 16); }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t e = vb + k;
+                    if (e >= e0 && e < e1) add((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu));
+                }
+            }
+        };
+
+        for (uint32_t r = un.r0 + warp; r < un.r1; r += nwarps) {
+            const uint64_t e0 = (uint64_t)r * cols + un.c0 + eoff, e1 = e0 + seg;
+            const uint64_t v0 = e0 >> 3, v1 = (e1 + 7) >> 3;
+            for (uint64_t v = v0 + lane; v < v1; v += 128) {
+                uint4 q[4];
+                bool ok[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t vv = v + 32u * j;
+                    ok[j] = vv < v1;
+                    if (ok[j]) q[j] = ld_stream_u4(dn_al + (vv << 3));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ok[j]) consume(q[j], (v + 32u * j) << 3, e0, e1);
+            }
+        }
+        zeros = warp_reduce_add(zeros);
+        if (lane == 0 && zeros) atomicAdd(&gh[0], zeros);
+        __syncthreads();
+        for (uint32_t b = tid; b < (uint32_t)HOT; b += blockDim.x) {
+            uint32_t s = 0;
+#pragma unroll
+            for (uint32_t c = 0; c < NCOPY; ++c) {
+                s += sh[(b << LOGC) | c];
+                sh[(b << LOGC) | c] = 0;
+            }
+            if (s) atomicAdd(&gh[b], s);
+        }
+        __syncthreads();
+    }
+}
+
+template <int HOT, int LOGC>
+static cudaError_t launch_dn_hist_t(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
+                                    uint32_t* tile_hist, int sm_count, cudaStream_t stream) {
+    const size_t smem = (size_t)HOT * (1u << LOGC) * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_dn_hist<HOT, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int per_sm = (int)((227u * 1024u) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 3) per_sm = 3; // 512 threads each
+    uint32_t grid = (uint32_t)(sm_count * per_sm);
+    if (grid > n_units) grid = n_units;
+    if (grid == 0) return cudaSuccess;
+    k_dn_hist<HOT, LOGC><<<grid, 512, smem, stream>>>(dn, cols, units, n_units, tile_hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dn_hist(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
+                           uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream) {
+    switch (variant) {
+    case 1: return launch_dn_hist_t<4096, 0>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 2: return launch_dn_hist_t<2048, 2>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 3: return launch_dn_hist_t<1024, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 4: return launch_dn_hist_t<1024, 5>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 5: return launch_dn_hist_t<4096, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 6: return launch_dn_hist_t<1536, 5>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    default: return launch_dn_hist_t<2048, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    }
+}
+
+// total[dn] = sum over tiles; max_dn = highest non-empty DN
+__global__ void k_hist_total(const uint32_t* __restrict__ tile_hist, uint32_t n_tiles, uint32_t* __restrict__ total,
+                             uint32_t* __restrict__ max_dn) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; // < 65536
+    uint32_t s = 0;
+    for (uint32_t t = 0; t < n_tiles; ++t) s += tile_hist[(size_t)t * 65536u + d];
+    total[d] = s;
+    unsigned m = warp_reduce_max(s ? d : 0u);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_dn, m);
+}
+cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint32_t* total, uint32_t* max_dn,
+                              cudaStream_t stream) {
+    k_hist_total<<<65536 / 256, 256, 0, stream>>>(tile_hist, n_tiles, total, max_dn);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// CLAHE tile statistics
+// =============================================================================================
+__global__ void k_clahe_tile256(const uint32_t* __restrict__ tile_hist, const uint16_t* __restrict__ lut,
+                                uint32_t max_dn, uint32_t* __restrict__ tile256) {
+    __shared__ uint32_t h[256];
+    const uint32_t t = blockIdx.x, part = blockIdx.y, nparts = gridDim.y;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t* th = tile_hist + (size_t)t * 65536u;
+    for (uint32_t d = 1 + part * blockDim.x + threadIdx.x; d <= max_dn; d += nparts * blockDim.x) {
+        const uint32_t c = th[d];
+        if (c) atomicAdd(&h[lut[d] & 255u], c);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&tile256[t * 256u + threadIdx.x], h[threadIdx.x]);
+}
+cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut, uint32_t n_tiles, uint32_t max_dn,
+                                 uint32_t* tile256, cudaStream_t stream) {
+    uint32_t parts = (max_dn + 2047) / 2048;
+    if (parts < 1) parts = 1;
+    if (parts > 32) parts = 32;
+    k_clahe_tile256<<<dim3(n_tiles, parts), 256, 0, stream>>>(tile_hist, lut, max_dn, tile256);
+    return cudaGetLastError();
+}
+
+// autoscale.rs:271-302. Every quantity is an integer or an integer multiple of 1/128 below 2^53, so the
+// f64 sums are exact and independent of summation order; products/quotients use explicit round-to-nearest
+// intrinsics (never contracted to FMA).
+__global__ void __launch_bounds__(256) k_clahe_cdf(const uint32_t* __restrict__ tile256,
+                                                   const uint64_t* __restrict__ tile_px, double* __restrict__ cdf,
+                                                   float* __restrict__ cdf32) {
+    __shared__ double s_ex[256];
+    __shared__ unsigned long long s_pre[256];
+    const uint32_t t = blockIdx.x, i = threadIdx.x;
+    uint32_t h = tile256[t * 256u + i];
+    const double avg = __ddiv_rn((double)tile_px[t], 256.0);       // :242-245
+    const double thr = fmax(__dmul_rn(2.0, avg), 1.0);             // :273
+    double ex = 0.0;
+    if ((double)h > thr) {                                         // :276-279
+        ex = __dsub_rn((double)h, thr);
+        h = (uint32_t)thr;
+    }
+    s_ex[i] = ex;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)i < o) s_ex[i] = __dadd_rn(s_ex[i], s_ex[i + o]);
+        __syncthreads();
+    }
+    const double excess = s_ex[0];
+    const double add_per_bin = floor(__ddiv_rn(excess, 256.0));    // :282
+    const double remf = round(__dsub_rn(excess, __dmul_rn(add_per_bin, 256.0))); // :283
+    const unsigned long long remainder = remf > 0.0 ? (unsigned long long)remf : 0ull;
+    h = (uint32_t)__dadd_rn((double)h, add_per_bin);               // :285
+    h += (uint32_t)(remainder / 256ull) + (i < (uint32_t)(remainder % 256ull) ? 1u : 0u); // :287-292
+    s_pre[i] = h;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) { // inclusive scan (integers)
+        unsigned long long v = (int)i >= o ? s_pre[i - o] : 0ull;
+        __syncthreads();
+        s_pre[i] += v;
+        __syncthreads();
+    }
+    const double total = fmax((double)s_pre[255], 1.0);            // :295
+    double c = __ddiv_rn((double)s_pre[i], total);                 // :299-300
+    c = c < 0.0 ? 0.0 : (c > 1.0 ? 1.0 : c);
+    cdf[t * 256u + i] = c;
+    if (cdf32) cdf32[t * 256u + i] = (float)c;
+}
+cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, uint32_t n_tiles, double* cdf,
+                             float* cdf32, cudaStream_t stream) {
+    k_clahe_cdf<<<n_tiles, 256, 0, stream>>>(tile256, tile_px, cdf, cdf32);
+    return cudaGetLastError();
+}
+
+// autoscale.rs:308-318 for one axis: f = g/tile - 0.5; t = max(floor(f),0); d = f - t; neighbours clamped.
+__global__ void k_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles,
+                             double* __restrict__ d, double* __restrict__ omd, uint16_t* __restrict__ t01) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double f = __dsub_rn(__ddiv_rn((double)(global_offset + i), (double)tile_size), 0.5);
+    const long long t = (long long)fmax(floor(f), 0.0);
+    const double dd = __dsub_rn(f, (double)t);
+    const long long hi = (long long)n_tiles - 1;
+    const long long t0 = t < 0 ? 0 : (t > hi ? hi : t);
+    const long long t1 = (t + 1) < 0 ? 0 : ((t + 1) > hi ? hi : (t + 1));
+    d[i] = dd;
+    omd[i] = __dsub_rn(1.0, dd);
+    t01[i] = (uint16_t)(t0 | (t1 << 8));
+}
+cudaError_t launch_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles, double* d,
+                              double* omd, uint16_t* t01, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_clahe_axis<<<(n + 255) / 256, 256, 0, stream>>>(n, global_offset, tile_size, n_tiles, d, omd, t01);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// Pass B — full-resolution apply (LUT only). 2 B/px read, 1 or 2 B/px written.
+// =============================================================================================
+constexpr uint32_t kLutHot = 8192; // DN range staged in shared memory; brighter DNs read the global LUT
+
+template <typename OutT>
+__global__ void __launch_bounds__(512) k_apply_lut(const uint16_t* __restrict__ dn, uint64_t n,
+                                                   const uint16_t* __restrict__ lut, OutT* __restrict__ out) {
+    __shared__ OutT s_lut[kLutHot];
+    for (uint32_t i = threadIdx.x; i < kLutHot; i += blockDim.x) s_lut[i] = (OutT)lut[i];
+    __syncthreads();
+    auto look = [&](uint32_t d) -> uint32_t { return d < kLutHot ? (uint32_t)s_lut[d] : (uint32_t)__ldg(&lut[d]); };
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dn) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(out) & (8 * sizeof(OutT) - 1)) == 0);
+    const uint64_t nvec = aligned ? (n >> 3) : 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint4 q = ld_stream_u4(dn + (v << 3));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[2 * k] = look(w[k] & 0xffffu);
+            o[2 * k + 1] = look(w[k] >> 16);
+        }
+        if (sizeof(OutT) == 1) {
+            uint2 p;
+            p.x = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+            p.y = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
+            st_stream_u2(out + (v << 3), p);
+        } else {
+            uint4 p;
+            p.x = o[0] | (o[1] << 16);
+            p.y = o[2] | (o[3] << 16);
+            p.z = o[4] | (o[5] << 16);
+            p.w = o[6] | (o[7] << 16);
+            st_stream_u4(out + (v << 3), p);
+        }
+    }
+    for (uint64_t e = (nvec << 3) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+        out[e] = (OutT)look(dn[e]);
+}
+cudaError_t launch_apply_lut(const uint16_t* dn, uint64_t n, const uint16_t* lut, uint8_t* out_u8, uint16_t* out_u16,
+                             int sm_count, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    uint64_t want = (n / 8 + 511) / 512;
+    uint32_t grid = (uint32_t)(want < (uint64_t)sm_count * 4 ? (want ? want : 1) : (uint64_t)sm_count * 4);
+    if (out_u8) k_apply_lut<uint8_t><<<grid, 512, 0, stream>>>(dn, n, lut, out_u8);
+    else k_apply_lut<uint16_t><<<grid, 512, 0, stream>>>(dn, n, lut, out_u16);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// CLAHE blend (exact): autoscale.rs:320-329 then :602.
+// =============================================================================================
+// Explicit _rn intrinsics keep the reference's operation order and forbid FMA contraction.
+__device__ __forceinline__ double clahe_blend_exact(double c00, double c01, double c10, double c11, double dx,
+                                                    double omdx, double dy, double omdy) {
+    const double top = __dadd_rn(__dmul_rn(c00, omdx), __dmul_rn(c01, dx));
+    const double bottom = __dadd_rn(__dmul_rn(c10, omdx), __dmul_rn(c11, dx));
+    return __dadd_rn(__dmul_rn(top, omdy), __dmul_rn(bottom, dy));
+}
+__device__ __forceinline__ uint32_t clahe_quantize(double v, double max_val) {
+    const double n = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); // clamp(0,1); NaN cannot occur
+    return (uint32_t)__dmul_rn(n, max_val);               // `as u16` truncation
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_apply_clahe(const uint16_t* __restrict__ dn, uint32_t rows, uint32_t cols,
+                                                     const uint16_t* __restrict__ lut, ClaheDev cl, double max_val,
+                                                     OutT* __restrict__ out, uint32_t* __restrict__ minmax) {
+    uint32_t mn = 0xffffffffu, mx = 0;
+    const uint32_t vec_per_row = (cols + 7) / 8;
+    const uint64_t total = (uint64_t)rows * vec_per_row;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(idx / vec_per_row);
+        const uint32_t c0 = (uint32_t)(idx % vec_per_row) * 8;
+        const double dy = cl.row_dy[r], omdy = cl.row_omdy[r];
+        const uint32_t ty = cl.row_t[r];
+        const double* cdf_t0 = cl.cdf + (size_t)(ty & 255u) * cl.tiles_x * 256u;
+        const double* cdf_t1 = cl.cdf + (size_t)(ty >> 8) * cl.tiles_x * 256u;
+        const uint64_t base = (uint64_t)r * cols + c0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < 8 && c0 + k < cols; ++k) {
+            const uint32_t c = c0 + k;
+            const uint32_t d = dn[base + k];
+            uint32_t o = 0;
+            if (d != 0) {
+                const uint32_t bin = lut[d] & 255u;
+                const uint32_t tx = cl.col_t[c];
+                const uint32_t x0 = (tx & 255u) * 256u + bin, x1 = (tx >> 8) * 256u + bin;
+                const double v = clahe_blend_exact(cdf_t0[x0], cdf_t0[x1], cdf_t1[x0], cdf_t1[x1], cl.col_dx[c],
+                                                   cl.col_omdx[c], dy, omdy);
+                o = clahe_quantize(v, max_val);
+            }
+            out[base + k] = (OutT)o;
+            mn = min(mn, o);
+            mx = max(mx, o);
+        }
+    }
+    mn = warp_reduce_min(mn);
+    mx = warp_reduce_max(mx);
+    if ((threadIdx.x & 31) == 0 && mn != 0xffffffffu) {
+        atomicMin(&minmax[0], mn);
+        atomicMax(&minmax[1], mx);
+    }
+}
+cudaError_t launch_apply_clahe(const uint16_t* dn, uint32_t rows, uint32_t cols, const uint16_t* lut, ClaheDev cl,
+                               int max_val, uint8_t* out_u8, uint16_t* out_u16, uint32_t* minmax, int sm_count,
+                               cudaStream_t stream) {
+    if (rows == 0 || cols == 0) return cudaSuccess;
+    const uint32_t grid = (uint32_t)sm_count * 8;
+    if (out_u8) k_apply_clahe<uint8_t><<<grid, 256, 0, stream>>>(dn, rows, cols, lut, cl, (double)max_val, out_u8, minmax);
+    else k_apply_clahe<uint16_t><<<grid, 256, 0, stream>>>(dn, rows, cols, lut, cl, (double)max_val, out_u16, minmax);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// scale_u16_to_u8 pieces (autoscale.rs:348-364)
+// =============================================================================================
+__global__ void __launch_bounds__(512) k_remap_u8(uint8_t* __restrict__ data, uint64_t n,
+                                                  const uint8_t* __restrict__ remap) {
+    __shared__ uint8_t s[256];
+    if (threadIdx.x < 256) s[threadIdx.x] = remap[threadIdx.x];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+    const uint64_t nvec = aligned ? n >> 4 : 0;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        uint4 q = *reinterpret_cast<const uint4*>(data + (v << 4));
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            w[k] = (uint32_t)s[w[k] & 255u] | ((uint32_t)s[(w[k] >> 8) & 255u] << 8) |
+                   ((uint32_t)s[(w[k] >> 16) & 255u] << 16) | ((uint32_t)s[w[k] >> 24] << 24);
+        *reinterpret_cast<uint4*>(data + (v << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (uint64_t e = (nvec << 4) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+        data[e] = s[data[e]];
+}
+cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, int sm_count, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_remap_u8<<<sm_count * 4, 512, 0, stream>>>(data, n, remap256);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(512) k_minmax_u16(const uint16_t* __restrict__ data, uint64_t n,
+                                                    uint32_t* __restrict__ minmax) {
+    uint32_t mn = 0xffffffffu, mx = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+    const uint64_t nvec = aligned ? n >> 3 : 0;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint4 q = ld_stream_u4(data + (v << 3));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mn = min(mn, min(w[k] & 0xffffu, w[k] >> 16));
+            mx = max(mx, max(w[k] & 0xffffu, w[k] >> 16));
+        }
+    }
+    for (uint64_t e = (nvec << 3) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        mn = min(mn, (uint32_t)data[e]);
+        mx = max(mx, (uint32_t)data[e]);
+    }
+    mn = warp_reduce_min(mn);
+    mx = warp_reduce_max(mx);
+    if ((threadIdx.x & 31) == 0 && mn != 0xffffffffu) {
+        atomicMin(&minmax[0], mn);
+        atomicMax(&minmax[1], mx);
+    }
+}
+cudaError_t launch_minmax_u16(const uint16_t* data, uint64_t n, uint32_t* minmax, int sm_count, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_minmax_u16<<<sm_count * 4, 512, 0, stream>>>(data, n, minmax);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(512) k_scale_u16_to_u8(const uint16_t* __restrict__ data, uint64_t n,
+                                                         const uint32_t* __restrict__ minmax,
+                                                         uint8_t* __restrict__ out) {
+    const float mn = (float)minmax[0], mx = (float)minmax[1];
+    const float scale = mx > mn ? __fdiv_rn(255.0f, __fsub_rn(mx, mn)) : 1.0f;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        float val = roundf(__fmul_rn(__fsub_rn((float)data[e], mn), scale));
+        val = val < 0.0f ? 0.0f : (val > 255.0f ? 255.0f : val);
+        out[e] = (uint8_t)val;
+    }
+}
+cudaError_t launch_scale_u16_to_u8(const uint16_t* data, uint64_t n, const uint32_t* minmax, uint8_t* out, int sm_count,
+                                   cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_scale_u16_to_u8<<<sm_count * 4, 512, 0, stream>>>(data, n, minmax, out);
+    return cudaGetLastError();
+}
+
+} // namespace sarpro

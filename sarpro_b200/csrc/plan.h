@@ -1,0 +1,99 @@
+// plan.h — host-side planner of the B200 raster path.
+//
+// The device passes reduce a raster to integer histograms; everything that is O(bins) and needs
+// the host libm (log10 / pow / powf, so results equal the reference's, which calls the same libm
+// through Rust's f64::log10 / powf) happens here, once per band, and is shipped back as small
+// look-up tables.  Follows, from the reference:
+//   pipeline.rs:19-22            dB + validity per distinct sample value
+//   autoscale.rs:35-160          compute_histogram_stats, evaluated over the value histogram
+//   autoscale.rs:368-448         autoscale_db_image      (Standard)
+//   autoscale.rs:452-659         autoscale_db_image_advanced
+//   autoscale.rs:348-364         scale_u16_to_u8 folded into the LUT
+//   autoscale.rs:710-742         autoscale_db_image_tamed_synrgb_u8
+//   synthetic_rgb.rs:10-67,88-178  channel LUTs
+//   fast_image_resize 5.x (Cargo.toml:33) Lanczos3 coefficient tables (resize.rs:39-40)
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/sarpro_gpu.h"
+
+namespace sarpro {
+
+constexpr int kDnBins = 65536;
+constexpr int kStatBins = 4096;   // autoscale.rs:103
+constexpr int kClaheBins = 256;   // autoscale.rs:593
+constexpr int kClaheTiles = 8;    // autoscale.rs:593
+constexpr double kClaheClip = 2.0;
+
+enum class PlanKind {
+    Autoscale,        // process_scalar_data_pipeline result (U8 incl. scale_u16_to_u8, or U16)
+    TamedSynRgbCopol, // autoscale_db_image_tamed_synrgb_u8(is_copol = true)
+    TamedSynRgbCross, // autoscale_db_image_tamed_synrgb_u8(is_copol = false)
+};
+
+// A "value histogram": distinct sample values (as dB, with validity) and their counts.
+// For u16 DN rasters the key is the DN itself (value table = dB of every u16, computed once).
+struct BandPlan {
+    sarpro_stats stats{};
+    bool any_valid = false;
+    bool clahe = false;            // lut holds 256-bin indices, blend happens on the device
+    uint16_t pre_min = 0, pre_max = 0; // min/max of the quantised samples before scale_u16_to_u8
+    std::vector<uint16_t> lut;     // kDnBins entries: DN -> final sample (or CLAHE bin)
+    uint32_t max_present_dn = 0;   // highest DN with a non-zero count
+};
+
+// dB value of every u16 DN after the f32 cast (pipeline.rs:19-20); valid iff > -50 (pipeline.rs:22).
+const double* dn_db_table();
+
+// Plan one band from its 65,536-bin DN histogram.
+void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out);
+
+// scale_u16_to_u8 (autoscale.rs:348-364) as a 65536-entry (or 256-entry) remap for given min/max.
+void make_u16_to_u8_remap(uint16_t mn, uint16_t mx, int n_entries, uint8_t* remap);
+
+// ---- general f32 rasters (polarization ops, calibrated inputs) -----------------------------
+// Stats from the device-built 4096-bin histogram over [min_db, max_db] (autoscale.rs:103-159).
+void stats_from_stat_histogram(const uint64_t* hist4096, uint64_t count, double min_db, double max_db, double mean_db,
+                               double std_db, sarpro_stats* st);
+// Window selection shared by both paths: fills low_clip / high_clip / gamma in st.
+void choose_window(int strategy, PlanKind kind, sarpro_stats* st);
+
+// ---- CLAHE tile statistics (autoscale.rs:235-302) ----------------------------------------
+struct ClaheGeom {
+    uint64_t rows = 0, cols = 0, tile_h = 0, tile_w = 0;
+};
+ClaheGeom clahe_geometry(uint64_t rows, uint64_t cols);
+
+// ---- Lanczos3 coefficient tables ---------------------------------------------------------
+struct ResampleAxis {
+    uint32_t in_size = 0, out_size = 0;
+    uint32_t window = 0;            // taps stored per output sample (padded with zeros)
+    int precision = 0;
+    std::vector<uint32_t> start;    // first source index per output sample
+    std::vector<uint32_t> size;     // taps actually used per output sample
+    std::vector<int32_t> coef;      // out_size * window fixed-point coefficients (fit i16 for u8 pixels)
+};
+// wide == false: u8 pixels (i16 coefficients, i32 accumulate); wide == true: u16 pixels (i32 / i64).
+void build_lanczos3_axis(uint32_t in_size, uint32_t out_size, bool wide, ResampleAxis* ax);
+
+// resize.rs:6-30
+void calculate_resize_dimensions(size_t cols, size_t rows, size_t target, size_t* new_cols, size_t* new_rows);
+// dims after the control flow of resize.rs:112-236 (resize unless long side == target, then pad)
+void resize_output_dims(size_t cols, size_t rows, bool has_target, size_t target, bool pad, size_t* resized_cols,
+                        size_t* resized_rows, size_t* out_cols, size_t* out_rows);
+
+// ---- synthetic RGB LUTs ------------------------------------------------------------------
+struct SynRgbLut {
+    uint8_t r[256];
+    uint8_t g[256];
+    std::vector<uint8_t> b; // 65536, index (v1 << 8) | v2
+    int floor_with_cushion = -1; // suppressed variant only
+};
+void build_synrgb_default_lut(SynRgbLut* lut);                       // synthetic_rgb.rs:10-50
+void build_synrgb_suppressed_lut(int floor_with_cushion, SynRgbLut* lut); // synthetic_rgb.rs:115-154
+// synthetic_rgb.rs:92-113: floor_with_cushion from the combined 256-bin histogram of both bands
+int synrgb_floor_from_histogram(const uint32_t* hist256, uint64_t n_per_band);
+
+} // namespace sarpro
