@@ -1,0 +1,124 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Integer outputs must be bit-exact; percentiles / window f64 bit-exact; mean/std within 1e-9 (the
+reference's serial Welford rounding is order-dependent and is not reproducible from histograms)."""
+import numpy as np
+import pytest
+
+import sarpro_b200 as S
+from oracle import pyoracle as O
+from tests.fixtures import CASES
+
+pytestmark = pytest.mark.gpu
+
+EXACT_STATS = ["valid_count", "min_db", "max_db", "median_db", "p01", "p02", "p05", "p10", "p25", "p75", "p90",
+               "p95", "p98", "p99", "low_clip", "high_clip", "gamma"]
+
+
+def check_stats(st, so):
+    for k in EXACT_STATS:
+        assert getattr(st, k) == getattr(so, k), k
+    assert abs(st.mean_db - so.mean_db) <= 1e-9 * max(1.0, abs(so.mean_db))
+    assert abs(st.std_db - so.std_db) <= 1e-9 * max(1.0, abs(so.std_db))
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("strategy", range(7))
+@pytest.mark.parametrize("bit_depth", [S.U8, S.U16])
+def test_process_scalar_data_pipeline(ctx, case, strategy, bit_depth):
+    dn = CASES[case](203, 317)  # neither divisible by 8
+    v = dn.astype(np.float32)
+    po = O.process_scalar_data_pipeline(v, bit_depth, strategy, want_db=False)
+    for arr in (v, dn):  # f32 API boundary and raw DN entry
+        u8, u16, st = ctx.process_scalar_data_pipeline(arr, bit_depth, strategy)
+        got, ref = (u8, po.u8) if bit_depth == S.U8 else (u16, po.u16)
+        assert np.array_equal(got, ref)
+        check_stats(st, po.stats)
+
+
+@pytest.mark.parametrize("strategy", [S.STANDARD, S.ROBUST, S.CLAHE, S.TAMED])
+@pytest.mark.parametrize("shape", [(1024, 1536), (777, 1201), (1500, 640)])
+def test_pipeline_single_resized(ctx, strategy, shape):
+    dn = CASES["speckle"](*shape)
+    v = dn.astype(np.float32)
+    for bd in (S.U8, S.U16):
+        for target, pad in ((256, True), (300, False), (None, True)):
+            ref, meta = O.pipeline_single(v, O.TIFF, bd, strategy, target, pad)
+            img = ctx.process_single(dn, S.TIFF, bd, strategy, target, pad)
+            got = img.gray if bd == S.U8 else img.gray16
+            assert got.shape == ref.shape
+            assert np.array_equal(got, ref), (strategy, bd, target, pad, int((got != ref).sum()))
+            assert (img.scale_x, img.scale_y, img.pad_left, img.pad_top) == (meta.scale_x, meta.scale_y, meta.pad_left, meta.pad_top)
+
+
+@pytest.mark.parametrize("strategy", range(7))
+@pytest.mark.parametrize("tamed_step", [True, False])
+def test_pipeline_synrgb(ctx, strategy, tamed_step):
+    vv = CASES["speckle"](900, 1400)
+    vh = CASES["speckle_vh"](900, 1400)
+    ref, meta = O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), strategy, 512, True,
+                                       tamed_band_step=tamed_step)
+    img = ctx.process_synrgb_jpeg(vv, vh, strategy, 512, True, tamed_band_step=tamed_step)
+    assert img.rgb.shape == ref.shape
+    assert np.array_equal(img.rgb, ref), int((img.rgb != ref).sum())
+
+
+@pytest.mark.parametrize("bit_depth", [S.U8, S.U16])
+def test_pipeline_multiband_tiff(ctx, bit_depth):
+    vv = CASES["speckle"](640, 1000)
+    vh = CASES["speckle_vh"](640, 1000)
+    r1, r2, meta = O.pipeline_multiband_tiff(vv.astype(np.float32), vh.astype(np.float32), bit_depth, S.CLAHE, 400, True)
+    img = ctx.process_multiband_tiff(vv, vh, bit_depth, S.CLAHE, 400, True)
+    g1, g2 = (img.gray, img.gray_band2) if bit_depth == S.U8 else (img.gray16, img.gray16_band2)
+    assert np.array_equal(g1, r1) and np.array_equal(g2, r2)
+
+
+@pytest.mark.parametrize("shape,target", [((480, 640), 200), ((640, 480), 200), ((333, 1000), 333), ((100, 90), 500),
+                                          ((1000, 1000), 128), ((50, 2000), 64)])
+@pytest.mark.parametrize("bit_depth", [S.U8, S.U16])
+@pytest.mark.parametrize("pad", [False, True])
+def test_resize_image_data_with_meta(ctx, shape, target, bit_depth, pad):
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256 if bit_depth == S.U8 else 65536, shape).astype(np.uint8 if bit_depth == S.U8 else np.uint16)
+    ref, mo = O.resize_image_data_with_meta(data, target, bit_depth, pad)
+    got, mg = ctx.resize_image_data_with_meta(data, target, bit_depth, pad)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref), int((got != ref).sum())
+    for f in ("cols", "rows", "scale_x", "scale_y", "pad_left", "pad_top"):
+        assert getattr(mg, f) == getattr(mo, f)
+
+
+def test_u16_required_error(ctx):
+    with pytest.raises(S.SarproError) as e:
+        ctx.resize_image_data_with_meta(None, 100, S.U16, False)
+    assert "U16 data required for U16 bit depth" in str(e.value)
+
+
+@pytest.mark.parametrize("strategy", [S.STANDARD, S.CLAHE, S.TAMED])
+def test_synthetic_rgb(ctx, strategy):
+    rng = np.random.default_rng(7)
+    b1 = rng.integers(0, 256, (300, 411)).astype(np.uint8)
+    b2 = rng.integers(0, 256, (300, 411)).astype(np.uint8)
+    b1[:40] = 0
+    b2[:35] = 0
+    b2[100:120] = 0
+    ref = O.create_synthetic_rgb_by_mode_and_strategy(0, strategy, b1, b2)
+    got = ctx.create_synthetic_rgb_by_mode_and_strategy(0, strategy, b1, b2)
+    assert np.array_equal(got, ref)
+
+
+def test_pol_ops_and_small_stages(ctx):
+    rng = np.random.default_rng(9)
+    a = rng.gamma(2.0, 100.0, (211, 307)).astype(np.float32)
+    b = rng.gamma(2.0, 40.0, (211, 307)).astype(np.float32)
+    b[0, :10] = 0
+    a[1, :10] = -b[1, :10]
+    for op, fn in ((O.OP_SUM, ctx.sum_arrays), (O.OP_DIFF, ctx.difference_arrays), (O.OP_RATIO, ctx.ratio_arrays),
+                   (O.OP_NDIFF, ctx.normalized_diff_arrays), (O.OP_LOGRATIO, ctx.log_ratio_arrays)):
+        assert np.array_equal(fn(a, b), O.pol_op(op, a, b))
+    d16 = rng.integers(3, 200, (100, 33)).astype(np.uint16)
+    assert np.array_equal(ctx.scale_u16_to_u8(d16), O.scale_u16_to_u8(d16))
+    assert np.array_equal(ctx.add_padding_to_square(d16, S.U16), O.add_padding_to_square(d16, O.U16))
+    db, mask = ctx.process_scalar_data_inplace(a)
+    dbo, masko = O.process_scalar_data_inplace(a)
+    assert np.array_equal(mask, masko)
+    assert np.allclose(db, dbo, rtol=1e-12, atol=0)  # contract: 1e-5 relative
