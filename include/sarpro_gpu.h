@@ -114,7 +114,21 @@ typedef struct sarpro_timing {
     uint32_t kernel_launches;
     uint32_t host_syncs; /* planner round trips */
     uint64_t h2d_bytes, d2h_bytes;
+    /* per-stage device time of the last call (CUDA events around the launches, summed over bands) */
+    float stage_ms[8];        /* indexed by sarpro_stage */
+    uint32_t stage_launches[8];
 } sarpro_timing;
+
+typedef enum sarpro_stage {
+    SARPRO_STAGE_HIST = 0,     /* pass A: DN / value histograms */
+    SARPRO_STAGE_PLAN = 1,     /* histogram totals, CLAHE tile statistics, table uploads */
+    SARPRO_STAGE_APPLY = 2,    /* pass B: LUT / CLAHE apply (+ fused horizontal Lanczos) */
+    SARPRO_STAGE_VRESIZE = 3,  /* vertical Lanczos */
+    SARPRO_STAGE_RGB = 4,      /* synthetic RGB composition */
+    SARPRO_STAGE_CONVERT = 5,  /* f32 -> DN bridge, polarization ops */
+    SARPRO_STAGE_COMM = 6,     /* collectives */
+    SARPRO_STAGE_OTHER = 7
+} sarpro_stage;
 
 typedef struct sarpro_ctx sarpro_ctx;
 

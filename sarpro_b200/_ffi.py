@@ -69,7 +69,11 @@ class Timing(C.Structure):
         ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("kernel_ms", C.c_float),
         ("kernel_launches", C.c_uint32), ("host_syncs", C.c_uint32),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("stage_ms", C.c_float * 8), ("stage_launches", C.c_uint32 * 8),
     ]
+
+
+STAGE_NAMES = ["hist", "plan", "apply", "vresize", "rgb", "convert", "comm", "other"]
 
 
 # every symbol include/sarpro_gpu.h declares: name -> (restype, argtypes)

@@ -281,9 +281,9 @@ int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
         const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0u};
         std::memcpy(ctx->h_scalars + 8 * b, init, sizeof(init));
         CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-        KL(launch_dn_hist(jobs[b].dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
+        KS(SARPRO_STAGE_HIST, launch_dn_hist(jobs[b].dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
                           ctx->sm_count, ctx->hist_variant, ctx->stream));
-        KL(launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
+        KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
                              (uint32_t*)w.scalars.p + 2, ctx->stream));
         CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -308,9 +308,9 @@ int run_clahe_stats(sarpro_ctx* ctx, int b) {
     RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
     RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
     CU(cudaMemsetAsync(w.tile256.p, 0, (size_t)ctx->n_tiles * 256 * 4, ctx->stream));
-    KL(launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles, w.plan.max_present_dn,
+    KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles, w.plan.max_present_dn,
                             (uint32_t*)w.tile256.p, ctx->stream));
-    KL(launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles, (double*)w.cdf.p,
+    KS(SARPRO_STAGE_PLAN, launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles, (double*)w.cdf.p,
                         (float*)w.cdf32.p, ctx->stream));
     return 0;
 }
@@ -351,12 +351,12 @@ int run_pass_b_full(sarpro_ctx* ctx, int b, const BandJob& j, void* dst) {
         return 0;
     }
     if (!uses_clahe(j)) {
-        KL(launch_apply_lut(j.dn, n, (const uint16_t*)w.lut.p, out8 ? (uint8_t*)dst : nullptr,
+        KS(SARPRO_STAGE_APPLY, launch_apply_lut(j.dn, n, (const uint16_t*)w.lut.p, out8 ? (uint8_t*)dst : nullptr,
                             out8 ? nullptr : (uint16_t*)dst, ctx->sm_count, ctx->stream));
         return 0;
     }
     RC(run_clahe_stats(ctx, b));
-    KL(launch_apply_clahe(j.dn, (uint32_t)j.rows, (uint32_t)j.cols, (const uint16_t*)w.lut.p, clahe_dev(ctx, b),
+    KS(SARPRO_STAGE_APPLY, launch_apply_clahe(j.dn, (uint32_t)j.rows, (uint32_t)j.cols, (const uint16_t*)w.lut.p, clahe_dev(ctx, b),
                           out8 ? 255 : 65535, out8 ? (uint8_t*)dst : nullptr, out8 ? nullptr : (uint16_t*)dst,
                           (uint32_t*)w.scalars.p, ctx->sm_count, ctx->stream));
     if (out8) { // scale_u16_to_u8 over the blended samples (autoscale.rs:691-693)
@@ -364,7 +364,7 @@ int run_pass_b_full(sarpro_ctx* ctx, int b, const BandJob& j, void* dst) {
         RC(clahe_minmax(ctx, b, &mn, &mx));
         if (!(mn == 0 && mx == 255)) {
             RC(upload_remap(ctx, b, mn, mx));
-            KL(launch_remap_u8((uint8_t*)dst, n, (const uint8_t*)w.remap.p, ctx->sm_count, ctx->stream));
+            KS(SARPRO_STAGE_APPLY, launch_remap_u8((uint8_t*)dst, n, (const uint8_t*)w.remap.p, ctx->sm_count, ctx->stream));
         }
     }
     return 0;
@@ -399,10 +399,10 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     a.temp = w.temp.p;
     a.ax = ah->dev();
     auto run = [&]() -> int {
-        KL(launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw,
+        KS(SARPRO_STAGE_APPLY, launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw,
                                   ah->smem, ctx->sm_count, ctx->stream));
         unsigned char* dst = (unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz;
-        KL(launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream));
+        KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream));
         return 0;
     };
     RC(run());
@@ -456,7 +456,7 @@ int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band*
     RC(reserve(ctx, w.dn, n * 2));
     RC(reserve(ctx, w.scalars, 64));
     CU(cudaMemsetAsync((uint32_t*)w.scalars.p + 3, 0, 4, ctx->stream));
-    KL(launch_f32_to_dn(fa, fb, op, n, ctx->valid_thresh, (uint16_t*)w.dn.p, (uint32_t*)w.scalars.p + 3, ctx->sm_count,
+    KS(SARPRO_STAGE_CONVERT, launch_f32_to_dn(fa, fb, op, n, ctx->valid_thresh, (uint16_t*)w.dn.p, (uint32_t*)w.scalars.p + 3, ctx->sm_count,
                         ctx->stream));
     CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b + 3, (uint32_t*)w.scalars.p + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -480,6 +480,7 @@ int begin_call(sarpro_ctx* ctx) {
     ctx->err.clear();
     CU(cudaSetDevice(ctx->device));
     std::memset(&ctx->timing, 0, sizeof(ctx->timing));
+    ctx->n_sev = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     return 0;
 }
@@ -489,6 +490,12 @@ int end_call(sarpro_ctx* ctx) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->timing.total_ms = ms;
+    for (int i = 0; i < ctx->n_sev; ++i) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, ctx->sev[2 * i], ctx->sev[2 * i + 1]));
+        ctx->timing.stage_ms[ctx->sev_stage[i]] += t;
+        ctx->timing.stage_launches[ctx->sev_stage[i]]++;
+    }
     return 0;
 }
 
@@ -640,6 +647,8 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (auto& ev : ctx->sev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMallocHost((void**)&ctx->h_hist, 2 * kDnBins * 4)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_lut, 2 * kDnBins * 2)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_scalars, 2 * 8 * 4)) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -678,6 +687,8 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_remap) cudaFreeHost(ctx->h_remap);
     for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->sev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -794,12 +805,12 @@ int sarpro_pipeline_synrgb(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_
             RC(reserve(ctx, ctx->hist256, 256 * 4));
             RC(reserve(ctx, ctx->rgbsel, 16));
             CU(cudaMemsetAsync(ctx->hist256.p, 0, 256 * 4, ctx->stream));
-            KL(launch_hist256_pair((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (uint32_t*)ctx->hist256.p, ctx->stream));
-            KL(launch_synrgb_floor((const uint32_t*)ctx->hist256.p, n, (uint32_t*)ctx->rgbsel.p, ctx->stream));
-            KL(launch_synrgb((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (const uint8_t*)ctx->rgb_luts.p,
+            KS(SARPRO_STAGE_RGB, launch_hist256_pair((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (uint32_t*)ctx->hist256.p, ctx->stream));
+            KS(SARPRO_STAGE_RGB, launch_synrgb_floor((const uint32_t*)ctx->hist256.p, n, (uint32_t*)ctx->rgbsel.p, ctx->stream));
+            KS(SARPRO_STAGE_RGB, launch_synrgb((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (const uint8_t*)ctx->rgb_luts.p,
                              (const uint32_t*)ctx->rgbsel.p, 0, 1, (uint8_t*)ctx->rgb.p, ctx->stream));
         } else {
-            KL(launch_synrgb((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (const uint8_t*)ctx->rgb_luts.p, nullptr,
+            KS(SARPRO_STAGE_RGB, launch_synrgb((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (const uint8_t*)ctx->rgb_luts.p, nullptr,
                              kSynRgbDefaultSet, 0, (uint8_t*)ctx->rgb.p, ctx->stream));
         }
     }
@@ -873,7 +884,7 @@ int sarpro_pol_op(sarpro_ctx* ctx, int op, const float* a, const float* b, size_
     RC(reserve(ctx, w.full, n * 4));
     CU(cudaMemcpyAsync(w.f32a.p, a, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(w.f32b.p, b, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    KL(launch_pol_op((const float*)w.f32a.p, (const float*)w.f32b.p, op, n, (float*)w.full.p, ctx->sm_count, ctx->stream));
+    KS(SARPRO_STAGE_CONVERT, launch_pol_op((const float*)w.f32a.p, (const float*)w.f32b.p, op, n, (float*)w.full.p, ctx->sm_count, ctx->stream));
     CU(cudaMemcpyAsync(out, w.full.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     return end_call(ctx);
 }
@@ -938,9 +949,9 @@ int sarpro_resize_image_data_with_meta(sarpro_ctx* ctx, const uint8_t* u8_data, 
         a.n_rows = (uint32_t)rows;
         a.temp = w.temp.p;
         a.ax = ah->dev();
-        KL(launch_hresize_planned(a, HSRC_IMAGE, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem,
+        KS(SARPRO_STAGE_APPLY, launch_hresize_planned(a, HSRC_IMAGE, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem,
                                   ctx->sm_count, ctx->stream));
-        KL(launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, region, (uint32_t)g.oc, 0, pix16, ctx->stream));
+        KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, region, (uint32_t)g.oc, 0, pix16, ctx->stream));
     }
     CU(cudaMemcpyAsync(dst, w.small.p, n_out * esz, cudaMemcpyDeviceToHost, ctx->stream));
     return end_call(ctx);
@@ -963,11 +974,11 @@ int sarpro_create_synthetic_rgb_by_mode_and_strategy(sarpro_ctx* ctx, int mode, 
         RC(reserve(ctx, ctx->hist256, 256 * 4));
         RC(reserve(ctx, ctx->rgbsel, 16));
         CU(cudaMemsetAsync(ctx->hist256.p, 0, 256 * 4, ctx->stream));
-        KL(launch_hist256_pair(d1, d2, n, (uint32_t*)ctx->hist256.p, ctx->stream));
-        KL(launch_synrgb_floor((const uint32_t*)ctx->hist256.p, n, (uint32_t*)ctx->rgbsel.p, ctx->stream));
-        KL(launch_synrgb(d1, d2, n, (const uint8_t*)ctx->rgb_luts.p, (const uint32_t*)ctx->rgbsel.p, 0, 1, (uint8_t*)ctx->rgb.p, ctx->stream));
+        KS(SARPRO_STAGE_RGB, launch_hist256_pair(d1, d2, n, (uint32_t*)ctx->hist256.p, ctx->stream));
+        KS(SARPRO_STAGE_RGB, launch_synrgb_floor((const uint32_t*)ctx->hist256.p, n, (uint32_t*)ctx->rgbsel.p, ctx->stream));
+        KS(SARPRO_STAGE_RGB, launch_synrgb(d1, d2, n, (const uint8_t*)ctx->rgb_luts.p, (const uint32_t*)ctx->rgbsel.p, 0, 1, (uint8_t*)ctx->rgb.p, ctx->stream));
     } else {
-        KL(launch_synrgb(d1, d2, n, (const uint8_t*)ctx->rgb_luts.p, nullptr, kSynRgbDefaultSet, 0, (uint8_t*)ctx->rgb.p, ctx->stream));
+        KS(SARPRO_STAGE_RGB, launch_synrgb(d1, d2, n, (const uint8_t*)ctx->rgb_luts.p, nullptr, kSynRgbDefaultSet, 0, (uint8_t*)ctx->rgb.p, ctx->stream));
     }
     CU(cudaMemcpyAsync(rgb, ctx->rgb.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
     return end_call(ctx);

@@ -94,6 +94,11 @@ struct sarpro_ctx {
     // timing
     cudaEvent_t ev[6] = {};
     sarpro_timing timing{};
+    // per-stage event pairs recorded during a call, resolved in end_call
+    static constexpr int kMaxStageEvents = 64;
+    cudaEvent_t sev[2 * kMaxStageEvents] = {};
+    int sev_stage[kMaxStageEvents] = {};
+    int n_sev = 0;
     int hist_variant = 0;
     float valid_thresh = 0.f;
     sarpro::CommState* comm = nullptr;
@@ -120,6 +125,18 @@ int end_call(sarpro_ctx* ctx);
     do {                               \
         CU(call);                      \
         ctx->timing.kernel_launches++; \
+    } while (0)
+// stage-timed kernel launch: CUDA events around the launch, attributed to sarpro_stage S
+#define KS(S, call)                                                                  \
+    do {                                                                             \
+        const int si__ = ctx->n_sev < sarpro_ctx::kMaxStageEvents ? ctx->n_sev : -1; \
+        if (si__ >= 0) CU(cudaEventRecord(ctx->sev[2 * si__], ctx->stream));         \
+        KL(call);                                                                    \
+        if (si__ >= 0) {                                                             \
+            CU(cudaEventRecord(ctx->sev[2 * si__ + 1], ctx->stream));                \
+            ctx->sev_stage[si__] = (S);                                              \
+            ctx->n_sev++;                                                            \
+        }                                                                            \
     } while (0)
 #define RC(call)               \
     do {                       \

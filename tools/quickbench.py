@@ -25,7 +25,7 @@ for variant in os.environ.get("VARIANTS", "0,1,2,3,4,5,6").split(","):
     for strat, name in ((S.ROBUST, "robust"), (S.CLAHE, "clahe")):
         out = torch.empty((2048, 2048, 3), dtype=torch.uint8, device=dev)
         times = []
-        for it in range(4):
+        for it in range(int(os.environ.get("ITERS", 4))):
             ctx.process_synrgb_jpeg(vv, vh, strat, 2048, True, out=out)
             t = ctx.timing()
             times.append(t.total_ms)
