@@ -7,6 +7,7 @@ from sarpro_b200.synth import synth_band
 
 
 def speckle(rows, cols, seed, **kw):
+    kw.setdefault("block", 16)  # small rasters still get every terrain class
     return synth_band(rows, cols, seed, **kw)
 
 
@@ -26,7 +27,7 @@ def homogeneous(rows, cols, seed):
 
 def high_dynamic(rows, cols, seed):
     """range > 40 dB and IQR >= 5 -> Standard branch 3 (gamma 0.9)."""
-    dn = synth_band(rows, cols, seed, point_targets=1e-3)
+    dn = synth_band(rows, cols, seed, point_targets=1e-3, block=16)
     dn[1, 50:60] = 1
     return dn
 
@@ -40,12 +41,14 @@ def all_zero(rows, cols):
 
 
 def skewed(rows, cols, seed, positive=True):
-    """|skew| > 0.5 for the Adaptive branches."""
+    """Two-level raster: 70 % of the pixels near one level, 30 % near another 30 dB away, so that
+    (mean - median) / std = +-0.65 -> the skewed Adaptive branches (autoscale.rs:506-512)."""
     rng = np.random.default_rng(seed)
-    base = rng.gamma(1.2, 1.0, (rows, cols))
-    db = (base * 6.0) if positive else (40.0 - base * 6.0)
-    dn = np.clip(np.rint(10 ** (np.clip(db, 0, 90) / 10.0)), 1, 65535).astype(np.uint16)
-    return dn
+    minority = rng.random((rows, cols)) < 0.3
+    lo = rng.integers(9, 12, (rows, cols))
+    hi = rng.integers(9990, 10011, (rows, cols))
+    dn = np.where(minority, hi, lo) if positive else np.where(minority, lo, hi)
+    return dn.astype(np.uint16)
 
 
 def heavy_tail(rows, cols, seed):
@@ -73,7 +76,7 @@ CASES = {
     "speckle_vh": lambda r, c: speckle(r, c, 12, cross_pol=True),
     "low_contrast": lambda r, c: low_contrast(r, c, 13),
     "homogeneous": lambda r, c: homogeneous(r, c, 14),
-    "high_dynamic": lambda r, c: high_dynamic(r, c, 15),
+    "high_dynamic": lambda r, c: high_dynamic(r, c, 11),
     "all_equal": lambda r, c: all_equal(r, c),
     "all_zero": lambda r, c: all_zero(r, c),
     "skew_pos": lambda r, c: skewed(r, c, 16, True),
