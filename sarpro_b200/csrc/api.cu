@@ -152,10 +152,14 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
         RC(reserve(ctx, ctx->row_dy, rows * 8));
         RC(reserve(ctx, ctx->row_omdy, rows * 8));
         RC(reserve(ctx, ctx->row_t, rows * 2));
+        RC(reserve(ctx, ctx->col_m, cols * 4));
+        RC(reserve(ctx, ctx->row_sat, rows * 2));
+        ctx->clahe_tile_w = g.tile_w;
+        ctx->clahe_tile_h = g.tile_h;
         KL(launch_clahe_axis((uint32_t)cols, 0, (uint32_t)g.tile_w, kClaheTiles, (double*)ctx->col_dx.p,
-                             (double*)ctx->col_omdx.p, (uint16_t*)ctx->col_t.p, ctx->stream));
+                             (double*)ctx->col_omdx.p, (uint16_t*)ctx->col_t.p, (int32_t*)ctx->col_m.p, nullptr, ctx->stream));
         KL(launch_clahe_axis((uint32_t)rows, (uint32_t)row_off, (uint32_t)g.tile_h, kClaheTiles, (double*)ctx->row_dy.p,
-                             (double*)ctx->row_omdy.p, (uint16_t*)ctx->row_t.p, ctx->stream));
+                             (double*)ctx->row_omdy.p, (uint16_t*)ctx->row_t.p, nullptr, (uint16_t*)ctx->row_sat.p, ctx->stream));
     }
     return 0;
 }
@@ -170,6 +174,9 @@ ClaheDev clahe_dev(sarpro_ctx* ctx, int b) {
     cl.row_dy = (const double*)ctx->row_dy.p;
     cl.row_omdy = (const double*)ctx->row_omdy.p;
     cl.row_t = (const uint16_t*)ctx->row_t.p;
+    cl.col_m = (const int32_t*)ctx->col_m.p;
+    cl.row_sat = (const uint16_t*)ctx->row_sat.p;
+    cl.inv2tw = ctx->clahe_tile_w ? (float)(1.0 / (2.0 * (double)ctx->clahe_tile_w)) : 0.f;
     cl.tiles_x = kClaheTiles;
     return cl;
 }
@@ -188,7 +195,7 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
     if (ctx->axes.size() > 64) { // bounded cache
         for (auto& kv : ctx->axes) {
             release(kv.second->start); release(kv.second->size); release(kv.second->coef);
-            release(kv.second->packed); release(kv.second->strips);
+            release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips);
             delete kv.second;
         }
         ctx->axes.clear();
@@ -223,6 +230,13 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
             rc = upload_vec(ctx, ap->strips, strips.data(), strips.size() * sizeof(HStrip));
             ap->has_strips = true;
         }
+        if (!rc && !wide && hfast_supported(ap->pairs) &&
+            hfast_build_strips(h.start.data(), h.size.data(), out, in, h.window, &ap->f_oxb, &ap->f_strips_h,
+                               &ap->f_rbw_words) == cudaSuccess) {
+            ap->f_n_strips = (uint32_t)ap->f_strips_h.size();
+            rc = upload_vec(ctx, ap->fstrips, ap->f_strips_h.data(), ap->f_strips_h.size() * sizeof(HStrip));
+            ap->fast = rc == 0;
+        }
     }
     if (!rc) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream); // host vectors are temporaries
@@ -231,6 +245,57 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
     if (rc) { delete ap; return rc; }
     ctx->axes[key] = ap;
     *res = ap;
+    return 0;
+}
+
+// ---- horizontal pass dispatch -----------------------------------------------------------------------
+// Row blocks of the production kernel: <= rpb source rows each, never straddling a vertical CLAHE cell
+// boundary (rows where floor(r/tile_h - 0.5) changes, autoscale.rs:308-310).
+int prepare_rowblocks(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe, uint32_t n_strips) {
+    const uint64_t th = clahe ? ctx->clahe_tile_h : 0;
+    if (ctx->rb_rows == rows && ctx->rb_row_off == row_off && ctx->rb_clahe == (int)clahe && ctx->rb_tile_h == th &&
+        ctx->n_rowblocks)
+        return 0;
+    const uint64_t want_blocks = std::max<uint64_t>(1, (uint64_t)ctx->sm_count * 8 / std::max(1u, n_strips));
+    uint64_t rpb = (rows + want_blocks - 1) / want_blocks;
+    rpb = std::max<uint64_t>(16, ((rpb + 3) / 4) * 4);
+    std::vector<uint64_t> cuts;
+    cuts.push_back(0);
+    if (clahe && th)
+        for (uint64_t k = 0; k < kClaheTiles; ++k) {
+            const uint64_t g = (th * (2 * k + 1) + 1) / 2; // first global row with 2r >= th*(2k+1)
+            if (g > row_off && g < row_off + rows) cuts.push_back(g - row_off);
+        }
+    cuts.push_back(rows);
+    std::vector<uint2> blocks;
+    for (size_t i = 0; i + 1 < cuts.size(); ++i)
+        for (uint64_t r = cuts[i]; r < cuts[i + 1]; r += rpb)
+            blocks.push_back(make_uint2((uint32_t)r, (uint32_t)std::min(cuts[i + 1], r + rpb)));
+    RC(reserve(ctx, ctx->rowblocks, std::max<size_t>(blocks.size() * sizeof(uint2), 16)));
+    if (!blocks.empty()) {
+        CU(cudaMemcpyAsync(ctx->rowblocks.p, blocks.data(), blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->n_rowblocks = (uint32_t)blocks.size();
+    ctx->rb_rows = rows;
+    ctx->rb_row_off = row_off;
+    ctx->rb_clahe = clahe;
+    ctx->rb_tile_h = th;
+    return 0;
+}
+
+int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
+    if (!pix16 && ah->fast && !ctx->force_exact) {
+        const bool clahe = src_kind == HSRC_DN_CLAHE;
+        RC(prepare_rowblocks(ctx, a.n_rows, row_off, clahe, ah->f_n_strips));
+        HResizeArgs af = a;
+        af.rbw_words = ah->f_rbw_words;
+        KS(SARPRO_STAGE_APPLY, launch_hfast(af, src_kind, (const HStrip*)ah->fstrips.p, ah->f_n_strips, (const uint2*)ctx->rowblocks.p,
+                                            ctx->n_rowblocks, ah->f_oxb, ctx->stream));
+        return 0;
+    }
+    KS(SARPRO_STAGE_APPLY, launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw,
+                                                  ah->smem, ctx->sm_count, ctx->stream));
     return 0;
 }
 
@@ -399,8 +464,7 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     a.temp = w.temp.p;
     a.ax = ah->dev();
     auto run = [&]() -> int {
-        KS(SARPRO_STAGE_APPLY, launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw,
-                                  ah->smem, ctx->sm_count, ctx->stream));
+        RC(run_hpass(ctx, a, src_kind, pix16, ah, 0));
         unsigned char* dst = (unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz;
         KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream));
         return 0;
@@ -656,6 +720,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     ctx->valid_thresh = compute_valid_thresh();
     dn_db_table();
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
+    if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     int rc = upload_rgb_luts(ctx);
     if (rc) {
         g_create_error = ctx->err;
@@ -675,11 +740,12 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
                           &w.temp, &w.small, &w.full, &w.scalars})
             release(*b);
     for (DevBuf* b : {&ctx->units, &ctx->tile_px, &ctx->col_dx, &ctx->col_omdx, &ctx->col_t, &ctx->row_dy, &ctx->row_omdy,
-                      &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts})
+                      &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts, &ctx->col_m, &ctx->row_sat,
+                      &ctx->rowblocks})
         release(*b);
     for (auto& kv : ctx->axes) {
         release(kv.second->start); release(kv.second->size); release(kv.second->coef);
-        release(kv.second->packed); release(kv.second->strips);
+        release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips);
         delete kv.second;
     }
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
@@ -949,8 +1015,7 @@ int sarpro_resize_image_data_with_meta(sarpro_ctx* ctx, const uint8_t* u8_data, 
         a.n_rows = (uint32_t)rows;
         a.temp = w.temp.p;
         a.ax = ah->dev();
-        KS(SARPRO_STAGE_APPLY, launch_hresize_planned(a, HSRC_IMAGE, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem,
-                                  ctx->sm_count, ctx->stream));
+        RC(run_hpass(ctx, a, HSRC_IMAGE, pix16, ah, 0));
         KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, region, (uint32_t)g.oc, 0, pix16, ctx->stream));
     }
     CU(cudaMemcpyAsync(dst, w.small.p, n_out * esz, cudaMemcpyDeviceToHost, ctx->stream));

@@ -21,9 +21,13 @@ struct DevBuf {
 
 struct AxisPlan {
     ResampleAxis h; // host copy
-    DevBuf start, size, coef, packed, strips;
+    DevBuf start, size, coef, packed, strips, fstrips;
     uint32_t pairs = 0, oxb = 0, rbw = 0, smem = 0, n_strips = 0;
     bool has_strips = false;
+    // production u8 kernel (kernels_hfast.cu)
+    bool fast = false;
+    uint32_t f_oxb = 0, f_rbw_words = 0, f_n_strips = 0;
+    std::vector<HStrip> f_strips_h;
     AxisDev dev() const {
         AxisDev d;
         d.start = (const uint32_t*)start.p;
@@ -81,6 +85,13 @@ struct sarpro_ctx {
     std::string err;
     sarpro::BandWs band[2];
     sarpro::DevBuf units, tile_px, col_dx, col_omdx, col_t, row_dy, row_omdy, row_t, rgb, hist256, rgbsel, rgb_luts;
+    sarpro::DevBuf col_m, row_sat, rowblocks;
+    uint64_t clahe_tile_w = 0, clahe_tile_h = 0;
+    // row-block cache of the horizontal pass
+    uint64_t rb_rows = 0, rb_row_off = 0, rb_tile_h = 0;
+    int rb_clahe = -1;
+    uint32_t n_rowblocks = 0;
+    int force_exact = 0; // SARPRO_FORCE_EXACT=1: generic kernels + exact f64 CLAHE everywhere (validation)
     // geometry caches
     uint64_t units_rows = 0, units_cols = 0, units_scene_rows = 0, units_row_off = 0;
     int units_clahe = -1;

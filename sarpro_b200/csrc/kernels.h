@@ -32,8 +32,10 @@ cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut,
 cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, uint32_t n_tiles, double* cdf,
                              float* cdf32, cudaStream_t stream);
 // per-row / per-column bilinear geometry (autoscale.rs:308-318): t01 = t0 | t1 << 8
+// t01 bit 7 is set when fl(omd + d) == 1.0; m = 2*g - tile*(2*t+1) (so d == m / (2*tile) exactly);
+// sat = trunc(clamp(fl(omd + d), 0, 1) * 255): the sample of a pixel whose four CDF values are exactly 1.0.
 cudaError_t launch_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles, double* d,
-                              double* omd, uint16_t* t01, cudaStream_t stream);
+                              double* omd, uint16_t* t01, int32_t* m, uint16_t* sat, cudaStream_t stream);
 
 struct ClaheDev {
     const double* cdf;      // [64][256]
@@ -44,6 +46,9 @@ struct ClaheDev {
     const double* row_dy;   // [local rows]
     const double* row_omdy;
     const uint16_t* row_t;
+    const int32_t* col_m;    // [cols]  2c - tile_w*(2tx+1)
+    const uint16_t* row_sat; // [local rows]
+    float inv2tw;            // 1 / (2*tile_w)
     int tiles_x;
 };
 
@@ -88,6 +93,7 @@ struct HResizeArgs {
     // rows to produce: temp row i <- source row (row0 + i), i < n_rows
     uint32_t row0, n_rows;
     void* temp;            // [n_rows][out_cols] same pixel type
+    uint32_t rbw_words;    // production kernel: shared row-buffer slots (16 B each)
     AxisDev ax;
 };
 // One CTA of the horizontal pass owns a strip of output columns; the strip's source span is staged per row.
@@ -107,6 +113,13 @@ cudaError_t hresize_build_strips(const uint32_t* start_h, const uint32_t* size_h
 cudaError_t launch_hresize_planned(const HResizeArgs& a, int src_kind, int pix16, const HStrip* strips_dev,
                                    uint32_t n_strips, uint32_t oxb, uint32_t rbw, uint32_t smem, int sm_count,
                                    cudaStream_t stream);
+// Production horizontal pass for u8 samples (kernels_hfast.cu): taps in registers, row-interleaved shared
+// staging, next-group prefetch, fp32 CLAHE fast path with exact fix-up. rowblocks: (first,last+1) source rows.
+bool hfast_supported(uint32_t pairs);
+cudaError_t hfast_build_strips(const uint32_t* start_h, const uint32_t* size_h, uint32_t out_size, uint32_t in_size,
+                               uint32_t window, uint32_t* strip_w_out, std::vector<HStrip>* strips, uint32_t* rbw_words);
+cudaError_t launch_hfast(const HResizeArgs& a, int src_kind, const HStrip* strips_dev, uint32_t n_strips,
+                         const uint2* rowblocks_dev, uint32_t n_rowblocks, uint32_t strip_w, cudaStream_t stream);
 // vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
                            void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream);

@@ -220,23 +220,32 @@ cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, u
 
 // autoscale.rs:308-318 for one axis: f = g/tile - 0.5; t = max(floor(f),0); d = f - t; neighbours clamped.
 __global__ void k_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles,
-                             double* __restrict__ d, double* __restrict__ omd, uint16_t* __restrict__ t01) {
+                             double* __restrict__ d, double* __restrict__ omd, uint16_t* __restrict__ t01,
+                             int32_t* __restrict__ m, uint16_t* __restrict__ sat) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double f = __dsub_rn(__ddiv_rn((double)(global_offset + i), (double)tile_size), 0.5);
+    const uint32_t g = global_offset + i;
+    const double f = __dsub_rn(__ddiv_rn((double)g, (double)tile_size), 0.5);
     const long long t = (long long)fmax(floor(f), 0.0);
     const double dd = __dsub_rn(f, (double)t);
+    const double om = __dsub_rn(1.0, dd);
     const long long hi = (long long)n_tiles - 1;
     const long long t0 = t < 0 ? 0 : (t > hi ? hi : t);
     const long long t1 = (t + 1) < 0 ? 0 : ((t + 1) > hi ? hi : (t + 1));
+    const double one = __dadd_rn(om, dd); // value of c*(1-d) + c*d for c == 1.0
     d[i] = dd;
-    omd[i] = __dsub_rn(1.0, dd);
-    t01[i] = (uint16_t)(t0 | (t1 << 8));
+    omd[i] = om;
+    t01[i] = (uint16_t)(t0 | (t1 << 8) | (one == 1.0 ? 0x80 : 0));
+    if (m) m[i] = (int32_t)(2ll * (long long)g - (long long)tile_size * (2 * t + 1));
+    if (sat) {
+        const double c = one < 0.0 ? 0.0 : (one > 1.0 ? 1.0 : one);
+        sat[i] = (uint16_t)__dmul_rn(c, 255.0);
+    }
 }
 cudaError_t launch_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles, double* d,
-                              double* omd, uint16_t* t01, cudaStream_t stream) {
+                              double* omd, uint16_t* t01, int32_t* m, uint16_t* sat, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_clahe_axis<<<(n + 255) / 256, 256, 0, stream>>>(n, global_offset, tile_size, n_tiles, d, omd, t01);
+    k_clahe_axis<<<(n + 255) / 256, 256, 0, stream>>>(n, global_offset, tile_size, n_tiles, d, omd, t01, m, sat);
     return cudaGetLastError();
 }
 
@@ -320,8 +329,8 @@ __global__ void __launch_bounds__(256) k_apply_clahe(const uint16_t* __restrict_
         const uint32_t c0 = (uint32_t)(idx % vec_per_row) * 8;
         const double dy = cl.row_dy[r], omdy = cl.row_omdy[r];
         const uint32_t ty = cl.row_t[r];
-        const double* cdf_t0 = cl.cdf + (size_t)(ty & 255u) * cl.tiles_x * 256u;
-        const double* cdf_t1 = cl.cdf + (size_t)(ty >> 8) * cl.tiles_x * 256u;
+        const double* cdf_t0 = cl.cdf + (size_t)(ty & 7u) * cl.tiles_x * 256u;
+        const double* cdf_t1 = cl.cdf + (size_t)((ty >> 8) & 7u) * cl.tiles_x * 256u;
         const uint64_t base = (uint64_t)r * cols + c0;
 #pragma unroll 1
         for (uint32_t k = 0; k < 8 && c0 + k < cols; ++k) {
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(256) k_apply_clahe(const uint16_t* __restrict_
             if (d != 0) {
                 const uint32_t bin = lut[d] & 255u;
                 const uint32_t tx = cl.col_t[c];
-                const uint32_t x0 = (tx & 255u) * 256u + bin, x1 = (tx >> 8) * 256u + bin;
+                const uint32_t x0 = (tx & 7u) * 256u + bin, x1 = ((tx >> 8) & 7u) * 256u + bin;
                 const double v = clahe_blend_exact(cdf_t0[x0], cdf_t0[x1], cdf_t1[x0], cdf_t1[x1], cl.col_dx[c],
                                                    cl.col_omdx[c], dy, omdy);
                 o = clahe_quantize(v, max_val);

@@ -81,8 +81,8 @@ struct Loader {
             const ClaheDev& cl = a.clahe;
             const double dy = cl.row_dy[r], omdy = cl.row_omdy[r];
             const uint32_t ty = cl.row_t[r];
-            const double* cdf_t0 = cl.cdf + (size_t)(ty & 255u) * cl.tiles_x * 256u;
-            const double* cdf_t1 = cl.cdf + (size_t)(ty >> 8) * cl.tiles_x * 256u;
+            const double* cdf_t0 = cl.cdf + (size_t)(ty & 7u) * cl.tiles_x * 256u;
+            const double* cdf_t1 = cl.cdf + (size_t)((ty >> 8) & 7u) * cl.tiles_x * 256u;
             const double max_val = PIX16 ? 65535.0 : 255.0;
 #pragma unroll 1
             for (int k = 0; k < 8; ++k) {
@@ -92,7 +92,7 @@ struct Loader {
                     if (d[k] != 0) {
                         const uint32_t bin = look(d[k]) & 255u;
                         const uint32_t tx = cl.col_t[cc];
-                        const uint32_t x0 = (tx & 255u) * 256u + bin, x1 = (tx >> 8) * 256u + bin;
+                        const uint32_t x0 = (tx & 7u) * 256u + bin, x1 = ((tx >> 8) & 7u) * 256u + bin;
                         double bl = blend_exact(cdf_t0[x0], cdf_t0[x1], cdf_t1[x0], cdf_t1[x1], cl.col_dx[cc],
                                                 cl.col_omdx[cc], dy, omdy);
                         bl = bl < 0.0 ? 0.0 : (bl > 1.0 ? 1.0 : bl);
