@@ -104,9 +104,15 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
     std::vector<HistUnit> units;
     const uint64_t target_px = 192 * 1024;
     if (!clahe) {
-        uint64_t chunk = std::max<uint64_t>(1, target_px / std::max<uint64_t>(cols, 1));
-        for (uint64_t r = 0; r < rows; r += chunk)
-            units.push_back(HistUnit{(uint32_t)r, (uint32_t)std::min(rows, r + chunk), 0u, (uint32_t)cols, 0u, 0u});
+        // column strips of <= 4096 samples so that a unit spans >= 48 rows (one row per warp and iteration)
+        const uint64_t n_strips = std::max<uint64_t>(1, (cols + 4095) / 4096);
+        const uint64_t sw = (((cols + n_strips - 1) / n_strips) + 7) & ~uint64_t(7);
+        for (uint64_t c0 = 0; c0 < cols; c0 += sw) {
+            const uint64_t c1 = std::min(cols, c0 + sw);
+            const uint64_t chunk = std::max<uint64_t>(1, target_px / (c1 - c0));
+            for (uint64_t r = 0; r < rows; r += chunk)
+                units.push_back(HistUnit{(uint32_t)r, (uint32_t)std::min(rows, r + chunk), (uint32_t)c0, (uint32_t)c1, 0u, 0u});
+        }
         ctx->n_tiles = 1;
     } else {
         const ClaheGeom g = clahe_geometry(scene_rows, cols);
@@ -300,13 +306,6 @@ int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, Ax
 }
 
 // ---- one band through the device passes -----------------------------------------------------------
-struct BandJob {
-    const uint16_t* dn = nullptr; // device
-    uint64_t rows = 0, cols = 0;
-    int strategy = 0, bit_depth = 0;
-    PlanKind kind = PlanKind::Autoscale;
-};
-
 OutGeom out_geometry(size_t cols, size_t rows, bool has_target, size_t target, bool pad) {
     OutGeom g;
     resize_output_dims(cols, rows, has_target, target, pad, &g.rc, &g.rr, &g.oc, &g.orr);
@@ -323,34 +322,41 @@ OutGeom out_geometry(size_t cols, size_t rows, bool has_target, size_t target, b
     return g;
 }
 
-bool uses_clahe(const BandJob& j) { return j.kind == PlanKind::Autoscale && j.strategy == SARPRO_STRATEGY_CLAHE; }
+
+// Pass A launches for band slot b (no synchronisation): per-tile DN histogram + totals.
+int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units) {
+    if (ctx->units_rows != rows || ctx->units_cols != cols || ctx->units_clahe != (int)clahe_units ||
+        ctx->units_scene_rows != rows || ctx->units_row_off != 0) {
+        RC(prepare_units(ctx, rows, cols, clahe_units, rows, 0));
+        ctx->units_rows = rows;
+        ctx->units_cols = cols;
+        ctx->units_clahe = clahe_units;
+        ctx->units_scene_rows = rows;
+        ctx->units_row_off = 0;
+    }
+    BandWs& w = ctx->band[b];
+    RC(reserve(ctx, w.tile_hist, (size_t)ctx->n_tiles * kDnBins * 4));
+    RC(reserve(ctx, w.total, kDnBins * 4));
+    RC(reserve(ctx, w.lut, kDnBins * 2));
+    RC(reserve(ctx, w.scalars, 64));
+    CU(cudaMemsetAsync(w.tile_hist.p, 0, (size_t)ctx->n_tiles * kDnBins * 4, ctx->stream));
+    const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0u};
+    std::memcpy(ctx->h_scalars + 8 * b, init, sizeof(init));
+    CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
+                                         ctx->sm_count, ctx->hist_variant, ctx->stream));
+    KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
+                                            (uint32_t*)w.scalars.p + 2, ctx->stream));
+    return 0;
+}
 
 // Pass A for `nb` bands of identical geometry, then one planner round trip for all of them.
 int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
-    const uint64_t rows = jobs[0].rows, cols = jobs[0].cols;
     bool any_clahe = false;
     for (int b = 0; b < nb; ++b) any_clahe |= uses_clahe(jobs[b]);
-    if (ctx->units_rows != rows || ctx->units_cols != cols || ctx->units_clahe != (int)any_clahe) {
-        RC(prepare_units(ctx, rows, cols, any_clahe, rows, 0));
-        ctx->units_rows = rows;
-        ctx->units_cols = cols;
-        ctx->units_clahe = any_clahe;
-    }
     for (int b = 0; b < nb; ++b) {
-        BandWs& w = ctx->band[b];
-        RC(reserve(ctx, w.tile_hist, (size_t)ctx->n_tiles * kDnBins * 4));
-        RC(reserve(ctx, w.total, kDnBins * 4));
-        RC(reserve(ctx, w.lut, kDnBins * 2));
-        RC(reserve(ctx, w.scalars, 64));
-        CU(cudaMemsetAsync(w.tile_hist.p, 0, (size_t)ctx->n_tiles * kDnBins * 4, ctx->stream));
-        const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0u};
-        std::memcpy(ctx->h_scalars + 8 * b, init, sizeof(init));
-        CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-        KS(SARPRO_STAGE_HIST, launch_dn_hist(jobs[b].dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
-                          ctx->sm_count, ctx->hist_variant, ctx->stream));
-        KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
-                             (uint32_t*)w.scalars.p + 2, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        RC(dn_pass_a_launch(ctx, b, jobs[b].dn, jobs[b].rows, jobs[b].cols, any_clahe));
+        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, ctx->band[b].total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->timing.host_syncs++;
@@ -485,6 +491,36 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     return 0;
 }
 
+// Pass B for a planned band: full resolution, pad only, or fused with the Lanczos resize.
+int dn_run_pass_b(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& g, void* canvas) {
+    BandWs& w = ctx->band[b];
+    const bool out8 = j.kind != PlanKind::Autoscale || j.bit_depth == SARPRO_U8;
+    const size_t esz = out8 ? 1 : 2;
+    if (!g.resize && !g.pad) return run_pass_b_full(ctx, b, j, canvas);
+    if (!g.resize) { // pad only: full-res apply, then copy into the zeroed canvas
+        RC(reserve(ctx, w.full, j.rows * j.cols * esz));
+        RC(run_pass_b_full(ctx, b, j, w.full.p));
+        CU(cudaMemsetAsync(canvas, 0, g.oc * g.orr * esz, ctx->stream));
+        CU(cudaMemcpy2DAsync((unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz, g.oc * esz, w.full.p,
+                             j.cols * esz, j.cols * esz, j.rows, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    }
+    return run_pass_b_resized(ctx, b, j, g, canvas);
+}
+
+// A band whose DN -> sample table is already known (general f32 rasters bridged through a key plane).
+int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint16_t* lut_host, uint32_t max_key,
+                            const OutGeom& g, void* canvas) {
+    BandWs& w = ctx->band[b];
+    RC(dn_pass_a_launch(ctx, b, j.dn, j.rows, j.cols, uses_clahe(j)));
+    std::memcpy(ctx->h_lut + (size_t)b * kDnBins, lut_host, kDnBins * 2);
+    CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+    w.plan.any_valid = true;
+    w.plan.clahe = uses_clahe(j);
+    w.plan.max_present_dn = max_key;
+    return dn_run_pass_b(ctx, b, j, g, canvas);
+}
+
 // ---- inputs ----------------------------------------------------------------------------------------
 // Brings band `in` (optionally op(in, in2)) to a u16 DN raster on the device. Returns SARPRO_ERR_INTERNAL + flag
 // when the samples are not u16-valued (general f32 path).
@@ -588,12 +624,6 @@ void fill_image(sarpro_image* out, const OutGeom& g, int channels, int bit_depth
 
 } // namespace sarpro
 
-namespace sarpro {
-int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const float* b_dev, int op, uint64_t rows,
-                       uint64_t cols, int bit_depth, int strategy, PlanKind kind, bool has_target, size_t target,
-                       bool pad, void* canvas_dev, sarpro_stats* stats);
-}
-
 namespace {
 
 // Produces one processed band (autoscale [+resize+pad]) into a device canvas owned by the ctx.
@@ -652,22 +682,12 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
         if (!integral[b]) {
             const float* fa = ins[b]->location == SARPRO_LOC_HOST ? (const float*)w.f32a.p : (const float*)ins[b]->data;
             const float* fb = ops[b] >= 0 ? (ins2[b]->location == SARPRO_LOC_HOST ? (const float*)w.f32b.p : (const float*)ins2[b]->data) : nullptr;
-            RC(f32_general_single(ctx, b, fa, fb, ops[b], rows, cols, bit_depths[b], strategies[b], kinds[b], has_target,
-                                  target, pad, w.small.p, stats ? &stats[b] : nullptr));
+            RC(f32_general_single(ctx, b, fa, fb, ops[b], rows, cols, bit_depths[b], strategies[b], kinds[b], *geom, w.small.p,
+                                  stats ? &stats[b] : nullptr));
             continue;
         }
         if (stats) stats[b] = w.plan.stats;
-        if (!geom->resize && !geom->pad) {
-            RC(run_pass_b_full(ctx, b, jobs[b], w.small.p));
-        } else if (!geom->resize) { // pad only: full-res apply, then copy into the zeroed canvas
-            RC(reserve(ctx, w.full, rows * cols * esz));
-            RC(run_pass_b_full(ctx, b, jobs[b], w.full.p));
-            CU(cudaMemsetAsync(w.small.p, 0, n_out * esz, ctx->stream));
-            CU(cudaMemcpy2DAsync((unsigned char*)w.small.p + (geom->pad_top * geom->oc + geom->pad_left) * esz,
-                                 geom->oc * esz, w.full.p, cols * esz, cols * esz, rows, cudaMemcpyDeviceToDevice, ctx->stream));
-        } else {
-            RC(run_pass_b_resized(ctx, b, jobs[b], *geom, w.small.p));
-        }
+        RC(dn_run_pass_b(ctx, b, jobs[b], *geom, w.small.p));
     }
     return 0;
 }

@@ -75,6 +75,15 @@ OutGeom out_geometry(size_t cols, size_t rows, bool has_target, size_t target, b
 
 struct CommState; // comm.cu
 
+// One band through the DN passes
+struct BandJob {
+    const uint16_t* dn = nullptr; // device
+    uint64_t rows = 0, cols = 0;
+    int strategy = 0, bit_depth = 0;
+    PlanKind kind = PlanKind::Autoscale;
+};
+inline bool uses_clahe(const BandJob& j) { return j.kind == PlanKind::Autoscale && j.strategy == SARPRO_STRATEGY_CLAHE; }
+
 } // namespace sarpro
 
 struct sarpro_ctx {
@@ -122,6 +131,14 @@ int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes);
 void release(DevBuf& b);
 int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res);
 int begin_call(sarpro_ctx* ctx);
+int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off);
+int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units);
+int dn_run_pass_b(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& g, void* canvas);
+int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint16_t* lut_host, uint32_t max_key,
+                            const OutGeom& g, void* canvas);
+int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const float* b_dev, int op, uint64_t rows,
+                       uint64_t cols, int bit_depth, int strategy, PlanKind kind, const OutGeom& g, void* canvas_dev,
+                       sarpro_stats* stats);
 int end_call(sarpro_ctx* ctx);
 
 #define CU(call)                                                                                             \

@@ -145,23 +145,13 @@ cudaError_t launch_f32_to_dn(const float* a, const float* b, int op, uint64_t n,
                              uint32_t* flag, int sm_count, cudaStream_t stream);
 cudaError_t launch_pol_op(const float* a, const float* b, int op, uint64_t n, float* out, int sm_count,
                           cudaStream_t stream);
-// generic path: order-preserving key of every sample's f32 value -> min/max over valid samples.
-// valid <=> v >= valid_thresh (host-derived bit pattern of the smallest f32 with dB > -50)
+// general f32 path (kernels_f32.cu; launchers declared in api_f32.cu): min/max/count over valid samples.
+// valid <=> v >= valid_thresh (the smallest f32 with dB > -50); valid samples are positive, so the bit
+// pattern orders like the value.
 struct F32Scan {
-    uint32_t min_key, max_key; // ordered-uint keys of min / max valid value
+    uint32_t min_key, max_key; // bit patterns of the min / max valid sample
     unsigned long long valid_count;
 };
-cudaError_t launch_f32_scan(const float* a, const float* b, int op, uint64_t n, float valid_thresh, F32Scan* out,
-                            int sm_count, cudaStream_t stream);
-// 4096-bin histogram (autoscale.rs:108-117) by searching host-built f32 bin-edge thresholds:
-// idx(v) = number of edges e_k (k = 1..4095) with v >= e_k.
-cudaError_t launch_f32_hist4096(const float* a, const float* b, int op, uint64_t n, float valid_thresh,
-                                const float* edges4096, unsigned long long* hist4096, int sm_count,
-                                cudaStream_t stream);
-// quantisation by thresholds: out = number of level edges q_k (k = 1..n_levels-1) with v >= q_k; invalid -> 0.
-cudaError_t launch_f32_quantize(const float* a, const float* b, int op, uint64_t n, float valid_thresh,
-                                const float* level_edges, uint32_t n_levels, uint8_t* out_u8, uint16_t* out_u16,
-                                int sm_count, cudaStream_t stream);
 // dB plane + mask (pipeline.rs:8-40) for callers that want them (device log10; see DESIGN.md tolerance)
 cudaError_t launch_db_mask(const float* v, uint64_t n, double* db, uint8_t* mask, int sm_count, cudaStream_t stream);
 

@@ -68,7 +68,7 @@ __device__ __noinline__ uint32_t hf_clahe_exact_impl(const uint16_t* __restrict_
     hf_clahe_exact_impl((LUT), (CL).cdf, (CL).col_dx, (CL).col_omdx, (CL).col_t, (CL).row_dy, (CL).row_omdy, (CL).row_t, (R), (C), (D))
 
 template <int SRC, int MAXP>
-__global__ void __launch_bounds__(256) k_hfast(HResizeArgs a, const HStrip* __restrict__ strips,
+__global__ void __launch_bounds__(256, (SRC == HSRC_DN_CLAHE ? 2 : 3)) k_hfast(HResizeArgs a, const HStrip* __restrict__ strips,
                                                const uint2* __restrict__ rowblocks, uint32_t strip_w) {
     extern __shared__ uint4 smem4[];
     unsigned char* const smem = reinterpret_cast<unsigned char*>(smem4);
@@ -124,6 +124,19 @@ __global__ void __launch_bounds__(256) k_hfast(HResizeArgs a, const HStrip* __re
     const size_t row_pitch = (size_t)a.src_cols * esz;
     const unsigned char* const col_base = reinterpret_cast<const unsigned char*>(a.src) + (size_t)c0 * esz;
     uint32_t mn = 0xffffffffu, mx = 0;
+
+    // CLAHE: per-column bilinear geometry of my 8 columns, fixed for the whole kernel
+    float cdx[8];
+    uint32_t cpack = 0; // 4 bits per column: tile-pair slot (3 bits) | fl(omdx+dx)==1 flag
+    if (SRC == HSRC_DN_CLAHE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t cc = c0 + k < a.src_cols ? c0 + k : a.src_cols - 1;
+            const uint32_t ct = a.clahe.col_t[cc];
+            cdx[k] = __fmul_rn((float)a.clahe.col_m[cc], a.clahe.inv2tw);
+            cpack |= ((((ct & 7u) - p_lo) & 7u) | ((ct & 0x80u) ? 8u : 0u)) << (4 * k);
+        }
+    }
 
     uint4 q[kFRows]; // raw samples of the next group: 8 samples of my vector column per row
     auto prefetch = [&](uint32_t g) {
@@ -206,6 +219,7 @@ __global__ void __launch_bounds__(256) k_hfast(HResizeArgs a, const HStrip* __re
                 if (fast) {
                     float sdy[kFRows], somdy[kFRows];
                     uint32_t satv[kFRows];
+                    uint32_t needmask = 0; // bit rr*8+k: sample must be recomputed exactly
 #pragma unroll
                     for (int rr = 0; rr < kFRows; ++rr) {
                         sdy[rr] = __fmul_rn((float)cl.row_dy[g + rr], kScaleQ);
@@ -214,11 +228,10 @@ __global__ void __launch_bounds__(256) k_hfast(HResizeArgs a, const HStrip* __re
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const uint32_t ct = cl.col_t[c0 + k];
-                        const float dx = __fmul_rn((float)cl.col_m[c0 + k], cl.inv2tw);
+                        const float dx = cdx[k];
                         const float omdx = __fsub_rn(1.0f, dx);
-                        const uint32_t cbase = kOffQuad + ((ct & 7u) - p_lo) * 4096u;
-                        const bool col_one = (ct & 0x80u) != 0;
+                        const uint32_t cbase = kOffQuad + ((cpack >> (4 * k)) & 7u) * 4096u;
+                        const bool col_one = ((cpack >> (4 * k)) & 8u) != 0;
 #pragma unroll
                         for (int rr = 0; rr < kFRows; ++rr) {
                             const uint32_t wq = (k >> 1) == 0 ? q[rr].x : ((k >> 1) == 1 ? q[rr].y : ((k >> 1) == 2 ? q[rr].z : q[rr].w));
@@ -234,22 +247,36 @@ __global__ void __launch_bounds__(256) k_hfast(HResizeArgs a, const HStrip* __re
                             const bool valid = d != 0;
                             uint32_t o = sat ? satv[rr] : kq;
                             const bool need = valid && (sat ? !col_one : !accept);
-                            o = valid ? o : 0u;
-                            uint32_t omin = o;
-                            if (need) { // rare: queue for the exact path
-                                uint32_t* s_defer = reinterpret_cast<uint32_t*>(smem + kOffDefer);
-                                const uint32_t slot = atomicAdd(&s_defer[kDeferCap], 1u);
-                                if (slot < kDeferCap) {
-                                    s_defer[slot] = ((uint32_t)rr << 28) | (tid * 8 + k);
-                                    o = 0;      // placeholder byte, patched after the barrier
-                                    omin = 255; // neutral for the running min
-                                } else {
-                                    o = omin = hf_clahe_exact(a.lut, cl, g + rr, c0 + k, d); // queue full: resolve in place
-                                }
-                            }
+                            o = (valid && !need) ? o : 0u;      // queued samples: placeholder 0, patched after the barrier
+                            needmask |= need ? (1u << (rr * 8 + k)) : 0u;
                             mx = max(mx, o);
-                            mn = min(mn, omin);
+                            mn = min(mn, need ? 255u : o);      // a queued sample is neutral for the running min
                             if (k < 4) w0[rr] |= o << (8 * k); else w1[rr] |= o << (8 * (k - 4));
+                        }
+                    }
+                    if (needmask) { // rare: queue for the exact path
+                        uint32_t* s_defer = reinterpret_cast<uint32_t*>(smem + kOffDefer);
+                        while (needmask) {
+                            const uint32_t b = __ffs(needmask) - 1;
+                            needmask &= needmask - 1;
+                            const uint32_t slot = atomicAdd(&s_defer[kDeferCap], 1u);
+                            const uint32_t rr = b >> 3, k = b & 7u;
+                            if (slot < kDeferCap) {
+                                s_defer[slot] = (rr << 28) | (tid * 8 + k);
+                            } else { // queue full: resolve in place
+                                const uint32_t d = reinterpret_cast<const uint16_t*>(a.src)[(size_t)(g + rr) * a.src_cols + c0 + k];
+                                uint32_t o = hf_clahe_exact(a.lut, cl, g + rr, c0 + k, d);
+                                mn = min(mn, o);
+                                mx = max(mx, o);
+                                const uint32_t sh = 8 * (k & 3u);
+                                uint32_t word = k < 4 ? w0[0] : w1[0]; // select row rr without dynamic indexing
+                                if (rr == 1) word = k < 4 ? w0[1] : w1[1];
+                                if (rr == 2) word = k < 4 ? w0[2] : w1[2];
+                                if (rr == 3) word = k < 4 ? w0[3] : w1[3];
+                                word = (word & ~(0xffu << sh)) | (o << sh);
+                                if (k < 4) { if (rr == 0) w0[0] = word; if (rr == 1) w0[1] = word; if (rr == 2) w0[2] = word; if (rr == 3) w0[3] = word; }
+                                else { if (rr == 0) w1[0] = word; if (rr == 1) w1[1] = word; if (rr == 2) w1[2] = word; if (rr == 3) w1[3] = word; }
+                            }
                         }
                     }
                 } else {

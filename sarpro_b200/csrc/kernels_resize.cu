@@ -341,9 +341,57 @@ __global__ void __launch_bounds__(256) k_vresize(const void* __restrict__ temp, 
         reinterpret_cast<uint16_t*>(out)[(size_t)oy * out_pitch + out_x0 + x] = (uint16_t)v;
     }
 }
+// u8 vertical pass, 4 adjacent columns per thread: two source rows are byte-interleaved (PRMT) so that one
+// dp2a consumes (tap k, tap k+1) x (row k, row k+1) of a column.
+__global__ void __launch_bounds__(128) k_vresize8x4(const uint8_t* __restrict__ temp, uint32_t temp_row0, uint32_t width,
+                                                    AxisDev ax, uint32_t oy0, uint8_t* __restrict__ out, uint32_t out_pitch,
+                                                    uint32_t out_x0) {
+    extern __shared__ int s_pair[]; // packed (tap k | tap k+1 << 16)
+    const uint32_t oy = oy0 + blockIdx.y;
+    const uint32_t n = ax.size[oy], start = ax.start[oy];
+    const uint32_t np = (n + 1) / 2;
+    for (uint32_t k = threadIdx.x; k < np; k += blockDim.x) {
+        const int c0 = ax.coef[(size_t)oy * ax.window + 2 * k];
+        const int c1 = 2 * k + 1 < n ? ax.coef[(size_t)oy * ax.window + 2 * k + 1] : 0;
+        s_pair[k] = (int)(((uint32_t)c0 & 0xffffu) | ((uint32_t)c1 << 16));
+    }
+    __syncthreads();
+    const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= width) return;
+    const int prec = ax.precision;
+    const int init = prec > 0 ? (1 << (prec - 1)) : 0;
+    int a0 = init, a1 = init, a2 = init, a3 = init;
+    const uint8_t* t = temp + (size_t)(start - temp_row0) * width + x;
+    const uint32_t last = n - 1;
+    for (uint32_t k = 0; k < np; ++k) {
+        const uint32_t r0 = 2 * k, r1 = min(2 * k + 1, last); // odd tail: tap is 0, row index stays in range
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(t + (size_t)r0 * width);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(t + (size_t)r1 * width);
+        const uint32_t lo = __byte_perm(w0, w1, 0x5140); // c0r0 c0r1 c1r0 c1r1
+        const uint32_t hi = __byte_perm(w0, w1, 0x7362); // c2r0 c2r1 c3r0 c3r1
+        const int p = s_pair[k];
+        a0 = dp2a_lo_su(p, lo, a0);
+        a1 = dp2a_hi_su(p, lo, a1);
+        a2 = dp2a_lo_su(p, hi, a2);
+        a3 = dp2a_hi_su(p, hi, a3);
+    }
+    auto clip = [&](int a) { int v = a >> prec; return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
+    uint8_t* o = out + (size_t)oy * out_pitch + out_x0 + x;
+    const uint32_t packed = clip(a0) | (clip(a1) << 8) | (clip(a2) << 16) | (clip(a3) << 24);
+    if (x + 4 <= width && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = packed;
+    else
+        for (uint32_t j = 0; j < 4 && x + j < width; ++j) o[j] = (uint8_t)(packed >> (8 * j));
+}
+
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
                            void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream) {
     if (oy1 <= oy0 || width == 0) return cudaSuccess;
+    if (!pix16 && width % 4 == 0 && (reinterpret_cast<uintptr_t>(temp) & 3) == 0) {
+        const dim3 grid((width / 4 + 127) / 128, oy1 - oy0);
+        const size_t smem = (size_t)(ax.window + 1) / 2 * sizeof(int) + 16;
+        k_vresize8x4<<<grid, 128, smem, stream>>>((const uint8_t*)temp, temp_row0, width, ax, oy0, (uint8_t*)out, out_pitch, out_x0);
+        return cudaGetLastError();
+    }
     const dim3 grid((width + 255) / 256, oy1 - oy0);
     const size_t smem = (size_t)ax.window * sizeof(int);
     if (pix16) k_vresize<true><<<grid, 256, smem, stream>>>(temp, temp_row0, width, ax, oy0, out, out_pitch, out_x0);

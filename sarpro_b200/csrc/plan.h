@@ -97,3 +97,21 @@ void build_synrgb_suppressed_lut(int floor_with_cushion, SynRgbLut* lut); // syn
 int synrgb_floor_from_histogram(const uint32_t* hist256, uint64_t n_per_band);
 
 } // namespace sarpro
+
+// ---- general f32 rasters: thresholds (plan_f32.cpp) -------------------------------------------
+namespace sarpro {
+// dB of an f32 sample exactly as pipeline.rs:19-20 computes it
+double db_of_sample(float v);
+// smallest f32 with dB > -50 (pipeline.rs:22)
+float valid_threshold();
+// edges[k] (k = 1..4095) = smallest f32 v in [min_v, max_v] whose stat-histogram index (autoscale.rs:113-116)
+// is >= k; +inf when no sample value reaches k. edges has 4096 entries, edges[0] = 0.
+void build_stat_edges(float min_v, float max_v, std::vector<float>* edges);
+enum class LevelKind { Quantize, TamedLinearU8, ClaheBin };
+// edges[k] (k = 1..n_levels) = smallest valid f32 v in [min_v, max_v] whose level is >= k, where level is
+//   Quantize      : cast_u16(clamp(pow((clip(db)-low)/range, gamma) * max_val, 0, max_val))   autoscale.rs:440-442
+//   TamedLinearU8 : cast_u8(clamp(((clip(db)-low)/range) * 255, 0, 255))                      autoscale.rs:734-736
+//   ClaheBin      : round(clamp((clip(db)-low)/range, 0, 1) * 255)                            autoscale.rs:585-587, 263
+void build_level_edges(LevelKind kind, double low, double high, double gamma, uint32_t n_levels, float min_v, float max_v,
+                       std::vector<float>* edges, uint32_t* level_of_min, uint32_t* level_of_max);
+} // namespace sarpro

@@ -1,0 +1,143 @@
+// plan_f32.cpp — host thresholds for rasters that are not u16-valued (see kernels_f32.cu).
+// Every index the reference computes from a sample is monotone in the sample value; the boundaries are
+// located here by evaluating the reference's own f64 expression (same libm) on f32 bit patterns.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <thread>
+
+#include "plan.h"
+
+namespace sarpro {
+namespace {
+
+inline uint32_t bits_of(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float float_of(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+constexpr uint32_t kInfBits = 0x7f800000u;
+
+inline uint64_t cast_u64(double x) {
+    if (!(x == x) || x <= 0.0) return 0;
+    if (x >= 18446744073709551616.0) return UINT64_MAX;
+    return (uint64_t)x;
+}
+inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Smallest bit pattern b in [lo, hi] with level(b) >= k, given a monotone `level`; kInfBits if none.
+// `guess` is an analytic estimate; a gallop around it brackets the boundary in a handful of evaluations.
+template <typename F>
+uint32_t first_reaching(F&& level, uint32_t k, uint32_t lo, uint32_t hi, uint32_t guess) {
+    if (level(hi) < k) return kInfBits;
+    if (level(lo) >= k) return lo;
+    // invariant: level(lo) < k <= level(hi)
+    uint32_t g = std::min(std::max(guess, lo + 1), hi);
+    uint32_t step = 1;
+    if (level(g) >= k) {
+        hi = g;
+        while (hi - lo > 1) {
+            const uint32_t t = hi - lo > step ? hi - step : lo + 1;
+            if (t <= lo) break;
+            if (level(t) >= k) { hi = t; step *= 4; }
+            else { lo = t; break; }
+        }
+    } else {
+        lo = g;
+        while (hi - lo > 1) {
+            const uint32_t t = hi - lo > step ? lo + step : hi - 1;
+            if (t >= hi) break;
+            if (level(t) < k) { lo = t; step *= 4; }
+            else { hi = t; break; }
+        }
+    }
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (level(mid) >= k) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
+template <typename F>
+void parallel_for(uint32_t n, F&& f) {
+    const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (n < 2048 || nt == 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    const uint32_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const uint32_t a = t * chunk, b = std::min(n, a + chunk);
+        if (a < b) th.emplace_back([&, a, b] { f(a, b); });
+    }
+    for (auto& x : th) x.join();
+}
+
+} // namespace
+
+double db_of_sample(float v) { return 10.0 * std::log10(std::fmax((double)v, 1e-10)); }
+
+float valid_threshold() {
+    uint32_t lo = 0, hi = bits_of(1.0f);
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (db_of_sample(float_of(mid)) > -50.0) hi = mid; else lo = mid;
+    }
+    return float_of(hi);
+}
+
+void build_stat_edges(float min_v, float max_v, std::vector<float>* edges) {
+    edges->assign(kStatBins, 0.0f);
+    const double min_db = db_of_sample(min_v), max_db = db_of_sample(max_v);
+    const double span = max_db - min_db;
+    const double inv_span = 1.0 / span;
+    auto level = [&](uint32_t b) -> uint32_t {
+        const double t = clampd((db_of_sample(float_of(b)) - min_db) * inv_span, 0.0, 1.0);
+        uint64_t idx = cast_u64(t * (double)kStatBins);
+        if (idx >= (uint64_t)kStatBins) idx = kStatBins - 1;
+        return (uint32_t)idx;
+    };
+    const uint32_t lo = bits_of(min_v), hi = bits_of(max_v);
+    parallel_for(kStatBins - 1, [&](uint32_t a, uint32_t b) {
+        for (uint32_t i = a; i < b; ++i) {
+            const uint32_t k = i + 1;
+            const double db = min_db + span * ((double)k / (double)kStatBins);
+            const uint32_t guess = bits_of((float)std::pow(10.0, db / 10.0));
+            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, guess));
+        }
+    });
+}
+
+void build_level_edges(LevelKind kind, double low, double high, double gamma, uint32_t n_levels, float min_v, float max_v,
+                       std::vector<float>* edges, uint32_t* level_of_min, uint32_t* level_of_max) {
+    edges->assign((size_t)n_levels + 1, 0.0f);
+    const double range = std::fmax(high - low, 1.0);
+    const double max_val = (double)n_levels;
+    auto level = [&](uint32_t b) -> uint32_t {
+        const double db = db_of_sample(float_of(b));
+        const double clipped = std::fmin(std::fmax(db, low), high);
+        const double n = (clipped - low) / range;
+        double q;
+        if (kind == LevelKind::Quantize) q = clampd(std::pow(n, gamma) * max_val, 0.0, max_val);
+        else if (kind == LevelKind::TamedLinearU8) q = clampd(n * 255.0, 0.0, 255.0);
+        else {
+            q = std::round(clampd(n, 0.0, 1.0) * 255.0);
+            if (!(q == q)) q = 0.0;
+            q = clampd(q, 0.0, 255.0);
+        }
+        if (!(q == q) || q <= 0.0) return 0;
+        return q >= max_val ? n_levels : (uint32_t)q;
+    };
+    const uint32_t lo = bits_of(min_v), hi = bits_of(max_v);
+    if (level_of_min) *level_of_min = level(lo);
+    if (level_of_max) *level_of_max = level(hi);
+    parallel_for(n_levels, [&](uint32_t a, uint32_t b) {
+        for (uint32_t i = a; i < b; ++i) {
+            const uint32_t k = i + 1;
+            double frac = (kind == LevelKind::ClaheBin) ? ((double)k - 0.5) / 255.0 : (double)k / max_val;
+            if (kind == LevelKind::Quantize && gamma != 1.0) frac = std::pow(frac, 1.0 / gamma);
+            const double db = low + range * frac;
+            const uint32_t guess = bits_of((float)std::pow(10.0, db / 10.0));
+            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, guess));
+        }
+    });
+}
+
+} // namespace sarpro

@@ -122,3 +122,60 @@ def test_pol_ops_and_small_stages(ctx):
     dbo, masko = O.process_scalar_data_inplace(a)
     assert np.array_equal(mask, masko)
     assert np.allclose(db, dbo, rtol=1e-12, atol=0)  # contract: 1e-5 relative
+
+
+# ---- general f32 rasters: polarization ops and non-integer inputs (thresholds instead of DN tables) ----
+def _check_stats_f32(st, so):
+    for k in EXACT_STATS:
+        assert getattr(st, k) == getattr(so, k), k
+    # mean/std come from fp32 logs on this path (documented): log lines and the Adaptive test only
+    assert abs(st.mean_db - so.mean_db) <= 1e-4
+    assert abs(st.std_db - so.std_db) <= 1e-4
+
+
+@pytest.mark.parametrize("op", [S.OP_SUM, S.OP_DIFF, S.OP_RATIO, S.OP_NDIFF, S.OP_LOGRATIO])
+@pytest.mark.parametrize("strategy", range(7))
+@pytest.mark.parametrize("bit_depth", [S.U8, S.U16])
+def test_pipeline_single_pol_op(ctx, op, strategy, bit_depth):
+    vv = CASES["speckle"](301, 423).astype(np.float32)
+    vh = CASES["speckle_vh"](301, 423).astype(np.float32)
+    comb = O.pol_op(op, vv, vh)
+    po = O.process_scalar_data_pipeline(comb, bit_depth, strategy, want_db=False)
+    img = ctx.process_single(vv, S.TIFF, bit_depth, strategy, None, False, op=op, band2=vh)
+    got, ref = (img.gray, po.u8) if bit_depth == S.U8 else (img.gray16, po.u16)
+    assert np.array_equal(got, ref), (int((got != ref).sum()), int(np.abs(got.astype(int) - ref.astype(int)).max()))
+    if strategy != S.ADAPTIVE or True:
+        _check_stats_f32(img.stats[0], po.stats)
+
+
+@pytest.mark.parametrize("strategy", [S.STANDARD, S.ROBUST, S.CLAHE, S.EQUALIZED])
+@pytest.mark.parametrize("bit_depth", [S.U8, S.U16])
+def test_non_integer_band_resized(ctx, strategy, bit_depth):
+    """A calibrated (non-integer) f32 band through autoscale + Lanczos + pad."""
+    dn = CASES["speckle"](640, 900).astype(np.float32)
+    v = (dn * dn * np.float32(3.7e-4)).astype(np.float32)  # sigma0-like
+    v[:, :30] = 0
+    ref, meta = O.pipeline_single(v, O.TIFF, bit_depth, strategy, 256, True)
+    img = ctx.process_single(v, S.TIFF, bit_depth, strategy, 256, True)
+    got = img.gray if bit_depth == S.U8 else img.gray16
+    assert np.array_equal(got, ref), int((got != ref).sum())
+    u8, u16, st = ctx.process_scalar_data_pipeline(v, bit_depth, strategy)
+    po = O.process_scalar_data_pipeline(v, bit_depth, strategy, want_db=False)
+    assert np.array_equal(u8 if bit_depth == S.U8 else u16, po.u8 if bit_depth == S.U8 else po.u16)
+    _check_stats_f32(st, po.stats)
+
+
+def test_f32_edge_cases(ctx):
+    neg = -np.abs(np.random.default_rng(1).normal(size=(64, 80))).astype(np.float32)  # diff with a < b: all invalid
+    u8, _, st = ctx.process_scalar_data_pipeline(neg, S.U8, S.ROBUST)
+    assert st.valid_count == 0 and not u8.any()
+    const = np.full((50, 70), 0.37, np.float32)  # degenerate: all equal
+    po = O.process_scalar_data_pipeline(const, S.U16, S.DEFAULT, want_db=False)
+    _, u16, st = ctx.process_scalar_data_pipeline(const, S.U16, S.DEFAULT)
+    assert np.array_equal(u16, po.u16) and st.p99 == po.stats.p99
+    nan = np.random.default_rng(2).gamma(2.0, 3.0, (40, 60)).astype(np.float32)
+    nan[::7, ::5] = np.nan
+    nan[1::9, ::4] = np.inf
+    po = O.process_scalar_data_pipeline(nan, S.U8, S.EQUALIZED, want_db=False)
+    u8, _, st = ctx.process_scalar_data_pipeline(nan, S.U8, S.EQUALIZED)
+    assert np.array_equal(u8, po.u8)
