@@ -7,10 +7,32 @@ pure-Python path: importing works anywhere, using it needs the built library and
 from . import _ffi
 from ._ffi import (ADAPTIVE, CLAHE, DEFAULT, EQUALIZED, JPEG, OP_DIFF, OP_LOGRATIO, OP_NDIFF, OP_NONE, OP_RATIO,
                    OP_SUM, ROBUST, STANDARD, STRATEGY_NAMES, TAMED, TIFF, U8, U16)
-from .api import Context, ProcessedImage, SarproError, plan_from_dn_histogram, shard_rows
+import os as _os
+
+from .api import (Context, ProcessedImage, SarproError, comm_unique_id, plan_from_dn_histogram, shard_halo_rows,
+                  shard_rows)
+
+
+def _locate_nccl():
+    """Point the library at the NCCL torch ships (the library dlopen()s it lazily; no link-time dependency)."""
+    if _os.environ.get("SARPRO_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = _os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if _os.path.exists(cand):
+                _os.environ["SARPRO_NCCL_LIB"] = cand
+    except Exception:
+        pass
+
+
+_locate_nccl()
 
 __all__ = [
-    "Context", "ProcessedImage", "SarproError", "plan_from_dn_histogram", "shard_rows", "_ffi",
+    "Context", "ProcessedImage", "SarproError", "plan_from_dn_histogram", "shard_rows", "shard_halo_rows",
+    "comm_unique_id", "_ffi",
     "STANDARD", "ROBUST", "ADAPTIVE", "EQUALIZED", "CLAHE", "TAMED", "DEFAULT", "STRATEGY_NAMES",
     "U8", "U16", "TIFF", "JPEG", "OP_NONE", "OP_SUM", "OP_DIFF", "OP_RATIO", "OP_NDIFF", "OP_LOGRATIO",
 ]

@@ -293,6 +293,31 @@ class Context:
                               scale_x=img.meta.scale_x, scale_y=img.meta.scale_y, pad_left=img.meta.pad_left,
                               pad_top=img.meta.pad_top, stats=[st])
 
+    # -- multi-GPU: one scene row-band-sharded over the ranks of a communicator -----------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        self._check(self._lib.sarpro_comm_init(self._h, unique_id, int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._check(self._lib.sarpro_comm_destroy(self._h))
+
+    def process_synrgb_sharded(self, band1_rows, band2_rows, scene_rows, strategy, target_size, pad=False,
+                               mode=F.SYNRGB_DEFAULT, tamed_band_step=True, out=None, want_output=True) -> ProcessedImage:
+        """save.rs:317-368 on THIS rank's rows [h0,h1) of the scene (see shard_halo_rows); every rank gets the image."""
+        b1, k1 = self._band(band1_rows)
+        b2, k2 = self._band(band2_rows)
+        _, cols = k1.shape
+        oc, orr = self.resize_output_dims(cols, scene_rows, target_size, pad)
+        if want_output:
+            img, out = self._image(oc, orr, 3, U8, out)
+        else:
+            img, out = F.Image(None, F.LOC_HOST, U8, 0, 0, 0, 0, 0, F.ResizeMeta()), None
+        self._check(self._lib.sarpro_pipeline_synrgb_sharded(
+            self._h, C.byref(b1), C.byref(b2), int(scene_rows), strategy, mode, int(target_size is not None),
+            int(target_size or 0), int(bool(pad)), int(bool(tamed_band_step)), C.byref(img)))
+        del k2
+        return ProcessedImage(img.cols, img.rows, U8, JPEG, rgb=out, scale_x=img.meta.scale_x, scale_y=img.meta.scale_y,
+                              pad_left=img.meta.pad_left, pad_top=img.meta.pad_top)
+
     def process_multiband_tiff(self, band1, band2, bit_depth, strategy, target_size=None, pad=False) -> ProcessedImage:
         """save.rs:199-316; api/mod.rs:133-200."""
         b1, k1 = self._band(band1)
@@ -327,6 +352,25 @@ class Context:
         del k2
         return ProcessedImage(img.cols, img.rows, U8, JPEG, rgb=out, scale_x=img.meta.scale_x, scale_y=img.meta.scale_y,
                               pad_left=img.meta.pad_left, pad_top=img.meta.pad_top, stats=[st[0], st[1]])
+
+
+def comm_unique_id() -> bytes:
+    """128-byte ncclUniqueId (rank 0 creates it; ship it to the other ranks with any transport)."""
+    buf = C.create_string_buffer(128)
+    rc = F.lib().sarpro_comm_unique_id(buf)
+    if rc != F.OK:
+        raise SarproError(rc, "sarpro_comm_unique_id failed (libnccl.so.2 not loadable? set SARPRO_NCCL_LIB)")
+    return buf.raw
+
+
+def shard_halo_rows(rows, cols, target, world, rank, clahe):
+    """Scene rows [h0,h1) a rank must hold: its own band plus the vertical Lanczos halo."""
+    h0, h1 = C.c_size_t(), C.c_size_t()
+    rc = F.lib().sarpro_shard_halo_rows(rows, cols, int(target is not None), int(target or 0), world, rank, int(bool(clahe)),
+                                        C.byref(h0), C.byref(h1))
+    if rc != F.OK:
+        raise SarproError(rc, "sarpro_shard_halo_rows: invalid argument")
+    return h0.value, h1.value
 
 
 def plan_from_dn_histogram(hist65536, bit_depth, strategy):

@@ -100,7 +100,9 @@ int upload_rgb_luts(sarpro_ctx* ctx) {
 
 // ---- histogram work units ---------------------------------------------------------------------
 // local rows [0, rows) are scene rows [row_off, row_off+rows); tiles follow the scene geometry.
-int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uint64_t scene_rows, uint64_t row_off) {
+// own0/own1: local rows that are counted (a sharded rank also holds halo rows it must not count).
+int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uint64_t scene_rows, uint64_t row_off,
+                  uint64_t own0, uint64_t own1) {
     std::vector<HistUnit> units;
     const uint64_t target_px = 192 * 1024;
     if (!clahe) {
@@ -110,8 +112,8 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
         for (uint64_t c0 = 0; c0 < cols; c0 += sw) {
             const uint64_t c1 = std::min(cols, c0 + sw);
             const uint64_t chunk = std::max<uint64_t>(1, target_px / (c1 - c0));
-            for (uint64_t r = 0; r < rows; r += chunk)
-                units.push_back(HistUnit{(uint32_t)r, (uint32_t)std::min(rows, r + chunk), (uint32_t)c0, (uint32_t)c1, 0u, 0u});
+            for (uint64_t r = own0; r < own1; r += chunk)
+                units.push_back(HistUnit{(uint32_t)r, (uint32_t)std::min(own1, r + chunk), (uint32_t)c0, (uint32_t)c1, 0u, 0u});
         }
         ctx->n_tiles = 1;
     } else {
@@ -119,7 +121,7 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
         for (uint64_t ty = 0; ty < kClaheTiles; ++ty) {
             const uint64_t gr0 = ty * g.tile_h, gr1 = std::min((ty + 1) * g.tile_h, scene_rows);
             // intersect with the local band
-            const uint64_t a = std::max(gr0, row_off), b = std::min(gr1, row_off + rows);
+            const uint64_t a = std::max(gr0, row_off + own0), b = std::min(gr1, row_off + own1);
             if (a >= b) continue;
             for (uint64_t tx = 0; tx < kClaheTiles; ++tx) {
                 const uint64_t c0 = tx * g.tile_w, c1 = std::min((tx + 1) * g.tile_w, cols);
@@ -325,14 +327,27 @@ OutGeom out_geometry(size_t cols, size_t rows, bool has_target, size_t target, b
 
 // Pass A launches for band slot b (no synchronisation): per-tile DN histogram + totals.
 int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units) {
+    ShardGeom sg;
+    sg.scene_rows = rows;
+    sg.row_off = 0;
+    sg.own0 = 0;
+    sg.own1 = rows;
+    return dn_pass_a_launch_sharded(ctx, b, dn, rows, cols, clahe_units, sg);
+}
+
+int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units,
+                             const ShardGeom& sg) {
     if (ctx->units_rows != rows || ctx->units_cols != cols || ctx->units_clahe != (int)clahe_units ||
-        ctx->units_scene_rows != rows || ctx->units_row_off != 0) {
-        RC(prepare_units(ctx, rows, cols, clahe_units, rows, 0));
+        ctx->units_scene_rows != sg.scene_rows || ctx->units_row_off != sg.row_off || ctx->units_own0 != sg.own0 ||
+        ctx->units_own1 != sg.own1) {
+        RC(prepare_units(ctx, rows, cols, clahe_units, sg.scene_rows, sg.row_off, sg.own0, sg.own1));
         ctx->units_rows = rows;
         ctx->units_cols = cols;
         ctx->units_clahe = clahe_units;
-        ctx->units_scene_rows = rows;
-        ctx->units_row_off = 0;
+        ctx->units_scene_rows = sg.scene_rows;
+        ctx->units_row_off = sg.row_off;
+        ctx->units_own0 = sg.own0;
+        ctx->units_own1 = sg.own1;
     }
     BandWs& w = ctx->band[b];
     RC(reserve(ctx, w.tile_hist, (size_t)ctx->n_tiles * kDnBins * 4));
@@ -506,6 +521,26 @@ int dn_run_pass_b(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& g, vo
         return 0;
     }
     return run_pass_b_resized(ctx, b, j, g, canvas);
+}
+
+// synthetic_rgb.rs:182-197 on two device-resident u8 bands -> ctx->rgb (interleaved RGB)
+int synrgb_compose(sarpro_ctx* ctx, int strategy, const uint8_t* c1, const uint8_t* c2, size_t n) {
+    RC(reserve(ctx, ctx->rgb, std::max<size_t>(n * 3, 16)));
+    if (!n) return 0;
+    const bool suppressed = strategy == SARPRO_STRATEGY_TAMED || strategy == SARPRO_STRATEGY_CLAHE; // synthetic_rgb.rs:189-195
+    if (suppressed) {
+        RC(reserve(ctx, ctx->hist256, 256 * 4));
+        RC(reserve(ctx, ctx->rgbsel, 16));
+        CU(cudaMemsetAsync(ctx->hist256.p, 0, 256 * 4, ctx->stream));
+        KS(SARPRO_STAGE_RGB, launch_hist256_pair(c1, c2, n, (uint32_t*)ctx->hist256.p, ctx->stream));
+        KS(SARPRO_STAGE_RGB, launch_synrgb_floor((const uint32_t*)ctx->hist256.p, n, (uint32_t*)ctx->rgbsel.p, ctx->stream));
+        KS(SARPRO_STAGE_RGB, launch_synrgb(c1, c2, n, (const uint8_t*)ctx->rgb_luts.p, (const uint32_t*)ctx->rgbsel.p, 0, 1,
+                                           (uint8_t*)ctx->rgb.p, ctx->stream));
+    } else {
+        KS(SARPRO_STAGE_RGB, launch_synrgb(c1, c2, n, (const uint8_t*)ctx->rgb_luts.p, nullptr, kSynRgbDefaultSet, 0,
+                                           (uint8_t*)ctx->rgb.p, ctx->stream));
+    }
+    return 0;
 }
 
 // A band whose DN -> sample table is already known (general f32 rasters bridged through a key plane).
@@ -884,22 +919,7 @@ int sarpro_pipeline_synrgb(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_
     OutGeom g;
     RC(produce_bands(ctx, ins, ins2, ops, 2, strategies, depths, kinds, has_target != 0, target, pad != 0, canvas, &g, stats2));
     const size_t n = g.oc * g.orr;
-    RC(reserve(ctx, ctx->rgb, std::max<size_t>(n * 3, 16)));
-    const bool suppressed = strategy == SARPRO_STRATEGY_TAMED || strategy == SARPRO_STRATEGY_CLAHE; // synthetic_rgb.rs:189-195
-    if (n) {
-        if (suppressed) {
-            RC(reserve(ctx, ctx->hist256, 256 * 4));
-            RC(reserve(ctx, ctx->rgbsel, 16));
-            CU(cudaMemsetAsync(ctx->hist256.p, 0, 256 * 4, ctx->stream));
-            KS(SARPRO_STAGE_RGB, launch_hist256_pair((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (uint32_t*)ctx->hist256.p, ctx->stream));
-            KS(SARPRO_STAGE_RGB, launch_synrgb_floor((const uint32_t*)ctx->hist256.p, n, (uint32_t*)ctx->rgbsel.p, ctx->stream));
-            KS(SARPRO_STAGE_RGB, launch_synrgb((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (const uint8_t*)ctx->rgb_luts.p,
-                             (const uint32_t*)ctx->rgbsel.p, 0, 1, (uint8_t*)ctx->rgb.p, ctx->stream));
-        } else {
-            KS(SARPRO_STAGE_RGB, launch_synrgb((const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n, (const uint8_t*)ctx->rgb_luts.p, nullptr,
-                             kSynRgbDefaultSet, 0, (uint8_t*)ctx->rgb.p, ctx->stream));
-        }
-    }
+    RC(synrgb_compose(ctx, strategy, (const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n));
     fill_image(out, g, 3, SARPRO_U8);
     RC(deliver(ctx, ctx->rgb.p, n * 3, out));
     return end_call(ctx);

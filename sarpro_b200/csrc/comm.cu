@@ -1,9 +1,125 @@
-// comm.cu — multi-GPU row-band sharding (one process per GPU).
+// comm.cu — multi-GPU row-band sharding of ONE scene (one process per GPU), SURVEY.md §8e.
+//
+// Each rank holds scene rows [h0,h1): its own band [r0,r1) plus the vertical Lanczos halo. All exchanged
+// quantities are integers, so the sharded result is bit-identical to the single-GPU result:
+//   1. DN histogram            all-reduce(sum)  2 x 65,536 u32            -> every rank plans redundantly
+//   2. CLAHE tile histograms   all-reduce(sum)  2 x 64 x 256 u32          -> every rank builds all 64 CDFs
+//   3. CLAHE sample min/max    all-reduce(max)  4 u32                      -> scale_u16_to_u8 decision
+//   4. resized rows            all-reduce(max)  2 x out_cols x out_rows u8 (disjoint rows, zero elsewhere)
+// NCCL is dlopen()ed (libnccl.so.2, the copy torch ships) so the library has no link-time dependency; the
+// host only moves the 128-byte ncclUniqueId between ranks.
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <cstring>
+#include <vector>
 
 #include "ctx.h"
 
 using namespace sarpro;
+
+namespace sarpro {
+
+typedef struct { char internal[128]; } nccl_unique_id;
+typedef void* nccl_comm_t;
+enum { kNcclUint8 = 1, kNcclUint32 = 3 };
+enum { kNcclSum = 0, kNcclMax = 2 };
+
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(nccl_unique_id*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string error;
+    bool ok = false;
+};
+
+static NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    std::vector<std::string> names;
+    if (const char* e = getenv("SARPRO_NCCL_LIB")) names.push_back(e);
+    names.push_back("libnccl.so.2");
+    names.push_back("libnccl.so");
+    for (const auto& n : names) {
+        api.handle = dlopen(n.c_str(), RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) {
+        api.error = std::string("cannot dlopen libnccl.so.2 (set SARPRO_NCCL_LIB): ") + (dlerror() ? dlerror() : "");
+        return api;
+    }
+#define SARPRO_SYM(field, name)                                                     \
+    *(void**)(&api.field) = dlsym(api.handle, name);                                \
+    if (!api.field) { api.error = std::string("missing NCCL symbol ") + name; return api; }
+    SARPRO_SYM(GetUniqueId, "ncclGetUniqueId")
+    SARPRO_SYM(CommInitRank, "ncclCommInitRank")
+    SARPRO_SYM(CommDestroy, "ncclCommDestroy")
+    SARPRO_SYM(AllReduce, "ncclAllReduce")
+    SARPRO_SYM(GroupStart, "ncclGroupStart")
+    SARPRO_SYM(GroupEnd, "ncclGroupEnd")
+    SARPRO_SYM(GetErrorString, "ncclGetErrorString")
+#undef SARPRO_SYM
+    api.ok = true;
+    return api;
+}
+
+struct CommState {
+    nccl_comm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+#define NC(call)                                                                                        \
+    do {                                                                                                \
+        int r__ = (call);                                                                               \
+        if (r__ != 0) return fail(ctx, SARPRO_ERR_COMM, "NCCL error %d (%s) at %s:%d", r__,             \
+                                  nccl().GetErrorString ? nccl().GetErrorString(r__) : "?", __FILE__, __LINE__); \
+    } while (0)
+
+// output rows [oy0, oy1) produced by `rank`: those whose window centre falls in the rank's row band
+static void owned_output_rows(size_t scene_rows, size_t out_rows, size_t r0, size_t r1, size_t* oy0, size_t* oy1) {
+    auto first_at_or_after = [&](size_t r) -> size_t { // smallest oy with floor((oy + 0.5) * scene/out) >= r
+        if (r == 0) return 0;
+        if (r >= scene_rows) return out_rows;
+        const double scale = (double)scene_rows / (double)out_rows;
+        size_t oy = (size_t)std::max(0.0, std::floor((double)r / scale - 0.5));
+        while (oy > 0 && (size_t)std::floor(((double)(oy - 1) + 0.5) * scale) >= r) --oy;
+        while (oy < out_rows && (size_t)std::floor(((double)oy + 0.5) * scale) < r) ++oy;
+        return oy;
+    };
+    *oy0 = first_at_or_after(r0);
+    *oy1 = first_at_or_after(r1);
+}
+
+static int shard_geometry(size_t scene_rows, size_t cols, bool has_target, size_t target, bool pad, int world, int rank,
+                          bool clahe, size_t* r0, size_t* r1, size_t* h0, size_t* h1, size_t* oy0, size_t* oy1,
+                          OutGeom* g_out) {
+    int rc = sarpro_shard_rows(scene_rows, world, rank, clahe, r0, r1);
+    if (rc) return rc;
+    const OutGeom g = out_geometry(cols, scene_rows, has_target, target, pad);
+    if (g_out) *g_out = g;
+    *h0 = *r0;
+    *h1 = *r1;
+    *oy0 = *oy1 = 0;
+    if (g.resize && g.rr > 0 && g.rc > 0) {
+        owned_output_rows(scene_rows, g.rr, *r0, *r1, oy0, oy1);
+        if (*oy1 > *oy0) {
+            ResampleAxis av;
+            build_lanczos3_axis((uint32_t)scene_rows, (uint32_t)g.rr, false, &av);
+            *h0 = std::min<size_t>(*h0, av.start[*oy0]);
+            *h1 = std::max<size_t>(*h1, (size_t)av.start[*oy1 - 1] + av.size[*oy1 - 1]);
+        }
+    }
+    return 0;
+}
+
+} // namespace sarpro
 
 extern "C" {
 
@@ -25,28 +141,229 @@ int sarpro_shard_rows(size_t rows, int world, int rank, int clahe, size_t* r0, s
 
 int sarpro_shard_halo_rows(size_t rows, size_t cols, int has_target, size_t target, int world, int rank, int clahe,
                            size_t* h0, size_t* h1) {
-    size_t r0, r1;
-    int rc = sarpro_shard_rows(rows, world, rank, clahe, &r0, &r1);
-    if (rc) return rc;
     if (!h0 || !h1) return SARPRO_ERR_INVALID_ARGUMENT;
-    *h0 = r0;
-    *h1 = r1;
-    (void)cols; (void)has_target; (void)target;
+    size_t r0, r1, oy0, oy1;
+    return shard_geometry(rows, cols, has_target != 0, target, false, world, rank, clahe != 0, &r0, &r1, h0, h1, &oy0, &oy1,
+                          nullptr);
+}
+
+int sarpro_comm_unique_id(void* out128) {
+    if (!out128) return SARPRO_ERR_INVALID_ARGUMENT;
+    NcclApi& api = nccl();
+    if (!api.ok) return SARPRO_ERR_COMM;
+    nccl_unique_id id;
+    if (api.GetUniqueId(&id) != 0) return SARPRO_ERR_COMM;
+    std::memcpy(out128, &id, 128);
     return SARPRO_OK;
 }
 
-int sarpro_comm_unique_id(void* out128) { (void)out128; return SARPRO_ERR_COMM; }
 int sarpro_comm_init(sarpro_ctx* ctx, const void* unique_id128, int rank, int world) {
-    (void)unique_id128; (void)rank; (void)world;
-    return fail(ctx, SARPRO_ERR_COMM, "multi-GPU support not built in this revision");
+    if (!ctx || !unique_id128 || world < 1 || rank < 0 || rank >= world) return SARPRO_ERR_INVALID_ARGUMENT;
+    NcclApi& api = nccl();
+    if (!api.ok) return fail(ctx, SARPRO_ERR_COMM, "%s", api.error.c_str());
+    CU(cudaSetDevice(ctx->device));
+    sarpro_comm_destroy(ctx);
+    nccl_unique_id id;
+    std::memcpy(&id, unique_id128, 128);
+    CommState* cs = new CommState();
+    cs->rank = rank;
+    cs->world = world;
+    int r = api.CommInitRank(&cs->comm, world, id, rank);
+    if (r != 0) {
+        delete cs;
+        return fail(ctx, SARPRO_ERR_COMM, "ncclCommInitRank failed: %s", api.GetErrorString(r));
+    }
+    ctx->comm = cs;
+    return SARPRO_OK;
 }
-int sarpro_comm_destroy(sarpro_ctx* ctx) { (void)ctx; return SARPRO_OK; }
+
+int sarpro_comm_destroy(sarpro_ctx* ctx) {
+    if (!ctx) return SARPRO_ERR_INVALID_ARGUMENT;
+    if (ctx->comm) {
+        if (ctx->comm->comm && nccl().ok) nccl().CommDestroy(ctx->comm->comm);
+        delete ctx->comm;
+        ctx->comm = nullptr;
+    }
+    return SARPRO_OK;
+}
+
 int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_band* b2, size_t scene_rows,
                                    int strategy, int mode, int has_target, size_t target, int pad, int tamed_band_step,
                                    sarpro_image* out) {
-    (void)b1; (void)b2; (void)scene_rows; (void)strategy; (void)mode; (void)has_target; (void)target; (void)pad;
-    (void)tamed_band_step; (void)out;
-    return fail(ctx, SARPRO_ERR_COMM, "multi-GPU support not built in this revision");
+    (void)mode;
+    RC(begin_call(ctx));
+    if (!b1 || !b2) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
+    NcclApi& api = nccl();
+    CommState* cs = ctx->comm;
+    const sarpro_band* ins[2] = {b1, b2};
+    for (int b = 0; b < 2; ++b) {
+        RC(check_band(ctx, ins[b]));
+        if (ins[b]->dtype != SARPRO_DT_U16) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "the sharded pipeline takes u16 DN bands");
+        if (ins[b]->rows != b1->rows || ins[b]->cols != b1->cols) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "bands differ in shape");
+    }
+    const size_t cols = b1->cols;
+    if (!has_target || std::max(cols, scene_rows) == target)
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "the sharded pipeline needs a resize target below the long side");
+    const bool clahe = strategy == SARPRO_STRATEGY_CLAHE;
+    size_t r0, r1, h0, h1, oy0, oy1;
+    OutGeom g;
+    RC(shard_geometry(scene_rows, cols, true, target, pad != 0, cs->world, cs->rank, clahe, &r0, &r1, &h0, &h1, &oy0, &oy1, &g));
+    if (b1->rows != h1 - h0)
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "rank %d must hold scene rows [%zu,%zu) (%zu rows), got %llu", cs->rank, h0, h1,
+                    h1 - h0, (unsigned long long)b1->rows);
+    const uint64_t rows = h1 - h0;
+    PlanKind kinds[2] = {PlanKind::Autoscale, PlanKind::Autoscale};
+    if (tamed_band_step && strategy == SARPRO_STRATEGY_TAMED) {
+        kinds[0] = PlanKind::TamedSynRgbCopol;
+        kinds[1] = PlanKind::TamedSynRgbCross;
+    }
+
+    // ---- stage + pass A on the owned rows ------------------------------------------------------------
+    BandJob jobs[2];
+    ShardGeom sg;
+    sg.scene_rows = scene_rows;
+    sg.row_off = h0;
+    sg.own0 = r0 - h0;
+    sg.own1 = r1 - h0;
+    for (int b = 0; b < 2; ++b) {
+        BandWs& w = ctx->band[b];
+        const uint16_t* dn = (const uint16_t*)ins[b]->data;
+        if (ins[b]->location == SARPRO_LOC_HOST) {
+            RC(reserve(ctx, w.dn, rows * cols * 2));
+            CU(cudaMemcpyAsync(w.dn.p, ins[b]->data, rows * cols * 2, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->timing.h2d_bytes += rows * cols * 2;
+            dn = (const uint16_t*)w.dn.p;
+        }
+        jobs[b].dn = dn;
+        jobs[b].rows = rows;
+        jobs[b].cols = cols;
+        jobs[b].strategy = strategy;
+        jobs[b].bit_depth = SARPRO_U8;
+        jobs[b].kind = kinds[b];
+        RC(dn_pass_a_launch_sharded(ctx, b, dn, rows, cols, clahe, sg));
+    }
+    // ---- 1. DN histogram all-reduce, then every rank plans ---------------------------------------------
+    NC(api.GroupStart());
+    for (int b = 0; b < 2; ++b)
+        NC(api.AllReduce(ctx->band[b].total.p, ctx->band[b].total.p, kDnBins, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
+    NC(api.GroupEnd());
+    for (int b = 0; b < 2; ++b)
+        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, ctx->band[b].total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->timing.host_syncs++;
+    for (int b = 0; b < 2; ++b) {
+        BandWs& w = ctx->band[b];
+        std::vector<uint64_t> h64(kDnBins);
+        const uint32_t* h32 = ctx->h_hist + (size_t)b * kDnBins;
+        for (int i = 0; i < kDnBins; ++i) h64[i] = h32[i];
+        plan_from_dn_histogram(h64.data(), SARPRO_U8, strategy, kinds[b], &w.plan);
+        std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+        CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // ---- 2. CLAHE tile histograms: local partial sums, all-reduce, CDFs everywhere ------------------------
+    const size_t esz = 1;
+    const size_t n_out = g.oc * g.orr;
+    AxisPlan *ah = nullptr, *av = nullptr;
+    const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
+    RC(get_axis(ctx, (uint32_t)cols, (uint32_t)g.rc, false, true, src_kind, &ah));
+    RC(get_axis(ctx, (uint32_t)scene_rows, (uint32_t)g.rr, false, false, 0, &av));
+    if (clahe) {
+        for (int b = 0; b < 2; ++b) {
+            BandWs& w = ctx->band[b];
+            RC(reserve(ctx, w.tile256, (size_t)ctx->n_tiles * 256 * 4));
+            RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
+            RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
+            CU(cudaMemsetAsync(w.tile256.p, 0, (size_t)ctx->n_tiles * 256 * 4, ctx->stream));
+            if (w.plan.any_valid)
+                KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles,
+                                                           w.plan.max_present_dn, (uint32_t*)w.tile256.p, ctx->stream));
+        }
+        NC(api.GroupStart());
+        for (int b = 0; b < 2; ++b)
+            NC(api.AllReduce(ctx->band[b].tile256.p, ctx->band[b].tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum,
+                             cs->comm, ctx->stream));
+        NC(api.GroupEnd());
+        for (int b = 0; b < 2; ++b) {
+            BandWs& w = ctx->band[b];
+            KS(SARPRO_STAGE_PLAN, launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles,
+                                                   (double*)w.cdf.p, (float*)w.cdf32.p, ctx->stream));
+        }
+    }
+    // ---- pass B: horizontal pass over the held rows ---------------------------------------------------------
+    HResizeArgs args[2];
+    for (int b = 0; b < 2; ++b) {
+        BandWs& w = ctx->band[b];
+        RC(reserve(ctx, w.temp, std::max<size_t>((size_t)rows * g.rc * esz, 16)));
+        RC(reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)));
+        CU(cudaMemsetAsync(w.small.p, 0, std::max<size_t>(n_out * esz, 1), ctx->stream));
+        HResizeArgs a{};
+        a.src = jobs[b].dn;
+        a.src_rows = (uint32_t)rows;
+        a.src_cols = (uint32_t)cols;
+        a.lut = (const uint16_t*)w.lut.p;
+        a.remap = nullptr;
+        if (clahe) a.clahe = clahe_dev(ctx, b);
+        a.minmax = clahe ? (uint32_t*)w.scalars.p : nullptr;
+        a.row0 = 0;
+        a.n_rows = (uint32_t)rows;
+        a.temp = w.temp.p;
+        a.ax = ah->dev();
+        args[b] = a;
+        if (w.plan.any_valid) RC(run_hpass(ctx, a, src_kind, 0, ah, h0));
+    }
+    // ---- 3. scale_u16_to_u8 decision for CLAHE: global sample min/max --------------------------------------------
+    if (clahe) {
+        // scalars[0] = min, [1] = max per band -> pack {max, ~min} so that one all-reduce(max) serves both
+        uint32_t packed[4];
+        for (int b = 0; b < 2; ++b)
+            CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b, ctx->band[b].scalars.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->timing.host_syncs++;
+        for (int b = 0; b < 2; ++b) {
+            packed[2 * b] = ctx->h_scalars[8 * b + 1];
+            packed[2 * b + 1] = ~ctx->h_scalars[8 * b];
+        }
+        RC(reserve(ctx, ctx->rgbsel, 64));
+        uint32_t* dpk = (uint32_t*)ctx->rgbsel.p + 4;
+        CU(cudaMemcpyAsync(dpk, packed, 16, cudaMemcpyHostToDevice, ctx->stream));
+        NC(api.AllReduce(dpk, dpk, 4, kNcclUint32, kNcclMax, cs->comm, ctx->stream));
+        CU(cudaMemcpyAsync(packed, dpk, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->timing.host_syncs++;
+        for (int b = 0; b < 2; ++b) {
+            if (!ctx->band[b].plan.any_valid) continue;
+            uint32_t mx = packed[2 * b], mn = ~packed[2 * b + 1];
+            if (mn == 0xffffffffu) { mn = 0; mx = 0; }
+            if (!(mn == 0 && mx == 255)) { // identity assumption failed (rare): redo with the remap table
+                RC(upload_remap(ctx, b, mn, mx));
+                args[b].remap = (const uint8_t*)ctx->band[b].remap.p;
+                args[b].minmax = nullptr;
+                RC(run_hpass(ctx, args[b], src_kind, 0, ah, h0));
+            }
+        }
+    }
+    // ---- vertical pass for the owned output rows, then 4. merge the rows of all ranks -------------------------------
+    for (int b = 0; b < 2; ++b) {
+        BandWs& w = ctx->band[b];
+        if (w.plan.any_valid && oy1 > oy0) {
+            unsigned char* dst = (unsigned char*)w.small.p + (g.pad_top * g.oc + g.pad_left) * esz;
+            KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, (uint32_t)h0, (uint32_t)g.rc, av->dev(), (uint32_t)oy0, (uint32_t)oy1, dst,
+                                                    (uint32_t)g.oc, 0, 0, ctx->stream));
+        }
+    }
+    if (n_out) {
+        NC(api.GroupStart());
+        for (int b = 0; b < 2; ++b)
+            NC(api.AllReduce(ctx->band[b].small.p, ctx->band[b].small.p, n_out, kNcclUint8, kNcclMax, cs->comm, ctx->stream));
+        NC(api.GroupEnd());
+    }
+    RC(synrgb_compose(ctx, strategy, (const uint8_t*)ctx->band[0].small.p, (const uint8_t*)ctx->band[1].small.p, n_out));
+    if (out) {
+        fill_image(out, g, 3, SARPRO_U8);
+        if (out->data) RC(deliver(ctx, ctx->rgb.p, n_out * 3, out));
+    }
+    return end_call(ctx);
 }
 
 } // extern "C"

@@ -82,6 +82,11 @@ struct BandJob {
     int strategy = 0, bit_depth = 0;
     PlanKind kind = PlanKind::Autoscale;
 };
+// Row-band sharding of a scene: the local raster holds scene rows [row_off, row_off + rows); the rank owns
+// (counts / produces statistics for) local rows [own0, own1); the rest is Lanczos halo.
+struct ShardGeom {
+    uint64_t scene_rows = 0, row_off = 0, own0 = 0, own1 = 0;
+};
 inline bool uses_clahe(const BandJob& j) { return j.kind == PlanKind::Autoscale && j.strategy == SARPRO_STRATEGY_CLAHE; }
 
 } // namespace sarpro
@@ -102,7 +107,7 @@ struct sarpro_ctx {
     uint32_t n_rowblocks = 0;
     int force_exact = 0; // SARPRO_FORCE_EXACT=1: generic kernels + exact f64 CLAHE everywhere (validation)
     // geometry caches
-    uint64_t units_rows = 0, units_cols = 0, units_scene_rows = 0, units_row_off = 0;
+    uint64_t units_rows = 0, units_cols = 0, units_scene_rows = 0, units_row_off = 0, units_own0 = 0, units_own1 = 0;
     int units_clahe = -1;
     uint32_t n_units = 0, n_tiles = 0;
     std::map<sarpro::AxisKey, sarpro::AxisPlan*> axes;
@@ -133,7 +138,17 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
 int begin_call(sarpro_ctx* ctx);
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off);
 int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units);
+int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units,
+                             const ShardGeom& sg);
 int dn_run_pass_b(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& g, void* canvas);
+int run_clahe_stats(sarpro_ctx* ctx, int b);
+int clahe_minmax(sarpro_ctx* ctx, int b, uint32_t* mn, uint32_t* mx);
+int upload_remap(sarpro_ctx* ctx, int b, uint32_t mn, uint32_t mx);
+ClaheDev clahe_dev(sarpro_ctx* ctx, int b);
+int deliver(sarpro_ctx* ctx, const void* dev_src, size_t bytes, sarpro_image* out);
+void fill_image(sarpro_image* out, const OutGeom& g, int channels, int bit_depth);
+int check_band(sarpro_ctx* ctx, const sarpro_band* b);
+int synrgb_compose(sarpro_ctx* ctx, int strategy, const uint8_t* c1, const uint8_t* c2, size_t n);
 int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint16_t* lut_host, uint32_t max_key,
                             const OutGeom& g, void* canvas);
 int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const float* b_dev, int op, uint64_t rows,
