@@ -14,8 +14,10 @@ synthetic scene.
   cpu_baseline  the CPU oracle (a C++ restatement of the reference's serial path) on a bounded crop of
           the same scene, on this box's host cores.
 
-N > 1 (torchrun, one rank per GPU): batch mode of BASELINE config 5 — every rank processes its own
-scene, no data-path collective ("weak" scaling); the barrier / max-over-ranks timing uses NCCL.
+N > 1 (torchrun, one rank per GPU): ONE scene row-band-sharded over the ranks (BASELINE config 3): every rank holds
+its band plus the Lanczos halo, the library all-reduces the integer DN / CLAHE-tile histograms, the CLAHE min/max
+and the resized rows over NCCL ("strong" scaling, result bit-identical to 1 GPU). The same run also times the batch
+mode of config 5 (one whole scene per rank, no collective) and reports it under "batch_mode".
 `--impl reference` times the oracle (the reference cannot be built here: no Rust toolchain) on a
 bounded sample with all host threads its threaded stage (the Lanczos resize) can use.
 """
@@ -169,105 +171,145 @@ def main():
     rows, cols = args.rows, args.cols
     strategy = S.STRATEGY_NAMES.index(args.strategy)
 
-    # scene of this rank (batch mode: scene index = rank)
-    vv = synth_band_torch(rows, cols, SEED_VV + 2 * rank, dev)
-    vh = synth_band_torch(rows, cols, SEED_VH + 2 * rank, dev, cross_pol=True)
-    oc, orr = S.Context.resize_output_dims(cols, rows, TARGET, True)
-    out_dev = torch.empty((orr, oc, 3), dtype=torch.uint8, device=dev)
-
+    sharded = world > 1
     ctx = S.Context(local_rank)
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
+    oc, orr = S.Context.resize_output_dims(cols, rows, TARGET, True)
+    out_dev = torch.empty((orr, oc, 3), dtype=torch.uint8, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def make_scene(scene):
+        return (synth_band_torch(rows, cols, SEED_VV + 2 * scene, dev),
+                synth_band_torch(rows, cols, SEED_VH + 2 * scene, dev, cross_pol=True))
+
+    def timed(fn, steps, warmup):
+        """K steps of fn() between barriers; CUDA events on the library's stream; max over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc = {"stage_ms": [0.0] * 8, "stage_n": [0] * 8, "launches": 0, "syncs": 0, "h2d": 0, "d2h": 0}
+        w0 = time.time()
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+            t = ctx.timing()
+            acc["launches"] += t.kernel_launches
+            acc["syncs"] += t.host_syncs
+            acc["h2d"], acc["d2h"] = int(t.h2d_bytes), int(t.d2h_bytes)
+            for i in range(8):
+                acc["stage_ms"][i] += t.stage_ms[i]
+                acc["stage_n"][i] += t.stage_launches[i]
+        ev1.record(stream)
+        barrier()
+        w1 = time.time()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms / steps, acc, (w0, w1)
+
+    sampler = ClockSampler(local_rank)
+    if sharded:
+        uid = [S.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+        vv_full, vh_full = make_scene(0)          # every rank synthesises the same scene and keeps its rows
+        h0, h1 = S.shard_halo_rows(rows, cols, TARGET, world, rank, strategy == S.CLAHE)
+        vv, vh = vv_full[h0:h1], vh_full[h0:h1]   # contiguous row slices (views)
+        step = lambda: ctx.process_synrgb_sharded(vv, vh, rows, strategy, TARGET, True, out=out_dev)
+    else:
+        vv, vh = make_scene(rank)
+        h0, h1 = 0, rows
+        step = lambda: ctx.process_synrgb_jpeg(vv, vh, strategy, TARGET, True, out=out_dev)
+
     # ---------------- kernel-only leg: inputs resident in HBM ---------------------------------
     for _ in range(args.warmup):
-        ctx.process_synrgb_jpeg(vv, vh, strategy, TARGET, True, out=out_dev)
-    sampler = ClockSampler(local_rank)
+        step()
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = [0.0] * 8
-    stage_n = [0] * 8
-    launches = 0
-    syncs = 0
-    wall0 = time.time()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        ctx.process_synrgb_jpeg(vv, vh, strategy, TARGET, True, out=out_dev)
-        t = ctx.timing()
-        launches += t.kernel_launches
-        syncs += t.host_syncs
-        for i in range(8):
-            stage_ms[i] += t.stage_ms[i]
-            stage_n[i] += t.stage_launches[i]
-    ev1.record(stream)
-    barrier()
-    wall1 = time.time()
-    ms = ev0.elapsed_time(ev1)
+    ms_per_step, acc, (wall0, wall1) = timed(step, args.steps, 0)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    ms_per_step = ms / args.steps
-    value = world * rows * cols / (ms_per_step * 1e-3) / 1e6
+    value = rows * cols / (ms_per_step * 1e-3) / 1e6   # one scene per step, however many ranks share it
+    stage_ms, stage_n, launches, syncs = acc["stage_ms"], acc["stage_n"], acc["launches"], acc["syncs"]
+
+    # batch mode (config 5): one whole scene per rank, no collective
+    batch = None
+    if sharded:
+        del vv, vh
+        bvv, bvh = vv_full, vh_full
+        bms, _, _ = timed(lambda: ctx.process_synrgb_jpeg(bvv, bvh, strategy, TARGET, True, out=out_dev), max(3, args.steps // 2), 2)
+        batch = {"value": round(world * rows * cols / (bms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "ms_per_step": round(bms, 4),
+                 "scaling": "weak", "parallelism": f"scene-per-GPU x{world}, no collective"}
+        vv, vh = vv_full[h0:h1], vh_full[h0:h1]
 
     # ---------------- end-to-end leg: host buffers through the C ABI ----------------------------
     e2e_steps = max(2, min(args.steps, 5))
-    vv_h = torch.empty((rows, cols), dtype=torch.int16).pin_memory()
-    vh_h = torch.empty((rows, cols), dtype=torch.int16).pin_memory()
+    lrows = h1 - h0
+    vv_h = torch.empty((lrows, cols), dtype=torch.int16).pin_memory()
+    vh_h = torch.empty((lrows, cols), dtype=torch.int16).pin_memory()
     vv_h.copy_(vv)
     vh_h.copy_(vh)
     vv_np = vv_h.numpy().view(np.uint16)
     vh_np = vh_h.numpy().view(np.uint16)
     out_h = torch.empty((orr, oc, 3), dtype=torch.uint8).pin_memory().numpy()
-    ctx.process_synrgb_jpeg(vv_np, vh_np, strategy, TARGET, True, out=out_h)  # warm-up (allocations)
+    if sharded:
+        estep = lambda: ctx.process_synrgb_sharded(vv_np, vh_np, rows, strategy, TARGET, True, out=out_h)
+    else:
+        estep = lambda: ctx.process_synrgb_jpeg(vv_np, vh_np, strategy, TARGET, True, out=out_h)
+    estep()  # warm-up (allocations)
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(e2e_steps):
-        ctx.process_synrgb_jpeg(vv_np, vh_np, strategy, TARGET, True, out=out_h)
+        estep()
         t = ctx.timing()
         h2d, d2h = int(t.h2d_bytes), int(t.d2h_bytes)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     if world > 1:
-        tt = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
-    e2e_value = world * rows * cols / (e2e_ms * 1e-3) / 1e6
+        tt = torch.tensor([e2e_ms, float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        e2e_ms = float(mx[0].item())
+        h2d, d2h = int(tt[1].item()), int(tt[2].item())
+    e2e_value = rows * cols / (e2e_ms * 1e-3) / 1e6
 
     if rank == 0:
         peak, peak_src = load_peaks()
         # dominant kernel: pass B (apply fused with horizontal Lanczos), one launch per band.
         n_apply = max(stage_n[S._ffi.STAGE_NAMES.index("apply")], 1)
         apply_ms = stage_ms[S._ffi.STAGE_NAMES.index("apply")] / n_apply
-        alg_bytes = rows * cols * 2 + rows * oc * 1  # read u16 DN once, write the h-resized u8 rows
+        alg_bytes = (h1 - h0) * cols * 2 + (h1 - h0) * oc * 1  # read the held u16 DN rows once, write the h-resized u8 rows
         achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "kernel": "k_hresize<DN_CLAHE,u8> (pass B)",
+                    "frac": round(achieved / peak, 4), "traffic": None, "kernel": "k_hfast<DN_CLAHE> (pass B: CLAHE apply fused with horizontal Lanczos)",
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,
                     "stage_ms_per_step": {S._ffi.STAGE_NAMES[i]: round(stage_ms[i] / args.steps, 4) for i in range(8) if stage_n[i]}}
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": {"workload": f"C3: dual-pol VV+VH {cols}x{rows} u16 GRD-like -> {args.strategy} autoscale -> Lanczos3 {TARGET}px "
-                                   f"+ pad -> synRGB; one scene per GPU",
+                                   f"+ pad -> synRGB" + (f"; ONE scene row-band-sharded over {world} GPUs (NCCL all-reduce of DN/tile histograms, min/max, resized rows)" if sharded else "; one scene on one GPU"),
                        "cache": "inputs (1.6 GB per scene) exceed the 126 MB L2; no flush needed",
-                       "scene_bytes": rows * cols * 4, "parallelism": f"scene-per-GPU x{world}"},
+                       "scene_bytes": rows * cols * 4, "parallelism": f"row-band x{world}" if sharded else "single GPU"},
             "clocks": clocks, "gpu_launches": launches, "host_syncs_per_step": syncs / args.steps,
             "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms, 3), "input": "pinned host u16 DN bands", "steps": e2e_steps},
             "roofline": roofline,
         }
+        if batch:
+            line["batch_mode"] = batch
         if not args.no_cpu_baseline and world == 1:
             crop_r, crop_c = 8000, 6250
             vvc = vv[:crop_r, :crop_c].cpu().numpy().view(np.uint16)

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "ctx.h"
@@ -97,9 +98,10 @@ static void owned_output_rows(size_t scene_rows, size_t out_rows, size_t r0, siz
     *oy1 = first_at_or_after(r1);
 }
 
+// av: the vertical Lanczos axis of the scene when the caller has it cached (else it is built here).
 static int shard_geometry(size_t scene_rows, size_t cols, bool has_target, size_t target, bool pad, int world, int rank,
                           bool clahe, size_t* r0, size_t* r1, size_t* h0, size_t* h1, size_t* oy0, size_t* oy1,
-                          OutGeom* g_out) {
+                          OutGeom* g_out, const ResampleAxis* av_cached = nullptr) {
     int rc = sarpro_shard_rows(scene_rows, world, rank, clahe, r0, r1);
     if (rc) return rc;
     const OutGeom g = out_geometry(cols, scene_rows, has_target, target, pad);
@@ -110,8 +112,9 @@ static int shard_geometry(size_t scene_rows, size_t cols, bool has_target, size_
     if (g.resize && g.rr > 0 && g.rc > 0) {
         owned_output_rows(scene_rows, g.rr, *r0, *r1, oy0, oy1);
         if (*oy1 > *oy0) {
-            ResampleAxis av;
-            build_lanczos3_axis((uint32_t)scene_rows, (uint32_t)g.rr, false, &av);
+            ResampleAxis local;
+            if (!av_cached) build_lanczos3_axis((uint32_t)scene_rows, (uint32_t)g.rr, false, &local);
+            const ResampleAxis& av = av_cached ? *av_cached : local;
             *h0 = std::min<size_t>(*h0, av.start[*oy0]);
             *h1 = std::max<size_t>(*h1, (size_t)av.start[*oy1 - 1] + av.size[*oy1 - 1]);
         }
@@ -207,8 +210,14 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "the sharded pipeline needs a resize target below the long side");
     const bool clahe = strategy == SARPRO_STRATEGY_CLAHE;
     size_t r0, r1, h0, h1, oy0, oy1;
-    OutGeom g;
-    RC(shard_geometry(scene_rows, cols, true, target, pad != 0, cs->world, cs->rank, clahe, &r0, &r1, &h0, &h1, &oy0, &oy1, &g));
+    OutGeom g = out_geometry(cols, scene_rows, true, target, pad != 0);
+    AxisPlan *ah = nullptr, *av = nullptr;
+    const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
+    if (g.rc == 0 || g.rr == 0) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "resize target yields an empty image");
+    RC(get_axis(ctx, (uint32_t)cols, (uint32_t)g.rc, false, true, src_kind, &ah));
+    RC(get_axis(ctx, (uint32_t)scene_rows, (uint32_t)g.rr, false, false, 0, &av));
+    RC(shard_geometry(scene_rows, cols, true, target, pad != 0, cs->world, cs->rank, clahe, &r0, &r1, &h0, &h1, &oy0, &oy1, &g,
+                      &av->h));
     if (b1->rows != h1 - h0)
         return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "rank %d must hold scene rows [%zu,%zu) (%zu rows), got %llu", cs->rank, h0, h1,
                     h1 - h0, (unsigned long long)b1->rows);
@@ -252,22 +261,21 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, ctx->band[b].total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->timing.host_syncs++;
-    for (int b = 0; b < 2; ++b) {
-        BandWs& w = ctx->band[b];
-        std::vector<uint64_t> h64(kDnBins);
-        const uint32_t* h32 = ctx->h_hist + (size_t)b * kDnBins;
-        for (int i = 0; i < kDnBins; ++i) h64[i] = h32[i];
-        plan_from_dn_histogram(h64.data(), SARPRO_U8, strategy, kinds[b], &w.plan);
-        std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
-        CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        auto plan_one = [&](int b) {
+            BandWs& w = ctx->band[b];
+            plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
+            std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+        };
+        std::thread t1(plan_one, 1);
+        plan_one(0);
+        t1.join();
+        for (int b = 0; b < 2; ++b)
+            CU(cudaMemcpyAsync(ctx->band[b].lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
     }
     // ---- 2. CLAHE tile histograms: local partial sums, all-reduce, CDFs everywhere ------------------------
     const size_t esz = 1;
     const size_t n_out = g.oc * g.orr;
-    AxisPlan *ah = nullptr, *av = nullptr;
-    const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
-    RC(get_axis(ctx, (uint32_t)cols, (uint32_t)g.rc, false, true, src_kind, &ah));
-    RC(get_axis(ctx, (uint32_t)scene_rows, (uint32_t)g.rr, false, false, 0, &av));
     if (clahe) {
         for (int b = 0; b < 2; ++b) {
             BandWs& w = ctx->band[b];

@@ -193,7 +193,42 @@ void make_u16_to_u8_remap(uint16_t mn, uint16_t mx, int n_entries, uint8_t* rema
     }
 }
 
-void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out) {
+namespace {
+
+// All 11 percentiles of autoscale.rs:142-159 in one walk over the 4096-bin histogram (same arithmetic as
+// estimate_percentile, autoscale.rs:120-140).
+void stats_percentiles_one_walk(const uint64_t* hist, uint64_t n, double min_db, double max_db, sarpro_stats* st) {
+    static const double ps[11] = {0.01, 0.02, 0.05, 0.10, 0.25, 0.5, 0.75, 0.90, 0.95, 0.98, 0.99};
+    double* dst[11] = {&st->p01, &st->p02, &st->p05, &st->p10, &st->p25, &st->median_db, &st->p75, &st->p90, &st->p95, &st->p98, &st->p99};
+    uint64_t target[11];
+    for (int i = 0; i < 11; ++i) {
+        uint64_t t = cast_u64(std::floor(ps[i] * (double)n));
+        if (t >= n) t = n - 1;
+        target[i] = t; // non-decreasing in i
+        *dst[i] = max_db;
+    }
+    const double span = max_db - min_db;
+    const double bin_width = span / (double)kStatBins;
+    uint64_t cumsum = 0;
+    int i = 0;
+    for (int b = 0; b < kStatBins && i < 11; ++b) {
+        const uint64_t h = hist[b];
+        const uint64_t next = cumsum + h;
+        while (i < 11 && target[i] < next) {
+            const uint64_t within = target[i] >= cumsum ? target[i] - cumsum : 0;
+            const double frac = h > 0 ? (double)within / (double)h : 0.0;
+            const double bin_start = min_db + (double)b * bin_width;
+            *dst[i] = bin_start + frac * bin_width;
+            ++i;
+        }
+        cumsum = next;
+    }
+}
+
+} // namespace
+
+template <typename CountT>
+static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out) {
     const double* db = dn_db_table();
     out->lut.assign(kDnBins, 0);
     out->clahe = false;
@@ -202,21 +237,29 @@ void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, P
     out->max_present_dn = 0;
     std::memset(&out->stats, 0, sizeof(out->stats));
 
-    // Pass 1 of compute_histogram_stats (autoscale.rs:37-55) over distinct values.
-    uint64_t count = 0, total = 0;
-    double min_db = std::numeric_limits<double>::infinity();
-    double max_db = -std::numeric_limits<double>::infinity();
-    long double sum = 0.0L;
+    // Distinct sample values present in the raster (typically ~1e3 of the 65,536 DNs): everything below is
+    // evaluated once per distinct value instead of once per pixel.
+    struct Present { uint32_t dn; uint64_t h; };
+    static thread_local std::vector<Present> present;
+    present.clear();
+    bool have_invalid = false;
     for (int dn = 0; dn < kDnBins; ++dn) {
         const uint64_t h = hist[dn];
         if (!h) continue;
-        total += h;
         out->max_present_dn = (uint32_t)dn;
-        if (!(db[dn] > -50.0)) continue; // pipeline.rs:22
-        count += h;
-        if (db[dn] < min_db) min_db = db[dn];
-        if (db[dn] > max_db) max_db = db[dn];
-        sum += (long double)h * (long double)db[dn];
+        if (db[dn] > -50.0) present.push_back(Present{(uint32_t)dn, h}); // pipeline.rs:22
+        else have_invalid = true;
+    }
+    // Pass 1 of compute_histogram_stats (autoscale.rs:37-55) over distinct values.
+    uint64_t count = 0;
+    double min_db = std::numeric_limits<double>::infinity();
+    double max_db = -std::numeric_limits<double>::infinity();
+    long double sum = 0.0L;
+    for (const Present& p : present) {
+        count += p.h;
+        if (db[p.dn] < min_db) min_db = db[p.dn];
+        if (db[p.dn] > max_db) max_db = db[p.dn];
+        sum += (long double)p.h * (long double)db[p.dn];
     }
     if (count == 0) return; // all-zero output (autoscale.rs:376-378, 466-468, 716-718); lut already 0
     out->any_valid = true;
@@ -225,82 +268,91 @@ void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, P
     // the correctly-rounded-to-~1e-15 statistics; they feed log lines and the Adaptive branch test only.
     const long double mean_l = sum / (long double)count;
     long double m2 = 0.0L;
-    for (int dn = 0; dn < kDnBins; ++dn) {
-        const uint64_t h = hist[dn];
-        if (!h || !(db[dn] > -50.0)) continue;
-        const long double d = (long double)db[dn] - mean_l;
-        m2 += (long double)h * d * d;
+    for (const Present& p : present) {
+        const long double d = (long double)db[p.dn] - mean_l;
+        m2 += (long double)p.h * d * d;
     }
     const double mean_db = (double)mean_l;
     const double std_db = count > 1 ? (double)sqrtl(m2 / (long double)count) : 0.0;
 
     // Pass 2 (autoscale.rs:103-117): 4096-bin histogram over [min,max].
-    std::vector<uint64_t> h4096(kStatBins, 0);
+    uint64_t h4096[kStatBins];
     const bool degenerate = std::fabs(max_db - min_db) < std::numeric_limits<double>::epsilon();
-    if (!degenerate) {
+    sarpro_stats& st = out->stats;
+    st.valid_count = count;
+    st.min_db = min_db;
+    st.max_db = max_db;
+    st.mean_db = mean_db;
+    st.std_db = std_db;
+    if (degenerate) { // autoscale.rs:81-100
+        st.median_db = min_db;
+        st.p01 = st.p02 = st.p05 = st.p10 = st.p25 = min_db;
+        st.p75 = st.p90 = st.p95 = st.p98 = st.p99 = max_db;
+    } else {
+        std::memset(h4096, 0, sizeof(h4096));
         const double span = max_db - min_db;
         const double inv_span = 1.0 / span;
-        for (int dn = 0; dn < kDnBins; ++dn) {
-            const uint64_t h = hist[dn];
-            if (!h || !(db[dn] > -50.0)) continue;
-            const double t = clampd((db[dn] - min_db) * inv_span, 0.0, 1.0);
+        for (const Present& p : present) {
+            const double t = clampd((db[p.dn] - min_db) * inv_span, 0.0, 1.0);
             uint64_t idx = cast_u64(t * (double)kStatBins);
             if (idx >= (uint64_t)kStatBins) idx = kStatBins - 1;
-            h4096[idx] += h;
+            h4096[idx] += p.h;
         }
+        stats_percentiles_one_walk(h4096, count, min_db, max_db, &st);
     }
-    stats_from_stat_histogram(h4096.data(), count, min_db, max_db, mean_db, std_db, &out->stats);
-    choose_window(strategy, kind, &out->stats);
-    const double low = out->stats.low_clip, high = out->stats.high_clip, gamma = out->stats.gamma;
+    choose_window(strategy, kind, &st);
+    const double low = st.low_clip, high = st.high_clip, gamma = st.gamma;
     const double range = std::fmax(high - low, 1.0); // autoscale.rs:429, 564, 729
 
     const bool tamed_rgb = kind != PlanKind::Autoscale;
     if (!tamed_rgb && strategy == SARPRO_STRATEGY_CLAHE) {
         // autoscale.rs:582-591 normalisation + :263 / :320 bin index; the blend runs on the device.
         out->clahe = true;
-        for (int dn = 0; dn < kDnBins; ++dn) {
-            if (!hist[dn] || !(db[dn] > -50.0)) continue;
-            const double clipped = std::fmin(std::fmax(db[dn], low), high);
+        for (const Present& p : present) {
+            const double clipped = std::fmin(std::fmax(db[p.dn], low), high);
             const double n = (clipped - low) / range;
             const double v = clampd(n, 0.0, 1.0);
-            double b = std::round(v * ((double)kClaheBins - 1.0));
+            const double b = std::round(v * ((double)kClaheBins - 1.0));
             long long bin = (b == b) ? (long long)b : 0;
             if (bin < 0) bin = 0;
             if (bin >= kClaheBins) bin = kClaheBins - 1;
-            out->lut[dn] = (uint16_t)bin;
+            out->lut[p.dn] = (uint16_t)bin;
         }
         return;
     }
 
     const double max_val = (tamed_rgb || bit_depth == SARPRO_U8) ? 255.0 : 65535.0;
     uint16_t mn = 65535, mx = 0;
-    for (int dn = 0; dn < kDnBins; ++dn) {
-        if (!hist[dn]) continue;
-        uint16_t q = 0;
-        if (db[dn] > -50.0) {
-            const double clipped = std::fmin(std::fmax(db[dn], low), high);
-            if (tamed_rgb) { // autoscale.rs:734-736
-                const double normalized = (clipped - low) / range;
-                q = cast_u8(clampd(normalized * 255.0, 0.0, 255.0));
-            } else {         // autoscale.rs:440-442 / 649-651
-                const double normalized = std::pow((clipped - low) / range, gamma);
-                q = cast_u16(clampd(normalized * max_val, 0.0, max_val));
-            }
-        } // invalid pixels are written as 0 (autoscale.rs:444, 653, 738)
-        out->lut[dn] = q;
+    if (have_invalid) { mn = 0; mx = 0; } // invalid pixels are written as 0 (autoscale.rs:444, 653, 738)
+    for (const Present& p : present) {
+        const double clipped = std::fmin(std::fmax(db[p.dn], low), high);
+        uint16_t q;
+        if (tamed_rgb) { // autoscale.rs:734-736
+            const double normalized = (clipped - low) / range;
+            q = cast_u8(clampd(normalized * 255.0, 0.0, 255.0));
+        } else {         // autoscale.rs:440-442 / 649-651
+            const double normalized = std::pow((clipped - low) / range, gamma);
+            q = cast_u16(clampd(normalized * max_val, 0.0, max_val));
+        }
+        out->lut[p.dn] = q;
         if (q < mn) mn = q;
         if (q > mx) mx = q;
     }
-    (void)total;
     out->pre_min = mn;
     out->pre_max = mx;
     if (!tamed_rgb && bit_depth == SARPRO_U8) {
         // scale_u16_to_u8 over ALL pixels incl. invalid zeros (autoscale.rs:669-670, 691-693)
         uint8_t remap[256];
         make_u16_to_u8_remap(mn, mx, 256, remap);
-        for (int dn = 0; dn < kDnBins; ++dn)
-            if (hist[dn]) out->lut[dn] = remap[out->lut[dn] > 255 ? 255 : out->lut[dn]];
+        for (const Present& p : present) out->lut[p.dn] = remap[out->lut[p.dn] > 255 ? 255 : out->lut[p.dn]];
     }
+}
+
+void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out) {
+    plan_from_dn_histogram_t<uint64_t>(hist, bit_depth, strategy, kind, out);
+}
+void plan_from_dn_histogram32(const uint32_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out) {
+    plan_from_dn_histogram_t<uint32_t>(hist, bit_depth, strategy, kind, out);
 }
 
 ClaheGeom clahe_geometry(uint64_t rows, uint64_t cols) {
