@@ -203,7 +203,7 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
     if (ctx->axes.size() > 64) { // bounded cache
         for (auto& kv : ctx->axes) {
             release(kv.second->start); release(kv.second->size); release(kv.second->coef);
-            release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips);
+            release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips);
             delete kv.second;
         }
         ctx->axes.clear();
@@ -244,6 +244,17 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
             ap->f_n_strips = (uint32_t)ap->f_strips_h.size();
             rc = upload_vec(ctx, ap->fstrips, ap->f_strips_h.data(), ap->f_strips_h.size() * sizeof(HStrip));
             ap->fast = rc == 0;
+        }
+        if (!rc && !wide && src_kind != HSRC_IMAGE && hpipe_supported(ap->pairs)) {
+            const uint32_t tile_w = (in + kClaheTiles - 1) / kClaheTiles;
+            const uint32_t max_vec = src_kind == HSRC_DN_CLAHE ? std::min(256u, tile_w / 8) : 256u;
+            std::vector<HStrip> ps;
+            if (hpipe_build_strips(h.start.data(), h.size.data(), out, in, h.window, max_vec, &ap->p_oxb, &ps, &ap->p_rbw_words) ==
+                cudaSuccess) {
+                ap->p_n_strips = (uint32_t)ps.size();
+                rc = upload_vec(ctx, ap->pstrips, ps.data(), ps.size() * sizeof(HStrip));
+                ap->pipe = rc == 0;
+            }
         }
     }
     if (!rc) {
@@ -292,7 +303,75 @@ int prepare_rowblocks(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool cla
     return 0;
 }
 
+// Table range for kernels_hpipe.cu: the smallest hot such that every PRESENT DN >= hot-1 has the table word `top`
+// (the tables are monotone and saturate above the window; the planner leaves absent DNs at 0, so presence comes
+// from the histogram; hist == nullptr: every DN <= max_present_dn counts as present). 0 when that needs more
+// than 2000 table entries.
+uint32_t hpipe_hot(const uint16_t* lut, const uint32_t* hist, uint32_t max_present_dn, uint32_t* top_out) {
+    const uint32_t top = lut[max_present_dn] & 255u;
+    uint32_t h = max_present_dn;
+    for (uint32_t d = max_present_dn;; --d) {
+        if (!hist || hist[d]) {
+            if ((lut[d] & 255u) == top) h = d; else break;
+        }
+        if (d == 0) break;
+    }
+    *top_out = top;
+    const uint32_t need = std::max(64u, (h + 1 + 7) & ~7u);
+    return need <= 2000 ? need : 0;
+}
+
+// Row blocks of kernels_hpipe.cu: multiples of 8 rows (both halves of a CTA get whole groups), never straddling a
+// vertical CLAHE cell boundary.
+int prepare_rowblocks2(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe, uint32_t n_strips) {
+    const uint64_t th = clahe ? ctx->clahe_tile_h : 0;
+    if (ctx->rb2_rows == rows && ctx->rb2_row_off == row_off && ctx->rb2_clahe == (int)clahe && ctx->rb2_tile_h == th &&
+        ctx->rb2_strips == n_strips && ctx->n_rowblocks2)
+        return 0;
+    const uint64_t want_blocks = std::max<uint64_t>(1, (uint64_t)ctx->sm_count * 12 / std::max(1u, n_strips));
+    uint64_t rpb = (rows + want_blocks - 1) / want_blocks;
+    rpb = std::min<uint64_t>(128, std::max<uint64_t>(32, ((rpb + 7) / 8) * 8));
+    std::vector<uint64_t> cuts;
+    cuts.push_back(0);
+    if (clahe && th)
+        for (uint64_t k = 0; k < kClaheTiles; ++k) {
+            const uint64_t g = (th * (2 * k + 1) + 1) / 2; // first global row with 2r >= th*(2k+1)
+            if (g > row_off && g < row_off + rows) cuts.push_back(g - row_off);
+        }
+    cuts.push_back(rows);
+    std::vector<uint2> blocks;
+    uint32_t max_rows = 0;
+    for (size_t i = 0; i + 1 < cuts.size(); ++i)
+        for (uint64_t r = cuts[i]; r < cuts[i + 1]; r += rpb) {
+            const uint64_t e = std::min(cuts[i + 1], r + rpb);
+            blocks.push_back(make_uint2((uint32_t)r, (uint32_t)e));
+            max_rows = std::max(max_rows, (uint32_t)(e - r));
+        }
+    RC(reserve(ctx, ctx->rowblocks2, std::max<size_t>(blocks.size() * sizeof(uint2), 16)));
+    if (!blocks.empty()) {
+        CU(cudaMemcpyAsync(ctx->rowblocks2.p, blocks.data(), blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->n_rowblocks2 = (uint32_t)blocks.size();
+    ctx->rb2_max_rows = max_rows;
+    ctx->rb2_rows = rows;
+    ctx->rb2_row_off = row_off;
+    ctx->rb2_clahe = clahe;
+    ctx->rb2_tile_h = th;
+    ctx->rb2_strips = n_strips;
+    return 0;
+}
+
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
+    if (!pix16 && ah->pipe && ctx->use_hpipe && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap) {
+        const bool clahe = src_kind == HSRC_DN_CLAHE;
+        RC(prepare_rowblocks2(ctx, a.n_rows, row_off, clahe, ah->p_n_strips));
+        HResizeArgs af = a;
+        af.rbw_words = ah->p_rbw_words;
+        KS(SARPRO_STAGE_APPLY, launch_hpipe(af, src_kind, (const HStrip*)ah->pstrips.p, ah->p_n_strips, (const uint2*)ctx->rowblocks2.p,
+                                            ctx->n_rowblocks2, ah->p_oxb, a.hot, ctx->rb2_max_rows, ctx->stream));
+        return 0;
+    }
     if (!pix16 && ah->fast && !ctx->force_exact) {
         const bool clahe = src_kind == HSRC_DN_CLAHE;
         RC(prepare_rowblocks(ctx, a.n_rows, row_off, clahe, ah->f_n_strips));
@@ -380,6 +459,7 @@ int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
         BandWs& w = ctx->band[b];
         plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, jobs[b].bit_depth, jobs[b].strategy, jobs[b].kind, &w.plan);
         std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+        w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
     };
     if (nb == 2) {
         std::thread t1(plan_one, 1);
@@ -483,6 +563,8 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     a.src_rows = (uint32_t)j.rows;
     a.src_cols = (uint32_t)j.cols;
     a.lut = (const uint16_t*)w.lut.p;
+    a.hot = w.hot;
+    a.hot_top = w.hot_top;
     a.remap = nullptr;
     if (clahe) a.clahe = clahe_dev(ctx, b);
     a.minmax = clahe ? (uint32_t*)w.scalars.p : nullptr;
@@ -559,6 +641,7 @@ int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint
     w.plan.any_valid = true;
     w.plan.clahe = uses_clahe(j);
     w.plan.max_present_dn = max_key;
+    w.hot = hpipe_hot(lut_host, nullptr, max_key, &w.hot_top);
     return dn_run_pass_b(ctx, b, j, g, canvas);
 }
 
@@ -782,6 +865,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     dn_db_table();
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
+    if (const char* v = getenv("SARPRO_HPIPE")) ctx->use_hpipe = atoi(v);
     int rc = upload_rgb_luts(ctx);
     if (rc) {
         g_create_error = ctx->err;
@@ -802,11 +886,11 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
             release(*b);
     for (DevBuf* b : {&ctx->units, &ctx->tile_px, &ctx->col_dx, &ctx->col_omdx, &ctx->col_t, &ctx->row_dy, &ctx->row_omdy,
                       &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts, &ctx->col_m, &ctx->row_sat,
-                      &ctx->rowblocks})
+                      &ctx->rowblocks, &ctx->rowblocks2})
         release(*b);
     for (auto& kv : ctx->axes) {
         release(kv.second->start); release(kv.second->size); release(kv.second->coef);
-        release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips);
+        release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips);
         delete kv.second;
     }
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);

@@ -266,6 +266,7 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
             BandWs& w = ctx->band[b];
             plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
             std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+            w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
         };
         std::thread t1(plan_one, 1);
         plan_one(0);
@@ -310,6 +311,8 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         a.src_rows = (uint32_t)rows;
         a.src_cols = (uint32_t)cols;
         a.lut = (const uint16_t*)w.lut.p;
+        a.hot = w.hot;
+        a.hot_top = w.hot_top;
         a.remap = nullptr;
         if (clahe) a.clahe = clahe_dev(ctx, b);
         a.minmax = clahe ? (uint32_t*)w.scalars.p : nullptr;

@@ -28,6 +28,10 @@ struct AxisPlan {
     bool fast = false;
     uint32_t f_oxb = 0, f_rbw_words = 0, f_n_strips = 0;
     std::vector<HStrip> f_strips_h;
+    // second-generation kernel (kernels_hpipe.cu)
+    bool pipe = false;
+    uint32_t p_oxb = 0, p_rbw_words = 0, p_n_strips = 0;
+    DevBuf pstrips;
     AxisDev dev() const {
         AxisDev d;
         d.start = (const uint32_t*)start.p;
@@ -59,6 +63,7 @@ struct BandWs {
     DevBuf scalars; // [0..1] minmax, [2] max_dn, [3] flag
     DevBuf edges, hist4096, f32scan; // general f32 path
     BandPlan plan;
+    uint32_t hot = 0, hot_top = 0; // table range / saturated table word for kernels_hpipe.cu (0 = not eligible)
 };
 
 constexpr uint32_t kSynRgbSets = 42; // 0..40 suppressed by floor_with_cushion, 41 default
@@ -105,6 +110,12 @@ struct sarpro_ctx {
     uint64_t rb_rows = 0, rb_row_off = 0, rb_tile_h = 0;
     int rb_clahe = -1;
     uint32_t n_rowblocks = 0;
+    // row blocks of kernels_hpipe.cu
+    sarpro::DevBuf rowblocks2;
+    uint64_t rb2_rows = 0, rb2_row_off = 0, rb2_tile_h = 0;
+    int rb2_clahe = -1;
+    uint32_t n_rowblocks2 = 0, rb2_max_rows = 0, rb2_strips = 0;
+    int use_hpipe = 1;   // SARPRO_HPIPE=0: previous production kernel (kernels_hfast.cu)
     int force_exact = 0; // SARPRO_FORCE_EXACT=1: generic kernels + exact f64 CLAHE everywhere (validation)
     // geometry caches
     uint64_t units_rows = 0, units_cols = 0, units_scene_rows = 0, units_row_off = 0, units_own0 = 0, units_own1 = 0;
@@ -134,6 +145,7 @@ namespace sarpro {
 int fail(sarpro_ctx* c, int code, const char* fmt, ...);
 int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes);
 void release(DevBuf& b);
+uint32_t hpipe_hot(const uint16_t* lut_host, const uint32_t* hist_host, uint32_t max_present_dn, uint32_t* top_out);
 int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res);
 int begin_call(sarpro_ctx* ctx);
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off);

@@ -94,6 +94,9 @@ struct HResizeArgs {
     uint32_t row0, n_rows;
     void* temp;            // [n_rows][out_cols] same pixel type
     uint32_t rbw_words;    // production kernel: shared row-buffer slots (16 B each)
+    uint32_t hot;          // HSRC_DN_*: table range for kernels_hpipe.cu (every present DN >= hot-1 shares the
+                           // table word of DN hot-1); 0 = unknown / not eligible
+    uint32_t hot_top;      // that table word (lut value of the saturated DNs)
     AxisDev ax;
 };
 // One CTA of the horizontal pass owns a strip of output columns; the strip's source span is staged per row.
@@ -120,6 +123,16 @@ cudaError_t hfast_build_strips(const uint32_t* start_h, const uint32_t* size_h, 
                                uint32_t window, uint32_t* strip_w_out, std::vector<HStrip>* strips, uint32_t* rbw_words);
 cudaError_t launch_hfast(const HResizeArgs& a, int src_kind, const HStrip* strips_dev, uint32_t n_strips,
                          const uint2* rowblocks_dev, uint32_t n_rowblocks, uint32_t strip_w, cudaStream_t stream);
+// Second-generation production pass (kernels_hpipe.cu): two 256-thread halves per CTA sharing lane-interleaved
+// tables, three-stage software pipeline, fp32 CLAHE bilinear form with exact fix-up queue. max_vec bounds the
+// strip's source span in 8-sample vectors (CLAHE: <= tile_w / 8 so a strip meets at most one cell boundary).
+bool hpipe_supported(uint32_t pairs);
+cudaError_t hpipe_build_strips(const uint32_t* start_h, const uint32_t* size_h, uint32_t out_size, uint32_t in_size,
+                               uint32_t window, uint32_t max_vec, uint32_t* strip_w_out, std::vector<HStrip>* strips,
+                               uint32_t* rbw_words);
+cudaError_t launch_hpipe(const HResizeArgs& a, int src_kind, const HStrip* strips_dev, uint32_t n_strips,
+                         const uint2* rowblocks_dev, uint32_t n_rowblocks, uint32_t strip_w, uint32_t hot,
+                         uint32_t max_rows, cudaStream_t stream);
 // vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
                            void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream);

@@ -114,9 +114,132 @@ static cudaError_t launch_dn_hist_t(const uint16_t* dn, uint64_t cols, const His
     return cudaGetLastError();
 }
 
+
+// ---- second generation: lean inner loop ---------------------------------------------------------------
+// Per 8-pixel vector: one range test on the OR of the four words, then per pixel one shift/mask (ALU pipe),
+// one IMAD (FMA pipe) and one shared-memory reduction — no per-pixel predicates. DN 0 is counted like any other
+// value (a run of identical DNs is one POPC-merged update per replica). Vectors that hold a DN >= HOT or that
+// straddle the unit's column range take the per-pixel path (two lanes per row for the ragged ends).
+// 1024 threads, one CTA per SM, NCOPY = 1 << LOGC lane-interleaved replicas: word (dn << LOGC) | (lane % NCOPY).
+__device__ __forceinline__ void red_shared_inc(uint32_t addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+template <int HOT, int LOGC>
+__global__ void __launch_bounds__(1024, 1) k_dn_hist2(const uint16_t* __restrict__ dn, uint64_t cols,
+                                                      const HistUnit* __restrict__ units, uint32_t n_units,
+                                                      uint32_t* __restrict__ tile_hist) {
+    extern __shared__ uint32_t sh[];
+    constexpr uint32_t NCOPY = 1u << LOGC;
+    constexpr uint32_t kHotMask = ~(uint32_t)(HOT - 1) & 0xffffu; // HOT is a power of two
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sh) + (lane & (NCOPY - 1)) * 4u;
+    for (uint32_t i = tid; i < (uint32_t)HOT * NCOPY; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+
+    const uint16_t* dn_al = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(dn) & ~uintptr_t(15));
+    const uint64_t eoff = (uint64_t)(dn - dn_al);
+
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const HistUnit un = units[u];
+        uint32_t* __restrict__ gh = tile_hist + (size_t)un.tile * 65536u;
+        const uint32_t seg = un.c1 - un.c0;
+
+        auto add_px = [&](uint32_t d) {
+            if (d < (uint32_t)HOT) red_shared_inc(sbase + (d << (LOGC + 2)));
+            else atomicAdd(&gh[d], 1u);
+        };
+        auto add_vec = [&](const uint4& q) {
+            if (((q.x | q.y | q.z | q.w) & (kHotMask * 0x10001u)) == 0) {
+                red_shared_inc(sbase + (q.x & 0xffffu) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.x >> 16) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.y & 0xffffu) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.y >> 16) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.z & 0xffffu) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.z >> 16) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.w & 0xffffu) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.w >> 16) * (4u * NCOPY));
+            } else {
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { add_px(w[k] & 0xffffu); add_px(w[k] >> 16); }
+            }
+        };
+
+        for (uint32_t r = un.r0 + warp; r < un.r1; r += nwarps) {
+            const uint64_t e0 = (uint64_t)r * cols + un.c0 + eoff, e1 = e0 + seg;
+            const uint64_t f0 = (e0 + 7) >> 3, f1 = e1 >> 3; // full vectors [f0, f1)
+            if (f0 < f1) {
+                for (uint64_t v = f0 + lane; v < f1; v += 128) {
+                    uint4 q[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t vv = v + 32u * j;
+                        ok[j] = vv < f1;
+                        if (ok[j]) q[j] = ld_stream_u4(dn_al + (vv << 3));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (ok[j]) add_vec(q[j]);
+                }
+                // ragged ends: elements [e0, f0*8) and [f1*8, e1)
+                if (lane < 2) {
+                    const uint64_t a = lane == 0 ? e0 : (f1 << 3), b = lane == 0 ? (f0 << 3) : e1;
+                    for (uint64_t e = a; e < b; ++e) add_px(dn_al[e]);
+                }
+            } else {
+                for (uint64_t e = e0 + lane; e < e1; e += 32) add_px(dn_al[e]);
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = tid; b < (uint32_t)HOT; b += blockDim.x) {
+            uint32_t s = 0;
+            if (NCOPY >= 4) {
+                uint4* p = reinterpret_cast<uint4*>(&sh[b << LOGC]);
+#pragma unroll
+                for (uint32_t c = 0; c < NCOPY / 4; ++c) {
+                    // rotate the starting replica per bin so that the lanes of a warp spread over the banks
+                    const uint32_t cc = (c + b) & (NCOPY / 4 - 1);
+                    const uint4 t = p[cc];
+                    s += t.x + t.y + t.z + t.w;
+                    p[cc] = make_uint4(0, 0, 0, 0);
+                }
+            } else {
+#pragma unroll
+                for (uint32_t c = 0; c < NCOPY; ++c) { s += sh[(b << LOGC) | c]; sh[(b << LOGC) | c] = 0; }
+            }
+            if (s) atomicAdd(&gh[b], s);
+        }
+        __syncthreads();
+    }
+}
+
+template <int HOT, int LOGC>
+static cudaError_t launch_dn_hist2_t(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
+                                     uint32_t* tile_hist, int sm_count, cudaStream_t stream) {
+    const size_t smem = (size_t)HOT * (1u << LOGC) * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_dn_hist2<HOT, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    uint32_t grid = (uint32_t)sm_count;
+    if (grid > n_units) grid = n_units;
+    if (grid == 0) return cudaSuccess;
+    k_dn_hist2<HOT, LOGC><<<grid, 1024, smem, stream>>>(dn, cols, units, n_units, tile_hist);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dn_hist(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
                            uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream) {
     switch (variant) {
+    case 10: return launch_dn_hist2_t<4096, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 11: return launch_dn_hist2_t<2048, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 12: return launch_dn_hist2_t<1024, 5>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 13: return launch_dn_hist2_t<2048, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 14: return launch_dn_hist2_t<1024, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);
     case 1: return launch_dn_hist_t<4096, 0>(dn, cols, units, n_units, tile_hist, sm_count, stream);
     case 2: return launch_dn_hist_t<2048, 2>(dn, cols, units, n_units, tile_hist, sm_count, stream);
     case 3: return launch_dn_hist_t<1024, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);

@@ -179,3 +179,25 @@ def test_f32_edge_cases(ctx):
     po = O.process_scalar_data_pipeline(nan, S.U8, S.EQUALIZED, want_db=False)
     u8, _, st = ctx.process_scalar_data_pipeline(nan, S.U8, S.EQUALIZED)
     assert np.array_equal(u8, po.u8)
+
+
+@pytest.mark.parametrize("strategy", [S.CLAHE, S.ROBUST, S.TAMED])
+@pytest.mark.parametrize("shape,target", [((3001, 4999), 1024), ((2500, 9000), 700), ((5003, 2001), 512)])
+def test_production_kernels_match_exact_kernels(strategy, shape, target, monkeypatch):
+    """The production pass B (kernels_hpipe.cu: fp32 bilinear form + fix-up queue, lane-interleaved tables, clamped
+    table range) against the generic exact kernels (SARPRO_FORCE_EXACT=1) and the previous production kernel
+    (SARPRO_HPIPE=0) on rasters large enough for several strips, CLAHE cells and row blocks; bright point targets
+    exercise the clamped table range. The exact kernels are the ones the other tests pin to the oracle."""
+    from sarpro_b200.synth import synth_pair
+    vv, vh = synth_pair(*shape, point_targets=1e-4)
+    vv[shape[0] // 2:, -300:] = 0  # invalid block on the right edge
+    outs = []
+    for env in ({"SARPRO_FORCE_EXACT": "1"}, {"SARPRO_HPIPE": "0"}, {"SARPRO_HPIPE": "1"}):
+        for k in ("SARPRO_FORCE_EXACT", "SARPRO_HPIPE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with S.Context(0) as c:
+            outs.append(c.process_synrgb_jpeg(vv, vh, strategy, target, True).rgb.copy())
+    assert np.array_equal(outs[0], outs[1]), int((outs[0] != outs[1]).sum())
+    assert np.array_equal(outs[0], outs[2]), int((outs[0] != outs[2]).sum())
