@@ -248,7 +248,7 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
         if (!rc && !wide && src_kind != HSRC_IMAGE && hpipe_supported(ap->pairs)) {
             const uint32_t tile_w = (in + kClaheTiles - 1) / kClaheTiles;
             const uint32_t max_vec = src_kind == HSRC_DN_CLAHE ? std::min(256u, tile_w / 8) : 256u;
-            std::vector<HStrip> ps;
+            std::vector<HStrip>& ps = ap->p_strips_h;
             if (hpipe_build_strips(h.start.data(), h.size.data(), out, in, h.window, max_vec, &ap->p_oxb, &ps, &ap->p_rbw_words) ==
                 cudaSuccess) {
                 ap->p_n_strips = (uint32_t)ps.size();
@@ -321,16 +321,13 @@ uint32_t hpipe_hot(const uint16_t* lut, const uint32_t* hist, uint32_t max_prese
     return need <= 2000 ? need : 0;
 }
 
-// Row blocks of kernels_hpipe.cu: multiples of 8 rows (both halves of a CTA get whole groups), never straddling a
-// vertical CLAHE cell boundary.
-int prepare_rowblocks2(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe, uint32_t n_strips) {
+// Piece lists of kernels_hpipe.cu: equal-weight runs of (strip, rows) per persistent CTA; pieces never straddle a
+// vertical CLAHE cell boundary (rows where floor(r/tile_h - 0.5) changes, autoscale.rs:308-310).
+int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe, AxisPlan* ah, int nsub) {
     const uint64_t th = clahe ? ctx->clahe_tile_h : 0;
-    if (ctx->rb2_rows == rows && ctx->rb2_row_off == row_off && ctx->rb2_clahe == (int)clahe && ctx->rb2_tile_h == th &&
-        ctx->rb2_strips == n_strips && ctx->n_rowblocks2)
+    if (ctx->pc_rows == rows && ctx->pc_row_off == row_off && ctx->pc_clahe == (int)clahe && ctx->pc_tile_h == th &&
+        ctx->pc_axis == ah && ctx->pc_nsub == nsub && ctx->pc_n_ctas)
         return 0;
-    const uint64_t want_blocks = std::max<uint64_t>(1, (uint64_t)ctx->sm_count * 12 / std::max(1u, n_strips));
-    uint64_t rpb = (rows + want_blocks - 1) / want_blocks;
-    rpb = std::min<uint64_t>(128, std::max<uint64_t>(32, ((rpb + 7) / 8) * 8));
     std::vector<uint64_t> cuts;
     cuts.push_back(0);
     if (clahe && th)
@@ -339,38 +336,41 @@ int prepare_rowblocks2(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool cl
             if (g > row_off && g < row_off + rows) cuts.push_back(g - row_off);
         }
     cuts.push_back(rows);
-    std::vector<uint2> blocks;
+    std::vector<uint32_t> pieces, first;
     uint32_t max_rows = 0;
-    for (size_t i = 0; i + 1 < cuts.size(); ++i)
-        for (uint64_t r = cuts[i]; r < cuts[i + 1]; r += rpb) {
-            const uint64_t e = std::min(cuts[i + 1], r + rpb);
-            blocks.push_back(make_uint2((uint32_t)r, (uint32_t)e));
-            max_rows = std::max(max_rows, (uint32_t)(e - r));
-        }
-    RC(reserve(ctx, ctx->rowblocks2, std::max<size_t>(blocks.size() * sizeof(uint2), 16)));
-    if (!blocks.empty()) {
-        CU(cudaMemcpyAsync(ctx->rowblocks2.p, blocks.data(), blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    ctx->n_rowblocks2 = (uint32_t)blocks.size();
-    ctx->rb2_max_rows = max_rows;
-    ctx->rb2_rows = rows;
-    ctx->rb2_row_off = row_off;
-    ctx->rb2_clahe = clahe;
-    ctx->rb2_tile_h = th;
-    ctx->rb2_strips = n_strips;
+    hpipe_build_pieces(ah->p_strips_h, cuts, (uint32_t)ctx->sm_count, 4u * (uint32_t)nsub, &pieces, &first, &max_rows);
+    RC(reserve(ctx, ctx->pieces, std::max<size_t>(pieces.size() * 4, 16)));
+    RC(reserve(ctx, ctx->cta_first, std::max<size_t>(first.size() * 4, 16)));
+    CU(cudaMemcpyAsync(ctx->pieces.p, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->cta_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->pc_n_ctas = (uint32_t)first.size() - 1;
+    ctx->pc_max_rows = max_rows;
+    ctx->pc_rows = rows;
+    ctx->pc_row_off = row_off;
+    ctx->pc_clahe = clahe;
+    ctx->pc_tile_h = th;
+    ctx->pc_axis = ah;
+    ctx->pc_nsub = nsub;
     return 0;
 }
 
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
     if (!pix16 && ah->pipe && ctx->use_hpipe && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap) {
         const bool clahe = src_kind == HSRC_DN_CLAHE;
-        RC(prepare_rowblocks2(ctx, a.n_rows, row_off, clahe, ah->p_n_strips));
-        HResizeArgs af = a;
-        af.rbw_words = ah->p_rbw_words;
-        KS(SARPRO_STAGE_APPLY, launch_hpipe(af, src_kind, (const HStrip*)ah->pstrips.p, ah->p_n_strips, (const uint2*)ctx->rowblocks2.p,
-                                            ctx->n_rowblocks2, ah->p_oxb, a.hot, ctx->rb2_max_rows, ctx->stream));
-        return 0;
+        // worst-case piece = a whole vertical cell (or the whole raster); 3 sub-blocks when the tables still fit
+        const uint32_t worst_rows = (uint32_t)std::min<uint64_t>(a.n_rows, clahe && ctx->clahe_tile_h ? ctx->clahe_tile_h : a.n_rows);
+        int nsub = ctx->hpipe_nsub ? ctx->hpipe_nsub : 3;
+        if (hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, ah->p_rbw_words) > 227 * 1024) nsub = 2;
+        if (hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, ah->p_rbw_words) <= 227 * 1024) {
+            RC(prepare_pieces(ctx, a.n_rows, row_off, clahe, ah, nsub));
+            HResizeArgs af = a;
+            af.rbw_words = ah->p_rbw_words;
+            KS(SARPRO_STAGE_APPLY, launch_hpipe(af, src_kind, nsub, (const HStrip*)ah->pstrips.p, (const uint32_t*)ctx->pieces.p,
+                                                (const uint32_t*)ctx->cta_first.p, ctx->pc_n_ctas, ah->p_oxb, a.hot, ctx->pc_max_rows,
+                                                ctx->stream));
+            return 0;
+        }
     }
     if (!pix16 && ah->fast && !ctx->force_exact) {
         const bool clahe = src_kind == HSRC_DN_CLAHE;
@@ -866,6 +866,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     if (const char* v = getenv("SARPRO_HPIPE")) ctx->use_hpipe = atoi(v);
+    if (const char* v = getenv("SARPRO_HPIPE_NSUB")) ctx->hpipe_nsub = atoi(v) == 2 ? 2 : (atoi(v) == 3 ? 3 : 0);
     int rc = upload_rgb_luts(ctx);
     if (rc) {
         g_create_error = ctx->err;
@@ -886,7 +887,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
             release(*b);
     for (DevBuf* b : {&ctx->units, &ctx->tile_px, &ctx->col_dx, &ctx->col_omdx, &ctx->col_t, &ctx->row_dy, &ctx->row_omdy,
                       &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts, &ctx->col_m, &ctx->row_sat,
-                      &ctx->rowblocks, &ctx->rowblocks2})
+                      &ctx->rowblocks, &ctx->pieces, &ctx->cta_first})
         release(*b);
     for (auto& kv : ctx->axes) {
         release(kv.second->start); release(kv.second->size); release(kv.second->coef);

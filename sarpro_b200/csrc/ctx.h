@@ -32,6 +32,7 @@ struct AxisPlan {
     bool pipe = false;
     uint32_t p_oxb = 0, p_rbw_words = 0, p_n_strips = 0;
     DevBuf pstrips;
+    std::vector<HStrip> p_strips_h;
     AxisDev dev() const {
         AxisDev d;
         d.start = (const uint32_t*)start.p;
@@ -110,11 +111,13 @@ struct sarpro_ctx {
     uint64_t rb_rows = 0, rb_row_off = 0, rb_tile_h = 0;
     int rb_clahe = -1;
     uint32_t n_rowblocks = 0;
-    // row blocks of kernels_hpipe.cu
-    sarpro::DevBuf rowblocks2;
-    uint64_t rb2_rows = 0, rb2_row_off = 0, rb2_tile_h = 0;
-    int rb2_clahe = -1;
-    uint32_t n_rowblocks2 = 0, rb2_max_rows = 0, rb2_strips = 0;
+    // piece lists of kernels_hpipe.cu (cached per geometry)
+    sarpro::DevBuf pieces, cta_first;
+    uint64_t pc_rows = 0, pc_row_off = 0, pc_tile_h = 0;
+    int pc_clahe = -1, pc_nsub = 0;
+    const void* pc_axis = nullptr;
+    uint32_t pc_n_ctas = 0, pc_max_rows = 0;
+    int hpipe_nsub = 0;  // SARPRO_HPIPE_NSUB: 0 = auto (3 sub-blocks when shared memory allows, else 2)
     int use_hpipe = 1;   // SARPRO_HPIPE=0: previous production kernel (kernels_hfast.cu)
     int force_exact = 0; // SARPRO_FORCE_EXACT=1: generic kernels + exact f64 CLAHE everywhere (validation)
     // geometry caches

@@ -130,9 +130,14 @@ bool hpipe_supported(uint32_t pairs);
 cudaError_t hpipe_build_strips(const uint32_t* start_h, const uint32_t* size_h, uint32_t out_size, uint32_t in_size,
                                uint32_t window, uint32_t max_vec, uint32_t* strip_w_out, std::vector<HStrip>* strips,
                                uint32_t* rbw_words);
-cudaError_t launch_hpipe(const HResizeArgs& a, int src_kind, const HStrip* strips_dev, uint32_t n_strips,
-                         const uint2* rowblocks_dev, uint32_t n_rowblocks, uint32_t strip_w, uint32_t hot,
-                         uint32_t max_rows, cudaStream_t stream);
+// Equal-weight contiguous runs of (strip, rows) pieces, one run per persistent CTA. pieces_flat: 4 words per piece
+// (strip, r0, r1, 0); cta_first: n_ctas + 1 entries. cuts: row positions no piece may straddle (0 ... rows).
+void hpipe_build_pieces(const std::vector<HStrip>& strips, const std::vector<uint64_t>& cuts, uint32_t n_ctas, uint32_t unit,
+                        std::vector<uint32_t>* pieces_flat, std::vector<uint32_t>* cta_first, uint32_t* max_rows);
+size_t hpipe_smem_bytes(int src_kind, int nsub, uint32_t hot, uint32_t max_rows, uint32_t rbw_words);
+cudaError_t launch_hpipe(const HResizeArgs& a, int src_kind, int nsub, const HStrip* strips_dev, const uint32_t* pieces_dev,
+                         const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t strip_w, uint32_t hot, uint32_t max_rows,
+                         cudaStream_t stream);
 // vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
                            void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream);
