@@ -360,7 +360,7 @@ int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, Ax
         const bool clahe = src_kind == HSRC_DN_CLAHE;
         // worst-case piece = a whole vertical cell (or the whole raster); 3 sub-blocks when the tables still fit
         const uint32_t worst_rows = (uint32_t)std::min<uint64_t>(a.n_rows, clahe && ctx->clahe_tile_h ? ctx->clahe_tile_h : a.n_rows);
-        int nsub = ctx->hpipe_nsub ? ctx->hpipe_nsub : 3;
+        int nsub = ctx->hpipe_nsub ? ctx->hpipe_nsub : 2;
         if (hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, ah->p_rbw_words) > 227 * 1024) nsub = 2;
         if (hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, ah->p_rbw_words) <= 227 * 1024) {
             RC(prepare_pieces(ctx, a.n_rows, row_off, clahe, ah, nsub));
@@ -438,38 +438,60 @@ int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_
     std::memcpy(ctx->h_scalars + 8 * b, init, sizeof(init));
     CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
-                                         ctx->sm_count, ctx->hist_variant, ctx->stream));
+                                         ctx->sm_count, ctx->hist_variant >= 0 ? ctx->hist_variant : w.hist_auto, ctx->stream));
     KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
                                             (uint32_t*)w.scalars.p + 2, ctx->stream));
     return 0;
 }
 
-// Pass A for `nb` bands of identical geometry, then one planner round trip for all of them.
-int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
+// Pass-A table shape for the next raster in this slot: the replicated shared histogram covers DN < 1024 (32 replicas,
+// conflict-free), < 2048 (16) or < 4096 (8); brighter pixels take a per-pixel global atomic, which is only cheap
+// when they are rare (< 2e-4 of the pixels, i.e. < 5 % of the warp iterations).
+int choose_hist_variant(const uint32_t* hist) {
+    uint64_t total = 0, ge1k = 0, ge2k = 0;
+    for (int d = 0; d < kDnBins; ++d) total += hist[d];
+    for (int d = 1024; d < kDnBins; ++d) ge1k += hist[d];
+    for (int d = 2048; d < kDnBins; ++d) ge2k += hist[d];
+    const uint64_t lim = total / 5000;
+    return ge1k <= lim ? 12 : (ge2k <= lim ? 11 : 10);
+}
+
+// Host planning of band b from its histogram in pinned memory; ships the DN -> sample / bin table.
+int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
+    BandWs& w = ctx->band[b];
+    w.hist_auto = choose_hist_variant(ctx->h_hist + (size_t)b * kDnBins);
+    plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan);
+    std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+    w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
+    CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// Pass A launches + histogram read-back for `nb` bands of identical geometry; ctx->ev[2 + b] marks band b's histogram
+// as being on the host.
+int run_pass_a(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
     bool any_clahe = false;
     for (int b = 0; b < nb; ++b) any_clahe |= uses_clahe(jobs[b]);
     for (int b = 0; b < nb; ++b) {
         RC(dn_pass_a_launch(ctx, b, jobs[b].dn, jobs[b].rows, jobs[b].cols, any_clahe));
         CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, ctx->band[b].total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->ev[2 + b], ctx->stream));
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Waits for band b's histogram, plans it on the host (the device keeps working on whatever is queued behind it:
+// the other band's pass A, or the previous band's pass B) and queues the table upload.
+int wait_and_plan(sarpro_ctx* ctx, int b, const BandJob& job) {
+    CU(cudaEventSynchronize(ctx->ev[2 + b]));
     ctx->timing.host_syncs++;
-    // plan the bands concurrently on the host (each ~0.1 ms), then ship the tables
-    auto plan_one = [&](int b) {
-        BandWs& w = ctx->band[b];
-        plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, jobs[b].bit_depth, jobs[b].strategy, jobs[b].kind, &w.plan);
-        std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
-        w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
-    };
-    if (nb == 2) {
-        std::thread t1(plan_one, 1);
-        plan_one(0);
-        t1.join();
-    } else {
-        for (int b = 0; b < nb; ++b) plan_one(b);
-    }
-    for (int b = 0; b < nb; ++b)
-        CU(cudaMemcpyAsync(ctx->band[b].lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+    return plan_band_and_upload(ctx, b, job);
+}
+
+// Pass A for `nb` bands, then the planner for all of them (callers that need every plan before pass B).
+int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
+    RC(run_pass_a(ctx, jobs, nb));
+    for (int b = 0; b < nb; ++b) RC(wait_and_plan(ctx, b, jobs[b]));
     return 0;
 }
 
@@ -575,21 +597,21 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     auto run = [&]() -> int {
         RC(run_hpass(ctx, a, src_kind, pix16, ah, 0));
         unsigned char* dst = (unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz;
-        KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream));
+        KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream, a.skip));
         return 0;
     };
     RC(run());
     if (clahe && out8) {
-        // scale_u16_to_u8 is the identity when the blended samples span exactly [0,255]; the first run
-        // assumed so. Verify, and redo the pass with the remap table in the (rare) other case.
-        uint32_t mn, mx;
-        RC(clahe_minmax(ctx, b, &mn, &mx));
-        if (!(mn == 0 && mx == 255)) {
-            RC(upload_remap(ctx, b, mn, mx));
-            a.remap = (const uint8_t*)w.remap.p;
-            a.minmax = nullptr;
-            RC(run());
-        }
+        // scale_u16_to_u8 (autoscale.rs:691-693) is the identity when the blended samples span exactly [0,255]; the
+        // first run assumed so. The check stays on the device: a one-block kernel builds the remap table and an
+        // "identity" flag, and the re-run kernels (always launched, no host round trip) return at once when it is set.
+        RC(reserve(ctx, w.remap, 256 + 16));
+        uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
+        KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream));
+        a.remap = (const uint8_t*)w.remap.p;
+        a.minmax = nullptr;
+        a.skip = flag;
+        RC(run());
     }
     return 0;
 }
@@ -786,8 +808,9 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
     int dnidx[2], ndn = 0;
     for (int b = 0; b < nb; ++b)
         if (integral[b]) { dnjobs[ndn] = jobs[b]; dnidx[ndn] = b; ndn++; }
-    if (ndn == nb && ndn > 0) {
-        RC(run_pass_a_and_plan(ctx, jobs, nb));
+    const bool pipelined = ndn == nb && ndn > 0; // plan band b on the host while the device works on the other band
+    if (pipelined) {
+        RC(run_pass_a(ctx, jobs, nb));
     } else {
         for (int k = 0; k < ndn; ++k) {
             // mixed case: plan band by band in its own slot
@@ -810,6 +833,7 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
                                   stats ? &stats[b] : nullptr));
             continue;
         }
+        if (pipelined) RC(wait_and_plan(ctx, b, jobs[b]));
         if (stats) stats[b] = w.plan.stats;
         RC(dn_run_pass_b(ctx, b, jobs[b], *geom, w.small.p));
     }

@@ -64,6 +64,7 @@ struct BandWs {
     DevBuf scalars; // [0..1] minmax, [2] max_dn, [3] flag
     DevBuf edges, hist4096, f32scan; // general f32 path
     BandPlan plan;
+    int hist_auto = 11;            // pass-A table shape for the next call (see choose_hist_variant)
     uint32_t hot = 0, hot_top = 0; // table range / saturated table word for kernels_hpipe.cu (0 = not eligible)
 };
 
@@ -138,7 +139,7 @@ struct sarpro_ctx {
     cudaEvent_t sev[2 * kMaxStageEvents] = {};
     int sev_stage[kMaxStageEvents] = {};
     int n_sev = 0;
-    int hist_variant = 0;
+    int hist_variant = -1; // SARPRO_HIST_VARIANT; -1 = per band, from the tail of the previous histogram of that slot
     float valid_thresh = 0.f;
     sarpro::CommState* comm = nullptr;
 };

@@ -90,6 +90,7 @@ struct HResizeArgs {
     const uint8_t* remap;  // HSRC_DN_CLAHE u8: 256-entry post-blend remap (scale_u16_to_u8) or nullptr
     ClaheDev clahe;        // HSRC_DN_CLAHE
     uint32_t* minmax;      // HSRC_DN_CLAHE: min/max of the blended samples (before remap)
+    const uint32_t* skip;  // optional device flag: the kernel returns at once when *skip != 0
     // rows to produce: temp row i <- source row (row0 + i), i < n_rows
     uint32_t row0, n_rows;
     void* temp;            // [n_rows][out_cols] same pixel type
@@ -140,7 +141,11 @@ cudaError_t launch_hpipe(const HResizeArgs& a, int src_kind, int nsub, const HSt
                          cudaStream_t stream);
 // vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
-                           void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream);
+                           void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream,
+                           const uint32_t* skip = nullptr);
+// scale_u16_to_u8 decision on the device (autoscale.rs:348-364 over the CLAHE samples): from minmax = {min, max}
+// builds the 256-entry remap and sets skip[0] = 1 when it is the identity (min == 0 && max == 255, or no sample).
+cudaError_t launch_clahe_remap_decide(const uint32_t* minmax, uint8_t* remap256, uint32_t* skip, cudaStream_t stream);
 
 // ---- small-image stages ---------------------------------------------------------------------
 // dst (dcols x drows) zero-filled, src (scols x srows) copied at (pad_left, pad_top). elem = 1 or 2 bytes.

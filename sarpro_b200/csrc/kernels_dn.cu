@@ -519,6 +519,24 @@ cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, 
     return cudaGetLastError();
 }
 
+// autoscale.rs:352-363 for the 256 possible CLAHE samples; same f32 operations as plan.cpp make_u16_to_u8_remap
+__global__ void __launch_bounds__(256) k_clahe_remap_decide(const uint32_t* __restrict__ minmax, uint8_t* __restrict__ remap,
+                                                            uint32_t* __restrict__ skip) {
+    uint32_t mn = minmax[0], mx = minmax[1];
+    if (mn == 0xffffffffu) { mn = 0; mx = 0; }
+    const bool identity = (mn == 0 && mx == 255) || (mn == 0 && mx == 0);
+    const float fmn = (float)mn, fmx = (float)mx;
+    const float scale = fmx > fmn ? __fdiv_rn(255.0f, __fsub_rn(fmx, fmn)) : 1.0f;
+    float val = roundf(__fmul_rn(__fsub_rn((float)threadIdx.x, fmn), scale));
+    val = val < 0.0f ? 0.0f : (val > 255.0f ? 255.0f : val);
+    remap[threadIdx.x] = (uint8_t)val;
+    if (threadIdx.x == 0) skip[0] = identity ? 1u : 0u;
+}
+cudaError_t launch_clahe_remap_decide(const uint32_t* minmax, uint8_t* remap256, uint32_t* skip, cudaStream_t stream) {
+    k_clahe_remap_decide<<<1, 256, 0, stream>>>(minmax, remap256, skip);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(512) k_minmax_u16(const uint16_t* __restrict__ data, uint64_t n,
                                                     uint32_t* __restrict__ minmax) {
     uint32_t mn = 0xffffffffu, mx = 0;

@@ -71,6 +71,7 @@ template <int SRC, int MAXP>
 __global__ void __launch_bounds__(256, (SRC == HSRC_DN_CLAHE ? 2 : 3)) k_hfast(HResizeArgs a, const HStrip* __restrict__ strips,
                                                const uint2* __restrict__ rowblocks, uint32_t strip_w) {
     extern __shared__ uint4 smem4[];
+    if (a.skip && *a.skip) return;
     unsigned char* const smem = reinterpret_cast<unsigned char*>(smem4);
     constexpr uint32_t kOffRows = SRC == HSRC_DN_CLAHE ? kOffRowsClahe : (SRC == HSRC_DN_LUT ? kOffRowsLut : kOffRowsImage);
     uint4* const s_rows = reinterpret_cast<uint4*>(smem + kOffRows);
