@@ -203,7 +203,7 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
     if (ctx->axes.size() > 64) { // bounded cache
         for (auto& kv : ctx->axes) {
             release(kv.second->start); release(kv.second->size); release(kv.second->coef);
-            release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips);
+            release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips); release(kv.second->sstrips);
             delete kv.second;
         }
         ctx->axes.clear();
@@ -249,11 +249,18 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
             const uint32_t tile_w = (in + kClaheTiles - 1) / kClaheTiles;
             const uint32_t max_vec = src_kind == HSRC_DN_CLAHE ? std::min(256u, tile_w / 8) : 256u;
             std::vector<HStrip>& ps = ap->p_strips_h;
-            if (hpipe_build_strips(h.start.data(), h.size.data(), out, in, h.window, max_vec, &ap->p_oxb, &ps, &ap->p_rbw_words) ==
+            if (hpipe_build_strips(h.start.data(), h.size.data(), out, in, h.window, max_vec, 256, &ap->p_oxb, &ps, &ap->p_rbw_words) ==
                 cudaSuccess) {
                 ap->p_n_strips = (uint32_t)ps.size();
                 rc = upload_vec(ctx, ap->pstrips, ps.data(), ps.size() * sizeof(HStrip));
                 ap->pipe = rc == 0;
+            }
+            std::vector<HStrip>& ss = ap->s_strips_h;
+            if (!rc && hpipe_build_strips(h.start.data(), h.size.data(), out, in, h.window, max_vec, 128, &ap->s_oxb, &ss,
+                                          &ap->s_rbw_words) == cudaSuccess) {
+                ap->s_n_strips = (uint32_t)ss.size();
+                rc = upload_vec(ctx, ap->sstrips, ss.data(), ss.size() * sizeof(HStrip));
+                ap->spec = rc == 0;
             }
         }
     }
@@ -338,7 +345,8 @@ int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe,
     cuts.push_back(rows);
     std::vector<uint32_t> pieces, first;
     uint32_t max_rows = 0;
-    hpipe_build_pieces(ah->p_strips_h, cuts, (uint32_t)ctx->sm_count, 4u * (uint32_t)nsub, &pieces, &first, &max_rows);
+    hpipe_build_pieces(nsub == 12 ? ah->s_strips_h : ah->p_strips_h, cuts, (uint32_t)ctx->sm_count, nsub == 12 ? 8u : 4u * (uint32_t)nsub,
+                       &pieces, &first, &max_rows);
     RC(reserve(ctx, ctx->pieces, std::max<size_t>(pieces.size() * 4, 16)));
     RC(reserve(ctx, ctx->cta_first, std::max<size_t>(first.size() * 4, 16)));
     CU(cudaMemcpyAsync(ctx->pieces.p, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -360,15 +368,20 @@ int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, Ax
         const bool clahe = src_kind == HSRC_DN_CLAHE;
         // worst-case piece = a whole vertical cell (or the whole raster); 3 sub-blocks when the tables still fit
         const uint32_t worst_rows = (uint32_t)std::min<uint64_t>(a.n_rows, clahe && ctx->clahe_tile_h ? ctx->clahe_tile_h : a.n_rows);
-        int nsub = ctx->hpipe_nsub ? ctx->hpipe_nsub : 2;
-        if (hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, ah->p_rbw_words) > 227 * 1024) nsub = 2;
-        if (hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, ah->p_rbw_words) <= 227 * 1024) {
+        // 12 = warp-specialised kernel (faster for the LUT strategies, where the taps weigh as much as the per-pixel stage);
+        // 2 / 3 = symmetric sub-blocks (faster for CLAHE)
+        int nsub = ctx->hpipe_nsub ? ctx->hpipe_nsub : (clahe ? 2 : 12);
+        if (nsub == 12 && !ah->spec) nsub = 2;
+        const uint32_t rbw = nsub == 12 ? ah->s_rbw_words : ah->p_rbw_words;
+        if (nsub == 3 && hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, rbw) > 227 * 1024) nsub = 2;
+        if (hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, rbw) <= 227 * 1024) {
             RC(prepare_pieces(ctx, a.n_rows, row_off, clahe, ah, nsub));
             HResizeArgs af = a;
-            af.rbw_words = ah->p_rbw_words;
-            KS(SARPRO_STAGE_APPLY, launch_hpipe(af, src_kind, nsub, (const HStrip*)ah->pstrips.p, (const uint32_t*)ctx->pieces.p,
-                                                (const uint32_t*)ctx->cta_first.p, ctx->pc_n_ctas, ah->p_oxb, a.hot, ctx->pc_max_rows,
-                                                ctx->stream));
+            af.rbw_words = rbw;
+            const bool sp = nsub == 12;
+            KS(SARPRO_STAGE_APPLY, launch_hpipe(af, src_kind, nsub, (const HStrip*)(sp ? ah->sstrips.p : ah->pstrips.p),
+                                                (const uint32_t*)ctx->pieces.p, (const uint32_t*)ctx->cta_first.p, ctx->pc_n_ctas,
+                                                sp ? ah->s_oxb : ah->p_oxb, a.hot, ctx->pc_max_rows, ctx->stream));
             return 0;
         }
     }
@@ -890,7 +903,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     if (const char* v = getenv("SARPRO_HPIPE")) ctx->use_hpipe = atoi(v);
-    if (const char* v = getenv("SARPRO_HPIPE_NSUB")) ctx->hpipe_nsub = atoi(v) == 2 ? 2 : (atoi(v) == 3 ? 3 : 0);
+    if (const char* v = getenv("SARPRO_HPIPE_NSUB")) ctx->hpipe_nsub = (atoi(v) == 2 || atoi(v) == 3 || atoi(v) == 12) ? atoi(v) : 0;
     int rc = upload_rgb_luts(ctx);
     if (rc) {
         g_create_error = ctx->err;
@@ -915,7 +928,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
         release(*b);
     for (auto& kv : ctx->axes) {
         release(kv.second->start); release(kv.second->size); release(kv.second->coef);
-        release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips);
+        release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips); release(kv.second->sstrips);
         delete kv.second;
     }
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);

@@ -33,6 +33,11 @@ struct AxisPlan {
     uint32_t p_oxb = 0, p_rbw_words = 0, p_n_strips = 0;
     DevBuf pstrips;
     std::vector<HStrip> p_strips_h;
+    // warp-specialised kernel: output strips of <= 128 columns
+    bool spec = false;
+    uint32_t s_oxb = 0, s_rbw_words = 0, s_n_strips = 0;
+    DevBuf sstrips;
+    std::vector<HStrip> s_strips_h;
     AxisDev dev() const {
         AxisDev d;
         d.start = (const uint32_t*)start.p;

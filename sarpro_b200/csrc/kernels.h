@@ -129,8 +129,8 @@ cudaError_t launch_hfast(const HResizeArgs& a, int src_kind, const HStrip* strip
 // strip's source span in 8-sample vectors (CLAHE: <= tile_w / 8 so a strip meets at most one cell boundary).
 bool hpipe_supported(uint32_t pairs);
 cudaError_t hpipe_build_strips(const uint32_t* start_h, const uint32_t* size_h, uint32_t out_size, uint32_t in_size,
-                               uint32_t window, uint32_t max_vec, uint32_t* strip_w_out, std::vector<HStrip>* strips,
-                               uint32_t* rbw_words);
+                               uint32_t window, uint32_t max_vec, uint32_t max_w, uint32_t* strip_w_out,
+                               std::vector<HStrip>* strips, uint32_t* rbw_words);
 // Equal-weight contiguous runs of (strip, rows) pieces, one run per persistent CTA. pieces_flat: 4 words per piece
 // (strip, r0, r1, 0); cta_first: n_ctas + 1 entries. cuts: row positions no piece may straddle (0 ... rows).
 void hpipe_build_pieces(const std::vector<HStrip>& strips, const std::vector<uint64_t>& cuts, uint32_t n_ctas, uint32_t unit,
