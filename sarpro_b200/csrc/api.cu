@@ -390,12 +390,15 @@ int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, Ax
         RC(prepare_rowblocks(ctx, a.n_rows, row_off, clahe, ah->f_n_strips));
         HResizeArgs af = a;
         af.rbw_words = ah->f_rbw_words;
-        KS(SARPRO_STAGE_APPLY, launch_hfast(af, src_kind, (const HStrip*)ah->fstrips.p, ah->f_n_strips, (const uint2*)ctx->rowblocks.p,
-                                            ctx->n_rowblocks, ah->f_oxb, ctx->stream));
+        // the device-gated re-run (a.skip) is accounted under OTHER: it normally returns at once
+        KS(a.skip ? SARPRO_STAGE_OTHER : SARPRO_STAGE_APPLY,
+           launch_hfast(af, src_kind, (const HStrip*)ah->fstrips.p, ah->f_n_strips, (const uint2*)ctx->rowblocks.p, ctx->n_rowblocks,
+                        ah->f_oxb, ctx->stream));
         return 0;
     }
-    KS(SARPRO_STAGE_APPLY, launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw,
-                                                  ah->smem, ctx->sm_count, ctx->stream));
+    KS(a.skip ? SARPRO_STAGE_OTHER : SARPRO_STAGE_APPLY,
+       launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem, ctx->sm_count,
+                              ctx->stream));
     return 0;
 }
 
@@ -610,7 +613,8 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     auto run = [&]() -> int {
         RC(run_hpass(ctx, a, src_kind, pix16, ah, 0));
         unsigned char* dst = (unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz;
-        KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream, a.skip));
+        KS(a.skip ? SARPRO_STAGE_OTHER : SARPRO_STAGE_VRESIZE,
+           launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream, a.skip));
         return 0;
     };
     RC(run());
