@@ -111,7 +111,7 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
         const uint64_t sw = (((cols + n_strips - 1) / n_strips) + 7) & ~uint64_t(7);
         for (uint64_t c0 = 0; c0 < cols; c0 += sw) {
             const uint64_t c1 = std::min(cols, c0 + sw);
-            const uint64_t chunk = std::max<uint64_t>(1, target_px / (c1 - c0));
+            const uint64_t chunk = std::max<uint64_t>(128, (target_px / (c1 - c0) + 64) / 128 * 128);
             for (uint64_t r = own0; r < own1; r += chunk)
                 units.push_back(HistUnit{(uint32_t)r, (uint32_t)std::min(own1, r + chunk), (uint32_t)c0, (uint32_t)c1, 0u, 0u});
         }
@@ -126,7 +126,8 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
             for (uint64_t tx = 0; tx < kClaheTiles; ++tx) {
                 const uint64_t c0 = tx * g.tile_w, c1 = std::min((tx + 1) * g.tile_w, cols);
                 if (c0 >= c1) continue;
-                const uint64_t chunk = std::max<uint64_t>(1, target_px / (c1 - c0));
+                // whole multiples of 128 rows: a warp of the pass-A kernel keeps 4 rows in flight, 32 warps per CTA
+                const uint64_t chunk = std::max<uint64_t>(128, (target_px / (c1 - c0) + 64) / 128 * 128);
                 for (uint64_t r = a; r < b; r += chunk)
                     units.push_back(HistUnit{(uint32_t)(r - row_off), (uint32_t)(std::min(b, r + chunk) - row_off),
                                              (uint32_t)c0, (uint32_t)c1, (uint32_t)(ty * kClaheTiles + tx), 0u});
@@ -453,8 +454,10 @@ int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_
     const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0u};
     std::memcpy(ctx->h_scalars + 8 * b, init, sizeof(init));
     CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync((uint32_t*)w.scalars.p + 4, 0, 16, ctx->stream)); // [4]: work-unit counter of pass A
     KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
-                                         ctx->sm_count, ctx->hist_variant >= 0 ? ctx->hist_variant : w.hist_auto, ctx->stream));
+                                         ctx->sm_count, ctx->hist_variant >= 0 ? ctx->hist_variant : w.hist_auto, ctx->stream,
+                                         (uint32_t*)w.scalars.p + 4));
     KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
                                             (uint32_t*)w.scalars.p + 2, ctx->stream));
     return 0;
@@ -469,7 +472,7 @@ int choose_hist_variant(const uint32_t* hist) {
     for (int d = 1024; d < kDnBins; ++d) ge1k += hist[d];
     for (int d = 2048; d < kDnBins; ++d) ge2k += hist[d];
     const uint64_t lim = total / 5000;
-    return ge1k <= lim ? 12 : (ge2k <= lim ? 11 : 10);
+    return ge1k <= lim ? 22 : (ge2k <= lim ? 21 : 20);
 }
 
 // Host planning of band b from its histogram in pinned memory; ships the DN -> sample / bin table.

@@ -69,7 +69,7 @@ struct BandWs {
     DevBuf scalars; // [0..1] minmax, [2] max_dn, [3] flag
     DevBuf edges, hist4096, f32scan; // general f32 path
     BandPlan plan;
-    int hist_auto = 11;            // pass-A table shape for the next call (see choose_hist_variant)
+    int hist_auto = 21;            // pass-A table shape for the next call (see choose_hist_variant)
     uint32_t hot = 0, hot_top = 0; // table range / saturated table word for kernels_hpipe.cu (0 = not eligible)
 };
 

@@ -18,8 +18,9 @@ struct HistUnit {
 
 // ---- pass A: DN histograms ----------------------------------------------------------------
 // tile_hist: [n_tiles][65536] u32, zeroed by the caller. Counts every pixel of every unit.
+// counter: one zeroed device word (work-unit counter of the third-generation kernel, variants >= 20); may be null.
 cudaError_t launch_dn_hist(const uint16_t* dn, uint64_t cols, const HistUnit* units_dev, uint32_t n_units,
-                           uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream);
+                           uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream, uint32_t* counter = nullptr);
 // total[dn] = sum_t tile_hist[t][dn]; max_dn[0] = highest DN with a non-zero total (atomicMax).
 cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint32_t* total, uint32_t* max_dn,
                               cudaStream_t stream);

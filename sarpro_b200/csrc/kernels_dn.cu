@@ -215,6 +215,137 @@ __global__ void __launch_bounds__(1024, 1) k_dn_hist2(const uint16_t* __restrict
     }
 }
 
+// ---- third generation: four rows in flight per warp, loads software-pipelined one step ahead, units fetched
+// from a device counter (no tail imbalance). Needs cols % 8 == 0 (all rows of a unit share the vector phase).
+template <int HOT, int LOGC>
+__global__ void __launch_bounds__(1024, 1) k_dn_hist3(const uint16_t* __restrict__ dn, uint64_t cols,
+                                                      const HistUnit* __restrict__ units, uint32_t n_units,
+                                                      uint32_t* __restrict__ tile_hist, uint32_t* __restrict__ counter) {
+    extern __shared__ uint32_t sh[];
+    __shared__ uint32_t s_unit;
+    constexpr uint32_t NCOPY = 1u << LOGC;
+    constexpr uint32_t kHotMask = ~(uint32_t)(HOT - 1) & 0xffffu;
+    constexpr int R = 4; // rows in flight per warp
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sh) + (lane & (NCOPY - 1)) * 4u;
+    for (uint32_t i = tid; i < (uint32_t)HOT * NCOPY; i += 1024) sh[i] = 0;
+
+    const uint16_t* dn_al = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(dn) & ~uintptr_t(15));
+    const uint32_t eoff = (uint32_t)(dn - dn_al);
+    const uint4* const dn4 = reinterpret_cast<const uint4*>(dn_al);
+    const uint32_t cols8 = (uint32_t)(cols >> 3);
+
+    for (;;) {
+        __syncthreads(); // table zeroed / previous flush done; s_unit free
+        if (tid == 0) s_unit = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= n_units) break;
+        const HistUnit un = units[u];
+        uint32_t* __restrict__ gh = tile_hist + (size_t)un.tile * 65536u;
+        const uint32_t off = un.c0 + eoff, seg = un.c1 - un.c0;
+        const uint32_t vf0 = (off + 7) >> 3, vf1 = (off + seg) >> 3; // full vectors [vf0, vf1) relative to the row start
+        const uint32_t nfull = vf1 > vf0 ? vf1 - vf0 : 0;
+
+        auto add_px = [&](uint32_t d) {
+            if (d < (uint32_t)HOT) red_shared_inc(sbase + (d << (LOGC + 2)));
+            else atomicAdd(&gh[d], 1u);
+        };
+        auto add_vec = [&](const uint4& q) {
+            if (((q.x | q.y | q.z | q.w) & (kHotMask * 0x10001u)) == 0) {
+                red_shared_inc(sbase + (q.x & 0xffffu) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.x >> 16) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.y & 0xffffu) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.y >> 16) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.z & 0xffffu) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.z >> 16) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.w & 0xffffu) * (4u * NCOPY));
+                red_shared_inc(sbase + (q.w >> 16) * (4u * NCOPY));
+            } else {
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { add_px(w[k] & 0xffffu); add_px(w[k] >> 16); }
+            }
+        };
+
+        for (uint32_t rbase = un.r0 + warp; rbase < un.r1; rbase += 32 * R) {
+            // vector index of (row j, full vector 0); rows beyond the unit are skipped
+            uint32_t vb[R];
+            bool rok[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const uint32_t r = rbase + 32u * j;
+                rok[j] = r < un.r1;
+                vb[j] = (rok[j] ? r : un.r0) * cols8 + vf0; // < 2^32 vectors for any raster in HBM
+            }
+            if (nfull) {
+                uint4 q[R], qn[R];
+                auto load = [&](uint4* dst, uint32_t i) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if (rok[j] && i < nfull) dst[j] = ld_stream_u4(dn4 + (size_t)(vb[j] + i));
+                };
+                load(q, lane);
+                for (uint32_t i = lane; i < nfull + 0u; i += 32) {
+                    load(qn, i + 32);
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if (rok[j]) add_vec(q[j]);
+#pragma unroll
+                    for (int j = 0; j < R; ++j) q[j] = qn[j];
+                }
+            }
+            // ragged ends: lanes 0..7 take (row j, side) = (lane >> 1, lane & 1)
+            if (lane < 2 * R) {
+                const int j = lane >> 1;
+                const uint32_t r = rbase + 32u * j;
+                if (r < un.r1) {
+                    const uint64_t rs = (uint64_t)r * cols; // element index of the row start (aligned view)
+                    uint64_t a, b;
+                    if (nfull) {
+                        a = (lane & 1) ? rs + ((uint64_t)vf1 << 3) : rs + off;
+                        b = (lane & 1) ? rs + off + seg : rs + ((uint64_t)vf0 << 3);
+                    } else {
+                        a = rs + off;
+                        b = (lane & 1) ? a : rs + off + seg;
+                    }
+                    for (uint64_t e = a; e < b; ++e) add_px(dn_al[e]);
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = tid; b < (uint32_t)HOT; b += 1024) {
+            uint32_t s = 0;
+            uint4* p = reinterpret_cast<uint4*>(&sh[b << LOGC]);
+#pragma unroll
+            for (uint32_t c = 0; c < NCOPY / 4; ++c) {
+                const uint32_t cc = (c + b) & (NCOPY / 4 - 1);
+                const uint4 t = p[cc];
+                s += t.x + t.y + t.z + t.w;
+                p[cc] = make_uint4(0, 0, 0, 0);
+            }
+            if (s) atomicAdd(&gh[b], s);
+        }
+    }
+}
+
+template <int HOT, int LOGC>
+static cudaError_t launch_dn_hist3_t(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
+                                     uint32_t* tile_hist, uint32_t* counter, int sm_count, cudaStream_t stream) {
+    const size_t smem = (size_t)HOT * (1u << LOGC) * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_dn_hist3<HOT, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    uint32_t grid = (uint32_t)sm_count;
+    if (grid > n_units) grid = n_units;
+    if (grid == 0) return cudaSuccess;
+    k_dn_hist3<HOT, LOGC><<<grid, 1024, smem, stream>>>(dn, cols, units, n_units, tile_hist, counter);
+    return cudaGetLastError();
+}
+
 template <int HOT, int LOGC>
 static cudaError_t launch_dn_hist2_t(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
                                      uint32_t* tile_hist, int sm_count, cudaStream_t stream) {
@@ -233,8 +364,12 @@ static cudaError_t launch_dn_hist2_t(const uint16_t* dn, uint64_t cols, const Hi
 }
 
 cudaError_t launch_dn_hist(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
-                           uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream) {
+                           uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream, uint32_t* counter) {
+    if (variant >= 20 && (!counter || cols % 8 != 0)) variant -= 10; // third generation needs the unit counter and cols % 8 == 0
     switch (variant) {
+    case 20: return launch_dn_hist3_t<4096, 3>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream);
+    case 21: return launch_dn_hist3_t<2048, 4>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream);
+    case 22: return launch_dn_hist3_t<1024, 5>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream);
     case 10: return launch_dn_hist2_t<4096, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
     case 11: return launch_dn_hist2_t<2048, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);
     case 12: return launch_dn_hist2_t<1024, 5>(dn, cols, units, n_units, tile_hist, sm_count, stream);
