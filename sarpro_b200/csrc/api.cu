@@ -186,6 +186,7 @@ ClaheDev clahe_dev(sarpro_ctx* ctx, int b) {
     cl.col_m = (const int32_t*)ctx->col_m.p;
     cl.row_sat = (const uint16_t*)ctx->row_sat.p;
     cl.inv2tw = ctx->clahe_tile_w ? (float)(1.0 / (2.0 * (double)ctx->clahe_tile_w)) : 0.f;
+    cl.tile_w = (uint32_t)ctx->clahe_tile_w;
     cl.tiles_x = kClaheTiles;
     return cl;
 }

@@ -29,6 +29,20 @@ __device__ __noinline__ uint32_t clahe_exact_sample_impl(const uint16_t* __restr
     v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
     return (uint32_t)__dmul_rn(v, 255.0);
 }
+// Column geometry of autoscale.rs:308-318 for global column g, bit-identical to k_clahe_axis (same f64 operations):
+// returns dx, 1-dx and the clamped tile pair (t0, t1).
+__device__ __forceinline__ void clahe_axis_exact(uint32_t g, uint32_t tile_size, uint32_t n_tiles, double* d, double* omd,
+                                                 uint32_t* t0, uint32_t* t1) {
+    const double f = __dsub_rn(__ddiv_rn((double)g, (double)tile_size), 0.5);
+    const long long t = (long long)fmax(floor(f), 0.0);
+    const double dd = __dsub_rn(f, (double)t);
+    const long long hi = (long long)n_tiles - 1;
+    *d = dd;
+    *omd = __dsub_rn(1.0, dd);
+    *t0 = (uint32_t)(t < 0 ? 0 : (t > hi ? hi : t));
+    *t1 = (uint32_t)((t + 1) < 0 ? 0 : ((t + 1) > hi ? hi : (t + 1)));
+}
+
 #define clahe_exact_sample(LUT, CL, R, C, D) \
     clahe_exact_sample_impl((LUT), (CL).cdf, (CL).col_dx, (CL).col_omdx, (CL).col_t, (CL).row_dy, (CL).row_omdy, (CL).row_t, (R), (C), (D))
 

@@ -325,33 +325,24 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     }
     // ---- 3. scale_u16_to_u8 decision for CLAHE: global sample min/max --------------------------------------------
     if (clahe) {
-        // scalars[0] = min, [1] = max per band -> pack {max, ~min} so that one all-reduce(max) serves both
-        uint32_t packed[4];
-        for (int b = 0; b < 2; ++b)
-            CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b, ctx->band[b].scalars.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        ctx->timing.host_syncs++;
-        for (int b = 0; b < 2; ++b) {
-            packed[2 * b] = ctx->h_scalars[8 * b + 1];
-            packed[2 * b + 1] = ~ctx->h_scalars[8 * b];
-        }
+        // scalars[0] = min, [1] = max per band -> pack {max, ~min} so that one all-reduce(max) serves both. Everything
+        // stays on the device: the merged extrema feed the remap/"identity" kernel, and the re-run of the horizontal
+        // pass is always launched but returns at once when the re-stretch is the identity (no host round trip).
         RC(reserve(ctx, ctx->rgbsel, 64));
         uint32_t* dpk = (uint32_t*)ctx->rgbsel.p + 4;
-        CU(cudaMemcpyAsync(dpk, packed, 16, cudaMemcpyHostToDevice, ctx->stream));
+        KS(SARPRO_STAGE_COMM, launch_minmax_pack((uint32_t*)ctx->band[0].scalars.p, (uint32_t*)ctx->band[1].scalars.p, dpk, 0, ctx->stream));
         NC(api.AllReduce(dpk, dpk, 4, kNcclUint32, kNcclMax, cs->comm, ctx->stream));
-        CU(cudaMemcpyAsync(packed, dpk, 16, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        ctx->timing.host_syncs++;
+        KS(SARPRO_STAGE_COMM, launch_minmax_pack((uint32_t*)ctx->band[0].scalars.p, (uint32_t*)ctx->band[1].scalars.p, dpk, 1, ctx->stream));
         for (int b = 0; b < 2; ++b) {
-            if (!ctx->band[b].plan.any_valid) continue;
-            uint32_t mx = packed[2 * b], mn = ~packed[2 * b + 1];
-            if (mn == 0xffffffffu) { mn = 0; mx = 0; }
-            if (!(mn == 0 && mx == 255)) { // identity assumption failed (rare): redo with the remap table
-                RC(upload_remap(ctx, b, mn, mx));
-                args[b].remap = (const uint8_t*)ctx->band[b].remap.p;
-                args[b].minmax = nullptr;
-                RC(run_hpass(ctx, args[b], src_kind, 0, ah, h0));
-            }
+            BandWs& w = ctx->band[b];
+            if (!w.plan.any_valid) continue;
+            RC(reserve(ctx, w.remap, 256 + 16));
+            uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
+            KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream));
+            args[b].remap = (const uint8_t*)w.remap.p;
+            args[b].minmax = nullptr;
+            args[b].skip = flag;
+            RC(run_hpass(ctx, args[b], src_kind, 0, ah, h0));
         }
     }
     // ---- vertical pass for the owned output rows, then 4. merge the rows of all ranks -------------------------------

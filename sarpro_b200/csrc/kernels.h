@@ -50,6 +50,7 @@ struct ClaheDev {
     const int32_t* col_m;    // [cols]  2c - tile_w*(2tx+1)
     const uint16_t* row_sat; // [local rows]
     float inv2tw;            // 1 / (2*tile_w)
+    uint32_t tile_w;         // CLAHE tile width (autoscale.rs:237)
     int tiles_x;
 };
 
@@ -62,6 +63,8 @@ cudaError_t launch_apply_lut(const uint16_t* dn, uint64_t n, const uint16_t* lut
 cudaError_t launch_apply_clahe(const uint16_t* dn, uint32_t rows, uint32_t cols, const uint16_t* lut, ClaheDev cl,
                                int max_val, uint8_t* out_u8, uint16_t* out_u16, uint32_t* minmax, int sm_count,
                                cudaStream_t stream);
+// packs (unpack = 0) / unpacks (1) {max, ~min} of two bands' {min, max} words into / from a 4-word vector
+cudaError_t launch_minmax_pack(uint32_t* scalars0, uint32_t* scalars1, uint32_t* packed4, int unpack, cudaStream_t stream);
 // in-place u8 remap through a 256-entry table
 cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, int sm_count, cudaStream_t stream);
 // min/max of a u16 array + u16 -> u8 remap (scale_u16_to_u8, autoscale.rs:348-364)

@@ -672,6 +672,23 @@ cudaError_t launch_clahe_remap_decide(const uint32_t* minmax, uint8_t* remap256,
     return cudaGetLastError();
 }
 
+// {max, ~min} of both bands in one 4-word vector, so that a single all-reduce(max) merges the ranks' CLAHE sample
+// extrema; unpack writes the merged values back to the bands' {min, max} words.
+__global__ void k_minmax_pack(uint32_t* __restrict__ s0, uint32_t* __restrict__ s1, uint32_t* __restrict__ packed, int unpack) {
+    uint32_t* s = threadIdx.x == 0 ? s0 : s1;
+    if (!unpack) {
+        packed[2 * threadIdx.x] = s[1];
+        packed[2 * threadIdx.x + 1] = ~s[0];
+    } else {
+        s[1] = packed[2 * threadIdx.x];
+        s[0] = ~packed[2 * threadIdx.x + 1];
+    }
+}
+cudaError_t launch_minmax_pack(uint32_t* scalars0, uint32_t* scalars1, uint32_t* packed4, int unpack, cudaStream_t stream) {
+    k_minmax_pack<<<1, 2, 0, stream>>>(scalars0, scalars1, packed4, unpack);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(512) k_minmax_u16(const uint16_t* __restrict__ data, uint64_t n,
                                                     uint32_t* __restrict__ minmax) {
     uint32_t mn = 0xffffffffu, mx = 0;
