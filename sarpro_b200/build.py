@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsarpro_gpu.so")
-SOURCES = ["api.cu", "api_f32.cu", "comm.cu", "kernels_dn.cu", "kernels_resize.cu", "kernels_hfast.cu", "kernels_hpipe.cu", "kernels_small.cu", "kernels_f32.cu", "plan.cpp", "plan_f32.cpp"]
+SOURCES = ["api.cu", "api_f32.cu", "comm.cu", "kernels_dn.cu", "kernels_resize.cu", "kernels_hfast.cu", "kernels_hpipe.cu", "kernels_hmma.cu", "kernels_small.cu", "kernels_f32.cu", "plan.cpp", "plan_f32.cpp"]
 HEADERS = ["ctx.h", "kernels.h", "plan.h", "common.cuh", "clahe_exact.cuh", os.path.join("..", "..", "include", "sarpro_gpu.h")]
 
 NVCC_FLAGS = [
@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "--fmad=false",            # Rust never contracts a*b+c; keep f32/f64 arithmetic IEEE op-by-op
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fno-fast-math,-Wall",
     "-Xptxas", "-v" if os.environ.get("SARPRO_PTXAS_V") else "-O3",
-]
+] + os.environ.get("SARPRO_NVCC_EXTRA", "").split()
 
 
 def nvcc() -> str:

@@ -162,13 +162,15 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
         RC(reserve(ctx, ctx->row_omdy, rows * 8));
         RC(reserve(ctx, ctx->row_t, rows * 2));
         RC(reserve(ctx, ctx->col_m, cols * 4));
-        RC(reserve(ctx, ctx->row_sat, rows * 2));
+        RC(reserve(ctx, ctx->row_sat, rows * 4)); // sat, then sat1
         ctx->clahe_tile_w = g.tile_w;
         ctx->clahe_tile_h = g.tile_h;
         KL(launch_clahe_axis((uint32_t)cols, 0, (uint32_t)g.tile_w, kClaheTiles, (double*)ctx->col_dx.p,
                              (double*)ctx->col_omdx.p, (uint16_t*)ctx->col_t.p, (int32_t*)ctx->col_m.p, nullptr, ctx->stream));
         KL(launch_clahe_axis((uint32_t)rows, (uint32_t)row_off, (uint32_t)g.tile_h, kClaheTiles, (double*)ctx->row_dy.p,
-                             (double*)ctx->row_omdy.p, (uint16_t*)ctx->row_t.p, nullptr, (uint16_t*)ctx->row_sat.p, ctx->stream));
+                             (double*)ctx->row_omdy.p, (uint16_t*)ctx->row_t.p, nullptr, (uint16_t*)ctx->row_sat.p, ctx->stream,
+                             (uint16_t*)ctx->row_sat.p + rows));
+        ctx->clahe_rows = rows;
     }
     return 0;
 }
@@ -185,6 +187,7 @@ ClaheDev clahe_dev(sarpro_ctx* ctx, int b) {
     cl.row_t = (const uint16_t*)ctx->row_t.p;
     cl.col_m = (const int32_t*)ctx->col_m.p;
     cl.row_sat = (const uint16_t*)ctx->row_sat.p;
+    cl.row_sat1 = (const uint16_t*)ctx->row_sat.p + ctx->clahe_rows;
     cl.inv2tw = ctx->clahe_tile_w ? (float)(1.0 / (2.0 * (double)ctx->clahe_tile_w)) : 0.f;
     cl.tile_w = (uint32_t)ctx->clahe_tile_w;
     cl.tiles_x = kClaheTiles;
@@ -206,6 +209,8 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
         for (auto& kv : ctx->axes) {
             release(kv.second->start); release(kv.second->size); release(kv.second->coef);
             release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips); release(kv.second->sstrips);
+        release(kv.second->m_btab); release(kv.second->m_ntile); release(kv.second->m_strips);
+            release(kv.second->m_btab); release(kv.second->m_ntile); release(kv.second->m_strips);
             delete kv.second;
         }
         ctx->axes.clear();
@@ -263,6 +268,22 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
                 ap->s_n_strips = (uint32_t)ss.size();
                 rc = upload_vec(ctx, ap->sstrips, ss.data(), ss.size() * sizeof(HStrip));
                 ap->spec = rc == 0;
+            }
+        }
+        if (!rc && !wide && src_kind != HSRC_IMAGE) {
+            const uint32_t tile_w = (in + kClaheTiles - 1) / kClaheTiles;
+            HMmaPlanHost mp;
+            if (hmma_build_plan(h.start.data(), h.size.data(), h.coef.data(), h.window, out, in,
+                                src_kind == HSRC_DN_CLAHE ? tile_w : 0u, &mp)) {
+                rc = upload_vec(ctx, ap->m_btab, mp.btab.data(), mp.btab.size() * sizeof(uint4));
+                if (!rc) rc = upload_vec(ctx, ap->m_ntile, mp.ntile.data(), mp.ntile.size() * sizeof(int4));
+                if (!rc) rc = upload_vec(ctx, ap->m_strips, mp.strips.data(), mp.strips.size() * sizeof(uint4));
+                ap->m_weights_h = mp.weights;
+                ap->mma = rc == 0;
+                if (!rc) { // the plan vectors are temporaries
+                    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+                    if (e != cudaSuccess) rc = fail(ctx, SARPRO_ERR_CUDA, "CUDA error %s", cudaGetErrorName(e));
+                }
             }
         }
     }
@@ -347,8 +368,11 @@ int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe,
     cuts.push_back(rows);
     std::vector<uint32_t> pieces, first;
     uint32_t max_rows = 0;
-    hpipe_build_pieces(nsub == 12 ? ah->s_strips_h : ah->p_strips_h, cuts, (uint32_t)ctx->sm_count, nsub == 12 ? 8u : 4u * (uint32_t)nsub,
-                       &pieces, &first, &max_rows);
+    if (nsub == 100) // tensor-core kernel: 16-row groups
+        hpipe_build_pieces(ah->m_weights_h, cuts, (uint32_t)ctx->sm_count, 16u, &pieces, &first, &max_rows);
+    else
+        hpipe_build_pieces(nsub == 12 ? ah->s_strips_h : ah->p_strips_h, cuts, (uint32_t)ctx->sm_count, nsub == 12 ? 8u : 4u * (uint32_t)nsub,
+                           &pieces, &first, &max_rows);
     RC(reserve(ctx, ctx->pieces, std::max<size_t>(pieces.size() * 4, 16)));
     RC(reserve(ctx, ctx->cta_first, std::max<size_t>(first.size() * 4, 16)));
     CU(cudaMemcpyAsync(ctx->pieces.p, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -366,6 +390,14 @@ int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe,
 }
 
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
+    if (!pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap &&
+        (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && hmma_smem_bytes(src_kind, a.hot) <= 227 * 1024) {
+        RC(prepare_pieces(ctx, a.n_rows, row_off, src_kind == HSRC_DN_CLAHE, ah, 100));
+        KS(SARPRO_STAGE_APPLY, launch_hmma(a, src_kind, (const uint4*)ah->m_btab.p, (const int4*)ah->m_ntile.p, (const uint4*)ah->m_strips.p,
+                                           (const uint32_t*)ctx->pieces.p, (const uint32_t*)ctx->cta_first.p, ctx->pc_n_ctas, a.hot,
+                                           ctx->stream));
+        return 0;
+    }
     if (!pix16 && ah->pipe && ctx->use_hpipe && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap) {
         const bool clahe = src_kind == HSRC_DN_CLAHE;
         // worst-case piece = a whole vertical cell (or the whole raster); 3 sub-blocks when the tables still fit
@@ -911,6 +943,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     if (const char* v = getenv("SARPRO_HPIPE")) ctx->use_hpipe = atoi(v);
+    if (const char* v = getenv("SARPRO_HMMA")) ctx->use_hmma = atoi(v);
     if (const char* v = getenv("SARPRO_HPIPE_NSUB")) ctx->hpipe_nsub = (atoi(v) == 2 || atoi(v) == 3 || atoi(v) == 12) ? atoi(v) : 0;
     int rc = upload_rgb_luts(ctx);
     if (rc) {
@@ -937,6 +970,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     for (auto& kv : ctx->axes) {
         release(kv.second->start); release(kv.second->size); release(kv.second->coef);
         release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips); release(kv.second->sstrips);
+        release(kv.second->m_btab); release(kv.second->m_ntile); release(kv.second->m_strips);
         delete kv.second;
     }
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);

@@ -15,7 +15,7 @@ __device__ __forceinline__ double clahe_blend_exact_rn(double c00, double c01, d
 
 // u8 sample of pixel (r, c) (local row, column) with DN d != 0. Arguments by value so that the kernel-parameter
 // struct never has to be materialised in local memory.
-__device__ __noinline__ uint32_t clahe_exact_sample_impl(const uint16_t* __restrict__ lut, const double* __restrict__ cdf,
+static __device__ __noinline__ uint32_t clahe_exact_sample_impl(const uint16_t* __restrict__ lut, const double* __restrict__ cdf,
                                                          const double* __restrict__ col_dx, const double* __restrict__ col_omdx,
                                                          const uint16_t* __restrict__ col_t, const double* __restrict__ row_dy,
                                                          const double* __restrict__ row_omdy, const uint16_t* __restrict__ row_t,

@@ -38,6 +38,10 @@ struct AxisPlan {
     uint32_t s_oxb = 0, s_rbw_words = 0, s_n_strips = 0;
     DevBuf sstrips;
     std::vector<HStrip> s_strips_h;
+    // tensor-core kernel (kernels_hmma.cu)
+    bool mma = false;
+    DevBuf m_btab, m_ntile, m_strips;
+    std::vector<HStrip> m_weights_h;
     AxisDev dev() const {
         AxisDev d;
         d.start = (const uint32_t*)start.p;
@@ -112,7 +116,7 @@ struct sarpro_ctx {
     sarpro::BandWs band[2];
     sarpro::DevBuf units, tile_px, col_dx, col_omdx, col_t, row_dy, row_omdy, row_t, rgb, hist256, rgbsel, rgb_luts;
     sarpro::DevBuf col_m, row_sat, rowblocks;
-    uint64_t clahe_tile_w = 0, clahe_tile_h = 0;
+    uint64_t clahe_tile_w = 0, clahe_tile_h = 0, clahe_rows = 0;
     // row-block cache of the horizontal pass
     uint64_t rb_rows = 0, rb_row_off = 0, rb_tile_h = 0;
     int rb_clahe = -1;
@@ -125,6 +129,7 @@ struct sarpro_ctx {
     uint32_t pc_n_ctas = 0, pc_max_rows = 0;
     int hpipe_nsub = 0;  // SARPRO_HPIPE_NSUB: 0 = auto (3 sub-blocks when shared memory allows, else 2)
     int use_hpipe = 1;   // SARPRO_HPIPE=0: previous production kernel (kernels_hfast.cu)
+    int use_hmma = 1;    // SARPRO_HMMA=0: second-generation kernels (kernels_hpipe.cu) instead of kernels_hmma.cu
     int force_exact = 0; // SARPRO_FORCE_EXACT=1: generic kernels + exact f64 CLAHE everywhere (validation)
     // geometry caches
     uint64_t units_rows = 0, units_cols = 0, units_scene_rows = 0, units_row_off = 0, units_own0 = 0, units_own1 = 0;

@@ -33,10 +33,12 @@ cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut,
 cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, uint32_t n_tiles, double* cdf,
                              float* cdf32, cudaStream_t stream);
 // per-row / per-column bilinear geometry (autoscale.rs:308-318): t01 = t0 | t1 << 8
-// t01 bit 7 is set when fl(omd + d) == 1.0; m = 2*g - tile*(2*t+1) (so d == m / (2*tile) exactly);
-// sat = trunc(clamp(fl(omd + d), 0, 1) * 255): the sample of a pixel whose four CDF values are exactly 1.0.
+// t01 bit 7 is set when fl(omd + d) == 1.0, bit 6 when it is 1 - 2^-53; m = 2*g - tile*(2*t+1) (so d == m / (2*tile) exactly);
+// sat = trunc(clamp(fl(omd + d), 0, 1) * 255): the sample of a pixel whose four CDF values are exactly 1.0 when the
+// other axis has fl(omd' + d') == 1.0; sat1: the same when the other axis has 1 - 2^-53.
 cudaError_t launch_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles, double* d,
-                              double* omd, uint16_t* t01, int32_t* m, uint16_t* sat, cudaStream_t stream);
+                              double* omd, uint16_t* t01, int32_t* m, uint16_t* sat, cudaStream_t stream,
+                              uint16_t* sat1 = nullptr);
 
 struct ClaheDev {
     const double* cdf;      // [64][256]
@@ -49,6 +51,7 @@ struct ClaheDev {
     const uint16_t* row_t;
     const int32_t* col_m;    // [cols]  2c - tile_w*(2tx+1)
     const uint16_t* row_sat; // [local rows]
+    const uint16_t* row_sat1; // [local rows]
     float inv2tw;            // 1 / (2*tile_w)
     uint32_t tile_w;         // CLAHE tile width (autoscale.rs:237)
     int tiles_x;
@@ -143,6 +146,26 @@ size_t hpipe_smem_bytes(int src_kind, int nsub, uint32_t hot, uint32_t max_rows,
 cudaError_t launch_hpipe(const HResizeArgs& a, int src_kind, int nsub, const HStrip* strips_dev, const uint32_t* pieces_dev,
                          const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t strip_w, uint32_t hot, uint32_t max_rows,
                          cudaStream_t stream);
+// A piece of the persistent pass-B kernels: rows [r0, r1) (inside one vertical CLAHE cell) of strip `strip`.
+struct HPiece {
+    uint32_t strip, r0, r1, pad;
+};
+uint32_t hpipe_lut_shift(uint32_t hot);
+// Third-generation pass B (kernels_hmma.cu): horizontal Lanczos taps on the integer tensor-core path (IMMA.16832),
+// samples packed straight into the A fragments. Plan: n-tiles of 8 output columns over 64-column source blocks.
+struct HMmaPlanHost {
+    std::vector<uint4> btab;     // permuted tap bytes, one uint4 per (n-tile block, k-step, lane)
+    std::vector<int4> ntile;     // {first block, last block, offset into btab in blocks, 0}
+    std::vector<uint4> strips;   // {first n-tile, end n-tile, first block, end block}
+    std::vector<HStrip> weights; // per strip, for hpipe_build_pieces (nvec = 8 * blocks)
+};
+// max_span: longest source span of a strip in columns (CLAHE: the tile width), 0 = unbounded. false when the axis
+// does not fit the kernel (in_size not a multiple of 8, more than three n-tiles in flight, ...).
+bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int32_t* coef_h, uint32_t window, uint32_t out_size,
+                     uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan);
+size_t hmma_smem_bytes(int src_kind, uint32_t hot);
+cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,
+                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t hot, cudaStream_t stream);
 // vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
                            void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream,

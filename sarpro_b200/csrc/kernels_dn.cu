@@ -479,7 +479,7 @@ cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, u
 // autoscale.rs:308-318 for one axis: f = g/tile - 0.5; t = max(floor(f),0); d = f - t; neighbours clamped.
 __global__ void k_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles,
                              double* __restrict__ d, double* __restrict__ omd, uint16_t* __restrict__ t01,
-                             int32_t* __restrict__ m, uint16_t* __restrict__ sat) {
+                             int32_t* __restrict__ m, uint16_t* __restrict__ sat, uint16_t* __restrict__ sat1) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t g = global_offset + i;
@@ -493,17 +493,23 @@ __global__ void k_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_s
     const double one = __dadd_rn(om, dd); // value of c*(1-d) + c*d for c == 1.0
     d[i] = dd;
     omd[i] = om;
-    t01[i] = (uint16_t)(t0 | (t1 << 8) | (one == 1.0 ? 0x80 : 0));
+    const double one_m = 0x1.fffffffffffffp-1; // 1 - 2^-53, the other value fl(om + d) takes
+    t01[i] = (uint16_t)(t0 | (t1 << 8) | (one == 1.0 ? 0x80 : 0) | (one == one_m ? 0x40 : 0));
     if (m) m[i] = (int32_t)(2ll * (long long)g - (long long)tile_size * (2 * t + 1));
     if (sat) {
         const double c = one < 0.0 ? 0.0 : (one > 1.0 ? 1.0 : one);
         sat[i] = (uint16_t)__dmul_rn(c, 255.0);
     }
+    if (sat1) { // the same sample when the other axis gives fl(om' + d') == 1 - 2^-53 (autoscale.rs:327-329 with CDFs 1.0)
+        const double v = __dadd_rn(__dmul_rn(one_m, om), __dmul_rn(one_m, dd));
+        const double c = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+        sat1[i] = (uint16_t)__dmul_rn(c, 255.0);
+    }
 }
 cudaError_t launch_clahe_axis(uint32_t n, uint32_t global_offset, uint32_t tile_size, uint32_t n_tiles, double* d,
-                              double* omd, uint16_t* t01, int32_t* m, uint16_t* sat, cudaStream_t stream) {
+                              double* omd, uint16_t* t01, int32_t* m, uint16_t* sat, cudaStream_t stream, uint16_t* sat1) {
     if (n == 0) return cudaSuccess;
-    k_clahe_axis<<<(n + 255) / 256, 256, 0, stream>>>(n, global_offset, tile_size, n_tiles, d, omd, t01, m, sat);
+    k_clahe_axis<<<(n + 255) / 256, 256, 0, stream>>>(n, global_offset, tile_size, n_tiles, d, omd, t01, m, sat, sat1);
     return cudaGetLastError();
 }
 

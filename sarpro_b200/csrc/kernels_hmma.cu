@@ -1,0 +1,659 @@
+// kernels_hmma.cu — pass B for u8 samples, third generation: the per-pixel stage (DN -> sample) fused with the
+// horizontal Lanczos pass, with the taps on the tensor-core integer path.
+//
+// The horizontal pass (resize.rs:39-50 -> fast_image_resize, i16 taps, i32 accumulate) is a banded matrix product
+//     temp[r][ox] = clamp((half + sum_c S[r][c] * W[c][ox]) >> precision),   S u8 samples, W i16 taps.
+// An i16 tap is 256*hi + lo (hi signed byte, lo unsigned byte), so the sum is 256 * (S x Whi) + (S x Wlo): two exact
+// u8 x s8 / u8 x u8 -> s32 products, which is what mma.sync.m16n8k32 (IMMA.16832) computes. Integer, hence bit-exact
+// whatever the summation order.
+//
+// A warp owns 16 source rows and walks 64-column blocks along a strip. Per block, lane (g = lane/4, q = lane%4) loads
+// the 16 DNs of columns 64*cb + 16q .. +15 for rows g and g+8 (two 128-bit streaming loads per row, prefetched one
+// block ahead into the registers just consumed), turns them into samples, and the packed samples ARE the A fragments
+// of two k-steps: the k index of an MMA is only summed over, so the host lays the tap bytes of the B fragments out in
+// the same permuted order (column 16q + 8s + 4r + i  <->  k-step s, register r, byte i of lane q). No sample ever
+// goes through shared memory. An output n-tile (8 output columns) is live while the walk crosses its window
+// (three accumulator slots, rotated), then it is scaled, clamped and stored.
+//
+// Per-pixel stage. LUT strategies: one shared-memory gather (R-way lane-interleaved table, as kernels_hpipe.cu).
+// CLAHE (autoscale.rs:307-330, :602): DN -> address of the pixel's bin entry in an 8-way replicated float4 table
+// holding the bilinear form of the four tile CDFs of the cell, u = A + B*dx + (C + D*dx)*dy in sample units, three
+// FFMAs in plain fp32 (|u| < 512, so its rounding error is ~2e-5). A carries +S where S bounds the total error of
+// the evaluation (computed per table entry when the piece's tables are built), so the true value lies in
+// [u - 2S, u]. One FADD.RD against 1.5*2^(23-F) truncates u to F fraction bits in the mantissa: if those bits are
+// not all zero, u >= n + 2^-F > n + 2S and floor(true) == floor(u) == n. Otherwise (2^-F of the pixels, F = 13
+// normally) the lane's pixels are recomputed with the reference's exact f64 operation order by the whole warp,
+// one pixel per lane, and patched into the fragment registers before the MMA.
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include "clahe_exact.cuh"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sarpro {
+
+namespace hm {
+constexpr uint32_t kThreads = 512, kWarps = 16;
+constexpr uint32_t kQuadEntries = 257;                       // 256 bins + the invalid-pixel entry
+constexpr uint32_t kQuadCellBytes = kQuadEntries * 8 * 16;   // one cell, 8 replicas
+constexpr int kSlots = 3;                                    // n-tiles in flight per warp
+constexpr float kBigC = 12582912.0f + 512.0f;                // u + kBigC (RD): low 16 bits = floor(u) + 512
+constexpr float kMarker = 480.0f;                            // floor of the marker entries (regular entries stay below 460)
+constexpr uint32_t kMarkerLess2 = (480u + 512u - 1u) * 0x10001u;
+} // namespace hm
+
+__device__ __forceinline__ uint32_t hm_lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <uint32_t OFF>
+__device__ __forceinline__ float4 hm_lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ uint32_t hm_keep(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint4 hm_ldg_u4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+// 128-bit streaming load, no L1 allocation, 256-byte L2 fetch granularity (the next block of the walk)
+__device__ __forceinline__ uint4 hm_ld_dn(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_u8u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct HMmaSmem {
+    uint32_t lut, quad, cdf, ctrl, total;
+};
+__host__ __device__ inline HMmaSmem hmma_layout(bool clahe, uint32_t lut_bytes) {
+    HMmaSmem L;
+    L.lut = 0;
+    uint32_t o = (lut_bytes + 15) & ~15u;
+    L.quad = o;
+    if (clahe) o += 2 * hm::kQuadCellBytes;
+    L.cdf = o;
+    if (clahe) o += 6 * 256 * 8;
+    L.ctrl = o;
+    o += 64;
+    L.total = o;
+    return L;
+}
+
+struct HMmaParams {
+    const uint4* btab;     // B fragments: [(boff + rel_block) * 2 + kstep][lane] = {hi r0, hi r1, lo r0, lo r1}
+    const int4* ntile;     // per n-tile: {first block, last block, boff, 0}
+    const uint4* strips;   // per strip: {first n-tile, end n-tile, first block, end block}
+    const HPiece* pieces;
+    const uint32_t* cta_first;
+    uint32_t hot, lut_shift;
+};
+
+// Error bound of the fp32 evaluation of one table entry (see the header), in sample units. X, Y bound |dx|, |dy|.
+__device__ __forceinline__ double hm_half_ulp(double x) {
+    const double ax = fabs(x);
+    if (ax < 1e-30) return 0.0;
+    int e;
+    frexp(ax, &e); // ax = m * 2^e, m in [0.5, 1)
+    return ldexp(1.0, e - 25); // half an ulp of the binade of ax (fp32: 24 significant bits)
+}
+__device__ __forceinline__ double hm_entry_error(double A, double B, double C, double D) {
+    const double X = 1.0, Y = 1.0;          // |dx| <= 1, |dy| <= 1 (autoscale.rs:308-318: d in [-0.5, 1))
+    const double ex = 2.0e-7, ey = 3.1e-8;  // |dxf - dx|, |dyf - dy| (see dx_of / the row geometry below)
+    const double aB = fabs(B), aC = fabs(C), aD = fabs(D), aA = fabs(A);
+    double e = hm_half_ulp(A) + hm_half_ulp(B) * X + hm_half_ulp(C) * Y + hm_half_ulp(D) * X * Y; // table roundings
+    e += (aB + aD * Y) * ex + (aC + aD * X) * ey;                                                 // geometry
+    e += hm_half_ulp(aC + aD * X) * Y;                                                            // t1 = fl(D*dx + C)
+    e += hm_half_ulp(aA + aB * X);                                                                // t2 = fl(B*dx + A)
+    e += hm_half_ulp(aA + aB * X + (aC + aD * X) * Y);                                            // u  = fl(t1*dy + t2)
+    return e * 1.05 + 1e-9; // second-order terms; the reference's own f64 roundings (< 1e-12)
+}
+
+template <bool CLAHE>
+__global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaParams pp) {
+    extern __shared__ uint4 smem4[];
+    unsigned char* const smem = reinterpret_cast<unsigned char*>(smem4);
+    constexpr uint32_t NT = hm::kThreads;
+    constexpr uint32_t FULL = 0xffffffffu;
+    if (a.skip && *a.skip) return;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t hot = pp.hot, lut_shift = pp.lut_shift; // table word of DN idx, replica r: byte (idx << lut_shift) + 4r
+    const HMmaSmem L = hmma_layout(CLAHE, hot << lut_shift);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, g = lane >> 2, q = lane & 3u;
+    if (sbase + (hot << lut_shift) > 65536u) __trap(); // 16-bit table addresses (dynamic smem starts low on sm_100)
+    uint32_t* const s_ctrl = reinterpret_cast<uint32_t*>(smem + L.ctrl);
+
+    {   // once per CTA: DN -> table word, R lane-interleaved replicas
+        uint4* s_lut4 = reinterpret_cast<uint4*>(smem + L.lut);
+        const uint32_t per = 1u << (lut_shift - 4); // uint4 per table entry
+        for (uint32_t i = tid; i < hot * per; i += NT) {
+            const uint32_t idx = i >> (lut_shift - 4), r0 = (i & (per - 1)) * 4u;
+            const uint32_t e = idx + 1 == hot ? a.hot_top : (a.lut[idx] & 255u);
+            uint4 v;
+            if (CLAHE) {
+                const uint32_t bin = idx ? e : 256u; // DN 0 is the only invalid DN (pipeline.rs:22)
+                const uint32_t b = sbase + L.quad + (bin * 8u + (r0 & 7u)) * 16u;
+                v = make_uint4(b, b + 16u, b + 32u, b + 48u);
+            } else {
+                v = make_uint4(e, e, e, e);
+            }
+            s_lut4[i] = v;
+        }
+    }
+    const uint32_t cols = a.src_cols;
+    const uint32_t cap2 = hm_keep((hot - 1u) * 0x10001u);
+    const uint32_t lut_mul = hm_keep(1u << lut_shift);
+    const uint32_t cj = hm_keep((sbase + L.lut + (lane & ((lut_mul >> 2) - 1u)) * 4u) * 0x10001u);
+    const int prec = a.ax.precision;
+    const int acc0 = prec > 0 ? (1 << (prec - 1)) : 0;
+    const uint16_t* const src = reinterpret_cast<const uint16_t*>(a.src);
+    // scale_u16_to_u8 (autoscale.rs:348-364) takes min/max over ALL samples, invalid pixels (written as 0) included
+    uint32_t mn2 = 0xffffffffu, mx2 = 0u;   // fast path: u16x2 running min / max of floor(u) + 512 (not yet clamped)
+    uint32_t mn_e = 0xffffffffu, mx_e = 0;  // exact-path samples
+
+    for (uint32_t pi = pp.cta_first[blockIdx.x]; pi < pp.cta_first[blockIdx.x + 1]; ++pi) {
+        const HPiece pc = pp.pieces[pi];
+        const uint4 st = pp.strips[pc.strip]; // {j0, j1, cb0, cb1}
+        __syncthreads(); // the previous piece is done with the tables
+        if (tid == 0) { s_ctrl[0] = 0; s_ctrl[1] = 0xffffffffu; s_ctrl[2] = 0; }
+
+        // ---- per-piece tables --------------------------------------------------------------------
+        uint32_t cellA = 0, bcol = 0xffffffffu, fbits = 13;
+        float magic = 1536.0f;
+        bool fixA = false, fixB = false; // saturated-entry markers in use for cell A / B
+        if (CLAHE) {
+            const ClaheDev& cl = a.clahe;
+            const uint32_t ty = cl.row_t[pc.r0]; // the piece lies inside one vertical bilinear cell
+            const uint32_t ty0 = ty & 7u, ty1 = (ty >> 8) & 7u;
+            const uint32_t first_col = min(st.z * 64u, cols - 1u), last_col = min(st.w * 64u, cols) - 1u;
+            cellA = cl.col_t[first_col] & 7u;
+            const uint32_t cellB = cl.col_t[last_col] & 7u; // == cellA or cellA + 1 (strip span <= tile width)
+            __syncthreads();
+            // first column of cell B; saturated-bin shortcut (all four CDFs exactly 1.0 -> sample 255) is valid for a
+            // cell only when fl(omdx+dx) == 1 for all of its columns in the strip and fl(omdy+dy) == 1 for all rows
+            int okA = 1, okB = 1, okR = 1;
+            for (uint32_t c = first_col + tid; c <= last_col; c += NT) {
+                const uint32_t ct = cl.col_t[c];
+                if ((ct & 7u) != cellA) atomicMin(&s_ctrl[1], c);
+                if (!(ct & 0x80u)) { if ((ct & 7u) == cellA) okA = 0; else okB = 0; }
+            }
+            for (uint32_t r = pc.r0 + tid; r < pc.r1; r += NT) if (cl.row_sat[r] != 255u) okR = 0;
+            okA = __syncthreads_and(okA);
+            okB = __syncthreads_and(okB);
+            okR = __syncthreads_and(okR);
+            bcol = s_ctrl[1];
+            const bool sat_ok[2] = {okA && okR, okB && okR};
+            fixA = !sat_ok[0];
+            fixB = !sat_ok[1];
+            // f64 CDFs of the (up to) 3 x 2 tiles of the piece, for the exact path
+            double* s_cdf = reinterpret_cast<double*>(smem + L.cdf);
+            for (uint32_t i = tid; i < 6 * 256; i += NT) {
+                const uint32_t t = i >> 8, bin = i & 255u;
+                const uint32_t tyy = t >= 3 ? ty1 : ty0, txx = min(cellA + (t % 3u), 7u);
+                s_cdf[i] = cl.cdf[((size_t)tyy * 8 + txx) * 256 + bin];
+            }
+            // bilinear-form table of both cells: pass 0 finds the largest evaluation error, pass 1 writes the entries
+            float4* s_quad = reinterpret_cast<float4*>(smem + L.quad);
+            double shift = 0.0;
+            for (int pass = 0; pass < 2; ++pass) {
+                float emax = 0.f;
+                for (uint32_t i = tid; i < 2 * hm::kQuadEntries; i += NT) {
+                    const uint32_t cs = i / hm::kQuadEntries, bin = i % hm::kQuadEntries;
+                    const uint32_t pcx = cs ? cellB : cellA;
+                    float4 qv = make_float4(0.5f, 0.f, 0.f, 0.f); // invalid pixel: sample 0 (autoscale.rs:604)
+                    if (bin != 256) {
+                        const uint32_t p1 = pcx + 1 < 8 ? pcx + 1 : 7;
+                        const double c00 = cl.cdf[((size_t)ty0 * 8 + pcx) * 256 + bin], c01 = cl.cdf[((size_t)ty0 * 8 + p1) * 256 + bin];
+                        const double c10 = cl.cdf[((size_t)ty1 * 8 + pcx) * 256 + bin], c11 = cl.cdf[((size_t)ty1 * 8 + p1) * 256 + bin];
+                        if (c00 == 0.0 && c01 == 0.0 && c10 == 0.0 && c11 == 0.0) {
+                            qv = make_float4(0.5f, 0.f, 0.f, 0.f);   // 0*x + 0*y == 0 exactly
+                        } else if (c00 == 1.0 && c01 == 1.0 && c10 == 1.0 && c11 == 1.0) {
+                            // v_ref = fl(fl(sx*omdy) + fl(sx*dy)), sx = fl(omdx + dx): 255 wherever both sums are exactly 1.0
+                            // (sat_ok); elsewhere the entry is a marker (floor 480) that the block fix-up resolves per pixel
+                            qv = make_float4(sat_ok[cs] ? 255.5f : hm::kMarker + 0.5f, 0.f, 0.f, 0.f);
+                        } else {
+                            const double A = 255.0 * c00, B = 255.0 * (c01 - c00), C = 255.0 * (c10 - c00);
+                            const double D = 255.0 * ((c11 - c10) - (c01 - c00));
+                            const double err = hm_entry_error(A + 1e-3, B, C, D);
+                            // |u| must stay below 512: the binade of the magic constants and the 16-bit biased floor
+                            const bool in_range = fabs(A) + fabs(B) + fabs(C) + fabs(D) < 460.0; // and below the marker
+                            if (pass == 0) {
+                                if (in_range) emax = fmaxf(emax, (float)err * 1.0001f);
+                            } else if (err <= shift && in_range) {
+                                qv = make_float4((float)(A + shift), (float)B, (float)C, (float)D);
+                            } else {
+                                qv = make_float4(0.f, 0.f, 0.f, 0.f); // fraction bits all zero: always the exact path
+#ifdef HM_DEBUG
+                                if ((blockIdx.x % 37) == 0) printf("  cta %u always-exact entry cell %u bin %u A %g B %g C %g D %g err %g\n", blockIdx.x, cs, bin, A, B, C, D, err);
+#endif
+                            }
+                        }
+                    }
+                    if (pass == 1) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) s_quad[(cs * hm::kQuadEntries + bin) * 8 + r] = qv;
+                    }
+                }
+                if (pass == 0) {
+                    atomicMax(&s_ctrl[2], __float_as_uint(emax));
+                    __syncthreads();
+                    const float em = __uint_as_float(s_ctrl[2]);
+                    // F fraction bits: the guard 2^-F must exceed 2*shift, shift >= every entry's error
+                    fbits = 10u;
+                    for (uint32_t f = 13u; f > 10u; --f)
+                        if ((double)em <= ldexp(0.45, -(int)f)) { fbits = f; break; }
+                    shift = ldexp(0.45, -(int)fbits);
+                    magic = (float)ldexp(1.5, 23 - (int)fbits);
+#ifdef HM_DEBUG
+                    if (tid == 0 && (blockIdx.x % 37) == 0)
+                        printf("cta %u piece %u strip %u rows %u-%u cells %u/%u bcol %u ok %d%d%d emax %g fbits %u\n", blockIdx.x, pi, pc.strip,
+                               pc.r0, pc.r1, cellA, cellB, bcol, okA, okB, okR, (double)em, fbits);
+#endif
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t fmask = hm_keep((1u << fbits) - 1u);
+        const float magic_k = __uint_as_float(hm_keep(__float_as_uint(magic)));
+
+        // exact u8 sample of pixel (r, c) (local row, column) with the reference's f64 operation order
+        auto exact_px = [&](uint32_t r, uint32_t c) -> uint32_t {
+            const uint32_t d = src[(size_t)r * cols + c];
+            const uint32_t word = reinterpret_cast<const uint32_t*>(smem + L.lut)[(size_t)min(d, hot - 1u) << (lut_shift - 2)];
+            if (!CLAHE) return word;
+            uint32_t o = 0;
+            if (d) {
+                const ClaheDev& cl = a.clahe;
+                const uint32_t tx = cl.col_t[c];
+                const uint32_t bin = (word - (sbase + L.quad)) >> 7;
+                const double* s_cdf = reinterpret_cast<const double*>(smem + L.cdf);
+                const uint32_t x0 = ((tx & 7u) - cellA) * 256u + bin, x1 = (((tx >> 8) & 7u) - cellA) * 256u + bin;
+                double v = clahe_blend_exact_rn(s_cdf[x0], s_cdf[x1], s_cdf[768 + x0], s_cdf[768 + x1], cl.col_dx[c], cl.col_omdx[c],
+                                                cl.row_dy[r], cl.row_omdy[r]);
+                v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+                o = (uint32_t)__dmul_rn(v, 255.0);
+            }
+            mn_e = min(mn_e, o);
+            mx_e = max(mx_e, o);
+            return o;
+        };
+
+        // ---- 16-row groups of the piece, handed out to the warps --------------------------------------
+        const uint32_t n_groups = (pc.r1 - pc.r0 + 15u) / 16u;
+        for (;;) {
+            uint32_t grp = 0;
+            if (lane == 0) grp = atomicAdd(&s_ctrl[0], 1u);
+            grp = __shfl_sync(FULL, grp, 0);
+            if (grp >= n_groups) break;
+            const uint32_t rbase = pc.r0 + grp * 16u;
+            // rows beyond the piece repeat its last row (never stored; duplicates do not disturb the min / max)
+            const uint32_t rA = min(rbase + g, pc.r1 - 1u), rB = min(rbase + g + 8u, pc.r1 - 1u);
+            const uint16_t* const pA = src + (size_t)rA * cols;
+            const uint16_t* const pB = src + (size_t)rB * cols;
+            const bool okA_row = rbase + g < pc.r1, okB_row = rbase + g + 8u < pc.r1;
+            uint8_t* const tA = reinterpret_cast<uint8_t*>(a.temp) + (size_t)(rbase + g - a.row0) * a.ax.out_size;
+            uint8_t* const tB = tA + (size_t)8 * a.ax.out_size;
+            float dyA = 0.f, dyB = 0.f;
+            // saturated pixels of rows A / B: byte masks (0 / 0xff) "sample is 254" and "neither 254 nor 255" for the two
+            // classes of columns (fl(omdx+dx) == 1.0 / == 1 - 2^-53); only read by the marker fix-up
+            uint32_t r254[2][2] = {{0, 0}, {0, 0}}, rodd[2][2] = {{0, 0}, {0, 0}};
+            if (CLAHE) {
+                dyA = (float)a.clahe.row_dy[rA];
+                dyB = (float)a.clahe.row_dy[rB];
+                if (fixA || fixB) {
+#pragma unroll
+                    for (int rw = 0; rw < 2; ++rw) {
+                        const uint32_t r = rw ? rB : rA;
+                        const uint32_t s0 = a.clahe.row_sat[r], s1 = a.clahe.row_sat1[r];
+                        r254[rw][0] = s0 == 254u ? 0xffu : 0u;
+                        r254[rw][1] = s1 == 254u ? 0xffu : 0u;
+                        rodd[rw][0] = (s0 != 254u && s0 != 255u) ? 0xffu : 0u;
+                        rodd[rw][1] = (s1 != 254u && s1 != 255u) ? 0xffu : 0u;
+                    }
+                }
+            }
+
+            int acc[hm::kSlots][4]; // sum of sample * tap: the hi-byte products are folded in (<< 8) block by block
+            uint32_t sj[hm::kSlots], sfb[hm::kSlots], slb[hm::kSlots], sbo[hm::kSlots];
+#pragma unroll
+            for (int s = 0; s < hm::kSlots; ++s) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[s][i] = 0;
+                sj[s] = st.x + s;
+                sfb[s] = 0xffffffffu; slb[s] = 0; sbo[s] = 0;
+                if (sj[s] < st.y) { const int4 m = pp.ntile[sj[s]]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = m.z; }
+            }
+            // columns past the raster repeat its last 8-sample vector (they carry zero taps)
+            auto vec_col = [&](uint32_t cb, uint32_t h) { return min(cb * 64u + q * 16u + h * 8u, cols - 8u); };
+            uint4 d[4]; // [0] row A cols 0..7, [1] row A cols 8..15, [2] row B cols 0..7, [3] row B cols 8..15
+            {
+                const uint32_t c0 = vec_col(st.z, 0), c1 = vec_col(st.z, 1);
+                d[0] = hm_ld_dn(pA + c0); d[1] = hm_ld_dn(pA + c1);
+                d[2] = hm_ld_dn(pB + c0); d[3] = hm_ld_dn(pB + c1);
+            }
+            for (uint32_t cb = st.z; cb < st.w; ++cb) {
+                // B fragments of the n-tiles whose window meets this block
+                uint4 bq[hm::kSlots][2];
+                bool act[hm::kSlots];
+#pragma unroll
+                for (int s = 0; s < hm::kSlots; ++s) {
+                    act[s] = cb >= sfb[s] && cb <= slb[s];
+                    if (act[s]) {
+                        const uint4* p = pp.btab + ((size_t)(sbo[s] + (cb - sfb[s])) * 2u) * 32u + lane;
+                        bq[s][0] = hm_ldg_u4(p);
+                        bq[s][1] = hm_ldg_u4(p + 32);
+                    }
+                }
+                const bool more = cb + 1 < st.w;
+                uint32_t w[4][2]; // packed samples: [vector][px 0..3 / 4..7]
+                uint32_t riskmask = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t c0 = vec_col(cb, h);
+                    const uint32_t cn = vec_col(cb + 1, h);
+                    float dx[8];
+                    uint32_t tag = 0;
+                    uint32_t cm0 = 0, cm1 = 0; // columns of the vector with fl(omdx+dx) == 1.0 / == 1 - 2^-53 (bit per column)
+                    bool fix = false;
+                    if (CLAHE) {
+                        // block entirely in cell A / entirely in cell B / holds the boundary (per-pixel select)
+                        tag = (cb * 64u + 64u <= bcol) ? 0u : (cb * 64u >= bcol ? 1u : 2u);
+                        // dx = m / (2*tile_w), m = 2c - tile_w*(2t+1) (k_clahe_axis); fp32: |dxf - dx| < 2e-7
+                        const uint32_t t0 = tag == 0 ? cellA : (tag == 1 ? cellA + 1u : (c0 >= bcol ? cellA + 1u : cellA));
+                        const int m0 = 2 * (int)c0 - (int)a.clahe.tile_w * (2 * (int)t0 + 1);
+                        const float dx0 = __fmul_rn((float)m0, a.clahe.inv2tw);
+                        const float dstep = __fmul_rn(2.0f, a.clahe.inv2tw);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) dx[k] = __fmaf_rn((float)k, dstep, dx0);
+                        fix = tag == 0 ? fixA : (tag == 1 ? fixB : (fixA || fixB));
+                        if (fix) {
+                            const uint4 ct = *reinterpret_cast<const uint4*>(a.clahe.col_t + c0);
+                            const uint32_t cw[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                cm0 |= (((cw[j] >> 7) & 1u) | ((cw[j] >> 22) & 2u)) << (2 * j);
+                                cm1 |= (((cw[j] >> 6) & 1u) | ((cw[j] >> 21) & 2u)) << (2 * j);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int rw = 0; rw < 2; ++rw) {
+                        const int v = rw * 2 + h;
+                        const uint4 cur = d[v];
+                        if (more) d[v] = hm_ld_dn((rw ? pB : pA) + cn);
+                        const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+                        uint32_t pr[4];
+                        if (!CLAHE) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t a2 = __vminu2(wv[j], cap2) * lut_mul + cj;
+                                const uint32_t e0 = hm_lds_u32(a2 & 0xffffu), e1 = hm_lds_u32(a2 >> 16);
+                                pr[j] = __byte_perm(e0, e1, 0x5410);
+                            }
+                            w[v][0] = __byte_perm(pr[0], pr[1], 0x6420);
+                            w[v][1] = __byte_perm(pr[2], pr[3], 0x6420);
+                        } else {
+                            const float dy = rw ? dyB : dyA;
+                            uint32_t racc = 0;
+                            auto body = [&](auto tag_c) {
+                                constexpr uint32_t TAG = decltype(tag_c)::value;
+                                constexpr uint32_t OFF = TAG == 1 ? hm::kQuadCellBytes : 0u;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint32_t a2 = __vminu2(wv[j], cap2) * lut_mul + cj;
+                                    uint32_t e0 = hm_lds_u32(a2 & 0xffffu), e1 = hm_lds_u32(a2 >> 16);
+                                    float x0 = dx[2 * j], x1 = dx[2 * j + 1];
+                                    if (TAG == 2) { // the pixel's own cell: cell B columns sit one tile further (dx - 1)
+                                        const bool b0 = c0 + 2 * j >= bcol, b1 = c0 + 2 * j + 1 >= bcol;
+                                        const bool vb = c0 >= bcol; // dx[] was built for the vector's first column
+                                        if (b0) e0 += hm::kQuadCellBytes;
+                                        if (b1) e1 += hm::kQuadCellBytes;
+                                        if (b0 && !vb) x0 = __fsub_rn(x0, 1.0f);
+                                        if (b1 && !vb) x1 = __fsub_rn(x1, 1.0f);
+                                    }
+                                    const float4 q0 = hm_lds_f4<OFF>(e0), q1 = hm_lds_f4<OFF>(e1);
+                                    const float u0 = __fmaf_rn(__fmaf_rn(q0.w, x0, q0.z), dy, __fmaf_rn(q0.y, x0, q0.x));
+                                    const float u1 = __fmaf_rn(__fmaf_rn(q1.w, x1, q1.z), dy, __fmaf_rn(q1.y, x1, q1.x));
+                                    const uint32_t m0 = __float_as_uint(__fadd_rd(u0, magic_k));
+                                    const uint32_t m1 = __float_as_uint(__fadd_rd(u1, magic_k));
+                                    racc |= ((m0 - 1u) ^ m0) | ((m1 - 1u) ^ m1); // bit F set <=> the F fraction bits are all zero
+                                    pr[j] = __byte_perm(__float_as_uint(__fadd_rd(u0, hm::kBigC)), __float_as_uint(__fadd_rd(u1, hm::kBigC)), 0x5410);
+                                }
+                            };
+                            if (tag == 0) body(std::integral_constant<uint32_t, 0>{});
+                            else if (tag == 1) body(std::integral_constant<uint32_t, 1>{});
+                            else body(std::integral_constant<uint32_t, 2>{});
+                            bool risky = racc > fmask;
+                            const uint32_t k0 = __viaddmin_s16x2_relu(pr[0], 0xFE00FE00u, 0x00FF00FFu);
+                            const uint32_t k1 = __viaddmin_s16x2_relu(pr[1], 0xFE00FE00u, 0x00FF00FFu);
+                            const uint32_t k2 = __viaddmin_s16x2_relu(pr[2], 0xFE00FE00u, 0x00FF00FFu);
+                            const uint32_t k3 = __viaddmin_s16x2_relu(pr[3], 0xFE00FE00u, 0x00FF00FFu);
+                            w[v][0] = __byte_perm(k0, k1, 0x6420);
+                            w[v][1] = __byte_perm(k2, k3, 0x6420);
+                            bool marked = false;
+                            if (fix) {
+                                // marker pixels (saturated entries, clamped to 255 above): 254 where the row / column class
+                                // says so (k_clahe_axis), the exact path for classes it does not cover
+                                uint32_t mk = 0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint32_t dd = __vminu2(pr[j], hm::kMarkerLess2) ^ pr[j];
+                                    mk |= (((dd & 0xffffu) ? 1u : 0u) | ((dd >> 16) ? 2u : 0u)) << (2 * j);
+                                }
+                                if (mk) {
+                                    marked = true;
+                                    const uint32_t n254 = (cm0 & r254[rw][0]) | (cm1 & r254[rw][1]);
+                                    const uint32_t odd = (~(cm0 | cm1) & 0xffu) | (cm0 & rodd[rw][0]) | (cm1 & rodd[rw][1]);
+                                    if (mk & odd) risky = true;
+                                    const uint32_t fm = mk & n254;
+                                    w[v][0] -= ((fm & 15u) * 0x00204081u) & 0x01010101u;
+                                    w[v][1] -= ((fm >> 4) * 0x00204081u) & 0x01010101u;
+                                }
+                            }
+                            if (risky) {
+                                riskmask |= 1u << v;
+                            } else if (!marked) {
+                                mn2 = __vimin3_u16x2(mn2, __vimin3_u16x2(pr[0], pr[1], pr[2]), pr[3]);
+                                mx2 = __vimax3_u16x2(mx2, __vimax3_u16x2(pr[0], pr[1], pr[2]), pr[3]);
+                            } else { // samples as stored
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const uint32_t o = (w[v][k >> 2] >> (8 * (k & 3))) & 255u;
+                                    mn_e = min(mn_e, o);
+                                    mx_e = max(mx_e, o);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (CLAHE) {
+                    // exact fix-up: the 32 pixels of a flagged lane, one per lane
+                    uint32_t need = __ballot_sync(FULL, riskmask != 0);
+                    while (need) {
+                        const uint32_t sl = __ffs(need) - 1u;
+                        need &= need - 1u;
+                        const uint32_t sg = sl >> 2, sq = sl & 3u;
+                        const uint32_t v = lane >> 3, k = lane & 7u; // my pixel of the flagged lane: vector v, sample k
+                        const uint32_t r = min(rbase + sg + ((v & 2u) ? 8u : 0u), pc.r1 - 1u);
+                        const uint32_t c = min(cb * 64u + sq * 16u + (v & 1u) * 8u, cols - 8u) + k;
+                        uint32_t b = exact_px(r, c) << (8u * (lane & 3u));
+                        b |= __shfl_xor_sync(FULL, b, 1);
+                        b |= __shfl_xor_sync(FULL, b, 2); // lanes 4m..4m+3 hold word m = samples 4m..4m+3 of the flagged lane
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            const uint32_t t = __shfl_sync(FULL, b, 4 * m);
+                            if (lane == sl) w[m >> 1][m & 1] = t;
+                        }
+                    }
+                }
+                // ---- the taps: two k-steps per block ------------------------------------------------------
+                const uint32_t ka[4] = {w[0][0], w[2][0], w[0][1], w[2][1]};
+                const uint32_t kb[4] = {w[1][0], w[3][0], w[1][1], w[3][1]};
+#pragma unroll
+                for (int s = 0; s < hm::kSlots; ++s) {
+                    if (act[s]) {
+                        int th[4] = {0, 0, 0, 0};
+                        mma_u8s8(th, ka, bq[s][0].x, bq[s][0].y);
+                        mma_u8u8(acc[s], ka, bq[s][0].z, bq[s][0].w);
+                        mma_u8s8(th, kb, bq[s][1].x, bq[s][1].y);
+                        mma_u8u8(acc[s], kb, bq[s][1].z, bq[s][1].w);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[s][i] += th[i] << 8;
+                        if (cb == slb[s]) { // the n-tile is complete: scale, clamp, store; the slot takes the next n-tile
+                            const uint32_t ox = sj[s] * 8u + q * 2u;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                int vv = (acc0 + acc[s][i]) >> prec;
+                                vv = vv < 0 ? 0 : (vv > 255 ? 255 : vv);
+                                if (((i & 2) ? okB_row : okA_row) && ox + (i & 1) < a.ax.out_size) ((i & 2) ? tB : tA)[ox + (i & 1)] = (uint8_t)vv;
+                                acc[s][i] = 0;
+                            }
+                            sj[s] += hm::kSlots;
+                            sfb[s] = 0xffffffffu;
+                            if (sj[s] < st.y) { const int4 m = pp.ntile[sj[s]]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = m.z; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (CLAHE && a.minmax) {
+        if (mn2 != 0xffffffffu) { // fast-path extrema: biased by 512 and not yet clamped
+            const int lo = (int)min(mn2 & 0xffffu, mn2 >> 16) - 512, hi = (int)max(mx2 & 0xffffu, mx2 >> 16) - 512;
+            mn_e = min(mn_e, (uint32_t)(lo < 0 ? 0 : (lo > 255 ? 255 : lo)));
+            mx_e = max(mx_e, (uint32_t)(hi < 0 ? 0 : (hi > 255 ? 255 : hi)));
+        }
+        const uint32_t mnw = warp_reduce_min(mn_e), mxw = warp_reduce_max(mx_e);
+        if (lane == 0 && mnw != 0xffffffffu) {
+            atomicMin(&a.minmax[0], mnw);
+            atomicMax(&a.minmax[1], mxw);
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+// n-tiles (8 output columns), their 64-column source blocks, the permuted tap bytes, and strips of n-tiles whose
+// source span is at most max_span columns (CLAHE: one tile width, so that a strip meets at most one cell boundary).
+bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int32_t* coef_h, uint32_t window, uint32_t out_size,
+                     uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan) {
+    plan->btab.clear();
+    plan->ntile.clear();
+    plan->strips.clear();
+    plan->weights.clear();
+    if (out_size == 0 || in_size < 8 || (in_size % 8) != 0) return false;
+    const uint32_t n_nt = (out_size + 7) / 8;
+    uint32_t boff = 0;
+    for (uint32_t j = 0; j < n_nt; ++j) {
+        uint32_t ws = 0xffffffffu, we = 0;
+        for (uint32_t ox = j * 8; ox < std::min(out_size, j * 8 + 8); ++ox) {
+            if (size_h[ox] == 0) continue;
+            ws = std::min(ws, start_h[ox]);
+            we = std::max(we, start_h[ox] + size_h[ox]);
+        }
+        if (we == 0) { ws = 0; we = 1; }
+        if (j && ws / 64 < (uint32_t)plan->ntile.back().x) return false; // windows must advance monotonically
+        if (j && (we - 1) / 64 < (uint32_t)plan->ntile.back().y) return false;
+        const uint32_t fb = ws / 64, lb = (we - 1) / 64;
+        plan->ntile.push_back(make_int4((int)fb, (int)lb, (int)boff, 0));
+        for (uint32_t cb = fb; cb <= lb; ++cb)
+            for (uint32_t s = 0; s < 2; ++s)
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    const uint32_t n = lane >> 2, qq = lane & 3u, ox = j * 8 + n;
+                    uint32_t reg[4] = {0, 0, 0, 0}; // hi r0, hi r1, lo r0, lo r1
+                    for (uint32_t r = 0; r < 2; ++r)
+                        for (uint32_t i = 0; i < 4; ++i) {
+                            const uint32_t c = cb * 64 + qq * 16 + s * 8 + r * 4 + i;
+                            int32_t tap = 0;
+                            if (ox < out_size && c >= start_h[ox] && c < start_h[ox] + size_h[ox])
+                                tap = coef_h[(size_t)ox * window + (c - start_h[ox])];
+                            if (tap < -32768 || tap > 32767) return false;
+                            const uint32_t lo = (uint32_t)tap & 255u, hi = (uint32_t)(tap >> 8) & 255u;
+                            reg[r] |= hi << (8 * i);
+                            reg[2 + r] |= lo << (8 * i);
+                        }
+                    plan->btab.push_back(make_uint4(reg[0], reg[1], reg[2], reg[3]));
+                }
+        boff += lb - fb + 1;
+    }
+    // strips
+    uint32_t j0 = 0;
+    while (j0 < n_nt) {
+        uint32_t j1 = j0 + 1;
+        auto span = [&](uint32_t e) { return ((uint32_t)plan->ntile[e - 1].y + 1 - (uint32_t)plan->ntile[j0].x) * 64u; };
+        if (max_span && span(j1) > max_span) return false;
+        while (j1 < n_nt && j1 - j0 < 32 && (!max_span || span(j1 + 1) <= max_span)) ++j1;
+        const uint32_t cb0 = (uint32_t)plan->ntile[j0].x, cb1 = (uint32_t)plan->ntile[j1 - 1].y + 1;
+        // at most kSlots n-tiles of the strip meet any block, and n-tile j + kSlots starts after n-tile j ends
+        for (uint32_t cb = cb0; cb < cb1; ++cb) {
+            uint32_t n = 0;
+            for (uint32_t j = j0; j < j1; ++j)
+                if ((uint32_t)plan->ntile[j].x <= cb && cb <= (uint32_t)plan->ntile[j].y) ++n;
+            if (n > (uint32_t)hm::kSlots) return false;
+        }
+        plan->strips.push_back(make_uint4(j0, j1, cb0, cb1));
+        plan->weights.push_back(HStrip{cb0 * 64, (cb1 - cb0) * 8});
+        j0 = j1;
+    }
+    return true;
+}
+
+size_t hmma_smem_bytes(int src_kind, uint32_t hot) {
+    return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hpipe_lut_shift(hot)).total;
+}
+
+cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,
+                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t hot, cudaStream_t stream) {
+    if (a.n_rows == 0 || a.ax.out_size == 0 || n_ctas == 0) return cudaSuccess;
+    const bool clahe = src_kind == HSRC_DN_CLAHE;
+    const size_t smem = hmma_smem_bytes(src_kind, hot);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    HMmaParams pp;
+    pp.btab = btab_dev;
+    pp.ntile = ntile_dev;
+    pp.strips = strips_dev;
+    pp.pieces = reinterpret_cast<const HPiece*>(pieces_dev);
+    pp.cta_first = cta_first_dev;
+    pp.hot = hot;
+    pp.lut_shift = hpipe_lut_shift(hot);
+    if (clahe) {
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_hmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        k_hmma<true><<<n_ctas, hm::kThreads, smem, stream>>>(a, pp);
+    } else {
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_hmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        k_hmma<false><<<n_ctas, hm::kThreads, smem, stream>>>(a, pp);
+    }
+    return cudaGetLastError();
+}
+
+} // namespace sarpro

@@ -94,10 +94,7 @@ __host__ __device__ inline HPipeSmem hpipe_layout(bool clahe, uint32_t nsub, uin
     return L;
 }
 
-// A piece: rows [r0, r1) (inside one vertical CLAHE cell) of strip `strip`. CTA b runs pieces [first[b], first[b+1]).
-struct HPiece {
-    uint32_t strip, r0, r1, pad;
-};
+// A piece (HPiece, kernels.h): rows [r0, r1) of strip `strip`. CTA b runs pieces [first[b], first[b+1]).
 
 struct HPipeParams {
     const HStrip* strips;
