@@ -279,6 +279,7 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
                 if (!rc) rc = upload_vec(ctx, ap->m_ntile, mp.ntile.data(), mp.ntile.size() * sizeof(int4));
                 if (!rc) rc = upload_vec(ctx, ap->m_strips, mp.strips.data(), mp.strips.size() * sizeof(uint4));
                 ap->m_weights_h = mp.weights;
+                ap->m_b_bytes = mp.b_bytes;
                 ap->mma = rc == 0;
                 if (!rc) { // the plan vectors are temporaries
                     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -391,11 +392,11 @@ int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe,
 
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
     if (!pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap &&
-        (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && hmma_smem_bytes(src_kind, a.hot) <= 227 * 1024) {
+        (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && hmma_smem_bytes(src_kind, a.hot, ah->m_b_bytes) <= 227 * 1024) {
         RC(prepare_pieces(ctx, a.n_rows, row_off, src_kind == HSRC_DN_CLAHE, ah, 100));
         KS(SARPRO_STAGE_APPLY, launch_hmma(a, src_kind, (const uint4*)ah->m_btab.p, (const int4*)ah->m_ntile.p, (const uint4*)ah->m_strips.p,
                                            (const uint32_t*)ctx->pieces.p, (const uint32_t*)ctx->cta_first.p, ctx->pc_n_ctas, a.hot,
-                                           ctx->stream));
+                                           ah->m_b_bytes, ctx->stream));
         return 0;
     }
     if (!pix16 && ah->pipe && ctx->use_hpipe && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap) {

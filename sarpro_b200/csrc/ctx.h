@@ -42,6 +42,7 @@ struct AxisPlan {
     bool mma = false;
     DevBuf m_btab, m_ntile, m_strips;
     std::vector<HStrip> m_weights_h;
+    uint32_t m_b_bytes = 0;
     AxisDev dev() const {
         AxisDev d;
         d.start = (const uint32_t*)start.p;

@@ -158,14 +158,16 @@ struct HMmaPlanHost {
     std::vector<int4> ntile;     // {first block, last block, offset into btab in blocks, 0}
     std::vector<uint4> strips;   // {first n-tile, end n-tile, first block, end block}
     std::vector<HStrip> weights; // per strip, for hpipe_build_pieces (nvec = 8 * blocks)
+    uint32_t b_bytes = 0;        // tap bytes of the largest strip (staged in shared memory)
 };
 // max_span: longest source span of a strip in columns (CLAHE: the tile width), 0 = unbounded. false when the axis
 // does not fit the kernel (in_size not a multiple of 8, more than three n-tiles in flight, ...).
 bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int32_t* coef_h, uint32_t window, uint32_t out_size,
                      uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan);
-size_t hmma_smem_bytes(int src_kind, uint32_t hot);
+size_t hmma_smem_bytes(int src_kind, uint32_t hot, uint32_t b_bytes);
 cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,
-                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t hot, cudaStream_t stream);
+                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t hot, uint32_t b_bytes,
+                        cudaStream_t stream);
 // vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
                            void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream,

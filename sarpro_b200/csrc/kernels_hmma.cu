@@ -7,12 +7,12 @@
 // u8 x s8 / u8 x u8 -> s32 products, which is what mma.sync.m16n8k32 (IMMA.16832) computes. Integer, hence bit-exact
 // whatever the summation order.
 //
-// A warp owns 16 source rows and walks 64-column blocks along a strip. Per block, lane (g = lane/4, q = lane%4) loads
-// the 16 DNs of columns 64*cb + 16q .. +15 for rows g and g+8 (two 128-bit streaming loads per row, prefetched one
-// block ahead into the registers just consumed), turns them into samples, and the packed samples ARE the A fragments
-// of two k-steps: the k index of an MMA is only summed over, so the host lays the tap bytes of the B fragments out in
-// the same permuted order (column 16q + 8s + 4r + i  <->  k-step s, register r, byte i of lane q). No sample ever
-// goes through shared memory. An output n-tile (8 output columns) is live while the walk crosses its window
+// A warp owns 16 source rows and walks 64-column blocks (two k-steps of 32 columns) along a strip. Per k-step, lane
+// (g = lane/4, q = lane%4) loads the 8 DNs of columns 32*ks + 8q .. +7 for rows g and g+8 (128-bit streaming loads,
+// prefetched one block ahead into the registers just consumed), turns them into samples, and the packed samples ARE
+// the A fragments: the k index of an MMA is only summed over, so the host lays the tap bytes of the B fragments out in
+// the same permuted order (column 32*ks + 8q + 4r + i  <->  register r, byte i of lane q). No sample ever goes through
+// shared memory; the strip's B fragments are staged there once per piece. An output n-tile (8 output columns) is live while the walk crosses its window
 // (three accumulator slots, rotated), then it is scaled, clamped and stored.
 //
 // Per-pixel stage. LUT strategies: one shared-memory gather (R-way lane-interleaved table, as kernels_hpipe.cu).
@@ -39,6 +39,7 @@ constexpr uint32_t kThreads = 512, kWarps = 16;
 constexpr uint32_t kQuadEntries = 257;                       // 256 bins + the invalid-pixel entry
 constexpr uint32_t kQuadCellBytes = kQuadEntries * 8 * 16;   // one cell, 8 replicas
 constexpr int kSlots = 3;                                    // n-tiles in flight per warp
+constexpr uint32_t kMaxStripB = 80 * 1024;                   // B fragments of one strip (shared memory)
 constexpr float kBigC = 12582912.0f + 512.0f;                // u + kBigC (RD): low 16 bits = floor(u) + 512
 constexpr float kMarker = 480.0f;                            // floor of the marker entries (regular entries stay below 460)
 constexpr uint32_t kMarkerLess2 = (480u + 512u - 1u) * 0x10001u;
@@ -55,10 +56,23 @@ __device__ __forceinline__ float4 hm_lds_f4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
     return v;
 }
+// float4 at shared address a + off; off is warp-uniform, so the add folds into the LDS operand (R + UR)
+__device__ __forceinline__ float4 hm_lds_f4u(uint32_t a, uint32_t off) {
+    float4 v;
+    asm volatile("{ .reg .u32 t; add.u32 t, %4, %5; ld.shared.v4.f32 {%0,%1,%2,%3}, [t]; }"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(a), "r"(off));
+    return v;
+}
 __device__ __forceinline__ uint32_t hm_keep(uint32_t v) {
     uint32_t r;
     asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
     return r;
+}
+__device__ __forceinline__ uint4 hm_lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ uint4 hm_ldg_u4(const uint4* p) {
     uint4 r;
@@ -85,9 +99,9 @@ __device__ __forceinline__ void mma_u8u8(int (&c)[4], const uint32_t (&a)[4], ui
 }
 
 struct HMmaSmem {
-    uint32_t lut, quad, cdf, ctrl, total;
+    uint32_t lut, quad, cdf, ctrl, bfrag, total;
 };
-__host__ __device__ inline HMmaSmem hmma_layout(bool clahe, uint32_t lut_bytes) {
+__host__ __device__ inline HMmaSmem hmma_layout(bool clahe, uint32_t lut_bytes, uint32_t b_bytes) {
     HMmaSmem L;
     L.lut = 0;
     uint32_t o = (lut_bytes + 15) & ~15u;
@@ -97,17 +111,19 @@ __host__ __device__ inline HMmaSmem hmma_layout(bool clahe, uint32_t lut_bytes) 
     if (clahe) o += 6 * 256 * 8;
     L.ctrl = o;
     o += 64;
+    L.bfrag = o;
+    o += b_bytes;
     L.total = o;
     return L;
 }
 
 struct HMmaParams {
-    const uint4* btab;     // B fragments: [(boff + rel_block) * 2 + kstep][lane] = {hi r0, hi r1, lo r0, lo r1}
-    const int4* ntile;     // per n-tile: {first block, last block, boff, 0}
-    const uint4* strips;   // per strip: {first n-tile, end n-tile, first block, end block}
+    const uint4* btab;     // B fragments: [koff + (kstep - first kstep)][lane] = {hi r0, hi r1, lo r0, lo r1}
+    const int4* ntile;     // per n-tile: {first k-step, last k-step, koff, 0}; a k-step is 32 source columns
+    const uint4* strips;   // per strip: {first n-tile, end n-tile, first block, end block}; a block is two k-steps
     const HPiece* pieces;
     const uint32_t* cta_first;
-    uint32_t hot, lut_shift;
+    uint32_t hot, lut_shift, b_bytes; // b_bytes: the largest strip's B fragments (staged in shared memory)
 };
 
 // Error bound of the fp32 evaluation of one table entry (see the header), in sample units. X, Y bound |dx|, |dy|.
@@ -139,8 +155,8 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
     if (a.skip && *a.skip) return;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t hot = pp.hot, lut_shift = pp.lut_shift; // table word of DN idx, replica r: byte (idx << lut_shift) + 4r
-    const HMmaSmem L = hmma_layout(CLAHE, hot << lut_shift);
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, g = lane >> 2, q = lane & 3u;
+    const HMmaSmem L = hmma_layout(CLAHE, hot << lut_shift, pp.b_bytes);
+    const uint32_t tid = threadIdx.x, lane = hm_keep(tid & 31u), g = hm_keep(lane >> 2), q = hm_keep(lane & 3u);
     if (sbase + (hot << lut_shift) > 65536u) __trap(); // 16-bit table addresses (dynamic smem starts low on sm_100)
     uint32_t* const s_ctrl = reinterpret_cast<uint32_t*>(smem + L.ctrl);
 
@@ -171,12 +187,24 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
     // scale_u16_to_u8 (autoscale.rs:348-364) takes min/max over ALL samples, invalid pixels (written as 0) included
     uint32_t mn2 = 0xffffffffu, mx2 = 0u;   // fast path: u16x2 running min / max of floor(u) + 512 (not yet clamped)
     uint32_t mn_e = 0xffffffffu, mx_e = 0;  // exact-path samples
+    uint32_t staged_strip = 0xffffffffu;
+    const uint32_t sb_lane = hm_keep(sbase + L.bfrag + lane * 16u);
+    const uint32_t relu_c = hm_keep(0xFE00FE00u); // -512 per half
 
     for (uint32_t pi = pp.cta_first[blockIdx.x]; pi < pp.cta_first[blockIdx.x + 1]; ++pi) {
         const HPiece pc = pp.pieces[pi];
         const uint4 st = pp.strips[pc.strip]; // {j0, j1, cb0, cb1}
         __syncthreads(); // the previous piece is done with the tables
         if (tid == 0) { s_ctrl[0] = 0; s_ctrl[1] = 0xffffffffu; s_ctrl[2] = 0; }
+        const uint32_t koff0 = (uint32_t)pp.ntile[st.x].z;
+        if (staged_strip != pc.strip) { // the strip's B fragments
+            const int4 ml = pp.ntile[st.y - 1u];
+            const uint32_t n16 = ((uint32_t)ml.z + (uint32_t)(ml.y - ml.x + 1) - koff0) * 32u;
+            uint4* s_b = reinterpret_cast<uint4*>(smem + L.bfrag);
+            const uint4* gb = pp.btab + (size_t)koff0 * 32u;
+            for (uint32_t i = tid; i < n16; i += NT) s_b[i] = hm_ldg_u4(gb + i);
+            staged_strip = pc.strip;
+        }
 
         // ---- per-piece tables --------------------------------------------------------------------
         uint32_t cellA = 0, bcol = 0xffffffffu, fbits = 13;
@@ -317,7 +345,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
             float dyA = 0.f, dyB = 0.f;
             // saturated pixels of rows A / B: byte masks (0 / 0xff) "sample is 254" and "neither 254 nor 255" for the two
             // classes of columns (fl(omdx+dx) == 1.0 / == 1 - 2^-53); only read by the marker fix-up
-            uint32_t r254[2][2] = {{0, 0}, {0, 0}}, rodd[2][2] = {{0, 0}, {0, 0}};
+            uint32_t rowcls = 0; // bit rw*4 + cls*2: sample is 254; bit rw*4 + cls*2 + 1: neither 254 nor 255
             if (CLAHE) {
                 dyA = (float)a.clahe.row_dy[rA];
                 dyB = (float)a.clahe.row_dy[rB];
@@ -326,10 +354,8 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                     for (int rw = 0; rw < 2; ++rw) {
                         const uint32_t r = rw ? rB : rA;
                         const uint32_t s0 = a.clahe.row_sat[r], s1 = a.clahe.row_sat1[r];
-                        r254[rw][0] = s0 == 254u ? 0xffu : 0u;
-                        r254[rw][1] = s1 == 254u ? 0xffu : 0u;
-                        rodd[rw][0] = (s0 != 254u && s0 != 255u) ? 0xffu : 0u;
-                        rodd[rw][1] = (s1 != 254u && s1 != 255u) ? 0xffu : 0u;
+                        rowcls |= ((s0 == 254u ? 1u : 0u) | ((s0 != 254u && s0 != 255u) ? 2u : 0u) | (s1 == 254u ? 4u : 0u) |
+                                   ((s1 != 254u && s1 != 255u) ? 8u : 0u)) << (4 * rw);
                     }
                 }
             }
@@ -342,29 +368,17 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                 for (int i = 0; i < 4; ++i) acc[s][i] = 0;
                 sj[s] = st.x + s;
                 sfb[s] = 0xffffffffu; slb[s] = 0; sbo[s] = 0;
-                if (sj[s] < st.y) { const int4 m = pp.ntile[sj[s]]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = m.z; }
+                if (sj[s] < st.y) { const int4 m = pp.ntile[sj[s]]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = (m.z - koff0 - m.x) * 512u; }
             }
             // columns past the raster repeat its last 8-sample vector (they carry zero taps)
-            auto vec_col = [&](uint32_t cb, uint32_t h) { return min(cb * 64u + q * 16u + h * 8u, cols - 8u); };
-            uint4 d[4]; // [0] row A cols 0..7, [1] row A cols 8..15, [2] row B cols 0..7, [3] row B cols 8..15
+            auto vec_col = [&](uint32_t cb, uint32_t h) { return min(cb * 64u + h * 32u + q * 8u, cols - 8u); };
+            uint4 d[4]; // [0] row A k-step 0 (cols 8q..8q+7 of the block), [1] row A k-step 1 (cols 32+8q..), [2], [3]: row B
             {
                 const uint32_t c0 = vec_col(st.z, 0), c1 = vec_col(st.z, 1);
                 d[0] = hm_ld_dn(pA + c0); d[1] = hm_ld_dn(pA + c1);
                 d[2] = hm_ld_dn(pB + c0); d[3] = hm_ld_dn(pB + c1);
             }
             for (uint32_t cb = st.z; cb < st.w; ++cb) {
-                // B fragments of the n-tiles whose window meets this block
-                uint4 bq[hm::kSlots][2];
-                bool act[hm::kSlots];
-#pragma unroll
-                for (int s = 0; s < hm::kSlots; ++s) {
-                    act[s] = cb >= sfb[s] && cb <= slb[s];
-                    if (act[s]) {
-                        const uint4* p = pp.btab + ((size_t)(sbo[s] + (cb - sfb[s])) * 2u) * 32u + lane;
-                        bq[s][0] = hm_ldg_u4(p);
-                        bq[s][1] = hm_ldg_u4(p + 32);
-                    }
-                }
                 const bool more = cb + 1 < st.w;
                 uint32_t w[4][2]; // packed samples: [vector][px 0..3 / 4..7]
                 uint32_t riskmask = 0;
@@ -397,14 +411,14 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                             }
                         }
                     }
+                    if (!CLAHE) {
 #pragma unroll
-                    for (int rw = 0; rw < 2; ++rw) {
-                        const int v = rw * 2 + h;
-                        const uint4 cur = d[v];
-                        if (more) d[v] = hm_ld_dn((rw ? pB : pA) + cn);
-                        const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
-                        uint32_t pr[4];
-                        if (!CLAHE) {
+                        for (int rw = 0; rw < 2; ++rw) {
+                            const int v = rw * 2 + h;
+                            const uint4 cur = d[v];
+                            if (more) d[v] = hm_ld_dn((rw ? pB : pA) + cn);
+                            const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+                            uint32_t pr[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const uint32_t a2 = __vminu2(wv[j], cap2) * lut_mul + cj;
@@ -413,63 +427,93 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                             }
                             w[v][0] = __byte_perm(pr[0], pr[1], 0x6420);
                             w[v][1] = __byte_perm(pr[2], pr[3], 0x6420);
-                        } else {
-                            const float dy = rw ? dyB : dyA;
-                            uint32_t racc = 0;
-                            auto body = [&](auto tag_c) {
-                                constexpr uint32_t TAG = decltype(tag_c)::value;
-                                constexpr uint32_t OFF = TAG == 1 ? hm::kQuadCellBytes : 0u;
+                        }
+                    } else {
+                        // both rows of the k-step together: 16 table words first, then the bin entries in groups of four
+                        // (the shared loads are issued in source order, so the order below is the software pipeline)
+                        uint32_t e[2][8];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint32_t a2 = __vminu2(wv[j], cap2) * lut_mul + cj;
-                                    uint32_t e0 = hm_lds_u32(a2 & 0xffffu), e1 = hm_lds_u32(a2 >> 16);
-                                    float x0 = dx[2 * j], x1 = dx[2 * j + 1];
-                                    if (TAG == 2) { // the pixel's own cell: cell B columns sit one tile further (dx - 1)
-                                        const bool b0 = c0 + 2 * j >= bcol, b1 = c0 + 2 * j + 1 >= bcol;
-                                        const bool vb = c0 >= bcol; // dx[] was built for the vector's first column
-                                        if (b0) e0 += hm::kQuadCellBytes;
-                                        if (b1) e1 += hm::kQuadCellBytes;
-                                        if (b0 && !vb) x0 = __fsub_rn(x0, 1.0f);
-                                        if (b1 && !vb) x1 = __fsub_rn(x1, 1.0f);
-                                    }
-                                    const float4 q0 = hm_lds_f4<OFF>(e0), q1 = hm_lds_f4<OFF>(e1);
-                                    const float u0 = __fmaf_rn(__fmaf_rn(q0.w, x0, q0.z), dy, __fmaf_rn(q0.y, x0, q0.x));
-                                    const float u1 = __fmaf_rn(__fmaf_rn(q1.w, x1, q1.z), dy, __fmaf_rn(q1.y, x1, q1.x));
-                                    const uint32_t m0 = __float_as_uint(__fadd_rd(u0, magic_k));
-                                    const uint32_t m1 = __float_as_uint(__fadd_rd(u1, magic_k));
-                                    racc |= ((m0 - 1u) ^ m0) | ((m1 - 1u) ^ m1); // bit F set <=> the F fraction bits are all zero
-                                    pr[j] = __byte_perm(__float_as_uint(__fadd_rd(u0, hm::kBigC)), __float_as_uint(__fadd_rd(u1, hm::kBigC)), 0x5410);
+                        for (int rw = 0; rw < 2; ++rw) {
+                            const int v = rw * 2 + h;
+                            const uint4 cur = d[v];
+                            if (more) d[v] = hm_ld_dn((rw ? pB : pA) + cn);
+                            const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t a2 = __vminu2(wv[j], cap2) * lut_mul + cj;
+                                e[rw][2 * j] = hm_lds_u32(a2 & 0xffffu);
+                                e[rw][2 * j + 1] = hm_lds_u32(a2 >> 16);
+                            }
+                        }
+                        uint32_t celloff = tag == 1 ? hm::kQuadCellBytes : 0u; // warp-uniform
+                        if (tag == 2) { // the pixel's own cell: cell B columns sit one tile further (dx - 1)
+                            const bool vb = c0 >= bcol; // dx[] was built for the vector's first column
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                if (c0 + k >= bcol) {
+                                    e[0][k] += hm::kQuadCellBytes;
+                                    e[1][k] += hm::kQuadCellBytes;
+                                    if (!vb) dx[k] = __fsub_rn(dx[k], 1.0f);
                                 }
-                            };
-                            if (tag == 0) body(std::integral_constant<uint32_t, 0>{});
-                            else if (tag == 1) body(std::integral_constant<uint32_t, 1>{});
-                            else body(std::integral_constant<uint32_t, 2>{});
-                            bool risky = racc > fmask;
-                            const uint32_t k0 = __viaddmin_s16x2_relu(pr[0], 0xFE00FE00u, 0x00FF00FFu);
-                            const uint32_t k1 = __viaddmin_s16x2_relu(pr[1], 0xFE00FE00u, 0x00FF00FFu);
-                            const uint32_t k2 = __viaddmin_s16x2_relu(pr[2], 0xFE00FE00u, 0x00FF00FFu);
-                            const uint32_t k3 = __viaddmin_s16x2_relu(pr[3], 0xFE00FE00u, 0x00FF00FFu);
+                            }
+                        }
+                        uint32_t prr[2][4], racc[2] = {0, 0};
+                        float4 qa[4], qb[4];
+                        auto load4 = [&](float4 (&qq)[4], int rw, int k0) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) qq[i] = hm_lds_f4u(e[rw][k0 + i], celloff);
+                        };
+                        auto comp4 = [&](const float4 (&qq)[4], int rw, int k0) {
+                            const float dy = rw ? dyB : dyA;
+                            uint32_t lo[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float x = dx[k0 + i];
+                                const float u = __fmaf_rn(__fmaf_rn(qq[i].w, x, qq[i].z), dy, __fmaf_rn(qq[i].y, x, qq[i].x));
+                                const uint32_t m = __float_as_uint(__fadd_rd(u, magic_k));
+                                racc[rw] |= (m - 1u) ^ m; // bit F set <=> the F fraction bits are all zero
+                                lo[i] = __float_as_uint(__fadd_rd(u, hm::kBigC));
+                            }
+                            prr[rw][k0 / 2] = __byte_perm(lo[0], lo[1], 0x5410);
+                            prr[rw][k0 / 2 + 1] = __byte_perm(lo[2], lo[3], 0x5410);
+                        };
+                        load4(qa, 0, 0);
+                        load4(qb, 0, 4);
+                        comp4(qa, 0, 0);
+                        load4(qa, 1, 0);
+                        comp4(qb, 0, 4);
+                        load4(qb, 1, 4);
+                        comp4(qa, 1, 0);
+                        comp4(qb, 1, 4);
+#pragma unroll
+                        for (int rw = 0; rw < 2; ++rw) {
+                            const int v = rw * 2 + h;
+                            const uint32_t (&pr)[4] = prr[rw];
+                            bool risky = racc[rw] > fmask;
+                            const uint32_t k0 = __viaddmin_s16x2_relu(pr[0], relu_c, 0x00FF00FFu);
+                            const uint32_t k1 = __viaddmin_s16x2_relu(pr[1], relu_c, 0x00FF00FFu);
+                            const uint32_t k2 = __viaddmin_s16x2_relu(pr[2], relu_c, 0x00FF00FFu);
+                            const uint32_t k3 = __viaddmin_s16x2_relu(pr[3], relu_c, 0x00FF00FFu);
                             w[v][0] = __byte_perm(k0, k1, 0x6420);
                             w[v][1] = __byte_perm(k2, k3, 0x6420);
                             bool marked = false;
-                            if (fix) {
-                                // marker pixels (saturated entries, clamped to 255 above): 254 where the row / column class
-                                // says so (k_clahe_axis), the exact path for classes it does not cover
+                            // marker pixels (saturated entries of a cell without the closed form; clamped to 255 above): 254
+                            // where the row / column class says so (k_clahe_axis), the exact path for classes it does not cover
+                            if (fix && (__vimax3_u16x2(__vimax3_u16x2(pr[0], pr[1], pr[2]), pr[3], hm::kMarkerLess2) != hm::kMarkerLess2)) {
                                 uint32_t mk = 0;
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const uint32_t dd = __vminu2(pr[j], hm::kMarkerLess2) ^ pr[j];
                                     mk |= (((dd & 0xffffu) ? 1u : 0u) | ((dd >> 16) ? 2u : 0u)) << (2 * j);
                                 }
-                                if (mk) {
-                                    marked = true;
-                                    const uint32_t n254 = (cm0 & r254[rw][0]) | (cm1 & r254[rw][1]);
-                                    const uint32_t odd = (~(cm0 | cm1) & 0xffu) | (cm0 & rodd[rw][0]) | (cm1 & rodd[rw][1]);
-                                    if (mk & odd) risky = true;
-                                    const uint32_t fm = mk & n254;
-                                    w[v][0] -= ((fm & 15u) * 0x00204081u) & 0x01010101u;
-                                    w[v][1] -= ((fm >> 4) * 0x00204081u) & 0x01010101u;
-                                }
+                                marked = true;
+                                const uint32_t rc = rowcls >> (4 * rw);
+                                const uint32_t n254 = ((rc & 1u) ? cm0 : 0u) | ((rc & 4u) ? cm1 : 0u);
+                                const uint32_t odd = (~(cm0 | cm1) & 0xffu) | ((rc & 2u) ? cm0 : 0u) | ((rc & 8u) ? cm1 : 0u);
+                                if (mk & odd) risky = true;
+                                const uint32_t fm = mk & n254;
+                                w[v][0] -= ((fm & 15u) * 0x00204081u) & 0x01010101u;
+                                w[v][1] -= ((fm >> 4) * 0x00204081u) & 0x01010101u;
                             }
                             if (risky) {
                                 riskmask |= 1u << v;
@@ -496,7 +540,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                         const uint32_t sg = sl >> 2, sq = sl & 3u;
                         const uint32_t v = lane >> 3, k = lane & 7u; // my pixel of the flagged lane: vector v, sample k
                         const uint32_t r = min(rbase + sg + ((v & 2u) ? 8u : 0u), pc.r1 - 1u);
-                        const uint32_t c = min(cb * 64u + sq * 16u + (v & 1u) * 8u, cols - 8u) + k;
+                        const uint32_t c = min(cb * 64u + (v & 1u) * 32u + sq * 8u, cols - 8u) + k;
                         uint32_t b = exact_px(r, c) << (8u * (lane & 3u));
                         b |= __shfl_xor_sync(FULL, b, 1);
                         b |= __shfl_xor_sync(FULL, b, 2); // lanes 4m..4m+3 hold word m = samples 4m..4m+3 of the flagged lane
@@ -510,17 +554,26 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                 // ---- the taps: two k-steps per block ------------------------------------------------------
                 const uint32_t ka[4] = {w[0][0], w[2][0], w[0][1], w[2][1]};
                 const uint32_t kb[4] = {w[1][0], w[3][0], w[1][1], w[3][1]};
+                const uint32_t ks0 = cb * 2u;
 #pragma unroll
                 for (int s = 0; s < hm::kSlots; ++s) {
-                    if (act[s]) {
+                    // k-steps of this block inside the n-tile's window (an exhausted slot has sfb = ~0)
+                    const bool a0 = ks0 >= sfb[s] && ks0 <= slb[s], a1 = ks0 + 1u >= sfb[s] && ks0 + 1u <= slb[s];
+                    if (a0 || a1) {
                         int th[4] = {0, 0, 0, 0};
-                        mma_u8s8(th, ka, bq[s][0].x, bq[s][0].y);
-                        mma_u8u8(acc[s], ka, bq[s][0].z, bq[s][0].w);
-                        mma_u8s8(th, kb, bq[s][1].x, bq[s][1].y);
-                        mma_u8u8(acc[s], kb, bq[s][1].z, bq[s][1].w);
+                        if (a0) {
+                            const uint4 b = hm_lds_u4(sb_lane + sbo[s] + ks0 * 512u);
+                            mma_u8s8(th, ka, b.x, b.y);
+                            mma_u8u8(acc[s], ka, b.z, b.w);
+                        }
+                        if (a1) {
+                            const uint4 b = hm_lds_u4(sb_lane + sbo[s] + ks0 * 512u + 512u);
+                            mma_u8s8(th, kb, b.x, b.y);
+                            mma_u8u8(acc[s], kb, b.z, b.w);
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[s][i] += th[i] << 8;
-                        if (cb == slb[s]) { // the n-tile is complete: scale, clamp, store; the slot takes the next n-tile
+                        if (ks0 + 1u >= slb[s]) { // the n-tile is complete: scale, clamp, store; the slot takes the next n-tile
                             const uint32_t ox = sj[s] * 8u + q * 2u;
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -531,7 +584,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                             }
                             sj[s] += hm::kSlots;
                             sfb[s] = 0xffffffffu;
-                            if (sj[s] < st.y) { const int4 m = pp.ntile[sj[s]]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = m.z; }
+                            if (sj[s] < st.y) { const int4 m = pp.ntile[sj[s]]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = (m.z - koff0 - m.x) * 512u; }
                         }
                     }
                 }
@@ -561,9 +614,10 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
     plan->ntile.clear();
     plan->strips.clear();
     plan->weights.clear();
+    plan->b_bytes = 0;
     if (out_size == 0 || in_size < 8 || (in_size % 8) != 0) return false;
     const uint32_t n_nt = (out_size + 7) / 8;
-    uint32_t boff = 0;
+    uint32_t koff = 0;
     for (uint32_t j = 0; j < n_nt; ++j) {
         uint32_t ws = 0xffffffffu, we = 0;
         for (uint32_t ox = j * 8; ox < std::min(out_size, j * 8 + 8); ++ox) {
@@ -572,61 +626,65 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
             we = std::max(we, start_h[ox] + size_h[ox]);
         }
         if (we == 0) { ws = 0; we = 1; }
-        if (j && ws / 64 < (uint32_t)plan->ntile.back().x) return false; // windows must advance monotonically
-        if (j && (we - 1) / 64 < (uint32_t)plan->ntile.back().y) return false;
-        const uint32_t fb = ws / 64, lb = (we - 1) / 64;
-        plan->ntile.push_back(make_int4((int)fb, (int)lb, (int)boff, 0));
-        for (uint32_t cb = fb; cb <= lb; ++cb)
-            for (uint32_t s = 0; s < 2; ++s)
-                for (uint32_t lane = 0; lane < 32; ++lane) {
-                    const uint32_t n = lane >> 2, qq = lane & 3u, ox = j * 8 + n;
-                    uint32_t reg[4] = {0, 0, 0, 0}; // hi r0, hi r1, lo r0, lo r1
-                    for (uint32_t r = 0; r < 2; ++r)
-                        for (uint32_t i = 0; i < 4; ++i) {
-                            const uint32_t c = cb * 64 + qq * 16 + s * 8 + r * 4 + i;
-                            int32_t tap = 0;
-                            if (ox < out_size && c >= start_h[ox] && c < start_h[ox] + size_h[ox])
-                                tap = coef_h[(size_t)ox * window + (c - start_h[ox])];
-                            if (tap < -32768 || tap > 32767) return false;
-                            const uint32_t lo = (uint32_t)tap & 255u, hi = (uint32_t)(tap >> 8) & 255u;
-                            reg[r] |= hi << (8 * i);
-                            reg[2 + r] |= lo << (8 * i);
-                        }
-                    plan->btab.push_back(make_uint4(reg[0], reg[1], reg[2], reg[3]));
-                }
-        boff += lb - fb + 1;
+        const uint32_t fk = ws / 32, lk = (we - 1) / 32;
+        if (j && (fk < (uint32_t)plan->ntile.back().x || lk < (uint32_t)plan->ntile.back().y)) return false; // windows advance
+        plan->ntile.push_back(make_int4((int)fk, (int)lk, (int)koff, 0));
+        for (uint32_t ks = fk; ks <= lk; ++ks)
+            for (uint32_t lane = 0; lane < 32; ++lane) {
+                const uint32_t n = lane >> 2, qq = lane & 3u, ox = j * 8 + n;
+                uint32_t reg[4] = {0, 0, 0, 0}; // hi r0, hi r1, lo r0, lo r1
+                for (uint32_t r = 0; r < 2; ++r)
+                    for (uint32_t i = 0; i < 4; ++i) {
+                        // k-step ks holds columns 32*ks + 8*q + 4*r + i (the order the samples are packed in)
+                        const uint32_t c = ks * 32 + qq * 8 + r * 4 + i;
+                        int32_t tap = 0;
+                        if (ox < out_size && c >= start_h[ox] && c < start_h[ox] + size_h[ox])
+                            tap = coef_h[(size_t)ox * window + (c - start_h[ox])];
+                        if (tap < -32768 || tap > 32767) return false;
+                        const uint32_t lo = (uint32_t)tap & 255u, hi = (uint32_t)(tap >> 8) & 255u;
+                        reg[r] |= hi << (8 * i);
+                        reg[2 + r] |= lo << (8 * i);
+                    }
+                plan->btab.push_back(make_uint4(reg[0], reg[1], reg[2], reg[3]));
+            }
+        koff += lk - fk + 1;
     }
     // strips
     uint32_t j0 = 0;
     while (j0 < n_nt) {
         uint32_t j1 = j0 + 1;
-        auto span = [&](uint32_t e) { return ((uint32_t)plan->ntile[e - 1].y + 1 - (uint32_t)plan->ntile[j0].x) * 64u; };
-        if (max_span && span(j1) > max_span) return false;
-        while (j1 < n_nt && j1 - j0 < 32 && (!max_span || span(j1 + 1) <= max_span)) ++j1;
-        const uint32_t cb0 = (uint32_t)plan->ntile[j0].x, cb1 = (uint32_t)plan->ntile[j1 - 1].y + 1;
-        // at most kSlots n-tiles of the strip meet any block, and n-tile j + kSlots starts after n-tile j ends
+        auto span = [&](uint32_t e) { return ((uint32_t)plan->ntile[e - 1].y / 2 + 1 - (uint32_t)plan->ntile[j0].x / 2) * 64u; };
+        auto bbytes = [&](uint32_t e) {
+            return ((uint32_t)plan->ntile[e - 1].z + (uint32_t)(plan->ntile[e - 1].y - plan->ntile[e - 1].x + 1) - (uint32_t)plan->ntile[j0].z) * 512u;
+        };
+        if ((max_span && span(j1) > max_span) || bbytes(j1) > hm::kMaxStripB) return false;
+        while (j1 < n_nt && j1 - j0 < 32 && (!max_span || span(j1 + 1) <= max_span) && bbytes(j1 + 1) <= hm::kMaxStripB) ++j1;
+        const uint32_t cb0 = (uint32_t)plan->ntile[j0].x / 2, cb1 = (uint32_t)plan->ntile[j1 - 1].y / 2 + 1;
+        // at most kSlots n-tiles of the strip meet any block, so n-tile j + kSlots starts after n-tile j has ended
         for (uint32_t cb = cb0; cb < cb1; ++cb) {
             uint32_t n = 0;
             for (uint32_t j = j0; j < j1; ++j)
-                if ((uint32_t)plan->ntile[j].x <= cb && cb <= (uint32_t)plan->ntile[j].y) ++n;
+                if ((uint32_t)plan->ntile[j].x / 2 <= cb && cb <= (uint32_t)plan->ntile[j].y / 2) ++n;
             if (n > (uint32_t)hm::kSlots) return false;
         }
         plan->strips.push_back(make_uint4(j0, j1, cb0, cb1));
         plan->weights.push_back(HStrip{cb0 * 64, (cb1 - cb0) * 8});
+        plan->b_bytes = std::max(plan->b_bytes, bbytes(j1));
         j0 = j1;
     }
     return true;
 }
 
-size_t hmma_smem_bytes(int src_kind, uint32_t hot) {
-    return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hpipe_lut_shift(hot)).total;
+size_t hmma_smem_bytes(int src_kind, uint32_t hot, uint32_t b_bytes) {
+    return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hpipe_lut_shift(hot), b_bytes).total;
 }
 
 cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,
-                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t hot, cudaStream_t stream) {
+                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t hot, uint32_t b_bytes,
+                        cudaStream_t stream) {
     if (a.n_rows == 0 || a.ax.out_size == 0 || n_ctas == 0) return cudaSuccess;
     const bool clahe = src_kind == HSRC_DN_CLAHE;
-    const size_t smem = hmma_smem_bytes(src_kind, hot);
+    const size_t smem = hmma_smem_bytes(src_kind, hot, b_bytes);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     HMmaParams pp;
     pp.btab = btab_dev;
@@ -636,6 +694,7 @@ cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_de
     pp.cta_first = cta_first_dev;
     pp.hot = hot;
     pp.lut_shift = hpipe_lut_shift(hot);
+    pp.b_bytes = b_bytes;
     if (clahe) {
         static size_t configured = 0;
         if (smem > configured) {
