@@ -40,6 +40,7 @@ constexpr uint32_t kQuadEntries = 257;                       // 256 bins + the i
 constexpr uint32_t kQuadCellBytes = kQuadEntries * 8 * 16;   // one cell, 8 replicas
 constexpr int kSlots = 3;                                    // n-tiles in flight per warp
 constexpr uint32_t kMaxStripB = 80 * 1024;                   // B fragments of one strip (shared memory)
+constexpr uint32_t kMaxStripVecs = 1024;                     // 8-column vectors of one strip (128 blocks)
 constexpr float kBigC = 12582912.0f + 512.0f;                // u + kBigC (RD): low 16 bits = floor(u) + 512
 constexpr float kMarker = 480.0f;                            // floor of the marker entries (regular entries stay below 460)
 constexpr uint32_t kMarkerLess2 = (480u + 512u - 1u) * 0x10001u;
@@ -99,7 +100,7 @@ __device__ __forceinline__ void mma_u8u8(int (&c)[4], const uint32_t (&a)[4], ui
 }
 
 struct HMmaSmem {
-    uint32_t lut, quad, cdf, ctrl, bfrag, total;
+    uint32_t lut, quad, cdf, ctrl, nt, cm, bfrag, total;
 };
 __host__ __device__ inline HMmaSmem hmma_layout(bool clahe, uint32_t lut_bytes, uint32_t b_bytes) {
     HMmaSmem L;
@@ -111,6 +112,10 @@ __host__ __device__ inline HMmaSmem hmma_layout(bool clahe, uint32_t lut_bytes, 
     if (clahe) o += 6 * 256 * 8;
     L.ctrl = o;
     o += 64;
+    L.nt = o;   // n-tile table of the strip: {first k-step, last k-step, byte offset of its fragments - first*512, 0}
+    o += 32 * 16;
+    L.cm = o;   // per 8-column vector of the strip: columns with fl(omdx+dx) == 1.0 | (== 1 - 2^-53) << 8
+    if (clahe) o += hm::kMaxStripVecs * 2;
     L.bfrag = o;
     o += b_bytes;
     L.total = o;
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t hot = pp.hot, lut_shift = pp.lut_shift; // table word of DN idx, replica r: byte (idx << lut_shift) + 4r
     const HMmaSmem L = hmma_layout(CLAHE, hot << lut_shift, pp.b_bytes);
+    const uint32_t cols = a.src_cols;
     const uint32_t tid = threadIdx.x, lane = hm_keep(tid & 31u), g = hm_keep(lane >> 2), q = hm_keep(lane & 3u);
     if (sbase + (hot << lut_shift) > 65536u) __trap(); // 16-bit table addresses (dynamic smem starts low on sm_100)
     uint32_t* const s_ctrl = reinterpret_cast<uint32_t*>(smem + L.ctrl);
@@ -177,12 +183,11 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
             s_lut4[i] = v;
         }
     }
-    const uint32_t cols = a.src_cols;
     const uint32_t cap2 = hm_keep((hot - 1u) * 0x10001u);
     const uint32_t lut_mul = hm_keep(1u << lut_shift);
     const uint32_t cj = hm_keep((sbase + L.lut + (lane & ((lut_mul >> 2) - 1u)) * 4u) * 0x10001u);
     const int prec = a.ax.precision;
-    const int acc0 = prec > 0 ? (1 << (prec - 1)) : 0;
+    const int acc0 = (int)hm_keep(prec > 0 ? (1u << (prec - 1)) : 0u);
     const uint16_t* const src = reinterpret_cast<const uint16_t*>(a.src);
     // scale_u16_to_u8 (autoscale.rs:348-364) takes min/max over ALL samples, invalid pixels (written as 0) included
     uint32_t mn2 = 0xffffffffu, mx2 = 0u;   // fast path: u16x2 running min / max of floor(u) + 512 (not yet clamped)
@@ -203,6 +208,26 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
             uint4* s_b = reinterpret_cast<uint4*>(smem + L.bfrag);
             const uint4* gb = pp.btab + (size_t)koff0 * 32u;
             for (uint32_t i = tid; i < n16; i += NT) s_b[i] = hm_ldg_u4(gb + i);
+            int4* s_nt = reinterpret_cast<int4*>(smem + L.nt);
+            for (uint32_t i = tid; i < st.y - st.x; i += NT) {
+                const int4 m = pp.ntile[st.x + i];
+                s_nt[i] = make_int4(m.x, m.y, (int)(((uint32_t)m.z - koff0 - (uint32_t)m.x) * 512u), 0);
+            }
+            if (CLAHE) {
+                uint16_t* s_cm = reinterpret_cast<uint16_t*>(smem + L.cm);
+                for (uint32_t i = tid; i < (st.w - st.z) * 8u; i += NT) {
+                    const uint32_t c = min(st.z * 64u + i * 8u, cols - 8u);
+                    const uint4 ct = *reinterpret_cast<const uint4*>(a.clahe.col_t + c);
+                    const uint32_t cw[4] = {ct.x, ct.y, ct.z, ct.w};
+                    uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        m0 |= (((cw[j] >> 7) & 1u) | ((cw[j] >> 22) & 2u)) << (2 * j);
+                        m1 |= (((cw[j] >> 6) & 1u) | ((cw[j] >> 21) & 2u)) << (2 * j);
+                    }
+                    s_cm[i] = (uint16_t)(m0 | (m1 << 8));
+                }
+            }
             staged_strip = pc.strip;
         }
 
@@ -303,6 +328,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
         }
         __syncthreads();
         const uint32_t fmask = hm_keep((1u << fbits) - 1u);
+        const int twA = (int)hm_keep(a.clahe.tile_w * (2u * cellA + 1u)), twB = (int)hm_keep(a.clahe.tile_w * (2u * cellA + 3u));
         const float magic_k = __uint_as_float(hm_keep(__float_as_uint(magic)));
 
         // exact u8 sample of pixel (r, c) (local row, column) with the reference's f64 operation order
@@ -327,6 +353,8 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
             return o;
         };
 
+        const int4* const s_nt = reinterpret_cast<const int4*>(smem + L.nt);
+        const uint16_t* const s_cm = reinterpret_cast<const uint16_t*>(smem + L.cm);
         // ---- 16-row groups of the piece, handed out to the warps --------------------------------------
         const uint32_t n_groups = (pc.r1 - pc.r0 + 15u) / 16u;
         for (;;) {
@@ -337,8 +365,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
             const uint32_t rbase = pc.r0 + grp * 16u;
             // rows beyond the piece repeat its last row (never stored; duplicates do not disturb the min / max)
             const uint32_t rA = min(rbase + g, pc.r1 - 1u), rB = min(rbase + g + 8u, pc.r1 - 1u);
-            const uint16_t* const pA = src + (size_t)rA * cols;
-            const uint16_t* const pB = src + (size_t)rB * cols;
+            const uint32_t oA = rA * cols, oB = rB * cols; // element offsets (< 2^32 for any raster in HBM)
             const bool okA_row = rbase + g < pc.r1, okB_row = rbase + g + 8u < pc.r1;
             uint8_t* const tA = reinterpret_cast<uint8_t*>(a.temp) + (size_t)(rbase + g - a.row0) * a.ax.out_size;
             uint8_t* const tB = tA + (size_t)8 * a.ax.out_size;
@@ -368,47 +395,41 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                 for (int i = 0; i < 4; ++i) acc[s][i] = 0;
                 sj[s] = st.x + s;
                 sfb[s] = 0xffffffffu; slb[s] = 0; sbo[s] = 0;
-                if (sj[s] < st.y) { const int4 m = pp.ntile[sj[s]]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = (m.z - koff0 - m.x) * 512u; }
+                if (sj[s] < st.y) { const int4 m = s_nt[sj[s] - st.x]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = m.z; }
             }
             // columns past the raster repeat its last 8-sample vector (they carry zero taps)
             auto vec_col = [&](uint32_t cb, uint32_t h) { return min(cb * 64u + h * 32u + q * 8u, cols - 8u); };
             uint4 d[4]; // [0] row A k-step 0 (cols 8q..8q+7 of the block), [1] row A k-step 1 (cols 32+8q..), [2], [3]: row B
             {
                 const uint32_t c0 = vec_col(st.z, 0), c1 = vec_col(st.z, 1);
-                d[0] = hm_ld_dn(pA + c0); d[1] = hm_ld_dn(pA + c1);
-                d[2] = hm_ld_dn(pB + c0); d[3] = hm_ld_dn(pB + c1);
+                d[0] = hm_ld_dn(src + (oA + c0)); d[1] = hm_ld_dn(src + (oA + c1));
+                d[2] = hm_ld_dn(src + (oB + c0)); d[3] = hm_ld_dn(src + (oB + c1));
             }
             for (uint32_t cb = st.z; cb < st.w; ++cb) {
                 const bool more = cb + 1 < st.w;
                 uint32_t w[4][2]; // packed samples: [vector][px 0..3 / 4..7]
                 uint32_t riskmask = 0;
+                // block entirely in cell A / entirely in cell B / holds the boundary (per-pixel select)
+                const uint32_t tag = !CLAHE ? 0u : ((cb * 64u + 64u <= bcol) ? 0u : (cb * 64u >= bcol ? 1u : 2u));
+                const bool fix = CLAHE && (tag == 0 ? fixA : (tag == 1 ? fixB : (fixA || fixB)));
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t c0 = vec_col(cb, h);
                     const uint32_t cn = vec_col(cb + 1, h);
                     float dx[8];
-                    uint32_t tag = 0;
                     uint32_t cm0 = 0, cm1 = 0; // columns of the vector with fl(omdx+dx) == 1.0 / == 1 - 2^-53 (bit per column)
-                    bool fix = false;
                     if (CLAHE) {
-                        // block entirely in cell A / entirely in cell B / holds the boundary (per-pixel select)
-                        tag = (cb * 64u + 64u <= bcol) ? 0u : (cb * 64u >= bcol ? 1u : 2u);
-                        // dx = m / (2*tile_w), m = 2c - tile_w*(2t+1) (k_clahe_axis); fp32: |dxf - dx| < 2e-7
-                        const uint32_t t0 = tag == 0 ? cellA : (tag == 1 ? cellA + 1u : (c0 >= bcol ? cellA + 1u : cellA));
-                        const int m0 = 2 * (int)c0 - (int)a.clahe.tile_w * (2 * (int)t0 + 1);
+                        // dx = m / (2*tile_w), m = 2c - tile_w*(2t+1) (k_clahe_axis), t = the cell of the vector's first column;
+                        // fp32: |dxf - dx| < 2e-7
+                        const int m0 = 2 * (int)c0 - (c0 >= bcol ? twB : twA);
                         const float dx0 = __fmul_rn((float)m0, a.clahe.inv2tw);
                         const float dstep = __fmul_rn(2.0f, a.clahe.inv2tw);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) dx[k] = __fmaf_rn((float)k, dstep, dx0);
-                        fix = tag == 0 ? fixA : (tag == 1 ? fixB : (fixA || fixB));
                         if (fix) {
-                            const uint4 ct = *reinterpret_cast<const uint4*>(a.clahe.col_t + c0);
-                            const uint32_t cw[4] = {ct.x, ct.y, ct.z, ct.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                cm0 |= (((cw[j] >> 7) & 1u) | ((cw[j] >> 22) & 2u)) << (2 * j);
-                                cm1 |= (((cw[j] >> 6) & 1u) | ((cw[j] >> 21) & 2u)) << (2 * j);
-                            }
+                            const uint32_t cmw = s_cm[(cb - st.z) * 8u + h * 4u + q]; // (beyond the raster: the clamped vector's)
+                            cm0 = cmw & 255u;
+                            cm1 = cmw >> 8;
                         }
                     }
                     if (!CLAHE) {
@@ -416,7 +437,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                         for (int rw = 0; rw < 2; ++rw) {
                             const int v = rw * 2 + h;
                             const uint4 cur = d[v];
-                            if (more) d[v] = hm_ld_dn((rw ? pB : pA) + cn);
+                            if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn));
                             const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
                             uint32_t pr[4];
 #pragma unroll
@@ -436,7 +457,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                         for (int rw = 0; rw < 2; ++rw) {
                             const int v = rw * 2 + h;
                             const uint4 cur = d[v];
-                            if (more) d[v] = hm_ld_dn((rw ? pB : pA) + cn);
+                            if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn));
                             const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -584,7 +605,7 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                             }
                             sj[s] += hm::kSlots;
                             sfb[s] = 0xffffffffu;
-                            if (sj[s] < st.y) { const int4 m = pp.ntile[sj[s]]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = (m.z - koff0 - m.x) * 512u; }
+                            if (sj[s] < st.y) { const int4 m = s_nt[sj[s] - st.x]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = m.z; }
                         }
                     }
                 }
@@ -657,8 +678,10 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
         auto bbytes = [&](uint32_t e) {
             return ((uint32_t)plan->ntile[e - 1].z + (uint32_t)(plan->ntile[e - 1].y - plan->ntile[e - 1].x + 1) - (uint32_t)plan->ntile[j0].z) * 512u;
         };
-        if ((max_span && span(j1) > max_span) || bbytes(j1) > hm::kMaxStripB) return false;
-        while (j1 < n_nt && j1 - j0 < 32 && (!max_span || span(j1 + 1) <= max_span) && bbytes(j1 + 1) <= hm::kMaxStripB) ++j1;
+        if ((max_span && span(j1) > max_span) || bbytes(j1) > hm::kMaxStripB || span(j1) > hm::kMaxStripVecs * 8u) return false;
+        while (j1 < n_nt && j1 - j0 < 32 && (!max_span || span(j1 + 1) <= max_span) && bbytes(j1 + 1) <= hm::kMaxStripB &&
+               span(j1 + 1) <= hm::kMaxStripVecs * 8u)
+            ++j1;
         const uint32_t cb0 = (uint32_t)plan->ntile[j0].x / 2, cb1 = (uint32_t)plan->ntile[j1 - 1].y / 2 + 1;
         // at most kSlots n-tiles of the strip meet any block, so n-tile j + kSlots starts after n-tile j has ended
         for (uint32_t cb = cb0; cb < cb1; ++cb) {
