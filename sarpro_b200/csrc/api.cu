@@ -796,6 +796,15 @@ int end_call(sarpro_ctx* ctx) {
         ctx->timing.stage_ms[ctx->sev_stage[i]] += t;
         ctx->timing.stage_launches[ctx->sev_stage[i]]++;
     }
+    if (getenv("SARPRO_TRACE")) { // exploration: device timeline of the stage-timed launches of this call
+        for (int i = 0; i < ctx->n_sev; ++i) {
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, ctx->ev[0], ctx->sev[2 * i]);
+            cudaEventElapsedTime(&t1, ctx->ev[0], ctx->sev[2 * i + 1]);
+            fprintf(stderr, "trace %2d stage %d  %8.3f -> %8.3f ms (%.3f)\n", i, ctx->sev_stage[i], t0, t1, t1 - t0);
+        }
+        fprintf(stderr, "trace total %.3f ms\n", ms);
+    }
     return 0;
 }
 

@@ -436,14 +436,14 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
 #pragma unroll
                         for (int rw = 0; rw < 2; ++rw) {
                             const int v = rw * 2 + h;
-                            const uint4 cur = d[v];
-                            if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn));
-                            const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
-                            uint32_t pr[4];
+                            const uint32_t wv[4] = {d[v].x, d[v].y, d[v].z, d[v].w};
+                            uint32_t a2[4], pr[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) a2[j] = __vminu2(wv[j], cap2) * lut_mul + cj;
+                            if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn)); // the DNs are consumed: prefetch in place
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const uint32_t a2 = __vminu2(wv[j], cap2) * lut_mul + cj;
-                                const uint32_t e0 = hm_lds_u32(a2 & 0xffffu), e1 = hm_lds_u32(a2 >> 16);
+                                const uint32_t e0 = hm_lds_u32(a2[j] & 0xffffu), e1 = hm_lds_u32(a2[j] >> 16);
                                 pr[j] = __byte_perm(e0, e1, 0x5410);
                             }
                             w[v][0] = __byte_perm(pr[0], pr[1], 0x6420);
@@ -456,14 +456,15 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
 #pragma unroll
                         for (int rw = 0; rw < 2; ++rw) {
                             const int v = rw * 2 + h;
-                            const uint4 cur = d[v];
-                            if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn));
-                            const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+                            const uint32_t wv[4] = {d[v].x, d[v].y, d[v].z, d[v].w};
+                            uint32_t a2[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) a2[j] = __vminu2(wv[j], cap2) * lut_mul + cj;
+                            if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn)); // the DNs are consumed: prefetch in place
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const uint32_t a2 = __vminu2(wv[j], cap2) * lut_mul + cj;
-                                e[rw][2 * j] = hm_lds_u32(a2 & 0xffffu);
-                                e[rw][2 * j + 1] = hm_lds_u32(a2 >> 16);
+                                e[rw][2 * j] = hm_lds_u32(a2[j] & 0xffffu);
+                                e[rw][2 * j + 1] = hm_lds_u32(a2[j] >> 16);
                             }
                         }
                         uint32_t celloff = tag == 1 ? hm::kQuadCellBytes : 0u; // warp-uniform

@@ -182,22 +182,41 @@ def test_f32_edge_cases(ctx):
 
 
 @pytest.mark.parametrize("strategy", [S.CLAHE, S.ROBUST, S.TAMED])
-@pytest.mark.parametrize("shape,target", [((3001, 4999), 1024), ((2500, 9000), 700), ((5003, 2001), 512)])
+@pytest.mark.parametrize("shape,target", [((3001, 4999), 1024), ((2500, 9000), 700), ((5003, 2001), 512), ((3001, 5000), 1024),
+                                          ((1031, 2048), 300), ((517, 25000), 2048), ((2100, 4096), 2048)])
 def test_production_kernels_match_exact_kernels(strategy, shape, target, monkeypatch):
-    """The production pass B (kernels_hpipe.cu: fp32 bilinear form + fix-up queue, lane-interleaved tables, clamped
-    table range) against the generic exact kernels (SARPRO_FORCE_EXACT=1) and the previous production kernel
-    (SARPRO_HPIPE=0) on rasters large enough for several strips, CLAHE cells and row blocks; bright point targets
-    exercise the clamped table range. The exact kernels are the ones the other tests pin to the oracle."""
+    """The production pass-B kernels against the generic exact kernels (SARPRO_FORCE_EXACT=1, the ones the other tests
+    pin to the oracle) on rasters large enough for several strips, CLAHE cells and row groups: the tensor-core kernel
+    (kernels_hmma.cu: IMMA taps, fp32 bilinear form with truncation-bit risk test, warp-cooperative exact fix-up, marker
+    fix-up of saturated bins in the border cells; used when the column count is a multiple of 8), the second-generation
+    kernels (SARPRO_HMMA=0, kernels_hpipe.cu) and the first production kernel (SARPRO_HPIPE=0). Bright point targets
+    exercise the clamped table range, the zeroed block the invalid-pixel entry."""
     from sarpro_b200.synth import synth_pair
     vv, vh = synth_pair(*shape, point_targets=1e-4)
     vv[shape[0] // 2:, -300:] = 0  # invalid block on the right edge
     outs = []
-    for env in ({"SARPRO_FORCE_EXACT": "1"}, {"SARPRO_HPIPE": "0"}, {"SARPRO_HPIPE": "1"}):
-        for k in ("SARPRO_FORCE_EXACT", "SARPRO_HPIPE"):
+    envs = ({"SARPRO_FORCE_EXACT": "1"}, {"SARPRO_HMMA": "0", "SARPRO_HPIPE": "0"}, {"SARPRO_HMMA": "0"}, {})
+    for env in envs:
+        for k in ("SARPRO_FORCE_EXACT", "SARPRO_HPIPE", "SARPRO_HMMA"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         with S.Context(0) as c:
             outs.append(c.process_synrgb_jpeg(vv, vh, strategy, target, True).rgb.copy())
-    assert np.array_equal(outs[0], outs[1]), int((outs[0] != outs[1]).sum())
-    assert np.array_equal(outs[0], outs[2]), int((outs[0] != outs[2]).sum())
+    for i in range(1, len(outs)):
+        assert np.array_equal(outs[0], outs[i]), (envs[i], int((outs[0] != outs[i]).sum()))
+
+
+def test_tensor_core_pass_b_against_oracle(ctx):
+    """kernels_hmma.cu straight against the CPU oracle (columns a multiple of 8, partial last row group, point targets,
+    an invalid block), CLAHE and a LUT strategy, u8 single band and synRGB."""
+    from sarpro_b200.synth import synth_pair
+    vv, vh = synth_pair(1211, 2048, point_targets=1e-4)
+    vv[300:500, -120:] = 0
+    for strategy in (S.CLAHE, S.ROBUST):
+        ref, _ = O.pipeline_single(vv.astype(np.float32), O.TIFF, S.U8, strategy, 640, True)
+        img = ctx.process_single(vv, S.TIFF, S.U8, strategy, 640, True)
+        assert np.array_equal(img.gray, ref), (strategy, int((img.gray != ref).sum()))
+    ref, _ = O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), S.CLAHE, 1024, True)
+    img = ctx.process_synrgb_jpeg(vv, vh, S.CLAHE, 1024, True)
+    assert np.array_equal(img.rgb, ref), int((img.rgb != ref).sum())
