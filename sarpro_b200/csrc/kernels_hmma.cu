@@ -553,6 +553,18 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                         }
                     }
                 }
+                // tap fragments of the k-steps of this block that lie inside the windows of the n-tiles in flight (an
+                // exhausted slot has sfb = ~0); in flight while the fix-up below runs
+                const uint32_t ks0 = cb * 2u;
+                uint4 bf[hm::kSlots][2];
+                bool a0[hm::kSlots], a1[hm::kSlots];
+#pragma unroll
+                for (int s = 0; s < hm::kSlots; ++s) {
+                    a0[s] = ks0 >= sfb[s] && ks0 <= slb[s];
+                    a1[s] = ks0 + 1u >= sfb[s] && ks0 + 1u <= slb[s];
+                    if (a0[s]) bf[s][0] = hm_lds_u4(sb_lane + sbo[s] + ks0 * 512u);
+                    if (a1[s]) bf[s][1] = hm_lds_u4(sb_lane + sbo[s] + ks0 * 512u + 512u);
+                }
                 if (CLAHE) {
                     // exact fix-up: the 32 pixels of a flagged lane, one per lane
                     uint32_t need = __ballot_sync(FULL, riskmask != 0);
@@ -576,22 +588,17 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                 // ---- the taps: two k-steps per block ------------------------------------------------------
                 const uint32_t ka[4] = {w[0][0], w[2][0], w[0][1], w[2][1]};
                 const uint32_t kb[4] = {w[1][0], w[3][0], w[1][1], w[3][1]};
-                const uint32_t ks0 = cb * 2u;
 #pragma unroll
                 for (int s = 0; s < hm::kSlots; ++s) {
-                    // k-steps of this block inside the n-tile's window (an exhausted slot has sfb = ~0)
-                    const bool a0 = ks0 >= sfb[s] && ks0 <= slb[s], a1 = ks0 + 1u >= sfb[s] && ks0 + 1u <= slb[s];
-                    if (a0 || a1) {
+                    if (a0[s] || a1[s]) {
                         int th[4] = {0, 0, 0, 0};
-                        if (a0) {
-                            const uint4 b = hm_lds_u4(sb_lane + sbo[s] + ks0 * 512u);
-                            mma_u8s8(th, ka, b.x, b.y);
-                            mma_u8u8(acc[s], ka, b.z, b.w);
+                        if (a0[s]) {
+                            mma_u8s8(th, ka, bf[s][0].x, bf[s][0].y);
+                            mma_u8u8(acc[s], ka, bf[s][0].z, bf[s][0].w);
                         }
-                        if (a1) {
-                            const uint4 b = hm_lds_u4(sb_lane + sbo[s] + ks0 * 512u + 512u);
-                            mma_u8s8(th, kb, b.x, b.y);
-                            mma_u8u8(acc[s], kb, b.z, b.w);
+                        if (a1[s]) {
+                            mma_u8s8(th, kb, bf[s][1].x, bf[s][1].y);
+                            mma_u8u8(acc[s], kb, bf[s][1].z, bf[s][1].w);
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[s][i] += th[i] << 8;
@@ -699,8 +706,11 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
     return true;
 }
 
+// 32 lane-private replicas (conflict-free gathers) when the table still fits the 16-bit address range, else 16 or 8
+static uint32_t hmma_lut_shift(uint32_t hot) { return hot <= 500 ? 7u : hpipe_lut_shift(hot); }
+
 size_t hmma_smem_bytes(int src_kind, uint32_t hot, uint32_t b_bytes) {
-    return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hpipe_lut_shift(hot), b_bytes).total;
+    return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hmma_lut_shift(hot), b_bytes).total;
 }
 
 cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,
@@ -717,7 +727,7 @@ cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_de
     pp.pieces = reinterpret_cast<const HPiece*>(pieces_dev);
     pp.cta_first = cta_first_dev;
     pp.hot = hot;
-    pp.lut_shift = hpipe_lut_shift(hot);
+    pp.lut_shift = hmma_lut_shift(hot);
     pp.b_bytes = b_bytes;
     if (clahe) {
         static size_t configured = 0;
