@@ -14,10 +14,11 @@ synthetic scene.
   cpu_baseline  the CPU oracle (a C++ restatement of the reference's serial path) on a bounded crop of
           the same scene, on this box's host cores.
 
-N > 1 (torchrun, one rank per GPU): ONE scene row-band-sharded over the ranks (BASELINE config 3): every rank holds
-its band plus the Lanczos halo, the library all-reduces the integer DN / CLAHE-tile histograms, the CLAHE min/max
-and the resized rows over NCCL ("strong" scaling, result bit-identical to 1 GPU). The same run also times the batch
-mode of config 5 (one whole scene per rank, no collective) and reports it under "batch_mode".
+N > 1 (torchrun, one rank per GPU): `value` / `e2e` are the batch mode of BASELINE config 5 — one whole scene per rank per
+step, no collective on the data path ("weak" scaling: per-GPU work fixed). The same run also times ONE scene
+row-band-sharded over the ranks (config 3: every rank holds its band plus the Lanczos halo, the library all-reduces the
+integer DN / CLAHE-tile histograms, the CLAHE min/max and the resized rows over NCCL; "strong" scaling, result bit-identical
+to 1 GPU) and reports it under "sharded_mode".
 `--impl reference` times the oracle (the reference cannot be built here: no Rust toolchain) on a
 bounded sample with all host threads its threaded stage (the Lanczos resize) can use.
 """
@@ -216,18 +217,11 @@ def main():
         return ms / steps, acc, (w0, w1)
 
     sampler = ClockSampler(local_rank)
-    if sharded:
-        uid = [S.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0], rank, world)
-        vv_full, vh_full = make_scene(0)          # every rank synthesises the same scene and keeps its rows
-        h0, h1 = S.shard_halo_rows(rows, cols, TARGET, world, rank, strategy == S.CLAHE)
-        vv, vh = vv_full[h0:h1], vh_full[h0:h1]   # contiguous row slices (views)
-        step = lambda: ctx.process_synrgb_sharded(vv, vh, rows, strategy, TARGET, True, out=out_dev)
-    else:
-        vv, vh = make_scene(rank)
-        h0, h1 = 0, rows
-        step = lambda: ctx.process_synrgb_jpeg(vv, vh, strategy, TARGET, True, out=out_dev)
+    # Primary leg at every N: one whole scene per rank (BASELINE config 5 at N > 1: scenes distributed over the GPUs, no
+    # collective on the data path) -> "weak" scaling, value = all ranks' scene pixels / max-over-ranks time.
+    vv, vh = make_scene(rank)
+    h0, h1 = 0, rows
+    step = lambda: ctx.process_synrgb_jpeg(vv, vh, strategy, TARGET, True, out=out_dev)
 
     # ---------------- kernel-only leg: inputs resident in HBM ---------------------------------
     for _ in range(args.warmup):
@@ -237,18 +231,43 @@ def main():
         time.sleep(0.25)
     ms_per_step, acc, (wall0, wall1) = timed(step, args.steps, 0)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    value = rows * cols / (ms_per_step * 1e-3) / 1e6   # one scene per step, however many ranks share it
+    value = world * rows * cols / (ms_per_step * 1e-3) / 1e6   # one scene per rank per step
     stage_ms, stage_n, launches, syncs = acc["stage_ms"], acc["stage_n"], acc["launches"], acc["syncs"]
 
-    # batch mode (config 5): one whole scene per rank, no collective
-    batch = None
+    # Secondary leg (N > 1): ONE scene row-band-sharded over the ranks (BASELINE config 3), "strong" scaling: every rank
+    # holds its band + the Lanczos halo; the library all-reduces the DN / CLAHE-tile histograms, the CLAHE min/max and the
+    # resized rows over NCCL; the result is bit-identical to 1 GPU.
+    shard = None
     if sharded:
-        del vv, vh
-        bvv, bvh = vv_full, vh_full
-        bms, _, _ = timed(lambda: ctx.process_synrgb_jpeg(bvv, bvh, strategy, TARGET, True, out=out_dev), max(3, args.steps // 2), 2)
-        batch = {"value": round(world * rows * cols / (bms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "ms_per_step": round(bms, 4),
-                 "scaling": "weak", "parallelism": f"scene-per-GPU x{world}, no collective"}
-        vv, vh = vv_full[h0:h1], vh_full[h0:h1]
+        uid = [S.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+        svv, svh = (vv, vh) if rank == 0 else make_scene(0)   # every rank synthesises the same scene and keeps its rows
+        sh0, sh1 = S.shard_halo_rows(rows, cols, TARGET, world, rank, strategy == S.CLAHE)
+        pvv, pvh = svv[sh0:sh1], svh[sh0:sh1]                 # contiguous row slices (views)
+        sstep = lambda: ctx.process_synrgb_sharded(pvv, pvh, rows, strategy, TARGET, True, out=out_dev)
+        sms, sacc, _ = timed(sstep, args.steps, args.warmup)
+        ph_vv = torch.empty((sh1 - sh0, cols), dtype=torch.int16).pin_memory()
+        ph_vh = torch.empty((sh1 - sh0, cols), dtype=torch.int16).pin_memory()
+        ph_vv.copy_(pvv)
+        ph_vh.copy_(pvh)
+        out_hs = torch.empty((orr, oc, 3), dtype=torch.uint8).pin_memory().numpy()
+        sest = lambda: ctx.process_synrgb_sharded(ph_vv.numpy().view(np.uint16), ph_vh.numpy().view(np.uint16), rows, strategy, TARGET,
+                                                  True, out=out_hs)
+        sest()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            sest()
+        barrier()
+        se2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / 3], device=dev, dtype=torch.float64)
+        dist.all_reduce(se2e, op=dist.ReduceOp.MAX)
+        shard = {"value": round(rows * cols / (sms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "ms_per_step": round(sms, 4), "scaling": "strong",
+                 "e2e_ms_per_step": round(float(se2e.item()), 3), "e2e_value": round(rows * cols / (float(se2e.item()) * 1e-3) / 1e6, 1),
+                 "stage_ms_per_step": {S._ffi.STAGE_NAMES[i]: round(sacc["stage_ms"][i] / args.steps, 4) for i in range(8) if sacc["stage_n"][i]},
+                 "parallelism": f"ONE scene row-band-sharded over {world} GPUs; NCCL all-reduce of DN / CLAHE-tile histograms, min/max, resized rows; "
+                                "bit-identical to 1 GPU"}
+        del pvv, pvh, svv, svh, ph_vv, ph_vh
 
     # ---------------- end-to-end leg: host buffers through the C ABI ----------------------------
     e2e_steps = max(2, min(args.steps, 5))
@@ -260,10 +279,7 @@ def main():
     vv_np = vv_h.numpy().view(np.uint16)
     vh_np = vh_h.numpy().view(np.uint16)
     out_h = torch.empty((orr, oc, 3), dtype=torch.uint8).pin_memory().numpy()
-    if sharded:
-        estep = lambda: ctx.process_synrgb_sharded(vv_np, vh_np, rows, strategy, TARGET, True, out=out_h)
-    else:
-        estep = lambda: ctx.process_synrgb_jpeg(vv_np, vh_np, strategy, TARGET, True, out=out_h)
+    estep = lambda: ctx.process_synrgb_jpeg(vv_np, vh_np, strategy, TARGET, True, out=out_h)
     estep()  # warm-up (allocations)
     barrier()
     t0 = time.perf_counter()
@@ -281,7 +297,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         e2e_ms = float(mx[0].item())
         h2d, d2h = int(tt[1].item()), int(tt[2].item())
-    e2e_value = rows * cols / (e2e_ms * 1e-3) / 1e6
+    e2e_value = world * rows * cols / (e2e_ms * 1e-3) / 1e6
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -292,7 +308,7 @@ def main():
         achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at the full C3 size, from the
         # ncu --set full capture summarised in profiles/ (same command line); None for other sizes
-        traffic = 869_100_000 if (rows, cols, world, args.strategy) == (ROWS, COLS, 1, "clahe") else None
+        traffic = 869_100_000 if (rows, cols, args.strategy) == (ROWS, COLS, "clahe") else None
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "k_hmma<CLAHE> (pass B: CLAHE apply fused with the horizontal Lanczos pass on IMMA.16832)",
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,
@@ -300,19 +316,19 @@ def main():
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-            "scaling": "strong" if sharded else "weak",
+            "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": {"workload": f"C3: dual-pol VV+VH {cols}x{rows} u16 GRD-like -> {args.strategy} autoscale -> Lanczos3 {TARGET}px "
-                                   f"+ pad -> synRGB" + (f"; ONE scene row-band-sharded over {world} GPUs (NCCL all-reduce of DN/tile histograms, min/max, resized rows)" if sharded else "; one scene on one GPU"),
+                                   f"+ pad -> synRGB" + (f"; one scene per GPU per step on {world} GPUs, no collective on the data path (config 5); the row-band-sharded single scene (config 3) is under sharded_mode" if sharded else "; one scene on one GPU"),
                        "cache": "inputs (1.6 GB per scene) exceed the 126 MB L2; no flush needed",
-                       "scene_bytes": rows * cols * 4, "parallelism": f"row-band x{world}" if sharded else "single GPU"},
+                       "scene_bytes": rows * cols * 4, "parallelism": f"scene-per-GPU x{world}" if sharded else "single GPU"},
             "clocks": clocks, "gpu_launches": launches, "host_syncs_per_step": syncs / args.steps,
             "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms, 3), "input": "pinned host u16 DN bands", "steps": e2e_steps},
             "roofline": roofline,
         }
-        if batch:
-            line["batch_mode"] = batch
+        if shard:
+            line["sharded_mode"] = shard
         if not args.no_cpu_baseline and world == 1:
             crop_r, crop_c = 8000, 6250
             vvc = vv[:crop_r, :crop_c].cpu().numpy().view(np.uint16)

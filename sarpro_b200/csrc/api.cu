@@ -391,6 +391,10 @@ int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe,
 }
 
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
+    if (getenv("SARPRO_TRACE"))
+        fprintf(stderr, "run_hpass: kind %d pix16 %d mma %d hot %u hot_top %u remap %p skip %p src%%16 %d smem %zu rows %u cols %u\n", src_kind, pix16,
+                (int)ah->mma, a.hot, a.hot_top, (const void*)a.remap, (const void*)a.skip, (int)(reinterpret_cast<uintptr_t>(a.src) % 16),
+                ah->mma ? hmma_smem_bytes(src_kind, a.hot ? a.hot : 1, ah->m_b_bytes) : 0, a.n_rows, a.src_cols);
     if (!pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap &&
         (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && hmma_smem_bytes(src_kind, a.hot, ah->m_b_bytes) <= 227 * 1024) {
         RC(prepare_pieces(ctx, a.n_rows, row_off, src_kind == HSRC_DN_CLAHE, ah, 100));

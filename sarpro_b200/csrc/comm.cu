@@ -76,6 +76,16 @@ struct CommState {
     int rank = 0, world = 1;
 };
 
+// CUDA events around a collective, attributed to SARPRO_STAGE_COMM (like KS in ctx.h)
+#define COMM_BEGIN()                                                                   \
+    int comm_si__ = ctx->n_sev < sarpro_ctx::kMaxStageEvents ? ctx->n_sev : -1;        \
+    if (comm_si__ >= 0) CU(cudaEventRecord(ctx->sev[2 * comm_si__], ctx->stream))
+#define COMM_END()                                                                     \
+    if (comm_si__ >= 0) {                                                              \
+        CU(cudaEventRecord(ctx->sev[2 * comm_si__ + 1], ctx->stream));                 \
+        ctx->sev_stage[comm_si__] = SARPRO_STAGE_COMM;                                 \
+        ctx->n_sev++;                                                                  \
+    }
 #define NC(call)                                                                                        \
     do {                                                                                                \
         int r__ = (call);                                                                               \
@@ -251,35 +261,30 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         jobs[b].bit_depth = SARPRO_U8;
         jobs[b].kind = kinds[b];
         RC(dn_pass_a_launch_sharded(ctx, b, dn, rows, cols, clahe, sg));
+        // ---- 1. DN histogram all-reduce of this band; ev[2 + b] marks the merged histogram as being on the host
+        {
+            COMM_BEGIN();
+            NC(api.AllReduce(w.total.p, w.total.p, kDnBins, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
+            COMM_END();
+        }
+        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->ev[2 + b], ctx->stream));
     }
-    // ---- 1. DN histogram all-reduce, then every rank plans ---------------------------------------------
-    NC(api.GroupStart());
-    for (int b = 0; b < 2; ++b)
-        NC(api.AllReduce(ctx->band[b].total.p, ctx->band[b].total.p, kDnBins, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
-    NC(api.GroupEnd());
-    for (int b = 0; b < 2; ++b)
-        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, ctx->band[b].total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->timing.host_syncs++;
-    {
-        auto plan_one = [&](int b) {
-            BandWs& w = ctx->band[b];
-            plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
-            std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
-            w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
-        };
-        std::thread t1(plan_one, 1);
-        plan_one(0);
-        t1.join();
-        for (int b = 0; b < 2; ++b)
-            CU(cudaMemcpyAsync(ctx->band[b].lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    // ---- 2. CLAHE tile histograms: local partial sums, all-reduce, CDFs everywhere ------------------------
+    // Per band: wait for its histogram, plan on the host (every rank plans redundantly) while the device works on what
+    // is queued behind it (band 1's pass A, then band 0's pass B), 2. all-reduce the CLAHE tile histograms, pass B over
+    // the held rows. The collectives are issued in the same order on every rank.
     const size_t esz = 1;
     const size_t n_out = g.oc * g.orr;
-    if (clahe) {
-        for (int b = 0; b < 2; ++b) {
-            BandWs& w = ctx->band[b];
+    HResizeArgs args[2];
+    for (int b = 0; b < 2; ++b) {
+        BandWs& w = ctx->band[b];
+        CU(cudaEventSynchronize(ctx->ev[2 + b]));
+        ctx->timing.host_syncs++;
+        plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
+        std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+        w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
+        CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+        if (clahe) {
             RC(reserve(ctx, w.tile256, (size_t)ctx->n_tiles * 256 * 4));
             RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
             RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
@@ -287,22 +292,15 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
             if (w.plan.any_valid)
                 KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles,
                                                            w.plan.max_present_dn, (uint32_t*)w.tile256.p, ctx->stream));
-        }
-        NC(api.GroupStart());
-        for (int b = 0; b < 2; ++b)
-            NC(api.AllReduce(ctx->band[b].tile256.p, ctx->band[b].tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum,
-                             cs->comm, ctx->stream));
-        NC(api.GroupEnd());
-        for (int b = 0; b < 2; ++b) {
-            BandWs& w = ctx->band[b];
+            {
+                COMM_BEGIN();
+                NC(api.AllReduce(w.tile256.p, w.tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
+                COMM_END();
+            }
             KS(SARPRO_STAGE_PLAN, launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles,
                                                    (double*)w.cdf.p, (float*)w.cdf32.p, ctx->stream));
         }
-    }
-    // ---- pass B: horizontal pass over the held rows ---------------------------------------------------------
-    HResizeArgs args[2];
-    for (int b = 0; b < 2; ++b) {
-        BandWs& w = ctx->band[b];
+        // ---- pass B: horizontal pass over the held rows
         RC(reserve(ctx, w.temp, std::max<size_t>((size_t)rows * g.rc * esz, 16)));
         RC(reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)));
         CU(cudaMemsetAsync(w.small.p, 0, std::max<size_t>(n_out * esz, 1), ctx->stream));
@@ -331,7 +329,9 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         RC(reserve(ctx, ctx->rgbsel, 64));
         uint32_t* dpk = (uint32_t*)ctx->rgbsel.p + 4;
         KS(SARPRO_STAGE_COMM, launch_minmax_pack((uint32_t*)ctx->band[0].scalars.p, (uint32_t*)ctx->band[1].scalars.p, dpk, 0, ctx->stream));
+        COMM_BEGIN();
         NC(api.AllReduce(dpk, dpk, 4, kNcclUint32, kNcclMax, cs->comm, ctx->stream));
+        COMM_END();
         KS(SARPRO_STAGE_COMM, launch_minmax_pack((uint32_t*)ctx->band[0].scalars.p, (uint32_t*)ctx->band[1].scalars.p, dpk, 1, ctx->stream));
         for (int b = 0; b < 2; ++b) {
             BandWs& w = ctx->band[b];
@@ -355,10 +355,12 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         }
     }
     if (n_out) {
+        COMM_BEGIN();
         NC(api.GroupStart());
         for (int b = 0; b < 2; ++b)
             NC(api.AllReduce(ctx->band[b].small.p, ctx->band[b].small.p, n_out, kNcclUint8, kNcclMax, cs->comm, ctx->stream));
         NC(api.GroupEnd());
+        COMM_END();
     }
     RC(synrgb_compose(ctx, strategy, (const uint8_t*)ctx->band[0].small.p, (const uint8_t*)ctx->band[1].small.p, n_out));
     if (out) {

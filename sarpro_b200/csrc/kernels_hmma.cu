@@ -193,12 +193,20 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
     uint32_t mn2 = 0xffffffffu, mx2 = 0u;   // fast path: u16x2 running min / max of floor(u) + 512 (not yet clamped)
     uint32_t mn_e = 0xffffffffu, mx_e = 0;  // exact-path samples
     uint32_t staged_strip = 0xffffffffu;
+#ifdef HM_DEBUG
+    const long long dbg_t0 = clock64();
+    long long dbg_setup = 0;
+    uint32_t dbg_exact = 0;
+#endif
     const uint32_t sb_lane = hm_keep(sbase + L.bfrag + lane * 16u);
     const uint32_t relu_c = hm_keep(0xFE00FE00u); // -512 per half
 
     for (uint32_t pi = pp.cta_first[blockIdx.x]; pi < pp.cta_first[blockIdx.x + 1]; ++pi) {
         const HPiece pc = pp.pieces[pi];
         const uint4 st = pp.strips[pc.strip]; // {j0, j1, cb0, cb1}
+#ifdef HM_DEBUG
+        const long long dbg_ts = clock64();
+#endif
         __syncthreads(); // the previous piece is done with the tables
         if (tid == 0) { s_ctrl[0] = 0; s_ctrl[1] = 0xffffffffu; s_ctrl[2] = 0; }
         const uint32_t koff0 = (uint32_t)pp.ntile[st.x].z;
@@ -355,6 +363,9 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
 
         const int4* const s_nt = reinterpret_cast<const int4*>(smem + L.nt);
         const uint16_t* const s_cm = reinterpret_cast<const uint16_t*>(smem + L.cm);
+#ifdef HM_DEBUG
+        dbg_setup += clock64() - dbg_ts;
+#endif
         // ---- 16-row groups of the piece, handed out to the warps --------------------------------------
         const uint32_t n_groups = (pc.r1 - pc.r0 + 15u) / 16u;
         for (;;) {
@@ -566,22 +577,42 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
                     if (a1[s]) bf[s][1] = hm_lds_u4(sb_lane + sbo[s] + ks0 * 512u + 512u);
                 }
                 if (CLAHE) {
-                    // exact fix-up: the 32 pixels of a flagged lane, one per lane
-                    uint32_t need = __ballot_sync(FULL, riskmask != 0);
-                    while (need) {
-                        const uint32_t sl = __ffs(need) - 1u;
-                        need &= need - 1u;
-                        const uint32_t sg = sl >> 2, sq = sl & 3u;
-                        const uint32_t v = lane >> 3, k = lane & 7u; // my pixel of the flagged lane: vector v, sample k
-                        const uint32_t r = min(rbase + sg + ((v & 2u) ? 8u : 0u), pc.r1 - 1u);
-                        const uint32_t c = min(cb * 64u + (v & 1u) * 32u + sq * 8u, cols - 8u) + k;
-                        uint32_t b = exact_px(r, c) << (8u * (lane & 3u));
-                        b |= __shfl_xor_sync(FULL, b, 1);
-                        b |= __shfl_xor_sync(FULL, b, 2); // lanes 4m..4m+3 hold word m = samples 4m..4m+3 of the flagged lane
+                    // exact fix-up: flagged vectors (8 pixels of one lane) are enumerated over the warp, ordered by (vector, lane),
+                    // and recomputed four at a time, one pixel per lane; each group of 8 lanes serves one flagged vector
+                    uint32_t bal[4];
 #pragma unroll
-                        for (int m = 0; m < 8; ++m) {
-                            const uint32_t t = __shfl_sync(FULL, b, 4 * m);
-                            if (lane == sl) w[m >> 1][m & 1] = t;
+                    for (int v = 0; v < 4; ++v) bal[v] = __ballot_sync(FULL, (riskmask >> v) & 1u);
+                    if (bal[0] | bal[1] | bal[2] | bal[3]) {
+                        const uint32_t c0n = __popc(bal[0]), c1n = c0n + __popc(bal[1]), c2n = c1n + __popc(bal[2]), total = c2n + __popc(bal[3]);
+                        for (uint32_t base = 0; base < total; base += 4u) {
+#ifdef HM_DEBUG
+                            dbg_exact++;
+#endif
+                            const uint32_t idx = base + (lane >> 3);
+                            const bool on = idx < total;
+                            // vector number and rank of the flagged lane among the lanes flagged for that vector
+                            const uint32_t v = !on ? 0u : (idx < c0n ? 0u : (idx < c1n ? 1u : (idx < c2n ? 2u : 3u)));
+                            const uint32_t n = idx - (v == 0 ? 0u : (v == 1 ? c0n : (v == 2 ? c1n : c2n)));
+                            const uint32_t bv = v == 0 ? bal[0] : (v == 1 ? bal[1] : (v == 2 ? bal[2] : bal[3]));
+                            const uint32_t sl = on ? __fns(bv, 0, n + 1) : 0u; // the flagged lane (n-th set bit)
+                            const uint32_t sg = sl >> 2, sq = sl & 3u, k = lane & 7u;
+                            const uint32_t r = min(rbase + sg + ((v & 2u) ? 8u : 0u), pc.r1 - 1u);
+                            const uint32_t c = min(cb * 64u + (v & 1u) * 32u + sq * 8u, cols - 8u) + k;
+                            uint32_t b = on ? exact_px(r, c) << (8u * (lane & 3u)) : 0u;
+                            b |= __shfl_xor_sync(FULL, b, 1);
+                            b |= __shfl_xor_sync(FULL, b, 2); // lanes 8s..8s+3 hold samples 0..3, lanes 8s+4..8s+7 samples 4..7
+#pragma unroll
+                            for (int sidx = 0; sidx < 4; ++sidx) { // hand slot sidx's two words to its flagged lane
+                                const uint32_t w0 = __shfl_sync(FULL, b, 8 * sidx), w1 = __shfl_sync(FULL, b, 8 * sidx + 4);
+                                const uint32_t tl = __shfl_sync(FULL, on ? (sl | (v << 8)) : 0xffffu, 8 * sidx);
+                                if ((tl & 0xffu) == lane && tl != 0xffffu) {
+                                    const uint32_t tv = tl >> 8;
+                                    if (tv == 0) { w[0][0] = w0; w[0][1] = w1; }
+                                    else if (tv == 1) { w[1][0] = w0; w[1][1] = w1; }
+                                    else if (tv == 2) { w[2][0] = w0; w[2][1] = w1; }
+                                    else { w[3][0] = w0; w[3][1] = w1; }
+                                }
+                            }
                         }
                     }
                 }
@@ -620,6 +651,9 @@ __global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaPar
             }
         }
     }
+#ifdef HM_DEBUG
+    if (tid == 0) printf("ctaend %u cycles %lld pieces %u exact %u setup %lld\n", blockIdx.x, clock64() - dbg_t0, pp.cta_first[blockIdx.x + 1] - pp.cta_first[blockIdx.x], dbg_exact, dbg_setup);
+#endif
     if (CLAHE && a.minmax) {
         if (mn2 != 0xffffffffu) { // fast-path extrema: biased by 512 and not yet clamped
             const int lo = (int)min(mn2 & 0xffffu, mn2 >> 16) - 512, hi = (int)max(mx2 & 0xffffu, mx2 >> 16) - 512;
