@@ -516,11 +516,11 @@ int choose_hist_variant(const uint32_t* hist) {
 // Host planning of band b from its histogram in pinned memory; ships the DN -> sample / bin table.
 int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     BandWs& w = ctx->band[b];
-    w.hist_auto = choose_hist_variant(ctx->h_hist + (size_t)b * kDnBins);
     plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan);
     std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
     w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
     CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+    w.hist_auto_pending = true; // pass-A table shape for the next call: chosen after this band's pass B is queued
     return 0;
 }
 
@@ -790,6 +790,11 @@ int begin_call(sarpro_ctx* ctx) {
 }
 int end_call(sarpro_ctx* ctx) {
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    for (int b = 0; b < 2; ++b) // host work kept off the critical path: runs while the device drains the queue
+        if (ctx->band[b].hist_auto_pending) {
+            ctx->band[b].hist_auto = choose_hist_variant(ctx->h_hist + (size_t)b * kDnBins);
+            ctx->band[b].hist_auto_pending = false;
+        }
     CU(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));

@@ -75,6 +75,7 @@ struct BandWs {
     DevBuf edges, hist4096, f32scan; // general f32 path
     BandPlan plan;
     int hist_auto = 21;            // pass-A table shape for the next call (see choose_hist_variant)
+    bool hist_auto_pending = false; // h_hist of this slot still has to go through choose_hist_variant
     uint32_t hot = 0, hot_top = 0; // table range / saturated table word for kernels_hpipe.cu (0 = not eligible)
 };
 

@@ -35,7 +35,7 @@
 namespace sarpro {
 
 namespace hm {
-constexpr uint32_t kThreads = 512, kWarps = 16;
+constexpr uint32_t kThreadsLut = 512, kThreadsClahe = 384;      // CLAHE: fewer warps, 168 registers each for the gather pipeline
 constexpr uint32_t kQuadEntries = 257;                       // 256 bins + the invalid-pixel entry
 constexpr uint32_t kQuadCellBytes = kQuadEntries * 8 * 16;   // one cell, 8 replicas
 constexpr int kSlots = 3;                                    // n-tiles in flight per warp
@@ -152,10 +152,10 @@ __device__ __forceinline__ double hm_entry_error(double A, double B, double C, d
 }
 
 template <bool CLAHE>
-__global__ void __launch_bounds__(hm::kThreads, 1) k_hmma(HResizeArgs a, HMmaParams pp) {
+__global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1) k_hmma(HResizeArgs a, HMmaParams pp) {
     extern __shared__ uint4 smem4[];
     unsigned char* const smem = reinterpret_cast<unsigned char*>(smem4);
-    constexpr uint32_t NT = hm::kThreads;
+    constexpr uint32_t NT = CLAHE ? hm::kThreadsClahe : hm::kThreadsLut;
     constexpr uint32_t FULL = 0xffffffffu;
     if (a.skip && *a.skip) return;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
@@ -770,7 +770,7 @@ cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_de
             if (e != cudaSuccess) return e;
             configured = smem;
         }
-        k_hmma<true><<<n_ctas, hm::kThreads, smem, stream>>>(a, pp);
+        k_hmma<true><<<n_ctas, hm::kThreadsClahe, smem, stream>>>(a, pp);
     } else {
         static size_t configured = 0;
         if (smem > configured) {
@@ -778,7 +778,7 @@ cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_de
             if (e != cudaSuccess) return e;
             configured = smem;
         }
-        k_hmma<false><<<n_ctas, hm::kThreads, smem, stream>>>(a, pp);
+        k_hmma<false><<<n_ctas, hm::kThreadsLut, smem, stream>>>(a, pp);
     }
     return cudaGetLastError();
 }
