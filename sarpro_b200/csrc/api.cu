@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <string>
@@ -545,6 +546,15 @@ int wait_and_plan(sarpro_ctx* ctx, int b, const BandJob& job) {
     return plan_band_and_upload(ctx, b, job);
 }
 
+// wait_and_plan; when `side` is given, everything from the table upload on is issued on that stream (ctx->stream is
+// switched; the caller switches it back).
+int wait_and_plan_on(sarpro_ctx* ctx, int b, const BandJob& job, cudaStream_t side) {
+    CU(cudaEventSynchronize(ctx->ev[2 + b]));
+    ctx->timing.host_syncs++;
+    if (side) ctx->stream = side;
+    return plan_band_and_upload(ctx, b, job);
+}
+
 // Pass A for `nb` bands, then the planner for all of them (callers that need every plan before pass B).
 int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
     RC(run_pass_a(ctx, jobs, nb));
@@ -779,12 +789,16 @@ int check_band(sarpro_ctx* ctx, const sarpro_band* b) {
     return 0;
 }
 
+double host_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 int begin_call(sarpro_ctx* ctx) {
     if (!ctx) return SARPRO_ERR_INVALID_ARGUMENT;
     ctx->err.clear();
     CU(cudaSetDevice(ctx->device));
     std::memset(&ctx->timing, 0, sizeof(ctx->timing));
     ctx->n_sev = 0;
+    ctx->host_t0 = host_ms();
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     return 0;
 }
@@ -810,7 +824,8 @@ int end_call(sarpro_ctx* ctx) {
             float t0 = 0, t1 = 0;
             cudaEventElapsedTime(&t0, ctx->ev[0], ctx->sev[2 * i]);
             cudaEventElapsedTime(&t1, ctx->ev[0], ctx->sev[2 * i + 1]);
-            fprintf(stderr, "trace %2d stage %d  %8.3f -> %8.3f ms (%.3f)\n", i, ctx->sev_stage[i], t0, t1, t1 - t0);
+            fprintf(stderr, "trace %2d stage %d  %8.3f -> %8.3f ms (%.3f)  issued by the host at %.3f\n", i, ctx->sev_stage[i], t0, t1, t1 - t0,
+                    ctx->sev_host[i]);
         }
         fprintf(stderr, "trace total %.3f ms\n", ms);
     }
@@ -905,9 +920,25 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
                                   stats ? &stats[b] : nullptr));
             continue;
         }
-        if (pipelined) RC(wait_and_plan(ctx, b, jobs[b]));
-        if (stats) stats[b] = w.plan.stats;
-        RC(dn_run_pass_b(ctx, b, jobs[b], *geom, w.small.p));
+        // Second band of a pipelined pair: its planner upload, CLAHE statistics, pass B and vertical pass go to the side
+        // stream, so that its persistent CTAs fill the SMs the first band's pass B leaves early (the piece runs do not
+        // end together) and its small kernels overlap the first band's. Pass A of this band is complete (host-synced
+        // in wait_and_plan); the main stream joins before anything consumes the canvas.
+        const bool side = pipelined && nb == 2 && b == 1 && ctx->two_stream && ctx->stream2;
+        cudaStream_t main_stream = ctx->stream;
+        int rc = 0;
+        if (pipelined) rc = wait_and_plan_on(ctx, b, jobs[b], side ? ctx->stream2 : nullptr);
+        if (!rc) {
+            if (stats) stats[b] = w.plan.stats;
+            rc = dn_run_pass_b(ctx, b, jobs[b], *geom, w.small.p);
+        }
+        if (side) {
+            cudaError_t e1 = cudaEventRecord(ctx->ev_join, ctx->stream2);
+            ctx->stream = main_stream;
+            cudaError_t e2 = cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
+            if (!rc) { CU(e1); CU(e2); }
+        }
+        RC(rc);
     }
     return 0;
 }
@@ -949,6 +980,8 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (auto& ev : ctx->sev)
@@ -963,6 +996,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     if (const char* v = getenv("SARPRO_HPIPE")) ctx->use_hpipe = atoi(v);
     if (const char* v = getenv("SARPRO_HMMA")) ctx->use_hmma = atoi(v);
+    if (const char* v = getenv("SARPRO_TWO_STREAM")) ctx->two_stream = atoi(v);
     if (const char* v = getenv("SARPRO_HPIPE_NSUB")) ctx->hpipe_nsub = (atoi(v) == 2 || atoi(v) == 3 || atoi(v) == 12) ? atoi(v) : 0;
     int rc = upload_rgb_luts(ctx);
     if (rc) {
@@ -1001,6 +1035,8 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     for (auto& ev : ctx->sev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 

@@ -112,6 +112,9 @@ inline bool uses_clahe(const BandJob& j) { return j.kind == PlanKind::Autoscale 
 struct sarpro_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr; // side stream: the second band's pass B (see produce_bands)
+    cudaEvent_t ev_join = nullptr;
+    int two_stream = 1;             // SARPRO_TWO_STREAM=0: everything on `stream`
     bool own_stream = true;
     int sm_count = 148;
     std::string err;
@@ -150,6 +153,8 @@ struct sarpro_ctx {
     static constexpr int kMaxStageEvents = 64;
     cudaEvent_t sev[2 * kMaxStageEvents] = {};
     int sev_stage[kMaxStageEvents] = {};
+    double sev_host[kMaxStageEvents] = {}; // host time of the launch (ms since begin_call; SARPRO_TRACE)
+    double host_t0 = 0;
     int n_sev = 0;
     int hist_variant = -1; // SARPRO_HIST_VARIANT; -1 = per band, from the tail of the previous histogram of that slot
     float valid_thresh = 0.f;
@@ -159,6 +164,7 @@ struct sarpro_ctx {
 namespace sarpro {
 
 int fail(sarpro_ctx* c, int code, const char* fmt, ...);
+double host_ms();
 int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes);
 void release(DevBuf& b);
 uint32_t hpipe_hot(const uint16_t* lut_host, const uint32_t* hist_host, uint32_t max_present_dn, uint32_t* top_out);
@@ -206,6 +212,7 @@ int end_call(sarpro_ctx* ctx);
         if (si__ >= 0) {                                                             \
             CU(cudaEventRecord(ctx->sev[2 * si__ + 1], ctx->stream));                \
             ctx->sev_stage[si__] = (S);                                              \
+            ctx->sev_host[si__] = sarpro::host_ms() - ctx->host_t0;                  \
             ctx->n_sev++;                                                            \
         }                                                                            \
     } while (0)
