@@ -308,7 +308,7 @@ def main():
         achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at the full C3 size, from the
         # ncu --set full capture summarised in profiles/ (same command line); None for other sizes
-        traffic = 869_100_000 if (rows, cols, args.strategy) == (ROWS, COLS, "clahe") else None
+        traffic = 872_600_000 if (rows, cols, args.strategy) == (ROWS, COLS, "clahe") else None
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "k_hmma<CLAHE> (pass B: CLAHE apply fused with the horizontal Lanczos pass on IMMA.16832)",
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,

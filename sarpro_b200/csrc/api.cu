@@ -517,11 +517,14 @@ int choose_hist_variant(const uint32_t* hist) {
 // Host planning of band b from its histogram in pinned memory; ships the DN -> sample / bin table.
 int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     BandWs& w = ctx->band[b];
+    const bool trace = getenv("SARPRO_TRACE") != nullptr;
+    const double t_a = trace ? host_ms() - ctx->host_t0 : 0;
     plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan);
     std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
     w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
     CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
     w.hist_auto_pending = true; // pass-A table shape for the next call: chosen after this band's pass B is queued
+    if (trace) fprintf(stderr, "trace host: band %d histogram on the host at %.3f ms, planned and table queued at %.3f ms\n", b, t_a, host_ms() - ctx->host_t0);
     return 0;
 }
 
