@@ -370,8 +370,9 @@ int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe,
     cuts.push_back(rows);
     std::vector<uint32_t> pieces, first;
     uint32_t max_rows = 0;
-    if (nsub == 100) // tensor-core kernel: 16-row groups
-        hpipe_build_pieces(ah->m_weights_h, cuts, (uint32_t)ctx->sm_count, 16u, &pieces, &first, &max_rows);
+    if (nsub == 100) // tensor-core kernel: whole rounds of 16-row groups (one group per warp: 12 warps for CLAHE, 16 otherwise), so
+                     // that only the last piece of a vertical cell ends with a partly filled round
+        hpipe_build_pieces(ah->m_weights_h, cuts, (uint32_t)ctx->sm_count, 16u * hmma_warps(clahe), &pieces, &first, &max_rows);
     else
         hpipe_build_pieces(nsub == 12 ? ah->s_strips_h : ah->p_strips_h, cuts, (uint32_t)ctx->sm_count, nsub == 12 ? 8u : 4u * (uint32_t)nsub,
                            &pieces, &first, &max_rows);

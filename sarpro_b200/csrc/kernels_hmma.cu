@@ -293,6 +293,15 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                             // v_ref = fl(fl(sx*omdy) + fl(sx*dy)), sx = fl(omdx + dx): 255 wherever both sums are exactly 1.0
                             // (sat_ok); elsewhere the entry is a marker (floor 480) that the block fix-up resolves per pixel
                             qv = make_float4(sat_ok[cs] ? 255.5f : hm::kMarker + 0.5f, 0.f, 0.f, 0.f);
+                        } else if (c00 == c01 && c00 == c10 && c00 == c11) {
+                            // Four identical CDF values c (the clamped corner cell, or tiles that agree at this bin): the
+                            // reference's c*omdx + c*dx, ... differs from c by a few ulps only, |255*v_ref - 255*c| < 3e-13 for
+                            // every pixel, so the sample is floor(255*c) everywhere unless 255*c sits that close to an integer.
+                            // Without this, a bin whose fp32 u = A happened to have zero fraction bits would flag every one of
+                            // its pixels in the cell.
+                            const double U = 255.0 * c00, fl = floor(U);
+                            const bool clear = U - fl > 2e-12 && fl + 1.0 - U > 2e-12;
+                            qv = clear ? make_float4((float)(fl + 0.5), 0.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
                         } else {
                             const double A = 255.0 * c00, B = 255.0 * (c01 - c00), C = 255.0 * (c10 - c00);
                             const double D = 255.0 * ((c11 - c10) - (c01 - c00));
@@ -742,6 +751,8 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
 
 // 32 lane-private replicas (conflict-free gathers) when the table still fits the 16-bit address range, else 16 or 8
 static uint32_t hmma_lut_shift(uint32_t hot) { return hot <= 500 ? 7u : hpipe_lut_shift(hot); }
+
+uint32_t hmma_warps(bool clahe) { return (clahe ? hm::kThreadsClahe : hm::kThreadsLut) / 32u; }
 
 size_t hmma_smem_bytes(int src_kind, uint32_t hot, uint32_t b_bytes) {
     return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hmma_lut_shift(hot), b_bytes).total;
