@@ -114,7 +114,9 @@ typedef struct sarpro_timing {
     uint32_t kernel_launches;
     uint32_t host_syncs; /* planner round trips */
     uint64_t h2d_bytes, d2h_bytes;
-    /* per-stage device time of the last call (CUDA events around the launches, summed over bands) */
+    /* per-stage device time of the last call (CUDA events around the launches, summed over bands). Pass A, pass B and the
+       collectives are timed by default; the environment variable SARPRO_STAGE_TIMING=all times every launch (each event pair
+       costs a few microseconds of host time per call). */
     float stage_ms[8];        /* indexed by sarpro_stage */
     uint32_t stage_launches[8];
 } sarpro_timing;

@@ -1001,6 +1001,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if (const char* v = getenv("SARPRO_HPIPE")) ctx->use_hpipe = atoi(v);
     if (const char* v = getenv("SARPRO_HMMA")) ctx->use_hmma = atoi(v);
     if (const char* v = getenv("SARPRO_TWO_STREAM")) ctx->two_stream = atoi(v);
+    if (getenv("SARPRO_TRACE") || (getenv("SARPRO_STAGE_TIMING") && std::string(getenv("SARPRO_STAGE_TIMING")) == "all")) ctx->stage_mask = 0xffu;
     if (const char* v = getenv("SARPRO_HPIPE_NSUB")) ctx->hpipe_nsub = (atoi(v) == 2 || atoi(v) == 3 || atoi(v) == 12) ? atoi(v) : 0;
     int rc = upload_rgb_luts(ctx);
     if (rc) {

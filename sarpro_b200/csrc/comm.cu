@@ -78,7 +78,7 @@ struct CommState {
 
 // CUDA events around a collective, attributed to SARPRO_STAGE_COMM (like KS in ctx.h)
 #define COMM_BEGIN()                                                                   \
-    int comm_si__ = ctx->n_sev < sarpro_ctx::kMaxStageEvents ? ctx->n_sev : -1;        \
+    int comm_si__ = (((ctx->stage_mask >> SARPRO_STAGE_COMM) & 1u) && ctx->n_sev < sarpro_ctx::kMaxStageEvents) ? ctx->n_sev : -1; \
     if (comm_si__ >= 0) CU(cudaEventRecord(ctx->sev[2 * comm_si__], ctx->stream))
 #define COMM_END()                                                                     \
     if (comm_si__ >= 0) {                                                              \

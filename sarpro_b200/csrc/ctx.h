@@ -156,6 +156,9 @@ struct sarpro_ctx {
     double sev_host[kMaxStageEvents] = {}; // host time of the launch (ms since begin_call; SARPRO_TRACE)
     double host_t0 = 0;
     int n_sev = 0;
+    // stages that get CUDA event pairs (each pair costs ~3 us of host time per call): pass A, pass B and the collectives by
+    // default; SARPRO_STAGE_TIMING=all (or SARPRO_TRACE) times every launch
+    uint32_t stage_mask = (1u << SARPRO_STAGE_HIST) | (1u << SARPRO_STAGE_APPLY) | (1u << SARPRO_STAGE_COMM);
     int hist_variant = -1; // SARPRO_HIST_VARIANT; -1 = per band, from the tail of the previous histogram of that slot
     float valid_thresh = 0.f;
     sarpro::CommState* comm = nullptr;
@@ -206,7 +209,7 @@ int end_call(sarpro_ctx* ctx);
 // stage-timed kernel launch: CUDA events around the launch, attributed to sarpro_stage S
 #define KS(S, call)                                                                  \
     do {                                                                             \
-        const int si__ = ctx->n_sev < sarpro_ctx::kMaxStageEvents ? ctx->n_sev : -1; \
+        const int si__ = (((ctx->stage_mask >> (S)) & 1u) && ctx->n_sev < sarpro_ctx::kMaxStageEvents) ? ctx->n_sev : -1; \
         if (si__ >= 0) CU(cudaEventRecord(ctx->sev[2 * si__], ctx->stream));         \
         KL(call);                                                                    \
         if (si__ >= 0) {                                                             \
