@@ -233,6 +233,14 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
 int sarpro_plan_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int strategy, sarpro_stats* stats,
                                   uint16_t* lut16);
 
+/* Horizontal Lanczos3 pass of one row of u8 samples (resize.rs:39-50, first pass of the crate's separable resize) computed
+ * twice on the host: directly from the fixed-point taps (out_direct) and by replaying the tensor-core kernel's plan — strips,
+ * n-tile slots, k-step windows and the permuted hi/lo tap bytes of its B fragments — in the device's order (out_replay).
+ * Returns 1 when the plan exists for this axis (0: the axis falls back to the other kernels, out_replay untouched).
+ * max_span: longest strip in source columns (the CLAHE tile width), 0 = unbounded. */
+int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t out_size, size_t max_span,
+                                  uint8_t* out_direct, uint8_t* out_replay);
+
 #ifdef __cplusplus
 }
 #endif

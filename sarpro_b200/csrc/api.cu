@@ -398,7 +398,8 @@ int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, Ax
                 (int)ah->mma, a.hot, a.hot_top, (const void*)a.remap, (const void*)a.skip, (int)(reinterpret_cast<uintptr_t>(a.src) % 16),
                 ah->mma ? hmma_smem_bytes(src_kind, a.hot ? a.hot : 1, ah->m_b_bytes) : 0, a.n_rows, a.src_cols);
     if (!pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap &&
-        (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && hmma_smem_bytes(src_kind, a.hot, ah->m_b_bytes) <= 227 * 1024) {
+        (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && (uint64_t)a.src_rows * a.src_cols < (1ull << 32) &&
+        hmma_smem_bytes(src_kind, a.hot, ah->m_b_bytes) <= 227 * 1024) {
         RC(prepare_pieces(ctx, a.n_rows, row_off, src_kind == HSRC_DN_CLAHE, ah, 100));
         KS(SARPRO_STAGE_APPLY, launch_hmma(a, src_kind, (const uint4*)ah->m_btab.p, (const int4*)ah->m_ntile.p, (const uint4*)ah->m_strips.p,
                                            (const uint32_t*)ctx->pieces.p, (const uint32_t*)ctx->cta_first.p, ctx->pc_n_ctas, a.hot,
@@ -1078,6 +1079,24 @@ int sarpro_resize_output_dims(size_t cols, size_t rows, int has_target, size_t t
     size_t rc, rr;
     resize_output_dims(cols, rows, has_target != 0, target, pad != 0, &rc, &rr, out_cols, out_rows);
     return SARPRO_OK;
+}
+
+int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t out_size, size_t max_span, uint8_t* out_direct,
+                                  uint8_t* out_replay) {
+    if (!samples || !out_direct || !out_replay || in_size == 0 || out_size == 0) return SARPRO_ERR_INVALID_ARGUMENT;
+    ResampleAxis ax;
+    build_lanczos3_axis((uint32_t)in_size, (uint32_t)out_size, false, &ax);
+    for (uint32_t ox = 0; ox < out_size; ++ox) { // fast_image_resize u8 horizontal pass: i32 accumulate from 1 << (p - 1), >> p, clamp
+        int acc = ax.precision > 0 ? (1 << (ax.precision - 1)) : 0;
+        for (uint32_t k = 0; k < ax.size[ox]; ++k) acc += (int)samples[ax.start[ox] + k] * ax.coef[(size_t)ox * ax.window + k];
+        int v = acc >> ax.precision;
+        out_direct[ox] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+    HMmaPlanHost plan;
+    if (!hmma_build_plan(ax.start.data(), ax.size.data(), ax.coef.data(), ax.window, (uint32_t)out_size, (uint32_t)in_size, (uint32_t)max_span, &plan))
+        return 0;
+    hmma_replay_row(plan, samples, (uint32_t)in_size, (uint32_t)out_size, ax.precision, out_replay);
+    return 1;
 }
 
 int sarpro_plan_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int strategy, sarpro_stats* stats,

@@ -164,6 +164,7 @@ struct HMmaPlanHost {
 // does not fit the kernel (in_size not a multiple of 8, more than three n-tiles in flight, ...).
 bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int32_t* coef_h, uint32_t window, uint32_t out_size,
                      uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan);
+bool hmma_replay_row(const HMmaPlanHost& plan, const uint8_t* samples, uint32_t in_size, uint32_t out_size, int precision, uint8_t* out);
 size_t hmma_smem_bytes(int src_kind, uint32_t hot, uint32_t b_bytes);
 uint32_t hmma_warps(bool clahe); // warps per CTA of the instantiation
 cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,

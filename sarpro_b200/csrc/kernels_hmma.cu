@@ -141,7 +141,7 @@ __device__ __forceinline__ double hm_half_ulp(double x) {
 }
 __device__ __forceinline__ double hm_entry_error(double A, double B, double C, double D) {
     const double X = 1.0, Y = 1.0;          // |dx| <= 1, |dy| <= 1 (autoscale.rs:308-318: d in [-0.5, 1))
-    const double ex = 2.0e-7, ey = 3.1e-8;  // |dxf - dx|, |dyf - dy| (see dx_of / the row geometry below)
+    const double ex = 2.4e-7, ey = 3.1e-8;  // |dxf - dx|, |dyf - dy| (see dx_of / the row geometry below)
     const double aB = fabs(B), aC = fabs(C), aD = fabs(D), aA = fabs(A);
     double e = hm_half_ulp(A) + hm_half_ulp(B) * X + hm_half_ulp(C) * Y + hm_half_ulp(D) * X * Y; // table roundings
     e += (aB + aD * Y) * ex + (aC + aD * X) * ey;                                                 // geometry
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                     uint32_t cm0 = 0, cm1 = 0; // columns of the vector with fl(omdx+dx) == 1.0 / == 1 - 2^-53 (bit per column)
                     if (CLAHE) {
                         // dx = m / (2*tile_w), m = 2c - tile_w*(2t+1) (k_clahe_axis), t = the cell of the vector's first column;
-                        // fp32: |dxf - dx| < 2e-7
+                        // fp32: |dxf - dx| < 2.4e-7
                         const int m0 = 2 * (int)c0 - (c0 >= bcol ? twB : twA);
                         const float dx0 = __fmul_rn((float)m0, a.clahe.inv2tw);
                         const float dstep = __fmul_rn(2.0f, a.clahe.inv2tw);
@@ -687,7 +687,7 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
     plan->strips.clear();
     plan->weights.clear();
     plan->b_bytes = 0;
-    if (out_size == 0 || in_size < 8 || (in_size % 8) != 0) return false;
+    if (out_size == 0 || in_size < 8 || (in_size % 8) != 0 || in_size >= (1u << 22)) return false; // (2c - tile_w*(2t+1) exact in fp32)
     const uint32_t n_nt = (out_size + 7) / 8;
     uint32_t koff = 0;
     for (uint32_t j = 0; j < n_nt; ++j) {
@@ -751,6 +751,58 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
 
 // 32 lane-private replicas (conflict-free gathers) when the table still fits the 16-bit address range, else 16 or 8
 static uint32_t hmma_lut_shift(uint32_t hot) { return hot <= 500 ? 7u : hpipe_lut_shift(hot); }
+
+// Host replay of the kernel's walk for one row of u8 samples (test hook): strips, slot rotation, k-step windows, the
+// permuted tap bytes (hi * 256 + lo) and the final shift / clamp, in the order the device follows. out has out_size bytes.
+bool hmma_replay_row(const HMmaPlanHost& plan, const uint8_t* samples, uint32_t in_size, uint32_t out_size, int precision, uint8_t* out) {
+    const int acc0 = precision > 0 ? (1 << (precision - 1)) : 0;
+    for (const uint4& st : plan.strips) {
+        const uint32_t koff0 = (uint32_t)plan.ntile[st.x].z;
+        int acc[hm::kSlots][8];
+        uint32_t sj[hm::kSlots], sfb[hm::kSlots], slb[hm::kSlots], sbo[hm::kSlots];
+        auto load_slot = [&](int s) {
+            sfb[s] = 0xffffffffu; slb[s] = 0; sbo[s] = 0;
+            if (sj[s] < st.y) { const int4 m = plan.ntile[sj[s]]; sfb[s] = (uint32_t)m.x; slb[s] = (uint32_t)m.y; sbo[s] = (uint32_t)m.z - koff0 - (uint32_t)m.x; }
+        };
+        for (int s = 0; s < hm::kSlots; ++s) {
+            for (int i = 0; i < 8; ++i) acc[s][i] = 0;
+            sj[s] = st.x + s;
+            load_slot(s);
+        }
+        for (uint32_t cb = st.z; cb < st.w; ++cb)
+            for (int s = 0; s < hm::kSlots; ++s) {
+                bool any = false;
+                for (uint32_t h = 0; h < 2; ++h) {
+                    const uint32_t ks = cb * 2 + h;
+                    if (!(ks >= sfb[s] && ks <= slb[s])) continue;
+                    any = true;
+                    const uint4* b = plan.btab.data() + (size_t)(koff0 + sbo[s] + ks) * 32u; // fragments of this k-step, 32 lanes
+                    for (uint32_t lane = 0; lane < 32; ++lane) {
+                        const uint32_t n = lane >> 2, q = lane & 3u;
+                        const uint32_t reg[4] = {b[lane].x, b[lane].y, b[lane].z, b[lane].w};
+                        for (uint32_t r = 0; r < 2; ++r)
+                            for (uint32_t i = 0; i < 4; ++i) {
+                                const uint32_t c = std::min(ks * 32 + q * 8, in_size - 8) + r * 4 + i; // the column the kernel loads
+                                const int hi = (int)(int8_t)((reg[r] >> (8 * i)) & 255u), lo = (int)((reg[2 + r] >> (8 * i)) & 255u);
+                                acc[s][n] += (int)samples[c] * (hi * 256 + lo);
+                            }
+                    }
+                }
+                if (any && cb * 2 + 1 >= slb[s]) {
+                    for (uint32_t n = 0; n < 8; ++n) {
+                        const uint32_t ox = sj[s] * 8 + n;
+                        int v = (acc0 + acc[s][n]) >> precision;
+                        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+                        if (ox < out_size) out[ox] = (uint8_t)v;
+                        acc[s][n] = 0;
+                    }
+                    sj[s] += hm::kSlots;
+                    load_slot(s);
+                }
+            }
+    }
+    return true;
+}
 
 uint32_t hmma_warps(bool clahe) { return (clahe ? hm::kThreadsClahe : hm::kThreadsLut) / 32u; }
 

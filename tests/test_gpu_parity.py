@@ -220,3 +220,33 @@ def test_tensor_core_pass_b_against_oracle(ctx):
     ref, _ = O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), S.CLAHE, 1024, True)
     img = ctx.process_synrgb_jpeg(vv, vh, S.CLAHE, 1024, True)
     assert np.array_equal(img.rgb, ref), int((img.rgb != ref).sum())
+
+
+def test_full_size_scene_cross_kernels(monkeypatch):
+    """BASELINE's full size (25,000 x 16,000 per band, the C3 scene of bench.py): the production path (tensor-core pass B,
+    second band on the side stream) must give the same RGB bytes as the second-generation kernels on one stream, for CLAHE
+    and for a LUT strategy, and repeated calls on one context must be identical (no state leaks between calls)."""
+    import torch
+    from sarpro_b200.synth import SEED_VH, SEED_VV, synth_band_torch
+    dev = torch.device("cuda:0")
+    vv = synth_band_torch(16000, 25000, SEED_VV, dev)
+    vh = synth_band_torch(16000, 25000, SEED_VH, dev, cross_pol=True)
+    outs = {}
+    for name, env in (("old", {"SARPRO_HMMA": "0", "SARPRO_TWO_STREAM": "0"}), ("new", {})):
+        for k in ("SARPRO_HMMA", "SARPRO_TWO_STREAM", "SARPRO_HPIPE", "SARPRO_FORCE_EXACT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with S.Context(0) as c:
+            for strategy in (S.CLAHE, S.ROBUST):
+                out = torch.empty((2048, 2048, 3), dtype=torch.uint8, device=dev)
+                c.process_synrgb_jpeg(vv, vh, strategy, 2048, True, out=out)
+                first = out.clone()
+                c.process_synrgb_jpeg(vh, vv, strategy, 2048, True, out=out)  # different call in between
+                c.process_synrgb_jpeg(vv, vh, strategy, 2048, True, out=out)
+                assert torch.equal(first, out), (name, strategy)
+                outs[(name, strategy)] = first.cpu().numpy()
+    for strategy in (S.CLAHE, S.ROBUST):
+        a, b = outs[("old", strategy)], outs[("new", strategy)]
+        assert a.shape == (2048, 2048, 3) and a[(2048 - 1311) // 2 + 5:-(2048 - 1311) // 2 - 5].any()
+        assert np.array_equal(a, b), (strategy, int((a != b).sum()))

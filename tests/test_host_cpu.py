@@ -96,3 +96,29 @@ def test_shard_rows(lib_built):
                     assert all(b[0] % tile_h == 0 for b in bands)
     with pytest.raises(S.SarproError):
         S.shard_rows(100, 2, 2, False)
+
+
+@pytest.mark.parametrize("in_size,out_size,max_span", [(25000, 2048, 3125), (25000, 2048, 0), (25000, 1024, 3125), (16000, 1311, 0),
+                                                        (4096, 2048, 512), (9000, 700, 1125), (2048, 300, 256), (5000, 1024, 625),
+                                                        (1400, 512, 175), (4999, 1024, 0), (640, 600, 0)])
+def test_tensor_core_tap_plan_replays_the_horizontal_pass(lib_built, in_size, out_size, max_span):
+    """Host logic of kernels_hmma.cu: the n-tile / k-step plan and the permuted hi/lo tap bytes of the B fragments, replayed
+    in the device's order on one row, must give the same bytes as the direct fixed-point Lanczos3 pass (and as the oracle's)."""
+    rng = np.random.default_rng(in_size * 7 + out_size)
+    row = rng.integers(0, 256, in_size).astype(np.uint8)
+    row[: in_size // 9] = 255  # saturated run: the negative lobes must clamp identically
+    direct = np.zeros(out_size, np.uint8)
+    replay = np.full(out_size, 7, np.uint8)
+    rc = _ffi.lib().sarpro_lanczos_row_plan_check(row.ctypes.data, in_size, out_size, max_span, direct.ctypes.data, replay.ctypes.data)
+    assert rc in (0, 1)
+    ref = O.resize_u8_image(np.tile(row, (1, 1)), out_size, 1) if hasattr(O, "resize_u8_image") else None
+    if ref is not None:
+        assert np.array_equal(direct, np.asarray(ref).reshape(-1))
+    if rc == 0:
+        # only axes the kernel does not take: widths that are not a multiple of 8, or scale factors below ~6.5, where more
+        # than three n-tiles (8 output columns) meet one 64-column block; those run on the other pass-B kernels
+        assert in_size % 8 != 0 or in_size < 7 * out_size
+    else:
+        assert np.array_equal(direct, replay)
+    if in_size % 8 == 0 and in_size >= 8 * out_size:
+        assert rc == 1
