@@ -243,7 +243,17 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
     static thread_local std::vector<Present> present;
     present.clear();
     bool have_invalid = false;
-    for (int dn = 0; dn < kDnBins; ++dn) {
+    // the brightest present DN first (wide loads from the top): a GRD band uses a few thousand of the 65,536 bins, and
+    // this scan sits on the critical path between pass A and pass B
+    int top = kDnBins;
+    if (sizeof(CountT) == 4) {
+        const uint64_t* h8 = reinterpret_cast<const uint64_t*>(hist);
+        int i = kDnBins / 2;
+        while (i >= 4 && !(h8[i - 1] | h8[i - 2] | h8[i - 3] | h8[i - 4])) i -= 4;
+        top = i * 2;
+    }
+    while (top > 0 && !hist[top - 1]) --top;
+    for (int dn = 0; dn < top; ++dn) {
         const uint64_t h = hist[dn];
         if (!h) continue;
         out->max_present_dn = (uint32_t)dn;
