@@ -25,7 +25,6 @@
 // normally) the lane's pixels are recomputed with the reference's exact f64 operation order by the whole warp,
 // one pixel per lane, and patched into the fragment registers before the MMA.
 #include <algorithm>
-#include <cstdio>
 #include <vector>
 
 #include "clahe_exact.cuh"
@@ -193,20 +192,12 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     uint32_t mn2 = 0xffffffffu, mx2 = 0u;   // fast path: u16x2 running min / max of floor(u) + 512 (not yet clamped)
     uint32_t mn_e = 0xffffffffu, mx_e = 0;  // exact-path samples
     uint32_t staged_strip = 0xffffffffu;
-#ifdef HM_DEBUG
-    const long long dbg_t0 = clock64();
-    long long dbg_setup = 0;
-    uint32_t dbg_exact = 0;
-#endif
     const uint32_t sb_lane = hm_keep(sbase + L.bfrag + lane * 16u);
     const uint32_t relu_c = hm_keep(0xFE00FE00u); // -512 per half
 
     for (uint32_t pi = pp.cta_first[blockIdx.x]; pi < pp.cta_first[blockIdx.x + 1]; ++pi) {
         const HPiece pc = pp.pieces[pi];
         const uint4 st = pp.strips[pc.strip]; // {j0, j1, cb0, cb1}
-#ifdef HM_DEBUG
-        const long long dbg_ts = clock64();
-#endif
         __syncthreads(); // the previous piece is done with the tables
         if (tid == 0) { s_ctrl[0] = 0; s_ctrl[1] = 0xffffffffu; s_ctrl[2] = 0; }
         const uint32_t koff0 = (uint32_t)pp.ntile[st.x].z;
@@ -314,9 +305,6 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                                 qv = make_float4((float)(A + shift), (float)B, (float)C, (float)D);
                             } else {
                                 qv = make_float4(0.f, 0.f, 0.f, 0.f); // fraction bits all zero: always the exact path
-#ifdef HM_DEBUG
-                                if ((blockIdx.x % 37) == 0) printf("  cta %u always-exact entry cell %u bin %u A %g B %g C %g D %g err %g\n", blockIdx.x, cs, bin, A, B, C, D, err);
-#endif
                             }
                         }
                     }
@@ -335,11 +323,6 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                         if ((double)em <= ldexp(0.45, -(int)f)) { fbits = f; break; }
                     shift = ldexp(0.45, -(int)fbits);
                     magic = (float)ldexp(1.5, 23 - (int)fbits);
-#ifdef HM_DEBUG
-                    if (tid == 0 && (blockIdx.x % 37) == 0)
-                        printf("cta %u piece %u strip %u rows %u-%u cells %u/%u bcol %u ok %d%d%d emax %g fbits %u\n", blockIdx.x, pi, pc.strip,
-                               pc.r0, pc.r1, cellA, cellB, bcol, okA, okB, okR, (double)em, fbits);
-#endif
                 }
             }
         }
@@ -372,9 +355,6 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
 
         const int4* const s_nt = reinterpret_cast<const int4*>(smem + L.nt);
         const uint16_t* const s_cm = reinterpret_cast<const uint16_t*>(smem + L.cm);
-#ifdef HM_DEBUG
-        dbg_setup += clock64() - dbg_ts;
-#endif
         // ---- 16-row groups of the piece, handed out to the warps --------------------------------------
         const uint32_t n_groups = (pc.r1 - pc.r0 + 15u) / 16u;
         for (;;) {
@@ -594,9 +574,6 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                     if (bal[0] | bal[1] | bal[2] | bal[3]) {
                         const uint32_t c0n = __popc(bal[0]), c1n = c0n + __popc(bal[1]), c2n = c1n + __popc(bal[2]), total = c2n + __popc(bal[3]);
                         for (uint32_t base = 0; base < total; base += 4u) {
-#ifdef HM_DEBUG
-                            dbg_exact++;
-#endif
                             const uint32_t idx = base + (lane >> 3);
                             const bool on = idx < total;
                             // vector number and rank of the flagged lane among the lanes flagged for that vector
@@ -660,9 +637,6 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
             }
         }
     }
-#ifdef HM_DEBUG
-    if (tid == 0) printf("ctaend %u cycles %lld pieces %u exact %u setup %lld\n", blockIdx.x, clock64() - dbg_t0, pp.cta_first[blockIdx.x + 1] - pp.cta_first[blockIdx.x], dbg_exact, dbg_setup);
-#endif
     if (CLAHE && a.minmax) {
         if (mn2 != 0xffffffffu) { // fast-path extrema: biased by 512 and not yet clamped
             const int lo = (int)min(mn2 & 0xffffu, mn2 >> 16) - 512, hi = (int)max(mx2 & 0xffffu, mx2 >> 16) - 512;
