@@ -524,7 +524,7 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan);
     const double t_b = trace ? host_ms() - ctx->host_t0 : 0;
     // only DNs up to the brightest present one are ever looked up (stale entries beyond it are never read)
-    const size_t n_lut = std::min<size_t>(kDnBins, ((size_t)w.plan.max_present_dn + 1 + 63) & ~size_t(63));
+    const size_t n_lut = getenv("SARPRO_FULL_LUT") ? (size_t)kDnBins : std::min<size_t>(kDnBins, ((size_t)w.plan.max_present_dn + 1 + 63) & ~size_t(63));
     std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), n_lut * 2);
     w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
     CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, n_lut * 2, cudaMemcpyHostToDevice, ctx->stream));

@@ -231,6 +231,7 @@ def test_full_size_scene_cross_kernels(monkeypatch):
     dev = torch.device("cuda:0")
     vv = synth_band_torch(16000, 25000, SEED_VV, dev)
     vh = synth_band_torch(16000, 25000, SEED_VH, dev, cross_pol=True)
+    torch.cuda.synchronize(dev)  # the library works on its own stream: the generators (torch's stream) must have finished
     outs = {}
     for name, env in (("old", {"SARPRO_HMMA": "0", "SARPRO_TWO_STREAM": "0"}), ("new", {})):
         for k in ("SARPRO_HMMA", "SARPRO_TWO_STREAM", "SARPRO_HPIPE", "SARPRO_FORCE_EXACT"):
@@ -241,12 +242,18 @@ def test_full_size_scene_cross_kernels(monkeypatch):
             for strategy in (S.CLAHE, S.ROBUST):
                 out = torch.empty((2048, 2048, 3), dtype=torch.uint8, device=dev)
                 c.process_synrgb_jpeg(vv, vh, strategy, 2048, True, out=out)
-                first = out.clone()
+                outs[(name, strategy, 1)] = out.cpu().numpy().copy()
                 c.process_synrgb_jpeg(vh, vv, strategy, 2048, True, out=out)  # different call in between
                 c.process_synrgb_jpeg(vv, vh, strategy, 2048, True, out=out)
-                assert torch.equal(first, out), (name, strategy)
-                outs[(name, strategy)] = first.cpu().numpy()
+                outs[(name, strategy, 3)] = out.cpu().numpy().copy()
     for strategy in (S.CLAHE, S.ROBUST):
-        a, b = outs[("old", strategy)], outs[("new", strategy)]
-        assert a.shape == (2048, 2048, 3) and a[(2048 - 1311) // 2 + 5:-(2048 - 1311) // 2 - 5].any()
-        assert np.array_equal(a, b), (strategy, int((a != b).sum()))
+        ref = outs[("new", strategy, 1)]
+        assert ref.shape == (2048, 2048, 3) and ref[(2048 - 1311) // 2 + 5:-(2048 - 1311) // 2 - 5].any()
+        bad = {}
+        for k, v in outs.items():
+            if k[1] == strategy and not np.array_equal(v, ref):
+                d = v != ref
+                ys, xs = np.nonzero(d.any(axis=2))
+                bad[k] = (int(d.sum()), [int(d[..., ch].sum()) for ch in range(3)], int(ys.min()), int(ys.max()), int(xs.min()), int(xs.max()),
+                          int(np.abs(v.astype(int) - ref.astype(int)).max()))
+        assert not bad, bad

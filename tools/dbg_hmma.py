@@ -49,7 +49,8 @@ if os.environ.get("TIME", "1") == "1":
         for k in ("SARPRO_HMMA",):
             os.environ.pop(k, None)
         os.environ.update(env)
-        ctx = S.Context(0)
+        torch.cuda.synchronize()
+ctx = S.Context(0)
         for strat, name in ((S.CLAHE, "clahe"), (S.ROBUST, "robust")):
             ts = []
             for it in range(5):

@@ -7,6 +7,7 @@ from sarpro_b200.synth import SEED_VH, SEED_VV, synth_band_torch
 dev = torch.device("cuda:0")
 k = int(os.environ.get("SCENE", 1))
 vh = synth_band_torch(16000, 25000, SEED_VH + 2 * k, dev, cross_pol=True)
+torch.cuda.synchronize()
 ctx = S.Context(0)
 for it in range(2):
     img = ctx.process_single(vh, S.TIFF, S.U8, S.CLAHE, 2048, False)

@@ -9,6 +9,7 @@ rows = int(os.environ.get("ROWS", 16000)); cols = int(os.environ.get("COLS", 250
 strat = S.STRATEGY_NAMES.index(sys.argv[1] if len(sys.argv) > 1 else "clahe")
 dev = torch.device("cuda:0")
 vv = synth_band_torch(rows, cols, SEED_VV, dev); vh = synth_band_torch(rows, cols, SEED_VH, dev, cross_pol=True)
+torch.cuda.synchronize()
 ctx = S.Context(0)
 out = torch.empty((2048, 2048, 3), dtype=torch.uint8, device=dev)
 for _ in range(int(os.environ.get("ITERS", 2))):
