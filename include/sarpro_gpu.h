@@ -17,6 +17,10 @@
  *   - enum discriminants equal the Rust declaration order;
  *   - pointers are HOST pointers unless the parameter is named *_dev or the descriptor says
  *     SARPRO_LOC_DEVICE.  Pinned host memory (sarpro_host_alloc) makes the copies asynchronous.
+ *     Device buffers are read and written on the context's stream (sarpro_ctx_set_stream, or the
+ *     library's own non-blocking stream): work that produces them on another stream must have
+ *     completed (or that stream must be the context's) before the call; every call returns with its
+ *     outputs complete.
  *   - there is NO CPU fallback: without a CUDA device sarpro_ctx_create fails with
  *     SARPRO_ERR_NO_DEVICE and nothing else can be called.
  */
