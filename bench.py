@@ -220,6 +220,7 @@ def main():
     # Primary leg at every N: one whole scene per rank (BASELINE config 5 at N > 1: scenes distributed over the GPUs, no
     # collective on the data path) -> "weak" scaling, value = all ranks' scene pixels / max-over-ranks time.
     vv, vh = make_scene(rank)
+    torch.cuda.synchronize(dev)  # generated on torch's current stream; the library reads them on `stream`
     h0, h1 = 0, rows
     step = lambda: ctx.process_synrgb_jpeg(vv, vh, strategy, TARGET, True, out=out_dev)
 
@@ -252,6 +253,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
         svv, svh = (vv, vh) if rank == 0 else make_scene(0)   # every rank synthesises the same scene and keeps its rows
+        torch.cuda.synchronize(dev)
         sh0, sh1 = S.shard_halo_rows(rows, cols, TARGET, world, rank, strategy == S.CLAHE)
         pvv, pvh = svv[sh0:sh1], svh[sh0:sh1]                 # contiguous row slices (views)
         sstep = lambda: ctx.process_synrgb_sharded(pvv, pvh, rows, strategy, TARGET, True, out=out_dev)
