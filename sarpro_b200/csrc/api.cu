@@ -521,7 +521,8 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     BandWs& w = ctx->band[b];
     const bool trace = getenv("SARPRO_TRACE") != nullptr;
     const double t_a = trace ? host_ms() - ctx->host_t0 : 0;
-    plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan);
+    plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan,
+                             (int)std::min<uint32_t>(ctx->h_scalars[8 * b + 6] + 1u, kDnBins));
     const double t_b = trace ? host_ms() - ctx->host_t0 : 0;
     // only DNs up to the brightest present one are ever looked up (stale entries beyond it are never read)
     const size_t n_lut = getenv("SARPRO_FULL_LUT") ? (size_t)kDnBins : std::min<size_t>(kDnBins, ((size_t)w.plan.max_present_dn + 1 + 63) & ~size_t(63));
@@ -541,6 +542,8 @@ int run_pass_a(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
     for (int b = 0; b < nb; ++b) {
         RC(dn_pass_a_launch(ctx, b, jobs[b].dn, jobs[b].rows, jobs[b].cols, any_clahe));
         CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, ctx->band[b].total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        // brightest present DN (k_hist_total): bounds the planner's walk over the histogram
+        CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b + 6, (uint32_t*)ctx->band[b].scalars.p + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaEventRecord(ctx->ev[2 + b], ctx->stream));
     }
     return 0;

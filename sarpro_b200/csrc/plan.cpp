@@ -228,7 +228,7 @@ void stats_percentiles_one_walk(const uint64_t* hist, uint64_t n, double min_db,
 } // namespace
 
 template <typename CountT>
-static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out) {
+static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out, int top_hint = -1) {
     const double* db = dn_db_table();
     out->lut.assign(kDnBins, 0);
     out->clahe = false;
@@ -246,7 +246,9 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
     // the brightest present DN first (wide loads from the top): a GRD band uses a few thousand of the 65,536 bins, and
     // this scan sits on the critical path between pass A and pass B
     int top = kDnBins;
-    if (sizeof(CountT) == 4) {
+    if (top_hint >= 0 && top_hint <= kDnBins) {
+        top = top_hint; // (the pinned histogram was just written by the device: every line read here comes from DRAM)
+    } else if (sizeof(CountT) == 4) {
         const uint64_t* h8 = reinterpret_cast<const uint64_t*>(hist);
         int i = kDnBins / 2;
         while (i >= 4 && !(h8[i - 1] | h8[i - 2] | h8[i - 3] | h8[i - 4])) i -= 4;
@@ -361,8 +363,8 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
 void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out) {
     plan_from_dn_histogram_t<uint64_t>(hist, bit_depth, strategy, kind, out);
 }
-void plan_from_dn_histogram32(const uint32_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out) {
-    plan_from_dn_histogram_t<uint32_t>(hist, bit_depth, strategy, kind, out);
+void plan_from_dn_histogram32(const uint32_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out, int top_hint) {
+    plan_from_dn_histogram_t<uint32_t>(hist, bit_depth, strategy, kind, out, top_hint);
 }
 
 ClaheGeom clahe_geometry(uint64_t rows, uint64_t cols) {

@@ -49,7 +49,8 @@ const double* dn_db_table();
 
 // Plan one band from its 65,536-bin DN histogram.
 void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out);
-void plan_from_dn_histogram32(const uint32_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out);
+// top_hint: number of leading bins that can be non-zero (brightest present DN + 1) when the caller knows it, else -1
+void plan_from_dn_histogram32(const uint32_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out, int top_hint = -1);
 
 // scale_u16_to_u8 (autoscale.rs:348-364) as a 65536-entry (or 256-entry) remap for given min/max.
 void make_u16_to_u8_remap(uint16_t mn, uint16_t mx, int n_entries, uint8_t* remap);
