@@ -59,7 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-cudart", "static", "-ldl", "-lpthread",
+        cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-cudart", "static", "-ldl", "-lpthread", "-lrt",
+               "-Xlinker", "--no-undefined",   # a missing definition must fail the build, not the first call
                "-gencode", "arch=compute_100a,code=sm_100a"]
         subprocess.check_call(cmd)
     return LIB

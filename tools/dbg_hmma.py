@@ -50,7 +50,7 @@ if os.environ.get("TIME", "1") == "1":
             os.environ.pop(k, None)
         os.environ.update(env)
         torch.cuda.synchronize()
-ctx = S.Context(0)
+        ctx = S.Context(0)
         for strat, name in ((S.CLAHE, "clahe"), (S.ROBUST, "robust")):
             ts = []
             for it in range(5):
