@@ -12,8 +12,8 @@
 // prefetched one block ahead into the registers just consumed), turns them into samples, and the packed samples ARE
 // the A fragments: the k index of an MMA is only summed over, so the host lays the tap bytes of the B fragments out in
 // the same permuted order (column 32*ks + 8q + 4r + i  <->  register r, byte i of lane q). No sample ever goes through
-// shared memory; the strip's B fragments are staged there once per piece. An output n-tile (8 output columns) is live while the walk crosses its window
-// (three accumulator slots, rotated), then it is scaled, clamped and stored.
+// shared memory; the strip's B fragments are staged there once per piece. An output n-tile (8 output columns) is live
+// while the walk crosses its window (three accumulator slots, rotated), then it is scaled, clamped and stored.
 //
 // Per-pixel stage. LUT strategies: one shared-memory gather (R-way lane-interleaved table, as kernels_hpipe.cu).
 // CLAHE (autoscale.rs:307-330, :602): DN -> address of the pixel's bin entry in an 8-way replicated float4 table
@@ -22,8 +22,10 @@
 // the evaluation (computed per table entry when the piece's tables are built), so the true value lies in
 // [u - 2S, u]. One FADD.RD against 1.5*2^(23-F) truncates u to F fraction bits in the mantissa: if those bits are
 // not all zero, u >= n + 2^-F > n + 2S and floor(true) == floor(u) == n. Otherwise (2^-F of the pixels, F = 13
-// normally) the lane's pixels are recomputed with the reference's exact f64 operation order by the whole warp,
-// one pixel per lane, and patched into the fragment registers before the MMA.
+// normally) the 8-pixel vector is flagged; the warp enumerates its flagged vectors and recomputes them four at a time,
+// one pixel per lane, with the reference's exact f64 operation order, and patches the fragment registers before the
+// MMA. Entries whose four CDF values are identical are resolved when the table is built; bins whose CDFs are all 1.0
+// use a marker entry in the cells where the reference's f64 roundings decide between 254 and 255.
 #include <algorithm>
 #include <vector>
 
