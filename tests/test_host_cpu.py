@@ -122,3 +122,12 @@ def test_tensor_core_tap_plan_replays_the_horizontal_pass(lib_built, in_size, ou
         assert np.array_equal(direct, replay)
     if in_size % 8 == 0 and in_size >= 8 * out_size:
         assert rc == 1
+
+
+def test_rust_sys_crate_matches_the_header():
+    """integration/sarpro-gpu-sys/src/lib.rs (source only, there is no Rust toolchain here) declares exactly the
+    entry points of include/sarpro_gpu.h with the argument lists the generator derives from it."""
+    r = subprocess.run([os.sys.executable, os.path.join(ROOT, "integration", "gen_sys.py"), "--check"])
+    assert r.returncode == 0
+    lib_rs = open(os.path.join(ROOT, "integration", "sarpro-gpu-sys", "src", "lib.rs")).read()
+    assert set(re.findall(r"pub fn (sarpro_[a-z0-9_]+)\(", lib_rs)) == set(_ffi.SYMBOLS)
