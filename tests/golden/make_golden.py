@@ -25,3 +25,14 @@ out["resize8"] = O.resize_u8_image(out["img8"], 57, 41)
 out["resize16"] = O.resize_u16_image(out["img16"], 41, 57)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_small.npz"), **out)
 print("wrote golden_small.npz", {k: v.shape for k, v in out.items() if k.startswith("synrgb")})
+
+# A scene wide enough for the tensor-core pass B (kernels_hmma.cu: source width a multiple of 8, scale factor 8): only the
+# outputs and a checksum of the (seeded, regenerated) inputs are stored.
+import hashlib  # noqa: E402
+wvv, wvh = synth_pair(640, 2048, scene=5, point_targets=1e-4)
+wide = {"input_sha256": np.frombuffer(hashlib.sha256(wvv.tobytes() + wvh.tobytes()).digest(), np.uint8)}
+for s, name in ((O.CLAHE, "clahe"), (O.ROBUST, "robust"), (O.TAMED, "tamed")):
+    rgb, _ = O.pipeline_synrgb_jpeg(wvv.astype(np.float32), wvh.astype(np.float32), s, 256, True)
+    wide[f"synrgb_{name}"] = rgb
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_wide.npz"), **wide)
+print("wrote golden_wide.npz", {k: v.shape for k, v in wide.items()})

@@ -257,3 +257,14 @@ def test_full_size_scene_cross_kernels(monkeypatch):
                 bad[k] = (int(d.sum()), [int(d[..., ch].sum()) for ch in range(3)], int(ys.min()), int(ys.max()), int(xs.min()), int(xs.max()),
                           int(np.abs(v.astype(int) - ref.astype(int)).max()))
         assert not bad, bad
+
+
+@pytest.mark.parametrize("strategy,name", [(S.CLAHE, "clahe"), (S.ROBUST, "robust"), (S.TAMED, "tamed")])
+def test_golden_wide_scene_on_the_device(ctx, strategy, name):
+    """Committed golden outputs (tests/golden/golden_wide.npz, written by make_golden.py from the oracle) for a scene wide
+    enough for the tensor-core pass B: the CUDA path reproduces them byte for byte, from u16 DN and from f32 bands."""
+    from tests.test_oracle_cpu import _wide_scene
+    g, vv, vh = _wide_scene()
+    for a, b in ((vv, vh), (vv.astype(np.float32), vh.astype(np.float32))):
+        img = ctx.process_synrgb_jpeg(a, b, strategy, 256, True)
+        assert np.array_equal(img.rgb, g[f"synrgb_{name}"]), int((img.rgb != g[f"synrgb_{name}"]).sum())

@@ -203,3 +203,19 @@ def test_golden_vectors():
         assert np.array_equal(rgb, g[f"synrgb_{s}"])
     assert np.array_equal(O.resize_u8_image(g["img8"], 57, 41), g["resize8"])
     assert np.array_equal(O.resize_u16_image(g["img16"], 41, 57), g["resize16"])
+
+
+def _wide_scene():
+    import hashlib
+    from sarpro_b200.synth import synth_pair
+    g = np.load(os.path.join(GOLDEN, "golden_wide.npz"))
+    vv, vh = synth_pair(640, 2048, scene=5, point_targets=1e-4)
+    assert np.array_equal(np.frombuffer(hashlib.sha256(vv.tobytes() + vh.tobytes()).digest(), np.uint8), g["input_sha256"])
+    return g, vv, vh
+
+
+def test_golden_wide_scene():
+    """The wide committed scene (the shape the tensor-core pass B takes): the oracle still reproduces it."""
+    g, vv, vh = _wide_scene()
+    rgb, _ = O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), O.CLAHE, 256, True)
+    assert np.array_equal(rgb, g["synrgb_clahe"])
