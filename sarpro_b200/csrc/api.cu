@@ -353,6 +353,13 @@ uint32_t hpipe_hot(const uint16_t* lut, const uint32_t* hist, uint32_t max_prese
     return need <= 2000 ? need : 0;
 }
 
+// The same from a plan (the planner walked the present DNs already: no second scan of the histogram on the critical path).
+uint32_t hpipe_hot_from_plan(const BandPlan& plan, uint32_t* top_out) {
+    *top_out = plan.lut[plan.max_present_dn] & 255u;
+    const uint32_t need = std::max(64u, (plan.sat_from_dn + 1 + 7) & ~7u);
+    return need <= 2000 ? need : 0;
+}
+
 // Piece lists of kernels_hpipe.cu: equal-weight runs of (strip, rows) per persistent CTA; pieces never straddle a
 // vertical CLAHE cell boundary (rows where floor(r/tile_h - 0.5) changes, autoscale.rs:308-310).
 int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe, AxisPlan* ah, int nsub) {
@@ -521,16 +528,18 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     BandWs& w = ctx->band[b];
     const bool trace = getenv("SARPRO_TRACE") != nullptr;
     const double t_a = trace ? host_ms() - ctx->host_t0 : 0;
+    g_plan_trace_on = trace;
     plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan,
                              (int)std::min<uint32_t>(ctx->h_scalars[8 * b + 6] + 1u, kDnBins));
     const double t_b = trace ? host_ms() - ctx->host_t0 : 0;
     // only DNs up to the brightest present one are ever looked up (stale entries beyond it are never read)
     const size_t n_lut = getenv("SARPRO_FULL_LUT") ? (size_t)kDnBins : std::min<size_t>(kDnBins, ((size_t)w.plan.max_present_dn + 1 + 63) & ~size_t(63));
     std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), n_lut * 2);
-    w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
+    w.hot = w.plan.any_valid ? hpipe_hot_from_plan(w.plan, &w.hot_top) : 0;
     CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, n_lut * 2, cudaMemcpyHostToDevice, ctx->stream));
     w.hist_auto_pending = true; // pass-A table shape for the next call: chosen after this band's pass B is queued
-    if (trace) fprintf(stderr, "trace host: band %d histogram on the host at %.3f ms, planned at %.3f, table queued at %.3f ms\n", b, t_a, t_b, host_ms() - ctx->host_t0);
+    if (trace) fprintf(stderr, "trace host: band %d histogram on the host at %.3f ms, planned at %.3f, table queued at %.3f ms; planner us: table cleared %.1f, scan %.1f, moments %.1f, percentiles %.1f, table %.1f\n", b, t_a, t_b, host_ms() - ctx->host_t0,
+                       g_plan_trace_us[0], g_plan_trace_us[1], g_plan_trace_us[2], g_plan_trace_us[3], g_plan_trace_us[4]);
     return 0;
 }
 
@@ -918,11 +927,13 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
             RC(rc);
         }
     }
+    bool join_pending = false;
+    int break_rc = 0;
     for (int b = 0; b < nb; ++b) {
         BandWs& w = ctx->band[b];
         const bool out8 = kinds[b] != PlanKind::Autoscale || bit_depths[b] == SARPRO_U8;
         const size_t esz = out8 ? 1 : 2;
-        RC(reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)));
+        if ((break_rc = reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)))) break;
         canvases[b] = w.small.p;
         if (!integral[b]) {
             const float* fa = ins[b]->location == SARPRO_LOC_HOST ? (const float*)w.f32a.p : (const float*)ins[b]->data;
@@ -931,11 +942,13 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
                                   stats ? &stats[b] : nullptr));
             continue;
         }
-        // Second band of a pipelined pair: its planner upload, CLAHE statistics, pass B and vertical pass go to the side
-        // stream, so that its persistent CTAs fill the SMs the first band's pass B leaves early (the piece runs do not
-        // end together) and its small kernels overlap the first band's. Pass A of this band is complete (host-synced
-        // in wait_and_plan); the main stream joins before anything consumes the canvas.
-        const bool side = pipelined && nb == 2 && b == 1 && ctx->two_stream && ctx->stream2;
+        // First band of a pipelined pair: its planner upload, CLAHE statistics, pass B and vertical pass go to the side
+        // stream. Its pass A is complete (host-synced in wait_and_plan), so the table upload and the CLAHE statistics
+        // run while the second band's pass A still streams on the main stream (they used to queue behind it: 60 us of
+        // idle device between the two passes), and pass B's persistent CTAs move in as that pass A drains. The second
+        // band's chain follows its pass A on the main stream; its persistent CTAs fill the SMs the first band's pass B
+        // leaves early (the piece runs do not end together). The main stream joins after both chains are queued.
+        const bool side = pipelined && nb == 2 && b == 0 && ctx->two_stream && ctx->stream2;
         cudaStream_t main_stream = ctx->stream;
         int rc = 0;
         if (pipelined) rc = wait_and_plan_on(ctx, b, jobs[b], side ? ctx->stream2 : nullptr);
@@ -946,12 +959,17 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
         if (side) {
             cudaError_t e1 = cudaEventRecord(ctx->ev_join, ctx->stream2);
             ctx->stream = main_stream;
-            cudaError_t e2 = cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
-            if (!rc) { CU(e1); CU(e2); }
+            join_pending = true;
+            if (!rc) CU(e1);
         }
-        RC(rc);
+        if (rc) break_rc = rc;
+        if (rc) break;
     }
-    return 0;
+    if (join_pending) { // also on the error path: the side stream must not run past this call unobserved
+        cudaError_t e2 = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+        if (!break_rc) CU(e2);
+    }
+    return break_rc;
 }
 
 } // namespace

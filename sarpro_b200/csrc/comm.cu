@@ -282,7 +282,7 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         ctx->timing.host_syncs++;
         plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
         std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
-        w.hot = w.plan.any_valid ? hpipe_hot(w.plan.lut.data(), ctx->h_hist + (size_t)b * kDnBins, w.plan.max_present_dn, &w.hot_top) : 0;
+        w.hot = w.plan.any_valid ? hpipe_hot_from_plan(w.plan, &w.hot_top) : 0;
         CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
         if (clahe) {
             RC(reserve(ctx, w.tile256, (size_t)ctx->n_tiles * 256 * 4));

@@ -171,6 +171,7 @@ double host_ms();
 int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes);
 void release(DevBuf& b);
 uint32_t hpipe_hot(const uint16_t* lut_host, const uint32_t* hist_host, uint32_t max_present_dn, uint32_t* top_out);
+uint32_t hpipe_hot_from_plan(const BandPlan& plan, uint32_t* top_out);
 int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res);
 int begin_call(sarpro_ctx* ctx);
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off);

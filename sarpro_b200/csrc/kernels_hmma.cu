@@ -47,6 +47,11 @@ constexpr float kMarker = 480.0f;                            // floor of the mar
 constexpr uint32_t kMarkerLess2 = (480u + 512u - 1u) * 0x10001u;
 } // namespace hm
 
+__device__ __forceinline__ uint32_t hm_lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t hm_lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -69,6 +74,18 @@ __device__ __forceinline__ float4 hm_lds_f4u(uint32_t a, uint32_t off) {
 __device__ __forceinline__ uint32_t hm_keep(uint32_t v) {
     uint32_t r;
     asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+// A loop invariant ptxas must hold in a register: it sees through hm_keep's mov and re-derives such values inside the
+// loop (the packed table base as an extra IMAD by 0x10001 per pixel pair, the clamp bias as a MOV per VIADDMNMX); a
+// value that went through a shuffle cannot be re-derived.
+__device__ __forceinline__ uint32_t hm_pin(uint32_t v, uint32_t lane) {
+    return __shfl_sync(0xffffffffu, v, (int)lane);
+}
+// a * b + c as one IMAD (left to the compiler, the multiply and the add end up in different basic blocks)
+__device__ __forceinline__ uint32_t hm_mad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
 __device__ __forceinline__ uint4 hm_lds_u4(uint32_t addr) {
@@ -186,7 +203,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     }
     const uint32_t cap2 = hm_keep((hot - 1u) * 0x10001u);
     const uint32_t lut_mul = hm_keep(1u << lut_shift);
-    const uint32_t cj = hm_keep((sbase + L.lut + (lane & ((lut_mul >> 2) - 1u)) * 4u) * 0x10001u);
+    const uint32_t cj = hm_pin((sbase + L.lut + (lane & ((lut_mul >> 2) - 1u)) * 4u) * 0x10001u, lane);
     const int prec = a.ax.precision;
     const int acc0 = (int)hm_keep(prec > 0 ? (1u << (prec - 1)) : 0u);
     const uint16_t* const src = reinterpret_cast<const uint16_t*>(a.src);
@@ -195,7 +212,11 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     uint32_t mn_e = 0xffffffffu, mx_e = 0;  // exact-path samples
     uint32_t staged_strip = 0xffffffffu;
     const uint32_t sb_lane = hm_keep(sbase + L.bfrag + lane * 16u);
-    const uint32_t relu_c = hm_keep(0xFE00FE00u); // -512 per half
+    const uint32_t cols8 = hm_pin(cols - 8u, lane);
+    const uint32_t cm_base = hm_pin(sbase + L.cm + q * 2u, lane);
+    const float inv2tw = __uint_as_float(hm_pin(__float_as_uint(CLAHE ? a.clahe.inv2tw : 0.f), lane));
+    const float dstep = __uint_as_float(hm_pin(__float_as_uint(__fmul_rn(2.0f, inv2tw)), lane));
+    const uint32_t relu_c = hm_pin(0xFE00FE00u ^ lane, lane) ^ lane; // -512 per half (a shuffled constant would be folded)
 
     for (uint32_t pi = pp.cta_first[blockIdx.x]; pi < pp.cta_first[blockIdx.x + 1]; ++pi) {
         const HPiece pc = pp.pieces[pi];
@@ -367,7 +388,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
             const uint32_t rbase = pc.r0 + grp * 16u;
             // rows beyond the piece repeat its last row (never stored; duplicates do not disturb the min / max)
             const uint32_t rA = min(rbase + g, pc.r1 - 1u), rB = min(rbase + g + 8u, pc.r1 - 1u);
-            const uint32_t oA = rA * cols, oB = rB * cols; // element offsets (< 2^32 for any raster in HBM)
+            const uint32_t oA = hm_pin(rA * cols, lane), oB = hm_pin(rB * cols, lane); // element offsets (< 2^32 for any raster in HBM)
             const bool okA_row = rbase + g < pc.r1, okB_row = rbase + g + 8u < pc.r1;
             uint8_t* const tA = reinterpret_cast<uint8_t*>(a.temp) + (size_t)(rbase + g - a.row0) * a.ax.out_size;
             uint8_t* const tB = tA + (size_t)8 * a.ax.out_size;
@@ -400,7 +421,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                 if (sj[s] < st.y) { const int4 m = s_nt[sj[s] - st.x]; sfb[s] = m.x; slb[s] = m.y; sbo[s] = m.z; }
             }
             // columns past the raster repeat its last 8-sample vector (they carry zero taps)
-            auto vec_col = [&](uint32_t cb, uint32_t h) { return min(cb * 64u + h * 32u + q * 8u, cols - 8u); };
+            auto vec_col = [&](uint32_t cb, uint32_t h) { return min(cb * 64u + h * 32u + q * 8u, cols8); };
             uint4 d[4]; // [0] row A k-step 0 (cols 8q..8q+7 of the block), [1] row A k-step 1 (cols 32+8q..), [2], [3]: row B
             {
                 const uint32_t c0 = vec_col(st.z, 0), c1 = vec_col(st.z, 1);
@@ -424,12 +445,11 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                         // dx = m / (2*tile_w), m = 2c - tile_w*(2t+1) (k_clahe_axis), t = the cell of the vector's first column;
                         // fp32: |dxf - dx| < 2.4e-7
                         const int m0 = 2 * (int)c0 - (c0 >= bcol ? twB : twA);
-                        const float dx0 = __fmul_rn((float)m0, a.clahe.inv2tw);
-                        const float dstep = __fmul_rn(2.0f, a.clahe.inv2tw);
+                        const float dx0 = __fmul_rn((float)m0, inv2tw);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) dx[k] = __fmaf_rn((float)k, dstep, dx0);
                         if (fix) {
-                            const uint32_t cmw = s_cm[(cb - st.z) * 8u + h * 4u + q]; // (beyond the raster: the clamped vector's)
+                            const uint32_t cmw = hm_lds_u16(cm_base + ((cb - st.z) * 8u + h * 4u) * 2u); // (beyond the raster: the clamped vector's)
                             cm0 = cmw & 255u;
                             cm1 = cmw >> 8;
                         }
@@ -441,7 +461,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                             const uint32_t wv[4] = {d[v].x, d[v].y, d[v].z, d[v].w};
                             uint32_t a2[4], pr[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) a2[j] = __vminu2(wv[j], cap2) * lut_mul + cj;
+                            for (int j = 0; j < 4; ++j) a2[j] = hm_mad(__vminu2(wv[j], cap2), lut_mul, cj);
                             if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn)); // the DNs are consumed: prefetch in place
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -461,7 +481,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                             const uint32_t wv[4] = {d[v].x, d[v].y, d[v].z, d[v].w};
                             uint32_t a2[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) a2[j] = __vminu2(wv[j], cap2) * lut_mul + cj;
+                            for (int j = 0; j < 4; ++j) a2[j] = hm_mad(__vminu2(wv[j], cap2), lut_mul, cj);
                             if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn)); // the DNs are consumed: prefetch in place
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {

@@ -2,6 +2,8 @@
 // which never fuses a*b+c, and its f64/f32 results are reproduced operation by operation.
 #include "plan.h"
 
+#include <chrono>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -227,14 +229,24 @@ void stats_percentiles_one_walk(const uint64_t* hist, uint64_t n, double min_db,
 
 } // namespace
 
+// SARPRO_TRACE: host time stamps inside the planner (us since the call): scan done, stats, percentiles, table
+double g_plan_trace_us[6];
+bool g_plan_trace_on = false;
+static inline void plan_stamp(int i, const std::chrono::steady_clock::time_point& t0) {
+    if (g_plan_trace_on) g_plan_trace_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+}
+
 template <typename CountT>
 static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out, int top_hint = -1) {
+    const auto t0 = std::chrono::steady_clock::now();
     const double* db = dn_db_table();
-    out->lut.assign(kDnBins, 0);
+    if (out->lut.size() != (size_t)kDnBins) out->lut.resize(kDnBins);
+    std::memset(out->lut.data(), 0, (size_t)kDnBins * sizeof(uint16_t)); // (vector::assign is a 2-byte loop at -O2: 20 us)
     out->clahe = false;
     out->any_valid = false;
     out->pre_min = out->pre_max = 0;
     out->max_present_dn = 0;
+    out->sat_from_dn = 0;
     std::memset(&out->stats, 0, sizeof(out->stats));
 
     // Distinct sample values present in the raster (typically ~1e3 of the 65,536 DNs): everything below is
@@ -242,6 +254,7 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
     struct Present { uint32_t dn; uint64_t h; };
     static thread_local std::vector<Present> present;
     present.clear();
+    plan_stamp(0, t0);
     bool have_invalid = false;
     // the brightest present DN first (wide loads from the top): a GRD band uses a few thousand of the 65,536 bins, and
     // this scan sits on the critical path between pass A and pass B
@@ -255,13 +268,24 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
         top = i * 2;
     }
     while (top > 0 && !hist[top - 1]) --top;
-    for (int dn = 0; dn < top; ++dn) {
+    auto take = [&](int dn) {
         const uint64_t h = hist[dn];
-        if (!h) continue;
+        if (!h) return;
         out->max_present_dn = (uint32_t)dn;
         if (db[dn] > -50.0) present.push_back(Present{(uint32_t)dn, h}); // pipeline.rs:22
         else have_invalid = true;
+    };
+    int dn0 = 0;
+    if (sizeof(CountT) == 4) { // above the speckle range only point targets are present: skip empty bins eight at a time
+        for (; dn0 + 8 <= top; dn0 += 8) {
+            uint64_t q[4];
+            std::memcpy(q, hist + dn0, 32);
+            if (!(q[0] | q[1] | q[2] | q[3])) continue;
+            for (int k = 0; k < 8; ++k) take(dn0 + k);
+        }
     }
+    for (; dn0 < top; ++dn0) take(dn0);
+    plan_stamp(1, t0);
     // Pass 1 of compute_histogram_stats (autoscale.rs:37-55) over distinct values.
     uint64_t count = 0;
     double min_db = std::numeric_limits<double>::infinity();
@@ -287,6 +311,7 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
     const double mean_db = (double)mean_l;
     const double std_db = count > 1 ? (double)sqrtl(m2 / (long double)count) : 0.0;
 
+    plan_stamp(2, t0);
     // Pass 2 (autoscale.rs:103-117): 4096-bin histogram over [min,max].
     uint64_t h4096[kStatBins];
     const bool degenerate = std::fabs(max_db - min_db) < std::numeric_limits<double>::epsilon();
@@ -312,7 +337,21 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
         }
         stats_percentiles_one_walk(h4096, count, min_db, max_db, &st);
     }
+    plan_stamp(3, t0);
     choose_window(strategy, kind, &st);
+    // The lowest present DN from which every present DN up to the brightest one carries that one's table word (the tables
+    // are monotone and saturate above the window): bounds the shared-memory table of pass B (hpipe_hot_from_plan).
+    auto set_sat_from = [&]() {
+        const uint32_t top_word = out->lut[out->max_present_dn] & 255u;
+        uint32_t h = out->max_present_dn;
+        bool all = true;
+        for (size_t i = present.size(); i-- > 0;) {
+            if (present[i].dn > out->max_present_dn) continue;
+            if ((out->lut[present[i].dn] & 255u) == top_word) h = present[i].dn; else { all = false; break; }
+        }
+        if (all && have_invalid && top_word == 0) h = 0; // invalid DNs are present with word 0
+        out->sat_from_dn = h;
+    };
     const double low = st.low_clip, high = st.high_clip, gamma = st.gamma;
     const double range = std::fmax(high - low, 1.0); // autoscale.rs:429, 564, 729
 
@@ -330,6 +369,8 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
             if (bin >= kClaheBins) bin = kClaheBins - 1;
             out->lut[p.dn] = (uint16_t)bin;
         }
+        set_sat_from();
+        plan_stamp(4, t0);
         return;
     }
 
@@ -358,6 +399,7 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
         make_u16_to_u8_remap(mn, mx, 256, remap);
         for (const Present& p : present) out->lut[p.dn] = remap[out->lut[p.dn] > 255 ? 255 : out->lut[p.dn]];
     }
+    set_sat_from();
 }
 
 void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out) {

@@ -42,10 +42,13 @@ struct BandPlan {
     uint16_t pre_min = 0, pre_max = 0; // min/max of the quantised samples before scale_u16_to_u8
     std::vector<uint16_t> lut;     // kDnBins entries: DN -> final sample (or CLAHE bin)
     uint32_t max_present_dn = 0;   // highest DN with a non-zero count
+    uint32_t sat_from_dn = 0;      // lowest present DN from which all present DNs share the brightest one's table word (low byte)
 };
 
 // dB value of every u16 DN after the f32 cast (pipeline.rs:19-20); valid iff > -50 (pipeline.rs:22).
 const double* dn_db_table();
+extern double g_plan_trace_us[6]; // SARPRO_TRACE: stamps inside the last plan_from_dn_histogram* call
+extern bool g_plan_trace_on;
 
 // Plan one band from its 65,536-bin DN histogram.
 void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out);
