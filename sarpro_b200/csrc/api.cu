@@ -470,17 +470,17 @@ OutGeom out_geometry(size_t cols, size_t rows, bool has_target, size_t target, b
 
 
 // Pass A launches for band slot b (no synchronisation): per-tile DN histogram + totals.
-int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units) {
+int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units, int phase) {
     ShardGeom sg;
     sg.scene_rows = rows;
     sg.row_off = 0;
     sg.own0 = 0;
     sg.own1 = rows;
-    return dn_pass_a_launch_sharded(ctx, b, dn, rows, cols, clahe_units, sg);
+    return dn_pass_a_launch_sharded(ctx, b, dn, rows, cols, clahe_units, sg, phase);
 }
 
 int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units,
-                             const ShardGeom& sg) {
+                             const ShardGeom& sg, int phase) {
     if (ctx->units_rows != rows || ctx->units_cols != cols || ctx->units_clahe != (int)clahe_units ||
         ctx->units_scene_rows != sg.scene_rows || ctx->units_row_off != sg.row_off || ctx->units_own0 != sg.own0 ||
         ctx->units_own1 != sg.own1) {
@@ -494,31 +494,33 @@ int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_
         ctx->units_own1 = sg.own1;
     }
     BandWs& w = ctx->band[b];
-    RC(reserve(ctx, w.tile_hist, (size_t)ctx->n_tiles * kDnBins * 4));
-    RC(reserve(ctx, w.total, kDnBins * 4));
-    RC(reserve(ctx, w.lut, kDnBins * 2));
-    RC(reserve(ctx, w.scalars, 64));
-    CU(cudaMemsetAsync(w.tile_hist.p, 0, (size_t)ctx->n_tiles * kDnBins * 4, ctx->stream));
-    const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0u};
-    std::memcpy(ctx->h_scalars + 8 * b, init, sizeof(init));
-    CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync((uint32_t*)w.scalars.p + 4, 0, 16, ctx->stream)); // [4]: work-unit counter of pass A
+    if (phase != 2) {
+        RC(reserve(ctx, w.tile_hist, (size_t)ctx->n_tiles * kDnBins * 4));
+        RC(reserve(ctx, w.total, kDnBins * 4));
+        RC(reserve(ctx, w.lut, kDnBins * 2));
+        RC(reserve(ctx, w.scalars, 64));
+        RC(reserve(ctx, w.present, kPresentWords * 4));
+        CU(cudaMemsetAsync(w.tile_hist.p, 0, (size_t)ctx->n_tiles * kDnBins * 4, ctx->stream));
+        const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0u};
+        std::memcpy(ctx->h_scalars + 8 * b, init, sizeof(init));
+        CU(cudaMemcpyAsync(w.scalars.p, ctx->h_scalars + 8 * b, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync((uint32_t*)w.scalars.p + 4, 0, 16, ctx->stream)); // [4]: work-unit counter of pass A, [5]: present-list allocator
+    }
+    if (phase == 1) return 0;
     KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
                                          ctx->sm_count, ctx->hist_variant >= 0 ? ctx->hist_variant : w.hist_auto, ctx->stream,
                                          (uint32_t*)w.scalars.p + 4));
     KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
-                                            (uint32_t*)w.scalars.p + 2, ctx->stream));
+                                            (uint32_t*)w.scalars.p + 2, (uint32_t*)w.scalars.p + 5, (uint2*)w.present.p, kPresentCap,
+                                            ctx->stream));
     return 0;
 }
 
 // Pass-A table shape for the next raster in this slot: the replicated shared histogram covers DN < 1024 (32 replicas,
 // conflict-free), < 2048 (16) or < 4096 (8); brighter pixels take a per-pixel global atomic, which is only cheap
 // when they are rare (< 4e-4 of the pixels).
-int choose_hist_variant(const uint32_t* hist) {
-    uint64_t total = 0, ge1k = 0, ge2k = 0;
-    for (int d = 0; d < kDnBins; ++d) total += hist[d];
-    for (int d = 1024; d < kDnBins; ++d) ge1k += hist[d];
-    for (int d = 2048; d < kDnBins; ++d) ge2k += hist[d];
+int choose_hist_variant(const BandPlan& plan) {
+    const uint64_t total = plan.px_total, ge1k = plan.px_ge1024, ge2k = plan.px_ge2048; // counted by the planner
     const uint64_t lim = total / 2500; // measured on the C3 co-pol band (2.1e-4 of the pixels at DN >= 1024): 0.174 ms with the 1024-DN table, 0.187 ms with the 2048-DN one
     return ge1k <= lim ? 22 : (ge2k <= lim ? 21 : 20);
 }
@@ -529,8 +531,16 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     const bool trace = getenv("SARPRO_TRACE") != nullptr;
     const double t_a = trace ? host_ms() - ctx->host_t0 : 0;
     g_plan_trace_on = trace;
-    plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan,
-                             (int)std::min<uint32_t>(ctx->h_scalars[8 * b + 6] + 1u, kDnBins));
+    // the planner reads the device-compacted list of present DNs; the dense totals only when that list overflowed
+    const uint32_t* hp = ctx->h_present + (size_t)b * kPresentWords;
+    if (getenv("SARPRO_DENSE_PLAN") ||
+        !plan_from_present_list(hp, hp + 512, kPresentCap, job.bit_depth, job.strategy, job.kind, &w.plan)) {
+        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->timing.host_syncs++;
+        plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan,
+                                 (int)std::min<uint32_t>(ctx->h_scalars[8 * b + 6] + 1u, kDnBins));
+    }
     const double t_b = trace ? host_ms() - ctx->host_t0 : 0;
     // only DNs up to the brightest present one are ever looked up (stale entries beyond it are never read)
     const size_t n_lut = getenv("SARPRO_FULL_LUT") ? (size_t)kDnBins : std::min<size_t>(kDnBins, ((size_t)w.plan.max_present_dn + 1 + 63) & ~size_t(63));
@@ -548,12 +558,22 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
 int run_pass_a(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
     bool any_clahe = false;
     for (int b = 0; b < nb; ++b) any_clahe |= uses_clahe(jobs[b]);
+    // every band's cleared workspaces first, so that nothing but k_hist_total sits between two bands' histogram kernels
+    for (int b = 0; b < nb; ++b) RC(dn_pass_a_launch(ctx, b, jobs[b].dn, jobs[b].rows, jobs[b].cols, any_clahe, 1));
     for (int b = 0; b < nb; ++b) {
-        RC(dn_pass_a_launch(ctx, b, jobs[b].dn, jobs[b].rows, jobs[b].cols, any_clahe));
-        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, ctx->band[b].total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        // brightest present DN (k_hist_total): bounds the planner's walk over the histogram
-        CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b + 6, (uint32_t*)ctx->band[b].scalars.p + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaEventRecord(ctx->ev[2 + b], ctx->stream));
+        RC(dn_pass_a_launch(ctx, b, jobs[b].dn, jobs[b].rows, jobs[b].cols, any_clahe, 2));
+        // The read-back of all but the last band goes through the side stream: on the main stream the two copies would
+        // hold the next band's histogram kernel back.
+        cudaStream_t rs = ctx->stream;
+        if (b + 1 < nb && ctx->two_stream && ctx->stream2) {
+            CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev[4], 0));
+            rs = ctx->stream2;
+        }
+        // the present DNs (k_hist_total) and the brightest one (bounds the planner's walk if it has to read the dense totals)
+        CU(cudaMemcpyAsync(ctx->h_present + (size_t)b * kPresentWords, ctx->band[b].present.p, kPresentWords * 4, cudaMemcpyDeviceToHost, rs));
+        CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b + 6, (uint32_t*)ctx->band[b].scalars.p + 2, 4, cudaMemcpyDeviceToHost, rs));
+        CU(cudaEventRecord(ctx->ev[2 + b], rs));
     }
     return 0;
 }
@@ -826,7 +846,7 @@ int end_call(sarpro_ctx* ctx) {
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     for (int b = 0; b < 2; ++b) // host work kept off the critical path: runs while the device drains the queue
         if (ctx->band[b].hist_auto_pending) {
-            ctx->band[b].hist_auto = choose_hist_variant(ctx->h_hist + (size_t)b * kDnBins);
+            ctx->band[b].hist_auto = choose_hist_variant(ctx->band[b].plan);
             ctx->band[b].hist_auto_pending = false;
         }
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1016,6 +1036,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     for (auto& ev : ctx->sev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMallocHost((void**)&ctx->h_hist, 2 * kDnBins * 4)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_present, 2 * kPresentWords * 4)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_lut, 2 * kDnBins * 2)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_scalars, 2 * 8 * 4)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_remap, 2 * 256)) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -1044,7 +1065,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& w : ctx->band)
         for (DevBuf* b : {&w.dn, &w.f32a, &w.f32b, &w.tile_hist, &w.total, &w.lut, &w.tile256, &w.cdf, &w.cdf32, &w.remap,
-                          &w.temp, &w.small, &w.full, &w.scalars})
+                          &w.temp, &w.small, &w.full, &w.scalars, &w.present})
             release(*b);
     for (DevBuf* b : {&ctx->units, &ctx->tile_px, &ctx->col_dx, &ctx->col_omdx, &ctx->col_t, &ctx->row_dy, &ctx->row_omdy,
                       &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts, &ctx->col_m, &ctx->row_sat,
@@ -1057,6 +1078,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
         delete kv.second;
     }
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
+    if (ctx->h_present) cudaFreeHost(ctx->h_present);
     if (ctx->h_lut) cudaFreeHost(ctx->h_lut);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_remap) cudaFreeHost(ctx->h_remap);

@@ -71,7 +71,8 @@ struct BandWs {
     DevBuf f32a, f32b; // f32 staging
     DevBuf tile_hist, total, lut, tile256, cdf, cdf32, remap;
     DevBuf temp, small, full;
-    DevBuf scalars; // [0..1] minmax, [2] max_dn, [3] flag
+    DevBuf scalars; // [0..1] minmax, [2] max_dn, [3] flag, [4] pass-A work-unit counter, [5] present-list allocator
+    DevBuf present; // k_hist_total: 256 {offset, count} + kPresentCap {dn, count} (see plan_from_present_list)
     DevBuf edges, hist4096, f32scan; // general f32 path
     BandPlan plan;
     int hist_auto = 21;            // pass-A table shape for the next call (see choose_hist_variant)
@@ -143,6 +144,7 @@ struct sarpro_ctx {
     std::map<sarpro::AxisKey, sarpro::AxisPlan*> axes;
     // pinned staging
     uint32_t* h_hist = nullptr;    // [2][65536]
+    uint32_t* h_present = nullptr; // [2][2 * (256 + kPresentCap)]
     uint16_t* h_lut = nullptr;     // [2][65536]
     uint32_t* h_scalars = nullptr; // [2][8]
     uint8_t* h_remap = nullptr;    // [2][256]
@@ -175,9 +177,10 @@ uint32_t hpipe_hot_from_plan(const BandPlan& plan, uint32_t* top_out);
 int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res);
 int begin_call(sarpro_ctx* ctx);
 int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off);
-int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units);
+// phase: 0 = everything, 1 = only the preamble (workspaces, cleared histograms and counters), 2 = only the kernels
+int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units, int phase = 0);
 int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units,
-                             const ShardGeom& sg);
+                             const ShardGeom& sg, int phase = 0);
 int dn_run_pass_b(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& g, void* canvas);
 int run_clahe_stats(sarpro_ctx* ctx, int b);
 int clahe_minmax(sarpro_ctx* ctx, int b, uint32_t* mn, uint32_t* mx);

@@ -22,7 +22,10 @@ struct HistUnit {
 cudaError_t launch_dn_hist(const uint16_t* dn, uint64_t cols, const HistUnit* units_dev, uint32_t n_units,
                            uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream, uint32_t* counter = nullptr);
 // total[dn] = sum_t tile_hist[t][dn]; max_dn[0] = highest DN with a non-zero total (atomicMax).
+// present: 256 {offset, count} block entries followed by `cap` {dn, count} pairs (nullptr: totals only); *n_present
+// must be zero before the launch
 cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint32_t* total, uint32_t* max_dn,
+                              uint32_t* n_present, uint2* present, uint32_t cap,
                               cudaStream_t stream);
 
 // ---- CLAHE tile statistics ------------------------------------------------------------------

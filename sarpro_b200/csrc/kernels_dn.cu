@@ -385,19 +385,50 @@ cudaError_t launch_dn_hist(const uint16_t* dn, uint64_t cols, const HistUnit* un
     }
 }
 
-// total[dn] = sum over tiles; max_dn = highest non-empty DN
-__global__ void k_hist_total(const uint32_t* __restrict__ tile_hist, uint32_t n_tiles, uint32_t* __restrict__ total,
-                             uint32_t* __restrict__ max_dn) {
-    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; // < 65536
+// total[dn] = sum over tiles; max_dn = highest non-empty DN; and the non-empty bins as (dn, count) pairs for the host
+// planner (a GRD band uses ~1e3 of the 65,536 DNs: the planner reads 12 KB of pinned memory instead of scanning 256 KB
+// of it cold). Each block compacts its 256 DNs and takes pairs[off .. off+cnt) with one atomic; blk[block] = {off, cnt}.
+// The allocation order is arbitrary, the order inside a block and the block index give the DN order back. Pairs beyond
+// `cap` are dropped (the host sees off + cnt > cap and reads the dense totals instead).
+__global__ void __launch_bounds__(256) k_hist_total(const uint32_t* __restrict__ tile_hist, uint32_t n_tiles,
+                                                    uint32_t* __restrict__ total, uint32_t* __restrict__ max_dn,
+                                                    uint32_t* __restrict__ n_present, uint2* __restrict__ blk,
+                                                    uint2* __restrict__ pairs, uint32_t cap) {
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_off;
+    const uint32_t d = blockIdx.x * 256u + threadIdx.x; // < 65536
     uint32_t s = 0;
     for (uint32_t t = 0; t < n_tiles; ++t) s += tile_hist[(size_t)t * 65536u + d];
     total[d] = s;
     unsigned m = warp_reduce_max(s ? d : 0u);
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_dn, m);
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (lane == 0 && m) atomicMax(max_dn, m);
+    if (!blk) return;
+    const uint32_t bal = __ballot_sync(0xffffffffu, s != 0u);
+    if (lane == 0) s_w[wid] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, cnt = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+        const uint32_t c = s_w[i];
+        if (i < wid) before += c;
+        cnt += c;
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t off = cnt ? atomicAdd(n_present, cnt) : 0u;
+        s_off = off;
+        blk[blockIdx.x] = make_uint2(off, cnt);
+    }
+    __syncthreads();
+    if (s) {
+        const uint32_t pos = s_off + before + __popc(bal & ((1u << lane) - 1u));
+        if (pos < cap) pairs[pos] = make_uint2(d, s);
+    }
 }
 cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint32_t* total, uint32_t* max_dn,
-                              cudaStream_t stream) {
-    k_hist_total<<<65536 / 256, 256, 0, stream>>>(tile_hist, n_tiles, total, max_dn);
+                              uint32_t* n_present, uint2* present, uint32_t cap, cudaStream_t stream) {
+    k_hist_total<<<65536 / 256, 256, 0, stream>>>(tile_hist, n_tiles, total, max_dn, n_present, present,
+                                                  present ? present + 256 : nullptr, cap);
     return cudaGetLastError();
 }
 

@@ -377,7 +377,6 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
         };
 
         const int4* const s_nt = reinterpret_cast<const int4*>(smem + L.nt);
-        const uint16_t* const s_cm = reinterpret_cast<const uint16_t*>(smem + L.cm);
         // ---- 16-row groups of the piece, handed out to the warps --------------------------------------
         const uint32_t n_groups = (pc.r1 - pc.r0 + 15u) / 16u;
         for (;;) {

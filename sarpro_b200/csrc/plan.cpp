@@ -3,6 +3,7 @@
 #include "plan.h"
 
 #include <chrono>
+#include <memory>
 
 #include <algorithm>
 #include <cmath>
@@ -40,6 +41,16 @@ inline uint8_t cast_u8f(float x) {
     return (uint8_t)x;
 }
 // Rust clamp: NaN propagates.
+// v.max(lo).min(hi) (autoscale.rs:440, 583, 649, 734) for operands that are never NaN, without the libm calls
+inline double clip_nn(double v, double lo, double hi) {
+    const double a = v < lo ? lo : v;
+    return a > hi ? hi : a;
+}
+// f64::round (half away from zero) for 0 <= v < 2^31: v - trunc(v) is exact
+inline double round_nn(double v) {
+    const double t = (double)(int32_t)v;
+    return (v - t >= 0.5) ? t + 1.0 : t;
+}
 inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 inline float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -236,26 +247,73 @@ static inline void plan_stamp(int i, const std::chrono::steady_clock::time_point
     if (g_plan_trace_on) g_plan_trace_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
 }
 
-template <typename CountT>
-static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out, int top_hint = -1) {
-    const auto t0 = std::chrono::steady_clock::now();
-    const double* db = dn_db_table();
+struct Present { uint32_t dn; uint64_t h; };
+// the valid present DNs of the plan in progress, ascending (one uninitialised buffer per thread, sized for every DN)
+struct PresentList {
+    Present* b = nullptr;
+    Present* e = nullptr;
+    const Present* begin() const { return b; }
+    const Present* end() const { return e; }
+    size_t size() const { return (size_t)(e - b); }
+    const Present& operator[](size_t i) const { return b[i]; }
+};
+static thread_local std::unique_ptr<Present[]> t_present_buf;
+
+// Start of a plan: cleared outputs. Returns the (thread-local) list the caller fills with the valid present DNs in
+// ascending order through a PlanCollector.
+static PresentList plan_begin(BandPlan* out) {
     if (out->lut.size() != (size_t)kDnBins) out->lut.resize(kDnBins);
     std::memset(out->lut.data(), 0, (size_t)kDnBins * sizeof(uint16_t)); // (vector::assign is a 2-byte loop at -O2: 20 us)
     out->clahe = false;
     out->any_valid = false;
+    out->have_invalid = false;
     out->pre_min = out->pre_max = 0;
     out->max_present_dn = 0;
     out->sat_from_dn = 0;
+    out->px_total = out->px_ge1024 = out->px_ge2048 = 0;
     std::memset(&out->stats, 0, sizeof(out->stats));
+    if (!t_present_buf) t_present_buf.reset(new Present[kDnBins]);
+    PresentList l;
+    l.b = l.e = t_present_buf.get();
+    return l;
+}
+// Collector of the present DNs (ascending): counters stay in registers, the list is written through a raw pointer
+// (updating the plan's fields and push_back per entry made this the slowest part of the planner).
+struct PlanCollector {
+    const double* db;
+    Present* w;
+    uint32_t max_dn = 0;
+    uint64_t total = 0, ge1k = 0, ge2k = 0;
+    bool invalid = false;
+    inline void take(uint32_t dn, uint64_t h) {
+        if (!h) return;
+        max_dn = dn;
+        total += h;
+        ge1k += dn >= 1024 ? h : 0;
+        ge2k += dn >= 2048 ? h : 0;
+        if (db[dn] > -50.0) *w++ = Present{dn, h}; // pipeline.rs:22
+        else invalid = true;
+    }
+    void finish(BandPlan* out, PresentList& present) {
+        present.e = w;
+        out->max_present_dn = max_dn;
+        out->px_total = total;
+        out->px_ge1024 = ge1k;
+        out->px_ge2048 = ge2k;
+        out->have_invalid = invalid;
+    }
+};
+static void plan_finish(const PresentList& present, int bit_depth, int strategy, PlanKind kind, BandPlan* out,
+                        const std::chrono::steady_clock::time_point& t0);
 
+template <typename CountT>
+static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out, int top_hint = -1) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const double* db = dn_db_table();
     // Distinct sample values present in the raster (typically ~1e3 of the 65,536 DNs): everything below is
     // evaluated once per distinct value instead of once per pixel.
-    struct Present { uint32_t dn; uint64_t h; };
-    static thread_local std::vector<Present> present;
-    present.clear();
+    PresentList present = plan_begin(out);
     plan_stamp(0, t0);
-    bool have_invalid = false;
     // the brightest present DN first (wide loads from the top): a GRD band uses a few thousand of the 65,536 bins, and
     // this scan sits on the critical path between pass A and pass B
     int top = kDnBins;
@@ -268,23 +326,43 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
         top = i * 2;
     }
     while (top > 0 && !hist[top - 1]) --top;
-    auto take = [&](int dn) {
-        const uint64_t h = hist[dn];
-        if (!h) return;
-        out->max_present_dn = (uint32_t)dn;
-        if (db[dn] > -50.0) present.push_back(Present{(uint32_t)dn, h}); // pipeline.rs:22
-        else have_invalid = true;
-    };
+    PlanCollector col{db, present.b};
     int dn0 = 0;
     if (sizeof(CountT) == 4) { // above the speckle range only point targets are present: skip empty bins eight at a time
         for (; dn0 + 8 <= top; dn0 += 8) {
             uint64_t q[4];
             std::memcpy(q, hist + dn0, 32);
             if (!(q[0] | q[1] | q[2] | q[3])) continue;
-            for (int k = 0; k < 8; ++k) take(dn0 + k);
+            for (int k = 0; k < 8; ++k) col.take((uint32_t)(dn0 + k), hist[dn0 + k]);
         }
     }
-    for (; dn0 < top; ++dn0) take(dn0);
+    for (; dn0 < top; ++dn0) col.take((uint32_t)dn0, hist[dn0]);
+    col.finish(out, present);
+    plan_finish(present, bit_depth, strategy, kind, out, t0);
+}
+
+bool plan_from_present_list(const uint32_t* blk, const uint32_t* pairs, uint32_t cap, int bit_depth, int strategy, PlanKind kind,
+                            BandPlan* out) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int b = 0; b < 256; ++b)
+        if ((uint64_t)blk[2 * b] + blk[2 * b + 1] > cap) return false; // more present DNs than the list holds
+    const double* db = dn_db_table();
+    PresentList present = plan_begin(out);
+    plan_stamp(0, t0);
+    PlanCollector col{db, present.b};
+    for (int b = 0; b < 256; ++b) {
+        const uint32_t* p = pairs + 2 * (size_t)blk[2 * b];
+        for (uint32_t i = 0; i < blk[2 * b + 1]; ++i) col.take(p[2 * i] & 0xffffu, p[2 * i + 1]);
+    }
+    col.finish(out, present);
+    plan_finish(present, bit_depth, strategy, kind, out, t0);
+    return true;
+}
+
+static void plan_finish(const PresentList& present, int bit_depth, int strategy, PlanKind kind, BandPlan* out,
+                        const std::chrono::steady_clock::time_point& t0) {
+    const double* db = dn_db_table();
+    const bool have_invalid = out->have_invalid;
     plan_stamp(1, t0);
     // Pass 1 of compute_histogram_stats (autoscale.rs:37-55) over distinct values.
     uint64_t count = 0;
@@ -360,10 +438,10 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
         // autoscale.rs:582-591 normalisation + :263 / :320 bin index; the blend runs on the device.
         out->clahe = true;
         for (const Present& p : present) {
-            const double clipped = std::fmin(std::fmax(db[p.dn], low), high);
+            const double clipped = clip_nn(db[p.dn], low, high);
             const double n = (clipped - low) / range;
             const double v = clampd(n, 0.0, 1.0);
-            const double b = std::round(v * ((double)kClaheBins - 1.0));
+            const double b = round_nn(v * ((double)kClaheBins - 1.0)); // v in [0, 1]
             long long bin = (b == b) ? (long long)b : 0;
             if (bin < 0) bin = 0;
             if (bin >= kClaheBins) bin = kClaheBins - 1;
@@ -378,7 +456,7 @@ static void plan_from_dn_histogram_t(const CountT* hist, int bit_depth, int stra
     uint16_t mn = 65535, mx = 0;
     if (have_invalid) { mn = 0; mx = 0; } // invalid pixels are written as 0 (autoscale.rs:444, 653, 738)
     for (const Present& p : present) {
-        const double clipped = std::fmin(std::fmax(db[p.dn], low), high);
+        const double clipped = clip_nn(db[p.dn], low, high);
         uint16_t q;
         if (tamed_rgb) { // autoscale.rs:734-736
             const double normalized = (clipped - low) / range;

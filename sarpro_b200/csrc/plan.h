@@ -43,6 +43,8 @@ struct BandPlan {
     std::vector<uint16_t> lut;     // kDnBins entries: DN -> final sample (or CLAHE bin)
     uint32_t max_present_dn = 0;   // highest DN with a non-zero count
     uint32_t sat_from_dn = 0;      // lowest present DN from which all present DNs share the brightest one's table word (low byte)
+    bool have_invalid = false;     // some present DN is invalid (dB <= -50: DN 0)
+    uint64_t px_total = 0, px_ge1024 = 0, px_ge2048 = 0; // pixels in all / in the bright bins (pass-A table shape of the next call)
 };
 
 // dB value of every u16 DN after the f32 cast (pipeline.rs:19-20); valid iff > -50 (pipeline.rs:22).
@@ -54,6 +56,12 @@ extern bool g_plan_trace_on;
 void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out);
 // top_hint: number of leading bins that can be non-zero (brightest present DN + 1) when the caller knows it, else -1
 void plan_from_dn_histogram32(const uint32_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out, int top_hint = -1);
+// The same from the device-compacted list of non-empty bins (k_hist_total): blk = 256 {offset, count} entries, one per
+// block of 256 DNs, into pairs = {dn, count} entries. false (nothing planned) when the list overflowed `cap`.
+constexpr uint32_t kPresentCap = 4096;
+constexpr size_t kPresentWords = 2 * (256 + (size_t)kPresentCap); // u32 words of the block table + the pairs
+bool plan_from_present_list(const uint32_t* blk, const uint32_t* pairs, uint32_t cap, int bit_depth, int strategy, PlanKind kind,
+                            BandPlan* out);
 
 // scale_u16_to_u8 (autoscale.rs:348-364) as a 65536-entry (or 256-entry) remap for given min/max.
 void make_u16_to_u8_remap(uint16_t mn, uint16_t mx, int n_entries, uint8_t* remap);

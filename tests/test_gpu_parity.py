@@ -268,3 +268,29 @@ def test_golden_wide_scene_on_the_device(ctx, strategy, name):
     for a, b in ((vv, vh), (vv.astype(np.float32), vh.astype(np.float32))):
         img = ctx.process_synrgb_jpeg(a, b, strategy, 256, True)
         assert np.array_equal(img.rgb, g[f"synrgb_{name}"]), int((img.rgb != g[f"synrgb_{name}"]).sum())
+
+
+@pytest.mark.parametrize("strategy", [S.STANDARD, S.ADAPTIVE, S.CLAHE])
+def test_present_list_planner_matches_dense_planner(strategy, monkeypatch):
+    """The planner reads the device-compacted list of present DNs (k_hist_total); SARPRO_DENSE_PLAN=1 makes it scan the dense
+    65,536-bin totals as before. Same statistics and samples, also for a raster with more distinct DNs than the list holds
+    (every u16 value: the library falls back to the dense totals by itself), both against the oracle."""
+    from sarpro_b200.synth import synth_band
+    rng = np.random.default_rng(5)
+    grd = synth_band(900, 1400, 3, block=16)
+    grd[5:9, 100:300] = 60000
+    wide = rng.integers(0, 65536, size=(700, 900), dtype=np.uint16)  # ~65k distinct DNs: list overflow
+    for dn in (grd, wide):
+        po = O.process_scalar_data_pipeline(dn.astype(np.float32), S.U8, strategy)
+        got = {}
+        for dense in ("", "1"):
+            monkeypatch.delenv("SARPRO_DENSE_PLAN", raising=False)
+            if dense:
+                monkeypatch.setenv("SARPRO_DENSE_PLAN", "1")
+            with S.Context(0) as c:
+                u8, _, st = c.process_scalar_data_pipeline(dn, S.U8, strategy)
+                got[dense] = (u8.copy(), st)
+        assert np.array_equal(got[""][0], got["1"][0])
+        assert np.array_equal(got[""][0], po.u8)
+        for k in ("valid_count", "min_db", "max_db", "mean_db", "std_db", "median_db", "p01", "p99", "low_clip", "high_clip", "gamma"):
+            assert getattr(got[""][1], k) == getattr(got["1"][1], k), k
