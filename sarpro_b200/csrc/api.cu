@@ -533,11 +533,13 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     g_plan_trace_on = trace;
     // the planner reads the device-compacted list of present DNs; the dense totals only when that list overflowed
     const uint32_t* hp = ctx->h_present + (size_t)b * kPresentWords;
+    bool dense = false;
     if (getenv("SARPRO_DENSE_PLAN") ||
         !plan_from_present_list(hp, hp + 512, kPresentCap, job.bit_depth, job.strategy, job.kind, &w.plan)) {
         CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         ctx->timing.host_syncs++;
+        dense = true;
         plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, job.bit_depth, job.strategy, job.kind, &w.plan,
                                  (int)std::min<uint32_t>(ctx->h_scalars[8 * b + 6] + 1u, kDnBins));
     }
@@ -548,7 +550,8 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     w.hot = w.plan.any_valid ? hpipe_hot_from_plan(w.plan, &w.hot_top) : 0;
     CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, n_lut * 2, cudaMemcpyHostToDevice, ctx->stream));
     w.hist_auto_pending = true; // pass-A table shape for the next call: chosen after this band's pass B is queued
-    if (trace) fprintf(stderr, "trace host: band %d histogram on the host at %.3f ms, planned at %.3f, table queued at %.3f ms; planner us: table cleared %.1f, scan %.1f, moments %.1f, percentiles %.1f, table %.1f\n", b, t_a, t_b, host_ms() - ctx->host_t0,
+    if (trace) fprintf(stderr, "trace host: band %d histogram on the host at %.3f ms, planned at %.3f, table queued at %.3f ms; planner (%s) us: table cleared %.1f, scan %.1f, moments %.1f, percentiles %.1f, table %.1f\n", b, t_a, t_b, host_ms() - ctx->host_t0,
+                       dense ? "dense totals" : "present list",
                        g_plan_trace_us[0], g_plan_trace_us[1], g_plan_trace_us[2], g_plan_trace_us[3], g_plan_trace_us[4]);
     return 0;
 }

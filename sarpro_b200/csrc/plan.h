@@ -58,7 +58,7 @@ void plan_from_dn_histogram(const uint64_t* hist, int bit_depth, int strategy, P
 void plan_from_dn_histogram32(const uint32_t* hist, int bit_depth, int strategy, PlanKind kind, BandPlan* out, int top_hint = -1);
 // The same from the device-compacted list of non-empty bins (k_hist_total): blk = 256 {offset, count} entries, one per
 // block of 256 DNs, into pairs = {dn, count} entries. false (nothing planned) when the list overflowed `cap`.
-constexpr uint32_t kPresentCap = 4096;
+constexpr uint32_t kPresentCap = 8192; // a 400 MP GRD scene with point targets has ~5,500 distinct DNs
 constexpr size_t kPresentWords = 2 * (256 + (size_t)kPresentCap); // u32 words of the block table + the pairs
 bool plan_from_present_list(const uint32_t* blk, const uint32_t* pairs, uint32_t cap, int bit_depth, int strategy, PlanKind kind,
                             BandPlan* out);
