@@ -319,10 +319,14 @@ def main():
         achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at the full C3 size, from the
         # ncu --set full capture summarised in profiles/ (same command line); None for other sizes
-        traffic = 872_600_000 if (rows, cols, args.strategy) == (ROWS, COLS, "clahe") else None
+        full_c3 = (rows, cols, args.strategy) == (ROWS, COLS, "clahe")
+        traffic = 871_000_000 if full_c3 else None  # profiles/r01q_ncu_full_hmma.md: 859.7 MB read + 11.3 MB written
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "k_hmma<CLAHE> (pass B: CLAHE apply fused with the horizontal Lanczos pass on IMMA.16832)",
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,
+                    # what the same ncu capture names as the busiest unit of this kernel (a note, not a second roofline)
+                    "limiter": ("L1TEX LSU data pipe (shared-memory table gathers): l1tex__data_pipe_lsu_wavefronts 74 % of peak on "
+                                "average, 84 % on the busiest SM; DRAM 19 % (profiles/r01q_ncu_full_hmma.md)") if full_c3 else None,
                     "stage_ms_per_step": {S._ffi.STAGE_NAMES[i]: round(stage_ms[i] / args.steps, 4) for i in range(8) if stage_n[i]}}
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,

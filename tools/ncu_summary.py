@@ -11,6 +11,10 @@ WANT = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
     "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__cycles_active.avg",
+    # the L1TEX data pipe (shared-memory and global wavefronts): the busiest unit of pass B
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.max.pct_of_peak_sustained_elapsed",
+    "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg", "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_shared.avg",
+    "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
