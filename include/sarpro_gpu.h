@@ -236,6 +236,13 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
  * For CLAHE the LUT holds the 256-bin index of autoscale.rs:263 (the blend needs pixel positions). */
 int sarpro_plan_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int strategy, sarpro_stats* stats,
                                   uint16_t* lut16);
+/* The same plan from the list of non-empty DN bins in the layout the device writes for the planner (k_hist_total): blocks =
+ * 256 {offset, count} pairs of u32, one per block of 256 consecutive DNs, into pairs = {dn, count} entries of u32; the DNs of a
+ * block are ascending, the blocks may sit in pairs[] in any order. Returns 1 and fills stats / lut16 like the call above, or 0
+ * (nothing written) when some block's offset + count exceeds cap, i.e. the list overflowed and the caller must use the dense
+ * histogram. */
+int sarpro_plan_from_present_list(const uint32_t* blocks, const uint32_t* pairs, uint32_t cap, int bit_depth, int strategy,
+                                  sarpro_stats* stats, uint16_t* lut16);
 
 /* Horizontal Lanczos3 pass of one row of u8 samples (resize.rs:39-50, first pass of the crate's separable resize) computed
  * twice on the host: directly from the fixed-point taps (out_direct) and by replaying the tensor-core kernel's plan — strips,

@@ -112,6 +112,7 @@ SYMBOLS = {
     "sarpro_shard_halo_rows": (_I, [_SZ, _SZ, _I, _SZ, _I, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "sarpro_pipeline_synrgb_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, _SZ, _I, _I, C.POINTER(Image)]),
     "sarpro_plan_from_dn_histogram": (_I, [_P, _I, _I, C.POINTER(Stats), _P]),
+    "sarpro_plan_from_present_list": (_I, [_P, _P, C.c_uint32, _I, _I, C.POINTER(Stats), _P]),
     "sarpro_lanczos_row_plan_check": (_I, [_P, _SZ, _SZ, _SZ, _P, _P]),
 }
 

@@ -385,6 +385,38 @@ def plan_from_dn_histogram(hist65536, bit_depth, strategy):
     return st, lut
 
 
+def present_list_from_histogram(hist65536, cap, order=None):
+    """Host emulation of the list k_hist_total writes for the planner: (blocks[256, 2], pairs[cap, 2]) of uint32. `order` is
+    the order in which the 256 blocks allocate their pairs (any permutation; the device's is arbitrary)."""
+    h = np.asarray(hist65536).astype(np.uint64).reshape(256, 256)
+    blocks = np.zeros((256, 2), np.uint32)
+    pairs = np.full((cap, 2), 0xDEADBEEF, np.uint32)
+    alloc = 0
+    for b in (range(256) if order is None else order):
+        (nz,) = np.nonzero(h[b])
+        blocks[b] = (alloc if nz.size else 0, nz.size)
+        keep = nz[: max(0, min(nz.size, cap - alloc))]  # pairs beyond cap are dropped
+        pairs[alloc:alloc + keep.size, 0] = b * 256 + keep
+        pairs[alloc:alloc + keep.size, 1] = h[b][keep]
+        alloc += nz.size
+    return blocks, pairs
+
+
+def plan_from_present_list(blocks, pairs, bit_depth, strategy):
+    """Host-only planner entry on the device-compacted list of present DNs. Returns (stats, lut) or None when the list
+    overflowed its capacity."""
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint32)
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint32)
+    assert blocks.shape == (256, 2) and pairs.ndim == 2 and pairs.shape[1] == 2
+    lut = np.zeros(65536, np.uint16)
+    st = F.Stats()
+    rc = F.lib().sarpro_plan_from_present_list(blocks.ctypes.data, pairs.ctypes.data, pairs.shape[0], bit_depth, strategy,
+                                               C.byref(st), lut.ctypes.data)
+    if rc < 0:
+        raise SarproError(rc, "sarpro_plan_from_present_list failed")
+    return (st, lut) if rc == 1 else None
+
+
 def shard_rows(rows, world, rank, clahe):
     r0, r1 = C.c_size_t(), C.c_size_t()
     rc = F.lib().sarpro_shard_rows(rows, world, rank, int(bool(clahe)), C.byref(r0), C.byref(r1))

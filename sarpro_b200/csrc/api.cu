@@ -1148,6 +1148,16 @@ int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t
     return 1;
 }
 
+int sarpro_plan_from_present_list(const uint32_t* blocks, const uint32_t* pairs, uint32_t cap, int bit_depth, int strategy,
+                                  sarpro_stats* stats, uint16_t* lut16) {
+    if (!blocks || !pairs) return SARPRO_ERR_INVALID_ARGUMENT;
+    BandPlan p;
+    if (!plan_from_present_list(blocks, pairs, cap, bit_depth, strategy, PlanKind::Autoscale, &p)) return 0;
+    if (stats) *stats = p.stats;
+    if (lut16) std::memcpy(lut16, p.lut.data(), kDnBins * 2);
+    return 1;
+}
+
 int sarpro_plan_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int strategy, sarpro_stats* stats,
                                   uint16_t* lut16) {
     if (!hist65536) return SARPRO_ERR_INVALID_ARGUMENT;

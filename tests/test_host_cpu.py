@@ -53,6 +53,31 @@ def test_product_does_not_touch_the_oracle():
 
 @pytest.mark.parametrize("case", sorted(CASES))
 @pytest.mark.parametrize("strategy", range(7))
+def test_present_list_planner_equals_dense_planner(lib_built, case, strategy):
+    """The production planner input is the device-compacted list of present DNs (k_hist_total: one {offset, count} entry per
+    block of 256 DNs into a {dn, count} pair list, blocks allocated in arbitrary order). Emulated on the host, with the blocks
+    shuffled, it must give the plan of the dense 65,536-bin histogram bit for bit (which the next test pins to the oracle);
+    a list that overflowed its capacity must be refused (the library then reads the dense totals)."""
+    dn = CASES[case](203, 317)
+    rng = np.random.default_rng(strategy)
+    dn.ravel()[rng.integers(0, dn.size, 40)] = rng.integers(1, 65536, 40)  # sparse bright DNs in the upper blocks
+    hist = np.bincount(dn.ravel(), minlength=65536).astype(np.uint64)
+    n_present = int((hist > 0).sum())
+    for bit_depth in (S.U8, S.U16):
+        st, lut = S.plan_from_dn_histogram(hist, bit_depth, strategy)
+        blocks, pairs = S.present_list_from_histogram(hist, 8192, order=rng.permutation(256))
+        got = S.plan_from_present_list(blocks, pairs, bit_depth, strategy)
+        assert got is not None
+        assert got[0].as_dict() == st.as_dict() or all(
+            (a == b) or (a != a and b != b) for a, b in zip(got[0].as_dict().values(), st.as_dict().values()))
+        assert np.array_equal(got[1], lut)
+    if n_present > 8:
+        blocks, pairs = S.present_list_from_histogram(hist, n_present - 1)
+        assert S.plan_from_present_list(blocks, pairs, S.U8, strategy) is None
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("strategy", range(7))
 @pytest.mark.parametrize("bit_depth", [S.U8, S.U16])
 def test_planner_matches_oracle(lib_built, case, strategy, bit_depth):
     dn = CASES[case](203, 317)
