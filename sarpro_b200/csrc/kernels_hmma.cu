@@ -37,6 +37,17 @@ namespace sarpro {
 
 namespace hm {
 constexpr uint32_t kThreadsLut = 512, kThreadsClahe = 384;      // CLAHE: fewer warps, 168 registers each for the gather pipeline
+// Experimental first-gather table of the CLAHE instantiation (build with SARPRO_NVCC_EXTRA=-DSARPRO_HMMA_PACKED_LUT; off by
+// default, NOT yet run on a GPU): 16-bit entries, two DNs per 32-bit word, 32 lane-private replicas in the bytes the
+// 16-replica table of 32-bit entries takes (hot << 6) -> every lane reads its own bank, one wavefront per gather instead of
+// ~2.4 with DN ranges above 500 (profiles/r01q_ncu_full_hmma.md: the co-pol launch has 14.7 M bank conflicts and takes 555 us,
+// the cross-pol launch, whose 32-replica table is conflict-free, 504 us). Entry of (DN idx, replica r): u16 at byte
+// ((idx >> 1) << 7) + 4 r + 2 (idx & 1), holding the byte offset of the bin's entry inside a quad cell.
+#ifdef SARPRO_HMMA_PACKED_LUT
+constexpr bool kPackedLut = true;
+#else
+constexpr bool kPackedLut = false;
+#endif
 constexpr uint32_t kQuadEntries = 257;                       // 256 bins + the invalid-pixel entry
 constexpr uint32_t kQuadCellBytes = kQuadEntries * 8 * 16;   // one cell, 8 replicas
 constexpr int kSlots = 3;                                    // n-tiles in flight per warp
@@ -184,7 +195,15 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     if (sbase + (hot << lut_shift) > 65536u) __trap(); // 16-bit table addresses (dynamic smem starts low on sm_100)
     uint32_t* const s_ctrl = reinterpret_cast<uint32_t*>(smem + L.ctrl);
 
-    {   // once per CTA: DN -> table word, R lane-interleaved replicas
+    if (CLAHE && hm::kPackedLut) { // once per CTA: DN -> 16-bit quad-cell offset, 32 lane-private replicas, two DNs per word
+        uint16_t* s_lut16 = reinterpret_cast<uint16_t*>(smem + L.lut);
+        for (uint32_t i = tid; i < hot * 32u; i += NT) {
+            const uint32_t idx = i >> 5, r = i & 31u;
+            const uint32_t e = idx + 1 == hot ? a.hot_top : (a.lut[idx] & 255u);
+            const uint32_t bin = idx ? e : 256u; // DN 0 is the only invalid DN (pipeline.rs:22)
+            s_lut16[((idx >> 1) * 32u + r) * 2u + (idx & 1u)] = (uint16_t)((bin * 8u + (r & 7u)) * 16u);
+        }
+    } else {   // once per CTA: DN -> table word, R lane-interleaved replicas
         uint4* s_lut4 = reinterpret_cast<uint4*>(smem + L.lut);
         const uint32_t per = 1u << (lut_shift - 4); // uint4 per table entry
         for (uint32_t i = tid; i < hot * per; i += NT) {
@@ -203,7 +222,9 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     }
     const uint32_t cap2 = hm_keep((hot - 1u) * 0x10001u);
     const uint32_t lut_mul = hm_keep(1u << lut_shift);
-    const uint32_t cj = hm_pin((sbase + L.lut + (lane & ((lut_mul >> 2) - 1u)) * 4u) * 0x10001u, lane);
+    const uint32_t cj = hm_pin((sbase + L.lut + (lane & ((CLAHE && hm::kPackedLut ? 128u : lut_mul) / 4u - 1u)) * 4u) * 0x10001u, lane);
+    // packed table: address of DN idx = idx * 64 + (idx & 1) * (2 - 64) + replica; both halves of a DN pair at once
+    const uint32_t odd_mul = CLAHE && hm::kPackedLut ? hm_pin(2u - 64u, lane) : 0u;
     const int prec = a.ax.precision;
     const int acc0 = (int)hm_keep(prec > 0 ? (1u << (prec - 1)) : 0u);
     const uint16_t* const src = reinterpret_cast<const uint16_t*>(a.src);
@@ -357,13 +378,16 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
         // exact u8 sample of pixel (r, c) (local row, column) with the reference's f64 operation order
         auto exact_px = [&](uint32_t r, uint32_t c) -> uint32_t {
             const uint32_t d = src[(size_t)r * cols + c];
-            const uint32_t word = reinterpret_cast<const uint32_t*>(smem + L.lut)[(size_t)min(d, hot - 1u) << (lut_shift - 2)];
+            const uint32_t di = min(d, hot - 1u);
+            const uint32_t word = CLAHE && hm::kPackedLut
+                                      ? reinterpret_cast<const uint16_t*>(smem + L.lut)[(size_t)(di >> 1) * 64u + (di & 1u)] // replica 0
+                                      : reinterpret_cast<const uint32_t*>(smem + L.lut)[(size_t)di << (lut_shift - 2)];
             if (!CLAHE) return word;
             uint32_t o = 0;
             if (d) {
                 const ClaheDev& cl = a.clahe;
                 const uint32_t tx = cl.col_t[c];
-                const uint32_t bin = (word - (sbase + L.quad)) >> 7;
+                const uint32_t bin = (hm::kPackedLut ? word : word - (sbase + L.quad)) >> 7;
                 const double* s_cdf = reinterpret_cast<const double*>(smem + L.cdf);
                 const uint32_t x0 = ((tx & 7u) - cellA) * 256u + bin, x1 = (((tx >> 8) & 7u) - cellA) * 256u + bin;
                 double v = clahe_blend_exact_rn(s_cdf[x0], s_cdf[x1], s_cdf[768 + x0], s_cdf[768 + x1], cl.col_dx[c], cl.col_omdx[c],
@@ -480,15 +504,20 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                             const uint32_t wv[4] = {d[v].x, d[v].y, d[v].z, d[v].w};
                             uint32_t a2[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) a2[j] = hm_mad(__vminu2(wv[j], cap2), lut_mul, cj);
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t vm = __vminu2(wv[j], cap2);
+                                a2[j] = hm_mad(vm, lut_mul, cj);
+                                if (hm::kPackedLut) a2[j] = hm_mad(vm & 0x00010001u, odd_mul, a2[j]);
+                            }
                             if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn)); // the DNs are consumed: prefetch in place
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                e[rw][2 * j] = hm_lds_u32(a2[j] & 0xffffu);
-                                e[rw][2 * j + 1] = hm_lds_u32(a2[j] >> 16);
+                                e[rw][2 * j] = hm::kPackedLut ? hm_lds_u16(a2[j] & 0xffffu) : hm_lds_u32(a2[j] & 0xffffu);
+                                e[rw][2 * j + 1] = hm::kPackedLut ? hm_lds_u16(a2[j] >> 16) : hm_lds_u32(a2[j] >> 16);
                             }
                         }
                         uint32_t celloff = tag == 1 ? hm::kQuadCellBytes : 0u; // warp-uniform
+                        if (hm::kPackedLut) celloff += sbase + L.quad;          // (the packed entries are offsets inside a cell)
                         if (tag == 2) { // the pixel's own cell: cell B columns sit one tile further (dx - 1)
                             const bool vb = c0 >= bcol; // dx[] was built for the vector's first column
 #pragma unroll
@@ -745,7 +774,10 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
 }
 
 // 32 lane-private replicas (conflict-free gathers) when the table still fits the 16-bit address range, else 16 or 8
-static uint32_t hmma_lut_shift(uint32_t hot) { return hot <= 500 ? 7u : hpipe_lut_shift(hot); }
+static uint32_t hmma_lut_shift(uint32_t hot, bool clahe) {
+    if (clahe && hm::kPackedLut) return 6u; // packed 16-bit entries: 32 replicas in hot << 6 bytes
+    return hot <= 500 ? 7u : hpipe_lut_shift(hot);
+}
 
 // Host replay of the kernel's walk for one row of u8 samples (test hook): strips, slot rotation, k-step windows, the
 // permuted tap bytes (hi * 256 + lo) and the final shift / clamp, in the order the device follows. out has out_size bytes.
@@ -802,7 +834,7 @@ bool hmma_replay_row(const HMmaPlanHost& plan, const uint8_t* samples, uint32_t 
 uint32_t hmma_warps(bool clahe) { return (clahe ? hm::kThreadsClahe : hm::kThreadsLut) / 32u; }
 
 size_t hmma_smem_bytes(int src_kind, uint32_t hot, uint32_t b_bytes) {
-    return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hmma_lut_shift(hot), b_bytes).total;
+    return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hmma_lut_shift(hot, src_kind == HSRC_DN_CLAHE), b_bytes).total;
 }
 
 cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,
@@ -819,7 +851,7 @@ cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_de
     pp.pieces = reinterpret_cast<const HPiece*>(pieces_dev);
     pp.cta_first = cta_first_dev;
     pp.hot = hot;
-    pp.lut_shift = hmma_lut_shift(hot);
+    pp.lut_shift = hmma_lut_shift(hot, clahe);
     pp.b_bytes = b_bytes;
     if (clahe) {
         static size_t configured = 0;
