@@ -1,5 +1,9 @@
 """Joins `ncu --page source --print-source sass` (per-instruction counts) with nvdisasm -g line info to give
-instructions executed / stall samples per CUDA source line.  usage: line_profile.py rep.ncu-rep obj.o mangled_fn [kernel_idx]"""
+instructions executed / stall samples per CUDA source line.  usage: line_profile.py rep.ncu-rep obj.o mangled_fn [kernel_idx]
+e.g. TOP=60 python tools/line_profile.py gpurun_out/r01q_full.ncu-rep sarpro_b200/build/kernels_hmma.cu.o \
+     _ZN6sarpro6k_hmmaILb1EEEvNS_11HResizeArgsENS_10HMmaParamsE 0
+kernel_idx counts the launches in the report (all kernels, in capture order); the object must be the build the report was
+captured from (the instruction counts are matched one to one)."""
 import csv, re, subprocess, sys, os, tempfile, collections
 rep, obj, fn = sys.argv[1:4]; kidx = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
