@@ -48,6 +48,15 @@ constexpr bool kPackedLut = true;
 #else
 constexpr bool kPackedLut = false;
 #endif
+// Experimental epilogue (-DSARPRO_HMMA_STG64; off by default, NOT yet run on a GPU): the four lanes of a quad hold 2 of the 8
+// output columns of a finished n-tile each for rows g and g + 8; instead of four byte stores per lane (32 L1 tag requests per
+// n-tile and warp, 8.2 M per launch for 1.0 M sectors) the quad's samples are gathered with three shuffles and lane q = 0
+// stores 8 bytes per row (16 tag requests). Needs the output width to be a multiple of 8 (rows of `temp` 8-byte aligned).
+#ifdef SARPRO_HMMA_STG64
+constexpr bool kStg64 = true;
+#else
+constexpr bool kStg64 = false;
+#endif
 constexpr uint32_t kQuadEntries = 257;                       // 256 bins + the invalid-pixel entry
 constexpr uint32_t kQuadCellBytes = kQuadEntries * 8 * 16;   // one cell, 8 replicas
 constexpr int kSlots = 3;                                    // n-tiles in flight per warp
@@ -233,6 +242,8 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     uint32_t mn_e = 0xffffffffu, mx_e = 0;  // exact-path samples
     uint32_t staged_strip = 0xffffffffu;
     const uint32_t sb_lane = hm_keep(sbase + L.bfrag + lane * 16u);
+    // 8-byte stores of the resized rows: whole n-tiles only and 8-byte aligned rows
+    const bool wide_store = hm::kStg64 && (a.ax.out_size & 7u) == 0 && (reinterpret_cast<uintptr_t>(a.temp) & 7u) == 0;
     const uint32_t cols8 = hm_pin(cols - 8u, lane);
     const uint32_t cm_base = hm_pin(sbase + L.cm + q * 2u, lane);
     const float inv2tw = __uint_as_float(hm_pin(__float_as_uint(CLAHE ? a.clahe.inv2tw : 0.f), lane));
@@ -671,12 +682,28 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                         for (int i = 0; i < 4; ++i) acc[s][i] += th[i] << 8;
                         if (ks0 + 1u >= slb[s]) { // the n-tile is complete: scale, clamp, store; the slot takes the next n-tile
                             const uint32_t ox = sj[s] * 8u + q * 2u;
+                            if (hm::kStg64 && wide_store) { // (warp-uniform: the shuffles below are executed by all lanes)
+                                uint32_t x = 0; // bytes: row g col ox, row g col ox+1, row g+8 col ox, row g+8 col ox+1
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    int vv = (acc0 + acc[s][i]) >> prec;
+                                    vv = vv < 0 ? 0 : (vv > 255 ? 255 : vv);
+                                    x |= (uint32_t)vv << (8 * i);
+                                    acc[s][i] = 0;
+                                }
+                                const uint32_t y1 = __shfl_down_sync(FULL, x, 1), y2 = __shfl_down_sync(FULL, x, 2), y3 = __shfl_down_sync(FULL, x, 3);
+                                if (q == 0) { // columns sj*8 .. sj*8+7 of both rows (out_size is a multiple of 8: the tile is whole)
+                                    if (okA_row) *reinterpret_cast<uint2*>(tA + ox) = make_uint2(__byte_perm(x, y1, 0x5410), __byte_perm(y2, y3, 0x5410));
+                                    if (okB_row) *reinterpret_cast<uint2*>(tB + ox) = make_uint2(__byte_perm(x, y1, 0x7632), __byte_perm(y2, y3, 0x7632));
+                                }
+                            } else {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 int vv = (acc0 + acc[s][i]) >> prec;
                                 vv = vv < 0 ? 0 : (vv > 255 ? 255 : vv);
                                 if (((i & 2) ? okB_row : okA_row) && ox + (i & 1) < a.ax.out_size) ((i & 2) ? tB : tA)[ox + (i & 1)] = (uint8_t)vv;
                                 acc[s][i] = 0;
+                            }
                             }
                             sj[s] += hm::kSlots;
                             sfb[s] = 0xffffffffu;
