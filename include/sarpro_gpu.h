@@ -244,6 +244,18 @@ int sarpro_plan_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int 
 int sarpro_plan_from_present_list(const uint32_t* blocks, const uint32_t* pairs, uint32_t cap, int bit_depth, int strategy,
                                   sarpro_stats* stats, uint16_t* lut16);
 
+/* Test hook: the DEVICE planner (kernels_plan.cu: the single-CTA restatement of the host planner for the strategies without
+ * pow(): Robust, Equalized, Clahe, Tamed, Default and the Tamed-synRGB windows) on a 65,536-bin DN histogram given as u32
+ * counts in host memory. plan_kind: 0 = autoscale, 1 / 2 = autoscale_db_image_tamed_synrgb_u8 co- / cross-pol. Fills stats and
+ * lut16 like sarpro_plan_from_dn_histogram, and hot2 = {table range, table word of the saturated DNs} of the tensor-core pass B.
+ * Returns SARPRO_ERR_INVALID_ARGUMENT for a strategy the device planner does not cover. */
+int sarpro_plan_on_device(sarpro_ctx* ctx, const uint32_t* hist65536, int bit_depth, int strategy, int plan_kind,
+                          sarpro_stats* stats, uint16_t* lut16, uint32_t* hot2);
+/* The host planner on the same inputs (what the device planner must reproduce bit for bit, mean / std within 1e-12):
+ * sarpro_plan_from_dn_histogram with the plan kind and the table range as extra outputs. No GPU needed. */
+int sarpro_plan_kind_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int strategy, int plan_kind,
+                                       sarpro_stats* stats, uint16_t* lut16, uint32_t* hot2);
+
 /* Horizontal Lanczos3 pass of one row of u8 samples (resize.rs:39-50, first pass of the crate's separable resize) computed
  * twice on the host: directly from the fixed-point taps (out_direct) and by replaying the tensor-core kernel's plan — strips,
  * n-tile slots, k-step windows and the permuted hi/lo tap bytes of its B fragments — in the device's order (out_replay).

@@ -9,7 +9,7 @@ from ._ffi import (ADAPTIVE, CLAHE, DEFAULT, EQUALIZED, JPEG, OP_DIFF, OP_LOGRAT
                    OP_SUM, ROBUST, STANDARD, STRATEGY_NAMES, TAMED, TIFF, U8, U16)
 import os as _os
 
-from .api import (Context, ProcessedImage, SarproError, comm_unique_id, plan_from_dn_histogram, plan_from_present_list, present_list_from_histogram,
+from .api import (Context, ProcessedImage, SarproError, comm_unique_id, plan_from_dn_histogram, plan_kind_from_dn_histogram, plan_from_present_list, present_list_from_histogram,
                   shard_halo_rows,
                   shard_rows)
 
@@ -32,7 +32,7 @@ def _locate_nccl():
 _locate_nccl()
 
 __all__ = [
-    "Context", "ProcessedImage", "SarproError", "plan_from_dn_histogram", "plan_from_present_list", "present_list_from_histogram", "shard_rows", "shard_halo_rows",
+    "Context", "ProcessedImage", "SarproError", "plan_from_dn_histogram", "plan_kind_from_dn_histogram", "plan_from_present_list", "present_list_from_histogram", "shard_rows", "shard_halo_rows",
     "comm_unique_id", "_ffi",
     "STANDARD", "ROBUST", "ADAPTIVE", "EQUALIZED", "CLAHE", "TAMED", "DEFAULT", "STRATEGY_NAMES",
     "U8", "U16", "TIFF", "JPEG", "OP_NONE", "OP_SUM", "OP_DIFF", "OP_RATIO", "OP_NDIFF", "OP_LOGRATIO",

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsarpro_gpu.so")
+# SARPRO_GPU_LIB: an experimental build of the same library (sarpro_b200.build --variant=...), for A/B measurements
+LIB_PATH = os.environ.get("SARPRO_GPU_LIB") or os.path.join(_HERE, "libsarpro_gpu.so")
 
 # enums (Rust declaration order, src/types.rs)
 STANDARD, ROBUST, ADAPTIVE, EQUALIZED, CLAHE, TAMED, DEFAULT = range(7)
@@ -113,6 +114,8 @@ SYMBOLS = {
     "sarpro_pipeline_synrgb_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, _SZ, _I, _I, C.POINTER(Image)]),
     "sarpro_plan_from_dn_histogram": (_I, [_P, _I, _I, C.POINTER(Stats), _P]),
     "sarpro_plan_from_present_list": (_I, [_P, _P, C.c_uint32, _I, _I, C.POINTER(Stats), _P]),
+    "sarpro_plan_on_device": (_I, [_P, _P, _I, _I, _I, C.POINTER(Stats), _P, _P]),
+    "sarpro_plan_kind_from_dn_histogram": (_I, [_P, _I, _I, _I, C.POINTER(Stats), _P, _P]),
     "sarpro_lanczos_row_plan_check": (_I, [_P, _SZ, _SZ, _SZ, _P, _P]),
 }
 

@@ -181,6 +181,17 @@ class Context:
         self._check(self._lib.sarpro_autoscale_tamed_synrgb_u8(self._h, _ptr(v), rows, cols, int(bool(is_copol)), _ptr(out)))
         return out
 
+    def plan_on_device(self, hist65536, bit_depth, strategy, plan_kind=0):
+        """Test hook: the device planner (kernels_plan.cu) on a DN histogram: (stats, lut, (hot, hot_top))."""
+        h = np.ascontiguousarray(hist65536, dtype=np.uint32)
+        assert h.size == 65536
+        lut = np.zeros(65536, np.uint16)
+        hot = np.zeros(2, np.uint32)
+        st = F.Stats()
+        self._check(self._lib.sarpro_plan_on_device(self._h, h.ctypes.data, bit_depth, strategy, plan_kind, C.byref(st),
+                                                    lut.ctypes.data, hot.ctypes.data))
+        return st, lut, (int(hot[0]), int(hot[1]))
+
     def scale_u16_to_u8(self, data):
         """autoscale.rs:348-364"""
         d = _host(data, np.uint16)
@@ -383,6 +394,20 @@ def plan_from_dn_histogram(hist65536, bit_depth, strategy):
     if rc != F.OK:
         raise SarproError(rc, "sarpro_plan_from_dn_histogram failed")
     return st, lut
+
+
+def plan_kind_from_dn_histogram(hist65536, bit_depth, strategy, plan_kind=0):
+    """Host planner with the plan kind (0 autoscale, 1 / 2 Tamed-synRGB co- / cross-pol): (stats, lut, (hot, hot_top))."""
+    h = np.ascontiguousarray(hist65536, dtype=np.uint64)
+    assert h.size == 65536
+    lut = np.zeros(65536, np.uint16)
+    hot = np.zeros(2, np.uint32)
+    st = F.Stats()
+    rc = F.lib().sarpro_plan_kind_from_dn_histogram(h.ctypes.data, bit_depth, strategy, plan_kind, C.byref(st), lut.ctypes.data,
+                                                    hot.ctypes.data)
+    if rc != F.OK:
+        raise SarproError(rc, "sarpro_plan_kind_from_dn_histogram failed")
+    return st, lut, (int(hot[0]), int(hot[1]))
 
 
 def present_list_from_histogram(hist65536, cap, order=None):

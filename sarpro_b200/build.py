@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsarpro_gpu.so")
-SOURCES = ["api.cu", "api_f32.cu", "comm.cu", "kernels_dn.cu", "kernels_resize.cu", "kernels_hfast.cu", "kernels_hpipe.cu", "kernels_hmma.cu", "kernels_small.cu", "kernels_f32.cu", "plan.cpp", "plan_f32.cpp"]
+SOURCES = ["api.cu", "api_f32.cu", "comm.cu", "kernels_dn.cu", "kernels_resize.cu", "kernels_hmma.cu", "kernels_plan.cu", "kernels_small.cu", "kernels_f32.cu", "plan.cpp", "plan_f32.cpp"]
 HEADERS = ["ctx.h", "kernels.h", "plan.h", "common.cuh", "clahe_exact.cuh", os.path.join("..", "..", "include", "sarpro_gpu.h")]
 
 NVCC_FLAGS = [
@@ -35,9 +35,13 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", extra: list[str] | None = None) -> str:
+    """variant/extra: an experimental build (extra nvcc flags) into libsarpro_gpu_<variant>.so, selected at run time with
+    SARPRO_GPU_LIB=<path>; the default library is never touched by it."""
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + variant if variant else ""))
+    LIB = os.path.join(HERE, f"libsarpro_gpu_{variant}.so") if variant else globals()["LIB"]
+    flags = NVCC_FLAGS + (extra or [])
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -46,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, src + ".o")
         objs.append(obj)
         if force or _stale(obj, [sp] + hdrs):
-            cmd = [nvcc(), *NVCC_FLAGS, "-x", "cu", "-c", sp, "-o", obj]
+            cmd = [nvcc(), *flags, "-x", "cu", "-c", sp, "-o", obj]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -67,4 +71,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    ext = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--extra=")]
+    print(build(force="--force" in sys.argv, verbose=True, variant=var[0] if var else "", extra=ext))

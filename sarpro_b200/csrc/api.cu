@@ -202,21 +202,20 @@ int upload_vec(sarpro_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
     return 0;
 }
 
+// Drops every cached axis plan. Only called between calls (begin_call): inside a call the pipeline holds raw AxisPlan
+// pointers (the horizontal plan while it looks up the vertical one), so nothing may be evicted there.
+static void drop_axis_plans(sarpro_ctx* ctx) {
+    for (auto& kv : ctx->axes) delete kv.second; // ~AxisPlan releases the device tables
+    ctx->axes.clear();
+    for (auto& w : ctx->band) { w.pc_axis_id = 0; w.pc_n_ctas = 0; }
+}
+
 int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res) {
     const AxisKey key{in, out, wide ? 1 : 0, horiz ? 1 : 0, horiz ? src_kind : 0};
     auto it = ctx->axes.find(key);
     if (it != ctx->axes.end()) { *res = it->second; return 0; }
-    if (ctx->axes.size() > 64) { // bounded cache
-        for (auto& kv : ctx->axes) {
-            release(kv.second->start); release(kv.second->size); release(kv.second->coef);
-            release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips); release(kv.second->sstrips);
-        release(kv.second->m_btab); release(kv.second->m_ntile); release(kv.second->m_strips);
-            release(kv.second->m_btab); release(kv.second->m_ntile); release(kv.second->m_strips);
-            delete kv.second;
-        }
-        ctx->axes.clear();
-    }
     AxisPlan* ap = new AxisPlan();
+    ap->id = ctx->next_axis_id++;
     build_lanczos3_axis(in, out, wide, &ap->h);
     const ResampleAxis& h = ap->h;
     std::vector<uint32_t> packed;
@@ -232,12 +231,13 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
             }
         }
     }
+    HMmaPlanHost mp; // (outlives the uploads below: the stream is synchronised before it goes out of scope)
+    std::vector<HStrip> strips;
     int rc = upload_vec(ctx, ap->start, h.start.data(), h.start.size() * 4);
     if (!rc) rc = upload_vec(ctx, ap->size, h.size.data(), h.size.size() * 4);
     if (!rc) rc = upload_vec(ctx, ap->coef, h.coef.data(), h.coef.size() * 4);
     if (!rc) rc = upload_vec(ctx, ap->packed, packed.data(), packed.size() * 4);
     if (!rc && horiz) {
-        std::vector<HStrip> strips;
         cudaError_t e = hresize_build_strips(h.start.data(), h.size.data(), out, in, h.window, ap->pairs, wide ? 1 : 0,
                                              src_kind, &ap->oxb, &strips, &ap->rbw, &ap->smem);
         if (e != cudaSuccess) rc = fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "resize %u -> %u needs more shared memory than an SM has", in, out);
@@ -246,34 +246,8 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
             rc = upload_vec(ctx, ap->strips, strips.data(), strips.size() * sizeof(HStrip));
             ap->has_strips = true;
         }
-        if (!rc && !wide && hfast_supported(ap->pairs) &&
-            hfast_build_strips(h.start.data(), h.size.data(), out, in, h.window, &ap->f_oxb, &ap->f_strips_h,
-                               &ap->f_rbw_words) == cudaSuccess) {
-            ap->f_n_strips = (uint32_t)ap->f_strips_h.size();
-            rc = upload_vec(ctx, ap->fstrips, ap->f_strips_h.data(), ap->f_strips_h.size() * sizeof(HStrip));
-            ap->fast = rc == 0;
-        }
-        if (!rc && !wide && src_kind != HSRC_IMAGE && hpipe_supported(ap->pairs)) {
-            const uint32_t tile_w = (in + kClaheTiles - 1) / kClaheTiles;
-            const uint32_t max_vec = src_kind == HSRC_DN_CLAHE ? std::min(256u, tile_w / 8) : 256u;
-            std::vector<HStrip>& ps = ap->p_strips_h;
-            if (hpipe_build_strips(h.start.data(), h.size.data(), out, in, h.window, max_vec, 256, &ap->p_oxb, &ps, &ap->p_rbw_words) ==
-                cudaSuccess) {
-                ap->p_n_strips = (uint32_t)ps.size();
-                rc = upload_vec(ctx, ap->pstrips, ps.data(), ps.size() * sizeof(HStrip));
-                ap->pipe = rc == 0;
-            }
-            std::vector<HStrip>& ss = ap->s_strips_h;
-            if (!rc && hpipe_build_strips(h.start.data(), h.size.data(), out, in, h.window, max_vec, 128, &ap->s_oxb, &ss,
-                                          &ap->s_rbw_words) == cudaSuccess) {
-                ap->s_n_strips = (uint32_t)ss.size();
-                rc = upload_vec(ctx, ap->sstrips, ss.data(), ss.size() * sizeof(HStrip));
-                ap->spec = rc == 0;
-            }
-        }
         if (!rc && !wide && src_kind != HSRC_IMAGE) {
             const uint32_t tile_w = (in + kClaheTiles - 1) / kClaheTiles;
-            HMmaPlanHost mp;
             if (hmma_build_plan(h.start.data(), h.size.data(), h.coef.data(), h.window, out, in,
                                 src_kind == HSRC_DN_CLAHE ? tile_w : 0u, &mp)) {
                 rc = upload_vec(ctx, ap->m_btab, mp.btab.data(), mp.btab.size() * sizeof(uint4));
@@ -282,15 +256,11 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
                 ap->m_weights_h = mp.weights;
                 ap->m_b_bytes = mp.b_bytes;
                 ap->mma = rc == 0;
-                if (!rc) { // the plan vectors are temporaries
-                    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-                    if (e != cudaSuccess) rc = fail(ctx, SARPRO_ERR_CUDA, "CUDA error %s", cudaGetErrorName(e));
-                }
             }
         }
     }
     if (!rc) {
-        cudaError_t e = cudaStreamSynchronize(ctx->stream); // host vectors are temporaries
+        cudaError_t e = cudaStreamSynchronize(ctx->stream); // the host vectors are temporaries
         if (e != cudaSuccess) rc = fail(ctx, SARPRO_ERR_CUDA, "CUDA error %s", cudaGetErrorName(e));
     }
     if (rc) { delete ap; return rc; }
@@ -300,46 +270,11 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
 }
 
 // ---- horizontal pass dispatch -----------------------------------------------------------------------
-// Row blocks of the production kernel: <= rpb source rows each, never straddling a vertical CLAHE cell
-// boundary (rows where floor(r/tile_h - 0.5) changes, autoscale.rs:308-310).
-int prepare_rowblocks(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe, uint32_t n_strips) {
-    const uint64_t th = clahe ? ctx->clahe_tile_h : 0;
-    if (ctx->rb_rows == rows && ctx->rb_row_off == row_off && ctx->rb_clahe == (int)clahe && ctx->rb_tile_h == th &&
-        ctx->n_rowblocks)
-        return 0;
-    const uint64_t want_blocks = std::max<uint64_t>(1, (uint64_t)ctx->sm_count * 8 / std::max(1u, n_strips));
-    uint64_t rpb = (rows + want_blocks - 1) / want_blocks;
-    rpb = std::max<uint64_t>(16, ((rpb + 3) / 4) * 4);
-    std::vector<uint64_t> cuts;
-    cuts.push_back(0);
-    if (clahe && th)
-        for (uint64_t k = 0; k < kClaheTiles; ++k) {
-            const uint64_t g = (th * (2 * k + 1) + 1) / 2; // first global row with 2r >= th*(2k+1)
-            if (g > row_off && g < row_off + rows) cuts.push_back(g - row_off);
-        }
-    cuts.push_back(rows);
-    std::vector<uint2> blocks;
-    for (size_t i = 0; i + 1 < cuts.size(); ++i)
-        for (uint64_t r = cuts[i]; r < cuts[i + 1]; r += rpb)
-            blocks.push_back(make_uint2((uint32_t)r, (uint32_t)std::min(cuts[i + 1], r + rpb)));
-    RC(reserve(ctx, ctx->rowblocks, std::max<size_t>(blocks.size() * sizeof(uint2), 16)));
-    if (!blocks.empty()) {
-        CU(cudaMemcpyAsync(ctx->rowblocks.p, blocks.data(), blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    ctx->n_rowblocks = (uint32_t)blocks.size();
-    ctx->rb_rows = rows;
-    ctx->rb_row_off = row_off;
-    ctx->rb_clahe = clahe;
-    ctx->rb_tile_h = th;
-    return 0;
-}
-
-// Table range for kernels_hpipe.cu: the smallest hot such that every PRESENT DN >= hot-1 has the table word `top`
+// Table range for kernels_hmma.cu: the smallest hot such that every PRESENT DN >= hot-1 has the table word `top`
 // (the tables are monotone and saturate above the window; the planner leaves absent DNs at 0, so presence comes
 // from the histogram; hist == nullptr: every DN <= max_present_dn counts as present). 0 when that needs more
 // than 2000 table entries.
-uint32_t hpipe_hot(const uint16_t* lut, const uint32_t* hist, uint32_t max_present_dn, uint32_t* top_out) {
+uint32_t hmma_hot(const uint16_t* lut, const uint32_t* hist, uint32_t max_present_dn, uint32_t* top_out) {
     const uint32_t top = lut[max_present_dn] & 255u;
     uint32_t h = max_present_dn;
     for (uint32_t d = max_present_dn;; --d) {
@@ -354,18 +289,19 @@ uint32_t hpipe_hot(const uint16_t* lut, const uint32_t* hist, uint32_t max_prese
 }
 
 // The same from a plan (the planner walked the present DNs already: no second scan of the histogram on the critical path).
-uint32_t hpipe_hot_from_plan(const BandPlan& plan, uint32_t* top_out) {
+uint32_t hmma_hot_from_plan(const BandPlan& plan, uint32_t* top_out) {
     *top_out = plan.lut[plan.max_present_dn] & 255u;
     const uint32_t need = std::max(64u, (plan.sat_from_dn + 1 + 7) & ~7u);
     return need <= 2000 ? need : 0;
 }
 
-// Piece lists of kernels_hpipe.cu: equal-weight runs of (strip, rows) per persistent CTA; pieces never straddle a
-// vertical CLAHE cell boundary (rows where floor(r/tile_h - 0.5) changes, autoscale.rs:308-310).
-int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe, AxisPlan* ah, int nsub) {
+// Piece lists of kernels_hmma.cu for band slot `slot`: equal-weight runs of (strip, rows) per persistent CTA; pieces never
+// straddle a vertical CLAHE cell boundary (rows where floor(r/tile_h - 0.5) changes, autoscale.rs:308-310).
+int prepare_pieces(sarpro_ctx* ctx, int slot, uint64_t rows, uint64_t row_off, bool clahe, AxisPlan* ah) {
+    BandWs& w = ctx->band[slot];
     const uint64_t th = clahe ? ctx->clahe_tile_h : 0;
-    if (ctx->pc_rows == rows && ctx->pc_row_off == row_off && ctx->pc_clahe == (int)clahe && ctx->pc_tile_h == th &&
-        ctx->pc_axis == ah && ctx->pc_nsub == nsub && ctx->pc_n_ctas)
+    if (w.pc_rows == rows && w.pc_row_off == row_off && w.pc_clahe == (int)clahe && w.pc_tile_h == th && w.pc_axis_id == ah->id &&
+        w.pc_n_ctas)
         return 0;
     std::vector<uint64_t> cuts;
     cuts.push_back(0);
@@ -375,78 +311,56 @@ int prepare_pieces(sarpro_ctx* ctx, uint64_t rows, uint64_t row_off, bool clahe,
             if (g > row_off && g < row_off + rows) cuts.push_back(g - row_off);
         }
     cuts.push_back(rows);
+    // Whole rounds of 16-row groups, one group per warp (12 warps for CLAHE, 16 otherwise), so that only the last piece of a
+    // vertical cell ends with a partly filled round. Short rasters (a rank's band of a sharded scene) do not have a round per
+    // CTA: the unit shrinks to the groups a CTA gets, so that every SM still takes a share.
+    const uint32_t warps = hmma_warps(clahe);
+    const uint64_t groups = (rows + 15) / 16 * std::max<size_t>(1, ah->m_weights_h.size());
+    const uint32_t per_cta = (uint32_t)std::max<uint64_t>(1, groups / std::max(1, ctx->sm_count));
+    const uint32_t unit = 16u * std::min(warps, per_cta);
     std::vector<uint32_t> pieces, first;
     uint32_t max_rows = 0;
-    if (nsub == 100) // tensor-core kernel: whole rounds of 16-row groups (one group per warp: 12 warps for CLAHE, 16 otherwise), so
-                     // that only the last piece of a vertical cell ends with a partly filled round
-        hpipe_build_pieces(ah->m_weights_h, cuts, (uint32_t)ctx->sm_count, 16u * hmma_warps(clahe), &pieces, &first, &max_rows);
-    else
-        hpipe_build_pieces(nsub == 12 ? ah->s_strips_h : ah->p_strips_h, cuts, (uint32_t)ctx->sm_count, nsub == 12 ? 8u : 4u * (uint32_t)nsub,
-                           &pieces, &first, &max_rows);
-    RC(reserve(ctx, ctx->pieces, std::max<size_t>(pieces.size() * 4, 16)));
-    RC(reserve(ctx, ctx->cta_first, std::max<size_t>(first.size() * 4, 16)));
-    CU(cudaMemcpyAsync(ctx->pieces.p, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->cta_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    hmma_build_pieces(ah->m_weights_h, cuts, (uint32_t)ctx->sm_count, unit, &pieces, &first, &max_rows);
+    RC(reserve(ctx, w.pieces, std::max<size_t>(pieces.size() * 4, 16)));
+    RC(reserve(ctx, w.cta_first, std::max<size_t>(first.size() * 4, 16)));
+    CU(cudaMemcpyAsync(w.pieces.p, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(w.cta_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->pc_n_ctas = (uint32_t)first.size() - 1;
-    ctx->pc_max_rows = max_rows;
-    ctx->pc_rows = rows;
-    ctx->pc_row_off = row_off;
-    ctx->pc_clahe = clahe;
-    ctx->pc_tile_h = th;
-    ctx->pc_axis = ah;
-    ctx->pc_nsub = nsub;
+    w.pc_n_ctas = (uint32_t)first.size() - 1;
+    w.pc_unit = unit;
+    w.pc_rows = rows;
+    w.pc_row_off = row_off;
+    w.pc_clahe = clahe;
+    w.pc_tile_h = th;
+    w.pc_axis_id = ah->id;
     return 0;
 }
 
-int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
+// Horizontal pass: the tensor-core kernel (u8 samples from a DN raster, source width a multiple of 8, 16-byte aligned, tables
+// that fit shared memory) or the generic exact kernel (everything else: u8 / u16 images, u16 samples, odd widths, small scale
+// factors, the device-gated re-run with the scale_u16_to_u8 remap).
+int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
     if (getenv("SARPRO_TRACE"))
-        fprintf(stderr, "run_hpass: kind %d pix16 %d mma %d hot %u hot_top %u remap %p skip %p src%%16 %d smem %zu rows %u cols %u\n", src_kind, pix16,
-                (int)ah->mma, a.hot, a.hot_top, (const void*)a.remap, (const void*)a.skip, (int)(reinterpret_cast<uintptr_t>(a.src) % 16),
-                ah->mma ? hmma_smem_bytes(src_kind, a.hot ? a.hot : 1, ah->m_b_bytes) : 0, a.n_rows, a.src_cols);
-    if (!pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap &&
+        fprintf(stderr, "run_hpass: kind %d pix16 %d mma %d plan %p remap %p skip %p src%%16 %d smem %zu rows %u cols %u\n", src_kind, pix16,
+                (int)ah->mma, (const void*)a.plan, (const void*)a.remap, (const void*)a.skip, (int)(reinterpret_cast<uintptr_t>(a.src) % 16),
+                ah->mma ? hmma_smem_bytes(src_kind, ah->m_b_bytes) : 0, a.n_rows, a.src_cols);
+    HResizeArgs ag = a; // the generic kernel's arguments
+    if (!pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.plan && !a.remap &&
         (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && (uint64_t)a.src_rows * a.src_cols < (1ull << 32) &&
-        hmma_smem_bytes(src_kind, a.hot, ah->m_b_bytes) <= 227 * 1024) {
-        RC(prepare_pieces(ctx, a.n_rows, row_off, src_kind == HSRC_DN_CLAHE, ah, 100));
+        hmma_smem_bytes(src_kind, ah->m_b_bytes) <= 227 * 1024) {
+        RC(prepare_pieces(ctx, slot, a.n_rows, row_off, src_kind == HSRC_DN_CLAHE, ah));
+        BandWs& w = ctx->band[slot];
         KS(SARPRO_STAGE_APPLY, launch_hmma(a, src_kind, (const uint4*)ah->m_btab.p, (const int4*)ah->m_ntile.p, (const uint4*)ah->m_strips.p,
-                                           (const uint32_t*)ctx->pieces.p, (const uint32_t*)ctx->cta_first.p, ctx->pc_n_ctas, a.hot,
+                                           (const uint32_t*)w.pieces.p, (const uint32_t*)w.cta_first.p, w.pc_n_ctas,
                                            ah->m_b_bytes, ctx->stream));
-        return 0;
+        // Whether the band's table fits the tensor-core kernel (plan->hot != 0) is only known on the device when the band was
+        // planned there: the generic kernel is queued behind it and returns at once unless plan->use_generic is set.
+        if (!w.dev_planned && w.hot) return 0; // host-planned and eligible: nothing else to launch
+        if (!w.dev_planned && !w.hot) { /* host-planned, not eligible: k_hmma returned at once; run the generic kernel unconditionally */ }
+        else ag.run_if = &a.plan->use_generic;
     }
-    if (!pix16 && ah->pipe && ctx->use_hpipe && !ctx->force_exact && src_kind != HSRC_IMAGE && a.hot && !a.remap) {
-        const bool clahe = src_kind == HSRC_DN_CLAHE;
-        // worst-case piece = a whole vertical cell (or the whole raster); 3 sub-blocks when the tables still fit
-        const uint32_t worst_rows = (uint32_t)std::min<uint64_t>(a.n_rows, clahe && ctx->clahe_tile_h ? ctx->clahe_tile_h : a.n_rows);
-        // 12 = warp-specialised kernel (faster for the LUT strategies, where the taps weigh as much as the per-pixel stage);
-        // 2 / 3 = symmetric sub-blocks (faster for CLAHE)
-        int nsub = ctx->hpipe_nsub ? ctx->hpipe_nsub : (clahe ? 2 : 12);
-        if (nsub == 12 && !ah->spec) nsub = 2;
-        const uint32_t rbw = nsub == 12 ? ah->s_rbw_words : ah->p_rbw_words;
-        if (nsub == 3 && hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, rbw) > 227 * 1024) nsub = 2;
-        if (hpipe_smem_bytes(src_kind, nsub, a.hot, worst_rows, rbw) <= 227 * 1024) {
-            RC(prepare_pieces(ctx, a.n_rows, row_off, clahe, ah, nsub));
-            HResizeArgs af = a;
-            af.rbw_words = rbw;
-            const bool sp = nsub == 12;
-            KS(SARPRO_STAGE_APPLY, launch_hpipe(af, src_kind, nsub, (const HStrip*)(sp ? ah->sstrips.p : ah->pstrips.p),
-                                                (const uint32_t*)ctx->pieces.p, (const uint32_t*)ctx->cta_first.p, ctx->pc_n_ctas,
-                                                sp ? ah->s_oxb : ah->p_oxb, a.hot, ctx->pc_max_rows, ctx->stream));
-            return 0;
-        }
-    }
-    if (!pix16 && ah->fast && !ctx->force_exact) {
-        const bool clahe = src_kind == HSRC_DN_CLAHE;
-        RC(prepare_rowblocks(ctx, a.n_rows, row_off, clahe, ah->f_n_strips));
-        HResizeArgs af = a;
-        af.rbw_words = ah->f_rbw_words;
-        // the device-gated re-run (a.skip) is accounted under OTHER: it normally returns at once
-        KS(a.skip ? SARPRO_STAGE_OTHER : SARPRO_STAGE_APPLY,
-           launch_hfast(af, src_kind, (const HStrip*)ah->fstrips.p, ah->f_n_strips, (const uint2*)ctx->rowblocks.p, ctx->n_rowblocks,
-                        ah->f_oxb, ctx->stream));
-        return 0;
-    }
-    KS(a.skip ? SARPRO_STAGE_OTHER : SARPRO_STAGE_APPLY,
-       launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem, ctx->sm_count,
+    KS(a.skip || ag.run_if ? SARPRO_STAGE_OTHER : SARPRO_STAGE_APPLY,
+       launch_hresize_planned(ag, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem, ctx->sm_count,
                               ctx->stream));
     return 0;
 }
@@ -525,7 +439,31 @@ int choose_hist_variant(const BandPlan& plan) {
     return ge1k <= lim ? 22 : (ge2k <= lim ? 21 : 20);
 }
 
-// Host planning of band b from its histogram in pinned memory; ships the DN -> sample / bin table.
+// The plan of band slot b as the host planner left it (w.plan), shipped to the device for the kernels downstream.
+int upload_plan_dev(sarpro_ctx* ctx, int b) {
+    BandWs& w = ctx->band[b];
+    RC(reserve(ctx, w.plan_dev, sizeof(PlanDev)));
+    PlanDev& p = ctx->h_plan_up[b];
+    std::memset(&p, 0, sizeof(p));
+    p.any_valid = w.plan.any_valid;
+    p.have_invalid = w.plan.have_invalid;
+    p.max_present_dn = w.plan.max_present_dn;
+    p.sat_from_dn = w.plan.sat_from_dn;
+    p.hot = w.hot;
+    p.hot_top = w.hot_top;
+    p.use_generic = w.hot == 0;
+    p.clahe = w.plan.clahe;
+    p.pre_min = w.plan.pre_min;
+    p.pre_max = w.plan.pre_max;
+    p.px_total = w.plan.px_total;
+    p.px_ge1024 = w.plan.px_ge1024;
+    p.px_ge2048 = w.plan.px_ge2048;
+    p.stats = w.plan.stats;
+    CU(cudaMemcpyAsync(w.plan_dev.p, &p, sizeof(PlanDev), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// Host planning of band b from its histogram in pinned memory; ships the DN -> sample / bin table and the plan.
 int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     BandWs& w = ctx->band[b];
     const bool trace = getenv("SARPRO_TRACE") != nullptr;
@@ -547,8 +485,10 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     // only DNs up to the brightest present one are ever looked up (stale entries beyond it are never read)
     const size_t n_lut = getenv("SARPRO_FULL_LUT") ? (size_t)kDnBins : std::min<size_t>(kDnBins, ((size_t)w.plan.max_present_dn + 1 + 63) & ~size_t(63));
     std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), n_lut * 2);
-    w.hot = w.plan.any_valid ? hpipe_hot_from_plan(w.plan, &w.hot_top) : 0;
+    w.hot = w.plan.any_valid ? hmma_hot_from_plan(w.plan, &w.hot_top) : 0;
     CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, n_lut * 2, cudaMemcpyHostToDevice, ctx->stream));
+    RC(upload_plan_dev(ctx, b));
+    w.dev_planned = false;
     w.hist_auto_pending = true; // pass-A table shape for the next call: chosen after this band's pass B is queued
     if (trace) fprintf(stderr, "trace host: band %d histogram on the host at %.3f ms, planned at %.3f, table queued at %.3f ms; planner (%s) us: table cleared %.1f, scan %.1f, moments %.1f, percentiles %.1f, table %.1f\n", b, t_a, t_b, host_ms() - ctx->host_t0,
                        dense ? "dense totals" : "present list",
@@ -556,8 +496,34 @@ int plan_band_and_upload(sarpro_ctx* ctx, int b, const BandJob& job) {
     return 0;
 }
 
-// Pass A launches + histogram read-back for `nb` bands of identical geometry; ctx->ev[2 + b] marks band b's histogram
-// as being on the host.
+// Strategies planned on the device (kernels_plan.cu): no host round trip between pass A and pass B. SARPRO_HOST_PLAN=1 keeps
+// every band on the host planner (validation: the tests compare the two).
+bool plans_on_device(const sarpro_ctx* ctx, const BandJob& job) {
+    return !ctx->host_plan && plan_on_device_supported(job.strategy, (int)job.kind);
+}
+
+// Queues the device planner for band b behind its k_hist_total on ctx->stream, and the copy of the plan to pinned host
+// memory (read in end_call: statistics for the caller, the pass-A table shape of the next call).
+int plan_band_on_device(sarpro_ctx* ctx, int b, const BandJob& job) {
+    BandWs& w = ctx->band[b];
+    RC(reserve(ctx, w.plan_dev, sizeof(PlanDev)));
+    PlanParams pr;
+    pr.strategy = job.strategy;
+    pr.kind = (int)job.kind;
+    pr.bit_depth = job.bit_depth;
+    pr.clahe = uses_clahe(job);
+    KS(SARPRO_STAGE_PLAN, launch_plan_band((const uint32_t*)w.total.p, (const double*)ctx->db_table.p, pr, (uint16_t*)w.lut.p,
+                                           (PlanDev*)w.plan_dev.p, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->h_plan[b], w.plan_dev.p, sizeof(PlanDev), cudaMemcpyDeviceToHost, ctx->stream));
+    w.dev_planned = true;
+    w.plan_copy_pending = true;
+    w.plan.clahe = uses_clahe(job);
+    w.hist_auto_pending = true;
+    return 0;
+}
+
+// Pass A launches (+ the histogram read-back of the bands the HOST will plan) for `nb` bands of identical geometry;
+// ctx->ev[2 + b] marks band b's histogram as complete (device-planned bands) / on the host (host-planned bands).
 int run_pass_a(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
     bool any_clahe = false;
     for (int b = 0; b < nb; ++b) any_clahe |= uses_clahe(jobs[b]);
@@ -565,6 +531,10 @@ int run_pass_a(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
     for (int b = 0; b < nb; ++b) RC(dn_pass_a_launch(ctx, b, jobs[b].dn, jobs[b].rows, jobs[b].cols, any_clahe, 1));
     for (int b = 0; b < nb; ++b) {
         RC(dn_pass_a_launch(ctx, b, jobs[b].dn, jobs[b].rows, jobs[b].cols, any_clahe, 2));
+        if (plans_on_device(ctx, jobs[b])) {
+            CU(cudaEventRecord(ctx->ev[2 + b], ctx->stream));
+            continue;
+        }
         // The read-back of all but the last band goes through the side stream: on the main stream the two copies would
         // hold the next band's histogram kernel back.
         cudaStream_t rs = ctx->stream;
@@ -581,17 +551,19 @@ int run_pass_a(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
     return 0;
 }
 
-// Waits for band b's histogram, plans it on the host (the device keeps working on whatever is queued behind it:
-// the other band's pass A, or the previous band's pass B) and queues the table upload.
-int wait_and_plan(sarpro_ctx* ctx, int b, const BandJob& job) {
-    CU(cudaEventSynchronize(ctx->ev[2 + b]));
-    ctx->timing.host_syncs++;
-    return plan_band_and_upload(ctx, b, job);
-}
-
-// wait_and_plan; when `side` is given, everything from the table upload on is issued on that stream (ctx->stream is
-// switched; the caller switches it back).
-int wait_and_plan_on(sarpro_ctx* ctx, int b, const BandJob& job, cudaStream_t side) {
+// Plans band b once its histogram is complete. Device-planned strategies: the planner kernel is queued behind the histogram
+// (a stream dependency, the host does not wait). Host-planned strategies (Standard, Adaptive): waits for the read-back and
+// plans on the host while the device keeps working on whatever is queued behind it (the other band's pass A, or the
+// previous band's pass B), then queues the table upload. When `side` is given, everything from here on is issued on that
+// stream (ctx->stream is switched; the caller switches it back).
+int plan_band_on(sarpro_ctx* ctx, int b, const BandJob& job, cudaStream_t side) {
+    if (plans_on_device(ctx, job)) {
+        if (side) {
+            CU(cudaStreamWaitEvent(side, ctx->ev[2 + b], 0));
+            ctx->stream = side;
+        }
+        return plan_band_on_device(ctx, b, job);
+    }
     CU(cudaEventSynchronize(ctx->ev[2 + b]));
     ctx->timing.host_syncs++;
     if (side) ctx->stream = side;
@@ -601,7 +573,7 @@ int wait_and_plan_on(sarpro_ctx* ctx, int b, const BandJob& job, cudaStream_t si
 // Pass A for `nb` bands, then the planner for all of them (callers that need every plan before pass B).
 int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
     RC(run_pass_a(ctx, jobs, nb));
-    for (int b = 0; b < nb; ++b) RC(wait_and_plan(ctx, b, jobs[b]));
+    for (int b = 0; b < nb; ++b) RC(plan_band_on(ctx, b, jobs[b], nullptr));
     return 0;
 }
 
@@ -612,7 +584,7 @@ int run_clahe_stats(sarpro_ctx* ctx, int b) {
     RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
     RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
     CU(cudaMemsetAsync(w.tile256.p, 0, (size_t)ctx->n_tiles * 256 * 4, ctx->stream));
-    KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles, w.plan.max_present_dn,
+    KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles, (const PlanDev*)w.plan_dev.p,
                             (uint32_t*)w.tile256.p, ctx->stream));
     KS(SARPRO_STAGE_PLAN, launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles, (double*)w.cdf.p,
                         (float*)w.cdf32.p, ctx->stream));
@@ -645,12 +617,17 @@ int reset_minmax(sarpro_ctx* ctx, int b) {
     return 0;
 }
 
+// A band the HOST planned and found without a valid pixel (a device-planned band is not known here; its all-zero table
+// gives the same all-zero output).
+static inline bool known_all_invalid(const BandWs& w) { return !w.dev_planned && !w.plan.any_valid; }
+
 // Pass B, full resolution: dst is a device buffer of rows*cols samples of the job's bit depth.
 int run_pass_b_full(sarpro_ctx* ctx, int b, const BandJob& j, void* dst) {
     BandWs& w = ctx->band[b];
     const uint64_t n = j.rows * j.cols;
     const bool out8 = j.kind != PlanKind::Autoscale || j.bit_depth == SARPRO_U8;
-    if (!w.plan.any_valid) { // all-zero output (autoscale.rs:376-378, 466-468, 716-718)
+    if (known_all_invalid(w)) { // all-zero output (autoscale.rs:376-378, 466-468, 716-718); a device-planned band gets there
+                                // through its all-zero table
         CU(cudaMemsetAsync(dst, 0, n * (out8 ? 1 : 2), ctx->stream));
         return 0;
     }
@@ -680,9 +657,9 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     const bool out8 = j.kind != PlanKind::Autoscale || j.bit_depth == SARPRO_U8;
     const int pix16 = out8 ? 0 : 1;
     const size_t esz = out8 ? 1 : 2;
-    if (g.pad || !w.plan.any_valid) CU(cudaMemsetAsync(canvas, 0, g.oc * g.orr * esz, ctx->stream));
+    if (g.pad || known_all_invalid(w)) CU(cudaMemsetAsync(canvas, 0, g.oc * g.orr * esz, ctx->stream));
     if (g.rc == 0 || g.rr == 0) return 0;
-    if (!w.plan.any_valid) return 0; // resize of an all-zero raster is all zero
+    if (known_all_invalid(w)) return 0; // resize of an all-zero raster is all zero
     const bool clahe = uses_clahe(j);
     const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
     AxisPlan *ah, *av;
@@ -695,8 +672,7 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     a.src_rows = (uint32_t)j.rows;
     a.src_cols = (uint32_t)j.cols;
     a.lut = (const uint16_t*)w.lut.p;
-    a.hot = w.hot;
-    a.hot_top = w.hot_top;
+    a.plan = (const PlanDev*)w.plan_dev.p;
     a.remap = nullptr;
     if (clahe) a.clahe = clahe_dev(ctx, b);
     a.minmax = clahe ? (uint32_t*)w.scalars.p : nullptr;
@@ -705,7 +681,7 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     a.temp = w.temp.p;
     a.ax = ah->dev();
     auto run = [&]() -> int {
-        RC(run_hpass(ctx, a, src_kind, pix16, ah, 0));
+        RC(run_hpass(ctx, b, a, src_kind, pix16, ah, 0));
         unsigned char* dst = (unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz;
         KS(a.skip ? SARPRO_STAGE_OTHER : SARPRO_STAGE_VRESIZE,
            launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream, a.skip));
@@ -772,9 +748,13 @@ int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint
     std::memcpy(ctx->h_lut + (size_t)b * kDnBins, lut_host, kDnBins * 2);
     CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
     w.plan.any_valid = true;
+    w.plan.have_invalid = true;
     w.plan.clahe = uses_clahe(j);
     w.plan.max_present_dn = max_key;
-    w.hot = hpipe_hot(lut_host, nullptr, max_key, &w.hot_top);
+    w.plan.sat_from_dn = 0;
+    w.hot = hmma_hot(lut_host, nullptr, max_key, &w.hot_top);
+    w.dev_planned = false;
+    RC(upload_plan_dev(ctx, b));
     return dn_run_pass_b(ctx, b, j, g, canvas);
 }
 
@@ -823,6 +803,18 @@ int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band*
     return 0;
 }
 
+// Enum arguments of the C ABI (types.rs:8-14, 115-123, 170-173): anything outside the declared discriminants is an error,
+// never a silent default. Pass -2 for an argument the entry point does not take.
+int check_enums(sarpro_ctx* ctx, int op, int strategy, int bit_depth) {
+    if (op != -2 && (op < -1 || op > SARPRO_OP_LOGRATIO))
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "unknown polarization operation %d", op);
+    if (strategy != -2 && (strategy < SARPRO_STRATEGY_STANDARD || strategy > SARPRO_STRATEGY_DEFAULT))
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "unknown autoscale strategy %d", strategy);
+    if (bit_depth != -2 && bit_depth != SARPRO_U8 && bit_depth != SARPRO_U16)
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "unknown bit depth %d", bit_depth);
+    return 0;
+}
+
 int check_band(sarpro_ctx* ctx, const sarpro_band* b) {
     if (!b) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "band descriptor is NULL");
     if (b->rows * b->cols > 0 && !b->data) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "band data is NULL");
@@ -839,7 +831,10 @@ int begin_call(sarpro_ctx* ctx) {
     if (!ctx) return SARPRO_ERR_INVALID_ARGUMENT;
     ctx->err.clear();
     CU(cudaSetDevice(ctx->device));
+    if (ctx->axes.size() > 64) drop_axis_plans(ctx); // bounded cache; no plan pointer is held across calls
     std::memset(&ctx->timing, 0, sizeof(ctx->timing));
+    ctx->pending_stats[0] = ctx->pending_stats[1] = nullptr;
+    ctx->band[0].plan_copy_pending = ctx->band[1].plan_copy_pending = false;
     ctx->n_sev = 0;
     ctx->host_t0 = host_ms();
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -847,12 +842,34 @@ int begin_call(sarpro_ctx* ctx) {
 }
 int end_call(sarpro_ctx* ctx) {
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    for (int b = 0; b < 2; ++b) // host work kept off the critical path: runs while the device drains the queue
-        if (ctx->band[b].hist_auto_pending) {
-            ctx->band[b].hist_auto = choose_hist_variant(ctx->band[b].plan);
-            ctx->band[b].hist_auto_pending = false;
-        }
     CU(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < 2; ++b) {
+        BandWs& w = ctx->band[b];
+        if (w.plan_copy_pending) { // device-planned: the plan's host mirror is valid now
+            const PlanDev& p = ctx->h_plan[b];
+            w.plan.any_valid = p.any_valid != 0;
+            w.plan.have_invalid = p.have_invalid != 0;
+            w.plan.max_present_dn = p.max_present_dn;
+            w.plan.sat_from_dn = p.sat_from_dn;
+            w.plan.pre_min = (uint16_t)p.pre_min;
+            w.plan.pre_max = (uint16_t)p.pre_max;
+            w.plan.px_total = p.px_total;
+            w.plan.px_ge1024 = p.px_ge1024;
+            w.plan.px_ge2048 = p.px_ge2048;
+            w.plan.stats = p.stats;
+            w.hot = p.hot;
+            w.hot_top = p.hot_top;
+            w.plan_copy_pending = false;
+        }
+        if (ctx->pending_stats[b]) {
+            *ctx->pending_stats[b] = w.plan.stats;
+            ctx->pending_stats[b] = nullptr;
+        }
+        if (w.hist_auto_pending) { // pass-A table shape of the next call on this slot
+            w.hist_auto = choose_hist_variant(w.plan);
+            w.hist_auto_pending = false;
+        }
+    }
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->timing.total_ms = ms;
@@ -974,9 +991,12 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
         const bool side = pipelined && nb == 2 && b == 0 && ctx->two_stream && ctx->stream2;
         cudaStream_t main_stream = ctx->stream;
         int rc = 0;
-        if (pipelined) rc = wait_and_plan_on(ctx, b, jobs[b], side ? ctx->stream2 : nullptr);
+        if (pipelined) rc = plan_band_on(ctx, b, jobs[b], side ? ctx->stream2 : nullptr);
         if (!rc) {
-            if (stats) stats[b] = w.plan.stats;
+            if (stats) {
+                if (w.dev_planned) ctx->pending_stats[b] = &stats[b]; // filled in end_call from the plan's host mirror
+                else stats[b] = w.plan.stats;
+            }
             rc = dn_run_pass_b(ctx, b, jobs[b], *geom, w.small.p);
         }
         if (side) {
@@ -1043,15 +1063,19 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if ((e = cudaMallocHost((void**)&ctx->h_lut, 2 * kDnBins * 2)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_scalars, 2 * 8 * 4)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_remap, 2 * 256)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_plan, 2 * sizeof(PlanDev))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_plan_up, 2 * sizeof(PlanDev))) != cudaSuccess) return bail("cudaMallocHost", e);
     ctx->valid_thresh = compute_valid_thresh();
-    dn_db_table();
+    // the DN -> dB table of the device planner (pipeline.rs:19-20, evaluated with the host libm like the reference's)
+    if ((e = cudaMalloc(&ctx->db_table.p, kDnBins * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    ctx->db_table.cap = kDnBins * sizeof(double);
+    if ((e = cudaMemcpy(ctx->db_table.p, dn_db_table(), kDnBins * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+    if (const char* v = getenv("SARPRO_HOST_PLAN")) ctx->host_plan = atoi(v);
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
-    if (const char* v = getenv("SARPRO_HPIPE")) ctx->use_hpipe = atoi(v);
     if (const char* v = getenv("SARPRO_HMMA")) ctx->use_hmma = atoi(v);
     if (const char* v = getenv("SARPRO_TWO_STREAM")) ctx->two_stream = atoi(v);
     if (getenv("SARPRO_TRACE") || (getenv("SARPRO_STAGE_TIMING") && std::string(getenv("SARPRO_STAGE_TIMING")) == "all")) ctx->stage_mask = 0xffu;
-    if (const char* v = getenv("SARPRO_HPIPE_NSUB")) ctx->hpipe_nsub = (atoi(v) == 2 || atoi(v) == 3 || atoi(v) == 12) ? atoi(v) : 0;
     int rc = upload_rgb_luts(ctx);
     if (rc) {
         g_create_error = ctx->err;
@@ -1066,25 +1090,24 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    sarpro_comm_destroy(ctx); // NCCL communicator + CommState
     for (auto& w : ctx->band)
         for (DevBuf* b : {&w.dn, &w.f32a, &w.f32b, &w.tile_hist, &w.total, &w.lut, &w.tile256, &w.cdf, &w.cdf32, &w.remap,
-                          &w.temp, &w.small, &w.full, &w.scalars, &w.present})
+                          &w.temp, &w.small, &w.full, &w.scalars, &w.present, &w.edges, &w.hist4096, &w.f32scan, &w.pieces,
+                          &w.cta_first, &w.plan_dev})
             release(*b);
     for (DevBuf* b : {&ctx->units, &ctx->tile_px, &ctx->col_dx, &ctx->col_omdx, &ctx->col_t, &ctx->row_dy, &ctx->row_omdy,
-                      &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts, &ctx->col_m, &ctx->row_sat,
-                      &ctx->rowblocks, &ctx->pieces, &ctx->cta_first})
+                      &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts, &ctx->col_m, &ctx->row_sat, &ctx->db_table})
         release(*b);
-    for (auto& kv : ctx->axes) {
-        release(kv.second->start); release(kv.second->size); release(kv.second->coef);
-        release(kv.second->packed); release(kv.second->strips); release(kv.second->fstrips); release(kv.second->pstrips); release(kv.second->sstrips);
-        release(kv.second->m_btab); release(kv.second->m_ntile); release(kv.second->m_strips);
-        delete kv.second;
-    }
+    drop_axis_plans(ctx);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
     if (ctx->h_present) cudaFreeHost(ctx->h_present);
     if (ctx->h_lut) cudaFreeHost(ctx->h_lut);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_remap) cudaFreeHost(ctx->h_remap);
+    if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
+    if (ctx->h_plan_up) cudaFreeHost(ctx->h_plan_up);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->sev)
@@ -1168,11 +1191,51 @@ int sarpro_plan_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int 
     return SARPRO_OK;
 }
 
+int sarpro_plan_on_device(sarpro_ctx* ctx, const uint32_t* hist65536, int bit_depth, int strategy, int plan_kind,
+                          sarpro_stats* stats, uint16_t* lut16, uint32_t* hot2) {
+    RC(begin_call(ctx));
+    if (!hist65536) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    RC(check_enums(ctx, -2, strategy, bit_depth));
+    if (plan_kind < 0 || plan_kind > 2 || !plan_on_device_supported(strategy, plan_kind))
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "strategy %d (kind %d) is planned on the host", strategy, plan_kind);
+    BandWs& w = ctx->band[0];
+    RC(reserve(ctx, w.total, kDnBins * 4));
+    RC(reserve(ctx, w.lut, kDnBins * 2));
+    CU(cudaMemcpyAsync(w.total.p, hist65536, kDnBins * 4, cudaMemcpyHostToDevice, ctx->stream));
+    BandJob job;
+    job.strategy = strategy;
+    job.bit_depth = bit_depth;
+    job.kind = (PlanKind)plan_kind;
+    RC(plan_band_on_device(ctx, 0, job));
+    if (lut16) CU(cudaMemcpyAsync(lut16, w.lut.p, kDnBins * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    RC(end_call(ctx));
+    if (stats) *stats = w.plan.stats;
+    if (hot2) { hot2[0] = w.hot; hot2[1] = w.hot_top; }
+    return SARPRO_OK;
+}
+
+int sarpro_plan_kind_from_dn_histogram(const uint64_t* hist65536, int bit_depth, int strategy, int plan_kind,
+                                       sarpro_stats* stats, uint16_t* lut16, uint32_t* hot2) {
+    if (!hist65536 || plan_kind < 0 || plan_kind > 2) return SARPRO_ERR_INVALID_ARGUMENT;
+    BandPlan p;
+    plan_from_dn_histogram(hist65536, bit_depth, strategy, (PlanKind)plan_kind, &p);
+    if (stats) *stats = p.stats;
+    if (lut16) std::memcpy(lut16, p.lut.data(), kDnBins * 2);
+    if (hot2) {
+        hot2[1] = 0;
+        hot2[0] = p.any_valid ? hmma_hot_from_plan(p, &hot2[1]) : 0;
+    }
+    return SARPRO_OK;
+}
+
 // ---- fused pipelines ---------------------------------------------------------------------------------
 int sarpro_pipeline_single(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, int op, int format, int bit_depth,
                            int strategy, int has_target, size_t target, int pad, sarpro_image* out, sarpro_stats* stats) {
     RC(begin_call(ctx));
     if (!a || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    RC(check_enums(ctx, op, strategy, bit_depth));
+    if (op >= 0 && !b) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "a polarization operation needs two bands");
+    if (format != SARPRO_FORMAT_TIFF && format != SARPRO_FORMAT_JPEG) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "unknown output format %d", format);
     if (format == SARPRO_FORMAT_JPEG) bit_depth = SARPRO_U8; // save.rs:121
     const sarpro_band* ins[1] = {a};
     const sarpro_band* ins2[1] = {b};
@@ -1192,6 +1255,7 @@ int sarpro_pipeline_multiband_tiff(sarpro_ctx* ctx, const sarpro_band* b1, const
                                    sarpro_image* out2, sarpro_stats* stats2) {
     RC(begin_call(ctx));
     if (!b1 || !b2 || !out1 || !out2) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    RC(check_enums(ctx, -2, strategy, bit_depth));
     const sarpro_band* ins[2] = {b1, b2};
     const sarpro_band* ins2[2] = {nullptr, nullptr};
     const int ops[2] = {-1, -1};
@@ -1214,6 +1278,7 @@ int sarpro_pipeline_synrgb(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_
     (void)mode; // all four SyntheticRgbMode values alias Default (synthetic_rgb.rs:72-79)
     RC(begin_call(ctx));
     if (!b1 || !b2 || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    RC(check_enums(ctx, -2, strategy, -2));
     const sarpro_band* ins[2] = {b1, b2};
     const sarpro_band* ins2[2] = {nullptr, nullptr};
     const int ops[2] = {-1, -1};
@@ -1237,6 +1302,7 @@ int sarpro_pipeline_synrgb(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_
 static int stage_pipeline(sarpro_ctx* ctx, const void* data, int dtype, size_t rows, size_t cols, int bit_depth,
                           int strategy, PlanKind kind, uint8_t* out_u8, uint16_t* out_u16, sarpro_stats* stats) {
     RC(begin_call(ctx));
+    RC(check_enums(ctx, -2, strategy, bit_depth));
     sarpro_band band{data, dtype, SARPRO_LOC_HOST, rows, cols};
     const sarpro_band* ins[1] = {&band};
     const sarpro_band* ins2[1] = {nullptr};
@@ -1291,7 +1357,8 @@ int sarpro_pol_op(sarpro_ctx* ctx, int op, const float* a, const float* b, size_
     const size_t n = rows * cols;
     if (n == 0) return end_call(ctx);
     if (!a || !b || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
-    if (op < 0 || op > 4) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "unknown polarization operation %d", op);
+    if (op < 0) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "unknown polarization operation %d", op);
+    RC(check_enums(ctx, op, -2, -2));
     BandWs& w = ctx->band[0];
     RC(reserve(ctx, w.f32a, n * 4));
     RC(reserve(ctx, w.f32b, n * 4));
@@ -1306,6 +1373,7 @@ int sarpro_pol_op(sarpro_ctx* ctx, int op, const float* a, const float* b, size_
 int sarpro_add_padding_to_square(sarpro_ctx* ctx, const uint8_t* u8_data, const uint16_t* u16_data, size_t cols,
                                  size_t rows, int bit_depth, uint8_t* out_u8, uint16_t* out_u16) {
     RC(begin_call(ctx));
+    RC(check_enums(ctx, -2, -2, bit_depth));
     const void* src = bit_depth == SARPRO_U8 ? (const void*)u8_data : (const void*)u16_data;
     void* dst = bit_depth == SARPRO_U8 ? (void*)out_u8 : (void*)out_u16;
     if (bit_depth == SARPRO_U16 && !u16_data) return fail(ctx, SARPRO_ERR_U16_REQUIRED, "U16 data required for U16 bit depth");
@@ -1330,6 +1398,7 @@ int sarpro_resize_image_data_with_meta(sarpro_ctx* ctx, const uint8_t* u8_data, 
                                        size_t rows, int has_target, size_t target, int bit_depth, int pad,
                                        uint8_t* out_u8, uint16_t* out_u16, sarpro_resize_meta* meta) {
     RC(begin_call(ctx));
+    RC(check_enums(ctx, -2, -2, bit_depth));
     const int pix16 = bit_depth == SARPRO_U16;
     const size_t esz = pix16 ? 2 : 1;
     const OutGeom g = out_geometry(cols, rows, has_target != 0, target, pad != 0);
@@ -1363,7 +1432,7 @@ int sarpro_resize_image_data_with_meta(sarpro_ctx* ctx, const uint8_t* u8_data, 
         a.n_rows = (uint32_t)rows;
         a.temp = w.temp.p;
         a.ax = ah->dev();
-        RC(run_hpass(ctx, a, HSRC_IMAGE, pix16, ah, 0));
+        RC(run_hpass(ctx, 0, a, HSRC_IMAGE, pix16, ah, 0));
         KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, region, (uint32_t)g.oc, 0, pix16, ctx->stream));
     }
     CU(cudaMemcpyAsync(dst, w.small.p, n_out * esz, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1374,6 +1443,7 @@ int sarpro_create_synthetic_rgb_by_mode_and_strategy(sarpro_ctx* ctx, int mode, 
                                                      const uint8_t* band2, size_t n, uint8_t* rgb) {
     (void)mode;
     RC(begin_call(ctx));
+    RC(check_enums(ctx, -2, strategy, -2));
     if (n == 0) return end_call(ctx);
     if (!band1 || !band2 || !rgb) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
     RC(reserve(ctx, ctx->band[0].small, n));

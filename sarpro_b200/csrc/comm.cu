@@ -2,10 +2,10 @@
 //
 // Each rank holds scene rows [h0,h1): its own band [r0,r1) plus the vertical Lanczos halo. All exchanged
 // quantities are integers, so the sharded result is bit-identical to the single-GPU result:
-//   1. DN histogram            all-reduce(sum)  2 x 65,536 u32            -> every rank plans redundantly
-//   2. CLAHE tile histograms   all-reduce(sum)  2 x 64 x 256 u32          -> every rank builds all 64 CDFs
+//   1. DN histogram            all-reduce(sum)  2 x 65,536 u32 (one group) -> every rank plans redundantly (on the device)
+//   2. CLAHE tile histograms   all-reduce(sum)  2 x 64 x 256 u32 (one group) -> every rank builds all 64 CDFs
 //   3. CLAHE sample min/max    all-reduce(max)  4 u32                      -> scale_u16_to_u8 decision
-//   4. resized rows            all-reduce(max)  2 x out_cols x out_rows u8 (disjoint rows, zero elsewhere)
+//   4. resized rows            broadcast of each rank's own output rows (one fused group), <= 2 x out_cols x out_rows u8 in all
 // NCCL is dlopen()ed (libnccl.so.2, the copy torch ships) so the library has no link-time dependency; the
 // host only moves the 128-byte ncclUniqueId between ranks.
 #include <dlfcn.h>
@@ -32,6 +32,7 @@ struct NcclApi {
     int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -63,6 +64,7 @@ static NcclApi& nccl() {
     SARPRO_SYM(CommInitRank, "ncclCommInitRank")
     SARPRO_SYM(CommDestroy, "ncclCommDestroy")
     SARPRO_SYM(AllReduce, "ncclAllReduce")
+    SARPRO_SYM(Broadcast, "ncclBroadcast")
     SARPRO_SYM(GroupStart, "ncclGroupStart")
     SARPRO_SYM(GroupEnd, "ncclGroupEnd")
     SARPRO_SYM(GetErrorString, "ncclGetErrorString")
@@ -206,6 +208,7 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     (void)mode;
     RC(begin_call(ctx));
     if (!b1 || !b2) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    RC(check_enums(ctx, -2, strategy, -2));
     if (!ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
     NcclApi& api = nccl();
     CommState* cs = ctx->comm;
@@ -260,67 +263,108 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         jobs[b].strategy = strategy;
         jobs[b].bit_depth = SARPRO_U8;
         jobs[b].kind = kinds[b];
-        RC(dn_pass_a_launch_sharded(ctx, b, dn, rows, cols, clahe, sg));
-        // ---- 1. DN histogram all-reduce of this band; ev[2 + b] marks the merged histogram as being on the host
-        {
-            COMM_BEGIN();
-            NC(api.AllReduce(w.total.p, w.total.p, kDnBins, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
-            COMM_END();
-        }
-        CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaEventRecord(ctx->ev[2 + b], ctx->stream));
     }
-    // Per band: wait for its histogram, plan on the host (every rank plans redundantly) while the device works on what
-    // is queued behind it (band 1's pass A, then band 0's pass B), 2. all-reduce the CLAHE tile histograms, pass B over
-    // the held rows. The collectives are issued in the same order on every rank.
-    const size_t esz = 1;
-    const size_t n_out = g.oc * g.orr;
-    HResizeArgs args[2];
+    for (int b = 0; b < 2; ++b) RC(dn_pass_a_launch_sharded(ctx, b, jobs[b].dn, rows, cols, clahe, sg, 1));
+    for (int b = 0; b < 2; ++b) RC(dn_pass_a_launch_sharded(ctx, b, jobs[b].dn, rows, cols, clahe, sg, 2));
+    // ---- 1. DN histograms of both bands: one fused all-reduce (a group of two) ---------------------------------------------
+    {
+        COMM_BEGIN();
+        NC(api.GroupStart());
+        for (int b = 0; b < 2; ++b)
+            NC(api.AllReduce(ctx->band[b].total.p, ctx->band[b].total.p, kDnBins, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
+        NC(api.GroupEnd());
+        COMM_END();
+    }
+    // ---- plans: on the device for the gamma == 1 strategies (no host round trip; every rank plans redundantly from the
+    // merged histogram, bit-identically), else on the host from the merged dense totals
     for (int b = 0; b < 2; ++b) {
         BandWs& w = ctx->band[b];
-        CU(cudaEventSynchronize(ctx->ev[2 + b]));
-        ctx->timing.host_syncs++;
-        plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
-        std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
-        w.hot = w.plan.any_valid ? hpipe_hot_from_plan(w.plan, &w.hot_top) : 0;
-        CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
-        if (clahe) {
+        if (plans_on_device(ctx, jobs[b])) {
+            RC(plan_band_on_device(ctx, b, jobs[b]));
+        } else {
+            CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            ctx->timing.host_syncs++;
+            plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
+            std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+            w.hot = w.plan.any_valid ? hmma_hot_from_plan(w.plan, &w.hot_top) : 0;
+            CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+            RC(upload_plan_dev(ctx, b));
+            w.dev_planned = false;
+            w.hist_auto_pending = true;
+        }
+    }
+    // ---- 2. CLAHE tile histograms of both bands: one fused all-reduce, then every rank builds all 64 CDFs -------------------
+    if (clahe) {
+        for (int b = 0; b < 2; ++b) {
+            BandWs& w = ctx->band[b];
             RC(reserve(ctx, w.tile256, (size_t)ctx->n_tiles * 256 * 4));
             RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
             RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
             CU(cudaMemsetAsync(w.tile256.p, 0, (size_t)ctx->n_tiles * 256 * 4, ctx->stream));
-            if (w.plan.any_valid)
-                KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles,
-                                                           w.plan.max_present_dn, (uint32_t*)w.tile256.p, ctx->stream));
-            {
-                COMM_BEGIN();
-                NC(api.AllReduce(w.tile256.p, w.tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
-                COMM_END();
-            }
+            KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles,
+                                                       (const PlanDev*)w.plan_dev.p, (uint32_t*)w.tile256.p, ctx->stream));
+        }
+        {
+            COMM_BEGIN();
+            NC(api.GroupStart());
+            for (int b = 0; b < 2; ++b)
+                NC(api.AllReduce(ctx->band[b].tile256.p, ctx->band[b].tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum, cs->comm,
+                                 ctx->stream));
+            NC(api.GroupEnd());
+            COMM_END();
+        }
+        for (int b = 0; b < 2; ++b) {
+            BandWs& w = ctx->band[b];
             KS(SARPRO_STAGE_PLAN, launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles,
                                                    (double*)w.cdf.p, (float*)w.cdf32.p, ctx->stream));
         }
-        // ---- pass B: horizontal pass over the held rows
-        RC(reserve(ctx, w.temp, std::max<size_t>((size_t)rows * g.rc * esz, 16)));
-        RC(reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)));
-        CU(cudaMemsetAsync(w.small.p, 0, std::max<size_t>(n_out * esz, 1), ctx->stream));
-        HResizeArgs a{};
-        a.src = jobs[b].dn;
-        a.src_rows = (uint32_t)rows;
-        a.src_cols = (uint32_t)cols;
-        a.lut = (const uint16_t*)w.lut.p;
-        a.hot = w.hot;
-        a.hot_top = w.hot_top;
-        a.remap = nullptr;
-        if (clahe) a.clahe = clahe_dev(ctx, b);
-        a.minmax = clahe ? (uint32_t*)w.scalars.p : nullptr;
-        a.row0 = 0;
-        a.n_rows = (uint32_t)rows;
-        a.temp = w.temp.p;
-        a.ax = ah->dev();
-        args[b] = a;
-        if (w.plan.any_valid) RC(run_hpass(ctx, a, src_kind, 0, ah, h0));
     }
+    // ---- pass B: horizontal pass over the held rows; band 0 on the side stream so that band 1's persistent CTAs fill the
+    // SMs band 0's leave early
+    const size_t esz = 1;
+    const size_t n_out = g.oc * g.orr;
+    HResizeArgs args[2];
+    cudaStream_t main_stream = ctx->stream;
+    const bool two = ctx->two_stream && ctx->stream2;
+    if (two) {
+        CU(cudaEventRecord(ctx->ev[4], main_stream));
+        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev[4], 0));
+    }
+    int rc_b = 0;
+    for (int b = 0; b < 2 && !rc_b; ++b) {
+        BandWs& w = ctx->band[b];
+        ctx->stream = (two && b == 0) ? ctx->stream2 : main_stream;
+        auto body = [&]() -> int {
+            RC(reserve(ctx, w.temp, std::max<size_t>((size_t)rows * g.rc * esz, 16)));
+            RC(reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)));
+            CU(cudaMemsetAsync(w.small.p, 0, std::max<size_t>(n_out * esz, 1), ctx->stream));
+            HResizeArgs a{};
+            a.src = jobs[b].dn;
+            a.src_rows = (uint32_t)rows;
+            a.src_cols = (uint32_t)cols;
+            a.lut = (const uint16_t*)w.lut.p;
+            a.plan = (const PlanDev*)w.plan_dev.p;
+            a.remap = nullptr;
+            if (clahe) a.clahe = clahe_dev(ctx, b);
+            a.minmax = clahe ? (uint32_t*)w.scalars.p : nullptr;
+            a.row0 = 0;
+            a.n_rows = (uint32_t)rows;
+            a.temp = w.temp.p;
+            a.ax = ah->dev();
+            args[b] = a;
+            RC(run_hpass(ctx, b, a, src_kind, 0, ah, h0));
+            return 0;
+        };
+        rc_b = body();
+    }
+    ctx->stream = main_stream;
+    if (two) { // also on the error path: the side stream must not run past this call unobserved
+        cudaError_t e1 = cudaEventRecord(ctx->ev_join, ctx->stream2);
+        cudaError_t e2 = cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
+        if (!rc_b) { CU(e1); CU(e2); }
+    }
+    RC(rc_b);
     // ---- 3. scale_u16_to_u8 decision for CLAHE: global sample min/max --------------------------------------------
     if (clahe) {
         // scalars[0] = min, [1] = max per band -> pack {max, ~min} so that one all-reduce(max) serves both. Everything
@@ -335,30 +379,39 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         KS(SARPRO_STAGE_COMM, launch_minmax_pack((uint32_t*)ctx->band[0].scalars.p, (uint32_t*)ctx->band[1].scalars.p, dpk, 1, ctx->stream));
         for (int b = 0; b < 2; ++b) {
             BandWs& w = ctx->band[b];
-            if (!w.plan.any_valid) continue;
             RC(reserve(ctx, w.remap, 256 + 16));
             uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
             KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream));
             args[b].remap = (const uint8_t*)w.remap.p;
             args[b].minmax = nullptr;
             args[b].skip = flag;
-            RC(run_hpass(ctx, args[b], src_kind, 0, ah, h0));
+            RC(run_hpass(ctx, b, args[b], src_kind, 0, ah, h0));
         }
     }
-    // ---- vertical pass for the owned output rows, then 4. merge the rows of all ranks -------------------------------
+    // ---- vertical pass for the owned output rows, then 4. every rank's rows to every rank ---------------------------------
     for (int b = 0; b < 2; ++b) {
         BandWs& w = ctx->band[b];
-        if (w.plan.any_valid && oy1 > oy0) {
+        if (oy1 > oy0) {
             unsigned char* dst = (unsigned char*)w.small.p + (g.pad_top * g.oc + g.pad_left) * esz;
             KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, (uint32_t)h0, (uint32_t)g.rc, av->dev(), (uint32_t)oy0, (uint32_t)oy1, dst,
                                                     (uint32_t)g.oc, 0, 0, ctx->stream));
         }
     }
     if (n_out) {
+        // The canvases are zero outside a rank's own output rows: rank r's rows [oy0_r, oy1_r) (whole canvas rows, pad columns
+        // included) are broadcast in place from r, 2 x world broadcasts fused into one group (<= 0.55 MB per rank at C3 on 8
+        // GPUs, instead of an all-reduce over the 2 x 4 MB canvases).
         COMM_BEGIN();
         NC(api.GroupStart());
-        for (int b = 0; b < 2; ++b)
-            NC(api.AllReduce(ctx->band[b].small.p, ctx->band[b].small.p, n_out, kNcclUint8, kNcclMax, cs->comm, ctx->stream));
+        for (int r = 0; r < cs->world; ++r) {
+            size_t rr0, rr1, hh0, hh1, o0, o1;
+            RC(shard_geometry(scene_rows, cols, true, target, pad != 0, cs->world, r, clahe, &rr0, &rr1, &hh0, &hh1, &o0, &o1, nullptr, &av->h));
+            if (o1 <= o0) continue;
+            for (int b = 0; b < 2; ++b) {
+                unsigned char* rows_r = (unsigned char*)ctx->band[b].small.p + (g.pad_top + o0) * g.oc * esz;
+                NC(api.Broadcast(rows_r, rows_r, (o1 - o0) * g.oc * esz, kNcclUint8, r, cs->comm, ctx->stream));
+            }
+        }
         NC(api.GroupEnd());
         COMM_END();
     }

@@ -6,6 +6,11 @@
 
 namespace sarpro {
 
+// Opt-in to `bytes` of dynamic shared memory for kernel `func` on the CURRENT device. Function attributes are per device and
+// contexts on different devices may live in one process (and be used from different threads), so the record of what has been
+// configured is kept per (device, kernel) behind a mutex (kernels_small.cu).
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+
 // 128-bit streaming load that does not allocate in L1 (the rasters are read once per pass).
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
     uint4 r;

@@ -19,30 +19,27 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+void release(DevBuf& b);
+
+// One Lanczos axis (plan.cpp build_lanczos3_axis) with its device tables. Owned by the context's cache; plans are only
+// dropped between calls (begin_call), never while a call may still hold a pointer to one.
 struct AxisPlan {
     ResampleAxis h; // host copy
-    DevBuf start, size, coef, packed, strips, fstrips;
+    DevBuf start, size, coef, packed, strips;
     uint32_t pairs = 0, oxb = 0, rbw = 0, smem = 0, n_strips = 0;
     bool has_strips = false;
-    // production u8 kernel (kernels_hfast.cu)
-    bool fast = false;
-    uint32_t f_oxb = 0, f_rbw_words = 0, f_n_strips = 0;
-    std::vector<HStrip> f_strips_h;
-    // second-generation kernel (kernels_hpipe.cu)
-    bool pipe = false;
-    uint32_t p_oxb = 0, p_rbw_words = 0, p_n_strips = 0;
-    DevBuf pstrips;
-    std::vector<HStrip> p_strips_h;
-    // warp-specialised kernel: output strips of <= 128 columns
-    bool spec = false;
-    uint32_t s_oxb = 0, s_rbw_words = 0, s_n_strips = 0;
-    DevBuf sstrips;
-    std::vector<HStrip> s_strips_h;
     // tensor-core kernel (kernels_hmma.cu)
     bool mma = false;
     DevBuf m_btab, m_ntile, m_strips;
     std::vector<HStrip> m_weights_h;
     uint32_t m_b_bytes = 0;
+    uint64_t id = 0; // unique per plan: cache key of the piece lists (a recycled address must not match)
+    AxisPlan() = default;
+    AxisPlan(const AxisPlan&) = delete;
+    AxisPlan& operator=(const AxisPlan&) = delete;
+    ~AxisPlan() {
+        for (DevBuf* b : {&start, &size, &coef, &packed, &strips, &m_btab, &m_ntile, &m_strips}) release(*b);
+    }
     AxisDev dev() const {
         AxisDev d;
         d.start = (const uint32_t*)start.p;
@@ -77,7 +74,17 @@ struct BandWs {
     BandPlan plan;
     int hist_auto = 21;            // pass-A table shape for the next call (see choose_hist_variant)
     bool hist_auto_pending = false; // h_hist of this slot still has to go through choose_hist_variant
-    uint32_t hot = 0, hot_top = 0; // table range / saturated table word for kernels_hpipe.cu (0 = not eligible)
+    uint32_t hot = 0, hot_top = 0; // table range / saturated table word for kernels_hmma.cu (0 = not eligible)
+    // Piece lists of the persistent pass-B kernel for this slot (cached per geometry). Per slot, because the two bands of a
+    // pair run their pass B on different streams and may be cut differently: a shared list could be overwritten while the
+    // other band's kernel still reads it.
+    DevBuf plan_dev;                // PlanDev: the band's plan for the kernels downstream (device or host planner)
+    bool dev_planned = false;       // planned by kernels_plan.cu in this call: w.plan / hot are only valid after end_call
+    bool plan_copy_pending = false; // ctx->h_plan[slot] is being written by the device
+    DevBuf pieces, cta_first;
+    uint64_t pc_rows = 0, pc_row_off = 0, pc_tile_h = 0, pc_axis_id = 0;
+    int pc_clahe = -1;
+    uint32_t pc_n_ctas = 0, pc_unit = 0;
 };
 
 constexpr uint32_t kSynRgbSets = 42; // 0..40 suppressed by floor_with_cushion, 41 default
@@ -121,21 +128,10 @@ struct sarpro_ctx {
     std::string err;
     sarpro::BandWs band[2];
     sarpro::DevBuf units, tile_px, col_dx, col_omdx, col_t, row_dy, row_omdy, row_t, rgb, hist256, rgbsel, rgb_luts;
-    sarpro::DevBuf col_m, row_sat, rowblocks;
+    sarpro::DevBuf col_m, row_sat;
     uint64_t clahe_tile_w = 0, clahe_tile_h = 0, clahe_rows = 0;
-    // row-block cache of the horizontal pass
-    uint64_t rb_rows = 0, rb_row_off = 0, rb_tile_h = 0;
-    int rb_clahe = -1;
-    uint32_t n_rowblocks = 0;
-    // piece lists of kernels_hpipe.cu (cached per geometry)
-    sarpro::DevBuf pieces, cta_first;
-    uint64_t pc_rows = 0, pc_row_off = 0, pc_tile_h = 0;
-    int pc_clahe = -1, pc_nsub = 0;
-    const void* pc_axis = nullptr;
-    uint32_t pc_n_ctas = 0, pc_max_rows = 0;
-    int hpipe_nsub = 0;  // SARPRO_HPIPE_NSUB: 0 = auto (3 sub-blocks when shared memory allows, else 2)
-    int use_hpipe = 1;   // SARPRO_HPIPE=0: previous production kernel (kernels_hfast.cu)
-    int use_hmma = 1;    // SARPRO_HMMA=0: second-generation kernels (kernels_hpipe.cu) instead of kernels_hmma.cu
+    uint64_t next_axis_id = 1;
+    int use_hmma = 1;    // SARPRO_HMMA=0: the generic exact kernel (kernels_resize.cu) instead of kernels_hmma.cu (validation)
     int force_exact = 0; // SARPRO_FORCE_EXACT=1: generic kernels + exact f64 CLAHE everywhere (validation)
     // geometry caches
     uint64_t units_rows = 0, units_cols = 0, units_scene_rows = 0, units_row_off = 0, units_own0 = 0, units_own1 = 0;
@@ -148,6 +144,11 @@ struct sarpro_ctx {
     uint16_t* h_lut = nullptr;     // [2][65536]
     uint32_t* h_scalars = nullptr; // [2][8]
     uint8_t* h_remap = nullptr;    // [2][256]
+    sarpro::PlanDev* h_plan = nullptr;    // [2] device -> host mirror of the plans (read in end_call)
+    sarpro::PlanDev* h_plan_up = nullptr; // [2] staging of host-planned bands' plans on their way to the device
+    sarpro_stats* pending_stats[2] = {nullptr, nullptr}; // caller's stats structs to fill in end_call (device-planned bands)
+    sarpro::DevBuf db_table;       // [65536] f64: dB of every DN (device planner)
+    int host_plan = 0;             // SARPRO_HOST_PLAN=1: plan every band on the host (validation)
     // timing
     cudaEvent_t ev[6] = {};
     sarpro_timing timing{};
@@ -171,12 +172,12 @@ namespace sarpro {
 int fail(sarpro_ctx* c, int code, const char* fmt, ...);
 double host_ms();
 int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes);
-void release(DevBuf& b);
-uint32_t hpipe_hot(const uint16_t* lut_host, const uint32_t* hist_host, uint32_t max_present_dn, uint32_t* top_out);
-uint32_t hpipe_hot_from_plan(const BandPlan& plan, uint32_t* top_out);
+uint32_t hmma_hot(const uint16_t* lut_host, const uint32_t* hist_host, uint32_t max_present_dn, uint32_t* top_out);
+uint32_t hmma_hot_from_plan(const BandPlan& plan, uint32_t* top_out);
 int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res);
 int begin_call(sarpro_ctx* ctx);
-int run_hpass(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off);
+// slot: the band slot whose piece lists the tensor-core kernel uses
+int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off);
 // phase: 0 = everything, 1 = only the preamble (workspaces, cleared histograms and counters), 2 = only the kernels
 int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units, int phase = 0);
 int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units,
@@ -189,6 +190,7 @@ ClaheDev clahe_dev(sarpro_ctx* ctx, int b);
 int deliver(sarpro_ctx* ctx, const void* dev_src, size_t bytes, sarpro_image* out);
 void fill_image(sarpro_image* out, const OutGeom& g, int channels, int bit_depth);
 int check_band(sarpro_ctx* ctx, const sarpro_band* b);
+int check_enums(sarpro_ctx* ctx, int op, int strategy, int bit_depth); // -2 = not applicable
 int synrgb_compose(sarpro_ctx* ctx, int strategy, const uint8_t* c1, const uint8_t* c2, size_t n);
 int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint16_t* lut_host, uint32_t max_key,
                             const OutGeom& g, void* canvas);
@@ -196,6 +198,10 @@ int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const floa
                        uint64_t cols, int bit_depth, int strategy, PlanKind kind, const OutGeom& g, void* canvas_dev,
                        sarpro_stats* stats);
 int end_call(sarpro_ctx* ctx);
+struct BandJob;
+bool plans_on_device(const sarpro_ctx* ctx, const BandJob& job);
+int plan_band_on_device(sarpro_ctx* ctx, int b, const BandJob& job);
+int upload_plan_dev(sarpro_ctx* ctx, int b);
 
 #define CU(call)                                                                                             \
     do {                                                                                                     \

@@ -6,7 +6,39 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "../../include/sarpro_gpu.h"
+
 namespace sarpro {
+
+// ---- the plan of one band, in device memory ---------------------------------------------------
+// Written by the device planner (kernels_plan.cu) or uploaded by the host planner (plan.cpp); read by the kernels downstream,
+// so that no host round trip is needed between pass A and pass B. Mirrored to pinned host memory at the end of a call.
+constexpr uint32_t kHmmaMaxHot = 2000; // largest DN range the shared-memory table of kernels_hmma.cu takes
+struct PlanDev {
+    uint32_t any_valid;      // some pixel is valid (dB > -50, pipeline.rs:22)
+    uint32_t have_invalid;   // some present DN is invalid
+    uint32_t max_present_dn; // brightest DN with a non-zero count
+    uint32_t sat_from_dn;    // lowest present DN from which all present DNs share the brightest one's table word
+    uint32_t hot;            // table range of kernels_hmma.cu (0: more than kHmmaMaxHot entries needed)
+    uint32_t hot_top;        // table word of the DNs >= hot - 1
+    uint32_t use_generic;    // 1: the tensor-core pass B cannot take this band; the generic exact kernel runs instead
+    uint32_t clahe;
+    uint32_t pre_min, pre_max; // min / max of the quantised samples before scale_u16_to_u8
+    uint32_t pad0, pad1;
+    unsigned long long px_total, px_ge1024, px_ge2048, pad2;
+    sarpro_stats stats;
+};
+struct PlanParams {
+    int strategy;  // sarpro_strategy
+    int kind;      // 0 = autoscale, 1 = Tamed-synRGB co-pol, 2 = Tamed-synRGB cross-pol (PlanKind)
+    int bit_depth; // sarpro_bit_depth
+    int clahe;
+};
+// strategies the device planner covers (gamma == 1: no pow); the others are planned on the host
+bool plan_on_device_supported(int strategy, int kind);
+// total: [65536] u32 DN counts; db_table: [65536] f64 dB of every DN (plan.cpp dn_db_table); lut: [65536] u16 out
+cudaError_t launch_plan_band(const uint32_t* total, const double* db_table, const PlanParams& pr, uint16_t* lut, PlanDev* out,
+                             cudaStream_t stream);
 
 // ---- work decomposition -----------------------------------------------------------------
 // A histogram work unit: rows [r0,r1) x cols [c0,c1) of the local raster, all inside one tile.
@@ -30,7 +62,8 @@ cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint3
 
 // ---- CLAHE tile statistics ------------------------------------------------------------------
 // tile256[t][bin] = sum over dn>=1 of tile_hist[t][dn] where lut[dn] == bin (autoscale.rs:259-269)
-cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut, uint32_t n_tiles, uint32_t max_dn,
+// plan->max_present_dn bounds the walk (read on the device)
+cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut, uint32_t n_tiles, const PlanDev* plan,
                                  uint32_t* tile256, cudaStream_t stream);
 // clip / redistribute / CDF per tile (autoscale.rs:271-302). tile_px[t] = tile_rows*tile_cols.
 cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, uint32_t n_tiles, double* cdf,
@@ -101,13 +134,11 @@ struct HResizeArgs {
     ClaheDev clahe;        // HSRC_DN_CLAHE
     uint32_t* minmax;      // HSRC_DN_CLAHE: min/max of the blended samples (before remap)
     const uint32_t* skip;  // optional device flag: the kernel returns at once when *skip != 0
+    const uint32_t* run_if; // optional device flag (generic kernel): the kernel returns at once when *run_if == 0
+    const PlanDev* plan;   // HSRC_DN_* through kernels_hmma.cu: the band's plan (table range, kernel choice) in device memory
     // rows to produce: temp row i <- source row (row0 + i), i < n_rows
     uint32_t row0, n_rows;
     void* temp;            // [n_rows][out_cols] same pixel type
-    uint32_t rbw_words;    // production kernel: shared row-buffer slots (16 B each)
-    uint32_t hot;          // HSRC_DN_*: table range for kernels_hpipe.cu (every present DN >= hot-1 shares the
-                           // table word of DN hot-1); 0 = unknown / not eligible
-    uint32_t hot_top;      // that table word (lut value of the saturated DNs)
     AxisDev ax;
 };
 // One CTA of the horizontal pass owns a strip of output columns; the strip's source span is staged per row.
@@ -127,40 +158,22 @@ cudaError_t hresize_build_strips(const uint32_t* start_h, const uint32_t* size_h
 cudaError_t launch_hresize_planned(const HResizeArgs& a, int src_kind, int pix16, const HStrip* strips_dev,
                                    uint32_t n_strips, uint32_t oxb, uint32_t rbw, uint32_t smem, int sm_count,
                                    cudaStream_t stream);
-// Production horizontal pass for u8 samples (kernels_hfast.cu): taps in registers, row-interleaved shared
-// staging, next-group prefetch, fp32 CLAHE fast path with exact fix-up. rowblocks: (first,last+1) source rows.
-bool hfast_supported(uint32_t pairs);
-cudaError_t hfast_build_strips(const uint32_t* start_h, const uint32_t* size_h, uint32_t out_size, uint32_t in_size,
-                               uint32_t window, uint32_t* strip_w_out, std::vector<HStrip>* strips, uint32_t* rbw_words);
-cudaError_t launch_hfast(const HResizeArgs& a, int src_kind, const HStrip* strips_dev, uint32_t n_strips,
-                         const uint2* rowblocks_dev, uint32_t n_rowblocks, uint32_t strip_w, cudaStream_t stream);
-// Second-generation production pass (kernels_hpipe.cu): two 256-thread halves per CTA sharing lane-interleaved
-// tables, three-stage software pipeline, fp32 CLAHE bilinear form with exact fix-up queue. max_vec bounds the
-// strip's source span in 8-sample vectors (CLAHE: <= tile_w / 8 so a strip meets at most one cell boundary).
-bool hpipe_supported(uint32_t pairs);
-cudaError_t hpipe_build_strips(const uint32_t* start_h, const uint32_t* size_h, uint32_t out_size, uint32_t in_size,
-                               uint32_t window, uint32_t max_vec, uint32_t max_w, uint32_t* strip_w_out,
-                               std::vector<HStrip>* strips, uint32_t* rbw_words);
-// Equal-weight contiguous runs of (strip, rows) pieces, one run per persistent CTA. pieces_flat: 4 words per piece
-// (strip, r0, r1, 0); cta_first: n_ctas + 1 entries. cuts: row positions no piece may straddle (0 ... rows).
-void hpipe_build_pieces(const std::vector<HStrip>& strips, const std::vector<uint64_t>& cuts, uint32_t n_ctas, uint32_t unit,
-                        std::vector<uint32_t>* pieces_flat, std::vector<uint32_t>* cta_first, uint32_t* max_rows);
-size_t hpipe_smem_bytes(int src_kind, int nsub, uint32_t hot, uint32_t max_rows, uint32_t rbw_words);
-cudaError_t launch_hpipe(const HResizeArgs& a, int src_kind, int nsub, const HStrip* strips_dev, const uint32_t* pieces_dev,
-                         const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t strip_w, uint32_t hot, uint32_t max_rows,
-                         cudaStream_t stream);
+// Equal-weight contiguous runs of (strip, rows) pieces, one run per persistent CTA of the tensor-core pass B. pieces_flat:
+// 4 words per piece (strip, r0, r1, 0); cta_first: n_ctas + 1 entries. cuts: row positions no piece may straddle (0 ... rows);
+// unit: rows a CTA takes per round (16 per warp).
+void hmma_build_pieces(const std::vector<HStrip>& strips, const std::vector<uint64_t>& cuts, uint32_t n_ctas, uint32_t unit,
+                       std::vector<uint32_t>* pieces_flat, std::vector<uint32_t>* cta_first, uint32_t* max_rows);
 // A piece of the persistent pass-B kernels: rows [r0, r1) (inside one vertical CLAHE cell) of strip `strip`.
 struct HPiece {
     uint32_t strip, r0, r1, pad;
 };
-uint32_t hpipe_lut_shift(uint32_t hot);
-// Third-generation pass B (kernels_hmma.cu): horizontal Lanczos taps on the integer tensor-core path (IMMA.16832),
+// Production pass B for u8 samples (kernels_hmma.cu): horizontal Lanczos taps on the integer tensor-core path (IMMA.16832),
 // samples packed straight into the A fragments. Plan: n-tiles of 8 output columns over 64-column source blocks.
 struct HMmaPlanHost {
     std::vector<uint4> btab;     // permuted tap bytes, one uint4 per (n-tile block, k-step, lane)
     std::vector<int4> ntile;     // {first block, last block, offset into btab in blocks, 0}
     std::vector<uint4> strips;   // {first n-tile, end n-tile, first block, end block}
-    std::vector<HStrip> weights; // per strip, for hpipe_build_pieces (nvec = 8 * blocks)
+    std::vector<HStrip> weights; // per strip, for hmma_build_pieces (nvec = 8 * blocks)
     uint32_t b_bytes = 0;        // tap bytes of the largest strip (staged in shared memory)
 };
 // max_span: longest source span of a strip in columns (CLAHE: the tile width), 0 = unbounded. false when the axis
@@ -168,10 +181,10 @@ struct HMmaPlanHost {
 bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int32_t* coef_h, uint32_t window, uint32_t out_size,
                      uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan);
 bool hmma_replay_row(const HMmaPlanHost& plan, const uint8_t* samples, uint32_t in_size, uint32_t out_size, int precision, uint8_t* out);
-size_t hmma_smem_bytes(int src_kind, uint32_t hot, uint32_t b_bytes);
+size_t hmma_smem_bytes(int src_kind, uint32_t b_bytes);
 uint32_t hmma_warps(bool clahe); // warps per CTA of the instantiation
 cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,
-                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t hot, uint32_t b_bytes,
+                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t b_bytes,
                         cudaStream_t stream);
 // vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,

@@ -17,105 +17,7 @@ namespace sarpro {
 // =============================================================================================
 // Pass A — per-tile DN histogram.  2 B/px read; one shared-memory atomic per non-zero pixel.
 // =============================================================================================
-// Shared layout: NCOPY = 1 << LOGC interleaved sub-histograms, word (dn << LOGC) | (lane & (NCOPY-1)).
-// With NCOPY = 32 every lane owns a bank (no conflicts); smaller NCOPY trades conflicts for range.
-// DN 0 (black fill, long runs of identical values) is counted in a register; DN >= HOT (rare bright
-// targets) goes straight to the L2-resident tile histogram.
-template <int HOT, int LOGC>
-__global__ void __launch_bounds__(512) k_dn_hist(const uint16_t* __restrict__ dn, uint64_t cols,
-                                                 const HistUnit* __restrict__ units, uint32_t n_units,
-                                                 uint32_t* __restrict__ tile_hist) {
-    extern __shared__ uint32_t sh[];
-    constexpr uint32_t NCOPY = 1u << LOGC;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t mycopy = lane & (NCOPY - 1);
-    for (uint32_t i = tid; i < (uint32_t)HOT * NCOPY; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-
-    // 16-byte aligned view of the raster: element e of `dn` is element e + eoff of `dn_al`.
-    const uint16_t* dn_al = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(dn) & ~uintptr_t(15));
-    const uint64_t eoff = (uint64_t)(dn - dn_al);
-
-    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const HistUnit un = units[u];
-        uint32_t* __restrict__ gh = tile_hist + (size_t)un.tile * 65536u;
-        unsigned zeros = 0;
-        const uint32_t seg = un.c1 - un.c0;
-
-        auto add = [&](uint32_t d) {
-            if (d == 0) zeros++;
-            else if (d < (uint32_t)HOT) atomicAdd(&sh[(d << LOGC) | mycopy], 1u);
-            else atomicAdd(&gh[d], 1u);
-        };
-        auto consume = [&](const uint4& q, uint64_t vb, uint64_t e0, uint64_t e1) {
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-            if (vb >= e0 && vb + 8 <= e1) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { add(w[k] & 0xffffu); add(w[k] >> 16); }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint64_t e = vb + k;
-                    if (e >= e0 && e < e1) add((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu));
-                }
-            }
-        };
-
-        for (uint32_t r = un.r0 + warp; r < un.r1; r += nwarps) {
-            const uint64_t e0 = (uint64_t)r * cols + un.c0 + eoff, e1 = e0 + seg;
-            const uint64_t v0 = e0 >> 3, v1 = (e1 + 7) >> 3;
-            for (uint64_t v = v0 + lane; v < v1; v += 128) {
-                uint4 q[4];
-                bool ok[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint64_t vv = v + 32u * j;
-                    ok[j] = vv < v1;
-                    if (ok[j]) q[j] = ld_stream_u4(dn_al + (vv << 3));
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (ok[j]) consume(q[j], (v + 32u * j) << 3, e0, e1);
-            }
-        }
-        zeros = warp_reduce_add(zeros);
-        if (lane == 0 && zeros) atomicAdd(&gh[0], zeros);
-        __syncthreads();
-        for (uint32_t b = tid; b < (uint32_t)HOT; b += blockDim.x) {
-            uint32_t s = 0;
-#pragma unroll
-            for (uint32_t c = 0; c < NCOPY; ++c) {
-                s += sh[(b << LOGC) | c];
-                sh[(b << LOGC) | c] = 0;
-            }
-            if (s) atomicAdd(&gh[b], s);
-        }
-        __syncthreads();
-    }
-}
-
-template <int HOT, int LOGC>
-static cudaError_t launch_dn_hist_t(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
-                                    uint32_t* tile_hist, int sm_count, cudaStream_t stream) {
-    const size_t smem = (size_t)HOT * (1u << LOGC) * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_dn_hist<HOT, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    int per_sm = (int)((227u * 1024u) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 3) per_sm = 3; // 512 threads each
-    uint32_t grid = (uint32_t)(sm_count * per_sm);
-    if (grid > n_units) grid = n_units;
-    if (grid == 0) return cudaSuccess;
-    k_dn_hist<HOT, LOGC><<<grid, 512, smem, stream>>>(dn, cols, units, n_units, tile_hist);
-    return cudaGetLastError();
-}
-
-
-// ---- second generation: lean inner loop ---------------------------------------------------------------
+// ---- general kernel (any column count) --------------------------------------------------------------------
 // Per 8-pixel vector: one range test on the OR of the four words, then per pixel one shift/mask (ALU pipe),
 // one IMAD (FMA pipe) and one shared-memory reduction — no per-pixel predicates. DN 0 is counted like any other
 // value (a run of identical DNs is one POPC-merged update per replica). Vectors that hold a DN >= HOT or that
@@ -333,12 +235,7 @@ template <int HOT, int LOGC>
 static cudaError_t launch_dn_hist3_t(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
                                      uint32_t* tile_hist, uint32_t* counter, int sm_count, cudaStream_t stream) {
     const size_t smem = (size_t)HOT * (1u << LOGC) * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_dn_hist3<HOT, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_dn_hist3<HOT, LOGC>), smem)) return e;
     uint32_t grid = (uint32_t)sm_count;
     if (grid > n_units) grid = n_units;
     if (grid == 0) return cudaSuccess;
@@ -350,12 +247,7 @@ template <int HOT, int LOGC>
 static cudaError_t launch_dn_hist2_t(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
                                      uint32_t* tile_hist, int sm_count, cudaStream_t stream) {
     const size_t smem = (size_t)HOT * (1u << LOGC) * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_dn_hist2<HOT, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_dn_hist2<HOT, LOGC>), smem)) return e;
     uint32_t grid = (uint32_t)sm_count;
     if (grid > n_units) grid = n_units;
     if (grid == 0) return cudaSuccess;
@@ -365,23 +257,16 @@ static cudaError_t launch_dn_hist2_t(const uint16_t* dn, uint64_t cols, const Hi
 
 cudaError_t launch_dn_hist(const uint16_t* dn, uint64_t cols, const HistUnit* units, uint32_t n_units,
                            uint32_t* tile_hist, int sm_count, int variant, cudaStream_t stream, uint32_t* counter) {
-    if (variant >= 20 && (!counter || cols % 8 != 0)) variant -= 10; // third generation needs the unit counter and cols % 8 == 0
+    // variant: table shape 20 / 21 / 22 = DN < 4096 / 2048 / 1024 in the replicated shared histogram (8 / 16 / 32 replicas).
+    // The production kernel (k_dn_hist3) needs the unit counter and cols % 8 == 0; other rasters take the general kernel.
+    const bool gen3 = counter && cols % 8 == 0;
     switch (variant) {
-    case 20: return launch_dn_hist3_t<4096, 3>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream);
-    case 21: return launch_dn_hist3_t<2048, 4>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream);
-    case 22: return launch_dn_hist3_t<1024, 5>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream);
-    case 10: return launch_dn_hist2_t<4096, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 11: return launch_dn_hist2_t<2048, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 12: return launch_dn_hist2_t<1024, 5>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 13: return launch_dn_hist2_t<2048, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 14: return launch_dn_hist2_t<1024, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 1: return launch_dn_hist_t<4096, 0>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 2: return launch_dn_hist_t<2048, 2>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 3: return launch_dn_hist_t<1024, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 4: return launch_dn_hist_t<1024, 5>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 5: return launch_dn_hist_t<4096, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    case 6: return launch_dn_hist_t<1536, 5>(dn, cols, units, n_units, tile_hist, sm_count, stream);
-    default: return launch_dn_hist_t<2048, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 20: return gen3 ? launch_dn_hist3_t<4096, 3>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream)
+                         : launch_dn_hist2_t<4096, 3>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    case 22: return gen3 ? launch_dn_hist3_t<1024, 5>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream)
+                         : launch_dn_hist2_t<1024, 5>(dn, cols, units, n_units, tile_hist, sm_count, stream);
+    default: return gen3 ? launch_dn_hist3_t<2048, 4>(dn, cols, units, n_units, tile_hist, counter, sm_count, stream)
+                         : launch_dn_hist2_t<2048, 4>(dn, cols, units, n_units, tile_hist, sm_count, stream);
     }
 }
 
@@ -436,8 +321,9 @@ cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint3
 // CLAHE tile statistics
 // =============================================================================================
 __global__ void k_clahe_tile256(const uint32_t* __restrict__ tile_hist, const uint16_t* __restrict__ lut,
-                                uint32_t max_dn, uint32_t* __restrict__ tile256) {
+                                const PlanDev* __restrict__ plan, uint32_t* __restrict__ tile256) {
     __shared__ uint32_t h[256];
+    const uint32_t max_dn = plan->max_present_dn;
     const uint32_t t = blockIdx.x, part = blockIdx.y, nparts = gridDim.y;
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -449,12 +335,12 @@ __global__ void k_clahe_tile256(const uint32_t* __restrict__ tile_hist, const ui
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(&tile256[t * 256u + threadIdx.x], h[threadIdx.x]);
 }
-cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut, uint32_t n_tiles, uint32_t max_dn,
+cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut, uint32_t n_tiles, const PlanDev* plan,
                                  uint32_t* tile256, cudaStream_t stream) {
-    uint32_t parts = (max_dn + 2047) / 2048;
-    if (parts < 1) parts = 1;
-    if (parts > 32) parts = 32;
-    k_clahe_tile256<<<dim3(n_tiles, parts), 256, 0, stream>>>(tile_hist, lut, max_dn, tile256);
+    // the brightest present DN is only known on the device: a fixed split of the DN range (a GRD band ends below DN 4096
+    // except for point targets; CTAs whose share lies beyond max_dn return at once)
+    const uint32_t parts = 8;
+    k_clahe_tile256<<<dim3(n_tiles, parts), 256, 0, stream>>>(tile_hist, lut, plan, tile256);
     return cudaGetLastError();
 }
 

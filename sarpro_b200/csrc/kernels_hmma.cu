@@ -15,7 +15,7 @@
 // shared memory; the strip's B fragments are staged there once per piece. An output n-tile (8 output columns) is live
 // while the walk crosses its window (three accumulator slots, rotated), then it is scaled, clamped and stored.
 //
-// Per-pixel stage. LUT strategies: one shared-memory gather (R-way lane-interleaved table, as kernels_hpipe.cu).
+// Per-pixel stage. LUT strategies: one shared-memory gather (R-way lane-interleaved table).
 // CLAHE (autoscale.rs:307-330, :602): DN -> address of the pixel's bin entry in an 8-way replicated float4 table
 // holding the bilinear form of the four tile CDFs of the cell, u = A + B*dx + (C + D*dx)*dy in sample units, three
 // FFMAs in plain fp32 (|u| < 512, so its rounding error is ~2e-5). A carries +S where S bounds the total error of
@@ -37,26 +37,6 @@ namespace sarpro {
 
 namespace hm {
 constexpr uint32_t kThreadsLut = 512, kThreadsClahe = 384;      // CLAHE: fewer warps, 168 registers each for the gather pipeline
-// Experimental first-gather table of the CLAHE instantiation (build with SARPRO_NVCC_EXTRA=-DSARPRO_HMMA_PACKED_LUT; off by
-// default, NOT yet run on a GPU): 16-bit entries, two DNs per 32-bit word, 32 lane-private replicas in the bytes the
-// 16-replica table of 32-bit entries takes (hot << 6) -> every lane reads its own bank, one wavefront per gather instead of
-// ~2.4 with DN ranges above 500 (profiles/r01q_ncu_full_hmma.md: the co-pol launch has 14.7 M bank conflicts and takes 555 us,
-// the cross-pol launch, whose 32-replica table is conflict-free, 504 us). Entry of (DN idx, replica r): u16 at byte
-// ((idx >> 1) << 7) + 4 r + 2 (idx & 1), holding the byte offset of the bin's entry inside a quad cell.
-#ifdef SARPRO_HMMA_PACKED_LUT
-constexpr bool kPackedLut = true;
-#else
-constexpr bool kPackedLut = false;
-#endif
-// Experimental epilogue (-DSARPRO_HMMA_STG64; off by default, NOT yet run on a GPU): the four lanes of a quad hold 2 of the 8
-// output columns of a finished n-tile each for rows g and g + 8; instead of four byte stores per lane (32 L1 tag requests per
-// n-tile and warp, 8.2 M per launch for 1.0 M sectors) the quad's samples are gathered with three shuffles and lane q = 0
-// stores 8 bytes per row (16 tag requests). Needs the output width to be a multiple of 8 (rows of `temp` 8-byte aligned).
-#ifdef SARPRO_HMMA_STG64
-constexpr bool kStg64 = true;
-#else
-constexpr bool kStg64 = false;
-#endif
 constexpr uint32_t kQuadEntries = 257;                       // 256 bins + the invalid-pixel entry
 constexpr uint32_t kQuadCellBytes = kQuadEntries * 8 * 16;   // one cell, 8 replicas
 constexpr int kSlots = 3;                                    // n-tiles in flight per warp
@@ -166,8 +146,11 @@ struct HMmaParams {
     const uint4* strips;   // per strip: {first n-tile, end n-tile, first block, end block}; a block is two k-steps
     const HPiece* pieces;
     const uint32_t* cta_first;
-    uint32_t hot, lut_shift, b_bytes; // b_bytes: the largest strip's B fragments (staged in shared memory)
+    uint32_t b_bytes; // the largest strip's B fragments (staged in shared memory)
 };
+
+// 32 lane-private replicas (conflict-free gathers) when the table still fits the 16-bit address range, else 16 (<= 64 KB) or 8
+__host__ __device__ inline uint32_t hmma_lut_shift(uint32_t hot) { return hot <= 500 ? 7u : (hot <= 1000 ? 6u : 5u); }
 
 // Error bound of the fp32 evaluation of one table entry (see the header), in sample units. X, Y bound |dx|, |dy|.
 __device__ __forceinline__ double hm_half_ulp(double x) {
@@ -196,44 +179,37 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     constexpr uint32_t NT = CLAHE ? hm::kThreadsClahe : hm::kThreadsLut;
     constexpr uint32_t FULL = 0xffffffffu;
     if (a.skip && *a.skip) return;
+    // the table range comes from the band's plan in device memory (device or host planner): no host round trip before this launch
+    const uint32_t hot = a.plan->hot, hot_top = a.plan->hot_top;
+    if (hot == 0 || a.plan->use_generic) return; // the generic exact kernel (launched behind this one) takes the band
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t hot = pp.hot, lut_shift = pp.lut_shift; // table word of DN idx, replica r: byte (idx << lut_shift) + 4r
+    const uint32_t lut_shift = hmma_lut_shift(hot); // table word of DN idx, replica r: byte (idx << lut_shift) + 4r
     const HMmaSmem L = hmma_layout(CLAHE, hot << lut_shift, pp.b_bytes);
     const uint32_t cols = a.src_cols;
     const uint32_t tid = threadIdx.x, lane = hm_keep(tid & 31u), g = hm_keep(lane >> 2), q = hm_keep(lane & 3u);
     if (sbase + (hot << lut_shift) > 65536u) __trap(); // 16-bit table addresses (dynamic smem starts low on sm_100)
     uint32_t* const s_ctrl = reinterpret_cast<uint32_t*>(smem + L.ctrl);
 
-    if (CLAHE && hm::kPackedLut) { // once per CTA: DN -> 16-bit quad-cell offset, 32 lane-private replicas, two DNs per word
-        uint16_t* s_lut16 = reinterpret_cast<uint16_t*>(smem + L.lut);
-        for (uint32_t i = tid; i < hot * 32u; i += NT) {
-            const uint32_t idx = i >> 5, r = i & 31u;
-            const uint32_t e = idx + 1 == hot ? a.hot_top : (a.lut[idx] & 255u);
+    {   // once per CTA: DN -> table word, R lane-interleaved replicas
+    uint4* s_lut4 = reinterpret_cast<uint4*>(smem + L.lut);
+    const uint32_t per = 1u << (lut_shift - 4); // uint4 per table entry
+    for (uint32_t i = tid; i < hot * per; i += NT) {
+        const uint32_t idx = i >> (lut_shift - 4), r0 = (i & (per - 1)) * 4u;
+        const uint32_t e = idx + 1 == hot ? hot_top : (a.lut[idx] & 255u);
+        uint4 v;
+        if (CLAHE) {
             const uint32_t bin = idx ? e : 256u; // DN 0 is the only invalid DN (pipeline.rs:22)
-            s_lut16[((idx >> 1) * 32u + r) * 2u + (idx & 1u)] = (uint16_t)((bin * 8u + (r & 7u)) * 16u);
+            const uint32_t b = sbase + L.quad + (bin * 8u + (r0 & 7u)) * 16u;
+            v = make_uint4(b, b + 16u, b + 32u, b + 48u);
+        } else {
+            v = make_uint4(e, e, e, e);
         }
-    } else {   // once per CTA: DN -> table word, R lane-interleaved replicas
-        uint4* s_lut4 = reinterpret_cast<uint4*>(smem + L.lut);
-        const uint32_t per = 1u << (lut_shift - 4); // uint4 per table entry
-        for (uint32_t i = tid; i < hot * per; i += NT) {
-            const uint32_t idx = i >> (lut_shift - 4), r0 = (i & (per - 1)) * 4u;
-            const uint32_t e = idx + 1 == hot ? a.hot_top : (a.lut[idx] & 255u);
-            uint4 v;
-            if (CLAHE) {
-                const uint32_t bin = idx ? e : 256u; // DN 0 is the only invalid DN (pipeline.rs:22)
-                const uint32_t b = sbase + L.quad + (bin * 8u + (r0 & 7u)) * 16u;
-                v = make_uint4(b, b + 16u, b + 32u, b + 48u);
-            } else {
-                v = make_uint4(e, e, e, e);
-            }
-            s_lut4[i] = v;
-        }
+        s_lut4[i] = v;
+    }
     }
     const uint32_t cap2 = hm_keep((hot - 1u) * 0x10001u);
     const uint32_t lut_mul = hm_keep(1u << lut_shift);
-    const uint32_t cj = hm_pin((sbase + L.lut + (lane & ((CLAHE && hm::kPackedLut ? 128u : lut_mul) / 4u - 1u)) * 4u) * 0x10001u, lane);
-    // packed table: address of DN idx = idx * 64 + (idx & 1) * (2 - 64) + replica; both halves of a DN pair at once
-    const uint32_t odd_mul = CLAHE && hm::kPackedLut ? hm_pin(2u - 64u, lane) : 0u;
+    const uint32_t cj = hm_pin((sbase + L.lut + (lane & (lut_mul / 4u - 1u)) * 4u) * 0x10001u, lane);
     const int prec = a.ax.precision;
     const int acc0 = (int)hm_keep(prec > 0 ? (1u << (prec - 1)) : 0u);
     const uint16_t* const src = reinterpret_cast<const uint16_t*>(a.src);
@@ -243,7 +219,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     uint32_t staged_strip = 0xffffffffu;
     const uint32_t sb_lane = hm_keep(sbase + L.bfrag + lane * 16u);
     // 8-byte stores of the resized rows: whole n-tiles only and 8-byte aligned rows
-    const bool wide_store = hm::kStg64 && (a.ax.out_size & 7u) == 0 && (reinterpret_cast<uintptr_t>(a.temp) & 7u) == 0;
+    const bool wide_store = (a.ax.out_size & 7u) == 0 && (reinterpret_cast<uintptr_t>(a.temp) & 7u) == 0;
     const uint32_t cols8 = hm_pin(cols - 8u, lane);
     const uint32_t cm_base = hm_pin(sbase + L.cm + q * 2u, lane);
     const float inv2tw = __uint_as_float(hm_pin(__float_as_uint(CLAHE ? a.clahe.inv2tw : 0.f), lane));
@@ -390,15 +366,13 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
         auto exact_px = [&](uint32_t r, uint32_t c) -> uint32_t {
             const uint32_t d = src[(size_t)r * cols + c];
             const uint32_t di = min(d, hot - 1u);
-            const uint32_t word = CLAHE && hm::kPackedLut
-                                      ? reinterpret_cast<const uint16_t*>(smem + L.lut)[(size_t)(di >> 1) * 64u + (di & 1u)] // replica 0
-                                      : reinterpret_cast<const uint32_t*>(smem + L.lut)[(size_t)di << (lut_shift - 2)];
+            const uint32_t word = reinterpret_cast<const uint32_t*>(smem + L.lut)[(size_t)di << (lut_shift - 2)];
             if (!CLAHE) return word;
             uint32_t o = 0;
             if (d) {
                 const ClaheDev& cl = a.clahe;
                 const uint32_t tx = cl.col_t[c];
-                const uint32_t bin = (hm::kPackedLut ? word : word - (sbase + L.quad)) >> 7;
+                const uint32_t bin = (word - (sbase + L.quad)) >> 7;
                 const double* s_cdf = reinterpret_cast<const double*>(smem + L.cdf);
                 const uint32_t x0 = ((tx & 7u) - cellA) * 256u + bin, x1 = (((tx >> 8) & 7u) - cellA) * 256u + bin;
                 double v = clahe_blend_exact_rn(s_cdf[x0], s_cdf[x1], s_cdf[768 + x0], s_cdf[768 + x1], cl.col_dx[c], cl.col_omdx[c],
@@ -518,17 +492,15 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                             for (int j = 0; j < 4; ++j) {
                                 const uint32_t vm = __vminu2(wv[j], cap2);
                                 a2[j] = hm_mad(vm, lut_mul, cj);
-                                if (hm::kPackedLut) a2[j] = hm_mad(vm & 0x00010001u, odd_mul, a2[j]);
                             }
                             if (more) d[v] = hm_ld_dn(src + ((rw ? oB : oA) + cn)); // the DNs are consumed: prefetch in place
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                e[rw][2 * j] = hm::kPackedLut ? hm_lds_u16(a2[j] & 0xffffu) : hm_lds_u32(a2[j] & 0xffffu);
-                                e[rw][2 * j + 1] = hm::kPackedLut ? hm_lds_u16(a2[j] >> 16) : hm_lds_u32(a2[j] >> 16);
+                                e[rw][2 * j] = hm_lds_u32(a2[j] & 0xffffu);
+                                e[rw][2 * j + 1] = hm_lds_u32(a2[j] >> 16);
                             }
                         }
                         uint32_t celloff = tag == 1 ? hm::kQuadCellBytes : 0u; // warp-uniform
-                        if (hm::kPackedLut) celloff += sbase + L.quad;          // (the packed entries are offsets inside a cell)
                         if (tag == 2) { // the pixel's own cell: cell B columns sit one tile further (dx - 1)
                             const bool vb = c0 >= bcol; // dx[] was built for the vector's first column
 #pragma unroll
@@ -682,7 +654,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                         for (int i = 0; i < 4; ++i) acc[s][i] += th[i] << 8;
                         if (ks0 + 1u >= slb[s]) { // the n-tile is complete: scale, clamp, store; the slot takes the next n-tile
                             const uint32_t ox = sj[s] * 8u + q * 2u;
-                            if (hm::kStg64 && wide_store) { // (warp-uniform: the shuffles below are executed by all lanes)
+                            if (wide_store) { // (warp-uniform: the shuffles below are executed by all lanes)
                                 uint32_t x = 0; // bytes: row g col ox, row g col ox+1, row g+8 col ox, row g+8 col ox+1
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
@@ -800,11 +772,53 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
     return true;
 }
 
-// 32 lane-private replicas (conflict-free gathers) when the table still fits the 16-bit address range, else 16 or 8
-static uint32_t hmma_lut_shift(uint32_t hot, bool clahe) {
-    if (clahe && hm::kPackedLut) return 6u; // packed 16-bit entries: 32 replicas in hot << 6 bytes
-    return hot <= 500 ? 7u : hpipe_lut_shift(hot);
+// Cuts the (strip, row) space into contiguous equal-weight runs, one per CTA. `cuts` are the row positions where
+// a piece must end (vertical CLAHE cell boundaries; first = 0, last = rows). A piece's weight is rows x nvec.
+// Pieces are multiples of `unit` rows from their segment start, so that every warp of a CTA gets a whole 16-row group per round.
+void hmma_build_pieces(const std::vector<HStrip>& strips, const std::vector<uint64_t>& cuts, uint32_t n_ctas, uint32_t unit,
+                        std::vector<uint32_t>* pieces_flat, std::vector<uint32_t>* cta_first, uint32_t* max_rows) {
+    struct Seg { uint32_t strip, r0, r1; uint64_t w; };
+    std::vector<Seg> segs;
+    uint64_t total = 0;
+    for (uint32_t s = 0; s < strips.size(); ++s)
+        for (size_t i = 0; i + 1 < cuts.size(); ++i) {
+            if (cuts[i + 1] <= cuts[i]) continue;
+            const uint64_t units = (cuts[i + 1] - cuts[i] + unit - 1) / unit;
+            segs.push_back(Seg{s, (uint32_t)cuts[i], (uint32_t)cuts[i + 1], units * std::max(1u, strips[s].nvec)});
+            total += segs.back().w;
+        }
+    n_ctas = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_ctas, total / std::max<uint64_t>(1, 64)) ); // >= 64 vector-units per CTA
+    pieces_flat->clear();
+    cta_first->assign(1, 0);
+    *max_rows = 0;
+    uint64_t done = 0; // weight handed out so far
+    size_t si = 0;
+    uint32_t r = segs.empty() ? 0 : segs[0].r0;
+    for (uint32_t b = 0; b < n_ctas; ++b) {
+        const uint64_t target = total * (b + 1) / n_ctas;
+        while (si < segs.size() && (done < target || b + 1 == n_ctas)) {
+            const Seg& sg = segs[si];
+            const uint64_t nv = std::max(1u, strips[sg.strip].nvec);
+            const uint64_t units_left = (sg.r1 - r + unit - 1) / unit;
+            uint64_t take = b + 1 == n_ctas ? units_left : std::min<uint64_t>(units_left, (target - done + nv - 1) / nv);
+            if (take == 0) break;
+            const uint32_t r1 = (uint32_t)std::min<uint64_t>(sg.r1, (uint64_t)r + take * unit);
+            pieces_flat->push_back(sg.strip);
+            pieces_flat->push_back(r);
+            pieces_flat->push_back(r1);
+            pieces_flat->push_back(0);
+            *max_rows = std::max(*max_rows, r1 - r);
+            done += take * nv;
+            r = r1;
+            if (r >= sg.r1) {
+                ++si;
+                if (si < segs.size()) r = segs[si].r0;
+            }
+        }
+        cta_first->push_back((uint32_t)(pieces_flat->size() / 4));
+    }
 }
+
 
 // Host replay of the kernel's walk for one row of u8 samples (test hook): strips, slot rotation, k-step windows, the
 // permuted tap bytes (hi * 256 + lo) and the final shift / clamp, in the order the device follows. out has out_size bytes.
@@ -860,16 +874,19 @@ bool hmma_replay_row(const HMmaPlanHost& plan, const uint8_t* samples, uint32_t 
 
 uint32_t hmma_warps(bool clahe) { return (clahe ? hm::kThreadsClahe : hm::kThreadsLut) / 32u; }
 
-size_t hmma_smem_bytes(int src_kind, uint32_t hot, uint32_t b_bytes) {
-    return hmma_layout(src_kind == HSRC_DN_CLAHE, hot << hmma_lut_shift(hot, src_kind == HSRC_DN_CLAHE), b_bytes).total;
+// Shared memory for the largest table a plan may ask for (the launch does not know `hot`: it is in device memory). The three
+// table shapes top out at 500 << 7 = 1000 << 6 = 2000 << 5 = 64,000 bytes, so the bound is the same for every hot.
+size_t hmma_smem_bytes(int src_kind, uint32_t b_bytes) {
+    return hmma_layout(src_kind == HSRC_DN_CLAHE, kHmmaMaxHot << hmma_lut_shift(kHmmaMaxHot), b_bytes).total;
 }
 
 cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_dev, const int4* ntile_dev, const uint4* strips_dev,
-                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t hot, uint32_t b_bytes,
+                        const uint32_t* pieces_dev, const uint32_t* cta_first_dev, uint32_t n_ctas, uint32_t b_bytes,
                         cudaStream_t stream) {
     if (a.n_rows == 0 || a.ax.out_size == 0 || n_ctas == 0) return cudaSuccess;
+    if (!a.plan) return cudaErrorInvalidValue;
     const bool clahe = src_kind == HSRC_DN_CLAHE;
-    const size_t smem = hmma_smem_bytes(src_kind, hot, b_bytes);
+    const size_t smem = hmma_smem_bytes(src_kind, b_bytes);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     HMmaParams pp;
     pp.btab = btab_dev;
@@ -877,24 +894,12 @@ cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_de
     pp.strips = strips_dev;
     pp.pieces = reinterpret_cast<const HPiece*>(pieces_dev);
     pp.cta_first = cta_first_dev;
-    pp.hot = hot;
-    pp.lut_shift = hmma_lut_shift(hot, clahe);
     pp.b_bytes = b_bytes;
     if (clahe) {
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_hmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
+        if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_hmma<true>), smem)) return e;
         k_hmma<true><<<n_ctas, hm::kThreadsClahe, smem, stream>>>(a, pp);
     } else {
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_hmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
+        if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_hmma<false>), smem)) return e;
         k_hmma<false><<<n_ctas, hm::kThreadsLut, smem, stream>>>(a, pp);
     }
     return cudaGetLastError();

@@ -1,0 +1,384 @@
+// kernels_plan.cu — the band planner on the device (one CTA), for the strategies whose window needs no pow():
+// Robust / Equalized / Clahe / Tamed / Default and the two Tamed-synRGB kinds (gamma == 1, autoscale.rs:492-561, 721-736).
+//
+// It is plan.cpp's plan_finish() restated for a single thread block: the same f64 operations in the same order on the
+// same inputs, so every percentile, the window and the DN -> sample / bin table come out bit-identical to the host
+// planner (the tests compare the two on every fixture). What makes that possible:
+//   * the DN -> dB table (pipeline.rs:19-20) is data-independent: the host computes it once per context with the libm the
+//     reference uses and uploads it (512 KB); no transcendental runs here;
+//   * everything else in compute_histogram_stats (autoscale.rs:35-160) is +, -, *, /, floor and comparisons on f64, all
+//     IEEE-exact on the device when nothing is contracted (explicit __d*_rn intrinsics below; the build also passes --fmad=false);
+//   * gamma == 1: powf(x, 1.0) == x, so the quantisation (autoscale.rs:647-651) is a multiply and a truncating cast;
+//   * scale_u16_to_u8 (autoscale.rs:348-364) is f32 arithmetic with roundf — the same on both sides.
+// Not bit-identical to the reference (nor was the host planner): mean / std (serial Welford over pixels, order-dependent);
+// they only feed log lines on these strategies. Standard and Adaptive (pow with gamma != 1, the skew test on mean / std)
+// stay on the host planner.
+//
+// With the plan on the device no host round trip is left between pass A and pass B: the kernels downstream read the table
+// range (`hot`), the brightest present DN and the kernel choice from PlanDev.
+#include <cfloat>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sarpro {
+
+namespace {
+
+constexpr uint32_t kPlanThreads = 1024;
+constexpr uint32_t kDnPerThread = 65536 / kPlanThreads; // 64 consecutive DNs per thread
+constexpr int kStatBinsDev = 4096;
+
+__device__ __forceinline__ unsigned long long cast_u64_dev(double x) { // Rust `as u64`: truncate, saturate, NaN -> 0
+    if (!(x == x) || x <= 0.0) return 0ull;
+    if (x >= 18446744073709551616.0) return 0xffffffffffffffffull;
+    return (unsigned long long)x;
+}
+__device__ __forceinline__ uint32_t cast_u16_dev(double x) {
+    if (!(x == x) || x <= 0.0) return 0u;
+    if (x >= 65535.0) return 65535u;
+    return (uint32_t)x;
+}
+__device__ __forceinline__ uint32_t cast_u8_dev(double x) {
+    if (!(x == x) || x <= 0.0) return 0u;
+    if (x >= 255.0) return 255u;
+    return (uint32_t)x;
+}
+__device__ __forceinline__ double clampd_dev(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// block-wide reductions over 1024 threads (32 warps); every thread gets the result
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T* scratch /* 33 entries */) {
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads(); // scratch may still be read from the previous reduction
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        T w = scratch[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w = op(w, __shfl_xor_sync(0xffffffffu, w, o));
+        if (lane == 0) scratch[32] = w;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+struct OpAddU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; } };
+struct OpMinU32 { __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a < b ? a : b; } };
+struct OpMaxU32 { __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
+struct OpMaxI32 { __device__ int operator()(int a, int b) const { return a > b ? a : b; } };
+struct OpAddF64 { __device__ double operator()(double a, double b) const { return __dadd_rn(a, b); } };
+
+} // namespace
+
+__global__ void __launch_bounds__(kPlanThreads, 1)
+k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, PlanParams pr, uint16_t* __restrict__ lut,
+            PlanDev* __restrict__ out) {
+    __shared__ unsigned long long s_cum[kStatBinsDev]; // 4096-bin histogram (autoscale.rs:103-117), then its inclusive prefix sums
+    __shared__ unsigned long long s_u64[33];
+    __shared__ uint32_t s_u32[33];
+    __shared__ int s_i32[33];
+    __shared__ double s_f64[33];
+    __shared__ double s_pct[11];
+    __shared__ double s_win[3]; // low, high, range
+    __shared__ uint8_t s_remap[256];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t dn0 = tid * kDnPerThread;
+
+    // ---- present DNs: counts, range ------------------------------------------------------------------------------------
+    // valid <=> dB > -50 (pipeline.rs:22); for a u16 DN that is DN >= 1 (dB(1) = 0, dB(0) = -100), but the table decides.
+    unsigned long long cnt = 0, px = 0, ge1k = 0, ge2k = 0;
+    uint32_t first_valid = 0xffffffffu, last_valid = 0, last_present = 0;
+    uint32_t invalid_present = 0;
+    for (uint32_t k = 0; k < kDnPerThread; ++k) {
+        const uint32_t d = dn0 + k;
+        const uint32_t h = total[d];
+        if (!h) continue;
+        px += h;
+        if (d >= 1024) ge1k += h;
+        if (d >= 2048) ge2k += h;
+        last_present = d;
+        if (db[d] > -50.0) {
+            cnt += h;
+            if (first_valid == 0xffffffffu) first_valid = d;
+            last_valid = d;
+        } else {
+            invalid_present = 1;
+        }
+    }
+    const unsigned long long count = block_reduce(cnt, OpAddU64(), s_u64);
+    const unsigned long long px_total = block_reduce(px, OpAddU64(), s_u64);
+    const unsigned long long px_ge1024 = block_reduce(ge1k, OpAddU64(), s_u64);
+    const unsigned long long px_ge2048 = block_reduce(ge2k, OpAddU64(), s_u64);
+    const uint32_t min_dn = block_reduce(first_valid, OpMinU32(), s_u32);
+    const uint32_t max_valid_dn = block_reduce(last_valid, OpMaxU32(), s_u32);
+    const uint32_t max_present_dn = block_reduce(last_present, OpMaxU32(), s_u32);
+    const bool have_invalid = block_reduce(invalid_present, OpMaxU32(), s_u32) != 0;
+
+    if (count == 0) { // all-zero output (autoscale.rs:376-378, 466-468, 716-718): every table word is 0
+        for (uint32_t k = 0; k < kDnPerThread; ++k) lut[dn0 + k] = 0;
+        if (tid == 0) {
+            PlanDev p{};
+            p.max_present_dn = max_present_dn;
+            p.have_invalid = have_invalid;
+            p.hot = 64; // every present DN (only invalid ones) carries word 0
+            p.hot_top = 0;
+            p.clahe = pr.clahe;
+            p.px_total = px_total;
+            p.px_ge1024 = px_ge1024;
+            p.px_ge2048 = px_ge2048;
+            *out = p;
+        }
+        return;
+    }
+
+    // ---- pass 1 of compute_histogram_stats over distinct values (autoscale.rs:37-55) ----------------------------------
+    const double min_db = db[min_dn], max_db = db[max_valid_dn]; // dB is monotone in the DN
+    double sum = 0.0;
+    for (uint32_t k = 0; k < kDnPerThread; ++k) {
+        const uint32_t d = dn0 + k;
+        const uint32_t h = total[d];
+        if (h && db[d] > -50.0) sum = __dadd_rn(sum, __dmul_rn((double)h, db[d]));
+    }
+    const double mean_db = __ddiv_rn(block_reduce(sum, OpAddF64(), s_f64), (double)count);
+    double m2 = 0.0;
+    for (uint32_t k = 0; k < kDnPerThread; ++k) {
+        const uint32_t d = dn0 + k;
+        const uint32_t h = total[d];
+        if (h && db[d] > -50.0) {
+            const double dd = __dsub_rn(db[d], mean_db);
+            m2 = __dadd_rn(m2, __dmul_rn((double)h, __dmul_rn(dd, dd)));
+        }
+    }
+    const double m2_all = block_reduce(m2, OpAddF64(), s_f64);
+    const double std_db = count > 1 ? sqrt(__ddiv_rn(m2_all, (double)count)) : 0.0;
+
+    // ---- pass 2 (autoscale.rs:103-117) + percentiles (:120-159) ---------------------------------------------------------
+    const bool degenerate = fabs(__dsub_rn(max_db, min_db)) < DBL_EPSILON; // autoscale.rs:81
+    if (!degenerate) {
+        for (uint32_t i = tid; i < (uint32_t)kStatBinsDev; i += kPlanThreads) s_cum[i] = 0ull;
+        __syncthreads();
+        const double span = __dsub_rn(max_db, min_db);
+        const double inv_span = __ddiv_rn(1.0, span);
+        for (uint32_t k = 0; k < kDnPerThread; ++k) {
+            const uint32_t d = dn0 + k;
+            const uint32_t h = total[d];
+            if (h && db[d] > -50.0) {
+                const double t = clampd_dev(__dmul_rn(__dsub_rn(db[d], min_db), inv_span), 0.0, 1.0);
+                unsigned long long idx = cast_u64_dev(__dmul_rn(t, (double)kStatBinsDev));
+                if (idx >= (unsigned long long)kStatBinsDev) idx = kStatBinsDev - 1;
+                atomicAdd(&s_cum[idx], (unsigned long long)h);
+            }
+        }
+        __syncthreads();
+        // inclusive prefix sums in place: four bins per thread, then the block-wide offsets
+        unsigned long long v[4], run = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { run += s_cum[tid * 4 + i]; v[i] = run; }
+        {
+            const uint32_t lane = tid & 31u, wid = tid >> 5;
+            unsigned long long inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long nb = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)lane >= o) inc += nb;
+            }
+            __syncthreads();
+            if (lane == 31) s_u64[wid] = inc;
+            __syncthreads();
+            unsigned long long warp_off = 0;
+            for (uint32_t w = 0; w < wid; ++w) warp_off += s_u64[w];
+            const unsigned long long off = warp_off + inc - run;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s_cum[tid * 4 + i] = v[i] + off;
+        }
+        __syncthreads();
+        if (tid < 11) { // estimate_percentile (autoscale.rs:120-140) for p = 1, 2, 5, 10, 25, 50, 75, 90, 95, 98, 99 %
+            const double ps[11] = {0.01, 0.02, 0.05, 0.10, 0.25, 0.5, 0.75, 0.90, 0.95, 0.98, 0.99};
+            unsigned long long target = cast_u64_dev(floor(__dmul_rn(ps[tid], (double)count)));
+            if (target >= count) target = count - 1;
+            // first bin b with target < cumsum(b) (the inclusive sums are non-decreasing)
+            int lo = 0, hi = kStatBinsDev - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_cum[mid] > target) hi = mid; else lo = mid + 1;
+            }
+            const int b = lo;
+            const unsigned long long before = b ? s_cum[b - 1] : 0ull;
+            const unsigned long long h = s_cum[b] - before;
+            const unsigned long long within = target >= before ? target - before : 0ull;
+            const double frac = h > 0 ? __ddiv_rn((double)within, (double)h) : 0.0;
+            const double bin_width = __ddiv_rn(span, (double)kStatBinsDev);
+            const double bin_start = __dadd_rn(min_db, __dmul_rn((double)b, bin_width));
+            s_pct[tid] = __dadd_rn(bin_start, __dmul_rn(frac, bin_width));
+        }
+    } else if (tid < 11) {
+        s_pct[tid] = tid <= 5 ? min_db : max_db; // autoscale.rs:81-100: p01..p25 and the median = min, p75..p99 = max
+    }
+    __syncthreads();
+    const double p01 = s_pct[0], p02 = s_pct[1], p05 = s_pct[2], p10 = s_pct[3], p25 = s_pct[4], med = s_pct[5], p75 = s_pct[6],
+                 p90 = s_pct[7], p95 = s_pct[8], p98 = s_pct[9], p99 = s_pct[10];
+
+    // ---- window (plan.cpp choose_window; only the gamma == 1 arms) ------------------------------------------------------
+    if (tid == 0) {
+        double low, high;
+        if (pr.kind == 1) { // TamedSynRgbCopol, autoscale.rs:721-723
+            low = fmin(p02, p05);
+            high = p99;
+        } else if (pr.kind == 2) { // TamedSynRgbCross, autoscale.rs:724-727
+            low = p05;
+            high = p99;
+        } else if (pr.strategy == SARPRO_STRATEGY_ROBUST) { // autoscale.rs:492-499
+            const double iqr = __dsub_rn(p75, p25);
+            const double thr = __dmul_rn(2.5, iqr);
+            low = fmax(fmax(__dsub_rn(p25, thr), p01), min_db);
+            high = fmin(fmin(__dadd_rn(p75, thr), p99), max_db);
+        } else if (pr.strategy == SARPRO_STRATEGY_EQUALIZED || pr.strategy == SARPRO_STRATEGY_CLAHE) { // :539-548
+            low = p01;
+            high = p99;
+        } else if (pr.strategy == SARPRO_STRATEGY_TAMED) { // :549-553
+            low = p25;
+            high = p99;
+        } else { // Default, :554-561
+            low = p05;
+            high = p95;
+        }
+        s_win[0] = low;
+        s_win[1] = high;
+        s_win[2] = fmax(__dsub_rn(high, low), 1.0); // autoscale.rs:429, 564, 729
+    }
+    __syncthreads();
+    const double low = s_win[0], high = s_win[1], range = s_win[2];
+
+    // ---- the table ------------------------------------------------------------------------------------------------------
+    const bool tamed_rgb = pr.kind != 0;
+    const bool clahe = !tamed_rgb && pr.strategy == SARPRO_STRATEGY_CLAHE;
+    const double max_val = (tamed_rgb || pr.bit_depth == SARPRO_U8) ? 255.0 : 65535.0;
+    uint32_t q[kDnPerThread];
+    uint32_t mn = 65535u, mx = 0u;
+#pragma unroll 4
+    for (uint32_t k = 0; k < kDnPerThread; ++k) {
+        const uint32_t d = dn0 + k;
+        const uint32_t h = total[d];
+        uint32_t w = 0; // absent and invalid DNs keep word 0 (invalid pixels are written as 0, autoscale.rs:444, 653, 738)
+        if (h && db[d] > -50.0) {
+            const double v = db[d];
+            const double a = v < low ? low : v;           // v.max(low).min(high), autoscale.rs:440, 583, 649, 734
+            const double clipped = a > high ? high : a;
+            const double n = __ddiv_rn(__dsub_rn(clipped, low), range);
+            if (clahe) { // autoscale.rs:585-587 then the bin of :263 / :320
+                const double c = clampd_dev(n, 0.0, 1.0);
+                const double s = __dmul_rn(c, 255.0);
+                const double t = (double)(int)s;
+                double b = (__dsub_rn(s, t) >= 0.5) ? __dadd_rn(t, 1.0) : t; // f64::round for 0 <= s <= 255
+                long long bin = (b == b) ? (long long)b : 0;
+                if (bin < 0) bin = 0;
+                if (bin > 255) bin = 255;
+                w = (uint32_t)bin;
+            } else if (tamed_rgb) { // autoscale.rs:734-736
+                w = cast_u8_dev(clampd_dev(__dmul_rn(n, 255.0), 0.0, 255.0));
+            } else {                // autoscale.rs:649-651 with gamma == 1 (powf(x, 1) == x)
+                w = cast_u16_dev(clampd_dev(__dmul_rn(n, max_val), 0.0, max_val));
+            }
+            mn = min(mn, w);
+            mx = max(mx, w);
+        }
+        q[k] = w;
+    }
+    uint32_t pre_min = 0, pre_max = 0;
+    if (!clahe) {
+        if (have_invalid) { mn = 0; } // invalid pixels are samples of value 0
+        pre_min = block_reduce(mn, OpMinU32(), s_u32);
+        pre_max = block_reduce(mx, OpMaxU32(), s_u32);
+        if (!tamed_rgb && pr.bit_depth == SARPRO_U8) { // scale_u16_to_u8 over ALL pixels (autoscale.rs:352-363, :669-670, :691-693)
+            if (tid < 256) {
+                const float fmn = (float)pre_min, fmx = (float)pre_max;
+                const float scale = fmx > fmn ? __fdiv_rn(255.0f, __fsub_rn(fmx, fmn)) : 1.0f;
+                float val = roundf(__fmul_rn(__fsub_rn((float)tid, fmn), scale));
+                val = val < 0.0f ? 0.0f : (val > 255.0f ? 255.0f : val);
+                s_remap[tid] = (uint8_t)val;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (uint32_t k = 0; k < kDnPerThread; ++k) {
+                const uint32_t d = dn0 + k;
+                if (total[d] && db[d] > -50.0) q[k] = s_remap[q[k] > 255u ? 255u : q[k]];
+            }
+        }
+    }
+    // 64 consecutive u16 = 128 B per thread: eight 16-byte stores
+    uint4* lut4 = reinterpret_cast<uint4*>(lut + dn0);
+#pragma unroll
+    for (uint32_t k = 0; k < kDnPerThread; k += 8)
+        lut4[k / 8] = make_uint4(q[k] | (q[k + 1] << 16), q[k + 2] | (q[k + 3] << 16), q[k + 4] | (q[k + 5] << 16), q[k + 6] | (q[k + 7] << 16));
+
+    // ---- table range of the tensor-core pass B (plan.cpp set_sat_from, api.cu hmma_hot_from_plan) -----------------------
+    // sat_from = the lowest valid present DN from which every valid present DN up to the brightest present one carries the
+    // brightest one's table word (low byte).
+    uint32_t top_word;
+    {
+        if (tid == max_present_dn / kDnPerThread) s_u32[0] = q[max_present_dn % kDnPerThread] & 255u;
+        __syncthreads();
+        top_word = s_u32[0];
+        __syncthreads();
+    }
+    int last_nontop = -1;
+    for (uint32_t k = 0; k < kDnPerThread; ++k) {
+        const uint32_t d = dn0 + k;
+        if (total[d] && db[d] > -50.0 && d <= max_present_dn && (q[k] & 255u) != top_word) last_nontop = (int)d;
+    }
+    last_nontop = block_reduce(last_nontop, OpMaxI32(), s_i32);
+    uint32_t first_after = 0xffffffffu;
+    for (uint32_t k = 0; k < kDnPerThread; ++k) {
+        const uint32_t d = dn0 + k;
+        if (total[d] && db[d] > -50.0 && (int)d > last_nontop && first_after == 0xffffffffu) first_after = d;
+    }
+    first_after = block_reduce(first_after, OpMinU32(), s_u32);
+    if (tid == 0) {
+        uint32_t h = first_after == 0xffffffffu ? max_present_dn : first_after;
+        if (last_nontop < 0 && have_invalid && top_word == 0) h = 0; // invalid DNs are present with word 0
+        const uint32_t need = max(64u, (h + 1u + 7u) & ~7u);
+        PlanDev p{};
+        p.any_valid = 1;
+        p.have_invalid = have_invalid;
+        p.max_present_dn = max_present_dn;
+        p.sat_from_dn = h;
+        p.hot = need <= kHmmaMaxHot ? need : 0u;
+        p.hot_top = top_word;
+        p.use_generic = p.hot == 0;
+        p.clahe = clahe;
+        p.pre_min = pre_min;
+        p.pre_max = pre_max;
+        p.px_total = px_total;
+        p.px_ge1024 = px_ge1024;
+        p.px_ge2048 = px_ge2048;
+        sarpro_stats& st = p.stats;
+        st.valid_count = count;
+        st.min_db = min_db;
+        st.max_db = max_db;
+        st.mean_db = mean_db;
+        st.std_db = std_db;
+        st.median_db = med;
+        st.p01 = p01; st.p02 = p02; st.p05 = p05; st.p10 = p10; st.p25 = p25;
+        st.p75 = p75; st.p90 = p90; st.p95 = p95; st.p98 = p98; st.p99 = p99;
+        st.low_clip = low;
+        st.high_clip = high;
+        st.gamma = 1.0;
+        *out = p;
+    }
+}
+
+bool plan_on_device_supported(int strategy, int kind) {
+    if (kind != 0) return true; // Tamed-synRGB windows (autoscale.rs:721-727)
+    return strategy == SARPRO_STRATEGY_ROBUST || strategy == SARPRO_STRATEGY_EQUALIZED || strategy == SARPRO_STRATEGY_CLAHE ||
+           strategy == SARPRO_STRATEGY_TAMED || strategy == SARPRO_STRATEGY_DEFAULT;
+}
+
+cudaError_t launch_plan_band(const uint32_t* total, const double* db_table, const PlanParams& pr, uint16_t* lut, PlanDev* out,
+                             cudaStream_t stream) {
+    k_plan_band<<<1, kPlanThreads, 0, stream>>>(total, db_table, pr, lut, out);
+    return cudaGetLastError();
+}
+
+} // namespace sarpro

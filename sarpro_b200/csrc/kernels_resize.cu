@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) k_hresize(HResizeArgs a, const HStrip* __
                                                  uint32_t rows_per_block) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (a.skip && *a.skip) return;
+    if (a.run_if && !*a.run_if) return;
     using Pix = typename std::conditional<PIX16, uint16_t, uint8_t>::type;
     const uint32_t tid = threadIdx.x, oxb = blockDim.x;
     const uint32_t ox = blockIdx.x * oxb + tid;
@@ -277,12 +278,7 @@ cudaError_t hresize_build_strips(const uint32_t* start_h, const uint32_t* size_h
 template <int SRC, bool PIX16>
 static cudaError_t launch_hresize_t(const HResizeArgs& a, const HStrip* strips_dev, uint32_t n_strips, uint32_t oxb,
                                     uint32_t rbw, uint32_t smem, int sm_count, cudaStream_t stream) {
-    static uint32_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_hresize<SRC, PIX16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_hresize<SRC, PIX16>), smem)) return e;
     // rows per block: enough blocks to fill the machine a few times over, multiple of the row group
     uint32_t target_blocks = (uint32_t)sm_count * 8;
     uint32_t yblocks = std::max(1u, target_blocks / std::max(1u, n_strips));

@@ -1,9 +1,27 @@
 // kernels_small.cu — synthetic RGB (synthetic_rgb.rs), polarization algebra (ops.rs) and the
 // f32 -> DN bridge for rasters that were read from u16 TIFFs as f32 (gdal.rs:123).
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace sarpro {
+
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> configured; // (device, kernel) -> opted-in bytes
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = configured[std::make_pair(dev, func)];
+    if (bytes <= have) return cudaSuccess;
+    if (cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) return e;
+    have = bytes;
+    return cudaSuccess;
+}
 
 // ---------------------------------------------------------------------------------------------
 // synthetic_rgb.rs:92-98 — combined 256-bin histogram of both (resized + padded) bands

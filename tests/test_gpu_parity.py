@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
 Integer outputs must be bit-exact; percentiles / window f64 bit-exact; mean/std within 1e-9 (the
 reference's serial Welford rounding is order-dependent and is not reproducible from histograms)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -185,19 +187,19 @@ def test_f32_edge_cases(ctx):
 @pytest.mark.parametrize("shape,target", [((3001, 4999), 1024), ((2500, 9000), 700), ((5003, 2001), 512), ((3001, 5000), 1024),
                                           ((1031, 2048), 300), ((517, 25000), 2048), ((2100, 4096), 2048)])
 def test_production_kernels_match_exact_kernels(strategy, shape, target, monkeypatch):
-    """The production pass-B kernels against the generic exact kernels (SARPRO_FORCE_EXACT=1, the ones the other tests
-    pin to the oracle) on rasters large enough for several strips, CLAHE cells and row groups: the tensor-core kernel
+    """The production pass-B kernel against the generic exact kernels (SARPRO_FORCE_EXACT=1, the ones the other tests pin
+    to the oracle) on rasters large enough for several strips, CLAHE cells and row groups: the tensor-core kernel
     (kernels_hmma.cu: IMMA taps, fp32 bilinear form with truncation-bit risk test, warp-cooperative exact fix-up, marker
-    fix-up of saturated bins in the border cells; used when the column count is a multiple of 8), the second-generation
-    kernels (SARPRO_HMMA=0, kernels_hpipe.cu) and the first production kernel (SARPRO_HPIPE=0). Bright point targets
-    exercise the clamped table range, the zeroed block the invalid-pixel entry."""
+    fix-up of saturated bins in the border cells; used when the column count is a multiple of 8) and the generic kernel with
+    the fast per-pixel tables (SARPRO_HMMA=0). Bright point targets exercise the clamped table range, the zeroed block the
+    invalid-pixel entry."""
     from sarpro_b200.synth import synth_pair
     vv, vh = synth_pair(*shape, point_targets=1e-4)
     vv[shape[0] // 2:, -300:] = 0  # invalid block on the right edge
     outs = []
-    envs = ({"SARPRO_FORCE_EXACT": "1"}, {"SARPRO_HMMA": "0", "SARPRO_HPIPE": "0"}, {"SARPRO_HMMA": "0"}, {})
+    envs = ({"SARPRO_FORCE_EXACT": "1"}, {"SARPRO_HMMA": "0"}, {})
     for env in envs:
-        for k in ("SARPRO_FORCE_EXACT", "SARPRO_HPIPE", "SARPRO_HMMA"):
+        for k in ("SARPRO_FORCE_EXACT", "SARPRO_HMMA"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -222,41 +224,109 @@ def test_tensor_core_pass_b_against_oracle(ctx):
     assert np.array_equal(img.rgb, ref), int((img.rgb != ref).sum())
 
 
-def test_full_size_scene_cross_kernels(monkeypatch):
-    """BASELINE's full size (25,000 x 16,000 per band, the C3 scene of bench.py): the production path (tensor-core pass B,
-    second band on the side stream) must give the same RGB bytes as the second-generation kernels on one stream, for CLAHE
-    and for a LUT strategy, and repeated calls on one context must be identical (no state leaks between calls)."""
+@pytest.mark.parametrize("strategy", [S.CLAHE, S.ROBUST])
+def test_full_size_scene_against_oracle(strategy):
+    """BASELINE's full size (25,000 x 16,000 per band, the C3 / C2 scene of bench.py) through the production path (tensor-core
+    pass B, second band on the side stream) against the CPU oracle on the very same rasters: the 2048 x 2048 synRGB must be
+    byte-identical. Also: a different call in between and a repeat on the same context give the same bytes (no state leaks
+    between calls). The oracle takes about a minute per strategy on the GPU box's host."""
     import torch
     from sarpro_b200.synth import SEED_VH, SEED_VV, synth_band_torch
     dev = torch.device("cuda:0")
     vv = synth_band_torch(16000, 25000, SEED_VV, dev)
     vh = synth_band_torch(16000, 25000, SEED_VH, dev, cross_pol=True)
     torch.cuda.synchronize(dev)  # the library works on its own stream: the generators (torch's stream) must have finished
-    outs = {}
-    for name, env in (("old", {"SARPRO_HMMA": "0", "SARPRO_TWO_STREAM": "0"}), ("new", {})):
-        for k in ("SARPRO_HMMA", "SARPRO_TWO_STREAM", "SARPRO_HPIPE", "SARPRO_FORCE_EXACT"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        with S.Context(0) as c:
-            for strategy in (S.CLAHE, S.ROBUST):
-                out = torch.empty((2048, 2048, 3), dtype=torch.uint8, device=dev)
-                c.process_synrgb_jpeg(vv, vh, strategy, 2048, True, out=out)
-                outs[(name, strategy, 1)] = out.cpu().numpy().copy()
-                c.process_synrgb_jpeg(vh, vv, strategy, 2048, True, out=out)  # different call in between
-                c.process_synrgb_jpeg(vv, vh, strategy, 2048, True, out=out)
-                outs[(name, strategy, 3)] = out.cpu().numpy().copy()
-    for strategy in (S.CLAHE, S.ROBUST):
-        ref = outs[("new", strategy, 1)]
-        assert ref.shape == (2048, 2048, 3) and ref[(2048 - 1311) // 2 + 5:-(2048 - 1311) // 2 - 5].any()
-        bad = {}
-        for k, v in outs.items():
-            if k[1] == strategy and not np.array_equal(v, ref):
-                d = v != ref
-                ys, xs = np.nonzero(d.any(axis=2))
-                bad[k] = (int(d.sum()), [int(d[..., ch].sum()) for ch in range(3)], int(ys.min()), int(ys.max()), int(xs.min()), int(xs.max()),
-                          int(np.abs(v.astype(int) - ref.astype(int)).max()))
-        assert not bad, bad
+    with S.Context(0) as c:
+        out = torch.empty((2048, 2048, 3), dtype=torch.uint8, device=dev)
+        c.process_synrgb_jpeg(vv, vh, strategy, 2048, True, out=out)
+        first = out.cpu().numpy().copy()
+        c.process_synrgb_jpeg(vh, vv, strategy, 2048, True, out=out)  # different call in between
+        c.process_synrgb_jpeg(vv, vh, strategy, 2048, True, out=out)
+        again = out.cpu().numpy().copy()
+    assert np.array_equal(first, again)
+    assert first[(2048 - 1311) // 2 + 5:-(2048 - 1311) // 2 - 5].any()
+    vv_h = vv.cpu().numpy().view(np.uint16)
+    vh_h = vh.cpu().numpy().view(np.uint16)
+    del vv, vh, out
+    torch.cuda.empty_cache()
+    O.set_resize_threads(os.cpu_count() or 1)  # (the oracle's Lanczos stage may use threads like the crate's rayon feature; same result)
+    ref, _ = O.pipeline_synrgb_jpeg(vv_h.astype(np.float32), vh_h.astype(np.float32), strategy, 2048, True)
+    d = first != ref
+    assert not d.any(), (int(d.sum()), [int(d[..., ch].sum()) for ch in range(3)],
+                         int(np.abs(first.astype(int) - ref.astype(int)).max()))
+
+
+def _oracle_tamed(dn, is_copol):
+    db, mask = O.process_scalar_data_inplace(dn.astype(np.float32))
+    return O.autoscale_db_image_tamed_synrgb_u8(db, mask, is_copol)
+
+
+def test_autoscale_tamed_synrgb_u8_stage(ctx):
+    """autoscale.rs:710-742 through its own stage entry point (sarpro_autoscale_tamed_synrgb_u8), co- and cross-pol, on every
+    fixture and on a raster of more than 64 K pixels; no scale_u16_to_u8 re-stretch on this path."""
+    for case in sorted(CASES):
+        dn = CASES[case](203, 317)
+        for is_copol in (True, False):
+            ref = _oracle_tamed(dn, is_copol)
+            got = ctx.autoscale_db_image_tamed_synrgb_u8(dn.astype(np.float32), is_copol)
+            assert np.array_equal(got, ref), (case, is_copol, int((got != ref).sum()))
+    dn = CASES["speckle"](1100, 1900)
+    for is_copol in (True, False):
+        ref = _oracle_tamed(dn, is_copol)
+        got = ctx.autoscale_db_image_tamed_synrgb_u8(dn.astype(np.float32), is_copol)
+        assert np.array_equal(got, ref), (is_copol, int((got != ref).sum()))
+
+
+def test_process_scalar_data_inplace_large(ctx):
+    """pipeline.rs:8-40 on a raster well beyond 64 K pixels: mask exact, dB within 1e-12 relative (contract 1e-5)."""
+    rng = np.random.default_rng(11)
+    a = rng.gamma(2.0, 100.0, (1500, 2100)).astype(np.float32)
+    a[::17, ::13] = 0
+    a[5, :100] = -1.0
+    a[6, :100] = np.float32(9.9e-6)   # just below the validity threshold
+    a[7, :100] = np.float32(1.01e-5)  # just above it
+    db, mask = ctx.process_scalar_data_inplace(a)
+    dbo, masko = O.process_scalar_data_inplace(a)
+    assert np.array_equal(mask, masko)
+    assert np.allclose(db, dbo, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("strategy", [S.CLAHE, S.EQUALIZED])
+def test_u16_resized_output_above_4mp(ctx, strategy):
+    """U16 bit depth with a resize target that leaves more than 4 MP: the generic horizontal kernel with u16 samples (i32
+    taps, i64 accumulate) and the u16 vertical pass, single band and multiband TIFF."""
+    vv = CASES["speckle"](3000, 4400)
+    vh = CASES["speckle_vh"](3000, 4400)
+    ref, meta = O.pipeline_single(vv.astype(np.float32), O.TIFF, S.U16, strategy, 2600, True)
+    img = ctx.process_single(vv, S.TIFF, S.U16, strategy, 2600, True)
+    assert img.gray16.shape == ref.shape and ref.size > 4_000_000
+    assert np.array_equal(img.gray16, ref), int((img.gray16 != ref).sum())
+    r1, r2, _ = O.pipeline_multiband_tiff(vv.astype(np.float32), vh.astype(np.float32), S.U16, strategy, 2600, False)
+    mb = ctx.process_multiband_tiff(vv, vh, S.U16, strategy, 2600, False)
+    assert np.array_equal(mb.gray16, r1) and np.array_equal(mb.gray16_band2, r2)
+
+
+def test_axis_cache_survives_many_shapes():
+    """More than 64 distinct resize shapes on one context (the axis-plan cache is bounded and is only emptied between
+    calls): every result still matches the oracle."""
+    rng = np.random.default_rng(3)
+    with S.Context(0) as c:
+        for i in range(40):  # two axes per call
+            rows, cols = 60 + 3 * i, 90 + 5 * i
+            data = rng.integers(0, 256, (rows, cols)).astype(np.uint8)
+            ref, _ = O.resize_image_data_with_meta(data, 40 + i, S.U8, True)
+            got, _ = c.resize_image_data_with_meta(data, 40 + i, S.U8, True)
+            assert np.array_equal(got, ref), i
+
+
+def test_enum_arguments_are_validated(ctx):
+    dn = CASES["speckle"](64, 80)
+    with pytest.raises(S.SarproError):
+        ctx.process_single(dn.astype(np.float32), S.TIFF, S.U8, S.ROBUST, None, False, op=5, band2=dn.astype(np.float32))
+    with pytest.raises(S.SarproError):
+        ctx.process_scalar_data_pipeline(dn, S.U8, 7)
+    with pytest.raises(S.SarproError):
+        ctx.process_scalar_data_pipeline(dn, 2, S.ROBUST)
 
 
 @pytest.mark.parametrize("strategy,name", [(S.CLAHE, "clahe"), (S.ROBUST, "robust"), (S.TAMED, "tamed")])
@@ -294,3 +364,65 @@ def test_present_list_planner_matches_dense_planner(strategy, monkeypatch):
         assert np.array_equal(got[""][0], po.u8)
         for k in ("valid_count", "min_db", "max_db", "mean_db", "std_db", "median_db", "p01", "p99", "low_clip", "high_clip", "gamma"):
             assert getattr(got[""][1], k) == getattr(got["1"][1], k), k
+
+
+# ---- the device planner (kernels_plan.cu) against the host planner (plan.cpp) -------------------------------------------
+_DEV_PLAN_CASES = [(S.ROBUST, 0), (S.EQUALIZED, 0), (S.CLAHE, 0), (S.TAMED, 0), (S.DEFAULT, 0), (S.TAMED, 1), (S.TAMED, 2)]
+
+
+def _fixture_histograms():
+    from sarpro_b200.synth import synth_band
+    rng = np.random.default_rng(17)
+    hists = {}
+    for case in sorted(CASES):
+        hists[case] = np.bincount(CASES[case](203, 317).ravel(), minlength=65536)
+    hists["grd"] = np.bincount(synth_band(900, 1400, 3, block=16, point_targets=1e-4).ravel(), minlength=65536)
+    hists["every_dn"] = np.bincount(rng.integers(0, 65536, size=700 * 900, dtype=np.uint16), minlength=65536)
+    hists["no_valid"] = np.bincount(np.zeros(1000, np.uint16), minlength=65536)
+    one = np.zeros(65536, np.int64)
+    one[777] = 12345
+    hists["single_dn"] = one
+    big = np.zeros(65536, np.int64)   # counts beyond 2^31 in total: 64-bit prefix sums
+    big[100:4000] = 1_000_000
+    big[0] = 5
+    hists["four_billion"] = big
+    return hists
+
+
+@pytest.mark.parametrize("strategy,kind", _DEV_PLAN_CASES)
+@pytest.mark.parametrize("bit_depth", [S.U8, S.U16])
+def test_device_planner_matches_host_planner(ctx, strategy, kind, bit_depth):
+    """Every percentile, the window, the whole DN -> sample / bin table and the table range of the tensor-core pass B are
+    bit-identical between the single-CTA device planner and the host planner; mean / std agree to 1e-12 (the host sums in
+    long double, the device in f64 trees; neither is the reference's serial Welford)."""
+    for name, hist in _fixture_histograms().items():
+        st_h, lut_h, hot_h = S.plan_kind_from_dn_histogram(hist, bit_depth, strategy, kind)
+        st_d, lut_d, hot_d = ctx.plan_on_device(hist, bit_depth, strategy, kind)
+        for k in EXACT_STATS:
+            assert getattr(st_d, k) == getattr(st_h, k), (name, k, getattr(st_d, k), getattr(st_h, k))
+        assert abs(st_d.mean_db - st_h.mean_db) <= 1e-12 * max(1.0, abs(st_h.mean_db)), name
+        assert abs(st_d.std_db - st_h.std_db) <= 1e-12 * max(1.0, abs(st_h.std_db)), name
+        assert np.array_equal(lut_d, lut_h), (name, int((lut_d != lut_h).sum()))
+        if st_h.valid_count:
+            assert hot_d == hot_h, (name, hot_d, hot_h)
+
+
+@pytest.mark.parametrize("strategy", [S.CLAHE, S.ROBUST, S.TAMED])
+def test_device_plan_and_host_plan_give_the_same_image(strategy, monkeypatch):
+    """SARPRO_HOST_PLAN=1 (every band planned on the host, two round trips) against the default (planned on the device, none):
+    same bytes, same statistics, and the default path reports zero host synchronisations."""
+    from sarpro_b200.synth import synth_pair
+    vv, vh = synth_pair(1211, 2048, point_targets=1e-4)
+    got = {}
+    for host_plan in ("", "1"):
+        monkeypatch.delenv("SARPRO_HOST_PLAN", raising=False)
+        if host_plan:
+            monkeypatch.setenv("SARPRO_HOST_PLAN", "1")
+        with S.Context(0) as c:
+            img = c.process_synrgb_jpeg(vv, vh, strategy, 640, True)
+            got[host_plan] = (img.rgb.copy(), img.stats, c.timing().host_syncs)
+    assert np.array_equal(got[""][0], got["1"][0])
+    assert got[""][2] == 0 and got["1"][2] >= 2
+    for a, b in zip(got[""][1], got["1"][1]):
+        for k in EXACT_STATS:
+            assert getattr(a, k) == getattr(b, k), k
