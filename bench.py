@@ -1,26 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the raster hot path (BASELINE.json metric).
+"""bench.py — headline benchmark of the raster hot path (BASELINE.json metric), one JSON line per run.
 
-Metric: Mpixel/s of the ~400 MP dual-pol synRGB + CLAHE pipeline (25,000 x 16,000 u16 per band ->
-CLAHE autoscale -> Lanczos3 to 2048 px long side -> pad to square -> suppressed synthetic RGB),
-scene pixels (the pair counted once) per second. One "step" = one pass of that pipeline over one
-synthetic scene.
+Metric: Mpixel/s of the ~400 MP dual-pol synRGB + CLAHE pipeline (25,000 x 16,000 u16 per band -> CLAHE autoscale ->
+Lanczos3 to 2048 px long side -> pad to square -> suppressed synthetic RGB), scene pixels (the pair counted once) per
+second. One "step" = one pass of that pipeline over one synthetic scene.
 
-  value   whole-job Mpixel/s with the two bands already resident in HBM (device pointers through the
-          C ABI), timed with CUDA events on the stream the library launches on, max over ranks.
-  e2e     the same call with HOST (pinned) u16 bands and a host RGB result: H2D + kernels + D2H.
-  roofline  the dominant kernel of the step (pass B: CLAHE apply fused with the horizontal Lanczos),
-          algorithmic bytes / its mean CUDA-event duration inside the timed region, vs MEASURED_PEAKS.
-  cpu_baseline  the CPU oracle (a C++ restatement of the reference's serial path) on a bounded crop of
-          the same scene, on this box's host cores.
+  value   whole-job Mpixel/s with the bands already resident in HBM (device pointers through the C ABI), timed with CUDA
+          events on the stream the library launches on, max over ranks.
+  e2e     the same call with HOST (pinned) u16 bands and a host RGB result: H2D + kernels + D2H inside the timed region.
+  roofline  the dominant kernel of the step (pass B: CLAHE apply fused with the horizontal Lanczos pass), algorithmic bytes /
+          its mean CUDA-event duration inside the timed region, vs MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (a C++ restatement of the reference's serial path) on a bounded crop of the same scene.
 
-N > 1 (torchrun, one rank per GPU): `value` / `e2e` are the batch mode of BASELINE config 5 — one whole scene per rank per
-step, no collective on the data path ("weak" scaling: per-GPU work fixed). The same run also times ONE scene
-row-band-sharded over the ranks (config 3: every rank holds its band plus the Lanczos halo, the library all-reduces the
-integer DN / CLAHE-tile histograms, the CLAHE min/max and the resized rows over NCCL; "strong" scaling, result bit-identical
-to 1 GPU) and reports it under "sharded_mode".
-`--impl reference` times the oracle (the reference cannot be built here: no Rust toolchain) on a
-bounded sample with all host threads its threaded stage (the Lanczos resize) can use.
+--config selects the BASELINE.json configuration (default c3, the one the metric is quoted on):
+  c1  VV 4096 x 4096 -> Standard -> u8 gray, no resize (the reference's CPU-runnable case)
+  c2  as c3 with Robust autoscale (default synRGB map)
+  c3  dual-pol 25,000 x 16,000 -> CLAHE -> 2048 px + pad -> suppressed synRGB
+  c4  full-resolution log-ratio and n-diff of the pair -> Equalized -> two u16 bands, no downsample
+  c5  batch of scenes -> 1024 px padded multiband u8 tiles (reference defaults, params.rs:33), scenes distributed over the GPUs
+
+N > 1 (torchrun, one rank per GPU). c3 / c2: `value` is ONE scene row-band-sharded over the ranks ("strong" scaling: every
+rank holds its band plus the Lanczos halo; integer histogram / CLAHE-tile all-reduces and a broadcast of the owned output rows
+inside the library; the result is compared byte for byte with the single-GPU result of the same scene in this run —
+"parity_ok"; the line is not printed if that fails). The scenes-per-GPU replicas (config 5's distribution, no collective on the
+data path) are reported under "batch_mode". c1: independent replicas. c4: the pair row-sharded. c5: scenes distributed.
+
+`--impl reference` times the oracle (the reference cannot be built here: no Rust toolchain) on a bounded sample with all host
+threads its threaded stage (the Lanczos resize) can use.
 """
 from __future__ import annotations
 
@@ -94,42 +100,69 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(vv_crop, vh_crop, threads):
-    """Oracle (reference restatement) on a crop: save.rs:317-368 order, CLAHE, 2048-proportional target."""
+# ------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (reference restatement) on a bounded sample
+# ------------------------------------------------------------------------------------------------------------------------
+def cpu_sample(cfg, vv_crop, vh_crop, threads, full_cols):
+    """One pass of config `cfg` of the oracle on a crop; returns (Mpixel/s, seconds, note)."""
     import numpy as np
     from oracle import pyoracle as O
     O.set_resize_threads(threads)
     rows, cols = vv_crop.shape
-    target = max(64, int(round(TARGET * cols / COLS)))
     a = vv_crop.astype(np.float32)
-    b = vh_crop.astype(np.float32)
+    b = vh_crop.astype(np.float32) if vh_crop is not None else None
     t0 = time.perf_counter()
-    O.pipeline_synrgb_jpeg(a, b, O.CLAHE, target, True)
+    if cfg == "c1":
+        O.pipeline_single(a, O.TIFF, O.U8, O.STANDARD, None, False)
+        note = "Standard -> u8, no resize"
+    elif cfg == "c4":
+        for op in (O.OP_LOGRATIO, O.OP_NDIFF):
+            O.pipeline_single(O.pol_op(op, a, b), O.TIFF, O.U16, O.EQUALIZED, None, False)
+        note = "log-ratio + n-diff -> Equalized -> u16, no resize"
+    elif cfg == "c5":
+        target = max(64, int(round(1024 * cols / full_cols)))
+        O.pipeline_multiband_tiff(a, b, O.U8, O.CLAHE, target, True)
+        note = f"CLAHE -> {target}px + pad multiband u8"
+    else:
+        target = max(64, int(round(TARGET * cols / full_cols)))
+        O.pipeline_synrgb_jpeg(a, b, O.ROBUST if cfg == "c2" else O.CLAHE, target, True)
+        note = f"synRGB+{'Robust' if cfg == 'c2' else 'CLAHE'} -> {target}px + pad"
     dt = time.perf_counter() - t0
-    return rows * cols / dt / 1e6, dt, target
+    return rows * cols / dt / 1e6, dt, note
+
+
+WORKLOADS = {
+    "c1": "C1: single-band VV 4096x4096 u16 -> dB -> Standard autoscale -> u8 gray (no resize)",
+    "c2": "C2: dual-pol VV+VH {cols}x{rows} u16 GRD-like -> Robust autoscale -> Lanczos3 2048px + pad -> synRGB",
+    "c3": "C3: dual-pol VV+VH {cols}x{rows} u16 GRD-like -> CLAHE autoscale -> Lanczos3 2048px + pad -> synRGB",
+    "c4": "C4: full-resolution log-ratio and n-diff of VV/VH {cols}x{rows} u16 -> Equalized autoscale -> two u16 bands (no downsample)",
+    "c5": "C5: batch of dual-pol {cols}x{rows} scenes -> CLAHE -> 1024px padded multiband u8 tiles, scenes distributed over the GPUs",
+}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    import numpy as np
     from sarpro_b200.synth import synth_pair
     cores = os.cpu_count() or 1
-    rows, cols = 4000, 6250  # 1/16 of the full scene: 25 MP per band
+    cfg = args.config
+    rows, cols = (2048, 2048) if cfg == "c1" else (4000, 6250)  # 1/4 of C1; 1/16 of the full scene: 25 MP per band
+    full_cols = 4096 if cfg == "c1" else COLS
     vv, vh = synth_pair(rows, cols)
     vals = []
+    note = ""
     for i in range(args.warmup + args.steps):
-        v, dt, target = cpu_sample(vv, vh, cores)
+        v, dt, note = cpu_sample(cfg, vv, None if cfg == "c1" else vh, cores, full_cols)
         if i >= args.warmup:
             vals.append((v, dt))
     mpx = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(d for _, d in vals) / len(vals)
-    sample = f"{rows}x{cols} crop per band (1/16 of the scene), synRGB+CLAHE -> {target}px + pad, per step"
+    sample = f"{rows}x{cols} crop per band, {note}, per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": round(mpx, 3), "unit": "Mpixel/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3 dual-pol 25000x16000 u16 -> CLAHE -> 2048px + pad -> synRGB (reference timed on a bounded crop)"},
+        "scaling": "strong" if (cfg in ("c2", "c3", "c4") and args.gpus > 1) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[cfg].format(rows=ROWS, cols=COLS) + " (reference timed on a bounded crop)"},
         "cpu_baseline": {"value": round(mpx, 3), "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "reference path is serial (SURVEY F1); only the Lanczos stage uses the threads"},
         "e2e": {"value": round(mpx, 3), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -137,16 +170,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=ROWS)
     ap.add_argument("--cols", type=int, default=COLS)
-    ap.add_argument("--strategy", default="clahe")
+    ap.add_argument("--scenes", type=int, default=0, help="c5: scenes in the batch (default 8 per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-load-window", action="store_true", help="skip the ~1 s of untimed steps around the timed region (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -164,20 +200,20 @@ def main():
     import sarpro_b200 as S
     from sarpro_b200.synth import SEED_VH, SEED_VV, synth_band_torch
 
+    cfg = args.config
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    rows, cols = args.rows, args.cols
-    strategy = S.STRATEGY_NAMES.index(args.strategy)
+    rows, cols = (4096, 4096) if cfg == "c1" else (args.rows, args.cols)
+    strategy = {"c1": S.STANDARD, "c2": S.ROBUST, "c3": S.CLAHE, "c4": S.EQUALIZED, "c5": S.CLAHE}[cfg]
+    target = 1024 if cfg == "c5" else TARGET
 
-    sharded = world > 1
     ctx = S.Context(local_rank)
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
-    oc, orr = S.Context.resize_output_dims(cols, rows, TARGET, True)
-    out_dev = torch.empty((orr, oc, 3), dtype=torch.uint8, device=dev)
+    names = S._ffi.STAGE_NAMES
 
     def barrier():
         if world > 1:
@@ -188,169 +224,235 @@ def main():
         return (synth_band_torch(rows, cols, SEED_VV + 2 * scene, dev),
                 synth_band_torch(rows, cols, SEED_VH + 2 * scene, dev, cross_pol=True))
 
+    def pinned_u16(t):
+        h = torch.empty(tuple(t.shape), dtype=torch.int16).pin_memory()
+        h.copy_(t)
+        return h.numpy().view(np.uint16)
+
     def timed(fn, steps, warmup):
         """K steps of fn() between barriers; CUDA events on the library's stream; max over ranks."""
         for _ in range(warmup):
             fn()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        acc = {"stage_ms": [0.0] * 8, "stage_n": [0] * 8, "launches": 0, "syncs": 0, "h2d": 0, "d2h": 0}
-        w0 = time.time()
+        acc = {"stage_ms": [0.0] * 8, "stage_n": [0] * 8, "launches": 0, "syncs": 0}
         ev0.record(stream)
         for _ in range(steps):
             fn()
             t = ctx.timing()
             acc["launches"] += t.kernel_launches
             acc["syncs"] += t.host_syncs
-            acc["h2d"], acc["d2h"] = int(t.h2d_bytes), int(t.d2h_bytes)
             for i in range(8):
                 acc["stage_ms"][i] += t.stage_ms[i]
                 acc["stage_n"][i] += t.stage_launches[i]
         ev1.record(stream)
         barrier()
-        w1 = time.time()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
             tt = torch.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
-        return ms / steps, acc, (w0, w1)
+        return ms / steps, acc
 
-    sampler = ClockSampler(local_rank)
-    # Primary leg at every N: one whole scene per rank (BASELINE config 5 at N > 1: scenes distributed over the GPUs, no
-    # collective on the data path) -> "weak" scaling, value = all ranks' scene pixels / max-over-ranks time.
-    vv, vh = make_scene(rank)
-    torch.cuda.synchronize(dev)  # generated on torch's current stream; the library reads them on `stream`
-    h0, h1 = 0, rows
-    step = lambda: ctx.process_synrgb_jpeg(vv, vh, strategy, TARGET, True, out=out_dev)
-
-    # ---------------- kernel-only leg: inputs resident in HBM ---------------------------------
-    # The timed region is short (K steps of ~2 ms) against nvidia-smi's 100 ms sampling period, so the same step keeps
-    # running untimed for ~0.7 s before and ~0.5 s after it: the clock samples are taken under the load that is timed, the
-    # timed region in the middle of it. (Every rank runs the same number of load steps.)
-    for _ in range(args.warmup):
-        step()
-    if rank == 0:
-        sampler.start()
-    load0 = time.time()
-    for _ in range(400):
-        step()
-    ms_per_step, acc, (wall0, wall1) = timed(step, args.steps, 0)
-    for _ in range(300):
-        step()
-    clocks = sampler.stop(load0 + 0.25, time.time()) if rank == 0 else None
-    if clocks is not None:
-        clocks["window"] = "same step looped for %.1f s around the timed region" % (time.time() - load0)
-    value = world * rows * cols / (ms_per_step * 1e-3) / 1e6   # one scene per rank per step
-    stage_ms, stage_n, launches, syncs = acc["stage_ms"], acc["stage_n"], acc["launches"], acc["syncs"]
-
-    # Secondary leg (N > 1): ONE scene row-band-sharded over the ranks (BASELINE config 3), "strong" scaling: every rank
-    # holds its band + the Lanczos halo; the library all-reduces the DN / CLAHE-tile histograms, the CLAHE min/max and the
-    # resized rows over NCCL; the result is bit-identical to 1 GPU.
-    shard = None
-    if sharded:
-        uid = [S.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0], rank, world)
-        svv, svh = (vv, vh) if rank == 0 else make_scene(0)   # every rank synthesises the same scene and keeps its rows
-        torch.cuda.synchronize(dev)
-        sh0, sh1 = S.shard_halo_rows(rows, cols, TARGET, world, rank, strategy == S.CLAHE)
-        pvv, pvh = svv[sh0:sh1], svh[sh0:sh1]                 # contiguous row slices (views)
-        sstep = lambda: ctx.process_synrgb_sharded(pvv, pvh, rows, strategy, TARGET, True, out=out_dev)
-        sms, sacc, _ = timed(sstep, args.steps, args.warmup)
-        ph_vv = torch.empty((sh1 - sh0, cols), dtype=torch.int16).pin_memory()
-        ph_vh = torch.empty((sh1 - sh0, cols), dtype=torch.int16).pin_memory()
-        ph_vv.copy_(pvv)
-        ph_vh.copy_(pvh)
-        out_hs = torch.empty((orr, oc, 3), dtype=torch.uint8).pin_memory().numpy()
-        sest = lambda: ctx.process_synrgb_sharded(ph_vv.numpy().view(np.uint16), ph_vh.numpy().view(np.uint16), rows, strategy, TARGET,
-                                                  True, out=out_hs)
-        sest()
+    def timed_e2e(fn, steps):
+        """Wall clock of `steps` calls with host buffers (H2D + kernels + D2H, the call returns after its last copy), max over ranks."""
+        fn()  # warm-up (allocations)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(3):
-            sest()
+        h2d = d2h = 0
+        for _ in range(steps):
+            fn()
+            t = ctx.timing()
+            h2d, d2h = int(t.h2d_bytes), int(t.d2h_bytes)
         barrier()
-        se2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / 3], device=dev, dtype=torch.float64)
-        dist.all_reduce(se2e, op=dist.ReduceOp.MAX)
-        shard = {"value": round(rows * cols / (sms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "ms_per_step": round(sms, 4), "scaling": "strong",
-                 "e2e_ms_per_step": round(float(se2e.item()), 3), "e2e_value": round(rows * cols / (float(se2e.item()) * 1e-3) / 1e6, 1),
-                 "stage_ms_per_step": {S._ffi.STAGE_NAMES[i]: round(sacc["stage_ms"][i] / args.steps, 4) for i in range(8) if sacc["stage_n"][i]},
-                 "parallelism": f"ONE scene row-band-sharded over {world} GPUs; NCCL all-reduce of DN / CLAHE-tile histograms, min/max, resized rows; "
-                                "bit-identical to 1 GPU"}
-        del pvv, pvh, svv, svh, ph_vv, ph_vh
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        if world > 1:
+            tt = torch.tensor([ms, float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+            mx = tt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            ms, h2d, d2h = float(mx[0].item()), int(tt[1].item()), int(tt[2].item())
+        return ms, h2d, d2h
 
-    # ---------------- end-to-end leg: host buffers through the C ABI ----------------------------
+    def with_load_window(step, steps):
+        """The timed region is short (K steps of ~1 ms) against nvidia-smi's 100 ms sampling period, so the same step keeps
+        running untimed for ~0.7 s before and ~0.5 s after it: the clock samples are taken under the load that is timed."""
+        sampler = ClockSampler(local_rank)
+        for _ in range(args.warmup):
+            step()
+        if rank == 0:
+            sampler.start()
+        load0 = time.time()
+        n_pre, n_post = (0, 0) if args.no_load_window else (400, 300)
+        for _ in range(n_pre):
+            step()
+        ms, acc = timed(step, steps, 0)
+        for _ in range(n_post):
+            step()
+        clocks = sampler.stop(load0 + 0.25, time.time()) if rank == 0 else None
+        if clocks is not None:
+            clocks["window"] = "same step looped for %.1f s around the timed region" % (time.time() - load0)
+        return ms, acc, clocks
+
+    peak, peak_src = load_peaks()
     e2e_steps = max(2, min(args.steps, 5))
-    lrows = h1 - h0
-    vv_h = torch.empty((lrows, cols), dtype=torch.int16).pin_memory()
-    vh_h = torch.empty((lrows, cols), dtype=torch.int16).pin_memory()
-    vv_h.copy_(vv)
-    vh_h.copy_(vh)
-    vv_np = vv_h.numpy().view(np.uint16)
-    vh_np = vh_h.numpy().view(np.uint16)
-    out_h = torch.empty((orr, oc, 3), dtype=torch.uint8).pin_memory().numpy()
-    estep = lambda: ctx.process_synrgb_jpeg(vv_np, vh_np, strategy, TARGET, True, out=out_h)
-    estep()  # warm-up (allocations)
-    barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    for _ in range(e2e_steps):
-        estep()
-        t = ctx.timing()
-        h2d, d2h = int(t.h2d_bytes), int(t.d2h_bytes)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    if world > 1:
-        tt = torch.tensor([e2e_ms, float(h2d), float(d2h)], device=dev, dtype=torch.float64)
-        mx = tt.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-        e2e_ms = float(mx[0].item())
-        h2d, d2h = int(tt[1].item()), int(tt[2].item())
-    e2e_value = world * rows * cols / (e2e_ms * 1e-3) / 1e6
+    line = None
 
-    if rank == 0:
-        peak, peak_src = load_peaks()
-        # dominant kernel: pass B (apply fused with horizontal Lanczos), one launch per band.
-        n_apply = max(stage_n[S._ffi.STAGE_NAMES.index("apply")], 1)
-        apply_ms = stage_ms[S._ffi.STAGE_NAMES.index("apply")] / n_apply
-        alg_bytes = (h1 - h0) * cols * 2 + (h1 - h0) * oc * 1  # read the held u16 DN rows once, write the h-resized u8 rows
-        achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at the full C3 size, from the
-        # ncu --set full capture summarised in profiles/ (same command line); None for other sizes
-        full_c3 = (rows, cols, args.strategy) == (ROWS, COLS, "clahe")
-        traffic = 871_000_000 if full_c3 else None  # profiles/r01q_ncu_full_hmma.md: 859.7 MB read + 11.3 MB written
-        roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "k_hmma<CLAHE> (pass B: CLAHE apply fused with the horizontal Lanczos pass on IMMA.16832)",
-                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,
-                    # what the same ncu capture names as the busiest unit of this kernel (a note, not a second roofline)
-                    "limiter": ("L1TEX LSU data pipe (shared-memory table gathers): l1tex__data_pipe_lsu_wavefronts 74 % of peak on "
-                                "average, 84 % on the busiest SM; DRAM 19 % (profiles/r01q_ncu_full_hmma.md)") if full_c3 else None,
-                    "stage_ms_per_step": {S._ffi.STAGE_NAMES[i]: round(stage_ms[i] / args.steps, 4) for i in range(8) if stage_n[i]}}
-        line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-            "scaling": "weak",
-            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": f"C3: dual-pol VV+VH {cols}x{rows} u16 GRD-like -> {args.strategy} autoscale -> Lanczos3 {TARGET}px "
-                                   f"+ pad -> synRGB" + (f"; one scene per GPU per step on {world} GPUs, no collective on the data path (config 5); the row-band-sharded single scene (config 3) is under sharded_mode" if sharded else "; one scene on one GPU"),
-                       "cache": "inputs (1.6 GB per scene) exceed the 126 MB L2; no flush needed",
-                       "scene_bytes": rows * cols * 4, "parallelism": f"scene-per-GPU x{world}" if sharded else "single GPU"},
-            "clocks": clocks, "gpu_launches": launches, "host_syncs_per_step": syncs / args.steps,
-            "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms, 3), "input": "pinned host u16 DN bands", "steps": e2e_steps},
-            "roofline": roofline,
-        }
-        if shard:
-            line["sharded_mode"] = shard
+    # ====================================================================================================================
+    if cfg in ("c2", "c3"):
+        oc, orr = S.Context.resize_output_dims(cols, rows, target, True)
+        out_dev = torch.empty((orr, oc, 3), dtype=torch.uint8, device=dev)
+        sharded = world > 1
+        # every rank synthesises scene 0 (same seeds -> the same bytes); a sharded rank only keeps its rows
+        vv, vh = make_scene(0)
+        torch.cuda.synchronize(dev)  # generated on torch's current stream; the library reads them on `stream`
+        single_step = lambda: ctx.process_synrgb_jpeg(vv, vh, strategy, target, True, out=out_dev)
+        parity_ok = None
+        if not sharded:
+            h0, h1 = 0, rows
+            step = single_step
+            ms_per_step, acc, clocks = with_load_window(step, args.steps)
+            vv_np, vh_np = pinned_u16(vv), pinned_u16(vh)
+            out_h = torch.empty((orr, oc, 3), dtype=torch.uint8).pin_memory().numpy()
+            e2e_ms, h2d, d2h = timed_e2e(lambda: ctx.process_synrgb_jpeg(vv_np, vh_np, strategy, target, True, out=out_h), e2e_steps)
+            batch = None
+        else:
+            uid = [S.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init(uid[0], rank, world)
+            # reference bytes for the parity check: the single-GPU pipeline on the whole scene (itself pinned to the oracle by
+            # tests/test_gpu_parity.py::test_full_size_scene_against_oracle)
+            single_step()
+            torch.cuda.synchronize(dev)
+            ref_rgb = out_dev.clone()
+            h0, h1 = S.shard_halo_rows(rows, cols, target, world, rank, strategy == S.CLAHE)
+            pvv, pvh = vv[h0:h1], vh[h0:h1]  # contiguous row slices (views)
+            step = lambda: ctx.process_synrgb_sharded(pvv, pvh, rows, strategy, target, True, out=out_dev)
+            out_dev.zero_()
+            step()
+            torch.cuda.synchronize(dev)
+            ok = torch.tensor([1 if torch.equal(out_dev, ref_rgb) else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            parity_ok = bool(int(ok.item()))
+            if not parity_ok:
+                if rank == 0:
+                    print(json.dumps({"error": "sharded result differs from the single-GPU result", "n_gpus": world}), file=sys.stderr, flush=True)
+                ctx.close()
+                dist.destroy_process_group()
+                sys.exit(1)
+            # batch mode (scenes per GPU, no collective on the data path): weak scaling, reported beside the headline
+            bms, bacc = timed(single_step, args.steps, args.warmup)
+            ms_per_step, acc, clocks = with_load_window(step, args.steps)
+            pvv_np, pvh_np = pinned_u16(pvv), pinned_u16(pvh)
+            out_h = torch.empty((orr, oc, 3), dtype=torch.uint8).pin_memory().numpy()
+            e2e_ms, h2d, d2h = timed_e2e(lambda: ctx.process_synrgb_sharded(pvv_np, pvh_np, rows, strategy, target, True, out=out_h), e2e_steps)
+            batch = {"value": round(world * rows * cols / (bms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "ms_per_step": round(bms, 4),
+                     "scaling": "weak", "parallelism": f"one whole scene per GPU per step on {world} GPUs, no collective on the data path",
+                     "host_syncs_per_step": bacc["syncs"] / args.steps}
+        value = rows * cols / (ms_per_step * 1e-3) / 1e6
+        e2e_value = rows * cols / (e2e_ms * 1e-3) / 1e6
+        if rank == 0:
+            stage_ms, stage_n = acc["stage_ms"], acc["stage_n"]
+            n_apply = max(stage_n[names.index("apply")], 1)
+            apply_ms = stage_ms[names.index("apply")] / n_apply
+            alg_bytes = (h1 - h0) * cols * 2 + (h1 - h0) * oc * 1  # read the held u16 DN rows once, write the h-resized u8 rows
+            achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
+            full = (rows, cols) == (ROWS, COLS) and world == 1
+            kname = "k_hmma<CLAHE>" if cfg == "c3" else "k_hmma<LUT>"
+            roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                        "traffic": (871_000_000 if cfg == "c3" else None) if full else None,  # profiles/r02_ncu_full_hmma.md
+                        "kernel": f"{kname} (pass B: per-pixel stage fused with the horizontal Lanczos pass on IMMA.16832), one launch per band",
+                        "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,
+                        "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 4) for i in range(8) if stage_n[i]}}
+            par = (f"ONE scene row-band-sharded over {world} GPUs (tile-row aligned bands + Lanczos halo); NCCL: fused all-reduce of both bands' DN "
+                   "histograms, of their CLAHE tile histograms, of the sample min/max, broadcast of the owned output rows; planned on the device") \
+                if sharded else "single GPU"
+            line = {
+                "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+                "scaling": "strong" if sharded else "weak",
+                "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+                "config": {"workload": WORKLOADS[cfg].format(rows=rows, cols=cols), "config": cfg,
+                           "cache": "inputs (1.6 GB per scene) exceed the 126 MB L2; no flush needed",
+                           "scene_bytes": rows * cols * 4, "parallelism": par},
+                "clocks": clocks, "gpu_launches": acc["launches"], "host_syncs_per_step": acc["syncs"] / args.steps,
+                "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": round(e2e_ms, 3), "input": "pinned host u16 DN bands" + (" (each rank its row band + halo)" if sharded else ""),
+                        "steps": e2e_steps},
+                "roofline": roofline,
+            }
+            if sharded:
+                line["parity_ok"] = parity_ok
+                line["batch_mode"] = batch
+        if not sharded and rank == 0 and (rows, cols) == (ROWS, COLS) and not args.no_cpu_baseline:
+            # the real drop-in boundary of the Rust caller: host Array2<f32> bands (gdal.rs:123) -> 2x the upload + the f32 -> DN bridge
+            vv_f = torch.empty((rows, cols), dtype=torch.float32).pin_memory()
+            vh_f = torch.empty((rows, cols), dtype=torch.float32).pin_memory()
+            vv_f.copy_(vv.to(torch.int32).bitwise_and_(0xffff))
+            vh_f.copy_(vh.to(torch.int32).bitwise_and_(0xffff))
+            f_ms, f_h2d, f_d2h = timed_e2e(lambda: ctx.process_synrgb_jpeg(vv_f.numpy(), vh_f.numpy(), strategy, target, True, out=out_h), 2)
+            line["e2e_f32_boundary"] = {"value": round(rows * cols / (f_ms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "ms_per_step": round(f_ms, 3),
+                                        "h2d_bytes_per_step": f_h2d, "d2h_bytes_per_step": f_d2h,
+                                        "input": "pinned host f32 bands (the reference's Array2<f32> boundary, gdal.rs:123)"}
+            del vv_f, vh_f
+
+    # ====================================================================================================================
+    elif cfg == "c1":
+        vv = synth_band_torch(rows, cols, SEED_VV + 2 * rank, dev)
+        torch.cuda.synchronize(dev)
+        out_dev = torch.empty((rows, cols), dtype=torch.uint8, device=dev)
+        step = lambda: ctx.process_single(vv, S.TIFF, S.U8, strategy, None, False, out=out_dev)
+        ms_per_step, acc, clocks = with_load_window(step, args.steps)
+        vv_np = pinned_u16(vv)
+        out_h = torch.empty((rows, cols), dtype=torch.uint8).pin_memory().numpy()
+        e2e_ms, h2d, d2h = timed_e2e(lambda: ctx.process_single(vv_np, S.TIFF, S.U8, strategy, None, False, out=out_h), e2e_steps)
+        value = world * rows * cols / (ms_per_step * 1e-3) / 1e6
+        if rank == 0:
+            stage_ms, stage_n = acc["stage_ms"], acc["stage_n"]
+            apply_ms = stage_ms[names.index("apply")] / max(stage_n[names.index("apply")], 1)
+            alg_bytes = rows * cols * 3  # k_apply_lut: read u16 DN, write u8
+            achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
+            line = {
+                "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOADS[cfg], "config": cfg,
+                           "cache": "the 33.5 MB raster fits the 126 MB L2: a 256 MB buffer is written between the timed steps' inputs? no - "
+                                    "steps run back to back and the raster stays L2-resident; this config is launch-latency-bound (SURVEY 8d: 12.8 us of traffic)",
+                           "parallelism": "single GPU" if world == 1 else f"replicas only: one raster per GPU x{world}"},
+                "clocks": clocks, "gpu_launches": acc["launches"], "host_syncs_per_step": acc["syncs"] / args.steps,
+                "e2e": {"value": round(world * rows * cols / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 3), "input": "pinned host u16 DN band", "steps": e2e_steps},
+                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                             "traffic": None, "kernel": "k_apply_lut (pass B at full resolution: DN -> u8 through the 65,536-entry table)",
+                             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,
+                             "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 4) for i in range(8) if stage_n[i]},
+                             "note": "L2-resident input: the fraction is against the HBM copy peak and may exceed what DRAM alone would allow"},
+            }
+
+    # ====================================================================================================================
+    elif cfg == "c4":
+        from bench_extra import run_c4
+        line, clocks = run_c4(args, ctx, S, dev, stream, rank, world, rows, cols, make_scene, pinned_u16, timed, timed_e2e,
+                              with_load_window, peak, peak_src, names, METRIC, WORKLOADS)
+    elif cfg == "c5":
+        from bench_extra import run_c5
+        line, clocks = run_c5(args, ctx, S, dev, stream, rank, world, rows, cols, target, make_scene, pinned_u16, timed, timed_e2e,
+                              with_load_window, peak, peak_src, names, METRIC, WORKLOADS)
+
+    if rank == 0 and line is not None:
         if not args.no_cpu_baseline and world == 1:
-            crop_r, crop_c = 8000, 6250
-            vvc = vv[:crop_r, :crop_c].cpu().numpy().view(np.uint16)
-            vhc = vh[:crop_r, :crop_c].cpu().numpy().view(np.uint16)
-            v, dt, target = cpu_sample(vvc, vhc, 1)
+            full_cols = 4096 if cfg == "c1" else COLS
+            if cfg == "c1":
+                crop_r, crop_c = 4096, 4096
+                vvc, vhc = vv.cpu().numpy().view(np.uint16), None
+            else:
+                crop_r, crop_c = (8000, 6250) if cfg in ("c2", "c3") else (4000, 6250)
+                vvc = vv[:crop_r, :crop_c].cpu().numpy().view(np.uint16)
+                vhc = vh[:crop_r, :crop_c].cpu().numpy().view(np.uint16)
+            v, dt, note = cpu_sample(cfg, vvc, vhc, 1, full_cols)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": "Mpixel/s", "cores": 1, "kind": "port",
-                                    "sample": f"{crop_r}x{crop_c} crop per band of the same scene -> {target}px + pad, {dt:.1f} s, serial like the reference (SURVEY F1)"}
+                                    "sample": f"{crop_r}x{crop_c} crop per band of the same scene, {note}, {dt:.1f} s, serial like the reference (SURVEY F1)"}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

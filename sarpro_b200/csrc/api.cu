@@ -301,7 +301,7 @@ int prepare_pieces(sarpro_ctx* ctx, int slot, uint64_t rows, uint64_t row_off, b
     BandWs& w = ctx->band[slot];
     const uint64_t th = clahe ? ctx->clahe_tile_h : 0;
     if (w.pc_rows == rows && w.pc_row_off == row_off && w.pc_clahe == (int)clahe && w.pc_tile_h == th && w.pc_axis_id == ah->id &&
-        w.pc_n_ctas)
+        w.pc_n_ctas && w.pc_spare == ctx->pair_spare)
         return 0;
     std::vector<uint64_t> cuts;
     cuts.push_back(0);
@@ -315,12 +315,14 @@ int prepare_pieces(sarpro_ctx* ctx, int slot, uint64_t rows, uint64_t row_off, b
     // vertical cell ends with a partly filled round. Short rasters (a rank's band of a sharded scene) do not have a round per
     // CTA: the unit shrinks to the groups a CTA gets, so that every SM still takes a share.
     const uint32_t warps = hmma_warps(clahe);
+    // band 0 of a pipelined pair leaves ctx->pair_spare SMs to band 1's planner and CLAHE statistics, which run beside it
+    const uint32_t n_ctas = (uint32_t)std::max(1, ctx->sm_count - (slot == 0 ? ctx->pair_spare : 0));
     const uint64_t groups = (rows + 15) / 16 * std::max<size_t>(1, ah->m_weights_h.size());
-    const uint32_t per_cta = (uint32_t)std::max<uint64_t>(1, groups / std::max(1, ctx->sm_count));
+    const uint32_t per_cta = (uint32_t)std::max<uint64_t>(1, groups / n_ctas);
     const uint32_t unit = 16u * std::min(warps, per_cta);
     std::vector<uint32_t> pieces, first;
     uint32_t max_rows = 0;
-    hmma_build_pieces(ah->m_weights_h, cuts, (uint32_t)ctx->sm_count, unit, &pieces, &first, &max_rows);
+    hmma_build_pieces(ah->m_weights_h, cuts, n_ctas, unit, &pieces, &first, &max_rows);
     RC(reserve(ctx, w.pieces, std::max<size_t>(pieces.size() * 4, 16)));
     RC(reserve(ctx, w.cta_first, std::max<size_t>(first.size() * 4, 16)));
     CU(cudaMemcpyAsync(w.pieces.p, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -328,6 +330,7 @@ int prepare_pieces(sarpro_ctx* ctx, int slot, uint64_t rows, uint64_t row_off, b
     CU(cudaStreamSynchronize(ctx->stream));
     w.pc_n_ctas = (uint32_t)first.size() - 1;
     w.pc_unit = unit;
+    w.pc_spare = ctx->pair_spare;
     w.pc_rows = rows;
     w.pc_row_off = row_off;
     w.pc_clahe = clahe;
@@ -336,33 +339,40 @@ int prepare_pieces(sarpro_ctx* ctx, int slot, uint64_t rows, uint64_t row_off, b
     return 0;
 }
 
-// Horizontal pass: the tensor-core kernel (u8 samples from a DN raster, source width a multiple of 8, 16-byte aligned, tables
-// that fit shared memory) or the generic exact kernel (everything else: u8 / u16 images, u16 samples, odd widths, small scale
-// factors, the device-gated re-run with the scale_u16_to_u8 remap).
-int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off) {
+// Horizontal pass with the generic exact kernel (u8 / u16 images, u16 samples, odd widths, small scale factors, the
+// device-gated re-runs: a.skip / a.run_if).
+int run_hpass_generic(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah) {
+    KS(a.skip || a.run_if ? SARPRO_STAGE_OTHER : SARPRO_STAGE_APPLY,
+       launch_hresize_planned(a, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem, ctx->sm_count,
+                              ctx->stream));
+    return 0;
+}
+
+// Horizontal pass of a DN band: the tensor-core kernel when the shape allows it (u8 samples, source width a multiple of 8,
+// 16-byte aligned raster, at most three n-tiles per block), else the generic exact kernel. *gate is set when the tensor-core
+// kernel was launched for a band whose table range is only known on the device (planned there): the kernel returns at once
+// if the table does not fit (plan->use_generic), and the caller queues the generic kernel gated on that flag BEHIND the
+// band's vertical pass (a gated launch still needs its shared memory: queued right behind the tensor-core kernel it would
+// wait for the other band's persistent CTAs to leave and hold the vertical pass back).
+int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off, bool* gate) {
+    BandWs& w = ctx->band[slot];
+    if (gate) *gate = false;
     if (getenv("SARPRO_TRACE"))
         fprintf(stderr, "run_hpass: kind %d pix16 %d mma %d plan %p remap %p skip %p src%%16 %d smem %zu rows %u cols %u\n", src_kind, pix16,
                 (int)ah->mma, (const void*)a.plan, (const void*)a.remap, (const void*)a.skip, (int)(reinterpret_cast<uintptr_t>(a.src) % 16),
                 ah->mma ? hmma_smem_bytes(src_kind, ah->m_b_bytes) : 0, a.n_rows, a.src_cols);
-    HResizeArgs ag = a; // the generic kernel's arguments
-    if (!pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.plan && !a.remap &&
-        (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && (uint64_t)a.src_rows * a.src_cols < (1ull << 32) &&
-        hmma_smem_bytes(src_kind, ah->m_b_bytes) <= 227 * 1024) {
+    const bool shape_ok = !pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.plan && !a.remap &&
+                          (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && (uint64_t)a.src_rows * a.src_cols < (1ull << 32) &&
+                          hmma_smem_bytes(src_kind, ah->m_b_bytes) <= 227 * 1024;
+    if (shape_ok && (w.dev_planned || w.hot)) {
         RC(prepare_pieces(ctx, slot, a.n_rows, row_off, src_kind == HSRC_DN_CLAHE, ah));
-        BandWs& w = ctx->band[slot];
         KS(SARPRO_STAGE_APPLY, launch_hmma(a, src_kind, (const uint4*)ah->m_btab.p, (const int4*)ah->m_ntile.p, (const uint4*)ah->m_strips.p,
                                            (const uint32_t*)w.pieces.p, (const uint32_t*)w.cta_first.p, w.pc_n_ctas,
                                            ah->m_b_bytes, ctx->stream));
-        // Whether the band's table fits the tensor-core kernel (plan->hot != 0) is only known on the device when the band was
-        // planned there: the generic kernel is queued behind it and returns at once unless plan->use_generic is set.
-        if (!w.dev_planned && w.hot) return 0; // host-planned and eligible: nothing else to launch
-        if (!w.dev_planned && !w.hot) { /* host-planned, not eligible: k_hmma returned at once; run the generic kernel unconditionally */ }
-        else ag.run_if = &a.plan->use_generic;
+        if (gate) *gate = w.dev_planned;
+        return 0;
     }
-    KS(a.skip || ag.run_if ? SARPRO_STAGE_OTHER : SARPRO_STAGE_APPLY,
-       launch_hresize_planned(ag, src_kind, pix16, (const HStrip*)ah->strips.p, ah->n_strips, ah->oxb, ah->rbw, ah->smem, ctx->sm_count,
-                              ctx->stream));
-    return 0;
+    return run_hpass_generic(ctx, a, src_kind, pix16, ah);
 }
 
 // ---- one band through the device passes -----------------------------------------------------------
@@ -421,8 +431,10 @@ int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_
         CU(cudaMemsetAsync((uint32_t*)w.scalars.p + 4, 0, 16, ctx->stream)); // [4]: work-unit counter of pass A, [5]: present-list allocator
     }
     if (phase == 1) return 0;
+    // (persistent CTAs pulling work units: any grid works; ctx->pair_spare SMs are left to the other band's small kernels)
     KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
-                                         ctx->sm_count, ctx->hist_variant >= 0 ? ctx->hist_variant : w.hist_auto, ctx->stream,
+                                         std::max(1, ctx->sm_count - (b == 1 ? ctx->pair_spare : 0)),
+                                         ctx->hist_variant >= 0 ? ctx->hist_variant : w.hist_auto, ctx->stream,
                                          (uint32_t*)w.scalars.p + 4));
     KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
                                             (uint32_t*)w.scalars.p + 2, (uint32_t*)w.scalars.p + 5, (uint2*)w.present.p, kPresentCap,
@@ -507,13 +519,14 @@ bool plans_on_device(const sarpro_ctx* ctx, const BandJob& job) {
 int plan_band_on_device(sarpro_ctx* ctx, int b, const BandJob& job) {
     BandWs& w = ctx->band[b];
     RC(reserve(ctx, w.plan_dev, sizeof(PlanDev)));
+    RC(reserve(ctx, w.plan_scratch, plan_scratch_bytes()));
     PlanParams pr;
     pr.strategy = job.strategy;
     pr.kind = (int)job.kind;
     pr.bit_depth = job.bit_depth;
     pr.clahe = uses_clahe(job);
     KS(SARPRO_STAGE_PLAN, launch_plan_band((const uint32_t*)w.total.p, (const double*)ctx->db_table.p, pr, (uint16_t*)w.lut.p,
-                                           (PlanDev*)w.plan_dev.p, ctx->stream));
+                                           (PlanDev*)w.plan_dev.p, w.plan_scratch.p, ctx->stream));
     CU(cudaMemcpyAsync(&ctx->h_plan[b], w.plan_dev.p, sizeof(PlanDev), cudaMemcpyDeviceToHost, ctx->stream));
     w.dev_planned = true;
     w.plan_copy_pending = true;
@@ -640,13 +653,12 @@ int run_pass_b_full(sarpro_ctx* ctx, int b, const BandJob& j, void* dst) {
     KS(SARPRO_STAGE_APPLY, launch_apply_clahe(j.dn, (uint32_t)j.rows, (uint32_t)j.cols, (const uint16_t*)w.lut.p, clahe_dev(ctx, b),
                           out8 ? 255 : 65535, out8 ? (uint8_t*)dst : nullptr, out8 ? nullptr : (uint16_t*)dst,
                           (uint32_t*)w.scalars.p, ctx->sm_count, ctx->stream));
-    if (out8) { // scale_u16_to_u8 over the blended samples (autoscale.rs:691-693)
-        uint32_t mn, mx;
-        RC(clahe_minmax(ctx, b, &mn, &mx));
-        if (!(mn == 0 && mx == 255)) {
-            RC(upload_remap(ctx, b, mn, mx));
-            KS(SARPRO_STAGE_APPLY, launch_remap_u8((uint8_t*)dst, n, (const uint8_t*)w.remap.p, ctx->sm_count, ctx->stream));
-        }
+    if (out8) { // scale_u16_to_u8 over the blended samples (autoscale.rs:691-693): decided on the device, the remap pass
+                // is always queued and returns at once when the re-stretch is the identity (no host round trip)
+        RC(reserve(ctx, w.remap, 256 + 16));
+        uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
+        KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream));
+        KS(SARPRO_STAGE_OTHER, launch_remap_u8((uint8_t*)dst, n, (const uint8_t*)w.remap.p, ctx->sm_count, ctx->stream, flag));
     }
     return 0;
 }
@@ -680,25 +692,38 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     a.n_rows = (uint32_t)j.rows;
     a.temp = w.temp.p;
     a.ax = ah->dev();
-    auto run = [&]() -> int {
-        RC(run_hpass(ctx, b, a, src_kind, pix16, ah, 0));
-        unsigned char* dst = (unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz;
-        KS(a.skip ? SARPRO_STAGE_OTHER : SARPRO_STAGE_VRESIZE,
-           launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream, a.skip));
-        return 0;
-    };
-    RC(run());
+    unsigned char* dst = (unsigned char*)canvas + (g.pad_top * g.oc + g.pad_left) * esz;
+    // 1. horizontal pass (tensor-core kernel or generic), 2. vertical pass
+    bool gate = false;
+    RC(run_hpass(ctx, b, a, src_kind, pix16, ah, 0, &gate));
+    KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16, ctx->stream));
+    // 3. device-gated re-runs, all queued without a host round trip; each returns at once in the common case:
+    //    - the generic horizontal kernel when the band's table did not fit the tensor-core kernel (plan->use_generic);
+    //    - CLAHE u8: scale_u16_to_u8 (autoscale.rs:691-693) is the identity when the blended samples span exactly [0,255];
+    //      the first run assumed so and tracked the true min / max. A one-block kernel builds the remap table and the
+    //      flags; the horizontal pass is repeated with the remap when it is not the identity;
+    //    - the vertical pass again when either of the two ran.
+    const uint32_t* use_generic = gate ? &a.plan->use_generic : nullptr;
+    if (gate) {
+        HResizeArgs ag = a;
+        ag.run_if = use_generic;
+        RC(run_hpass_generic(ctx, ag, src_kind, pix16, ah));
+    }
     if (clahe && out8) {
-        // scale_u16_to_u8 (autoscale.rs:691-693) is the identity when the blended samples span exactly [0,255]; the
-        // first run assumed so. The check stays on the device: a one-block kernel builds the remap table and an
-        // "identity" flag, and the re-run kernels (always launched, no host round trip) return at once when it is set.
         RC(reserve(ctx, w.remap, 256 + 16));
         uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
-        KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream));
-        a.remap = (const uint8_t*)w.remap.p;
-        a.minmax = nullptr;
-        a.skip = flag;
-        RC(run());
+        KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream,
+                                                        gate ? a.plan : nullptr));
+        HResizeArgs ar = a;
+        ar.remap = (const uint8_t*)w.remap.p;
+        ar.minmax = nullptr;
+        ar.skip = flag;
+        RC(run_hpass_generic(ctx, ar, src_kind, pix16, ah));
+        KS(SARPRO_STAGE_OTHER, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16,
+                                              ctx->stream, flag + 1));
+    } else if (gate) {
+        KS(SARPRO_STAGE_OTHER, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, dst, (uint32_t)g.oc, 0, pix16,
+                                              ctx->stream, nullptr, use_generic));
     }
     return 0;
 }
@@ -956,6 +981,7 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
     for (int b = 0; b < nb; ++b)
         if (integral[b]) { dnjobs[ndn] = jobs[b]; dnidx[ndn] = b; ndn++; }
     const bool pipelined = ndn == nb && ndn > 0; // plan band b on the host while the device works on the other band
+    ctx->pair_spare = (pipelined && nb == 2 && ctx->two_stream && ctx->stream2) ? ctx->spare_sms : 0;
     if (pipelined) {
         RC(run_pass_a(ctx, jobs, nb));
     } else {
@@ -1075,6 +1101,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     if (const char* v = getenv("SARPRO_HMMA")) ctx->use_hmma = atoi(v);
     if (const char* v = getenv("SARPRO_TWO_STREAM")) ctx->two_stream = atoi(v);
+    if (const char* v = getenv("SARPRO_SPARE_SMS")) ctx->spare_sms = std::max(0, std::min(16, atoi(v)));
     if (getenv("SARPRO_TRACE") || (getenv("SARPRO_STAGE_TIMING") && std::string(getenv("SARPRO_STAGE_TIMING")) == "all")) ctx->stage_mask = 0xffu;
     int rc = upload_rgb_luts(ctx);
     if (rc) {
@@ -1095,7 +1122,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     for (auto& w : ctx->band)
         for (DevBuf* b : {&w.dn, &w.f32a, &w.f32b, &w.tile_hist, &w.total, &w.lut, &w.tile256, &w.cdf, &w.cdf32, &w.remap,
                           &w.temp, &w.small, &w.full, &w.scalars, &w.present, &w.edges, &w.hist4096, &w.f32scan, &w.pieces,
-                          &w.cta_first, &w.plan_dev})
+                          &w.cta_first, &w.plan_dev, &w.plan_scratch})
             release(*b);
     for (DevBuf* b : {&ctx->units, &ctx->tile_px, &ctx->col_dx, &ctx->col_omdx, &ctx->col_t, &ctx->row_dy, &ctx->row_omdy,
                       &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts, &ctx->col_m, &ctx->row_sat, &ctx->db_table})
@@ -1432,7 +1459,7 @@ int sarpro_resize_image_data_with_meta(sarpro_ctx* ctx, const uint8_t* u8_data, 
         a.n_rows = (uint32_t)rows;
         a.temp = w.temp.p;
         a.ax = ah->dev();
-        RC(run_hpass(ctx, 0, a, HSRC_IMAGE, pix16, ah, 0));
+        RC(run_hpass_generic(ctx, a, HSRC_IMAGE, pix16, ah));
         KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, region, (uint32_t)g.oc, 0, pix16, ctx->stream));
     }
     CU(cudaMemcpyAsync(dst, w.small.p, n_out * esz, cudaMemcpyDeviceToHost, ctx->stream));

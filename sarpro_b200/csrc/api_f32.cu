@@ -164,7 +164,7 @@ int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const floa
     a.n_rows = (uint32_t)rows;
     a.temp = w.temp.p;
     a.ax = ah->dev();
-    RC(run_hpass(ctx, slot, a, HSRC_IMAGE, pix16, ah, 0));
+    RC(run_hpass_generic(ctx, a, HSRC_IMAGE, pix16, ah));
     KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, 0, (uint32_t)g.rc, av->dev(), 0, (uint32_t)g.rr, region, (uint32_t)g.oc, 0,
                                             pix16, ctx->stream));
     return 0;

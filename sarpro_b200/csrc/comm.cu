@@ -325,6 +325,8 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     const size_t esz = 1;
     const size_t n_out = g.oc * g.orr;
     HResizeArgs args[2];
+    bool gates[2] = {false, false};
+    ctx->pair_spare = 0;
     cudaStream_t main_stream = ctx->stream;
     const bool two = ctx->two_stream && ctx->stream2;
     if (two) {
@@ -353,7 +355,7 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
             a.temp = w.temp.p;
             a.ax = ah->dev();
             args[b] = a;
-            RC(run_hpass(ctx, b, a, src_kind, 0, ah, h0));
+            RC(run_hpass(ctx, b, a, src_kind, 0, ah, h0, &gates[b]));
             return 0;
         };
         rc_b = body();
@@ -365,6 +367,23 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         if (!rc_b) { CU(e1); CU(e2); }
     }
     RC(rc_b);
+    // ---- vertical pass for the owned output rows (first run: assumes the tensor-core kernel took the band and the CLAHE
+    // re-stretch is the identity; the device-gated re-runs below repair it otherwise, see run_pass_b_resized)
+    auto vpass = [&](int b, int stage, const uint32_t* skip, const uint32_t* run_if) -> int {
+        BandWs& w = ctx->band[b];
+        if (oy1 <= oy0) return 0;
+        unsigned char* dst = (unsigned char*)w.small.p + (g.pad_top * g.oc + g.pad_left) * esz;
+        KS(stage, launch_vresize(w.temp.p, (uint32_t)h0, (uint32_t)g.rc, av->dev(), (uint32_t)oy0, (uint32_t)oy1, dst, (uint32_t)g.oc, 0, 0,
+                                 ctx->stream, skip, run_if));
+        return 0;
+    };
+    for (int b = 0; b < 2; ++b) RC(vpass(b, SARPRO_STAGE_VRESIZE, nullptr, nullptr));
+    for (int b = 0; b < 2; ++b)
+        if (gates[b]) {
+            HResizeArgs ag = args[b];
+            ag.run_if = &args[b].plan->use_generic;
+            RC(run_hpass_generic(ctx, ag, src_kind, 0, ah));
+        }
     // ---- 3. scale_u16_to_u8 decision for CLAHE: global sample min/max --------------------------------------------
     if (clahe) {
         // scalars[0] = min, [1] = max per band -> pack {max, ~min} so that one all-reduce(max) serves both. Everything
@@ -381,21 +400,18 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
             BandWs& w = ctx->band[b];
             RC(reserve(ctx, w.remap, 256 + 16));
             uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
-            KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream));
-            args[b].remap = (const uint8_t*)w.remap.p;
-            args[b].minmax = nullptr;
-            args[b].skip = flag;
-            RC(run_hpass(ctx, b, args[b], src_kind, 0, ah, h0));
+            KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream,
+                                                            gates[b] ? args[b].plan : nullptr));
+            HResizeArgs ar = args[b];
+            ar.remap = (const uint8_t*)w.remap.p;
+            ar.minmax = nullptr;
+            ar.skip = flag;
+            RC(run_hpass_generic(ctx, ar, src_kind, 0, ah));
+            RC(vpass(b, SARPRO_STAGE_OTHER, flag + 1, nullptr));
         }
-    }
-    // ---- vertical pass for the owned output rows, then 4. every rank's rows to every rank ---------------------------------
-    for (int b = 0; b < 2; ++b) {
-        BandWs& w = ctx->band[b];
-        if (oy1 > oy0) {
-            unsigned char* dst = (unsigned char*)w.small.p + (g.pad_top * g.oc + g.pad_left) * esz;
-            KS(SARPRO_STAGE_VRESIZE, launch_vresize(w.temp.p, (uint32_t)h0, (uint32_t)g.rc, av->dev(), (uint32_t)oy0, (uint32_t)oy1, dst,
-                                                    (uint32_t)g.oc, 0, 0, ctx->stream));
-        }
+    } else {
+        for (int b = 0; b < 2; ++b)
+            if (gates[b]) RC(vpass(b, SARPRO_STAGE_OTHER, nullptr, &args[b].plan->use_generic));
     }
     if (n_out) {
         // The canvases are zero outside a rank's own output rows: rank r's rows [oy0_r, oy1_r) (whole canvas rows, pad columns

@@ -78,6 +78,7 @@ struct BandWs {
     // Piece lists of the persistent pass-B kernel for this slot (cached per geometry). Per slot, because the two bands of a
     // pair run their pass B on different streams and may be cut differently: a shared list could be overwritten while the
     // other band's kernel still reads it.
+    DevBuf plan_scratch;            // device planner: list of present DNs when it does not fit shared memory
     DevBuf plan_dev;                // PlanDev: the band's plan for the kernels downstream (device or host planner)
     bool dev_planned = false;       // planned by kernels_plan.cu in this call: w.plan / hot are only valid after end_call
     bool plan_copy_pending = false; // ctx->h_plan[slot] is being written by the device
@@ -85,6 +86,7 @@ struct BandWs {
     uint64_t pc_rows = 0, pc_row_off = 0, pc_tile_h = 0, pc_axis_id = 0;
     int pc_clahe = -1;
     uint32_t pc_n_ctas = 0, pc_unit = 0;
+    int pc_spare = -1;
 };
 
 constexpr uint32_t kSynRgbSets = 42; // 0..40 suppressed by floor_with_cushion, 41 default
@@ -123,6 +125,8 @@ struct sarpro_ctx {
     cudaStream_t stream2 = nullptr; // side stream: the second band's pass B (see produce_bands)
     cudaEvent_t ev_join = nullptr;
     int two_stream = 1;             // SARPRO_TWO_STREAM=0: everything on `stream`
+    int spare_sms = 2;              // SARPRO_SPARE_SMS: SMs the persistent kernels of a band pair leave to the other band's small kernels
+    int pair_spare = 0;             // spare_sms while a pipelined pair is in flight, else 0
     bool own_stream = true;
     int sm_count = 148;
     std::string err;
@@ -176,8 +180,9 @@ uint32_t hmma_hot(const uint16_t* lut_host, const uint32_t* hist_host, uint32_t 
 uint32_t hmma_hot_from_plan(const BandPlan& plan, uint32_t* top_out);
 int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res);
 int begin_call(sarpro_ctx* ctx);
-// slot: the band slot whose piece lists the tensor-core kernel uses
-int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off);
+// slot: the band slot whose piece lists the tensor-core kernel uses; *gate: see api.cu
+int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off, bool* gate);
+int run_hpass_generic(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah);
 // phase: 0 = everything, 1 = only the preamble (workspaces, cleared histograms and counters), 2 = only the kernels
 int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units, int phase = 0);
 int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units,

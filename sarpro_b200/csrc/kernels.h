@@ -37,8 +37,10 @@ struct PlanParams {
 // strategies the device planner covers (gamma == 1: no pow); the others are planned on the host
 bool plan_on_device_supported(int strategy, int kind);
 // total: [65536] u32 DN counts; db_table: [65536] f64 dB of every DN (plan.cpp dn_db_table); lut: [65536] u16 out
+// scratch: plan_scratch_bytes() of device memory (the list of present DNs when it does not fit shared memory)
+size_t plan_scratch_bytes();
 cudaError_t launch_plan_band(const uint32_t* total, const double* db_table, const PlanParams& pr, uint16_t* lut, PlanDev* out,
-                             cudaStream_t stream);
+                             void* scratch, cudaStream_t stream);
 
 // ---- work decomposition -----------------------------------------------------------------
 // A histogram work unit: rows [r0,r1) x cols [c0,c1) of the local raster, all inside one tile.
@@ -105,7 +107,9 @@ cudaError_t launch_apply_clahe(const uint16_t* dn, uint32_t rows, uint32_t cols,
 // packs (unpack = 0) / unpacks (1) {max, ~min} of two bands' {min, max} words into / from a 4-word vector
 cudaError_t launch_minmax_pack(uint32_t* scalars0, uint32_t* scalars1, uint32_t* packed4, int unpack, cudaStream_t stream);
 // in-place u8 remap through a 256-entry table
-cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, int sm_count, cudaStream_t stream);
+// skip: optional device flag, the kernel returns at once when *skip != 0
+cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, int sm_count, cudaStream_t stream,
+                            const uint32_t* skip = nullptr);
 // min/max of a u16 array + u16 -> u8 remap (scale_u16_to_u8, autoscale.rs:348-364)
 cudaError_t launch_minmax_u16(const uint16_t* data, uint64_t n, uint32_t* minmax, int sm_count, cudaStream_t stream);
 cudaError_t launch_scale_u16_to_u8(const uint16_t* data, uint64_t n, const uint32_t* minmax, uint8_t* out, int sm_count,
@@ -189,10 +193,12 @@ cudaError_t launch_hmma(const HResizeArgs& a, int src_kind, const uint4* btab_de
 // vertical pass: out row oy (oy in [oy0, oy1)) from temp rows (start[oy] - temp_row0 + k)
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
                            void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream,
-                           const uint32_t* skip = nullptr);
+                           const uint32_t* skip = nullptr, const uint32_t* run_if = nullptr);
 // scale_u16_to_u8 decision on the device (autoscale.rs:348-364 over the CLAHE samples): from minmax = {min, max}
-// builds the 256-entry remap and sets skip[0] = 1 when it is the identity (min == 0 && max == 255, or no sample).
-cudaError_t launch_clahe_remap_decide(const uint32_t* minmax, uint8_t* remap256, uint32_t* skip, cudaStream_t stream);
+// builds the 256-entry remap and sets skip[0] = 1 when it is the identity (min == 0 && max == 255, or no sample);
+// skip[1] = 1 when, in addition, the band did not need the generic horizontal kernel (plan->use_generic == 0; plan may be null).
+cudaError_t launch_clahe_remap_decide(const uint32_t* minmax, uint8_t* remap256, uint32_t* skip, cudaStream_t stream,
+                                      const PlanDev* plan = nullptr);
 
 // ---- small-image stages ---------------------------------------------------------------------
 // dst (dcols x drows) zero-filled, src (scols x srows) copied at (pad_left, pad_top). elem = 1 or 2 bytes.

@@ -552,8 +552,9 @@ cudaError_t launch_apply_clahe(const uint16_t* dn, uint32_t rows, uint32_t cols,
 // scale_u16_to_u8 pieces (autoscale.rs:348-364)
 // =============================================================================================
 __global__ void __launch_bounds__(512) k_remap_u8(uint8_t* __restrict__ data, uint64_t n,
-                                                  const uint8_t* __restrict__ remap) {
+                                                  const uint8_t* __restrict__ remap, const uint32_t* __restrict__ skip) {
     __shared__ uint8_t s[256];
+    if (skip && *skip) return;
     if (threadIdx.x < 256) s[threadIdx.x] = remap[threadIdx.x];
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -571,15 +572,16 @@ __global__ void __launch_bounds__(512) k_remap_u8(uint8_t* __restrict__ data, ui
     for (uint64_t e = (nvec << 4) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
         data[e] = s[data[e]];
 }
-cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, int sm_count, cudaStream_t stream) {
+cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, int sm_count, cudaStream_t stream,
+                            const uint32_t* skip) {
     if (n == 0) return cudaSuccess;
-    k_remap_u8<<<sm_count * 4, 512, 0, stream>>>(data, n, remap256);
+    k_remap_u8<<<sm_count * 4, 512, 0, stream>>>(data, n, remap256, skip);
     return cudaGetLastError();
 }
 
 // autoscale.rs:352-363 for the 256 possible CLAHE samples; same f32 operations as plan.cpp make_u16_to_u8_remap
 __global__ void __launch_bounds__(256) k_clahe_remap_decide(const uint32_t* __restrict__ minmax, uint8_t* __restrict__ remap,
-                                                            uint32_t* __restrict__ skip) {
+                                                            uint32_t* __restrict__ skip, const PlanDev* __restrict__ plan) {
     uint32_t mn = minmax[0], mx = minmax[1];
     if (mn == 0xffffffffu) { mn = 0; mx = 0; }
     const bool identity = (mn == 0 && mx == 255) || (mn == 0 && mx == 0);
@@ -588,10 +590,16 @@ __global__ void __launch_bounds__(256) k_clahe_remap_decide(const uint32_t* __re
     float val = roundf(__fmul_rn(__fsub_rn((float)threadIdx.x, fmn), scale));
     val = val < 0.0f ? 0.0f : (val > 255.0f ? 255.0f : val);
     remap[threadIdx.x] = (uint8_t)val;
-    if (threadIdx.x == 0) skip[0] = identity ? 1u : 0u;
+    if (threadIdx.x == 0) {
+        skip[0] = identity ? 1u : 0u;
+        // skip[1]: the vertical pass behind the re-run may be skipped only when neither the re-stretch nor the generic
+        // horizontal kernel (plan->use_generic: the first vertical pass ran on rows the tensor-core kernel never wrote) ran
+        skip[1] = (identity && !(plan && plan->use_generic)) ? 1u : 0u;
+    }
 }
-cudaError_t launch_clahe_remap_decide(const uint32_t* minmax, uint8_t* remap256, uint32_t* skip, cudaStream_t stream) {
-    k_clahe_remap_decide<<<1, 256, 0, stream>>>(minmax, remap256, skip);
+cudaError_t launch_clahe_remap_decide(const uint32_t* minmax, uint8_t* remap256, uint32_t* skip, cudaStream_t stream,
+                                      const PlanDev* plan) {
+    k_clahe_remap_decide<<<1, 256, 0, stream>>>(minmax, remap256, skip, plan);
     return cudaGetLastError();
 }
 

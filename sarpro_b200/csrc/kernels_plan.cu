@@ -26,7 +26,7 @@ namespace sarpro {
 namespace {
 
 constexpr uint32_t kPlanThreads = 1024;
-constexpr uint32_t kDnPerThread = 65536 / kPlanThreads; // 64 consecutive DNs per thread
+constexpr uint32_t kDnPerThread = 65536 / kPlanThreads; // 64 DNs per thread, interleaved: DN k * 1024 + tid (coalesced loads)
 constexpr int kStatBinsDev = 4096;
 
 __device__ __forceinline__ unsigned long long cast_u64_dev(double x) { // Rust `as u64`: truncate, saturate, NaN -> 0
@@ -72,9 +72,16 @@ struct OpAddF64 { __device__ double operator()(double a, double b) const { retur
 
 } // namespace
 
+// Entries of the present DNs, compacted by the kernel itself: in shared memory when there are at most kPlanCap of them (a GRD
+// band has a few thousand), else in a global scratch buffer (every u16 value present: same code, slower).
+constexpr uint32_t kPlanCap = 8192;
+constexpr size_t kPlanDynSmem = (size_t)kPlanCap * (8 + 4 + 2 + 2);
+constexpr size_t kPlanScratchBytes = (size_t)65536 * (8 + 4 + 2 + 2);
+
 __global__ void __launch_bounds__(kPlanThreads, 1)
 k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, PlanParams pr, uint16_t* __restrict__ lut,
-            PlanDev* __restrict__ out) {
+            PlanDev* __restrict__ out, unsigned char* __restrict__ scratch) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ unsigned long long s_cum[kStatBinsDev]; // 4096-bin histogram (autoscale.rs:103-117), then its inclusive prefix sums
     __shared__ unsigned long long s_u64[33];
     __shared__ uint32_t s_u32[33];
@@ -83,26 +90,74 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
     __shared__ double s_pct[11];
     __shared__ double s_win[3]; // low, high, range
     __shared__ uint8_t s_remap[256];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t dn0 = tid * kDnPerThread;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
 
-    // ---- present DNs: counts, range ------------------------------------------------------------------------------------
+    // ---- the present DNs, compacted -------------------------------------------------------------------------------------
+    // Thread t looks at DNs k * 1024 + t (coalesced, 64 independent loads), keeps a presence mask, and the block scans the
+    // per-thread counts into offsets. The list is not in DN order; nothing below depends on the order (sums of products
+    // run in list order, which is fixed, so the result is deterministic).
+    unsigned long long present_bits = 0;
+    uint32_t hh[kDnPerThread];
+#pragma unroll
+    for (uint32_t k = 0; k < kDnPerThread; ++k) hh[k] = total[k * kPlanThreads + tid];
+#pragma unroll
+    for (uint32_t k = 0; k < kDnPerThread; ++k) present_bits |= hh[k] ? (1ull << k) : 0ull;
+    const uint32_t mine = (uint32_t)__popcll(present_bits);
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += nb;
+    }
+    if (lane == 31) s_u32[wid] = inc;
+    __syncthreads();
+    uint32_t warp_off = 0, n_present = 0;
+    for (uint32_t w = 0; w < 32; ++w) {
+        const uint32_t c = s_u32[w];
+        if (w < wid) warp_off += c;
+        n_present += c;
+    }
+    __syncthreads();
+    const bool in_smem = n_present <= kPlanCap;
+    unsigned char* base = in_smem ? s_dyn : scratch;
+    const size_t cap = in_smem ? kPlanCap : 65536;
+    double* e_db = reinterpret_cast<double*>(base);
+    uint32_t* e_h = reinterpret_cast<uint32_t*>(base + cap * 8);
+    uint16_t* e_dn = reinterpret_cast<uint16_t*>(base + cap * 12);
+    uint16_t* e_q = reinterpret_cast<uint16_t*>(base + cap * 14);
+    {
+        uint32_t pos = warp_off + inc - mine;
+#pragma unroll
+        for (uint32_t k = 0; k < kDnPerThread; ++k)
+            if (hh[k]) {
+                e_dn[pos] = (uint16_t)(k * kPlanThreads + tid);
+                e_h[pos] = hh[k];
+                ++pos;
+            }
+    }
+    // every table word starts at 0: absent and invalid DNs keep it (invalid pixels are written as 0, autoscale.rs:444, 653, 738)
+    {
+        uint4* lut4 = reinterpret_cast<uint4*>(lut);
+        for (uint32_t i = tid; i < 65536u * 2u / 16u; i += kPlanThreads) lut4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads) e_db[i] = db[e_dn[i]];
+    __syncthreads();
+
     // valid <=> dB > -50 (pipeline.rs:22); for a u16 DN that is DN >= 1 (dB(1) = 0, dB(0) = -100), but the table decides.
     unsigned long long cnt = 0, px = 0, ge1k = 0, ge2k = 0;
     uint32_t first_valid = 0xffffffffu, last_valid = 0, last_present = 0;
     uint32_t invalid_present = 0;
-    for (uint32_t k = 0; k < kDnPerThread; ++k) {
-        const uint32_t d = dn0 + k;
-        const uint32_t h = total[d];
-        if (!h) continue;
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads) {
+        const uint32_t d = e_dn[i], h = e_h[i];
         px += h;
         if (d >= 1024) ge1k += h;
         if (d >= 2048) ge2k += h;
-        last_present = d;
-        if (db[d] > -50.0) {
+        last_present = max(last_present, d);
+        if (e_db[i] > -50.0) {
             cnt += h;
-            if (first_valid == 0xffffffffu) first_valid = d;
-            last_valid = d;
+            first_valid = min(first_valid, d);
+            last_valid = max(last_valid, d);
         } else {
             invalid_present = 1;
         }
@@ -117,7 +172,6 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
     const bool have_invalid = block_reduce(invalid_present, OpMaxU32(), s_u32) != 0;
 
     if (count == 0) { // all-zero output (autoscale.rs:376-378, 466-468, 716-718): every table word is 0
-        for (uint32_t k = 0; k < kDnPerThread; ++k) lut[dn0 + k] = 0;
         if (tid == 0) {
             PlanDev p{};
             p.max_present_dn = max_present_dn;
@@ -136,21 +190,15 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
     // ---- pass 1 of compute_histogram_stats over distinct values (autoscale.rs:37-55) ----------------------------------
     const double min_db = db[min_dn], max_db = db[max_valid_dn]; // dB is monotone in the DN
     double sum = 0.0;
-    for (uint32_t k = 0; k < kDnPerThread; ++k) {
-        const uint32_t d = dn0 + k;
-        const uint32_t h = total[d];
-        if (h && db[d] > -50.0) sum = __dadd_rn(sum, __dmul_rn((double)h, db[d]));
-    }
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads)
+        if (e_db[i] > -50.0) sum = __dadd_rn(sum, __dmul_rn((double)e_h[i], e_db[i]));
     const double mean_db = __ddiv_rn(block_reduce(sum, OpAddF64(), s_f64), (double)count);
     double m2 = 0.0;
-    for (uint32_t k = 0; k < kDnPerThread; ++k) {
-        const uint32_t d = dn0 + k;
-        const uint32_t h = total[d];
-        if (h && db[d] > -50.0) {
-            const double dd = __dsub_rn(db[d], mean_db);
-            m2 = __dadd_rn(m2, __dmul_rn((double)h, __dmul_rn(dd, dd)));
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads)
+        if (e_db[i] > -50.0) {
+            const double dd = __dsub_rn(e_db[i], mean_db);
+            m2 = __dadd_rn(m2, __dmul_rn((double)e_h[i], __dmul_rn(dd, dd)));
         }
-    }
     const double m2_all = block_reduce(m2, OpAddF64(), s_f64);
     const double std_db = count > 1 ? sqrt(__ddiv_rn(m2_all, (double)count)) : 0.0;
 
@@ -161,35 +209,31 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
         __syncthreads();
         const double span = __dsub_rn(max_db, min_db);
         const double inv_span = __ddiv_rn(1.0, span);
-        for (uint32_t k = 0; k < kDnPerThread; ++k) {
-            const uint32_t d = dn0 + k;
-            const uint32_t h = total[d];
-            if (h && db[d] > -50.0) {
-                const double t = clampd_dev(__dmul_rn(__dsub_rn(db[d], min_db), inv_span), 0.0, 1.0);
+        for (uint32_t i = tid; i < n_present; i += kPlanThreads)
+            if (e_db[i] > -50.0) {
+                const double t = clampd_dev(__dmul_rn(__dsub_rn(e_db[i], min_db), inv_span), 0.0, 1.0);
                 unsigned long long idx = cast_u64_dev(__dmul_rn(t, (double)kStatBinsDev));
                 if (idx >= (unsigned long long)kStatBinsDev) idx = kStatBinsDev - 1;
-                atomicAdd(&s_cum[idx], (unsigned long long)h);
+                atomicAdd(&s_cum[idx], (unsigned long long)e_h[i]);
             }
-        }
         __syncthreads();
         // inclusive prefix sums in place: four bins per thread, then the block-wide offsets
         unsigned long long v[4], run = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { run += s_cum[tid * 4 + i]; v[i] = run; }
         {
-            const uint32_t lane = tid & 31u, wid = tid >> 5;
-            unsigned long long inc = run;
+            unsigned long long inc64 = run;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long nb = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((int)lane >= o) inc += nb;
+                const unsigned long long nb = __shfl_up_sync(0xffffffffu, inc64, o);
+                if ((int)lane >= o) inc64 += nb;
             }
             __syncthreads();
-            if (lane == 31) s_u64[wid] = inc;
+            if (lane == 31) s_u64[wid] = inc64;
             __syncthreads();
-            unsigned long long warp_off = 0;
-            for (uint32_t w = 0; w < wid; ++w) warp_off += s_u64[w];
-            const unsigned long long off = warp_off + inc - run;
+            unsigned long long woff = 0;
+            for (uint32_t w = 0; w < wid; ++w) woff += s_u64[w];
+            const unsigned long long off = woff + inc64 - run;
 #pragma unroll
             for (int i = 0; i < 4; ++i) s_cum[tid * 4 + i] = v[i] + off;
         }
@@ -255,15 +299,11 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
     const bool tamed_rgb = pr.kind != 0;
     const bool clahe = !tamed_rgb && pr.strategy == SARPRO_STRATEGY_CLAHE;
     const double max_val = (tamed_rgb || pr.bit_depth == SARPRO_U8) ? 255.0 : 65535.0;
-    uint32_t q[kDnPerThread];
     uint32_t mn = 65535u, mx = 0u;
-#pragma unroll 4
-    for (uint32_t k = 0; k < kDnPerThread; ++k) {
-        const uint32_t d = dn0 + k;
-        const uint32_t h = total[d];
-        uint32_t w = 0; // absent and invalid DNs keep word 0 (invalid pixels are written as 0, autoscale.rs:444, 653, 738)
-        if (h && db[d] > -50.0) {
-            const double v = db[d];
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads) {
+        uint32_t w = 0;
+        if (e_db[i] > -50.0) {
+            const double v = e_db[i];
             const double a = v < low ? low : v;           // v.max(low).min(high), autoscale.rs:440, 583, 649, 734
             const double clipped = a > high ? high : a;
             const double n = __ddiv_rn(__dsub_rn(clipped, low), range);
@@ -284,7 +324,7 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
             mn = min(mn, w);
             mx = max(mx, w);
         }
-        q[k] = w;
+        e_q[i] = (uint16_t)w;
     }
     uint32_t pre_min = 0, pre_max = 0;
     if (!clahe) {
@@ -300,40 +340,29 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
                 s_remap[tid] = (uint8_t)val;
             }
             __syncthreads();
-#pragma unroll 4
-            for (uint32_t k = 0; k < kDnPerThread; ++k) {
-                const uint32_t d = dn0 + k;
-                if (total[d] && db[d] > -50.0) q[k] = s_remap[q[k] > 255u ? 255u : q[k]];
-            }
+            for (uint32_t i = tid; i < n_present; i += kPlanThreads)
+                if (e_db[i] > -50.0) e_q[i] = s_remap[e_q[i] > 255u ? 255u : e_q[i]];
         }
     }
-    // 64 consecutive u16 = 128 B per thread: eight 16-byte stores
-    uint4* lut4 = reinterpret_cast<uint4*>(lut + dn0);
-#pragma unroll
-    for (uint32_t k = 0; k < kDnPerThread; k += 8)
-        lut4[k / 8] = make_uint4(q[k] | (q[k + 1] << 16), q[k + 2] | (q[k + 3] << 16), q[k + 4] | (q[k + 5] << 16), q[k + 6] | (q[k + 7] << 16));
+    __syncthreads();
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads) lut[e_dn[i]] = e_q[i];
 
     // ---- table range of the tensor-core pass B (plan.cpp set_sat_from, api.cu hmma_hot_from_plan) -----------------------
     // sat_from = the lowest valid present DN from which every valid present DN up to the brightest present one carries the
     // brightest one's table word (low byte).
-    uint32_t top_word;
-    {
-        if (tid == max_present_dn / kDnPerThread) s_u32[0] = q[max_present_dn % kDnPerThread] & 255u;
-        __syncthreads();
-        top_word = s_u32[0];
-        __syncthreads();
-    }
+    uint32_t top_word = 0;
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads)
+        if (e_dn[i] == max_present_dn) s_u32[0] = e_q[i] & 255u;
+    __syncthreads();
+    top_word = s_u32[0];
+    __syncthreads();
     int last_nontop = -1;
-    for (uint32_t k = 0; k < kDnPerThread; ++k) {
-        const uint32_t d = dn0 + k;
-        if (total[d] && db[d] > -50.0 && d <= max_present_dn && (q[k] & 255u) != top_word) last_nontop = (int)d;
-    }
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads)
+        if (e_db[i] > -50.0 && (e_q[i] & 255u) != top_word) last_nontop = max(last_nontop, (int)e_dn[i]);
     last_nontop = block_reduce(last_nontop, OpMaxI32(), s_i32);
     uint32_t first_after = 0xffffffffu;
-    for (uint32_t k = 0; k < kDnPerThread; ++k) {
-        const uint32_t d = dn0 + k;
-        if (total[d] && db[d] > -50.0 && (int)d > last_nontop && first_after == 0xffffffffu) first_after = d;
-    }
+    for (uint32_t i = tid; i < n_present; i += kPlanThreads)
+        if (e_db[i] > -50.0 && (int)e_dn[i] > last_nontop) first_after = min(first_after, (uint32_t)e_dn[i]);
     first_after = block_reduce(first_after, OpMinU32(), s_u32);
     if (tid == 0) {
         uint32_t h = first_after == 0xffffffffu ? max_present_dn : first_after;
@@ -375,9 +404,12 @@ bool plan_on_device_supported(int strategy, int kind) {
            strategy == SARPRO_STRATEGY_TAMED || strategy == SARPRO_STRATEGY_DEFAULT;
 }
 
+size_t plan_scratch_bytes() { return kPlanScratchBytes; }
+
 cudaError_t launch_plan_band(const uint32_t* total, const double* db_table, const PlanParams& pr, uint16_t* lut, PlanDev* out,
-                             cudaStream_t stream) {
-    k_plan_band<<<1, kPlanThreads, 0, stream>>>(total, db_table, pr, lut, out);
+                             void* scratch, cudaStream_t stream) {
+    if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_plan_band), kPlanDynSmem)) return e;
+    k_plan_band<<<1, kPlanThreads, kPlanDynSmem, stream>>>(total, db_table, pr, lut, out, reinterpret_cast<unsigned char*>(scratch));
     return cudaGetLastError();
 }
 

@@ -313,9 +313,11 @@ cudaError_t launch_hresize_planned(const HResizeArgs& a, int src_kind, int pix16
 template <bool PIX16>
 __global__ void __launch_bounds__(256) k_vresize(const void* __restrict__ temp, uint32_t temp_row0, uint32_t width,
                                                  AxisDev ax, uint32_t oy0, void* __restrict__ out, uint32_t out_pitch,
-                                                 uint32_t out_x0, const uint32_t* __restrict__ skip) {
+                                                 uint32_t out_x0, const uint32_t* __restrict__ skip,
+                                                 const uint32_t* __restrict__ run_if) {
     extern __shared__ int s_coef[];
     if (skip && *skip) return;
+    if (run_if && !*run_if) return;
     const uint32_t oy = oy0 + blockIdx.y;
     const uint32_t n = ax.size[oy], start = ax.start[oy];
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) s_coef[k] = ax.coef[(size_t)oy * ax.window + k];
@@ -343,9 +345,11 @@ __global__ void __launch_bounds__(256) k_vresize(const void* __restrict__ temp, 
 // dp2a consumes (tap k, tap k+1) x (row k, row k+1) of a column.
 __global__ void __launch_bounds__(128) k_vresize8x4(const uint8_t* __restrict__ temp, uint32_t temp_row0, uint32_t width,
                                                     AxisDev ax, uint32_t oy0, uint8_t* __restrict__ out, uint32_t out_pitch,
-                                                    uint32_t out_x0, const uint32_t* __restrict__ skip) {
+                                                    uint32_t out_x0, const uint32_t* __restrict__ skip,
+                                                    const uint32_t* __restrict__ run_if) {
     extern __shared__ int s_pair[]; // packed (tap k | tap k+1 << 16)
     if (skip && *skip) return;
+    if (run_if && !*run_if) return;
     const uint32_t oy = oy0 + blockIdx.y;
     const uint32_t n = ax.size[oy], start = ax.start[oy];
     const uint32_t np = (n + 1) / 2;
@@ -384,18 +388,18 @@ __global__ void __launch_bounds__(128) k_vresize8x4(const uint8_t* __restrict__ 
 
 cudaError_t launch_vresize(const void* temp, uint32_t temp_row0, uint32_t width, AxisDev ax, uint32_t oy0, uint32_t oy1,
                            void* out, uint32_t out_pitch, uint32_t out_x0, int pix16, cudaStream_t stream,
-                           const uint32_t* skip) {
+                           const uint32_t* skip, const uint32_t* run_if) {
     if (oy1 <= oy0 || width == 0) return cudaSuccess;
     if (!pix16 && width % 4 == 0 && (reinterpret_cast<uintptr_t>(temp) & 3) == 0) {
         const dim3 grid((width / 4 + 127) / 128, oy1 - oy0);
         const size_t smem = (size_t)(ax.window + 1) / 2 * sizeof(int) + 16;
-        k_vresize8x4<<<grid, 128, smem, stream>>>((const uint8_t*)temp, temp_row0, width, ax, oy0, (uint8_t*)out, out_pitch, out_x0, skip);
+        k_vresize8x4<<<grid, 128, smem, stream>>>((const uint8_t*)temp, temp_row0, width, ax, oy0, (uint8_t*)out, out_pitch, out_x0, skip, run_if);
         return cudaGetLastError();
     }
     const dim3 grid((width + 255) / 256, oy1 - oy0);
     const size_t smem = (size_t)ax.window * sizeof(int);
-    if (pix16) k_vresize<true><<<grid, 256, smem, stream>>>(temp, temp_row0, width, ax, oy0, out, out_pitch, out_x0, skip);
-    else k_vresize<false><<<grid, 256, smem, stream>>>(temp, temp_row0, width, ax, oy0, out, out_pitch, out_x0, skip);
+    if (pix16) k_vresize<true><<<grid, 256, smem, stream>>>(temp, temp_row0, width, ax, oy0, out, out_pitch, out_x0, skip, run_if);
+    else k_vresize<false><<<grid, 256, smem, stream>>>(temp, temp_row0, width, ax, oy0, out, out_pitch, out_x0, skip, run_if);
     return cudaGetLastError();
 }
 

@@ -1,5 +1,10 @@
-"""torchrun worker: row-band-sharded synRGB of ONE scene across the ranks vs the single-GPU result (and the
-oracle on rank 0). Prints one line per rank; exit code 1 on mismatch."""
+"""torchrun worker: row-band-sharded synRGB of ONE scene across the ranks vs the single-GPU result (and, for shapes the
+oracle finishes in seconds, the oracle on rank 0). Prints one line per rank and shape; exit code 1 on mismatch.
+
+SHAPES="rows x cols x target,..." overrides the default list. The defaults cover: a raster whose width is not a multiple of 8
+(generic exact kernel), shapes with cols % 8 == 0 and at least 8 row groups of 16 rows per rank (tensor-core pass B, k_hmma,
+on every rank), and with FULL=1 the 16000 x 25000 C3 scene of bench.py (single-GPU result as the reference: that one is
+pinned to the oracle by tests/test_gpu_parity.py::test_full_size_scene_against_oracle)."""
 import os
 import sys
 
@@ -10,33 +15,48 @@ import torch
 import torch.distributed as dist
 
 import sarpro_b200 as S
-from sarpro_b200.synth import synth_pair
+from sarpro_b200.synth import SEED_VH, SEED_VV, synth_band_torch, synth_pair
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(lr)
-dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-rows, cols, target = int(os.environ.get("ROWS", 2003)), int(os.environ.get("COLS", 3011)), int(os.environ.get("TARGET", 512))
-vv, vh = synth_pair(rows, cols, block=32)
+dev = torch.device("cuda", lr)
+dist.init_process_group("nccl", device_id=dev)
+shapes = [(2003, 3011, 512), (4000, 8192, 1024), (1100 * world, 4096, 512)]
+if os.environ.get("SHAPES"):
+    shapes = [tuple(int(x) for x in s.split("x")) for s in os.environ["SHAPES"].split(",")]
+if os.environ.get("FULL"):
+    shapes.append((16000, 25000, 2048))
 ctx = S.Context(lr)
 uid = [S.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(uid[0], rank, world)
 bad = 0
-for strategy in (S.CLAHE, S.ROBUST, S.TAMED, S.STANDARD):
-    clahe = strategy == S.CLAHE
-    h0, h1 = S.shard_halo_rows(rows, cols, target, world, rank, clahe)
-    img = ctx.process_synrgb_sharded(vv[h0:h1], vh[h0:h1], rows, strategy, target, True)
-    single = ctx.process_synrgb_jpeg(vv, vh, strategy, target, True)
-    same = np.array_equal(img.rgb, single.rgb)
-    msg = f"rank {rank}/{world} strategy {S.STRATEGY_NAMES[strategy]} rows[{h0},{h1}) sharded==single: {same}"
-    if rank == 0:
-        from oracle import pyoracle as O
-        ref, _ = O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), strategy, target, True)
-        ok = np.array_equal(img.rgb, ref)
-        msg += f" sharded==oracle: {ok}"
-        same = same and ok
-    print(msg, flush=True)
-    bad += 0 if same else 1
+for rows, cols, target in shapes:
+    big = rows * cols > 40_000_000
+    if big:  # device generator (same seeds on every rank -> same scene)
+        vv = synth_band_torch(rows, cols, SEED_VV, dev)
+        vh = synth_band_torch(rows, cols, SEED_VH, dev, cross_pol=True)
+        torch.cuda.synchronize(dev)
+    else:
+        vv, vh = synth_pair(rows, cols, block=32, point_targets=1e-4)
+    for strategy in (S.CLAHE, S.ROBUST, S.TAMED, S.STANDARD):
+        clahe = strategy == S.CLAHE
+        h0, h1 = S.shard_halo_rows(rows, cols, target, world, rank, clahe)
+        img = ctx.process_synrgb_sharded(vv[h0:h1], vh[h0:h1], rows, strategy, target, True)
+        t = ctx.timing()
+        single = ctx.process_synrgb_jpeg(vv, vh, strategy, target, True)
+        same = np.array_equal(img.rgb, single.rgb)
+        msg = (f"rank {rank}/{world} {rows}x{cols}->{target} {S.STRATEGY_NAMES[strategy]} rows[{h0},{h1}) sharded==single: {same} "
+               f"(host syncs {t.host_syncs}, launches {t.kernel_launches})")
+        if rank == 0 and not big:
+            from oracle import pyoracle as O
+            ref, _ = O.pipeline_synrgb_jpeg(np.asarray(vv).astype(np.float32), np.asarray(vh).astype(np.float32), strategy, target, True)
+            ok = np.array_equal(img.rgb, ref)
+            msg += f" sharded==oracle: {ok}"
+            same = same and ok
+        print(msg, flush=True)
+        bad += 0 if same else 1
+    del vv, vh
 t = torch.tensor([bad], device="cuda")
 dist.all_reduce(t)
 ctx.comm_destroy()
