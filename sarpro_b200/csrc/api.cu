@@ -516,22 +516,48 @@ bool plans_on_device(const sarpro_ctx* ctx, const BandJob& job) {
 
 // Queues the device planner for band b behind its k_hist_total on ctx->stream, and the copy of the plan to pinned host
 // memory (read in end_call: statistics for the caller, the pass-A table shape of the next call).
-int plan_band_on_device(sarpro_ctx* ctx, int b, const BandJob& job) {
-    BandWs& w = ctx->band[b];
-    RC(reserve(ctx, w.plan_dev, sizeof(PlanDev)));
-    RC(reserve(ctx, w.plan_scratch, plan_scratch_bytes()));
-    PlanParams pr;
-    pr.strategy = job.strategy;
-    pr.kind = (int)job.kind;
-    pr.bit_depth = job.bit_depth;
-    pr.clahe = uses_clahe(job);
-    KS(SARPRO_STAGE_PLAN, launch_plan_band((const uint32_t*)w.total.p, (const double*)ctx->db_table.p, pr, (uint16_t*)w.lut.p,
-                                           (PlanDev*)w.plan_dev.p, w.plan_scratch.p, ctx->stream));
-    CU(cudaMemcpyAsync(&ctx->h_plan[b], w.plan_dev.p, sizeof(PlanDev), cudaMemcpyDeviceToHost, ctx->stream));
-    w.dev_planned = true;
-    w.plan_copy_pending = true;
-    w.plan.clahe = uses_clahe(job);
-    w.hist_auto_pending = true;
+int plan_bands_on_device(sarpro_ctx* ctx, const int* slots, const BandJob* jobs, int nb) {
+    PlanJobs pj{};
+    for (int k = 0; k < nb; ++k) {
+        BandWs& w = ctx->band[slots[k]];
+        RC(reserve(ctx, w.plan_dev, sizeof(PlanDev)));
+        RC(reserve(ctx, w.plan_scratch, plan_scratch_bytes()));
+        PlanParams pr;
+        pr.strategy = jobs[k].strategy;
+        pr.kind = (int)jobs[k].kind;
+        pr.bit_depth = jobs[k].bit_depth;
+        pr.clahe = uses_clahe(jobs[k]);
+        pj.j[k] = PlanJob{(const uint32_t*)w.total.p, (uint16_t*)w.lut.p, (PlanDev*)w.plan_dev.p, w.plan_scratch.p, pr};
+    }
+    KS(SARPRO_STAGE_PLAN, launch_plan_bands(pj, nb, (const double*)ctx->db_table.p, ctx->stream));
+    for (int k = 0; k < nb; ++k) {
+        BandWs& w = ctx->band[slots[k]];
+        CU(cudaMemcpyAsync(&ctx->h_plan[slots[k]], w.plan_dev.p, sizeof(PlanDev), cudaMemcpyDeviceToHost, ctx->stream));
+        w.dev_planned = true;
+        w.plan_copy_pending = true;
+        w.plan.clahe = uses_clahe(jobs[k]);
+        w.hist_auto_pending = true;
+    }
+    return 0;
+}
+int plan_band_on_device(sarpro_ctx* ctx, int b, const BandJob& job) { return plan_bands_on_device(ctx, &b, &job, 1); }
+
+// CLAHE tile statistics (256-bin tile histograms through the table, then clip / redistribute / CDF) for the given band slots in
+// one launch each. all_reduce: optional hook between the two (sharded scene: the tile histograms are merged over the ranks).
+int run_clahe_stats_bands(sarpro_ctx* ctx, const int* slots, int nb, int (*all_reduce)(sarpro_ctx*, void*), void* arg) {
+    ClaheStatJobs cj{};
+    for (int k = 0; k < nb; ++k) {
+        BandWs& w = ctx->band[slots[k]];
+        RC(reserve(ctx, w.tile256, (size_t)ctx->n_tiles * 256 * 4));
+        RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
+        RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
+        CU(cudaMemsetAsync(w.tile256.p, 0, (size_t)ctx->n_tiles * 256 * 4, ctx->stream));
+        cj.j[k] = ClaheStatJob{(const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, (const PlanDev*)w.plan_dev.p, (uint32_t*)w.tile256.p,
+                               (double*)w.cdf.p, (float*)w.cdf32.p};
+    }
+    KS(SARPRO_STAGE_PLAN, launch_clahe_tile256_2(cj, nb, ctx->n_tiles, ctx->stream));
+    if (all_reduce) RC(all_reduce(ctx, arg));
+    KS(SARPRO_STAGE_PLAN, launch_clahe_cdf_2(cj, nb, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles, ctx->stream));
     return 0;
 }
 
@@ -591,18 +617,7 @@ int run_pass_a_and_plan(sarpro_ctx* ctx, const BandJob* jobs, int nb) {
 }
 
 // CLAHE tile CDFs for band b (after the LUT is on the device)
-int run_clahe_stats(sarpro_ctx* ctx, int b) {
-    BandWs& w = ctx->band[b];
-    RC(reserve(ctx, w.tile256, (size_t)ctx->n_tiles * 256 * 4));
-    RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
-    RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
-    CU(cudaMemsetAsync(w.tile256.p, 0, (size_t)ctx->n_tiles * 256 * 4, ctx->stream));
-    KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles, (const PlanDev*)w.plan_dev.p,
-                            (uint32_t*)w.tile256.p, ctx->stream));
-    KS(SARPRO_STAGE_PLAN, launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles, (double*)w.cdf.p,
-                        (float*)w.cdf32.p, ctx->stream));
-    return 0;
-}
+int run_clahe_stats(sarpro_ctx* ctx, int b) { return run_clahe_stats_bands(ctx, &b, 1, nullptr, nullptr); }
 
 // Reads back the CLAHE sample min/max of band b and returns whether scale_u16_to_u8 is the identity.
 int clahe_minmax(sarpro_ctx* ctx, int b, uint32_t* mn, uint32_t* mx) {

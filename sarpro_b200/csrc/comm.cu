@@ -277,11 +277,16 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     }
     // ---- plans: on the device for the gamma == 1 strategies (no host round trip; every rank plans redundantly from the
     // merged histogram, bit-identically), else on the host from the merged dense totals
-    for (int b = 0; b < 2; ++b) {
-        BandWs& w = ctx->band[b];
-        if (plans_on_device(ctx, jobs[b])) {
-            RC(plan_band_on_device(ctx, b, jobs[b]));
-        } else {
+    const int both[2] = {0, 1};
+    if (plans_on_device(ctx, jobs[0]) && plans_on_device(ctx, jobs[1])) {
+        RC(plan_bands_on_device(ctx, both, jobs, 2)); // one launch, one CTA per band
+    } else {
+        for (int b = 0; b < 2; ++b) {
+            BandWs& w = ctx->band[b];
+            if (plans_on_device(ctx, jobs[b])) {
+                RC(plan_band_on_device(ctx, b, jobs[b]));
+                continue;
+            }
             CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             ctx->timing.host_syncs++;
@@ -294,31 +299,23 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
             w.hist_auto_pending = true;
         }
     }
-    // ---- 2. CLAHE tile histograms of both bands: one fused all-reduce, then every rank builds all 64 CDFs -------------------
+    // ---- 2. CLAHE tile histograms of both bands: one launch, one fused all-reduce, then every rank builds all 64 CDFs -------
     if (clahe) {
-        for (int b = 0; b < 2; ++b) {
-            BandWs& w = ctx->band[b];
-            RC(reserve(ctx, w.tile256, (size_t)ctx->n_tiles * 256 * 4));
-            RC(reserve(ctx, w.cdf, (size_t)ctx->n_tiles * 256 * 8));
-            RC(reserve(ctx, w.cdf32, (size_t)ctx->n_tiles * 256 * 4));
-            CU(cudaMemsetAsync(w.tile256.p, 0, (size_t)ctx->n_tiles * 256 * 4, ctx->stream));
-            KS(SARPRO_STAGE_PLAN, launch_clahe_tile256((const uint32_t*)w.tile_hist.p, (const uint16_t*)w.lut.p, ctx->n_tiles,
-                                                       (const PlanDev*)w.plan_dev.p, (uint32_t*)w.tile256.p, ctx->stream));
-        }
-        {
-            COMM_BEGIN();
-            NC(api.GroupStart());
-            for (int b = 0; b < 2; ++b)
-                NC(api.AllReduce(ctx->band[b].tile256.p, ctx->band[b].tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum, cs->comm,
-                                 ctx->stream));
-            NC(api.GroupEnd());
-            COMM_END();
-        }
-        for (int b = 0; b < 2; ++b) {
-            BandWs& w = ctx->band[b];
-            KS(SARPRO_STAGE_PLAN, launch_clahe_cdf((const uint32_t*)w.tile256.p, (const uint64_t*)ctx->tile_px.p, ctx->n_tiles,
-                                                   (double*)w.cdf.p, (float*)w.cdf32.p, ctx->stream));
-        }
+        struct Hook {
+            static int reduce(sarpro_ctx* ctx, void*) {
+                NcclApi& api = nccl();
+                CommState* cs = ctx->comm;
+                COMM_BEGIN();
+                NC(api.GroupStart());
+                for (int b = 0; b < 2; ++b)
+                    NC(api.AllReduce(ctx->band[b].tile256.p, ctx->band[b].tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum, cs->comm,
+                                     ctx->stream));
+                NC(api.GroupEnd());
+                COMM_END();
+                return 0;
+            }
+        };
+        RC(run_clahe_stats_bands(ctx, both, 2, &Hook::reduce, nullptr));
     }
     // ---- pass B: horizontal pass over the held rows; band 0 on the side stream so that band 1's persistent CTAs fill the
     // SMs band 0's leave early

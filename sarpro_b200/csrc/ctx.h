@@ -206,6 +206,8 @@ int end_call(sarpro_ctx* ctx);
 struct BandJob;
 bool plans_on_device(const sarpro_ctx* ctx, const BandJob& job);
 int plan_band_on_device(sarpro_ctx* ctx, int b, const BandJob& job);
+int plan_bands_on_device(sarpro_ctx* ctx, const int* slots, const BandJob* jobs, int nb);
+int run_clahe_stats_bands(sarpro_ctx* ctx, const int* slots, int nb, int (*all_reduce)(sarpro_ctx*, void*), void* arg);
 int upload_plan_dev(sarpro_ctx* ctx, int b);
 
 #define CU(call)                                                                                             \

@@ -37,10 +37,18 @@ struct PlanParams {
 // strategies the device planner covers (gamma == 1: no pow); the others are planned on the host
 bool plan_on_device_supported(int strategy, int kind);
 // total: [65536] u32 DN counts; db_table: [65536] f64 dB of every DN (plan.cpp dn_db_table); lut: [65536] u16 out
-// scratch: plan_scratch_bytes() of device memory (the list of present DNs when it does not fit shared memory)
+// One planner job per band; scratch: plan_scratch_bytes() of device memory (the list of present DNs when it does not fit
+// shared memory). Up to two bands per launch (one CTA each).
+struct PlanJob {
+    const uint32_t* total;
+    uint16_t* lut;
+    PlanDev* out;
+    void* scratch;
+    PlanParams params;
+};
+struct PlanJobs { PlanJob j[2]; };
 size_t plan_scratch_bytes();
-cudaError_t launch_plan_band(const uint32_t* total, const double* db_table, const PlanParams& pr, uint16_t* lut, PlanDev* out,
-                             void* scratch, cudaStream_t stream);
+cudaError_t launch_plan_bands(const PlanJobs& jobs, int n_bands, const double* db_table, cudaStream_t stream);
 
 // ---- work decomposition -----------------------------------------------------------------
 // A histogram work unit: rows [r0,r1) x cols [c0,c1) of the local raster, all inside one tile.
@@ -64,9 +72,20 @@ cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint3
 
 // ---- CLAHE tile statistics ------------------------------------------------------------------
 // tile256[t][bin] = sum over dn>=1 of tile_hist[t][dn] where lut[dn] == bin (autoscale.rs:259-269)
-// plan->max_present_dn bounds the walk (read on the device)
+// plan->max_present_dn bounds the walk (read on the device). The *2 variants take both bands of a pair in one launch.
 cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut, uint32_t n_tiles, const PlanDev* plan,
                                  uint32_t* tile256, cudaStream_t stream);
+struct ClaheStatJob {
+    const uint32_t* tile_hist;
+    const uint16_t* lut;
+    const PlanDev* plan;
+    uint32_t* tile256;
+    double* cdf;
+    float* cdf32;
+};
+struct ClaheStatJobs { ClaheStatJob j[2]; };
+cudaError_t launch_clahe_tile256_2(const ClaheStatJobs& jobs, int n_bands, uint32_t n_tiles, cudaStream_t stream);
+cudaError_t launch_clahe_cdf_2(const ClaheStatJobs& jobs, int n_bands, const uint64_t* tile_px, uint32_t n_tiles, cudaStream_t stream);
 // clip / redistribute / CDF per tile (autoscale.rs:271-302). tile_px[t] = tile_rows*tile_cols.
 cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, uint32_t n_tiles, double* cdf,
                              float* cdf32, cudaStream_t stream);

@@ -320,10 +320,13 @@ cudaError_t launch_hist_total(const uint32_t* tile_hist, uint32_t n_tiles, uint3
 // =============================================================================================
 // CLAHE tile statistics
 // =============================================================================================
-__global__ void k_clahe_tile256(const uint32_t* __restrict__ tile_hist, const uint16_t* __restrict__ lut,
-                                const PlanDev* __restrict__ plan, uint32_t* __restrict__ tile256) {
+__global__ void k_clahe_tile256(ClaheStatJobs jobs) {
     __shared__ uint32_t h[256];
-    const uint32_t max_dn = plan->max_present_dn;
+    const ClaheStatJob& jb = jobs.j[blockIdx.z]; // one band per grid layer
+    const uint32_t* __restrict__ tile_hist = jb.tile_hist;
+    const uint16_t* __restrict__ lut = jb.lut;
+    uint32_t* __restrict__ tile256 = jb.tile256;
+    const uint32_t max_dn = jb.plan->max_present_dn;
     const uint32_t t = blockIdx.x, part = blockIdx.y, nparts = gridDim.y;
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -339,19 +342,26 @@ cudaError_t launch_clahe_tile256(const uint32_t* tile_hist, const uint16_t* lut,
                                  uint32_t* tile256, cudaStream_t stream) {
     // the brightest present DN is only known on the device: a fixed split of the DN range (a GRD band ends below DN 4096
     // except for point targets; CTAs whose share lies beyond max_dn return at once)
+    ClaheStatJobs jobs{};
+    jobs.j[0] = ClaheStatJob{tile_hist, lut, plan, tile256, nullptr, nullptr};
+    return launch_clahe_tile256_2(jobs, 1, n_tiles, stream);
+}
+cudaError_t launch_clahe_tile256_2(const ClaheStatJobs& jobs, int n_bands, uint32_t n_tiles, cudaStream_t stream) {
     const uint32_t parts = 8;
-    k_clahe_tile256<<<dim3(n_tiles, parts), 256, 0, stream>>>(tile_hist, lut, plan, tile256);
+    k_clahe_tile256<<<dim3(n_tiles, parts, (unsigned)n_bands), 256, 0, stream>>>(jobs);
     return cudaGetLastError();
 }
 
 // autoscale.rs:271-302. Every quantity is an integer or an integer multiple of 1/128 below 2^53, so the
 // f64 sums are exact and independent of summation order; products/quotients use explicit round-to-nearest
 // intrinsics (never contracted to FMA).
-__global__ void __launch_bounds__(256) k_clahe_cdf(const uint32_t* __restrict__ tile256,
-                                                   const uint64_t* __restrict__ tile_px, double* __restrict__ cdf,
-                                                   float* __restrict__ cdf32) {
+__global__ void __launch_bounds__(256) k_clahe_cdf(ClaheStatJobs jobs, const uint64_t* __restrict__ tile_px) {
     __shared__ double s_ex[256];
     __shared__ unsigned long long s_pre[256];
+    const ClaheStatJob& jb = jobs.j[blockIdx.y]; // one band per grid row
+    const uint32_t* __restrict__ tile256 = jb.tile256;
+    double* __restrict__ cdf = jb.cdf;
+    float* __restrict__ cdf32 = jb.cdf32;
     const uint32_t t = blockIdx.x, i = threadIdx.x;
     uint32_t h = tile256[t * 256u + i];
     const double avg = __ddiv_rn((double)tile_px[t], 256.0);       // :242-245
@@ -389,7 +399,12 @@ __global__ void __launch_bounds__(256) k_clahe_cdf(const uint32_t* __restrict__ 
 }
 cudaError_t launch_clahe_cdf(const uint32_t* tile256, const uint64_t* tile_px, uint32_t n_tiles, double* cdf,
                              float* cdf32, cudaStream_t stream) {
-    k_clahe_cdf<<<n_tiles, 256, 0, stream>>>(tile256, tile_px, cdf, cdf32);
+    ClaheStatJobs jobs{};
+    jobs.j[0] = ClaheStatJob{nullptr, nullptr, nullptr, const_cast<uint32_t*>(tile256), cdf, cdf32};
+    return launch_clahe_cdf_2(jobs, 1, tile_px, n_tiles, stream);
+}
+cudaError_t launch_clahe_cdf_2(const ClaheStatJobs& jobs, int n_bands, const uint64_t* tile_px, uint32_t n_tiles, cudaStream_t stream) {
+    k_clahe_cdf<<<dim3(n_tiles, (unsigned)n_bands), 256, 0, stream>>>(jobs, tile_px);
     return cudaGetLastError();
 }
 

@@ -75,20 +75,25 @@ struct OpAddF64 { __device__ double operator()(double a, double b) const { retur
 // Entries of the present DNs, compacted by the kernel itself: in shared memory when there are at most kPlanCap of them (a GRD
 // band has a few thousand), else in a global scratch buffer (every u16 value present: same code, slower).
 constexpr uint32_t kPlanCap = 8192;
-constexpr size_t kPlanDynSmem = (size_t)kPlanCap * (8 + 4 + 2 + 2);
+constexpr size_t kPlanDynSmem = (size_t)kPlanCap * (8 + 4 + 2 + 2) + 4096 * 8; // entries + the prefix sums of the stat histogram
 constexpr size_t kPlanScratchBytes = (size_t)65536 * (8 + 4 + 2 + 2);
 
 __global__ void __launch_bounds__(kPlanThreads, 1)
-k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, PlanParams pr, uint16_t* __restrict__ lut,
-            PlanDev* __restrict__ out, unsigned char* __restrict__ scratch) {
+k_plan_band(PlanJobs jobs, const double* __restrict__ db) {
+    // one CTA per band (blockIdx.x): the two bands of a pair can be planned by one launch
+    const uint32_t* __restrict__ total = jobs.j[blockIdx.x].total;
+    uint16_t* __restrict__ lut = jobs.j[blockIdx.x].lut;
+    PlanDev* __restrict__ out = jobs.j[blockIdx.x].out;
+    unsigned char* __restrict__ scratch = reinterpret_cast<unsigned char*>(jobs.j[blockIdx.x].scratch);
+    const PlanParams pr = jobs.j[blockIdx.x].params;
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ unsigned long long s_cum[kStatBinsDev]; // 4096-bin histogram (autoscale.rs:103-117), then its inclusive prefix sums
+    unsigned long long* const s_cum = reinterpret_cast<unsigned long long*>(s_dyn + (size_t)kPlanCap * 16); // inclusive prefix sums
+    __shared__ uint32_t s_hist[kStatBinsDev]; // 4096-bin histogram (autoscale.rs:103-117); a bin holds < 2^32 pixels (rasters are below 2^32 samples)
     __shared__ unsigned long long s_u64[33];
     __shared__ uint32_t s_u32[33];
     __shared__ int s_i32[33];
     __shared__ double s_f64[33];
     __shared__ double s_pct[11];
-    __shared__ double s_win[3]; // low, high, range
     __shared__ uint8_t s_remap[256];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
 
@@ -162,14 +167,42 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
             invalid_present = 1;
         }
     }
-    const unsigned long long count = block_reduce(cnt, OpAddU64(), s_u64);
-    const unsigned long long px_total = block_reduce(px, OpAddU64(), s_u64);
-    const unsigned long long px_ge1024 = block_reduce(ge1k, OpAddU64(), s_u64);
-    const unsigned long long px_ge2048 = block_reduce(ge2k, OpAddU64(), s_u64);
-    const uint32_t min_dn = block_reduce(first_valid, OpMinU32(), s_u32);
-    const uint32_t max_valid_dn = block_reduce(last_valid, OpMaxU32(), s_u32);
-    const uint32_t max_present_dn = block_reduce(last_present, OpMaxU32(), s_u32);
-    const bool have_invalid = block_reduce(invalid_present, OpMaxU32(), s_u32) != 0;
+    // one combined block reduction (two barriers) instead of eight: a single-CTA kernel is paced by its barriers
+    __shared__ unsigned long long s_r64[4][32];
+    __shared__ uint32_t s_r32[4][32];
+    __shared__ unsigned long long s_o64[4];
+    __shared__ uint32_t s_o32[4];
+    {
+        unsigned long long a[4] = {cnt, px, ge1k, ge2k};
+        uint32_t m[4] = {first_valid, ~last_valid, ~last_present, ~invalid_present}; // all as minima
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+                m[j] = min(m[j], __shfl_xor_sync(0xffffffffu, m[j], o));
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s_r64[j][wid] = a[j]; s_r32[j][wid] = m[j]; }
+        }
+        __syncthreads();
+        if (wid < 4) { // warp j finishes value j of both groups
+            unsigned long long x = s_r64[wid][lane];
+            uint32_t y = s_r32[wid][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x += __shfl_xor_sync(0xffffffffu, x, o);
+                y = min(y, __shfl_xor_sync(0xffffffffu, y, o));
+            }
+            if (lane == 0) { s_o64[wid] = x; s_o32[wid] = y; }
+        }
+        __syncthreads();
+    }
+    const unsigned long long count = s_o64[0], px_total = s_o64[1], px_ge1024 = s_o64[2], px_ge2048 = s_o64[3];
+    const uint32_t min_dn = s_o32[0], max_valid_dn = ~s_o32[1], max_present_dn = ~s_o32[2];
+    const bool have_invalid = (~s_o32[3]) != 0;
 
     if (count == 0) { // all-zero output (autoscale.rs:376-378, 466-468, 716-718): every table word is 0
         if (tid == 0) {
@@ -205,7 +238,7 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
     // ---- pass 2 (autoscale.rs:103-117) + percentiles (:120-159) ---------------------------------------------------------
     const bool degenerate = fabs(__dsub_rn(max_db, min_db)) < DBL_EPSILON; // autoscale.rs:81
     if (!degenerate) {
-        for (uint32_t i = tid; i < (uint32_t)kStatBinsDev; i += kPlanThreads) s_cum[i] = 0ull;
+        for (uint32_t i = tid; i < (uint32_t)kStatBinsDev; i += kPlanThreads) s_hist[i] = 0u;
         __syncthreads();
         const double span = __dsub_rn(max_db, min_db);
         const double inv_span = __ddiv_rn(1.0, span);
@@ -214,13 +247,13 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
                 const double t = clampd_dev(__dmul_rn(__dsub_rn(e_db[i], min_db), inv_span), 0.0, 1.0);
                 unsigned long long idx = cast_u64_dev(__dmul_rn(t, (double)kStatBinsDev));
                 if (idx >= (unsigned long long)kStatBinsDev) idx = kStatBinsDev - 1;
-                atomicAdd(&s_cum[idx], (unsigned long long)e_h[i]);
+                atomicAdd(&s_hist[idx], e_h[i]);
             }
         __syncthreads();
         // inclusive prefix sums in place: four bins per thread, then the block-wide offsets
         unsigned long long v[4], run = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { run += s_cum[tid * 4 + i]; v[i] = run; }
+        for (int i = 0; i < 4; ++i) { run += s_hist[tid * 4 + i]; v[i] = run; }
         {
             unsigned long long inc64 = run;
 #pragma unroll
@@ -265,35 +298,29 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
                  p90 = s_pct[7], p95 = s_pct[8], p98 = s_pct[9], p99 = s_pct[10];
 
     // ---- window (plan.cpp choose_window; only the gamma == 1 arms) ------------------------------------------------------
-    if (tid == 0) {
-        double low, high;
-        if (pr.kind == 1) { // TamedSynRgbCopol, autoscale.rs:721-723
-            low = fmin(p02, p05);
-            high = p99;
-        } else if (pr.kind == 2) { // TamedSynRgbCross, autoscale.rs:724-727
-            low = p05;
-            high = p99;
-        } else if (pr.strategy == SARPRO_STRATEGY_ROBUST) { // autoscale.rs:492-499
-            const double iqr = __dsub_rn(p75, p25);
-            const double thr = __dmul_rn(2.5, iqr);
-            low = fmax(fmax(__dsub_rn(p25, thr), p01), min_db);
-            high = fmin(fmin(__dadd_rn(p75, thr), p99), max_db);
-        } else if (pr.strategy == SARPRO_STRATEGY_EQUALIZED || pr.strategy == SARPRO_STRATEGY_CLAHE) { // :539-548
-            low = p01;
-            high = p99;
-        } else if (pr.strategy == SARPRO_STRATEGY_TAMED) { // :549-553
-            low = p25;
-            high = p99;
-        } else { // Default, :554-561
-            low = p05;
-            high = p95;
-        }
-        s_win[0] = low;
-        s_win[1] = high;
-        s_win[2] = fmax(__dsub_rn(high, low), 1.0); // autoscale.rs:429, 564, 729
+    double low, high; // (every thread computes the window: cheaper than a barrier)
+    if (pr.kind == 1) { // TamedSynRgbCopol, autoscale.rs:721-723
+        low = fmin(p02, p05);
+        high = p99;
+    } else if (pr.kind == 2) { // TamedSynRgbCross, autoscale.rs:724-727
+        low = p05;
+        high = p99;
+    } else if (pr.strategy == SARPRO_STRATEGY_ROBUST) { // autoscale.rs:492-499
+        const double iqr = __dsub_rn(p75, p25);
+        const double thr = __dmul_rn(2.5, iqr);
+        low = fmax(fmax(__dsub_rn(p25, thr), p01), min_db);
+        high = fmin(fmin(__dadd_rn(p75, thr), p99), max_db);
+    } else if (pr.strategy == SARPRO_STRATEGY_EQUALIZED || pr.strategy == SARPRO_STRATEGY_CLAHE) { // :539-548
+        low = p01;
+        high = p99;
+    } else if (pr.strategy == SARPRO_STRATEGY_TAMED) { // :549-553
+        low = p25;
+        high = p99;
+    } else { // Default, :554-561
+        low = p05;
+        high = p95;
     }
-    __syncthreads();
-    const double low = s_win[0], high = s_win[1], range = s_win[2];
+    const double range = fmax(__dsub_rn(high, low), 1.0); // autoscale.rs:429, 564, 729
 
     // ---- the table ------------------------------------------------------------------------------------------------------
     const bool tamed_rgb = pr.kind != 0;
@@ -329,8 +356,25 @@ k_plan_band(const uint32_t* __restrict__ total, const double* __restrict__ db, P
     uint32_t pre_min = 0, pre_max = 0;
     if (!clahe) {
         if (have_invalid) { mn = 0; } // invalid pixels are samples of value 0
-        pre_min = block_reduce(mn, OpMinU32(), s_u32);
-        pre_max = block_reduce(mx, OpMaxU32(), s_u32);
+        {   // {min, max} in one reduction: 16-bit values, packed as (mn << 16) | (0xffff - mx), minimum of both halves
+            uint32_t a = mn, b = 0xffffu - mx;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+                b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+            }
+            if (lane == 0) { s_r32[0][wid] = a; s_r32[1][wid] = b; }
+            __syncthreads();
+            if (wid < 2) {
+                uint32_t y = s_r32[wid][lane];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) y = min(y, __shfl_xor_sync(0xffffffffu, y, o));
+                if (lane == 0) s_o32[wid] = y;
+            }
+            __syncthreads();
+            pre_min = s_o32[0];
+            pre_max = 0xffffu - s_o32[1];
+        }
         if (!tamed_rgb && pr.bit_depth == SARPRO_U8) { // scale_u16_to_u8 over ALL pixels (autoscale.rs:352-363, :669-670, :691-693)
             if (tid < 256) {
                 const float fmn = (float)pre_min, fmx = (float)pre_max;
@@ -406,10 +450,10 @@ bool plan_on_device_supported(int strategy, int kind) {
 
 size_t plan_scratch_bytes() { return kPlanScratchBytes; }
 
-cudaError_t launch_plan_band(const uint32_t* total, const double* db_table, const PlanParams& pr, uint16_t* lut, PlanDev* out,
-                             void* scratch, cudaStream_t stream) {
+cudaError_t launch_plan_bands(const PlanJobs& jobs, int n_bands, const double* db_table, cudaStream_t stream) {
+    if (n_bands < 1 || n_bands > 2) return cudaErrorInvalidValue;
     if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_plan_band), kPlanDynSmem)) return e;
-    k_plan_band<<<1, kPlanThreads, kPlanDynSmem, stream>>>(total, db_table, pr, lut, out, reinterpret_cast<unsigned char*>(scratch));
+    k_plan_band<<<n_bands, kPlanThreads, kPlanDynSmem, stream>>>(jobs, db_table);
     return cudaGetLastError();
 }
 
