@@ -314,15 +314,16 @@ int prepare_pieces(sarpro_ctx* ctx, int slot, uint64_t rows, uint64_t row_off, b
     // Whole rounds of 16-row groups, one group per warp (12 warps for CLAHE, 16 otherwise), so that only the last piece of a
     // vertical cell ends with a partly filled round. Short rasters (a rank's band of a sharded scene) do not have a round per
     // CTA: the unit shrinks to the groups a CTA gets, so that every SM still takes a share.
+    const std::vector<HStrip>& weights = ah->m_weights_h;
     const uint32_t warps = hmma_warps(clahe);
     // band 0 of a pipelined pair leaves ctx->pair_spare SMs to band 1's planner and CLAHE statistics, which run beside it
     const uint32_t n_ctas = (uint32_t)std::max(1, ctx->sm_count - (slot == 0 ? ctx->pair_spare : 0));
-    const uint64_t groups = (rows + 15) / 16 * std::max<size_t>(1, ah->m_weights_h.size());
+    const uint64_t groups = (rows + 15) / 16 * std::max<size_t>(1, weights.size());
     const uint32_t per_cta = (uint32_t)std::max<uint64_t>(1, groups / n_ctas);
     const uint32_t unit = 16u * std::min(warps, per_cta);
     std::vector<uint32_t> pieces, first;
     uint32_t max_rows = 0;
-    hmma_build_pieces(ah->m_weights_h, cuts, n_ctas, unit, &pieces, &first, &max_rows);
+    hmma_build_pieces(weights, cuts, n_ctas, unit, &pieces, &first, &max_rows);
     RC(reserve(ctx, w.pieces, std::max<size_t>(pieces.size() * 4, 16)));
     RC(reserve(ctx, w.cta_first, std::max<size_t>(first.size() * 4, 16)));
     CU(cudaMemcpyAsync(w.pieces.p, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -361,10 +362,11 @@ int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int
         fprintf(stderr, "run_hpass: kind %d pix16 %d mma %d plan %p remap %p skip %p src%%16 %d smem %zu rows %u cols %u\n", src_kind, pix16,
                 (int)ah->mma, (const void*)a.plan, (const void*)a.remap, (const void*)a.skip, (int)(reinterpret_cast<uintptr_t>(a.src) % 16),
                 ah->mma ? hmma_smem_bytes(src_kind, ah->m_b_bytes) : 0, a.n_rows, a.src_cols);
-    const bool shape_ok = !pix16 && ah->mma && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.plan && !a.remap &&
-                          (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && (uint64_t)a.src_rows * a.src_cols < (1ull << 32) &&
-                          hmma_smem_bytes(src_kind, ah->m_b_bytes) <= 227 * 1024;
-    if (shape_ok && (w.dev_planned || w.hot)) {
+    const bool common_ok = !pix16 && ctx->use_hmma && !ctx->force_exact && src_kind != HSRC_IMAGE && a.plan && !a.remap &&
+                           (reinterpret_cast<uintptr_t>(a.src) % 16) == 0 && (uint64_t)a.src_rows * a.src_cols < (1ull << 32) &&
+                           (w.dev_planned || w.hot);
+    const bool shape_ok = common_ok && ah->mma && hmma_smem_bytes(src_kind, ah->m_b_bytes) <= 227 * 1024;
+    if (shape_ok) {
         RC(prepare_pieces(ctx, slot, a.n_rows, row_off, src_kind == HSRC_DN_CLAHE, ah));
         KS(SARPRO_STAGE_APPLY, launch_hmma(a, src_kind, (const uint4*)ah->m_btab.p, (const int4*)ah->m_ntile.p, (const uint4*)ah->m_strips.p,
                                            (const uint32_t*)w.pieces.p, (const uint32_t*)w.cta_first.p, w.pc_n_ctas,
