@@ -229,6 +229,14 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
                                    int strategy, int mode, int has_target, size_t target, int pad,
                                    int tamed_band_step, sarpro_image* out);
 
+/* Row-band-sharded polarization-op band at full resolution (BASELINE config 4: ops.rs:4-44 -> pipeline.rs:42-66 -> no resize): the
+ * rank passes ITS row band of both inputs (f32, or the raw u16 DN), any contiguous split of the scene's rows; the library merges
+ * the scan (min / max / valid count) and the 4096-bin stat histogram over the ranks (integers and bit patterns: identical to the
+ * unsharded values), every rank derives the same window, and the rank's rows of the result are written to `out` (rows x cols
+ * samples of bit_depth). All strategies except CLAHE (whose tile statistics need the scene geometry). */
+int sarpro_pipeline_single_sharded(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, size_t scene_rows, int op, int bit_depth,
+                                   int strategy, sarpro_image* out, sarpro_stats* stats);
+
 /* ---- host-only planner entry points (pure CPU; used by tests and by multi-rank hosts) ---- */
 /* Statistics + window + DN->sample LUT from a 65,536-bin DN histogram, i.e. what
  * compute_histogram_stats (autoscale.rs:35-160) + autoscale_db_image[_advanced] (:368-659) +

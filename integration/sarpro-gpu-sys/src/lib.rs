@@ -123,6 +123,7 @@ extern "C" {
     pub fn sarpro_shard_rows(rows: usize, world: c_int, rank: c_int, clahe: c_int, r0: *mut usize, r1: *mut usize) -> c_int;
     pub fn sarpro_shard_halo_rows(rows: usize, cols: usize, has_target: c_int, target: usize, world: c_int, rank: c_int, clahe: c_int, h0: *mut usize, h1: *mut usize) -> c_int;
     pub fn sarpro_pipeline_synrgb_sharded(ctx: *mut sarpro_ctx, b1: *const sarpro_band, b2: *const sarpro_band, scene_rows: usize, strategy: c_int, mode: c_int, has_target: c_int, target: usize, pad: c_int, tamed_band_step: c_int, out: *mut sarpro_image) -> c_int;
+    pub fn sarpro_pipeline_single_sharded(ctx: *mut sarpro_ctx, a: *const sarpro_band, b: *const sarpro_band, scene_rows: usize, op: c_int, bit_depth: c_int, strategy: c_int, out: *mut sarpro_image, stats: *mut sarpro_stats) -> c_int;
     pub fn sarpro_plan_from_dn_histogram(hist65536: *const u64, bit_depth: c_int, strategy: c_int, stats: *mut sarpro_stats, lut16: *mut u16) -> c_int;
     pub fn sarpro_plan_from_present_list(blocks: *const u32, pairs: *const u32, cap: u32, bit_depth: c_int, strategy: c_int, stats: *mut sarpro_stats, lut16: *mut u16) -> c_int;
     pub fn sarpro_plan_on_device(ctx: *mut sarpro_ctx, hist65536: *const u32, bit_depth: c_int, strategy: c_int, plan_kind: c_int, stats: *mut sarpro_stats, lut16: *mut u16, hot2: *mut u32) -> c_int;

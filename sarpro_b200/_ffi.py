@@ -112,6 +112,7 @@ SYMBOLS = {
     "sarpro_shard_rows": (_I, [_SZ, _I, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "sarpro_shard_halo_rows": (_I, [_SZ, _SZ, _I, _SZ, _I, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "sarpro_pipeline_synrgb_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, _SZ, _I, _I, C.POINTER(Image)]),
+    "sarpro_pipeline_single_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, C.POINTER(Image), C.POINTER(Stats)]),
     "sarpro_plan_from_dn_histogram": (_I, [_P, _I, _I, C.POINTER(Stats), _P]),
     "sarpro_plan_from_present_list": (_I, [_P, _P, C.c_uint32, _I, _I, C.POINTER(Stats), _P]),
     "sarpro_plan_on_device": (_I, [_P, _P, _I, _I, _I, C.POINTER(Stats), _P, _P]),

@@ -816,8 +816,23 @@ int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band*
         *dn_out = (const uint16_t*)w.dn.p;
         return 0;
     }
+    if (op >= 0 && in->dtype == SARPRO_DT_U16 && in2->dtype == SARPRO_DT_U16) {
+        // raw DN pair through a polarization op: the loaders of the general path read the u16 rasters directly (2 B per sample
+        // instead of the 4 B of the f32 the reference reads them as, gdal.rs:123; same values)
+        const sarpro_band* bs[2] = {in, in2};
+        DevBuf* stg[2] = {&w.f32a, &w.f32b};
+        for (int k = 0; k < 2; ++k)
+            if (bs[k]->location == SARPRO_LOC_HOST) {
+                RC(reserve(ctx, *stg[k], n * 2));
+                CU(cudaMemcpyAsync(stg[k]->p, bs[k]->data, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+                ctx->timing.h2d_bytes += n * 2;
+            }
+        *integral = false;
+        *dn_out = nullptr;
+        return 0;
+    }
     if (in->dtype != SARPRO_DT_F32 || (op >= 0 && in2->dtype != SARPRO_DT_F32))
-        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "polarization ops take f32 bands (ops.rs:4-44)");
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "polarization ops take two f32 bands or two u16 DN bands (ops.rs:4-44)");
     const float* fa = (const float*)in->data;
     const float* fb = op >= 0 ? (const float*)in2->data : nullptr;
     if (in->location == SARPRO_LOC_HOST) {
@@ -1019,9 +1034,10 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
         if ((break_rc = reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)))) break;
         canvases[b] = w.small.p;
         if (!integral[b]) {
-            const float* fa = ins[b]->location == SARPRO_LOC_HOST ? (const float*)w.f32a.p : (const float*)ins[b]->data;
-            const float* fb = ops[b] >= 0 ? (ins2[b]->location == SARPRO_LOC_HOST ? (const float*)w.f32b.p : (const float*)ins2[b]->data) : nullptr;
-            RC(f32_general_single(ctx, b, fa, fb, ops[b], rows, cols, bit_depths[b], strategies[b], kinds[b], *geom, w.small.p,
+            const void* fa = ins[b]->location == SARPRO_LOC_HOST ? w.f32a.p : ins[b]->data;
+            const void* fb = ops[b] >= 0 ? (ins2[b]->location == SARPRO_LOC_HOST ? w.f32b.p : ins2[b]->data) : nullptr;
+            const int a16 = ins[b]->dtype == SARPRO_DT_U16, b16 = ops[b] >= 0 && ins2[b]->dtype == SARPRO_DT_U16;
+            RC(f32_general_single(ctx, b, fa, fb, a16, b16, ops[b], rows, cols, bit_depths[b], strategies[b], kinds[b], *geom, w.small.p,
                                   stats ? &stats[b] : nullptr));
             continue;
         }

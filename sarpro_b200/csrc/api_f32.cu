@@ -24,7 +24,11 @@ namespace {
 inline float float_of_bits(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 } // namespace
 
-int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const float* b_dev, int op, uint64_t rows,
+// a_dev / b_dev: f32 rasters, or u16 DN rasters when a_u16 / b_u16 is set (the loaders convert: the f32 the reference would
+// have read from the same TIFF, gdal.rs:123). When the context is in a sharded call (ctx->shard_reduce), the raster is this
+// rank's row band of a scene: the scan and the stat histogram are merged over the ranks (integers and bit patterns: the merged
+// values are those of the whole scene) before every rank derives the same window redundantly.
+int f32_general_single(sarpro_ctx* ctx, int slot, const void* a_dev, const void* b_dev, int a_u16, int b_u16, int op, uint64_t rows,
                        uint64_t cols, int bit_depth, int strategy, PlanKind kind, const OutGeom& g, void* canvas,
                        sarpro_stats* stats_out) {
     BandWs& w = ctx->band[slot];
@@ -43,7 +47,8 @@ int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const floa
     F32Scan init{0xffffffffu, 0u, 0ull};
     CU(cudaMemsetAsync(w.f32scan.p, 0, 4096 * 8 + 64, ctx->stream));
     CU(cudaMemcpyAsync(scan_dev, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    KS(SARPRO_STAGE_HIST, launch_f32_scan(a_dev, b_dev, 0, 0, op, n, ctx->valid_thresh, scan_dev, ctx->sm_count, ctx->stream));
+    KS(SARPRO_STAGE_HIST, launch_f32_scan(a_dev, b_dev, a_u16, b_u16, op, n, ctx->valid_thresh, scan_dev, ctx->sm_count, ctx->stream));
+    if (ctx->shard_reduce) RC(comm_reduce_f32_scan(ctx, scan_dev));
     F32Scan scan;
     CU(cudaMemcpyAsync(&scan, scan_dev, sizeof(scan), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -75,9 +80,10 @@ int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const floa
         build_stat_edges(min_v, max_v, &edges);
         RC(reserve(ctx, w.edges, (size_t)65536 * 4 + 1024));
         CU(cudaMemcpyAsync(w.edges.p, edges.data(), kStatBins * 4, cudaMemcpyHostToDevice, ctx->stream));
-        KS(SARPRO_STAGE_HIST, launch_f32_hist4096(a_dev, b_dev, 0, 0, op, n, ctx->valid_thresh, (float)min_db,
+        KS(SARPRO_STAGE_HIST, launch_f32_hist4096(a_dev, b_dev, a_u16, b_u16, op, n, ctx->valid_thresh, (float)min_db,
                                                   (float)(4096.0 / (max_db - min_db)), (const float*)w.edges.p, hist_dev,
                                                   sums_dev, ctx->sm_count, ctx->stream));
+        if (ctx->shard_reduce) RC(comm_reduce_f32_hist(ctx, hist_dev, sums_dev));
         double sums[2];
         CU(cudaMemcpyAsync(h4096.data(), hist_dev, kStatBins * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(sums, sums_dev, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -103,7 +109,7 @@ int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const floa
         build_level_edges(LevelKind::ClaheBin, low, high, 1.0, 255, min_v, max_v, &ledges, nullptr, nullptr);
         CU(cudaMemcpyAsync(w.edges.p, ledges.data(), ledges.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         RC(reserve(ctx, w.dn, n * 2));
-        KS(SARPRO_STAGE_CONVERT, launch_f32_quantize(a_dev, b_dev, 0, 0, op, n, ctx->valid_thresh, (float)low, (float)high, 1.0f,
+        KS(SARPRO_STAGE_CONVERT, launch_f32_quantize(a_dev, b_dev, a_u16, b_u16, op, n, ctx->valid_thresh, (float)low, (float)high, 1.0f,
                                                      (const float*)w.edges.p, 255, nullptr, 1, nullptr, (uint16_t*)w.dn.p,
                                                      ctx->sm_count, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream)); // ledges is a host temporary
@@ -128,7 +134,7 @@ int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const floa
         // scale_u16_to_u8 over all pixels: levels are monotone in the sample, so the extrema are the levels of
         // the smallest / largest valid sample, plus 0 when any pixel is invalid (autoscale.rs:348-364, 669-670)
         uint32_t mn = lvl_min, mx = lvl_max;
-        if (scan.valid_count < n) mn = 0;
+        if (scan.valid_count < (ctx->shard_reduce ? ctx->shard_scene_px : n)) mn = 0;
         RC(reserve(ctx, w.remap, 256));
         make_u16_to_u8_remap((uint16_t)mn, (uint16_t)mx, 256, ctx->h_remap + 256 * slot);
         CU(cudaMemcpyAsync(w.remap.p, ctx->h_remap + 256 * slot, 256, cudaMemcpyHostToDevice, ctx->stream));
@@ -139,7 +145,7 @@ int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const floa
         RC(reserve(ctx, w.full, n * esz));
         plane = w.full.p;
     }
-    KS(SARPRO_STAGE_APPLY, launch_f32_quantize(a_dev, b_dev, 0, 0, op, n, ctx->valid_thresh, (float)low, (float)high, (float)gamma,
+    KS(SARPRO_STAGE_APPLY, launch_f32_quantize(a_dev, b_dev, a_u16, b_u16, op, n, ctx->valid_thresh, (float)low, (float)high, (float)gamma,
                                                (const float*)w.edges.p, n_levels, remap_dev, 0, out8 ? (uint8_t*)plane : nullptr,
                                                out8 ? nullptr : (uint16_t*)plane, ctx->sm_count, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream)); // ledges is a host temporary

@@ -23,8 +23,8 @@ namespace sarpro {
 
 typedef struct { char internal[128]; } nccl_unique_id;
 typedef void* nccl_comm_t;
-enum { kNcclUint8 = 1, kNcclUint32 = 3 };
-enum { kNcclSum = 0, kNcclMax = 2 };
+enum { kNcclUint8 = 1, kNcclUint32 = 3, kNcclUint64 = 5, kNcclFloat64 = 8 };
+enum { kNcclSum = 0, kNcclMax = 2, kNcclMin = 3 };
 
 struct NcclApi {
     void* handle = nullptr;
@@ -134,9 +134,80 @@ static int shard_geometry(size_t scene_rows, size_t cols, bool has_target, size_
     return 0;
 }
 
+// General (f32 / polarization-op) path of a sharded scene: merged scan {min key, max key, valid count} ...
+int comm_reduce_f32_scan(sarpro_ctx* ctx, F32Scan* scan_dev) {
+    if (!ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
+    NcclApi& api = nccl();
+    CommState* cs = ctx->comm;
+    COMM_BEGIN();
+    NC(api.GroupStart());
+    NC(api.AllReduce(&scan_dev->min_key, &scan_dev->min_key, 1, kNcclUint32, kNcclMin, cs->comm, ctx->stream));
+    NC(api.AllReduce(&scan_dev->max_key, &scan_dev->max_key, 1, kNcclUint32, kNcclMax, cs->comm, ctx->stream));
+    NC(api.AllReduce(&scan_dev->valid_count, &scan_dev->valid_count, 1, kNcclUint64, kNcclSum, cs->comm, ctx->stream));
+    NC(api.GroupEnd());
+    COMM_END();
+    return 0;
+}
+// ... and the merged 4096-bin stat histogram (exact integers) with the two log sums (mean / std: log lines only)
+int comm_reduce_f32_hist(sarpro_ctx* ctx, unsigned long long* hist4096_dev, double* sums2_dev) {
+    if (!ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
+    NcclApi& api = nccl();
+    CommState* cs = ctx->comm;
+    COMM_BEGIN();
+    NC(api.GroupStart());
+    NC(api.AllReduce(hist4096_dev, hist4096_dev, kStatBins, kNcclUint64, kNcclSum, cs->comm, ctx->stream));
+    NC(api.AllReduce(sums2_dev, sums2_dev, 2, kNcclFloat64, kNcclSum, cs->comm, ctx->stream));
+    NC(api.GroupEnd());
+    COMM_END();
+    return 0;
+}
+
 } // namespace sarpro
 
 extern "C" {
+
+int sarpro_pipeline_single_sharded(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, size_t scene_rows, int op, int bit_depth,
+                                   int strategy, sarpro_image* out, sarpro_stats* stats) {
+    RC(begin_call(ctx));
+    if (!a || !b || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    RC(check_enums(ctx, op, strategy, bit_depth));
+    if (op < 0) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "the sharded single-band pipeline takes a polarization operation");
+    if (!ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
+    if (strategy == SARPRO_STRATEGY_CLAHE)
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "CLAHE needs tile statistics of the whole scene: use the u16 synRGB sharded pipeline");
+    RC(check_band(ctx, a));
+    RC(check_band(ctx, b));
+    if (a->rows != b->rows || a->cols != b->cols || a->dtype != b->dtype)
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "bands differ in shape or type");
+    const uint64_t rows = a->rows, cols = a->cols, n = rows * cols;
+    const size_t esz = bit_depth == SARPRO_U8 ? 1 : 2;
+    const int is16 = a->dtype == SARPRO_DT_U16;
+    BandWs& w = ctx->band[0];
+    const void* pa = a->data;
+    const void* pb = b->data;
+    if (a->location == SARPRO_LOC_HOST) {
+        RC(reserve(ctx, w.f32a, std::max<size_t>(n * (is16 ? 2 : 4), 16)));
+        CU(cudaMemcpyAsync(w.f32a.p, a->data, n * (is16 ? 2 : 4), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += n * (is16 ? 2 : 4);
+        pa = w.f32a.p;
+    }
+    if (b->location == SARPRO_LOC_HOST) {
+        RC(reserve(ctx, w.f32b, std::max<size_t>(n * (is16 ? 2 : 4), 16)));
+        CU(cudaMemcpyAsync(w.f32b.p, b->data, n * (is16 ? 2 : 4), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += n * (is16 ? 2 : 4);
+        pb = w.f32b.p;
+    }
+    RC(reserve(ctx, w.small, std::max<size_t>(n * esz, 16)));
+    OutGeom g = out_geometry(cols, rows, false, 0, false);
+    ctx->shard_reduce = true;
+    ctx->shard_scene_px = (uint64_t)scene_rows * cols;
+    const int rc = f32_general_single(ctx, 0, pa, pb, is16, is16, op, rows, cols, bit_depth, strategy, PlanKind::Autoscale, g, w.small.p, stats);
+    ctx->shard_reduce = false;
+    RC(rc);
+    fill_image(out, g, 1, bit_depth);
+    if (out->data) RC(deliver(ctx, w.small.p, n * esz, out));
+    return end_call(ctx);
+}
 
 int sarpro_shard_rows(size_t rows, int world, int rank, int clahe, size_t* r0, size_t* r1) {
     if (!r0 || !r1 || world < 1 || rank < 0 || rank >= world) return SARPRO_ERR_INVALID_ARGUMENT;

@@ -152,6 +152,8 @@ struct sarpro_ctx {
     sarpro::PlanDev* h_plan_up = nullptr; // [2] staging of host-planned bands' plans on their way to the device
     sarpro_stats* pending_stats[2] = {nullptr, nullptr}; // caller's stats structs to fill in end_call (device-planned bands)
     sarpro::DevBuf db_table;       // [65536] f64: dB of every DN (device planner)
+    bool shard_reduce = false;     // inside a sharded general-path call: merge scan / stat histogram over the ranks
+    uint64_t shard_scene_px = 0;   // pixels of the whole scene in that call
     int host_plan = 0;             // SARPRO_HOST_PLAN=1: plan every band on the host (validation)
     // timing
     cudaEvent_t ev[6] = {};
@@ -199,7 +201,9 @@ int check_enums(sarpro_ctx* ctx, int op, int strategy, int bit_depth); // -2 = n
 int synrgb_compose(sarpro_ctx* ctx, int strategy, const uint8_t* c1, const uint8_t* c2, size_t n);
 int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint16_t* lut_host, uint32_t max_key,
                             const OutGeom& g, void* canvas);
-int f32_general_single(sarpro_ctx* ctx, int slot, const float* a_dev, const float* b_dev, int op, uint64_t rows,
+int comm_reduce_f32_scan(sarpro_ctx* ctx, F32Scan* scan_dev);                                    // comm.cu
+int comm_reduce_f32_hist(sarpro_ctx* ctx, unsigned long long* hist4096_dev, double* sums2_dev);  // comm.cu
+int f32_general_single(sarpro_ctx* ctx, int slot, const void* a_dev, const void* b_dev, int a_u16, int b_u16, int op, uint64_t rows,
                        uint64_t cols, int bit_depth, int strategy, PlanKind kind, const OutGeom& g, void* canvas_dev,
                        sarpro_stats* stats);
 int end_call(sarpro_ctx* ctx);

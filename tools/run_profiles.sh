@@ -1,13 +1,18 @@
-# Round-end measurement set (one gpurun call): bench, reference arm, ncu launch list, one full capture of pass B.
+# Round measurement set (one gpurun call): bench, reference arm, ncu launch list, one full capture of pass B, sanitizer logs.
 # Every step is bounded so that the call ends inside the GPU budget that is left.
-R=${R:-r01q}
+R=${R:-r02}
 set -x
-timeout 70 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
+timeout 120 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
+timeout 90 python bench.py --config c2 > gpurun_out/${R}_bench_c2.json 2>> gpurun_out/${R}_bench.err
+timeout 60 python bench.py --config c1 > gpurun_out/${R}_bench_c1.json 2>> gpurun_out/${R}_bench.err
 if [ -z "$QUICK" ]; then
-timeout 40 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/${R}_bench.err
+timeout 60 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/${R}_bench.err
 fi
-ITERS=2 timeout 45 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|sarpro' --csv --log-file gpurun_out/${R}_launches.csv python tools/prof_one.py clahe > gpurun_out/${R}_ncu.log 2>&1
+ITERS=3 timeout 60 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|sarpro' -s 26 --csv --log-file gpurun_out/${R}_launches.csv python tools/prof_plan.py > gpurun_out/${R}_ncu.log 2>&1
 if [ -z "$QUICK" ]; then
-ITERS=1 timeout 55 ncu --set full --clock-control none --import-source on -k regex:'k_hmma' -c 2 -o gpurun_out/${R}_full -f python tools/prof_one.py clahe >> gpurun_out/${R}_ncu.log 2>&1
+ITERS=2 timeout 120 ncu --set full --clock-control none --import-source on -k regex:'k_hmma' -s 2 -c 2 -o gpurun_out/${R}_full -f python tools/prof_plan.py >> gpurun_out/${R}_ncu.log 2>&1
+timeout 200 compute-sanitizer --tool memcheck python tools/sanitize_case.py > gpurun_out/${R}_sanitizer_memcheck.log 2>&1
+timeout 300 compute-sanitizer --tool racecheck python tools/sanitize_case.py > gpurun_out/${R}_sanitizer_racecheck.log 2>&1
 fi
 cat gpurun_out/${R}_bench.json
+tail -3 gpurun_out/${R}_sanitizer_*.log
