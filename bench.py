@@ -446,10 +446,14 @@ def main():
             if cfg == "c1":
                 crop_r, crop_c = 4096, 4096
                 vvc, vhc = vv.cpu().numpy().view(np.uint16), None
-            else:
-                crop_r, crop_c = (8000, 6250) if cfg in ("c2", "c3") else (4000, 6250)
+            elif cfg in ("c2", "c3"):
+                crop_r, crop_c = 8000, 6250
                 vvc = vv[:crop_r, :crop_c].cpu().numpy().view(np.uint16)
                 vhc = vh[:crop_r, :crop_c].cpu().numpy().view(np.uint16)
+            else:
+                from sarpro_b200.synth import synth_pair
+                crop_r, crop_c = 4000, 6250
+                vvc, vhc = synth_pair(crop_r, crop_c)  # same recipe as the device generator (numpy RNG)
             v, dt, note = cpu_sample(cfg, vvc, vhc, 1, full_cols)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": "Mpixel/s", "cores": 1, "kind": "port",
                                     "sample": f"{crop_r}x{crop_c} crop per band of the same scene, {note}, {dt:.1f} s, serial like the reference (SURVEY F1)"}

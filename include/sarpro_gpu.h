@@ -229,13 +229,45 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
                                    int strategy, int mode, int has_target, size_t target, int pad,
                                    int tamed_band_step, sarpro_image* out);
 
-/* Row-band-sharded polarization-op band at full resolution (BASELINE config 4: ops.rs:4-44 -> pipeline.rs:42-66 -> no resize): the
- * rank passes ITS row band of both inputs (f32, or the raw u16 DN), any contiguous split of the scene's rows; the library merges
- * the scan (min / max / valid count) and the 4096-bin stat histogram over the ranks (integers and bit patterns: identical to the
- * unsharded values), every rank derives the same window, and the rank's rows of the result are written to `out` (rows x cols
- * samples of bit_depth). All strategies except CLAHE (whose tile statistics need the scene geometry). */
+/* One or two polarization operations over the same pair (a, b), each autoscaled on its own into a full-resolution band (BASELINE
+ * config 4: log-ratio and normalised difference of VV / VH -> Equalized -> two u16 bands; the calls the reference makes one after
+ * the other, sentinel1.rs:1497-1579 -> ops.rs:4-44 -> pipeline.rs:42-66 -> save.rs:199-316 without a target size). The operands
+ * (f32, or the raw u16 DN) are read once per pass for both operations: 3 x (a + b) reads + one write per band. `outs` / `stats` hold
+ * n_ops entries; device-resident outputs are written in place.
+ * scene_rows == 0 or == a->rows: the bands are the whole scene. Otherwise the call is ONE RANK's contiguous row band of a scene of
+ * scene_rows rows (sarpro_comm_init first; any split of the rows): the library merges the scan (min / max / valid count) and the
+ * 4096-bin stat histograms over the ranks (integers and bit patterns: identical to the unsharded values), every rank derives the
+ * same windows, and the rank's rows of each result are written to outs[k]. All strategies except CLAHE (whose tile statistics need
+ * the scene geometry: sarpro_pipeline_single per operation, unsharded). */
+int sarpro_pipeline_polops(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, size_t scene_rows, int n_ops, const int* ops,
+                           int bit_depth, int strategy, sarpro_image* outs, sarpro_stats* stats);
+/* n_ops == 1 form of the above. */
 int sarpro_pipeline_single_sharded(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, size_t scene_rows, int op, int bit_depth,
                                    int strategy, sarpro_image* out, sarpro_stats* stats);
+
+/* ---- batch (BASELINE config 5) ------------------------------------------------------------ */
+/* One scene of a batch: the band pair of one product. A scene whose b1.data is NULL (or that has no pixels) is counted as
+ * skipped, like a product SafeReader::open_with_warnings_with_options returns None for (api/mod.rs:498-529). */
+typedef struct sarpro_scene {
+    sarpro_band b1, b2;
+} sarpro_scene;
+typedef enum sarpro_batch_kind {
+    SARPRO_BATCH_MULTIBAND = 0, /* two gray bands per scene (save.rs:199-316): outs[2k], outs[2k+1]; stats[2k], stats[2k+1] */
+    SARPRO_BATCH_SYNRGB = 1     /* one interleaved RGB image per scene (save.rs:317-368): outs[k]; stats[2k], stats[2k+1] */
+} sarpro_batch_kind;
+/* BatchReport (api/mod.rs:451-457) */
+typedef struct sarpro_batch_report {
+    uint64_t processed, skipped, errors;
+} sarpro_batch_report;
+/* The scene loop of process_directory_to_path (api/mod.rs:474-536; cli/runner.rs:294-345) over rasters that are already
+ * decoded: every scene goes through sarpro_pipeline_multiband_tiff or sarpro_pipeline_synrgb with the same parameters. Host
+ * rasters are staged through two device slots on a copy stream of their own, so scene k+1 uploads while scene k computes and
+ * its result goes back (pinned host memory - sarpro_host_alloc / sarpro_host_register - is what makes the copies asynchronous).
+ * continue_on_error != 0: a failing scene is counted in report->errors, its status goes to statuses[k] (may be NULL) and the
+ * loop goes on; otherwise the first error is returned. bit_depth is ignored for SARPRO_BATCH_SYNRGB (JPEG forces U8). */
+int sarpro_pipeline_batch(sarpro_ctx* ctx, const sarpro_scene* scenes, size_t n, int kind, int bit_depth, int strategy, int mode,
+                          int has_target, size_t target, int pad, int tamed_band_step, int continue_on_error, sarpro_image* outs,
+                          sarpro_stats* stats, int* statuses, sarpro_batch_report* report);
 
 /* ---- host-only planner entry points (pure CPU; used by tests and by multi-rank hosts) ---- */
 /* Statistics + window + DN->sample LUT from a 65,536-bin DN histogram, i.e. what

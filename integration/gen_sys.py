@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TMAP = {"int": "c_int", "size_t": "usize", "float": "f32", "double": "f64", "uint8_t": "u8", "uint16_t": "u16", "uint32_t": "u32",
         "uint64_t": "u64", "void": "c_void", "char": "c_char", "sarpro_ctx": "sarpro_ctx", "sarpro_stats": "sarpro_stats",
         "sarpro_band": "sarpro_band", "sarpro_image": "sarpro_image", "sarpro_resize_meta": "sarpro_resize_meta",
-        "sarpro_timing": "sarpro_timing"}
+        "sarpro_timing": "sarpro_timing", "sarpro_scene": "sarpro_scene", "sarpro_batch_report": "sarpro_batch_report"}
 
 
 def rtype(t):

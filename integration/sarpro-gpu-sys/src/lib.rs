@@ -48,6 +48,7 @@ pub struct sarpro_resize_meta {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy, Debug)]
 pub struct sarpro_band {
     pub data: *const c_void,
     pub dtype: i32,
@@ -83,6 +84,26 @@ pub struct sarpro_timing {
     pub stage_ms: [f32; 8],
     pub stage_launches: [u32; 8],
 }
+
+/// One scene of a batch (sarpro_scene): the band pair of one product.
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct sarpro_scene {
+    pub b1: sarpro_band,
+    pub b2: sarpro_band,
+}
+
+/// BatchReport (api/mod.rs:451-457)
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct sarpro_batch_report {
+    pub processed: u64,
+    pub skipped: u64,
+    pub errors: u64,
+}
+
+pub const SARPRO_BATCH_MULTIBAND: i32 = 0;
+pub const SARPRO_BATCH_SYNRGB: i32 = 1;
 
 pub const SARPRO_DT_F32: i32 = 0;
 pub const SARPRO_DT_U16: i32 = 1;
@@ -123,7 +144,9 @@ extern "C" {
     pub fn sarpro_shard_rows(rows: usize, world: c_int, rank: c_int, clahe: c_int, r0: *mut usize, r1: *mut usize) -> c_int;
     pub fn sarpro_shard_halo_rows(rows: usize, cols: usize, has_target: c_int, target: usize, world: c_int, rank: c_int, clahe: c_int, h0: *mut usize, h1: *mut usize) -> c_int;
     pub fn sarpro_pipeline_synrgb_sharded(ctx: *mut sarpro_ctx, b1: *const sarpro_band, b2: *const sarpro_band, scene_rows: usize, strategy: c_int, mode: c_int, has_target: c_int, target: usize, pad: c_int, tamed_band_step: c_int, out: *mut sarpro_image) -> c_int;
+    pub fn sarpro_pipeline_polops(ctx: *mut sarpro_ctx, a: *const sarpro_band, b: *const sarpro_band, scene_rows: usize, n_ops: c_int, ops: *const c_int, bit_depth: c_int, strategy: c_int, outs: *mut sarpro_image, stats: *mut sarpro_stats) -> c_int;
     pub fn sarpro_pipeline_single_sharded(ctx: *mut sarpro_ctx, a: *const sarpro_band, b: *const sarpro_band, scene_rows: usize, op: c_int, bit_depth: c_int, strategy: c_int, out: *mut sarpro_image, stats: *mut sarpro_stats) -> c_int;
+    pub fn sarpro_pipeline_batch(ctx: *mut sarpro_ctx, scenes: *const sarpro_scene, n: usize, kind: c_int, bit_depth: c_int, strategy: c_int, mode: c_int, has_target: c_int, target: usize, pad: c_int, tamed_band_step: c_int, continue_on_error: c_int, outs: *mut sarpro_image, stats: *mut sarpro_stats, statuses: *mut c_int, report: *mut sarpro_batch_report) -> c_int;
     pub fn sarpro_plan_from_dn_histogram(hist65536: *const u64, bit_depth: c_int, strategy: c_int, stats: *mut sarpro_stats, lut16: *mut u16) -> c_int;
     pub fn sarpro_plan_from_present_list(blocks: *const u32, pairs: *const u32, cap: u32, bit_depth: c_int, strategy: c_int, stats: *mut sarpro_stats, lut16: *mut u16) -> c_int;
     pub fn sarpro_plan_on_device(ctx: *mut sarpro_ctx, hist65536: *const u32, bit_depth: c_int, strategy: c_int, plan_kind: c_int, stats: *mut sarpro_stats, lut16: *mut u16, hot2: *mut u32) -> c_int;

@@ -65,6 +65,17 @@ class Image(C.Structure):
     ]
 
 
+class Scene(C.Structure):
+    _fields_ = [("b1", Band), ("b2", Band)]
+
+
+class BatchReport(C.Structure):
+    _fields_ = [("processed", C.c_uint64), ("skipped", C.c_uint64), ("errors", C.c_uint64)]
+
+
+BATCH_MULTIBAND, BATCH_SYNRGB = 0, 1
+
+
 class Timing(C.Structure):
     _fields_ = [
         ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("kernel_ms", C.c_float),
@@ -112,7 +123,10 @@ SYMBOLS = {
     "sarpro_shard_rows": (_I, [_SZ, _I, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "sarpro_shard_halo_rows": (_I, [_SZ, _SZ, _I, _SZ, _I, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "sarpro_pipeline_synrgb_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, _SZ, _I, _I, C.POINTER(Image)]),
+    "sarpro_pipeline_polops": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, C.POINTER(C.c_int), _I, _I, C.POINTER(Image), C.POINTER(Stats)]),
     "sarpro_pipeline_single_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, C.POINTER(Image), C.POINTER(Stats)]),
+    "sarpro_pipeline_batch": (_I, [_P, C.POINTER(Scene), _SZ, _I, _I, _I, _I, _I, _SZ, _I, _I, _I, C.POINTER(Image), C.POINTER(Stats),
+                                   C.POINTER(C.c_int), C.POINTER(BatchReport)]),
     "sarpro_plan_from_dn_histogram": (_I, [_P, _I, _I, C.POINTER(Stats), _P]),
     "sarpro_plan_from_present_list": (_I, [_P, _P, C.c_uint32, _I, _I, C.POINTER(Stats), _P]),
     "sarpro_plan_on_device": (_I, [_P, _P, _I, _I, _I, C.POINTER(Stats), _P, _P]),

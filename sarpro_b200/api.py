@@ -329,6 +329,72 @@ class Context:
         return ProcessedImage(img.cols, img.rows, U8, JPEG, rgb=out, scale_x=img.meta.scale_x, scale_y=img.meta.scale_y,
                               pad_left=img.meta.pad_left, pad_top=img.meta.pad_top)
 
+    def process_polops(self, band_a, band_b, ops, bit_depth, strategy, scene_rows=None, outs=None):
+        """One or two polarization operations over the same pair, each autoscaled into a full-resolution band
+        (sentinel1.rs:1497-1579 -> ops.rs:4-44 -> pipeline.rs:42-66; BASELINE config 4 with ops = (OP_LOGRATIO, OP_NDIFF)).
+        scene_rows: the bands are this rank's row band of a scene of that many rows (comm_init first).
+        Returns ([plane per op], [stats per op])."""
+        ba, ka = self._band(band_a)
+        bb, kb = self._band(band_b)
+        rows, cols = ka.shape
+        ops = list(ops)
+        n = len(ops)
+        imgs = (F.Image * n)()
+        keep = []
+        for o in range(n):
+            img, out = self._image(cols, rows, 1, bit_depth, None if outs is None else outs[o])
+            imgs[o] = img
+            keep.append(out)
+        st = (F.Stats * n)()
+        arr = (C.c_int * n)(*ops)
+        self._check(self._lib.sarpro_pipeline_polops(self._h, C.byref(ba), C.byref(bb), int(scene_rows or 0), n, arr, bit_depth, strategy,
+                                                     imgs, st))
+        del kb
+        return keep, [st[o] for o in range(n)]
+
+    def process_batch(self, scenes, kind, bit_depth, strategy, target_size=None, pad=False, mode=F.SYNRGB_DEFAULT,
+                      tamed_band_step=True, continue_on_error=True, outs=None):
+        """process_directory_to_path's scene loop (api/mod.rs:474-536) over decoded band pairs: `scenes` is a list of
+        (band1, band2) or None (a product the reader skips). kind: F.BATCH_MULTIBAND (two gray bands per scene) or
+        F.BATCH_SYNRGB (one RGB image per scene). The next scene's upload runs beside the current scene's kernels.
+        outs: optional list of preallocated outputs (numpy / torch), 2 per scene for MULTIBAND, 1 for SYNRGB.
+        Returns (list of outputs per scene | None for skipped / failed, statuses, report, stats)."""
+        n = len(scenes)
+        per = 2 if kind == F.BATCH_MULTIBAND else 1
+        arr = (F.Scene * max(n, 1))()
+        imgs = (F.Image * max(per * n, 1))()
+        keep, results = [], []
+        depth = bit_depth if kind == F.BATCH_MULTIBAND else U8
+        for k, sc in enumerate(scenes):
+            if sc is None:
+                arr[k] = F.Scene(F.Band(None, F.DT_U16, F.LOC_HOST, 0, 0), F.Band(None, F.DT_U16, F.LOC_HOST, 0, 0))
+                results.append(None)
+                continue
+            b1, k1 = self._band(sc[0])
+            b2, k2 = self._band(sc[1])
+            keep += [k1, k2]
+            arr[k] = F.Scene(b1, b2)
+            rows, cols = k1.shape
+            oc, orr = self.resize_output_dims(cols, rows, target_size, pad)
+            res = []
+            for j in range(per):
+                img, o = self._image(oc, orr, 1 if kind == F.BATCH_MULTIBAND else 3, depth, None if outs is None else outs[per * k + j])
+                imgs[per * k + j] = img
+                res.append(o)
+            results.append(res)
+        st = (F.Stats * max(2 * n, 1))()
+        status = (C.c_int * max(n, 1))()
+        rep = F.BatchReport()
+        self._check(self._lib.sarpro_pipeline_batch(self._h, arr, n, kind, bit_depth, strategy, mode, int(target_size is not None),
+                                                    int(target_size or 0), int(bool(pad)), int(bool(tamed_band_step)),
+                                                    int(bool(continue_on_error)), imgs, st, status, C.byref(rep)))
+        del keep
+        statuses = [status[k] for k in range(n)]
+        for k in range(n):
+            if statuses[k] != F.OK:
+                results[k] = None
+        return results, statuses, rep, [st[i] for i in range(2 * n)]
+
     def process_multiband_tiff(self, band1, band2, bit_depth, strategy, target_size=None, pad=False) -> ProcessedImage:
         """save.rs:199-316; api/mod.rs:133-200."""
         b1, k1 = self._band(band1)

@@ -1160,6 +1160,13 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     for (DevBuf* b : {&ctx->units, &ctx->tile_px, &ctx->col_dx, &ctx->col_omdx, &ctx->col_t, &ctx->row_dy, &ctx->row_omdy,
                       &ctx->row_t, &ctx->rgb, &ctx->hist256, &ctx->rgbsel, &ctx->rgb_luts, &ctx->col_m, &ctx->row_sat, &ctx->db_table})
         release(*b);
+    for (auto& slot : ctx->batch_stage)
+        for (DevBuf& b : slot) release(b);
+    if (ctx->stream_up) { cudaStreamSynchronize(ctx->stream_up); cudaStreamDestroy(ctx->stream_up); }
+    for (auto& ev : ctx->ev_up)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_chunk)
+        if (ev) cudaEventDestroy(ev);
     drop_axis_plans(ctx);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
     if (ctx->h_present) cudaFreeHost(ctx->h_present);

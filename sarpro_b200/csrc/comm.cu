@@ -134,29 +134,31 @@ static int shard_geometry(size_t scene_rows, size_t cols, bool has_target, size_
     return 0;
 }
 
-// General (f32 / polarization-op) path of a sharded scene: merged scan {min key, max key, valid count} ...
-int comm_reduce_f32_scan(sarpro_ctx* ctx, F32Scan* scan_dev) {
+// General (f32 / polarization-op) path of a sharded scene: merged scan {min key, max key, valid count} of nops operations ...
+int comm_reduce_f32_scan(sarpro_ctx* ctx, F32Scan* scan_dev, int nops) {
     if (!ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
     NcclApi& api = nccl();
     CommState* cs = ctx->comm;
     COMM_BEGIN();
     NC(api.GroupStart());
-    NC(api.AllReduce(&scan_dev->min_key, &scan_dev->min_key, 1, kNcclUint32, kNcclMin, cs->comm, ctx->stream));
-    NC(api.AllReduce(&scan_dev->max_key, &scan_dev->max_key, 1, kNcclUint32, kNcclMax, cs->comm, ctx->stream));
-    NC(api.AllReduce(&scan_dev->valid_count, &scan_dev->valid_count, 1, kNcclUint64, kNcclSum, cs->comm, ctx->stream));
+    for (int o = 0; o < nops; ++o) {
+        NC(api.AllReduce(&scan_dev[o].min_key, &scan_dev[o].min_key, 1, kNcclUint32, kNcclMin, cs->comm, ctx->stream));
+        NC(api.AllReduce(&scan_dev[o].max_key, &scan_dev[o].max_key, 1, kNcclUint32, kNcclMax, cs->comm, ctx->stream));
+        NC(api.AllReduce(&scan_dev[o].valid_count, &scan_dev[o].valid_count, 1, kNcclUint64, kNcclSum, cs->comm, ctx->stream));
+    }
     NC(api.GroupEnd());
     COMM_END();
     return 0;
 }
-// ... and the merged 4096-bin stat histogram (exact integers) with the two log sums (mean / std: log lines only)
-int comm_reduce_f32_hist(sarpro_ctx* ctx, unsigned long long* hist4096_dev, double* sums2_dev) {
+// ... and the merged 4096-bin stat histograms (exact integers; nops contiguous tables) with the log sums (mean / std: log lines only)
+int comm_reduce_f32_hist(sarpro_ctx* ctx, unsigned long long* hist4096_dev, double* sums_dev, int nops) {
     if (!ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
     NcclApi& api = nccl();
     CommState* cs = ctx->comm;
     COMM_BEGIN();
     NC(api.GroupStart());
-    NC(api.AllReduce(hist4096_dev, hist4096_dev, kStatBins, kNcclUint64, kNcclSum, cs->comm, ctx->stream));
-    NC(api.AllReduce(sums2_dev, sums2_dev, 2, kNcclFloat64, kNcclSum, cs->comm, ctx->stream));
+    NC(api.AllReduce(hist4096_dev, hist4096_dev, (size_t)nops * kStatBins, kNcclUint64, kNcclSum, cs->comm, ctx->stream));
+    NC(api.AllReduce(sums_dev, sums_dev, (size_t)nops * 2, kNcclFloat64, kNcclSum, cs->comm, ctx->stream));
     NC(api.GroupEnd());
     COMM_END();
     return 0;
@@ -166,47 +168,72 @@ int comm_reduce_f32_hist(sarpro_ctx* ctx, unsigned long long* hist4096_dev, doub
 
 extern "C" {
 
-int sarpro_pipeline_single_sharded(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, size_t scene_rows, int op, int bit_depth,
-                                   int strategy, sarpro_image* out, sarpro_stats* stats) {
+int sarpro_pipeline_polops(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, size_t scene_rows, int n_ops, const int* ops,
+                           int bit_depth, int strategy, sarpro_image* outs, sarpro_stats* stats) {
     RC(begin_call(ctx));
-    if (!a || !b || !out) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
-    RC(check_enums(ctx, op, strategy, bit_depth));
-    if (op < 0) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "the sharded single-band pipeline takes a polarization operation");
-    if (!ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
-    if (strategy == SARPRO_STRATEGY_CLAHE)
-        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "CLAHE needs tile statistics of the whole scene: use the u16 synRGB sharded pipeline");
+    if (!a || !b || !outs || !ops) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_ops < 1 || n_ops > 2) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "one or two polarization operations per call");
+    for (int o = 0; o < n_ops; ++o) {
+        RC(check_enums(ctx, ops[o], strategy, bit_depth));
+        if (ops[o] < 0) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "sarpro_pipeline_polops takes polarization operations (ops.rs:4-44)");
+    }
     RC(check_band(ctx, a));
     RC(check_band(ctx, b));
     if (a->rows != b->rows || a->cols != b->cols || a->dtype != b->dtype)
         return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "bands differ in shape or type");
     const uint64_t rows = a->rows, cols = a->cols, n = rows * cols;
+    const bool sharded = scene_rows != 0 && scene_rows != rows;
+    if (sharded && !ctx->comm) return fail(ctx, SARPRO_ERR_COMM, "sarpro_comm_init has not been called on this context");
+    if (sharded && scene_rows < rows) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "scene_rows is smaller than the rank's row band");
+    if (strategy == SARPRO_STRATEGY_CLAHE && (sharded || n_ops == 2))
+        return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "CLAHE needs the tile statistics of one whole band: use sarpro_pipeline_single per operation");
     const size_t esz = bit_depth == SARPRO_U8 ? 1 : 2;
     const int is16 = a->dtype == SARPRO_DT_U16;
+    const size_t isz = is16 ? 2 : 4;
     BandWs& w = ctx->band[0];
     const void* pa = a->data;
     const void* pb = b->data;
     if (a->location == SARPRO_LOC_HOST) {
-        RC(reserve(ctx, w.f32a, std::max<size_t>(n * (is16 ? 2 : 4), 16)));
-        CU(cudaMemcpyAsync(w.f32a.p, a->data, n * (is16 ? 2 : 4), cudaMemcpyHostToDevice, ctx->stream));
-        ctx->timing.h2d_bytes += n * (is16 ? 2 : 4);
+        RC(reserve(ctx, w.f32a, std::max<size_t>(n * isz, 16)));
+        CU(cudaMemcpyAsync(w.f32a.p, a->data, n * isz, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += n * isz;
         pa = w.f32a.p;
     }
     if (b->location == SARPRO_LOC_HOST) {
-        RC(reserve(ctx, w.f32b, std::max<size_t>(n * (is16 ? 2 : 4), 16)));
-        CU(cudaMemcpyAsync(w.f32b.p, b->data, n * (is16 ? 2 : 4), cudaMemcpyHostToDevice, ctx->stream));
-        ctx->timing.h2d_bytes += n * (is16 ? 2 : 4);
+        RC(reserve(ctx, w.f32b, std::max<size_t>(n * isz, 16)));
+        CU(cudaMemcpyAsync(w.f32b.p, b->data, n * isz, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += n * isz;
         pb = w.f32b.p;
     }
-    RC(reserve(ctx, w.small, std::max<size_t>(n * esz, 16)));
-    OutGeom g = out_geometry(cols, rows, false, 0, false);
-    ctx->shard_reduce = true;
-    ctx->shard_scene_px = (uint64_t)scene_rows * cols;
-    const int rc = f32_general_single(ctx, 0, pa, pb, is16, is16, op, rows, cols, bit_depth, strategy, PlanKind::Autoscale, g, w.small.p, stats);
+    const OutGeom g = out_geometry(cols, rows, false, 0, false);
+    const int slots[2] = {0, 1};
+    void* canvases[2] = {nullptr, nullptr};
+    for (int o = 0; o < n_ops; ++o) {
+        // device-resident outputs are written in place (no staging copy of a full-resolution band)
+        if (outs[o].data && outs[o].location == SARPRO_LOC_DEVICE) {
+            if (outs[o].capacity_bytes < n * esz) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "output buffer too small");
+            canvases[o] = outs[o].data;
+        } else {
+            RC(reserve(ctx, ctx->band[o].small, std::max<size_t>(n * esz, 16)));
+            canvases[o] = ctx->band[o].small.p;
+        }
+    }
+    ctx->shard_reduce = sharded;
+    ctx->shard_scene_px = (uint64_t)(sharded ? scene_rows : rows) * cols;
+    const int rc = f32_general(ctx, n_ops, slots, pa, pb, is16, is16, ops, rows, cols, bit_depth, strategy, PlanKind::Autoscale, g, canvases, stats);
     ctx->shard_reduce = false;
     RC(rc);
-    fill_image(out, g, 1, bit_depth);
-    if (out->data) RC(deliver(ctx, w.small.p, n * esz, out));
+    for (int o = 0; o < n_ops; ++o) {
+        void* dst = outs[o].data;
+        fill_image(&outs[o], g, 1, bit_depth);
+        if (dst && canvases[o] != dst) RC(deliver(ctx, canvases[o], n * esz, &outs[o]));
+    }
     return end_call(ctx);
+}
+
+int sarpro_pipeline_single_sharded(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, size_t scene_rows, int op, int bit_depth,
+                                   int strategy, sarpro_image* out, sarpro_stats* stats) {
+    return sarpro_pipeline_polops(ctx, a, b, scene_rows, 1, &op, bit_depth, strategy, out, stats);
 }
 
 int sarpro_shard_rows(size_t rows, int world, int rank, int clahe, size_t* r0, size_t* r1) {

@@ -171,6 +171,11 @@ struct sarpro_ctx {
     int hist_variant = -1; // SARPRO_HIST_VARIANT; -1 = per band, from the tail of the previous histogram of that slot
     float valid_thresh = 0.f;
     sarpro::CommState* comm = nullptr;
+    // batch / streamed uploads (api_batch.cu): a copy stream and two staging slots of a band pair, created on first use
+    cudaStream_t stream_up = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};  // upload of staging slot s complete
+    cudaEvent_t ev_chunk[16] = {};              // streamed single-scene upload: chunk c of a band has landed
+    sarpro::DevBuf batch_stage[2][2];           // [slot][band]
 };
 
 namespace sarpro {
@@ -201,8 +206,11 @@ int check_enums(sarpro_ctx* ctx, int op, int strategy, int bit_depth); // -2 = n
 int synrgb_compose(sarpro_ctx* ctx, int strategy, const uint8_t* c1, const uint8_t* c2, size_t n);
 int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint16_t* lut_host, uint32_t max_key,
                             const OutGeom& g, void* canvas);
-int comm_reduce_f32_scan(sarpro_ctx* ctx, F32Scan* scan_dev);                                    // comm.cu
-int comm_reduce_f32_hist(sarpro_ctx* ctx, unsigned long long* hist4096_dev, double* sums2_dev);  // comm.cu
+int comm_reduce_f32_scan(sarpro_ctx* ctx, F32Scan* scan_dev, int nops);                                    // comm.cu
+int comm_reduce_f32_hist(sarpro_ctx* ctx, unsigned long long* hist4096_dev, double* sums_dev, int nops);   // comm.cu
+int f32_general(sarpro_ctx* ctx, int nops, const int* slots, const void* a_dev, const void* b_dev, int a_u16, int b_u16, const int* ops,
+                uint64_t rows, uint64_t cols, int bit_depth, int strategy, PlanKind kind, const OutGeom& g, void* const* canvases,
+                sarpro_stats* stats);
 int f32_general_single(sarpro_ctx* ctx, int slot, const void* a_dev, const void* b_dev, int a_u16, int b_u16, int op, uint64_t rows,
                        uint64_t cols, int bit_depth, int strategy, PlanKind kind, const OutGeom& g, void* canvas_dev,
                        sarpro_stats* stats);

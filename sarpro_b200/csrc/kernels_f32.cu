@@ -1,6 +1,8 @@
 // kernels_f32.cu — rasters whose samples are not u16-valued: polarization ratios / normalised
 // differences (ops.rs:10-44) and calibrated f32 inputs. The op is fused into every loader, so the
-// combined f32 plane of the reference (a new Array2<f32>, ops.rs) is never written.
+// combined f32 plane of the reference (a new Array2<f32>, ops.rs) is never written. Every kernel takes
+// ONE or TWO operations over the same operand pair (NOPS): the two-band products of a pair (BASELINE config 4:
+// log-ratio and normalised difference of VV / VH) read the operands once per pass instead of once per band.
 //
 // Exactness without device transcendentals: every index the reference derives from a sample
 //   4096-bin stat index  autoscale.rs:113-116      quantised level  autoscale.rs:440-442 / 649-651
@@ -9,6 +11,9 @@
 // index boundary into an f32 threshold with the same libm the reference uses, and the device only
 // compares: index(v) = #{k : v >= edge[k]}. A fast __log2f-based guess lands within a step or two of the
 // answer; the two correction loops make the result independent of the guess.
+//
+// Loads: a thread takes 8 consecutive samples (one 128-bit load per u16 operand, two per f32 operand) when the
+// operand pointers are 16-byte aligned; the last partial vector and unaligned rasters take the scalar loader.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,45 +31,108 @@ __device__ __forceinline__ float f32_pol(int op, float a, float b) {
     }
 }
 
+__device__ __forceinline__ uint4 f32_ldg_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// 8 consecutive samples of one operand, starting at element i (i % 8 == 0); cnt of them exist
+__device__ __forceinline__ void f32_load8(const void* p, int is_u16, uint64_t i, uint32_t cnt, bool vec, float (&x)[8]) {
+    if (vec && cnt == 8) {
+        if (is_u16) {
+            const uint4 w = f32_ldg_stream(reinterpret_cast<const uint16_t*>(p) + i);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                x[2 * j] = (float)(ww[j] & 0xffffu);
+                x[2 * j + 1] = (float)(ww[j] >> 16);
+            }
+        } else {
+            const uint4 w0 = f32_ldg_stream(reinterpret_cast<const float*>(p) + i);
+            const uint4 w1 = f32_ldg_stream(reinterpret_cast<const float*>(p) + i + 4);
+            x[0] = __uint_as_float(w0.x); x[1] = __uint_as_float(w0.y); x[2] = __uint_as_float(w0.z); x[3] = __uint_as_float(w0.w);
+            x[4] = __uint_as_float(w1.x); x[5] = __uint_as_float(w1.y); x[6] = __uint_as_float(w1.z); x[7] = __uint_as_float(w1.w);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x[k] = 0.0f;
+            if ((uint32_t)k < cnt) x[k] = is_u16 ? (float)reinterpret_cast<const uint16_t*>(p)[i + k] : reinterpret_cast<const float*>(p)[i + k];
+        }
+    }
+}
+
 struct F32Src {
     const void* a;
     const void* b;
-    int a_u16, b_u16, op;
-    __device__ __forceinline__ float get(uint64_t i) const {
-        const float x = a_u16 ? (float)reinterpret_cast<const uint16_t*>(a)[i] : reinterpret_cast<const float*>(a)[i];
-        if (op < 0) return x;
-        const float y = b_u16 ? (float)reinterpret_cast<const uint16_t*>(b)[i] : reinterpret_cast<const float*>(b)[i];
-        return f32_pol(op, x, y);
+    int a_u16, b_u16;
+    int op[2];   // op[1] only read by the NOPS == 2 kernels
+    int vec;     // operand pointers are 16-byte aligned
+    // samples of vector v (elements 8v .. 8v+7) for every operation; returns how many of them exist
+    template <int NOPS>
+    __device__ __forceinline__ uint32_t get8(uint64_t v, uint64_t n, float (&out)[NOPS][8]) const {
+        const uint64_t i = v * 8;
+        const uint32_t cnt = (uint32_t)min((uint64_t)8, n - i);
+        float x[8], y[8];
+        f32_load8(a, a_u16, i, cnt, vec != 0, x);
+        const bool need_b = op[0] >= 0 || (NOPS == 2);
+        if (need_b) f32_load8(b, b_u16, i, cnt, vec != 0, y);
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[o][k] = op[o] < 0 ? x[k] : f32_pol(op[o], x[k], y[k]);
+        return cnt;
     }
 };
 
+static F32Src make_src(const void* a, const void* b, int a_u16, int b_u16, int op0, int op1) {
+    F32Src s{a, b, a_u16, b_u16, {op0, op1}, 0};
+    const bool need_b = op0 >= 0 || op1 >= 0;
+    s.vec = (reinterpret_cast<uintptr_t>(a) & 15u) == 0 && (!need_b || (reinterpret_cast<uintptr_t>(b) & 15u) == 0);
+    return s;
+}
+
 // ---- pass 1: min / max / count over valid samples (autoscale.rs:37-55) --------------------------------
+template <int NOPS>
 __global__ void __launch_bounds__(256) k_f32_scan(F32Src src, uint64_t n, float valid_thresh, F32Scan* __restrict__ out) {
-    uint32_t mn = 0xffffffffu, mx = 0;
-    unsigned long long cnt = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float v = src.get(i);
-        if (v >= valid_thresh) { // valid samples are positive: the bit pattern orders like the value
-            const uint32_t k = __float_as_uint(v);
-            mn = min(mn, k);
-            mx = max(mx, k);
-            cnt++;
+    uint32_t mn[NOPS], mx[NOPS], cnt[NOPS];
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o) { mn[o] = 0xffffffffu; mx[o] = 0; cnt[o] = 0; }
+    const uint64_t nvec = (n + 7) / 8, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        float s[NOPS][8];
+        const uint32_t c = src.get8<NOPS>(v, n, s);
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((uint32_t)k < c && s[o][k] >= valid_thresh) { // valid samples are positive: the bit pattern orders like the value
+                    const uint32_t key = __float_as_uint(s[o][k]);
+                    mn[o] = min(mn[o], key);
+                    mx[o] = max(mx[o], key);
+                    cnt[o]++; // < 2^32 per thread (n < 2^35)
+                }
+    }
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o) {
+        const uint32_t a = warp_reduce_min(mn[o]), b = warp_reduce_max(mx[o]);
+        unsigned long long c = cnt[o];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if ((threadIdx.x & 31) == 0 && c) {
+            atomicMin(&out[o].min_key, a);
+            atomicMax(&out[o].max_key, b);
+            atomicAdd(&out[o].valid_count, c);
         }
     }
-    mn = warp_reduce_min(mn);
-    mx = warp_reduce_max(mx);
-    unsigned c32 = warp_reduce_add((unsigned)cnt); // < 2^32 per warp by construction (n < 2^32)
-    if ((threadIdx.x & 31) == 0 && c32) {
-        atomicMin(&out->min_key, mn);
-        atomicMax(&out->max_key, mx);
-        atomicAdd(&out->valid_count, (unsigned long long)c32);
-    }
 }
-cudaError_t launch_f32_scan(const void* a, const void* b, int a_u16, int b_u16, int op, uint64_t n, float valid_thresh,
-                            F32Scan* out, int sm_count, cudaStream_t stream) {
+cudaError_t launch_f32_scan(const void* a, const void* b, int a_u16, int b_u16, int op0, int op1, int nops, uint64_t n,
+                            float valid_thresh, F32Scan* out, int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_f32_scan<<<sm_count * 8, 256, 0, stream>>>(F32Src{a, b, a_u16, b_u16, op}, n, valid_thresh, out);
+    const F32Src src = make_src(a, b, a_u16, b_u16, op0, nops == 2 ? op1 : -1);
+    if (nops == 2) k_f32_scan<2><<<sm_count * 8, 256, 0, stream>>>(src, n, valid_thresh, out);
+    else k_f32_scan<1><<<sm_count * 8, 256, 0, stream>>>(src, n, valid_thresh, out);
     return cudaGetLastError();
 }
 
@@ -79,104 +147,181 @@ __device__ __forceinline__ uint32_t edge_index(const float* __restrict__ edges, 
 // ---- pass 2: 4096-bin histogram over [min_db, max_db] + mean / M2 accumulators -----------------------
 struct F32HistArgs {
     float valid_thresh;
-    float min_db, inv_span4096; // guess: (db - min_db) * inv_span * 4096
-    const float* edges;         // [4096]: edges[k], k = 1..4095
-    unsigned long long* hist;   // [4096]
-    double* sums;               // [0] = sum(db - min_db), [1] = sum((db - min_db)^2)   (fp32 logs, f64 accumulation)
+    float min_db[2], inv_span4096[2]; // guess: (db - min_db) * inv_span * 4096
+    const float* edges[2];            // [4096]: edges[k], k = 1..4095
+    unsigned long long* hist[2];      // [4096]
+    double* sums[2];                  // [0] = sum(db - min_db), [1] = sum((db - min_db)^2)   (fp32 logs, f64 accumulation)
 };
+template <int NOPS>
 __global__ void __launch_bounds__(256) k_f32_hist4096(F32Src src, uint64_t n, F32HistArgs h) {
-    __shared__ float s_edges[4096];
-    __shared__ uint32_t s_hist[4096];
-    __shared__ double s_red[2][8];
-    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) {
-        s_edges[i] = h.edges[i];
-        s_hist[i] = 0;
-    }
+    extern __shared__ uint4 f32_smem[];
+    float* s_edges = reinterpret_cast<float*>(f32_smem);                 // [NOPS][4096]
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_edges + NOPS * 4096); // [NOPS][4096]
+    __shared__ double s_red[2][2][8];
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o)
+        for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) {
+            s_edges[o * 4096 + i] = h.edges[o][i];
+            s_hist[o * 4096 + i] = 0;
+        }
     __syncthreads();
-    double s1 = 0.0, s2 = 0.0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float v = src.get(i);
-        if (v >= h.valid_thresh) {
-            const float rel = __fsub_rn(3.0102999566f * __log2f(v), h.min_db);
-            const uint32_t idx = edge_index(s_edges, 4095, v, (int)(rel * h.inv_span4096));
-            atomicAdd(&s_hist[idx], 1u);
-            s1 += (double)rel;
-            s2 += (double)rel * (double)rel;
+    double s1[NOPS], s2[NOPS];
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o) { s1[o] = 0.0; s2[o] = 0.0; }
+    const uint64_t nvec = (n + 7) / 8, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        float s[NOPS][8];
+        const uint32_t c = src.get8<NOPS>(v, n, s);
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o) {
+            float r1 = 0.f, r2 = 0.f; // per-vector partial sums in fp32 (8 terms), then f64
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float x = s[o][k];
+                if ((uint32_t)k < c && x >= h.valid_thresh) {
+                    const float rel = __fsub_rn(3.0102999566f * __log2f(x), h.min_db[o]);
+                    const uint32_t idx = edge_index(s_edges + o * 4096, 4095, x, (int)(rel * h.inv_span4096[o]));
+                    atomicAdd(&s_hist[o * 4096 + idx], 1u);
+                    r1 += rel;
+                    r2 += rel * rel;
+                }
+            }
+            s1[o] += (double)r1;
+            s2[o] += (double)r2;
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    for (int o = 0; o < NOPS; ++o) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s1[o] += __shfl_xor_sync(0xffffffffu, s1[o], d);
+            s2[o] += __shfl_xor_sync(0xffffffffu, s2[o], d);
+        }
+        if ((threadIdx.x & 31) == 0) { s_red[o][0][threadIdx.x >> 5] = s1[o]; s_red[o][1][threadIdx.x >> 5] = s2[o]; }
     }
-    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = s1; s_red[1][threadIdx.x >> 5] = s2; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < NOPS) {
+        const int o = threadIdx.x;
         double a = 0, b = 0;
-        for (int w = 0; w < 8; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
-        atomicAdd(&h.sums[0], a);
-        atomicAdd(&h.sums[1], b);
+        for (int w = 0; w < 8; ++w) { a += s_red[o][0][w]; b += s_red[o][1][w]; }
+        atomicAdd(&h.sums[o][0], a);
+        atomicAdd(&h.sums[o][1], b);
     }
-    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x)
-        if (s_hist[i]) atomicAdd(&h.hist[i], (unsigned long long)s_hist[i]);
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o)
+        for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x)
+            if (s_hist[o * 4096 + i]) atomicAdd(&h.hist[o][i], (unsigned long long)s_hist[o * 4096 + i]);
 }
-cudaError_t launch_f32_hist4096(const void* a, const void* b, int a_u16, int b_u16, int op, uint64_t n, float valid_thresh,
-                                float min_db, float inv_span4096, const float* edges4096, unsigned long long* hist4096,
-                                double* sums, int sm_count, cudaStream_t stream) {
+cudaError_t launch_f32_hist4096(const void* a, const void* b, int a_u16, int b_u16, int op0, int op1, int nops, uint64_t n,
+                                float valid_thresh, const float* min_db, const float* inv_span4096, const float* const* edges4096,
+                                unsigned long long* const* hist4096, double* const* sums, int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    F32HistArgs h{valid_thresh, min_db, inv_span4096, edges4096, hist4096, sums};
-    k_f32_hist4096<<<sm_count * 4, 256, 0, stream>>>(F32Src{a, b, a_u16, b_u16, op}, n, h);
+    F32HistArgs h{};
+    h.valid_thresh = valid_thresh;
+    for (int o = 0; o < nops; ++o) {
+        h.min_db[o] = min_db[o]; h.inv_span4096[o] = inv_span4096[o]; h.edges[o] = edges4096[o]; h.hist[o] = hist4096[o]; h.sums[o] = sums[o];
+    }
+    const F32Src src = make_src(a, b, a_u16, b_u16, op0, nops == 2 ? op1 : -1);
+    const size_t smem = (size_t)nops * 4096 * 8;
+    if (nops == 2) {
+        if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(&k_f32_hist4096<2>), smem)) return e;
+        k_f32_hist4096<2><<<sm_count * 3, 256, smem, stream>>>(src, n, h);
+    } else {
+        k_f32_hist4096<1><<<sm_count * 4, 256, smem, stream>>>(src, n, h);
+    }
     return cudaGetLastError();
 }
 
 // ---- pass 3: quantisation by level thresholds -----------------------------------------------------------
 struct F32QuantArgs {
     float valid_thresh;
-    float low_db, high_db, inv_range, gamma; // guess only
-    const float* edges;                      // [n_levels + 1]: edges[k], k = 1..n_levels
-    uint32_t n_levels;                       // 255, 65535 or 255 (CLAHE bins)
-    const uint8_t* remap;                    // 256-entry scale_u16_to_u8 table or nullptr
-    int key_plane;                           // 1: write u16 key = level + 1 for valid, 0 for invalid (CLAHE bridge)
+    float low_db[2], high_db[2], inv_range[2], gamma[2]; // guess only
+    const float* edges[2];                               // [n_levels + 1]: edges[k], k = 1..n_levels
+    uint32_t n_levels;                                   // 255, 65535 or 255 (CLAHE bins)
+    const uint8_t* remap[2];                             // 256-entry scale_u16_to_u8 table or nullptr
+    int key_plane;                                       // 1: write u16 key = level + 1 for valid, 0 for invalid (CLAHE bridge)
+    void* out[2];
+    int out_vec;                                         // outputs are 16-byte aligned
 };
-template <typename OutT>
-__global__ void __launch_bounds__(256) k_f32_quantize(F32Src src, uint64_t n, F32QuantArgs qa, OutT* __restrict__ out) {
-    __shared__ float s_edges[257];
-    __shared__ uint8_t s_remap[256];
+template <int NOPS, typename OutT>
+__global__ void __launch_bounds__(256) k_f32_quantize(F32Src src, uint64_t n, F32QuantArgs qa) {
+    __shared__ float s_edges[NOPS][257];
+    __shared__ uint8_t s_remap[NOPS][256];
     const bool small = qa.n_levels <= 256;
-    if (small)
-        for (uint32_t i = threadIdx.x; i <= qa.n_levels; i += blockDim.x) s_edges[i] = qa.edges[i];
-    s_remap[threadIdx.x] = qa.remap ? qa.remap[threadIdx.x] : (uint8_t)threadIdx.x;
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o) {
+        if (small)
+            for (uint32_t i = threadIdx.x; i <= qa.n_levels; i += blockDim.x) s_edges[o][i] = qa.edges[o][i];
+        s_remap[o][threadIdx.x] = qa.remap[o] ? qa.remap[o][threadIdx.x] : (uint8_t)threadIdx.x;
+    }
     __syncthreads();
-    const float* edges = small ? s_edges : qa.edges;
     const float fl = (float)qa.n_levels;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float v = src.get(i);
-        uint32_t o = 0;
-        if (v >= qa.valid_thresh) {
-            float x = 3.0102999566f * __log2f(v);
-            x = fminf(fmaxf(x, qa.low_db), qa.high_db);
-            x = (x - qa.low_db) * qa.inv_range;
-            if (qa.gamma != 1.0f) x = __powf(fmaxf(x, 0.0f), qa.gamma);
-            const uint32_t lvl = edge_index(edges, qa.n_levels, v, (int)(x * fl));
-            o = qa.key_plane ? lvl + 1 : (sizeof(OutT) == 1 ? (uint32_t)s_remap[lvl & 255u] : lvl);
-        } else if (!qa.key_plane && sizeof(OutT) == 1) {
-            o = s_remap[0]; // invalid samples are 0 before scale_u16_to_u8 (autoscale.rs:444, 669-670)
+    const uint64_t nvec = (n + 7) / 8, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        float s[NOPS][8];
+        const uint32_t c = src.get8<NOPS>(v, n, s);
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o) {
+            const float* edges = small ? s_edges[o] : qa.edges[o];
+            uint32_t q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float x0 = s[o][k];
+                uint32_t r = 0;
+                if ((uint32_t)k < c && x0 >= qa.valid_thresh) {
+                    float x = 3.0102999566f * __log2f(x0);
+                    x = fminf(fmaxf(x, qa.low_db[o]), qa.high_db[o]);
+                    x = (x - qa.low_db[o]) * qa.inv_range[o];
+                    if (qa.gamma[o] != 1.0f) x = __powf(fmaxf(x, 0.0f), qa.gamma[o]);
+                    const uint32_t lvl = edge_index(edges, qa.n_levels, x0, (int)(x * fl));
+                    r = qa.key_plane ? lvl + 1 : (sizeof(OutT) == 1 ? (uint32_t)s_remap[o][lvl & 255u] : lvl);
+                } else if (!qa.key_plane && sizeof(OutT) == 1) {
+                    r = s_remap[o][0]; // invalid samples are 0 before scale_u16_to_u8 (autoscale.rs:444, 669-670)
+                }
+                q[k] = r;
+            }
+            OutT* out = reinterpret_cast<OutT*>(qa.out[o]) + v * 8;
+            if (c == 8 && qa.out_vec) {
+                if (sizeof(OutT) == 2) {
+                    *reinterpret_cast<uint4*>(out) = make_uint4(q[0] | (q[1] << 16), q[2] | (q[3] << 16), q[4] | (q[5] << 16), q[6] | (q[7] << 16));
+                } else {
+                    *reinterpret_cast<uint2*>(out) = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((uint32_t)k < c) out[k] = (OutT)q[k];
+            }
         }
-        out[i] = (OutT)o;
     }
 }
-cudaError_t launch_f32_quantize(const void* a, const void* b, int a_u16, int b_u16, int op, uint64_t n, float valid_thresh,
-                                float low_db, float high_db, float gamma, const float* level_edges, uint32_t n_levels,
-                                const uint8_t* remap, int key_plane, uint8_t* out_u8, uint16_t* out_u16, int sm_count,
-                                cudaStream_t stream) {
+cudaError_t launch_f32_quantize(const void* a, const void* b, int a_u16, int b_u16, int op0, int op1, int nops, uint64_t n,
+                                float valid_thresh, const float* low_db, const float* high_db, const float* gamma,
+                                const float* const* level_edges, uint32_t n_levels, const uint8_t* const* remap, int key_plane,
+                                void* const* out, int out_u8, int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    const float range = fmaxf(high_db - low_db, 1.0f);
-    F32QuantArgs qa{valid_thresh, low_db, high_db, 1.0f / range, gamma, level_edges, n_levels, remap, key_plane};
-    const F32Src src{a, b, a_u16, b_u16, op};
-    if (out_u8) k_f32_quantize<uint8_t><<<sm_count * 8, 256, 0, stream>>>(src, n, qa, out_u8);
-    else k_f32_quantize<uint16_t><<<sm_count * 8, 256, 0, stream>>>(src, n, qa, out_u16);
+    F32QuantArgs qa{};
+    qa.valid_thresh = valid_thresh;
+    qa.n_levels = n_levels;
+    qa.key_plane = key_plane;
+    qa.out_vec = 1;
+    for (int o = 0; o < nops; ++o) {
+        const float range = fmaxf(high_db[o] - low_db[o], 1.0f);
+        qa.low_db[o] = low_db[o]; qa.high_db[o] = high_db[o]; qa.inv_range[o] = 1.0f / range; qa.gamma[o] = gamma[o];
+        qa.edges[o] = level_edges[o];
+        qa.remap[o] = remap ? remap[o] : nullptr;
+        qa.out[o] = out[o];
+        if (reinterpret_cast<uintptr_t>(out[o]) & 15u) qa.out_vec = 0;
+    }
+    const F32Src src = make_src(a, b, a_u16, b_u16, op0, nops == 2 ? op1 : -1);
+    const int grid = sm_count * 8;
+    if (nops == 2) {
+        if (out_u8) k_f32_quantize<2, uint8_t><<<grid, 256, 0, stream>>>(src, n, qa);
+        else k_f32_quantize<2, uint16_t><<<grid, 256, 0, stream>>>(src, n, qa);
+    } else {
+        if (out_u8) k_f32_quantize<1, uint8_t><<<grid, 256, 0, stream>>>(src, n, qa);
+        else k_f32_quantize<1, uint16_t><<<grid, 256, 0, stream>>>(src, n, qa);
+    }
     return cudaGetLastError();
 }
 

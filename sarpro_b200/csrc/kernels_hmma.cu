@@ -36,7 +36,10 @@
 namespace sarpro {
 
 namespace hm {
-constexpr uint32_t kThreadsLut = 512, kThreadsClahe = 384;      // CLAHE: fewer warps, 168 registers each for the gather pipeline
+#ifndef SARPRO_HMMA_CLAHE_THREADS
+#define SARPRO_HMMA_CLAHE_THREADS 384
+#endif
+constexpr uint32_t kThreadsLut = 512, kThreadsClahe = SARPRO_HMMA_CLAHE_THREADS; // CLAHE: fewer warps, ~158 registers each for the gather pipeline
 constexpr uint32_t kQuadEntries = 257;                       // 256 bins + the invalid-pixel entry
 constexpr uint32_t kQuadCellBytes = kQuadEntries * 8 * 16;   // one cell, 8 replicas
 constexpr int kSlots = 3;                                    // n-tiles in flight per warp

@@ -27,9 +27,9 @@ inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v >
 // Smallest bit pattern b in [lo, hi] with level(b) >= k, given a monotone `level`; kInfBits if none.
 // `guess` is an analytic estimate; a gallop around it brackets the boundary in a handful of evaluations.
 template <typename F>
-uint32_t first_reaching(F&& level, uint32_t k, uint32_t lo, uint32_t hi, uint32_t guess) {
-    if (level(hi) < k) return kInfBits;
-    if (level(lo) >= k) return lo;
+uint32_t first_reaching(F&& level, uint32_t k, uint32_t lo, uint32_t hi, uint32_t guess, uint32_t level_lo, uint32_t level_hi) {
+    if (level_hi < k) return kInfBits;
+    if (level_lo >= k) return lo;
     // invariant: level(lo) < k <= level(hi)
     uint32_t g = std::min(std::max(guess, lo + 1), hi);
     uint32_t step = 1;
@@ -95,12 +95,13 @@ void build_stat_edges(float min_v, float max_v, std::vector<float>* edges) {
         return (uint32_t)idx;
     };
     const uint32_t lo = bits_of(min_v), hi = bits_of(max_v);
+    const uint32_t l_lo = level(lo), l_hi = level(hi);
     parallel_for(kStatBins - 1, [&](uint32_t a, uint32_t b) {
         for (uint32_t i = a; i < b; ++i) {
             const uint32_t k = i + 1;
             const double db = min_db + span * ((double)k / (double)kStatBins);
             const uint32_t guess = bits_of((float)std::pow(10.0, db / 10.0));
-            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, guess));
+            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, guess, l_lo, l_hi));
         }
     });
 }
@@ -115,7 +116,7 @@ void build_level_edges(LevelKind kind, double low, double high, double gamma, ui
         const double clipped = std::fmin(std::fmax(db, low), high);
         const double n = (clipped - low) / range;
         double q;
-        if (kind == LevelKind::Quantize) q = clampd(std::pow(n, gamma) * max_val, 0.0, max_val);
+        if (kind == LevelKind::Quantize) q = clampd((gamma == 1.0 ? n : std::pow(n, gamma)) * max_val, 0.0, max_val); // pow(n, 1.0) == n exactly
         else if (kind == LevelKind::TamedLinearU8) q = clampd(n * 255.0, 0.0, 255.0);
         else {
             q = std::round(clampd(n, 0.0, 1.0) * 255.0);
@@ -126,8 +127,9 @@ void build_level_edges(LevelKind kind, double low, double high, double gamma, ui
         return q >= max_val ? n_levels : (uint32_t)q;
     };
     const uint32_t lo = bits_of(min_v), hi = bits_of(max_v);
-    if (level_of_min) *level_of_min = level(lo);
-    if (level_of_max) *level_of_max = level(hi);
+    const uint32_t l_lo = level(lo), l_hi = level(hi);
+    if (level_of_min) *level_of_min = l_lo;
+    if (level_of_max) *level_of_max = l_hi;
     parallel_for(n_levels, [&](uint32_t a, uint32_t b) {
         for (uint32_t i = a; i < b; ++i) {
             const uint32_t k = i + 1;
@@ -135,7 +137,7 @@ void build_level_edges(LevelKind kind, double low, double high, double gamma, ui
             if (kind == LevelKind::Quantize && gamma != 1.0) frac = std::pow(frac, 1.0 / gamma);
             const double db = low + range * frac;
             const uint32_t guess = bits_of((float)std::pow(10.0, db / 10.0));
-            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, guess));
+            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, guess, l_lo, l_hi));
         }
     });
 }

@@ -183,6 +183,51 @@ def test_f32_edge_cases(ctx):
     assert np.array_equal(u8, po.u8)
 
 
+@pytest.mark.parametrize("strategy", [S.STANDARD, S.ROBUST, S.ADAPTIVE, S.EQUALIZED, S.TAMED, S.DEFAULT])
+@pytest.mark.parametrize("bit_depth", [S.U8, S.U16])
+def test_pipeline_polops_two_operations(ctx, strategy, bit_depth):
+    """BASELINE config 4's call (sarpro_pipeline_polops): log-ratio and normalised difference of the same pair, each autoscaled on
+    its own into a full-resolution band, operands read once per pass for both. Each band must equal the oracle's
+    pol_op -> process_scalar_data_pipeline of that operation alone; f32 operands and the raw u16 DN give the same bytes."""
+    vv = CASES["speckle"](487, 1001)
+    vh = CASES["speckle_vh"](487, 1001)
+    vh[100:140, 200:260] = 0   # invalid in one operand only
+    vv[300:310, :50] = 0
+    ops = (S.OP_LOGRATIO, S.OP_NDIFF)
+    refs = [O.process_scalar_data_pipeline(O.pol_op(op, vv.astype(np.float32), vh.astype(np.float32)), bit_depth, strategy, want_db=False)
+            for op in ops]
+    for a, b in ((vv.astype(np.float32), vh.astype(np.float32)), (vv, vh)):
+        planes, stats = ctx.process_polops(a, b, ops, bit_depth, strategy)
+        for k in range(2):
+            ref = refs[k].u8 if bit_depth == S.U8 else refs[k].u16
+            assert planes[k].shape == ref.shape and planes[k].dtype == ref.dtype
+            assert np.array_equal(planes[k], ref), (k, a.dtype, int((planes[k] != ref).sum()))
+            _check_stats_f32(stats[k], refs[k].stats)
+    # the one-operation form and the other operations through the same entry
+    for op in (S.OP_SUM, S.OP_DIFF, S.OP_RATIO):
+        ref = O.process_scalar_data_pipeline(O.pol_op(op, vv.astype(np.float32), vh.astype(np.float32)), bit_depth, strategy, want_db=False)
+        planes, stats = ctx.process_polops(vv, vh, (op,), bit_depth, strategy)
+        assert np.array_equal(planes[0], ref.u8 if bit_depth == S.U8 else ref.u16), op
+
+
+def test_pipeline_polops_degenerate_and_errors(ctx):
+    """One operation without a valid sample rides along with a regular one (diff with a < b everywhere: all zeros); CLAHE and a
+    third operation are refused with INVALID_ARGUMENT."""
+    vv = CASES["speckle"](120, 333)
+    vh = (vv.astype(np.uint32) + 7).astype(np.uint16)
+    ops = (S.OP_DIFF, S.OP_SUM)
+    planes, stats = ctx.process_polops(vv, vh, ops, S.U16, S.EQUALIZED)
+    assert stats[0].valid_count == 0 and not planes[0].any()
+    ref = O.process_scalar_data_pipeline(O.pol_op(S.OP_SUM, vv.astype(np.float32), vh.astype(np.float32)), S.U16, S.EQUALIZED, want_db=False)
+    assert np.array_equal(planes[1], ref.u16)
+    with pytest.raises(S.SarproError):
+        ctx.process_polops(vv, vh, ops, S.U8, S.CLAHE)
+    with pytest.raises(S.SarproError):
+        ctx.process_polops(vv, vh, (S.OP_SUM, S.OP_DIFF, S.OP_RATIO), S.U8, S.ROBUST)
+    with pytest.raises(S.SarproError):
+        ctx.process_polops(vv, vh, (7,), S.U8, S.ROBUST)
+
+
 @pytest.mark.parametrize("strategy", [S.CLAHE, S.ROBUST, S.TAMED])
 @pytest.mark.parametrize("shape,target", [((3001, 4999), 1024), ((2500, 9000), 700), ((5003, 2001), 512), ((3001, 5000), 1024),
                                           ((1031, 2048), 300), ((517, 25000), 2048), ((2100, 4096), 2048)])
@@ -426,3 +471,40 @@ def test_device_plan_and_host_plan_give_the_same_image(strategy, monkeypatch):
     for a, b in zip(got[""][1], got["1"][1]):
         for k in EXACT_STATS:
             assert getattr(a, k) == getattr(b, k), k
+
+
+# ---- batch entry (config 5) -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", [S.BATCH_MULTIBAND, S.BATCH_SYNRGB])
+def test_pipeline_batch_matches_single_calls_and_oracle(ctx, kind):
+    """sarpro_pipeline_batch (api/mod.rs:474-536's scene loop): scenes of differing shapes and dtypes, one skipped product,
+    one failing scene (bands of different shape) with continue_on_error; every processed scene equals the oracle's pipeline
+    on that scene, the report counts like BatchReport."""
+    from sarpro_b200.synth import synth_pair
+    shapes = [(900, 1400), (1211, 2048), (640, 777), (900, 1400)]
+    scenes = []
+    for i, sh in enumerate(shapes):
+        vv, vh = synth_pair(*sh, scene=i)
+        if i == 2:
+            vv, vh = vv.astype(np.float32), vh.astype(np.float32)  # the f32 boundary in the middle of a batch
+        scenes.append((vv, vh))
+    scenes.insert(1, None)                                             # skipped product
+    scenes.insert(3, (scenes[0][0], scenes[2][1]))                     # shapes differ -> error, loop continues
+    results, statuses, rep, stats = ctx.process_batch(scenes, kind, S.U8, S.CLAHE, 512, True)
+    assert (rep.processed, rep.skipped, rep.errors) == (4, 1, 1)
+    assert statuses[3] != 0 and results[3] is None and results[1] is None
+    for k, sc in enumerate(scenes):
+        if sc is None or k == 3:
+            continue
+        a, b = (np.asarray(x).astype(np.float32) for x in sc)
+        if kind == S.BATCH_SYNRGB:
+            ref, _ = O.pipeline_synrgb_jpeg(a, b, S.CLAHE, 512, True)
+            assert np.array_equal(results[k][0], ref), k
+        else:
+            r1, r2, _ = O.pipeline_multiband_tiff(a, b, S.U8, S.CLAHE, 512, True)
+            assert np.array_equal(results[k][0], r1) and np.array_equal(results[k][1], r2), k
+    # first error is returned when continue_on_error is off; scenes before it are processed
+    with pytest.raises(S.SarproError):
+        ctx.process_batch(scenes, kind, S.U8, S.CLAHE, 512, True, continue_on_error=False)
+    # an empty batch is a no-op
+    _, _, rep0, _ = ctx.process_batch([], kind, S.U8, S.ROBUST, 256, True)
+    assert (rep0.processed, rep0.skipped, rep0.errors) == (0, 0, 0)

@@ -56,6 +56,28 @@ for rows, cols, target in shapes:
             same = same and ok
         print(msg, flush=True)
         bad += 0 if same else 1
+    # config 4's call: two polarization operations at full resolution, any contiguous row split, merged scan / stat histograms
+    if not big or os.environ.get("POLOPS_BIG"):
+        r0, r1 = S.shard_rows(rows, world, rank, False)
+        for strategy, bd in ((S.EQUALIZED, S.U16), (S.ROBUST, S.U8), (S.STANDARD, S.U16)):
+            ops = (S.OP_LOGRATIO, S.OP_NDIFF)
+            mine, st = ctx.process_polops(vv[r0:r1], vh[r0:r1], ops, bd, strategy, scene_rows=rows)
+            whole, st1 = ctx.process_polops(vv, vh, ops, bd, strategy)
+            same = all(np.array_equal(np.asarray(mine[k]), np.asarray(whole[k])[r0:r1]) for k in range(2))
+            same = same and all(st[k].low_clip == st1[k].low_clip and st[k].high_clip == st1[k].high_clip and
+                                st[k].valid_count == st1[k].valid_count for k in range(2))
+            msg = f"rank {rank}/{world} {rows}x{cols} polops {S.STRATEGY_NAMES[strategy]} u{8 if bd == S.U8 else 16} rows[{r0},{r1}) sharded==single: {same}"
+            if rank == 0 and not big:
+                from oracle import pyoracle as O
+                a32, b32 = np.asarray(vv).astype(np.float32), np.asarray(vh).astype(np.float32)
+                ok = True
+                for k, op in enumerate(ops):
+                    po = O.process_scalar_data_pipeline(O.pol_op(op, a32, b32), bd, strategy, want_db=False)
+                    ok = ok and np.array_equal(np.asarray(mine[k]), (po.u8 if bd == S.U8 else po.u16)[r0:r1])
+                msg += f" sharded==oracle: {ok}"
+                same = same and ok
+            print(msg, flush=True)
+            bad += 0 if same else 1
     del vv, vh
 t = torch.tensor([bad], device="cuda")
 dist.all_reduce(t)
