@@ -20,7 +20,7 @@ second. One "step" = one pass of that pipeline over one synthetic scene.
   c5  batch of scenes -> 1024 px padded multiband u8 tiles (reference defaults, params.rs:33), scenes distributed over the GPUs
 
 N > 1 (torchrun, one rank per GPU). c3 / c2: `value` is ONE scene row-band-sharded over the ranks ("strong" scaling: every
-rank holds its band plus the Lanczos halo; integer histogram / CLAHE-tile all-reduces and a broadcast of the owned output rows
+rank holds its band plus the Lanczos halo; integer histogram / CLAHE-tile all-reduces and one all-gather of the owned output rows
 inside the library; the result is compared byte for byte with the single-GPU result of the same scene in this run —
 "parity_ok"; the line is not printed if that fails). The scenes-per-GPU replicas (config 5's distribution, no collective on the
 data path) are reported under "batch_mode". c1: independent replicas. c4: the pair row-sharded. c5: scenes distributed.
@@ -365,7 +365,7 @@ def main():
                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,
                         "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 4) for i in range(8) if stage_n[i]}}
             par = (f"ONE scene row-band-sharded over {world} GPUs (tile-row aligned bands + Lanczos halo); NCCL: fused all-reduce of both bands' DN "
-                   "histograms, of their CLAHE tile histograms, of the sample min/max, broadcast of the owned output rows; planned on the device") \
+                   "histograms, of their CLAHE tile histograms, one all-gather of the owned output rows with the sample min/max; planned on the device") \
                 if sharded else "single GPU"
             line = {
                 "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,

@@ -300,9 +300,18 @@ int sarpro_plan_kind_from_dn_histogram(const uint64_t* hist65536, int bit_depth,
  * twice on the host: directly from the fixed-point taps (out_direct) and by replaying the tensor-core kernel's plan — strips,
  * n-tile slots, k-step windows and the permuted hi/lo tap bytes of its B fragments — in the device's order (out_replay).
  * Returns 1 when the plan exists for this axis (0: the axis falls back to the other kernels, out_replay untouched).
- * max_span: longest strip in source columns (the CLAHE tile width), 0 = unbounded. */
-int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t out_size, size_t max_span,
+ * max_span: longest strip in source columns (the CLAHE tile width), 0 = unbounded. strip_ntiles: n-tiles (8 output columns) per
+ * strip, 0 = the default of 32 (a rank's band of a sharded scene uses shorter strips, see choose_strip_nt in api.cu). */
+int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t out_size, size_t max_span, size_t strip_ntiles,
                                   uint8_t* out_direct, uint8_t* out_replay);
+
+/* Test hook (host only): parameters and error bound of the guarded direct index the general f32 kernels use for the indices
+ * that are linear in dB, trunc((10 log10 v - low_db) / range_db * n) (stat bins autoscale.rs:113-116; quantised levels with
+ * gamma == 1, :440-442 / :649-651 / :732-734). The device evaluates t = ((e - e0) + (lg2(m) - f0)) * scale in fp32 (v = m 2^e,
+ * MUFU.LG2 on m) and takes floor(t) only when frac(t) lies in [guard, 1 - guard]; every other sample compares thresholds.
+ * guard == 1: the shortcut is off. */
+int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float min_v, float max_v, int* e0, float* f0, float* scale,
+                            float* guard);
 
 #ifdef __cplusplus
 }

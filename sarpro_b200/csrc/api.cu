@@ -210,8 +210,8 @@ static void drop_axis_plans(sarpro_ctx* ctx) {
     for (auto& w : ctx->band) { w.pc_axis_id = 0; w.pc_n_ctas = 0; }
 }
 
-int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res) {
-    const AxisKey key{in, out, wide ? 1 : 0, horiz ? 1 : 0, horiz ? src_kind : 0};
+int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res, uint32_t strip_nt) {
+    const AxisKey key{in, out, wide ? 1 : 0, horiz ? 1 : 0, horiz ? src_kind : 0, horiz ? strip_nt : 0u};
     auto it = ctx->axes.find(key);
     if (it != ctx->axes.end()) { *res = it->second; return 0; }
     AxisPlan* ap = new AxisPlan();
@@ -249,7 +249,7 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
         if (!rc && !wide && src_kind != HSRC_IMAGE) {
             const uint32_t tile_w = (in + kClaheTiles - 1) / kClaheTiles;
             if (hmma_build_plan(h.start.data(), h.size.data(), h.coef.data(), h.window, out, in,
-                                src_kind == HSRC_DN_CLAHE ? tile_w : 0u, &mp)) {
+                                src_kind == HSRC_DN_CLAHE ? tile_w : 0u, &mp, strip_nt)) {
                 rc = upload_vec(ctx, ap->m_btab, mp.btab.data(), mp.btab.size() * sizeof(uint4));
                 if (!rc) rc = upload_vec(ctx, ap->m_ntile, mp.ntile.data(), mp.ntile.size() * sizeof(int4));
                 if (!rc) rc = upload_vec(ctx, ap->m_strips, mp.strips.data(), mp.strips.size() * sizeof(uint4));
@@ -267,6 +267,20 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
     ctx->axes[key] = ap;
     *res = ap;
     return 0;
+}
+
+// Strip length (n-tiles of 8 output columns) of the tensor-core pass B for a raster of `rows` rows. A warp walks one 16-row
+// group along one strip at a time, so the number of such walks per warp sets the granularity of the launch: a whole scene has
+// thousands per SM, a rank's band of a sharded scene (2000 rows on 8 GPUs) would have less than one with full-length strips
+// and leave most warps idle. Shorter strips re-read the Lanczos window overlap (73 of 780 columns at 8 n-tiles), so the longest
+// strip that still gives every warp >= 2.3 walks wins. SARPRO_STRIP_NT overrides (measurement).
+uint32_t choose_strip_nt(const sarpro_ctx* ctx, uint64_t rows, uint64_t out_cols, bool clahe) {
+    if (const char* v = getenv("SARPRO_STRIP_NT")) return (uint32_t)std::max(1, std::min(32, atoi(v)));
+    const uint64_t n_nt = (out_cols + 7) / 8, groups = (rows + 15) / 16;
+    const uint64_t slots = (uint64_t)ctx->sm_count * hmma_warps(clahe);
+    for (uint32_t nt = 32; nt > 4; nt /= 2)
+        if (groups * ((n_nt + nt - 1) / nt) * 10 >= slots * 23) return nt;
+    return 4;
 }
 
 // ---- horizontal pass dispatch -----------------------------------------------------------------------
@@ -692,7 +706,7 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     const bool clahe = uses_clahe(j);
     const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
     AxisPlan *ah, *av;
-    RC(get_axis(ctx, (uint32_t)j.cols, (uint32_t)g.rc, pix16, true, src_kind, &ah));
+    RC(get_axis(ctx, (uint32_t)j.cols, (uint32_t)g.rc, pix16, true, src_kind, &ah, choose_strip_nt(ctx, j.rows, g.rc, clahe)));
     RC(get_axis(ctx, (uint32_t)j.rows, (uint32_t)g.rr, pix16, false, 0, &av));
     RC(reserve(ctx, w.temp, (size_t)j.rows * g.rc * esz));
     if (clahe) RC(run_clahe_stats(ctx, b));
@@ -1130,6 +1144,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     ctx->db_table.cap = kDnBins * sizeof(double);
     if ((e = cudaMemcpy(ctx->db_table.p, dn_db_table(), kDnBins * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
     if (const char* v = getenv("SARPRO_HOST_PLAN")) ctx->host_plan = atoi(v);
+    if (const char* v = getenv("SARPRO_F32_NO_GUARD")) ctx->f32_no_guard = atoi(v);
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     if (const char* v = getenv("SARPRO_HMMA")) ctx->use_hmma = atoi(v);
@@ -1162,6 +1177,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
         release(*b);
     for (auto& slot : ctx->batch_stage)
         for (DevBuf& b : slot) release(b);
+    release(ctx->gather);
     if (ctx->stream_up) { cudaStreamSynchronize(ctx->stream_up); cudaStreamDestroy(ctx->stream_up); }
     for (auto& ev : ctx->ev_up)
         if (ev) cudaEventDestroy(ev);
@@ -1220,8 +1236,8 @@ int sarpro_resize_output_dims(size_t cols, size_t rows, int has_target, size_t t
     return SARPRO_OK;
 }
 
-int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t out_size, size_t max_span, uint8_t* out_direct,
-                                  uint8_t* out_replay) {
+int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t out_size, size_t max_span, size_t strip_ntiles,
+                                  uint8_t* out_direct, uint8_t* out_replay) {
     if (!samples || !out_direct || !out_replay || in_size == 0 || out_size == 0) return SARPRO_ERR_INVALID_ARGUMENT;
     ResampleAxis ax;
     build_lanczos3_axis((uint32_t)in_size, (uint32_t)out_size, false, &ax);
@@ -1232,10 +1248,18 @@ int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t
         out_direct[ox] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
     }
     HMmaPlanHost plan;
-    if (!hmma_build_plan(ax.start.data(), ax.size.data(), ax.coef.data(), ax.window, (uint32_t)out_size, (uint32_t)in_size, (uint32_t)max_span, &plan))
+    if (!hmma_build_plan(ax.start.data(), ax.size.data(), ax.coef.data(), ax.window, (uint32_t)out_size, (uint32_t)in_size, (uint32_t)max_span, &plan,
+                         strip_ntiles ? (uint32_t)strip_ntiles : 32u))
         return 0;
     hmma_replay_row(plan, samples, (uint32_t)in_size, (uint32_t)out_size, ax.precision, out_replay);
     return 1;
+}
+
+int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float min_v, float max_v, int* e0, float* f0, float* scale,
+                            float* guard) {
+    if (!e0 || !f0 || !scale || !guard) return SARPRO_ERR_INVALID_ARGUMENT;
+    f32_guard(true, low_db, range_db, n, min_v, max_v, e0, f0, scale, guard);
+    return SARPRO_OK;
 }
 
 int sarpro_plan_from_present_list(const uint32_t* blocks, const uint32_t* pairs, uint32_t cap, int bit_depth, int strategy,

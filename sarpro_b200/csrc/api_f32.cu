@@ -15,15 +15,17 @@ cudaError_t launch_f32_scan(const void* a, const void* b, int a_u16, int b_u16, 
                             float valid_thresh, F32Scan* out, int sm_count, cudaStream_t stream);
 cudaError_t launch_f32_hist4096(const void* a, const void* b, int a_u16, int b_u16, int op0, int op1, int nops, uint64_t n,
                                 float valid_thresh, const float* min_db, const float* inv_span4096, const float* const* edges4096,
-                                unsigned long long* const* hist4096, double* const* sums, int sm_count, cudaStream_t stream);
+                                unsigned long long* const* hist4096, double* const* sums, const F32GuardHost* guards, int sm_count,
+                                cudaStream_t stream);
 cudaError_t launch_f32_quantize(const void* a, const void* b, int a_u16, int b_u16, int op0, int op1, int nops, uint64_t n,
                                 float valid_thresh, const float* low_db, const float* high_db, const float* gamma,
                                 const float* const* level_edges, uint32_t n_levels, const uint8_t* const* remap, int key_plane,
-                                void* const* out, int out_u8, int sm_count, cudaStream_t stream);
+                                void* const* out, int out_u8, const F32GuardHost* guards, int sm_count, cudaStream_t stream);
 
 namespace {
 inline float float_of_bits(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 constexpr size_t kScanOff = 0, kSumsOff = 64, kHistOff = 128; // joint workspace of a call: F32Scan[2] | double[2][2] | u64[2][4096]
+const F32GuardHost kNoGuard = {0, 0.f, 0.f, 1.f};
 } // namespace
 
 // a_dev / b_dev: f32 rasters, or u16 DN rasters when a_u16 / b_u16 is set (the loaders convert: the f32 the reference would
@@ -89,6 +91,7 @@ int f32_general(sarpro_ctx* ctx, int nops, const int* slots, const void* a_dev, 
     if (need_hist) {
         // an operation that needs no histogram (states 1-3) still rides along in a two-operation launch: its bins are ignored
         float fmin[2] = {0.f, 0.f}, finv[2] = {1.f, 1.f};
+        F32GuardHost hg[2] = {{0, 0.f, 0.f, 1.f}, {0, 0.f, 0.f, 1.f}};
         const float* edges_dev[2];
         for (int o = 0; o < nops; ++o) {
             BandWs& w = ctx->band[slots[o]];
@@ -98,13 +101,15 @@ int f32_general(sarpro_ctx* ctx, int nops, const int* slots, const void* a_dev, 
                 build_stat_edges(min_v[o], max_v[o], &edges[o]);
                 fmin[o] = (float)min_db[o];
                 finv[o] = (float)(4096.0 / (max_db[o] - min_db[o]));
+                f32_guard(!ctx->f32_no_guard, min_db[o], max_db[o] - min_db[o], kStatBins, min_v[o], max_v[o], &hg[o].e0, &hg[o].f0, &hg[o].scale,
+                          &hg[o].guard);
             } else {
                 edges[o].assign(kStatBins, std::numeric_limits<float>::infinity()); // everything in bin 0
             }
             CU(cudaMemcpyAsync(w.edges.p, edges[o].data(), kStatBins * 4, cudaMemcpyHostToDevice, ctx->stream));
         }
         KS(SARPRO_STAGE_HIST, launch_f32_hist4096(a_dev, b_dev, a_u16, b_u16, op0, op1, nops, n, ctx->valid_thresh, fmin, finv, edges_dev,
-                                                  hist_dev, sums_dev, ctx->sm_count, ctx->stream));
+                                                  hist_dev, sums_dev, hg, ctx->sm_count, ctx->stream));
         if (ctx->shard_reduce) RC(comm_reduce_f32_hist(ctx, hist_dev[0], sums_dev[0], nops));
         double sums[4];
         for (int o = 0; o < nops; ++o)
@@ -158,7 +163,7 @@ int f32_general(sarpro_ctx* ctx, int nops, const int* slots, const void* a_dev, 
         const float* le = (const float*)w.edges.p;
         void* key_out = w.dn.p;
         KS(SARPRO_STAGE_CONVERT, launch_f32_quantize(a_dev, b_dev, a_u16, b_u16, op0, -1, 1, n, ctx->valid_thresh, &lo_f, &hi_f, &g1, &le, 255,
-                                                     nullptr, 1, &key_out, 0, ctx->sm_count, ctx->stream));
+                                                     nullptr, 1, &key_out, 0, &kNoGuard, ctx->sm_count, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream)); // ledges is a host temporary
         std::vector<uint16_t> lut(kDnBins, 0);
         for (int k = 1; k <= 256; ++k) lut[k] = (uint16_t)(k - 1);
@@ -176,6 +181,7 @@ int f32_general(sarpro_ctx* ctx, int nops, const int* slots, const void* a_dev, 
     const float* le[2] = {nullptr, nullptr};
     const uint8_t* remap_dev[2] = {nullptr, nullptr};
     void* planes[2] = {nullptr, nullptr};
+    F32GuardHost qg[2] = {kNoGuard, kNoGuard};
     std::vector<float> ledges[2];
     for (int o = 0; o < nops; ++o) {
         BandWs& w = ctx->band[slots[o]];
@@ -195,6 +201,11 @@ int f32_general(sarpro_ctx* ctx, int nops, const int* slots, const void* a_dev, 
                           min_v[o], max_v[o], &ledges[o], &lvl_min, &lvl_max);
         CU(cudaMemcpyAsync(w.edges.p, ledges[o].data(), ledges[o].size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         lo_f[o] = (float)low; hi_f[o] = (float)high; gm_f[o] = (float)gamma;
+        // levels are linear in dB when gamma == 1 (autoscale.rs:440-442, 649-651 with range = max(high - low, 1)): most samples
+        // get their level from the guarded direct evaluation and never touch the threshold table (not when the range was
+        // raised to 1 dB: samples above high_clip then stop short of the top level)
+        f32_guard(gamma == 1.0 && high - low >= 1.0 && !ctx->f32_no_guard, low, high - low, n_levels, min_v[o], max_v[o], &qg[o].e0, &qg[o].f0,
+                  &qg[o].scale, &qg[o].guard);
         if (kind == PlanKind::Autoscale && out8) {
             // scale_u16_to_u8 over all pixels: levels are monotone in the sample, so the extrema are the levels of
             // the smallest / largest valid sample, plus 0 when any pixel is invalid (autoscale.rs:348-364, 669-670)
@@ -211,7 +222,7 @@ int f32_general(sarpro_ctx* ctx, int nops, const int* slots, const void* a_dev, 
         }
     }
     KS(SARPRO_STAGE_APPLY, launch_f32_quantize(a_dev, b_dev, a_u16, b_u16, op0, op1, nops, n, ctx->valid_thresh, lo_f, hi_f, gm_f, le, n_levels,
-                                               remap_dev, 0, planes, out8 ? 1 : 0, ctx->sm_count, ctx->stream));
+                                               remap_dev, 0, planes, out8 ? 1 : 0, qg, ctx->sm_count, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream)); // ledges are host temporaries
     if (!g.resize && !g.pad) return 0;
     // nops == 1 from here on

@@ -4,8 +4,8 @@
 // quantities are integers, so the sharded result is bit-identical to the single-GPU result:
 //   1. DN histogram            all-reduce(sum)  2 x 65,536 u32 (one group) -> every rank plans redundantly (on the device)
 //   2. CLAHE tile histograms   all-reduce(sum)  2 x 64 x 256 u32 (one group) -> every rank builds all 64 CDFs
-//   3. CLAHE sample min/max    all-reduce(max)  4 u32                      -> scale_u16_to_u8 decision
-//   4. resized rows            broadcast of each rank's own output rows (one fused group), <= 2 x out_cols x out_rows u8 in all
+//   3. resized rows + CLAHE sample min/max   ONE all-gather of a slot per rank: its own output rows of both bands and its
+//      extrema (16 bytes); the scale_u16_to_u8 decision is speculated (identity) and repaired in the rare other case
 // NCCL is dlopen()ed (libnccl.so.2, the copy torch ships) so the library has no link-time dependency; the
 // host only moves the 128-byte ncclUniqueId between ranks.
 #include <dlfcn.h>
@@ -33,6 +33,7 @@ struct NcclApi {
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -65,6 +66,7 @@ static NcclApi& nccl() {
     SARPRO_SYM(CommDestroy, "ncclCommDestroy")
     SARPRO_SYM(AllReduce, "ncclAllReduce")
     SARPRO_SYM(Broadcast, "ncclBroadcast")
+    SARPRO_SYM(AllGather, "ncclAllGather")
     SARPRO_SYM(GroupStart, "ncclGroupStart")
     SARPRO_SYM(GroupEnd, "ncclGroupEnd")
     SARPRO_SYM(GetErrorString, "ncclGetErrorString")
@@ -325,7 +327,8 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     AxisPlan *ah = nullptr, *av = nullptr;
     const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
     if (g.rc == 0 || g.rr == 0) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "resize target yields an empty image");
-    RC(get_axis(ctx, (uint32_t)cols, (uint32_t)g.rc, false, true, src_kind, &ah));
+    // (the strip length follows the rows this rank holds, b1->rows: see choose_strip_nt)
+    RC(get_axis(ctx, (uint32_t)cols, (uint32_t)g.rc, false, true, src_kind, &ah, choose_strip_nt(ctx, b1->rows, g.rc, clahe)));
     RC(get_axis(ctx, (uint32_t)scene_rows, (uint32_t)g.rr, false, false, 0, &av));
     RC(shard_geometry(scene_rows, cols, true, target, pad != 0, cs->world, cs->rank, clahe, &r0, &r1, &h0, &h1, &oy0, &oy1, &g,
                       &av->h));
@@ -462,12 +465,36 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         if (!rc_b) { CU(e1); CU(e2); }
     }
     RC(rc_b);
-    // ---- vertical pass for the owned output rows (first run: assumes the tensor-core kernel took the band and the CLAHE
-    // re-stretch is the identity; the device-gated re-runs below repair it otherwise, see run_pass_b_resized)
+    // ---- owned output rows of every rank: the row bands partition the resized rows. Each rank writes its rows of both
+    // bands into its slot of one buffer, with its CLAHE sample extrema in the slot's tail, and ONE all-gather moves rows and
+    // extrema together (the all-reduce of the extrema and the 2 x world broadcasts this replaces cost two more collective
+    // latencies per scene).
+    if (cs->world > 16) return fail(ctx, SARPRO_ERR_COMM, "the sharded pipeline takes at most 16 ranks");
+    GatherGeom gg{};
+    gg.world = (uint32_t)cs->world;
+    gg.out_pitch = (uint32_t)g.oc;
+    gg.pad_top = (uint32_t)g.pad_top;
+    gg.out_rows = (uint32_t)g.rr;
+    gg.clahe = clahe ? 1u : 0u;
+    for (int r = 0; r < cs->world; ++r) {
+        size_t rr0, rr1, hh0, hh1, o0, o1;
+        RC(shard_geometry(scene_rows, cols, true, target, pad != 0, cs->world, r, clahe, &rr0, &rr1, &hh0, &hh1, &o0, &o1, nullptr, &av->h));
+        gg.oy0[r] = (uint32_t)o0;
+        gg.oy1[r] = (uint32_t)o1;
+        gg.max_rows = std::max<uint32_t>(gg.max_rows, (uint32_t)(o1 - o0));
+    }
+    gg.slot_bytes = (uint32_t)(((2 * (size_t)gg.max_rows * g.oc + 15) & ~(size_t)15) + 16);
+    RC(reserve(ctx, ctx->gather, (size_t)cs->world * gg.slot_bytes));
+    unsigned char* const my_slot = (unsigned char*)ctx->gather.p + (size_t)cs->rank * gg.slot_bytes;
+    CU(cudaMemsetAsync(my_slot, 0, gg.slot_bytes, ctx->stream)); // pad columns of the rows
+    // vertical pass for the owned output rows, straight into the slot (first run: assumes the tensor-core kernel took the band
+    // and the CLAHE re-stretch is the identity; the gated re-runs below and the repair path further down cover the rest)
     auto vpass = [&](int b, int stage, const uint32_t* skip, const uint32_t* run_if) -> int {
         BandWs& w = ctx->band[b];
         if (oy1 <= oy0) return 0;
-        unsigned char* dst = (unsigned char*)w.small.p + (g.pad_top * g.oc + g.pad_left) * esz;
+        // output row oy lands at local row oy - oy0 of the band's part of the slot (the kernel indexes by absolute output row)
+        unsigned char* dst = my_slot + (size_t)b * gg.max_rows * g.oc + g.pad_left;
+        dst -= (size_t)oy0 * g.oc;
         KS(stage, launch_vresize(w.temp.p, (uint32_t)h0, (uint32_t)g.rc, av->dev(), (uint32_t)oy0, (uint32_t)oy1, dst, (uint32_t)g.oc, 0, 0,
                                  ctx->stream, skip, run_if));
         return 0;
@@ -478,58 +505,55 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
             HResizeArgs ag = args[b];
             ag.run_if = &args[b].plan->use_generic;
             RC(run_hpass_generic(ctx, ag, src_kind, 0, ah));
+            RC(vpass(b, SARPRO_STAGE_OTHER, nullptr, &args[b].plan->use_generic));
         }
-    // ---- 3. scale_u16_to_u8 decision for CLAHE: global sample min/max --------------------------------------------
-    if (clahe) {
-        // scalars[0] = min, [1] = max per band -> pack {max, ~min} so that one all-reduce(max) serves both. Everything
-        // stays on the device: the merged extrema feed the remap/"identity" kernel, and the re-run of the horizontal
-        // pass is always launched but returns at once when the re-stretch is the identity (no host round trip).
-        RC(reserve(ctx, ctx->rgbsel, 64));
-        uint32_t* dpk = (uint32_t*)ctx->rgbsel.p + 4;
-        KS(SARPRO_STAGE_COMM, launch_minmax_pack((uint32_t*)ctx->band[0].scalars.p, (uint32_t*)ctx->band[1].scalars.p, dpk, 0, ctx->stream));
-        COMM_BEGIN();
-        NC(api.AllReduce(dpk, dpk, 4, kNcclUint32, kNcclMax, cs->comm, ctx->stream));
-        COMM_END();
-        KS(SARPRO_STAGE_COMM, launch_minmax_pack((uint32_t*)ctx->band[0].scalars.p, (uint32_t*)ctx->band[1].scalars.p, dpk, 1, ctx->stream));
-        for (int b = 0; b < 2; ++b) {
-            BandWs& w = ctx->band[b];
-            RC(reserve(ctx, w.remap, 256 + 16));
-            uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
-            KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream,
-                                                            gates[b] ? args[b].plan : nullptr));
-            HResizeArgs ar = args[b];
-            ar.remap = (const uint8_t*)w.remap.p;
-            ar.minmax = nullptr;
-            ar.skip = flag;
-            RC(run_hpass_generic(ctx, ar, src_kind, 0, ah));
-            RC(vpass(b, SARPRO_STAGE_OTHER, flag + 1, nullptr));
+    RC(reserve(ctx, ctx->rgbsel, 64));
+    uint32_t* const nonident = (uint32_t*)ctx->rgbsel.p + 4; // set by the unpack kernel: some band's re-stretch is not the identity
+    auto exchange = [&]() -> int {
+        if (clahe)
+            KS(SARPRO_STAGE_COMM, launch_gather_tail((const uint32_t*)ctx->band[0].scalars.p, (const uint32_t*)ctx->band[1].scalars.p,
+                                                     (uint32_t*)(my_slot + gg.slot_bytes - 16), ctx->stream));
+        CU(cudaMemsetAsync(nonident, 0, 4, ctx->stream));
+        {
+            COMM_BEGIN();
+            NC(api.AllGather(my_slot, ctx->gather.p, gg.slot_bytes, kNcclUint8, cs->comm, ctx->stream));
+            COMM_END();
         }
-    } else {
-        for (int b = 0; b < 2; ++b)
-            if (gates[b]) RC(vpass(b, SARPRO_STAGE_OTHER, nullptr, &args[b].plan->use_generic));
-    }
-    if (n_out) {
-        // The canvases are zero outside a rank's own output rows: rank r's rows [oy0_r, oy1_r) (whole canvas rows, pad columns
-        // included) are broadcast in place from r, 2 x world broadcasts fused into one group (<= 0.55 MB per rank at C3 on 8
-        // GPUs, instead of an all-reduce over the 2 x 4 MB canvases).
-        COMM_BEGIN();
-        NC(api.GroupStart());
-        for (int r = 0; r < cs->world; ++r) {
-            size_t rr0, rr1, hh0, hh1, o0, o1;
-            RC(shard_geometry(scene_rows, cols, true, target, pad != 0, cs->world, r, clahe, &rr0, &rr1, &hh0, &hh1, &o0, &o1, nullptr, &av->h));
-            if (o1 <= o0) continue;
+        KS(SARPRO_STAGE_COMM, launch_gather_unpack((const unsigned char*)ctx->gather.p, gg, (unsigned char*)ctx->band[0].small.p,
+                                                   (unsigned char*)ctx->band[1].small.p, (uint32_t*)ctx->band[0].scalars.p,
+                                                   (uint32_t*)ctx->band[1].scalars.p, nonident, ctx->stream));
+        RC(synrgb_compose(ctx, strategy, (const uint8_t*)ctx->band[0].small.p, (const uint8_t*)ctx->band[1].small.p, n_out));
+        if (out) {
+            fill_image(out, g, 3, SARPRO_U8);
+            if (out->data) RC(deliver(ctx, ctx->rgb.p, n_out * 3, out));
+        }
+        return 0;
+    };
+    if (n_out) RC(exchange());
+    // ---- scale_u16_to_u8 after CLAHE (autoscale.rs:348-364) needs the sample extrema of the WHOLE scene. The result above
+    // assumed the re-stretch is the identity (extrema 0 / 255: any scene with an invalid pixel and a saturated one); the merged
+    // extrema arrive with the rows, and in the rare other case every rank (they all see the same merged values) repairs its
+    // rows with the remap table and the exchange runs once more.
+    if (clahe && n_out) {
+        CU(cudaMemcpyAsync(ctx->h_scalars + 7, nonident, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream)); // (the sync every call ends with; end_call's then returns at once)
+        if (ctx->h_scalars[7]) {
+            ctx->timing.host_syncs++;
             for (int b = 0; b < 2; ++b) {
-                unsigned char* rows_r = (unsigned char*)ctx->band[b].small.p + (g.pad_top + o0) * g.oc * esz;
-                NC(api.Broadcast(rows_r, rows_r, (o1 - o0) * g.oc * esz, kNcclUint8, r, cs->comm, ctx->stream));
+                BandWs& w = ctx->band[b];
+                RC(reserve(ctx, w.remap, 256 + 16));
+                uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
+                KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream,
+                                                                gates[b] ? args[b].plan : nullptr));
+                HResizeArgs ar = args[b];
+                ar.remap = (const uint8_t*)w.remap.p;
+                ar.minmax = nullptr;
+                ar.skip = flag; // a band whose own re-stretch is the identity keeps its rows
+                RC(run_hpass_generic(ctx, ar, src_kind, 0, ah));
+                RC(vpass(b, SARPRO_STAGE_OTHER, flag, nullptr));
             }
+            RC(exchange());
         }
-        NC(api.GroupEnd());
-        COMM_END();
-    }
-    RC(synrgb_compose(ctx, strategy, (const uint8_t*)ctx->band[0].small.p, (const uint8_t*)ctx->band[1].small.p, n_out));
-    if (out) {
-        fill_image(out, g, 3, SARPRO_U8);
-        if (out->data) RC(deliver(ctx, ctx->rgb.p, n_out * 3, out));
     }
     return end_call(ctx);
 }

@@ -58,8 +58,9 @@ struct AxisPlan {
 struct AxisKey {
     uint32_t in, out;
     int wide, horiz, src_kind;
+    uint32_t strip_nt; // n-tiles per strip of the tensor-core plan (horizontal axes only)
     bool operator<(const AxisKey& o) const {
-        return std::tie(in, out, wide, horiz, src_kind) < std::tie(o.in, o.out, o.wide, o.horiz, o.src_kind);
+        return std::tie(in, out, wide, horiz, src_kind, strip_nt) < std::tie(o.in, o.out, o.wide, o.horiz, o.src_kind, o.strip_nt);
     }
 };
 
@@ -155,6 +156,7 @@ struct sarpro_ctx {
     bool shard_reduce = false;     // inside a sharded general-path call: merge scan / stat histogram over the ranks
     uint64_t shard_scene_px = 0;   // pixels of the whole scene in that call
     int host_plan = 0;             // SARPRO_HOST_PLAN=1: plan every band on the host (validation)
+    int f32_no_guard = 0;          // SARPRO_F32_NO_GUARD=1: general f32 path compares thresholds for every sample (validation)
     // timing
     cudaEvent_t ev[6] = {};
     sarpro_timing timing{};
@@ -176,6 +178,7 @@ struct sarpro_ctx {
     cudaEvent_t ev_up[2] = {nullptr, nullptr};  // upload of staging slot s complete
     cudaEvent_t ev_chunk[16] = {};              // streamed single-scene upload: chunk c of a band has landed
     sarpro::DevBuf batch_stage[2][2];           // [slot][band]
+    sarpro::DevBuf gather;                      // sharded scene: all-gathered output rows + extrema of every rank (comm.cu)
 };
 
 namespace sarpro {
@@ -185,7 +188,9 @@ double host_ms();
 int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes);
 uint32_t hmma_hot(const uint16_t* lut_host, const uint32_t* hist_host, uint32_t max_present_dn, uint32_t* top_out);
 uint32_t hmma_hot_from_plan(const BandPlan& plan, uint32_t* top_out);
-int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res);
+// strip_nt: n-tiles (8 output columns) per strip of the tensor-core pass B; shorter strips = finer work units for short rasters
+int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res, uint32_t strip_nt = 32);
+uint32_t choose_strip_nt(const sarpro_ctx* ctx, uint64_t rows, uint64_t out_cols, bool clahe);
 int begin_call(sarpro_ctx* ctx);
 // slot: the band slot whose piece lists the tensor-core kernel uses; *gate: see api.cu
 int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off, bool* gate);

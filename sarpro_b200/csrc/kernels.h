@@ -125,6 +125,17 @@ cudaError_t launch_apply_clahe(const uint16_t* dn, uint32_t rows, uint32_t cols,
                                cudaStream_t stream);
 // packs (unpack = 0) / unpacks (1) {max, ~min} of two bands' {min, max} words into / from a 4-word vector
 cudaError_t launch_minmax_pack(uint32_t* scalars0, uint32_t* scalars1, uint32_t* packed4, int unpack, cudaStream_t stream);
+// Sharded scene, last exchange (comm.cu): every rank's slot of the all-gathered buffer holds its own output rows of both bands
+// (max_rows x out_pitch bytes per band, row oy of rank r at local row oy - oy0[r]) and a 16-byte tail {min0, max0, min1, max1}
+// with its CLAHE sample extrema. The kernel copies the rows into the two canvases (canvas row pad_top + oy), merges the extrema
+// over the ranks into the bands' scalars and writes flag[0] = 1 when scale_u16_to_u8 is not the identity for some band.
+struct GatherGeom {
+    uint32_t world, out_pitch, max_rows, slot_bytes, pad_top, out_rows, clahe, reserved;
+    uint32_t oy0[16], oy1[16];
+};
+cudaError_t launch_gather_unpack(const unsigned char* gathered, GatherGeom gg, unsigned char* canvas0, unsigned char* canvas1,
+                                 uint32_t* scalars0, uint32_t* scalars1, uint32_t* flag, cudaStream_t stream);
+cudaError_t launch_gather_tail(const uint32_t* scalars0, const uint32_t* scalars1, uint32_t* tail4, cudaStream_t stream);
 // in-place u8 remap through a 256-entry table
 // skip: optional device flag, the kernel returns at once when *skip != 0
 cudaError_t launch_remap_u8(uint8_t* data, uint64_t n, const uint8_t* remap256, int sm_count, cudaStream_t stream,
@@ -202,7 +213,7 @@ struct HMmaPlanHost {
 // max_span: longest source span of a strip in columns (CLAHE: the tile width), 0 = unbounded. false when the axis
 // does not fit the kernel (in_size not a multiple of 8, more than three n-tiles in flight, ...).
 bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int32_t* coef_h, uint32_t window, uint32_t out_size,
-                     uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan);
+                     uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan, uint32_t max_strip_ntiles = 32);
 bool hmma_replay_row(const HMmaPlanHost& plan, const uint8_t* samples, uint32_t in_size, uint32_t out_size, int precision, uint8_t* out);
 size_t hmma_smem_bytes(int src_kind, uint32_t b_bytes);
 uint32_t hmma_warps(bool clahe); // warps per CTA of the instantiation
@@ -243,6 +254,12 @@ cudaError_t launch_pol_op(const float* a, const float* b, int op, uint64_t n, fl
 // general f32 path (kernels_f32.cu; launchers declared in api_f32.cu): min/max/count over valid samples.
 // valid <=> v >= valid_thresh (the smallest f32 with dB > -50); valid samples are positive, so the bit
 // pattern orders like the value.
+// Parameters of the guarded direct index of the general f32 path (kernels_f32.cu f32_guarded_index; built by f32_guard in
+// plan_f32.cpp). guard >= 0.5: the shortcut is off and every sample takes the threshold comparison.
+struct F32GuardHost {
+    int e0;
+    float f0, scale, guard;
+};
 struct F32Scan {
     uint32_t min_key, max_key; // bit patterns of the min / max valid sample
     unsigned long long valid_count;

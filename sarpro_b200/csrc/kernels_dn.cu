@@ -635,6 +635,52 @@ cudaError_t launch_minmax_pack(uint32_t* scalars0, uint32_t* scalars1, uint32_t*
     return cudaGetLastError();
 }
 
+// ---- sharded scene: rows + extrema out of the all-gathered slots (see GatherGeom in kernels.h) ----------------------------
+__global__ void k_gather_tail(const uint32_t* __restrict__ s0, const uint32_t* __restrict__ s1, uint32_t* __restrict__ tail) {
+    const uint32_t* s = threadIdx.x < 2 ? s0 : s1;
+    tail[threadIdx.x] = s[threadIdx.x & 1u];
+}
+cudaError_t launch_gather_tail(const uint32_t* scalars0, const uint32_t* scalars1, uint32_t* tail4, cudaStream_t stream) {
+    k_gather_tail<<<1, 4, 0, stream>>>(scalars0, scalars1, tail4);
+    return cudaGetLastError();
+}
+__global__ void __launch_bounds__(128) k_gather_unpack(const unsigned char* __restrict__ gathered, GatherGeom gg,
+                                                       unsigned char* __restrict__ canvas0, unsigned char* __restrict__ canvas1,
+                                                       uint32_t* __restrict__ scalars0, uint32_t* __restrict__ scalars1,
+                                                       uint32_t* __restrict__ flag) {
+    const uint32_t oy = blockIdx.x, b = blockIdx.y;
+    if (oy == 0 && b == 0 && threadIdx.x < 2 && gg.clahe) { // merged extrema of band threadIdx.x
+        uint32_t mn = 0xffffffffu, mx = 0;
+        for (uint32_t r = 0; r < gg.world; ++r) {
+            const uint32_t* t = reinterpret_cast<const uint32_t*>(gathered + (size_t)(r + 1) * gg.slot_bytes - 16) + 2 * threadIdx.x;
+            if (t[0] != 0xffffffffu) { mn = min(mn, t[0]); mx = max(mx, t[1]); }
+        }
+        uint32_t* s = threadIdx.x ? scalars1 : scalars0;
+        s[0] = mn;
+        s[1] = mx;
+        if (mn == 0xffffffffu) { mn = 0; mx = 0; }
+        const bool identity = (mn == 0 && mx == 255) || (mn == 0 && mx == 0); // as k_clahe_remap_decide
+        if (!identity) atomicOr(flag, 1u);
+    }
+    uint32_t r = 0;
+    while (r + 1 < gg.world && !(oy >= gg.oy0[r] && oy < gg.oy1[r])) ++r;
+    if (!(oy >= gg.oy0[r] && oy < gg.oy1[r])) return; // a row no rank owns (cannot happen: the bands partition the rows)
+    const unsigned char* src = gathered + (size_t)r * gg.slot_bytes + ((size_t)b * gg.max_rows + (oy - gg.oy0[r])) * gg.out_pitch;
+    unsigned char* dst = (b ? canvas1 : canvas0) + (size_t)(gg.pad_top + oy) * gg.out_pitch;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | gg.out_pitch) & 15u) == 0) {
+        for (uint32_t i = threadIdx.x; i < gg.out_pitch / 16u; i += blockDim.x)
+            reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < gg.out_pitch; i += blockDim.x) dst[i] = src[i];
+    }
+}
+cudaError_t launch_gather_unpack(const unsigned char* gathered, GatherGeom gg, unsigned char* canvas0, unsigned char* canvas1,
+                                 uint32_t* scalars0, uint32_t* scalars1, uint32_t* flag, cudaStream_t stream) {
+    if (gg.out_rows == 0) return cudaSuccess;
+    k_gather_unpack<<<dim3(gg.out_rows, 2), 128, 0, stream>>>(gathered, gg, canvas0, canvas1, scalars0, scalars1, flag);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(512) k_minmax_u16(const uint16_t* __restrict__ data, uint64_t n,
                                                     uint32_t* __restrict__ minmax) {
     uint32_t mn = 0xffffffffu, mx = 0;

@@ -144,6 +144,35 @@ __device__ __forceinline__ uint32_t edge_index(const float* __restrict__ edges, 
     return (uint32_t)g;
 }
 
+// Guarded direct index. For the linear-in-dB index functions (stat bins; quantised levels with gamma == 1) the position
+//   t = (log2(v) - y_lo) * scale,   y_lo = low_dB / (10 log10 2),   scale = n * 10 log10 2 / range_dB
+// is evaluated in fp32 with a proven error bound E (host: f32_guard): log2(v) = e + lg2(m) with the exponent e exact and
+// MUFU.LG2 on the mantissa m in [1, 2) (absolute error <= 2^-22), y_lo split into integer and fraction so that the integer
+// parts cancel exactly. When frac(t) lies in [E, 1 - E] the reference's f64 index is floor(t) and no threshold is read; the
+// other samples (a share of 2E) take the exact threshold comparison. E >= 0.5 switches the shortcut off.
+struct F32Guard {
+    int e0;        // floor(y_lo)
+    float f0;      // y_lo - floor(y_lo)
+    float scale;   // n * 10 log10(2) / range
+    float guard;   // E
+};
+__device__ __forceinline__ float f32_split_log2(float x, int* e) {
+    const uint32_t b = __float_as_uint(x); // positive, normal (>= valid_thresh)
+    *e = (int)(b >> 23) - 127;
+    return __log2f(__uint_as_float((b & 0x7fffffu) | 0x3f800000u));
+}
+// returns true and the index when the shortcut decides; n = number of edges (indices 0..n)
+__device__ __forceinline__ bool f32_guarded_index(const F32Guard& gd, int e, float lg, uint32_t n, uint32_t top, uint32_t* idx) {
+    const float d = __fadd_rn((float)(e - gd.e0), __fsub_rn(lg, gd.f0));
+    const float t = __fmul_rn(d, gd.scale);
+    const float nf = (float)n;
+    if (t < -gd.guard) { *idx = 0; return true; }
+    if (t > nf + gd.guard) { *idx = top; return true; }
+    const float fl = floorf(t), fr = t - fl; // exact
+    if (fr >= gd.guard && fr <= 1.0f - gd.guard && fl >= 0.0f && fl < nf) { *idx = (uint32_t)fl; return true; }
+    return false;
+}
+
 // ---- pass 2: 4096-bin histogram over [min_db, max_db] + mean / M2 accumulators -----------------------
 struct F32HistArgs {
     float valid_thresh;
@@ -151,6 +180,7 @@ struct F32HistArgs {
     const float* edges[2];            // [4096]: edges[k], k = 1..4095
     unsigned long long* hist[2];      // [4096]
     double* sums[2];                  // [0] = sum(db - min_db), [1] = sum((db - min_db)^2)   (fp32 logs, f64 accumulation)
+    F32Guard guard[2];
 };
 template <int NOPS>
 __global__ void __launch_bounds__(256) k_f32_hist4096(F32Src src, uint64_t n, F32HistArgs h) {
@@ -179,8 +209,12 @@ __global__ void __launch_bounds__(256) k_f32_hist4096(F32Src src, uint64_t n, F3
             for (int k = 0; k < 8; ++k) {
                 const float x = s[o][k];
                 if ((uint32_t)k < c && x >= h.valid_thresh) {
-                    const float rel = __fsub_rn(3.0102999566f * __log2f(x), h.min_db[o]);
-                    const uint32_t idx = edge_index(s_edges + o * 4096, 4095, x, (int)(rel * h.inv_span4096[o]));
+                    int e;
+                    const float lg = f32_split_log2(x, &e);
+                    const float rel = __fsub_rn(3.0102999566f * __fadd_rn((float)e, lg), h.min_db[o]);
+                    uint32_t idx;
+                    if (!f32_guarded_index(h.guard[o], e, lg, 4096u, 4095u, &idx))
+                        idx = edge_index(s_edges + o * 4096, 4095, x, (int)(rel * h.inv_span4096[o]));
                     atomicAdd(&s_hist[o * 4096 + idx], 1u);
                     r1 += rel;
                     r2 += rel * rel;
@@ -214,12 +248,14 @@ __global__ void __launch_bounds__(256) k_f32_hist4096(F32Src src, uint64_t n, F3
 }
 cudaError_t launch_f32_hist4096(const void* a, const void* b, int a_u16, int b_u16, int op0, int op1, int nops, uint64_t n,
                                 float valid_thresh, const float* min_db, const float* inv_span4096, const float* const* edges4096,
-                                unsigned long long* const* hist4096, double* const* sums, int sm_count, cudaStream_t stream) {
+                                unsigned long long* const* hist4096, double* const* sums, const F32GuardHost* guards, int sm_count,
+                                cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     F32HistArgs h{};
     h.valid_thresh = valid_thresh;
     for (int o = 0; o < nops; ++o) {
         h.min_db[o] = min_db[o]; h.inv_span4096[o] = inv_span4096[o]; h.edges[o] = edges4096[o]; h.hist[o] = hist4096[o]; h.sums[o] = sums[o];
+        h.guard[o] = F32Guard{guards[o].e0, guards[o].f0, guards[o].scale, guards[o].guard};
     }
     const F32Src src = make_src(a, b, a_u16, b_u16, op0, nops == 2 ? op1 : -1);
     const size_t smem = (size_t)nops * 4096 * 8;
@@ -242,6 +278,7 @@ struct F32QuantArgs {
     int key_plane;                                       // 1: write u16 key = level + 1 for valid, 0 for invalid (CLAHE bridge)
     void* out[2];
     int out_vec;                                         // outputs are 16-byte aligned
+    F32Guard guard[2];
 };
 template <int NOPS, typename OutT>
 __global__ void __launch_bounds__(256) k_f32_quantize(F32Src src, uint64_t n, F32QuantArgs qa) {
@@ -269,11 +306,16 @@ __global__ void __launch_bounds__(256) k_f32_quantize(F32Src src, uint64_t n, F3
                 const float x0 = s[o][k];
                 uint32_t r = 0;
                 if ((uint32_t)k < c && x0 >= qa.valid_thresh) {
-                    float x = 3.0102999566f * __log2f(x0);
-                    x = fminf(fmaxf(x, qa.low_db[o]), qa.high_db[o]);
-                    x = (x - qa.low_db[o]) * qa.inv_range[o];
-                    if (qa.gamma[o] != 1.0f) x = __powf(fmaxf(x, 0.0f), qa.gamma[o]);
-                    const uint32_t lvl = edge_index(edges, qa.n_levels, x0, (int)(x * fl));
+                    int e;
+                    const float lg = f32_split_log2(x0, &e);
+                    uint32_t lvl;
+                    if (!f32_guarded_index(qa.guard[o], e, lg, qa.n_levels, qa.n_levels, &lvl)) {
+                        float x = 3.0102999566f * __fadd_rn((float)e, lg);
+                        x = fminf(fmaxf(x, qa.low_db[o]), qa.high_db[o]);
+                        x = (x - qa.low_db[o]) * qa.inv_range[o];
+                        if (qa.gamma[o] != 1.0f) x = __powf(fmaxf(x, 0.0f), qa.gamma[o]);
+                        lvl = edge_index(edges, qa.n_levels, x0, (int)(x * fl));
+                    }
                     r = qa.key_plane ? lvl + 1 : (sizeof(OutT) == 1 ? (uint32_t)s_remap[o][lvl & 255u] : lvl);
                 } else if (!qa.key_plane && sizeof(OutT) == 1) {
                     r = s_remap[o][0]; // invalid samples are 0 before scale_u16_to_u8 (autoscale.rs:444, 669-670)
@@ -298,7 +340,7 @@ __global__ void __launch_bounds__(256) k_f32_quantize(F32Src src, uint64_t n, F3
 cudaError_t launch_f32_quantize(const void* a, const void* b, int a_u16, int b_u16, int op0, int op1, int nops, uint64_t n,
                                 float valid_thresh, const float* low_db, const float* high_db, const float* gamma,
                                 const float* const* level_edges, uint32_t n_levels, const uint8_t* const* remap, int key_plane,
-                                void* const* out, int out_u8, int sm_count, cudaStream_t stream) {
+                                void* const* out, int out_u8, const F32GuardHost* guards, int sm_count, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     F32QuantArgs qa{};
     qa.valid_thresh = valid_thresh;
@@ -311,6 +353,7 @@ cudaError_t launch_f32_quantize(const void* a, const void* b, int a_u16, int b_u
         qa.edges[o] = level_edges[o];
         qa.remap[o] = remap ? remap[o] : nullptr;
         qa.out[o] = out[o];
+        qa.guard[o] = F32Guard{guards[o].e0, guards[o].f0, guards[o].scale, guards[o].guard};
         if (reinterpret_cast<uintptr_t>(out[o]) & 15u) qa.out_vec = 0;
     }
     const F32Src src = make_src(a, b, a_u16, b_u16, op0, nops == 2 ? op1 : -1);

@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
 // n-tiles (8 output columns), their 64-column source blocks, the permuted tap bytes, and strips of n-tiles whose
 // source span is at most max_span columns (CLAHE: one tile width, so that a strip meets at most one cell boundary).
 bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int32_t* coef_h, uint32_t window, uint32_t out_size,
-                     uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan) {
+                     uint32_t in_size, uint32_t max_span, HMmaPlanHost* plan, uint32_t max_strip_ntiles) {
     plan->btab.clear();
     plan->ntile.clear();
     plan->strips.clear();
@@ -756,7 +756,7 @@ bool hmma_build_plan(const uint32_t* start_h, const uint32_t* size_h, const int3
             return ((uint32_t)plan->ntile[e - 1].z + (uint32_t)(plan->ntile[e - 1].y - plan->ntile[e - 1].x + 1) - (uint32_t)plan->ntile[j0].z) * 512u;
         };
         if ((max_span && span(j1) > max_span) || bbytes(j1) > hm::kMaxStripB || span(j1) > hm::kMaxStripVecs * 8u) return false;
-        while (j1 < n_nt && j1 - j0 < 32 && (!max_span || span(j1 + 1) <= max_span) && bbytes(j1 + 1) <= hm::kMaxStripB &&
+        while (j1 < n_nt && j1 - j0 < std::min(32u, std::max(1u, max_strip_ntiles)) && (!max_span || span(j1 + 1) <= max_span) && bbytes(j1 + 1) <= hm::kMaxStripB &&
                span(j1 + 1) <= hm::kMaxStripVecs * 8u)
             ++j1;
         const uint32_t cb0 = (uint32_t)plan->ntile[j0].x / 2, cb1 = (uint32_t)plan->ntile[j1 - 1].y / 2 + 1;

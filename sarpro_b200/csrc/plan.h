@@ -121,6 +121,14 @@ float valid_threshold();
 // is >= k; +inf when no sample value reaches k. edges has 4096 entries, edges[0] = 0.
 void build_stat_edges(float min_v, float max_v, std::vector<float>* edges);
 enum class LevelKind { Quantize, TamedLinearU8, ClaheBin };
+// Parameters and error bound of the device's direct fp32 evaluation of a linear-in-dB index
+//   index(v) = trunc((dB(v) - low_db) / range_db * n)        (stat bins: n = 4096; quantised levels with gamma == 1)
+// for samples in [min_v, max_v]: the device computes t = ((e - e0) + (lg2(m) - f0)) * scale (kernels_f32.cu) and trusts
+// floor(t) only when frac(t) is at least `guard` away from both integers. guard covers: MUFU.LG2 on [1,2) (2^-22 absolute),
+// the fp32 roundings of f0, of the two additions and of the product, the fp32 rounding of scale, and the reference's own f64
+// roundings; times 1.5. on == false (gamma != 1, CLAHE bins, degenerate ranges): guard = 1, every sample compares thresholds.
+void f32_guard(bool on, double low_db, double range_db, uint32_t n, float min_v, float max_v, int* e0, float* f0, float* scale,
+               float* guard);
 // edges[k] (k = 1..n_levels) = smallest valid f32 v in [min_v, max_v] whose level is >= k, where level is
 //   Quantize      : cast_u16(clamp(pow((clip(db)-low)/range, gamma) * max_val, 0, max_val))   autoscale.rs:440-442
 //   TamedLinearU8 : cast_u8(clamp(((clip(db)-low)/range) * 255, 0, 255))                      autoscale.rs:734-736

@@ -142,4 +142,24 @@ void build_level_edges(LevelKind kind, double low, double high, double gamma, ui
     });
 }
 
+void f32_guard(bool on, double low_db, double range_db, uint32_t n, float min_v, float max_v, int* e0, float* f0, float* scale,
+               float* guard) {
+    *e0 = 0; *f0 = 0.f; *scale = 0.f; *guard = 1.0f;
+    if (!on || !(range_db > 0.0) || !std::isfinite(range_db) || !std::isfinite(low_db) || !(min_v > 0.f) || !std::isfinite(max_v)) return;
+    const double k = 10.0 * std::log10(2.0);         // dB per octave
+    const double y_lo = low_db / k;
+    const double fl = std::floor(y_lo);
+    if (std::fabs(fl) > 1e6) return;
+    const double sc = (double)n * k / range_db;
+    const double dmax = std::fmax(std::fabs(std::log2((double)min_v) - y_lo), std::fabs(std::log2((double)max_v) - y_lo)) + 1.0;
+    const double e_d = std::ldexp(1.0, -22) + 2.0 * std::ldexp(1.0, -25) + std::ldexp(1.0, -24) * dmax;
+    const double e_t = e_d * sc + ((double)n + 2.0) * std::ldexp(1.0, -23) + 1e-6;
+    const double g = 1.5 * e_t;
+    if (!(g < 0.45) || !(sc < 1e30)) return;         // too coarse to help: compare thresholds
+    *e0 = (int)fl;
+    *f0 = (float)(y_lo - fl);
+    *scale = (float)sc;
+    *guard = (float)g;
+}
+
 } // namespace sarpro

@@ -210,6 +210,26 @@ def test_pipeline_polops_two_operations(ctx, strategy, bit_depth):
         assert np.array_equal(planes[0], ref.u8 if bit_depth == S.U8 else ref.u16), op
 
 
+@pytest.mark.parametrize("strategy,bit_depth", [(S.EQUALIZED, S.U16), (S.ROBUST, S.U8), (S.TAMED, S.U16), (S.STANDARD, S.U16)])
+def test_pipeline_polops_large_guarded_index(strategy, bit_depth, monkeypatch):
+    """6 M pixels per band through the general f32 kernels with the guarded direct index (kernels_f32.cu: most samples get
+    their stat bin / level from one fp32 evaluation, the rest compare thresholds) and with the shortcut switched off
+    (SARPRO_F32_NO_GUARD=1): both must equal the oracle byte for byte, statistics included."""
+    from sarpro_b200.synth import synth_pair
+    vv, vh = synth_pair(2000, 3000, point_targets=1e-4)
+    ops = (S.OP_LOGRATIO, S.OP_NDIFF)
+    refs = [O.process_scalar_data_pipeline(O.pol_op(op, vv.astype(np.float32), vh.astype(np.float32)), bit_depth, strategy, want_db=False)
+            for op in ops]
+    for env in ("0", "1"):
+        monkeypatch.setenv("SARPRO_F32_NO_GUARD", env)
+        with S.Context(0) as c:
+            planes, stats = c.process_polops(vv, vh, ops, bit_depth, strategy)
+        for k in range(2):
+            ref = refs[k].u8 if bit_depth == S.U8 else refs[k].u16
+            assert np.array_equal(planes[k], ref), (env, k, int((planes[k] != ref).sum()))
+            _check_stats_f32(stats[k], refs[k].stats)
+
+
 def test_pipeline_polops_degenerate_and_errors(ctx):
     """One operation without a valid sample rides along with a regular one (diff with a < b everywhere: all zeros); CLAHE and a
     third operation are refused with INVALID_ARGUMENT."""

@@ -126,15 +126,17 @@ def test_shard_rows(lib_built):
 @pytest.mark.parametrize("in_size,out_size,max_span", [(25000, 2048, 3125), (25000, 2048, 0), (25000, 1024, 3125), (16000, 1311, 0),
                                                         (4096, 2048, 512), (9000, 700, 1125), (2048, 300, 256), (5000, 1024, 625),
                                                         (1400, 512, 175), (4999, 1024, 0), (640, 600, 0)])
-def test_tensor_core_tap_plan_replays_the_horizontal_pass(lib_built, in_size, out_size, max_span):
+@pytest.mark.parametrize("strip_nt", [0, 16, 8, 4, 1])
+def test_tensor_core_tap_plan_replays_the_horizontal_pass(lib_built, in_size, out_size, max_span, strip_nt):
     """Host logic of kernels_hmma.cu: the n-tile / k-step plan and the permuted hi/lo tap bytes of the B fragments, replayed
-    in the device's order on one row, must give the same bytes as the direct fixed-point Lanczos3 pass (and as the oracle's)."""
+    in the device's order on one row, must give the same bytes as the direct fixed-point Lanczos3 pass (and as the oracle's).
+    strip_nt: strips of at most that many n-tiles (0 = 32), the finer work units of a sharded rank's short band."""
     rng = np.random.default_rng(in_size * 7 + out_size)
     row = rng.integers(0, 256, in_size).astype(np.uint8)
     row[: in_size // 9] = 255  # saturated run: the negative lobes must clamp identically
     direct = np.zeros(out_size, np.uint8)
     replay = np.full(out_size, 7, np.uint8)
-    rc = _ffi.lib().sarpro_lanczos_row_plan_check(row.ctypes.data, in_size, out_size, max_span, direct.ctypes.data, replay.ctypes.data)
+    rc = _ffi.lib().sarpro_lanczos_row_plan_check(row.ctypes.data, in_size, out_size, max_span, strip_nt, direct.ctypes.data, replay.ctypes.data)
     assert rc in (0, 1)
     ref = O.resize_u8_image(np.tile(row, (1, 1)), out_size, 1) if hasattr(O, "resize_u8_image") else None
     if ref is not None:
@@ -156,3 +158,45 @@ def test_rust_sys_crate_matches_the_header():
     assert r.returncode == 0
     lib_rs = open(os.path.join(ROOT, "integration", "sarpro-gpu-sys", "src", "lib.rs")).read()
     assert set(re.findall(r"pub fn (sarpro_[a-z0-9_]+)\(", lib_rs)) == set(_ffi.SYMBOLS)
+
+
+@pytest.mark.parametrize("low,rng,n,vmin,vmax", [(-12.3, 21.7, 65535, 2e-3, 80.0), (-48.0, 47.5, 65535, 1.6e-5, 0.999), (3.1, 9.0, 255, 0.5, 40.0),
+                                                 (-30.0, 75.0, 4096, 1e-3, 3e4), (-0.7, 1.0, 65535, 0.7, 1.2), (10.0, 33.0, 4096, 10.0, 2e4)])
+def test_f32_guard_bound_holds_under_worst_case_log2_error(lib_built, low, rng, n, vmin, vmax):
+    """Host proof obligation of the general f32 kernels' shortcut (kernels_f32.cu f32_guarded_index): replaying the device's
+    fp32 operation sequence with the mantissa logarithm pushed to BOTH ends of MUFU.LG2's documented error (+-2^-22), every
+    sample the guard accepts gets the index the reference's f64 expression gives; and the guard accepts most samples."""
+    import ctypes as C
+    e0, f0, sc, gd = C.c_int(), C.c_float(), C.c_float(), C.c_float()
+    assert _ffi.lib().sarpro_f32_guard_params(low, rng, n, vmin, vmax, C.byref(e0), C.byref(f0), C.byref(sc), C.byref(gd)) == 0
+    g = np.float32(gd.value)
+    assert 0 < g < 0.45
+    r = np.random.default_rng(n + int(rng * 10))
+    v = np.exp(r.uniform(np.log(vmin), np.log(vmax), 400_000)).astype(np.float32)
+    # values sitting right at level boundaries as well
+    kk = r.integers(0, n + 1, 100_000)
+    vb = (10.0 ** ((low + rng * kk / n) / 10.0)).astype(np.float32)
+    vb = np.concatenate([vb, np.nextafter(vb, np.float32(0)), np.nextafter(vb, np.float32(np.inf))])
+    v = np.concatenate([v, vb[(vb >= vmin) & (vb <= vmax)]])
+    db = 10.0 * np.log10(v.astype(np.float64))
+    q = (np.clip(db, low, low + rng) - low) / rng * n
+    exact = np.where(q >= n, n, np.floor(np.clip(q, 0, None))).astype(np.int64)
+    bits = v.view(np.uint32)
+    e = (bits >> 23).astype(np.int32) - 127
+    m = ((bits & 0x7fffff) | 0x3f800000).view(np.float32)
+    accepted = 0
+    for delta in (-2.0 ** -22, 0.0, 2.0 ** -22):
+        lg = (np.log2(m.astype(np.float64)) + delta).astype(np.float32)
+        d = ((e - e0.value).astype(np.float32) + (lg - np.float32(f0.value)).astype(np.float32)).astype(np.float32)
+        t = (d * np.float32(sc.value)).astype(np.float32)
+        fl = np.floor(t)
+        fr = (t - fl).astype(np.float32)
+        idx = np.full(v.shape, -1, np.int64)
+        idx[t < -g] = 0
+        idx[t > np.float32(n) + g] = n
+        ok = (fr >= g) & (fr <= np.float32(1) - g) & (fl >= 0) & (fl < n) & (idx < 0)
+        idx[ok] = fl[ok].astype(np.int64)
+        dec = idx >= 0
+        assert np.array_equal(idx[dec], exact[dec]), int((idx[dec] != exact[dec]).sum())
+        accepted = int(dec[:400_000].sum())
+    assert accepted > 0.5 * 400_000
