@@ -245,6 +245,18 @@ int sarpro_pipeline_polops(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_b
 int sarpro_pipeline_single_sharded(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_band* b, size_t scene_rows, int op, int bit_depth,
                                    int strategy, sarpro_image* out, sarpro_stats* stats);
 
+/* ---- downsample-on-read (the reader's --size flow, sentinel1.rs:1074-1109 -> gdal.rs:145-177) ---------------------- */
+typedef enum sarpro_resample { SARPRO_RESAMPLE_AVERAGE = 0, SARPRO_RESAMPLE_LANCZOS = 1 } sarpro_resample;
+/* Output shape for a long-side target (aspect preserved, never enlarged) and the resampler the reader picks when the user
+ * gives none: Average for a reduction of 4 or more, Lanczos below (sentinel1.rs:1083-1102). Host only. */
+int sarpro_read_dims_for_target(size_t cols, size_t rows, size_t target, size_t* out_cols, size_t* out_rows, int* alg);
+/* GdalSarReader::read_band_resampled (gdal.rs:145-177): the raster (u16 DN as stored in the GRD TIFF, or f32) resampled to
+ * out_rows x out_cols f32 samples, host or device memory (out_location). The arithmetic is GDAL's RasterIO resampling, which
+ * lives in the system libgdal (version unpinned) and not in the reference tree: restated from the published algorithm of
+ * GDAL >= 3.3 - parity unpinned. */
+int sarpro_read_band_resampled(sarpro_ctx* ctx, const sarpro_band* in, size_t out_cols, size_t out_rows, int alg, float* out,
+                               int out_location);
+
 /* ---- batch (BASELINE config 5) ------------------------------------------------------------ */
 /* One scene of a batch: the band pair of one product. A scene whose b1.data is NULL (or that has no pixels) is counted as
  * skipped, like a product SafeReader::open_with_warnings_with_options returns None for (api/mod.rs:498-529). */

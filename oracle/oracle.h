@@ -129,6 +129,12 @@ int oracle_pipeline_synrgb_jpeg(const float* v1, const float* v2, size_t rows, s
  * the reference path is serial. 0/1 = serial. */
 void oracle_set_resize_threads(int n);
 
+/* ---- downsample-on-read (oracle_read.cpp; sentinel1.rs:1074-1109 -> gdal.rs:145-177). PARITY UNPINNED: restates the
+ * published resampling of the system libgdal (version unpinned, not on this box). alg: 0 = Average, 1 = Lanczos. */
+void oracle_read_dims_for_target(size_t cols, size_t rows, size_t target, size_t* out_cols, size_t* out_rows, int* alg);
+void oracle_read_band_resampled_u16(const uint16_t* src, size_t rows, size_t cols, size_t out_cols, size_t out_rows, int alg, float* out);
+void oracle_read_band_resampled_f32(const float* src, size_t rows, size_t cols, size_t out_cols, size_t out_rows, int alg, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,7 +49,7 @@ class ResizeMeta(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (building the checker is not using it)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_resize.cpp", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_resize.cpp", "oracle_read.cpp", "oracle.h", "Makefile")]
     if force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     ):
@@ -326,3 +326,26 @@ def pipeline_synrgb_jpeg(v1, v2, strategy, target, pad, mode=0, tamed_band_step=
 
 def set_resize_threads(n):
     lib().oracle_set_resize_threads(C.c_int(int(n)))
+
+
+RESAMPLE_AVERAGE, RESAMPLE_LANCZOS = 0, 1
+
+
+def read_dims_for_target(cols, rows, target):
+    """sentinel1.rs:1083-1102 -> (out_cols, out_rows, alg)."""
+    oc, orr, alg = C.c_size_t(), C.c_size_t(), C.c_int()
+    lib().oracle_read_dims_for_target(_sz(cols), _sz(rows), _sz(target), C.byref(oc), C.byref(orr), C.byref(alg))
+    return oc.value, orr.value, alg.value
+
+
+def read_band_resampled(src, out_cols, out_rows, alg):
+    """gdal.rs:145-177 (restated GDAL RasterIO resampling, parity unpinned): u16 or f32 raster -> f32 (out_rows, out_cols)."""
+    rows, cols = src.shape
+    out = np.empty((out_rows, out_cols), np.float32)
+    if src.dtype == np.uint16:
+        s = _c(src, np.uint16)
+        lib().oracle_read_band_resampled_u16(_p(s), _sz(rows), _sz(cols), _sz(out_cols), _sz(out_rows), C.c_int(alg), _p(out))
+    else:
+        s = _c(src, np.float32)
+        lib().oracle_read_band_resampled_f32(_p(s), _sz(rows), _sz(cols), _sz(out_cols), _sz(out_rows), C.c_int(alg), _p(out))
+    return out

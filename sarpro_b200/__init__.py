@@ -5,7 +5,7 @@ is the ctypes binding plus a host-side mirror of the reference's function names.
 pure-Python path: importing works anywhere, using it needs the built library and a B200.
 """
 from . import _ffi
-from ._ffi import (ADAPTIVE, BATCH_MULTIBAND, BATCH_SYNRGB, CLAHE, DEFAULT, EQUALIZED, JPEG, OP_DIFF, OP_LOGRATIO, OP_NDIFF, OP_NONE, OP_RATIO,
+from ._ffi import (ADAPTIVE, BATCH_MULTIBAND, BATCH_SYNRGB, RESAMPLE_AVERAGE, RESAMPLE_LANCZOS, CLAHE, DEFAULT, EQUALIZED, JPEG, OP_DIFF, OP_LOGRATIO, OP_NDIFF, OP_NONE, OP_RATIO,
                    OP_SUM, ROBUST, STANDARD, STRATEGY_NAMES, TAMED, TIFF, U8, U16)
 import os as _os
 
@@ -35,5 +35,5 @@ __all__ = [
     "Context", "ProcessedImage", "SarproError", "plan_from_dn_histogram", "plan_kind_from_dn_histogram", "plan_from_present_list", "present_list_from_histogram", "shard_rows", "shard_halo_rows",
     "comm_unique_id", "_ffi",
     "STANDARD", "ROBUST", "ADAPTIVE", "EQUALIZED", "CLAHE", "TAMED", "DEFAULT", "STRATEGY_NAMES",
-    "U8", "U16", "TIFF", "JPEG", "BATCH_MULTIBAND", "BATCH_SYNRGB", "OP_NONE", "OP_SUM", "OP_DIFF", "OP_RATIO", "OP_NDIFF", "OP_LOGRATIO",
+    "U8", "U16", "TIFF", "JPEG", "BATCH_MULTIBAND", "BATCH_SYNRGB", "RESAMPLE_AVERAGE", "RESAMPLE_LANCZOS", "OP_NONE", "OP_SUM", "OP_DIFF", "OP_RATIO", "OP_NDIFF", "OP_LOGRATIO",
 ]

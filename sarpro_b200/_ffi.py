@@ -74,6 +74,7 @@ class BatchReport(C.Structure):
 
 
 BATCH_MULTIBAND, BATCH_SYNRGB = 0, 1
+RESAMPLE_AVERAGE, RESAMPLE_LANCZOS = 0, 1
 
 
 class Timing(C.Structure):
@@ -125,6 +126,8 @@ SYMBOLS = {
     "sarpro_pipeline_synrgb_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, _SZ, _I, _I, C.POINTER(Image)]),
     "sarpro_pipeline_polops": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, C.POINTER(C.c_int), _I, _I, C.POINTER(Image), C.POINTER(Stats)]),
     "sarpro_pipeline_single_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, C.POINTER(Image), C.POINTER(Stats)]),
+    "sarpro_read_dims_for_target": (_I, [_SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ), C.POINTER(C.c_int)]),
+    "sarpro_read_band_resampled": (_I, [_P, C.POINTER(Band), _SZ, _SZ, _I, _P, _I]),
     "sarpro_pipeline_batch": (_I, [_P, C.POINTER(Scene), _SZ, _I, _I, _I, _I, _I, _SZ, _I, _I, _I, C.POINTER(Image), C.POINTER(Stats),
                                    C.POINTER(C.c_int), C.POINTER(BatchReport)]),
     "sarpro_plan_from_dn_histogram": (_I, [_P, _I, _I, C.POINTER(Stats), _P]),

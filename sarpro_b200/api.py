@@ -352,6 +352,26 @@ class Context:
         del kb
         return keep, [st[o] for o in range(n)]
 
+    @staticmethod
+    def read_dims_for_target(cols, rows, target):
+        """sentinel1.rs:1083-1102 -> (out_cols, out_rows, resampler)."""
+        oc, orr, alg = C.c_size_t(), C.c_size_t(), C.c_int()
+        rc = F.lib().sarpro_read_dims_for_target(cols, rows, target, C.byref(oc), C.byref(orr), C.byref(alg))
+        if rc != F.OK:
+            raise SarproError(rc, "sarpro_read_dims_for_target: invalid argument")
+        return oc.value, orr.value, alg.value
+
+    def read_band_resampled(self, band, out_cols, out_rows, alg, out=None):
+        """GdalSarReader::read_band_resampled (gdal.rs:145-177) on the GPU: u16 / f32 raster (numpy or torch CUDA tensor) ->
+        f32 (out_rows, out_cols); `out` may be a torch CUDA f32 tensor (stays on the device for the pipelines)."""
+        b, keep = self._band(band)
+        if out is None:
+            out = np.empty((out_rows, out_cols), np.float32)
+        loc = F.LOC_DEVICE if _is_torch(out) else F.LOC_HOST
+        self._check(self._lib.sarpro_read_band_resampled(self._h, C.byref(b), out_cols, out_rows, alg, _ptr(out), loc))
+        del keep
+        return out
+
     def process_batch(self, scenes, kind, bit_depth, strategy, target_size=None, pad=False, mode=F.SYNRGB_DEFAULT,
                       tamed_band_step=True, continue_on_error=True, outs=None):
         """process_directory_to_path's scene loop (api/mod.rs:474-536) over decoded band pairs: `scenes` is a list of

@@ -254,6 +254,25 @@ cudaError_t launch_pol_op(const float* a, const float* b, int op, uint64_t n, fl
 // general f32 path (kernels_f32.cu; launchers declared in api_f32.cu): min/max/count over valid samples.
 // valid <=> v >= valid_thresh (the smallest f32 with dB > -50); valid samples are positive, so the bit
 // pattern orders like the value.
+// ---- downsample-on-read (kernels_read.cu; tables from plan_read.cpp) ----
+// Average: output index d covers source [start[d], end[d]) with the first / last sample weighted by its covered fraction
+struct ReadAvgAxis {
+    const int* start;
+    const int* end;
+    const double* w_first;
+    const double* w_last;
+};
+// Lanczos: output index d = sum_k src[start[d] + k] * w[d * window + k], k < count[d]
+struct ReadConvAxis {
+    const int* start;
+    const int* count;
+    const double* w;
+    int window;
+};
+cudaError_t launch_read_average(const void* src, int src_u16, uint32_t rows, uint32_t cols, const ReadAvgAxis& ax, const ReadAvgAxis& ay,
+                                float* out, uint32_t out_rows, uint32_t out_cols, cudaStream_t stream);
+cudaError_t launch_read_lanczos(const void* src, int src_u16, uint32_t rows, uint32_t cols, const ReadConvAxis& ax, const ReadConvAxis& ay,
+                                double* tmp, float* out, uint32_t out_rows, uint32_t out_cols, cudaStream_t stream);
 // Parameters of the guarded direct index of the general f32 path (kernels_f32.cu f32_guarded_index; built by f32_guard in
 // plan_f32.cpp). guard >= 0.5: the shortcut is off and every sample takes the threshold comparison.
 struct F32GuardHost {

@@ -120,6 +120,20 @@ float valid_threshold();
 // edges[k] (k = 1..4095) = smallest f32 v in [min_v, max_v] whose stat-histogram index (autoscale.rs:113-116)
 // is >= k; +inf when no sample value reaches k. edges has 4096 entries, edges[0] = 0.
 void build_stat_edges(float min_v, float max_v, std::vector<float>* edges);
+// ---- downsample-on-read (plan_read.cpp) ----
+void read_dims_for_target(uint64_t cols, uint64_t rows, uint64_t target, uint64_t* out_cols, uint64_t* out_rows, int* alg);
+struct ReadAverageAxisHost {
+    std::vector<int> start, end;
+    std::vector<double> w_first, w_last;
+};
+struct ReadLanczosAxisHost {
+    std::vector<int> start, count;
+    std::vector<double> w;
+    int window = 0;
+};
+void build_read_average_axis(uint64_t in, uint64_t out, ReadAverageAxisHost* a);
+void build_read_lanczos_axis(uint64_t in, uint64_t out, ReadLanczosAxisHost* a);
+
 enum class LevelKind { Quantize, TamedLinearU8, ClaheBin };
 // Parameters and error bound of the device's direct fp32 evaluation of a linear-in-dB index
 //   index(v) = trunc((dB(v) - low_db) / range_db * n)        (stat bins: n = 4096; quantised levels with gamma == 1)

@@ -528,3 +528,52 @@ def test_pipeline_batch_matches_single_calls_and_oracle(ctx, kind):
     # an empty batch is a no-op
     _, _, rep0, _ = ctx.process_batch([], kind, S.U8, S.ROBUST, 256, True)
     assert (rep0.processed, rep0.skipped, rep0.errors) == (0, 0, 0)
+
+
+# ---- downsample-on-read (f2) ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,out", [((1600, 2500), (205, 131)), ((1311, 2048), (512, 328)), ((999, 1777), (100, 57)),
+                                       ((64, 40000), (2048, 4)), ((700, 900), (900, 700)), ((3000, 180), (12, 200))])
+@pytest.mark.parametrize("alg", [S.RESAMPLE_AVERAGE, S.RESAMPLE_LANCZOS])
+def test_read_band_resampled_matches_oracle(ctx, shape, out, alg):
+    """sarpro_read_band_resampled (gdal.rs:145-177) against the oracle's restatement of GDAL's RasterIO resampling: every f32
+    sample bit-identical (f64 accumulation in the same order on both sides), u16 DN and f32 sources, host and device buffers,
+    reductions from 1 (identity shape) to 20, spans wider than the staged segment (64 x 40000 -> 2048 columns is 19.5 per
+    output pixel; 3000 x 180 -> 12 columns falls back to direct loads)."""
+    import torch
+    rows, cols = shape
+    oc, orr = out
+    if alg == S.RESAMPLE_LANCZOS and (cols / oc > 6 or rows / orr > 6):
+        pytest.skip("the reader only picks Lanczos below a reduction of 4")
+    dn = CASES["speckle"](rows, cols)
+    ref = O.read_band_resampled(dn, oc, orr, alg)
+    got = ctx.read_band_resampled(dn, oc, orr, alg)
+    assert got.dtype == np.float32 and got.shape == (orr, oc)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), int((got != ref).sum())
+    f = (dn.astype(np.float32) * np.float32(0.37)).astype(np.float32)
+    ref_f = O.read_band_resampled(f, oc, orr, alg)
+    dev_in = torch.from_numpy(f).cuda()
+    dev_out = torch.empty((orr, oc), dtype=torch.float32, device="cuda")
+    ctx.read_band_resampled(dev_in, oc, orr, alg, out=dev_out)
+    assert np.array_equal(dev_out.cpu().numpy().view(np.uint32), ref_f.view(np.uint32))
+
+
+def test_read_then_pipeline_is_the_cli_size_flow(ctx):
+    """The flow the CLI takes with --size (sentinel1.rs:1074-1109 then save.rs:317-368): both bands averaged down on read, the
+    f32 rasters (left on the device) through the synRGB pipeline at the same target. Equals the oracle's chain byte for byte."""
+    import torch
+    from sarpro_b200.synth import synth_pair
+    vv, vh = synth_pair(3000, 4700)
+    oc, orr, alg = S.Context.read_dims_for_target(4700, 3000, 512)
+    assert (oc, orr, alg) == O.read_dims_for_target(4700, 3000, 512)
+    small = []
+    for band in (vv, vh):
+        t = torch.empty((orr, oc), dtype=torch.float32, device="cuda")
+        ctx.read_band_resampled(band, oc, orr, alg, out=t)
+        small.append(t)
+    img = ctx.process_synrgb_jpeg(small[0], small[1], S.CLAHE, 512, True)
+    r1 = O.read_band_resampled(vv, oc, orr, alg)
+    r2 = O.read_band_resampled(vh, oc, orr, alg)
+    ref, _ = O.pipeline_synrgb_jpeg(r1, r2, S.CLAHE, 512, True)
+    assert np.array_equal(img.rgb, ref), int((img.rgb != ref).sum())
+    with pytest.raises(S.SarproError):
+        ctx.read_band_resampled(vv, 5000, 3000, S.RESAMPLE_AVERAGE)  # never enlarges

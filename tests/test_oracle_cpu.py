@@ -219,3 +219,46 @@ def test_golden_wide_scene():
     g, vv, vh = _wide_scene()
     rgb, _ = O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), O.CLAHE, 256, True)
     assert np.array_equal(rgb, g["synrgb_clahe"])
+
+
+# ---- downsample-on-read oracle (restated GDAL RasterIO resampling, parity unpinned) -------------------------------------
+def test_read_dims_for_target_matches_reader_arithmetic():
+    """sentinel1.rs:1083-1102: long side -> target, short side rounded, never enlarged; Average from a reduction of 4."""
+    assert O.read_dims_for_target(25000, 16000, 2048) == (2048, 1311, O.RESAMPLE_AVERAGE)
+    assert O.read_dims_for_target(16000, 25000, 2048) == (1311, 2048, O.RESAMPLE_AVERAGE)
+    assert O.read_dims_for_target(4096, 4096, 2048) == (2048, 2048, O.RESAMPLE_LANCZOS)   # reduction 2
+    assert O.read_dims_for_target(8192, 100, 2048) == (2048, 25, O.RESAMPLE_AVERAGE)     # reduction exactly 4
+    assert O.read_dims_for_target(1000, 800, 4000) == (1000, 800, O.RESAMPLE_LANCZOS)    # target above the long side: no upscale
+    assert O.read_dims_for_target(30000, 3, 100) == (100, 1, O.RESAMPLE_AVERAGE)         # short side at least 1
+
+
+def test_read_average_known_answers():
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 4000, (160, 240)).astype(np.uint16)
+    # integer reduction: plain block means (every weight is 1)
+    got = O.read_band_resampled(a, 24, 16, O.RESAMPLE_AVERAGE)
+    ref = a.reshape(16, 10, 24, 10).astype(np.float64).mean(axis=(1, 3)).astype(np.float32)
+    assert np.array_equal(got, ref)
+    # fractional reduction 2.5 along x, one row: pixel d covers [2.5 d, 2.5 d + 2.5)
+    row = np.arange(10, dtype=np.uint16)[None, :] * 100
+    got = O.read_band_resampled(row, 4, 1, O.RESAMPLE_AVERAGE)[0]
+    want = [(0 + 100 + 0.5 * 200) / 2.5, (0.5 * 200 + 300 + 400) / 2.5, (500 + 600 + 0.5 * 700) / 2.5, (0.5 * 700 + 800 + 900) / 2.5]
+    assert np.allclose(got, np.float32(want), rtol=0, atol=1e-4)
+    # a constant raster stays constant under both resamplers, u16 and f32 sources agree
+    c = np.full((333, 517), 1234, np.uint16)
+    for alg in (O.RESAMPLE_AVERAGE, O.RESAMPLE_LANCZOS):
+        for oc, orr in ((100, 64), (200, 129), (517, 333)):
+            r16 = O.read_band_resampled(c, oc, orr, alg)
+            assert np.allclose(r16, 1234.0, rtol=1e-6), (alg, oc, orr)
+            assert np.array_equal(r16, O.read_band_resampled(c.astype(np.float32), oc, orr, alg))
+
+
+def test_read_lanczos_is_a_normalised_low_pass():
+    rng = np.random.default_rng(4)
+    a = rng.gamma(4.0, 50.0, (300, 420)).astype(np.float32)
+    out = O.read_band_resampled(a, 210, 150, O.RESAMPLE_LANCZOS)       # reduction 2
+    assert out.shape == (150, 210)
+    assert abs(float(out.mean()) - float(a.mean())) < 0.01 * float(a.mean())
+    assert float(out.std()) < float(a.std())
+    ident = O.read_band_resampled(a, 420, 300, O.RESAMPLE_LANCZOS)     # same shape: the kernel collapses to the sample itself
+    assert np.allclose(ident, a, rtol=1e-5, atol=1e-3)
