@@ -58,7 +58,11 @@ typedef enum sarpro_synrgb_mode {
 typedef enum sarpro_output_format { SARPRO_FORMAT_TIFF = 0, SARPRO_FORMAT_JPEG = 1 } sarpro_output_format;
 
 typedef enum sarpro_dtype { SARPRO_DT_F32 = 0, SARPRO_DT_U16 = 1 } sarpro_dtype;
-typedef enum sarpro_location { SARPRO_LOC_HOST = 0, SARPRO_LOC_DEVICE = 1 } sarpro_location;
+typedef enum sarpro_location {
+    SARPRO_LOC_HOST = 0,
+    SARPRO_LOC_DEVICE = 1,
+    SARPRO_LOC_NONE = 2 /* outputs only: nothing is copied out, the result stays in the context (see sarpro_encode_last_jpeg) */
+} sarpro_location;
 
 typedef enum sarpro_status {
     SARPRO_OK = 0,
@@ -256,6 +260,18 @@ int sarpro_read_dims_for_target(size_t cols, size_t rows, size_t target, size_t*
  * GDAL >= 3.3 - parity unpinned. */
 int sarpro_read_band_resampled(sarpro_ctx* ctx, const sarpro_band* in, size_t out_cols, size_t out_rows, int alg, float* out,
                                int out_location);
+
+/* ---- encoder hand-off (writers) ---------------------------------------------------------------------------------------- */
+/* write_gray_jpeg / write_rgb_jpeg (io/writers/jpeg.rs:6-30; jpeg_encoder at quality 100: baseline, 4:4:4) on the GPU (nvJPEG,
+ * loaded at run time): a u8 gray (channels 1) or interleaved RGB (channels 3) image in host or device memory -> a complete JPEG
+ * stream in `out` (host memory). out == NULL: only *out_bytes (the stream length) is returned. The stream is a valid baseline
+ * JPEG of the same pixels, not the byte sequence jpeg_encoder would write. */
+int sarpro_encode_jpeg(sarpro_ctx* ctx, const sarpro_image* img, int quality, void* out, size_t capacity, size_t* out_bytes);
+/* The same for the u8 result the LAST pipeline call on this context left on the device: which = 0 the interleaved RGB of
+ * sarpro_pipeline_synrgb, 1 / 2 the gray band(s) of sarpro_pipeline_single / _multiband_tiff / _synrgb. With an output image of
+ * location SARPRO_LOC_NONE in the pipeline call, the raw pixels never cross PCIe: only the JPEG stream does. For the GeoTIFF
+ * writers (io/writers/tiff.rs:6-78) the hand-off is a pinned output buffer (sarpro_host_alloc) the raster is delivered into. */
+int sarpro_encode_last_jpeg(sarpro_ctx* ctx, int which, int quality, void* out, size_t capacity, size_t* out_bytes);
 
 /* ---- batch (BASELINE config 5) ------------------------------------------------------------ */
 /* One scene of a batch: the band pair of one product. A scene whose b1.data is NULL (or that has no pixels) is counted as

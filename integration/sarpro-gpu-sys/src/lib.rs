@@ -148,6 +148,8 @@ extern "C" {
     pub fn sarpro_pipeline_single_sharded(ctx: *mut sarpro_ctx, a: *const sarpro_band, b: *const sarpro_band, scene_rows: usize, op: c_int, bit_depth: c_int, strategy: c_int, out: *mut sarpro_image, stats: *mut sarpro_stats) -> c_int;
     pub fn sarpro_read_dims_for_target(cols: usize, rows: usize, target: usize, out_cols: *mut usize, out_rows: *mut usize, alg: *mut c_int) -> c_int;
     pub fn sarpro_read_band_resampled(ctx: *mut sarpro_ctx, in_: *const sarpro_band, out_cols: usize, out_rows: usize, alg: c_int, out: *mut f32, out_location: c_int) -> c_int;
+    pub fn sarpro_encode_jpeg(ctx: *mut sarpro_ctx, img: *const sarpro_image, quality: c_int, out: *mut c_void, capacity: usize, out_bytes: *mut usize) -> c_int;
+    pub fn sarpro_encode_last_jpeg(ctx: *mut sarpro_ctx, which: c_int, quality: c_int, out: *mut c_void, capacity: usize, out_bytes: *mut usize) -> c_int;
     pub fn sarpro_pipeline_batch(ctx: *mut sarpro_ctx, scenes: *const sarpro_scene, n: usize, kind: c_int, bit_depth: c_int, strategy: c_int, mode: c_int, has_target: c_int, target: usize, pad: c_int, tamed_band_step: c_int, continue_on_error: c_int, outs: *mut sarpro_image, stats: *mut sarpro_stats, statuses: *mut c_int, report: *mut sarpro_batch_report) -> c_int;
     pub fn sarpro_plan_from_dn_histogram(hist65536: *const u64, bit_depth: c_int, strategy: c_int, stats: *mut sarpro_stats, lut16: *mut u16) -> c_int;
     pub fn sarpro_plan_from_present_list(blocks: *const u32, pairs: *const u32, cap: u32, bit_depth: c_int, strategy: c_int, stats: *mut sarpro_stats, lut16: *mut u16) -> c_int;

@@ -20,7 +20,7 @@ U8, U16 = 0, 1
 OP_NONE, OP_SUM, OP_DIFF, OP_RATIO, OP_NDIFF, OP_LOGRATIO = -1, 0, 1, 2, 3, 4
 TIFF, JPEG = 0, 1
 DT_F32, DT_U16 = 0, 1
-LOC_HOST, LOC_DEVICE = 0, 1
+LOC_HOST, LOC_DEVICE, LOC_NONE = 0, 1, 2
 SYNRGB_DEFAULT, SYNRGB_RGB_RATIO, SYNRGB_SAR_URBAN, SYNRGB_ENHANCED = range(4)
 
 OK = 0
@@ -128,6 +128,8 @@ SYMBOLS = {
     "sarpro_pipeline_single_sharded": (_I, [_P, C.POINTER(Band), C.POINTER(Band), _SZ, _I, _I, _I, C.POINTER(Image), C.POINTER(Stats)]),
     "sarpro_read_dims_for_target": (_I, [_SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ), C.POINTER(C.c_int)]),
     "sarpro_read_band_resampled": (_I, [_P, C.POINTER(Band), _SZ, _SZ, _I, _P, _I]),
+    "sarpro_encode_jpeg": (_I, [_P, C.POINTER(Image), _I, _P, _SZ, C.POINTER(_SZ)]),
+    "sarpro_encode_last_jpeg": (_I, [_P, _I, _I, _P, _SZ, C.POINTER(_SZ)]),
     "sarpro_pipeline_batch": (_I, [_P, C.POINTER(Scene), _SZ, _I, _I, _I, _I, _I, _SZ, _I, _I, _I, C.POINTER(Image), C.POINTER(Stats),
                                    C.POINTER(C.c_int), C.POINTER(BatchReport)]),
     "sarpro_plan_from_dn_histogram": (_I, [_P, _I, _I, C.POINTER(Stats), _P]),

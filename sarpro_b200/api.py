@@ -134,9 +134,13 @@ class Context:
                                           C.byref(oc), C.byref(orr))
         return oc.value, orr.value
 
+    KEEP = "keep"  # as `out=`: the result stays in the context's device buffers (F.LOC_NONE), for encode_last_jpeg
+
     def _image(self, cols, rows, channels, bit_depth, out=None):
         dt = np.uint8 if bit_depth == U8 else np.uint16
         shape = (rows, cols) if channels == 1 else (rows, cols, channels)
+        if isinstance(out, str) and out == Context.KEEP:
+            return F.Image(None, F.LOC_NONE, bit_depth, 0, 0, 0, 0, 0, F.ResizeMeta()), None
         if out is None:
             out = np.empty(shape, dt)
             img = F.Image(out.ctypes.data, F.LOC_HOST, bit_depth, out.nbytes, 0, 0, 0, 0, F.ResizeMeta())
@@ -351,6 +355,33 @@ class Context:
                                                      imgs, st))
         del kb
         return keep, [st[o] for o in range(n)]
+
+    def encode_jpeg(self, image, quality=100):
+        """write_gray_jpeg / write_rgb_jpeg (io/writers/jpeg.rs:6-30) without the file: u8 (rows, cols) or (rows, cols, 3) array
+        (numpy or torch CUDA) -> bytes of a baseline JPEG stream (nvJPEG on the GPU)."""
+        if _is_torch(image):
+            shape, loc, keep = tuple(image.shape), F.LOC_DEVICE, image
+        else:
+            keep = np.ascontiguousarray(image, dtype=np.uint8)
+            shape, loc = keep.shape, F.LOC_HOST
+        ch = 1 if len(shape) == 2 else shape[2]
+        img = F.Image(_ptr(keep), loc, U8, shape[0] * shape[1] * ch, shape[1], shape[0], ch, 0, F.ResizeMeta())
+        n = C.c_size_t()
+        self._check(self._lib.sarpro_encode_jpeg(self._h, C.byref(img), quality, None, 0, C.byref(n)))
+        buf = (C.c_ubyte * n.value)()
+        self._check(self._lib.sarpro_encode_jpeg(self._h, C.byref(img), quality, buf, n.value, C.byref(n)))
+        return bytes(buf[: n.value])
+
+    def encode_last_jpeg(self, which=0, quality=100, capacity=None):
+        """JPEG of the u8 result the last pipeline call left on the device (0 = RGB, 1 / 2 = gray bands): only the stream
+        crosses PCIe. capacity: size of the receiving buffer (default: queried first)."""
+        n = C.c_size_t()
+        if capacity is None:
+            self._check(self._lib.sarpro_encode_last_jpeg(self._h, which, quality, None, 0, C.byref(n)))
+            capacity = n.value
+        buf = (C.c_ubyte * capacity)()
+        self._check(self._lib.sarpro_encode_last_jpeg(self._h, which, quality, buf, capacity, C.byref(n)))
+        return bytes(buf[: n.value])
 
     @staticmethod
     def read_dims_for_target(cols, rows, target):

@@ -137,10 +137,17 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
         ctx->n_tiles = kClaheTiles * kClaheTiles;
     }
     ctx->n_units = (uint32_t)units.size();
+    ctx->units_r1.clear();
     if (!units.empty()) {
         RC(reserve(ctx, ctx->units, units.size() * sizeof(HistUnit)));
         CU(cudaMemcpyAsync(ctx->units.p, units.data(), units.size() * sizeof(HistUnit), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream)); // `units` is a pageable temporary
+        // the same units ordered by their last row, for rasters that arrive in row chunks (streamed uploads)
+        std::vector<HistUnit> by_row(units);
+        std::stable_sort(by_row.begin(), by_row.end(), [](const HistUnit& x, const HistUnit& y) { return x.r1 < y.r1; });
+        RC(reserve(ctx, ctx->units_by_row, by_row.size() * sizeof(HistUnit)));
+        CU(cudaMemcpyAsync(ctx->units_by_row.p, by_row.data(), by_row.size() * sizeof(HistUnit), cudaMemcpyHostToDevice, ctx->stream));
+        for (const HistUnit& u : by_row) ctx->units_r1.push_back(u.r1);
+        CU(cudaStreamSynchronize(ctx->stream)); // `units` / `by_row` are pageable temporaries
     }
     if (clahe) {
         const ClaheGeom g = clahe_geometry(scene_rows, cols);
@@ -448,10 +455,25 @@ int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_
     }
     if (phase == 1) return 0;
     // (persistent CTAs pulling work units: any grid works; ctx->pair_spare SMs are left to the other band's small kernels)
-    KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p,
-                                         std::max(1, ctx->sm_count - (b == 1 ? ctx->pair_spare : 0)),
-                                         ctx->hist_variant >= 0 ? ctx->hist_variant : w.hist_auto, ctx->stream,
-                                         (uint32_t*)w.scalars.p + 4));
+    const int grid_sms = std::max(1, ctx->sm_count - (b == 1 ? ctx->pair_spare : 0));
+    const int variant = ctx->hist_variant >= 0 ? ctx->hist_variant : w.hist_auto;
+    const sarpro_ctx::StreamedBand& sb = ctx->streamed[b < 2 ? b : 0];
+    if (b < 2 && sb.n_chunks > 0 && ctx->units_r1.size() == ctx->n_units) {
+        // the raster is still arriving (stage_band): one launch per uploaded chunk over the units that end inside it
+        uint32_t done = 0;
+        for (int c = 0; c < sb.n_chunks; ++c) {
+            const uint32_t upto = (uint32_t)(std::upper_bound(ctx->units_r1.begin(), ctx->units_r1.end(), sb.row_end[c]) - ctx->units_r1.begin());
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[sb.ev0 + c], 0));
+            if (upto == done) continue;
+            if (done) CU(cudaMemsetAsync((uint32_t*)w.scalars.p + 4, 0, 4, ctx->stream)); // the kernels' work-unit counter
+            KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units_by_row.p + done, upto - done, (uint32_t*)w.tile_hist.p,
+                                                 grid_sms, variant, ctx->stream, (uint32_t*)w.scalars.p + 4));
+            done = upto;
+        }
+    } else {
+        KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p, grid_sms, variant,
+                                             ctx->stream, (uint32_t*)w.scalars.p + 4));
+    }
     KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
                                             (uint32_t*)w.scalars.p + 2, (uint32_t*)w.scalars.p + 5, (uint2*)w.present.p, kPresentCap,
                                             ctx->stream));
@@ -825,9 +847,29 @@ int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band*
     if (in->dtype == SARPRO_DT_U16 && op < 0) {
         if (in->location == SARPRO_LOC_DEVICE) { *dn_out = (const uint16_t*)in->data; return 0; }
         RC(reserve(ctx, w.dn, n * 2));
-        CU(cudaMemcpyAsync(w.dn.p, in->data, n * 2, cudaMemcpyHostToDevice, ctx->stream));
         ctx->timing.h2d_bytes += n * 2;
         *dn_out = (const uint16_t*)w.dn.p;
+        if (ctx->stream_upload && b < 2 && n * 2 >= (64u << 20) && in->rows >= 1024) {
+            // Streamed upload: row chunks on the copy stream, an event per chunk. Pass A consumes the chunks as they land and
+            // the other band's plan / pass B run beside this band's upload (PCIe is the bottleneck of a call with host
+            // rasters: 29 of 31 ms at C3). The previous call on this context ended with its streams drained, so nothing still
+            // reads the staging buffer.
+            RC(ensure_upload_stream(ctx));
+            sarpro_ctx::StreamedBand& sb = ctx->streamed[b];
+            const uint64_t per = ((in->rows + sarpro_ctx::kUploadChunks - 1) / sarpro_ctx::kUploadChunks + 127) & ~uint64_t(127);
+            sb.n_chunks = 0;
+            sb.ev0 = b * sarpro_ctx::kUploadChunks;
+            ctx->upload_in_flight = true;
+            for (uint64_t r = 0; r < in->rows; r += per) {
+                const uint64_t r1 = std::min<uint64_t>(in->rows, r + per);
+                CU(cudaMemcpyAsync((char*)w.dn.p + r * in->cols * 2, (const char*)in->data + r * in->cols * 2, (r1 - r) * in->cols * 2,
+                                   cudaMemcpyHostToDevice, ctx->stream_up));
+                CU(cudaEventRecord(ctx->ev_chunk[sb.ev0 + sb.n_chunks], ctx->stream_up));
+                sb.row_end[sb.n_chunks++] = (uint32_t)r1;
+            }
+            return 0;
+        }
+        CU(cudaMemcpyAsync(w.dn.p, in->data, n * 2, cudaMemcpyHostToDevice, ctx->stream));
         return 0;
     }
     if (op >= 0 && in->dtype == SARPRO_DT_U16 && in2->dtype == SARPRO_DT_U16) {
@@ -905,6 +947,10 @@ int begin_call(sarpro_ctx* ctx) {
     if (ctx->axes.size() > 64) drop_axis_plans(ctx); // bounded cache; no plan pointer is held across calls
     std::memset(&ctx->timing, 0, sizeof(ctx->timing));
     ctx->pending_stats[0] = ctx->pending_stats[1] = nullptr;
+    ctx->streamed[0].n_chunks = ctx->streamed[1].n_chunks = 0;
+    if (ctx->upload_in_flight && ctx->stream_up) { cudaStreamSynchronize(ctx->stream_up); ctx->upload_in_flight = false; }
+    if (!ctx->keep_last)
+        for (auto& l : ctx->last) l = sarpro_ctx::LastResult{}; // the buffers are about to be reused
     ctx->band[0].plan_copy_pending = ctx->band[1].plan_copy_pending = false;
     ctx->n_sev = 0;
     ctx->host_t0 = host_ms();
@@ -914,6 +960,7 @@ int begin_call(sarpro_ctx* ctx) {
 int end_call(sarpro_ctx* ctx) {
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->upload_in_flight = false; // every chunk event was waited for by the work that just completed
     for (int b = 0; b < 2; ++b) {
         BandWs& w = ctx->band[b];
         if (w.plan_copy_pending) { // device-planned: the plan's host mirror is valid now
@@ -964,6 +1011,7 @@ int end_call(sarpro_ctx* ctx) {
 }
 
 int deliver(sarpro_ctx* ctx, const void* dev_src, size_t bytes, sarpro_image* out) {
+    if (out->location == SARPRO_LOC_NONE) return 0; // the result stays in the context (sarpro_encode_last_jpeg)
     if (!out->data && bytes) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "output buffer is NULL");
     if (out->capacity_bytes < bytes)
         return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "output buffer holds %llu bytes, %llu needed",
@@ -1033,9 +1081,9 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
     } else {
         for (int k = 0; k < ndn; ++k) {
             // mixed case: plan band by band in its own slot
-            if (dnidx[k] != 0) std::swap(ctx->band[0], ctx->band[dnidx[k]]);
+            if (dnidx[k] != 0) { std::swap(ctx->band[0], ctx->band[dnidx[k]]); std::swap(ctx->streamed[0], ctx->streamed[dnidx[k]]); }
             int rc = run_pass_a_and_plan(ctx, &dnjobs[k], 1);
-            if (dnidx[k] != 0) std::swap(ctx->band[0], ctx->band[dnidx[k]]);
+            if (dnidx[k] != 0) { std::swap(ctx->band[0], ctx->band[dnidx[k]]); std::swap(ctx->streamed[0], ctx->streamed[dnidx[k]]); }
             RC(rc);
         }
     }
@@ -1145,6 +1193,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if ((e = cudaMemcpy(ctx->db_table.p, dn_db_table(), kDnBins * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
     if (const char* v = getenv("SARPRO_HOST_PLAN")) ctx->host_plan = atoi(v);
     if (const char* v = getenv("SARPRO_F32_NO_GUARD")) ctx->f32_no_guard = atoi(v);
+    if (const char* v = getenv("SARPRO_STREAM_UPLOAD")) ctx->stream_upload = atoi(v);
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     if (const char* v = getenv("SARPRO_HMMA")) ctx->use_hmma = atoi(v);
@@ -1167,6 +1216,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     sarpro_comm_destroy(ctx); // NCCL communicator + CommState
+    jpeg_state_destroy(ctx);
     for (auto& w : ctx->band)
         for (DevBuf* b : {&w.dn, &w.f32a, &w.f32b, &w.tile_hist, &w.total, &w.lut, &w.tile256, &w.cdf, &w.cdf32, &w.remap,
                           &w.temp, &w.small, &w.full, &w.scalars, &w.present, &w.edges, &w.hist4096, &w.f32scan, &w.pieces,
@@ -1178,6 +1228,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     for (auto& slot : ctx->batch_stage)
         for (DevBuf& b : slot) release(b);
     release(ctx->gather);
+    release(ctx->units_by_row);
     if (ctx->stream_up) { cudaStreamSynchronize(ctx->stream_up); cudaStreamDestroy(ctx->stream_up); }
     for (auto& ev : ctx->ev_up)
         if (ev) cudaEventDestroy(ev);
@@ -1338,6 +1389,7 @@ int sarpro_pipeline_single(sarpro_ctx* ctx, const sarpro_band* a, const sarpro_b
     RC(produce_bands(ctx, ins, ins2, ops, 1, strategies, depths, kinds, has_target != 0, target, pad != 0, canvas, &g, stats));
     fill_image(out, g, 1, bit_depth);
     RC(deliver(ctx, canvas[0], g.oc * g.orr * (bit_depth == SARPRO_U8 ? 1 : 2), out));
+    if (bit_depth == SARPRO_U8) ctx->last[1] = sarpro_ctx::LastResult{canvas[0], g.oc, g.orr};
     return end_call(ctx);
 }
 
@@ -1360,6 +1412,10 @@ int sarpro_pipeline_multiband_tiff(sarpro_ctx* ctx, const sarpro_band* b1, const
     fill_image(out2, g, 1, bit_depth);
     RC(deliver(ctx, canvas[0], bytes, out1));
     RC(deliver(ctx, canvas[1], bytes, out2));
+    if (bit_depth == SARPRO_U8) {
+        ctx->last[1] = sarpro_ctx::LastResult{canvas[0], g.oc, g.orr};
+        ctx->last[2] = sarpro_ctx::LastResult{canvas[1], g.oc, g.orr};
+    }
     return end_call(ctx);
 }
 
@@ -1386,6 +1442,9 @@ int sarpro_pipeline_synrgb(sarpro_ctx* ctx, const sarpro_band* b1, const sarpro_
     RC(synrgb_compose(ctx, strategy, (const uint8_t*)canvas[0], (const uint8_t*)canvas[1], n));
     fill_image(out, g, 3, SARPRO_U8);
     RC(deliver(ctx, ctx->rgb.p, n * 3, out));
+    ctx->last[0] = sarpro_ctx::LastResult{ctx->rgb.p, g.oc, g.orr};
+    ctx->last[1] = sarpro_ctx::LastResult{canvas[0], g.oc, g.orr};
+    ctx->last[2] = sarpro_ctx::LastResult{canvas[1], g.oc, g.orr};
     return end_call(ctx);
 }
 

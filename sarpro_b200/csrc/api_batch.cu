@@ -11,6 +11,8 @@ int ensure_upload_stream(sarpro_ctx* ctx) {
     if (!ctx->stream_up) CU(cudaStreamCreateWithFlags(&ctx->stream_up, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev_up)
         if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : ctx->ev_chunk)
+        if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     return 0;
 }
 

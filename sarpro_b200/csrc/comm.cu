@@ -523,6 +523,7 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
                                                    (unsigned char*)ctx->band[1].small.p, (uint32_t*)ctx->band[0].scalars.p,
                                                    (uint32_t*)ctx->band[1].scalars.p, nonident, ctx->stream));
         RC(synrgb_compose(ctx, strategy, (const uint8_t*)ctx->band[0].small.p, (const uint8_t*)ctx->band[1].small.p, n_out));
+        ctx->last[0] = sarpro_ctx::LastResult{ctx->rgb.p, g.oc, g.orr};
         if (out) {
             fill_image(out, g, 3, SARPRO_U8);
             if (out->data) RC(deliver(ctx, ctx->rgb.p, n_out * 3, out));

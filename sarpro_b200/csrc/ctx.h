@@ -103,6 +103,8 @@ struct OutGeom {
 OutGeom out_geometry(size_t cols, size_t rows, bool has_target, size_t target, bool pad);
 
 struct CommState; // comm.cu
+struct JpegState; // api_jpeg.cu
+void jpeg_state_destroy(sarpro_ctx* ctx);
 
 // One band through the DN passes
 struct BandJob {
@@ -176,8 +178,23 @@ struct sarpro_ctx {
     // batch / streamed uploads (api_batch.cu): a copy stream and two staging slots of a band pair, created on first use
     cudaStream_t stream_up = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr};  // upload of staging slot s complete
-    cudaEvent_t ev_chunk[16] = {};              // streamed single-scene upload: chunk c of a band has landed
+    cudaEvent_t ev_chunk[16] = {};              // streamed upload: chunk c of band b has landed (index b * kUploadChunks + c)
     sarpro::DevBuf batch_stage[2][2];           // [slot][band]
+    // streamed upload of a host u16 band: row chunks go out on the copy stream, pass A runs on each chunk as it
+    // lands (units ordered by their last row), and the first band's plan / pass B overlap the second band's upload
+    static constexpr int kUploadChunks = 8;
+    struct StreamedBand { int n_chunks = 0, ev0 = 0; uint32_t row_end[kUploadChunks] = {}; }; // ev0: first of its events in ev_chunk
+    StreamedBand streamed[2];
+    bool upload_in_flight = false;              // chunks were queued in a call that has not completed (error path): drain first
+    int stream_upload = 1;                      // SARPRO_STREAM_UPLOAD=0: one copy on the main stream (measurement)
+    sarpro::DevBuf units_by_row;                // the work units of pass A ordered by last row
+    std::vector<uint32_t> units_r1;             // their last rows (ascending), host copy
+    // u8 results of the last pipeline call that are still in the context's device buffers: [0] interleaved RGB, [1] / [2] the
+    // gray bands (sarpro_encode_last_jpeg encodes them where they lie). Cleared when a call that does not produce them begins.
+    struct LastResult { const void* dev = nullptr; size_t cols = 0, rows = 0; };
+    LastResult last[3];
+    bool keep_last = false; // set around calls that read `last` (begin_call clears it otherwise)
+    sarpro::JpegState* jpeg = nullptr;
     sarpro::DevBuf gather;                      // sharded scene: all-gathered output rows + extrema of every rank (comm.cu)
 };
 
@@ -192,6 +209,7 @@ uint32_t hmma_hot_from_plan(const BandPlan& plan, uint32_t* top_out);
 int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res, uint32_t strip_nt = 32);
 uint32_t choose_strip_nt(const sarpro_ctx* ctx, uint64_t rows, uint64_t out_cols, bool clahe);
 int begin_call(sarpro_ctx* ctx);
+int ensure_upload_stream(sarpro_ctx* ctx); // api_batch.cu
 // slot: the band slot whose piece lists the tensor-core kernel uses; *gate: see api.cu
 int run_hpass(sarpro_ctx* ctx, int slot, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah, uint64_t row_off, bool* gate);
 int run_hpass_generic(sarpro_ctx* ctx, const HResizeArgs& a, int src_kind, int pix16, AxisPlan* ah);

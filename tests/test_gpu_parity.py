@@ -577,3 +577,83 @@ def test_read_then_pipeline_is_the_cli_size_flow(ctx):
     assert np.array_equal(img.rgb, ref), int((img.rgb != ref).sum())
     with pytest.raises(S.SarproError):
         ctx.read_band_resampled(vv, 5000, 3000, S.RESAMPLE_AVERAGE)  # never enlarges
+
+
+# ---- encoder hand-off (f3) --------------------------------------------------------------------------------------------
+def _decode_jpeg(stream):
+    import io
+    from PIL import Image
+    im = Image.open(io.BytesIO(stream))
+    im.load()
+    return np.asarray(im), im
+
+
+def test_encode_jpeg_decodes_to_the_same_pixels(ctx):
+    """sarpro_encode_jpeg (io/writers/jpeg.rs:6-30 on the GPU): a baseline JPEG at quality 100 (all-ones quantisation tables,
+    4:4:4) must decode to the pixels that went in, within what two conforming q=100 codecs differ by: +-2 for gray (DCT
+    rounding), +-4 for RGB (YCbCr round trip on top). Host and device sources, odd sizes."""
+    import torch
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:517, 0:771]
+    gray = np.clip(128 + 90 * np.sin(xx / 37.0) * np.cos(yy / 23.0) + rng.normal(0, 12, xx.shape), 0, 255).astype(np.uint8)
+    dec, im = _decode_jpeg(ctx.encode_jpeg(gray, 100))
+    assert im.mode == "L" and dec.shape == gray.shape
+    assert int(np.abs(dec.astype(int) - gray.astype(int)).max()) <= 2
+    rgb = np.stack([gray, np.roll(gray, 40, 1), 255 - gray], axis=-1).copy()
+    for src in (rgb, torch.from_numpy(rgb).cuda()):
+        dec, im = _decode_jpeg(ctx.encode_jpeg(src, 100))
+        assert im.mode == "RGB" and dec.shape == rgb.shape
+        d = np.abs(dec.astype(int) - rgb.astype(int))
+        assert int(d.max()) <= 4 and float(d.mean()) < 0.8, (int(d.max()), float(d.mean()))
+    with pytest.raises(S.SarproError):
+        ctx.encode_jpeg(gray, 0)
+
+
+def test_pipeline_result_encoded_where_it_lies(ctx):
+    """The JPEG flow without the raw image crossing PCIe: sarpro_pipeline_synrgb with an output of location NONE, then
+    sarpro_encode_last_jpeg. The decoded stream equals the oracle's RGB within the codec tolerance; the gray bands likewise."""
+    vv = CASES["speckle"](900, 1400)
+    vh = CASES["speckle_vh"](900, 1400)
+    ref, _ = O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), S.CLAHE, 512, True)
+    img = ctx.process_synrgb_jpeg(vv, vh, S.CLAHE, 512, True, out=S.Context.KEEP)
+    assert img.rgb is None and (img.width, img.height) == (512, 512)
+    t = ctx.timing()
+    assert t.d2h_bytes == 0
+    dec, _ = _decode_jpeg(ctx.encode_last_jpeg(0, 100))
+    d = np.abs(dec.astype(int) - ref.astype(int))
+    assert dec.shape == ref.shape and int(d.max()) <= 4 and float(d.mean()) < 0.8, (int(d.max()), float(d.mean()))
+    g1, _ = _decode_jpeg(ctx.encode_last_jpeg(1, 100))
+    one = ctx.process_single(vv, S.JPEG, S.U8, S.CLAHE, 512, True)
+    assert int(np.abs(g1.astype(int) - one.gray.astype(int)).max()) <= 2
+    # a call that does not leave a u8 image invalidates the hand-off
+    ctx.process_polops(vv, vh, (S.OP_RATIO,), S.U16, S.ROBUST)
+    with pytest.raises(S.SarproError):
+        ctx.encode_last_jpeg(0, 100)
+
+
+# ---- streamed upload (f4) ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("strategy", [S.CLAHE, S.ROBUST, S.STANDARD])
+def test_streamed_upload_gives_the_same_bytes(strategy, monkeypatch):
+    """Host u16 bands of 64 MB and more are uploaded in row chunks on a copy stream, pass A consumes the chunks as they land
+    (work units ordered by their last row) and the first band's pass B runs beside the second band's upload. The result must
+    equal the one-copy path (SARPRO_STREAM_UPLOAD=0) and the device-resident path byte for byte; stats included."""
+    import torch
+    from sarpro_b200.synth import synth_pair
+    vv, vh = synth_pair(4200, 8192, point_targets=1e-4)   # 68.8 MB per band
+    outs = []
+    for env in ("1", "0"):
+        monkeypatch.setenv("SARPRO_STREAM_UPLOAD", env)
+        with S.Context(0) as c:
+            img = c.process_synrgb_jpeg(vv, vh, strategy, 1024, True)
+            outs.append(img.rgb.copy())
+            mb = c.process_multiband_tiff(vv, vh, S.U8, strategy, 700, False)
+            outs.append(np.stack([mb.gray, mb.gray_band2]))
+            st = [s.as_dict() for s in mb.stats]
+            again = c.process_synrgb_jpeg(vv, vh, strategy, 1024, True)  # a second call reuses the staging buffers
+            assert np.array_equal(again.rgb, img.rgb)
+        outs.append(st)
+    assert np.array_equal(outs[0], outs[3]) and np.array_equal(outs[1], outs[4]) and outs[2] == outs[5]
+    with S.Context(0) as c:
+        dvv, dvh = torch.from_numpy(vv.view(np.int16)).cuda(), torch.from_numpy(vh.view(np.int16)).cuda()
+        dev = c.process_synrgb_jpeg(dvv, dvh, strategy, 1024, True)
+    assert np.array_equal(dev.rgb, outs[0])
