@@ -18,6 +18,7 @@ second. One "step" = one pass of that pipeline over one synthetic scene.
   c3  dual-pol 25,000 x 16,000 -> CLAHE -> 2048 px + pad -> suppressed synRGB
   c4  full-resolution log-ratio and n-diff of the pair -> Equalized -> two u16 bands, no downsample
   c5  batch of scenes -> 1024 px padded multiband u8 tiles (reference defaults, params.rs:33), scenes distributed over the GPUs
+  read  the CLI's --size flow (not a BASELINE config): both bands averaged down on read, then the synRGB pipeline
 
 N > 1 (torchrun, one rank per GPU). c3 / c2: `value` is ONE scene row-band-sharded over the ranks ("strong" scaling: every
 rank holds its band plus the Lanczos halo; integer histogram / CLAHE-tile all-reduces and one all-gather of the owned output rows
@@ -137,6 +138,7 @@ WORKLOADS = {
     "c3": "C3: dual-pol VV+VH {cols}x{rows} u16 GRD-like -> CLAHE autoscale -> Lanczos3 2048px + pad -> synRGB",
     "c4": "C4: full-resolution log-ratio and n-diff of VV/VH {cols}x{rows} u16 -> Equalized autoscale -> two u16 bands (no downsample)",
     "c5": "C5: batch of dual-pol {cols}x{rows} scenes -> CLAHE -> 1024px padded multiband u8 tiles, scenes distributed over the GPUs",
+    "read": "downsample-on-read (SURVEY f2): VV+VH {cols}x{rows} u16 -> GDAL-style Average to 2048px long side (f32) -> CLAHE -> pad -> synRGB",
 }
 
 
@@ -207,9 +209,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     rows, cols = (4096, 4096) if cfg == "c1" else (args.rows, args.cols)
-    strategy = {"c1": S.STANDARD, "c2": S.ROBUST, "c3": S.CLAHE, "c4": S.EQUALIZED, "c5": S.CLAHE}[cfg]
+    strategy = {"c1": S.STANDARD, "c2": S.ROBUST, "c3": S.CLAHE, "c4": S.EQUALIZED, "c5": S.CLAHE, "read": S.CLAHE}[cfg]
     target = 1024 if cfg == "c5" else TARGET
 
+    if cfg == "read":
+        os.environ.setdefault("SARPRO_STAGE_TIMING", "all")  # the resampling kernel is timed under the `convert` stage
     ctx = S.Context(local_rank)
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
@@ -435,6 +439,10 @@ def main():
         from bench_extra import run_c4
         line, clocks = run_c4(args, ctx, S, dev, stream, rank, world, rows, cols, make_scene, pinned_u16, timed, timed_e2e,
                               with_load_window, peak, peak_src, names, METRIC, WORKLOADS)
+    elif cfg == "read":
+        from bench_extra import run_read
+        line, clocks = run_read(args, ctx, S, dev, stream, rank, world, rows, cols, target, make_scene, pinned_u16, timed, timed_e2e,
+                                with_load_window, peak, peak_src, names, METRIC, WORKLOADS)
     elif cfg == "c5":
         from bench_extra import run_c5
         line, clocks = run_c5(args, ctx, S, dev, stream, rank, world, rows, cols, target, make_scene, pinned_u16, timed, timed_e2e,
@@ -450,10 +458,16 @@ def main():
                 crop_r, crop_c = 8000, 6250
                 vvc = vv[:crop_r, :crop_c].cpu().numpy().view(np.uint16)
                 vhc = vh[:crop_r, :crop_c].cpu().numpy().view(np.uint16)
+            elif cfg == "read":
+                vvc = None
             else:
                 from sarpro_b200.synth import synth_pair
                 crop_r, crop_c = 4000, 6250
                 vvc, vhc = synth_pair(crop_r, crop_c)  # same recipe as the device generator (numpy RNG)
+            if vvc is None:
+                print(json.dumps(line), flush=True)
+                ctx.close()
+                return
             v, dt, note = cpu_sample(cfg, vvc, vhc, 1, full_cols)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": "Mpixel/s", "cores": 1, "kind": "port",
                                     "sample": f"{crop_r}x{crop_c} crop per band of the same scene, {note}, {dt:.1f} s, serial like the reference (SURVEY F1)"}

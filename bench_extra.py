@@ -167,3 +167,85 @@ def run_c5(args, ctx, S, dev, stream, rank, world, rows, cols, target, make_scen
             "parity_ok": parity_ok,
         }
     return line, clocks
+
+
+def run_read(args, ctx, S, dev, stream, rank, world, rows, cols, target, make_scene, pinned_u16, timed, timed_e2e, with_load_window, peak,
+             peak_src, names, METRIC, WORKLOADS):
+    """The CLI's --size flow on one GPU (replicas at N > 1): sarpro_read_band_resampled (Average) for both bands, the f32 rasters
+    stay on the device, then sarpro_pipeline_synrgb at the same target. The oracle of the same chain is timed beside it on a crop."""
+    import time
+
+    import numpy as np
+    import torch
+    vv, vh = make_scene(rank)
+    torch.cuda.synchronize(dev)
+    oc, orr, alg = S.Context.read_dims_for_target(cols, rows, target)
+    small = [torch.empty((orr, oc), dtype=torch.float32, device=dev) for _ in range(2)]
+    poc, porr = S.Context.resize_output_dims(oc, orr, target, True)
+    out_dev = torch.empty((porr, poc, 3), dtype=torch.uint8, device=dev)
+    read_ms = [0.0, 0]
+
+    def step():
+        for k, band in enumerate((vv, vh)):
+            ctx.read_band_resampled(band, oc, orr, alg, out=small[k])
+            t = ctx.timing()
+            read_ms[0] += t.stage_ms[names.index("convert")]
+            read_ms[1] += 1
+        ctx.process_synrgb_jpeg(small[0], small[1], S.CLAHE, target, True, out=out_dev)
+
+    ms_per_step, acc, clocks = with_load_window(step, args.steps)
+    vv_np, vh_np = pinned_u16(vv), pinned_u16(vh)
+    out_h = torch.empty((porr, poc, 3), dtype=torch.uint8).pin_memory().numpy()
+
+    def step_host():
+        for k, band in enumerate((vv_np, vh_np)):
+            ctx.read_band_resampled(band, oc, orr, alg, out=small[k])
+        ctx.process_synrgb_jpeg(small[0], small[1], S.CLAHE, target, True, out=out_h)
+
+    t0 = time.perf_counter()
+    step_host()
+    step_host()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / 2
+    line = None
+    if rank == 0:
+        k_ms = read_ms[0] / max(read_ms[1], 1)
+        alg_bytes = rows * cols * 2 + oc * orr * 4
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": round(world * rows * cols / (ms_per_step * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS["read"].format(rows=rows, cols=cols), "config": "read",
+                       "cache": "inputs (1.6 GB per scene) exceed the 126 MB L2; no flush needed",
+                       "parallelism": "single GPU" if world == 1 else f"replicas only: one scene per GPU x{world}",
+                       "resampler": "average" if alg == 0 else "lanczos", "read_shape": [orr, oc]},
+            "clocks": clocks, "gpu_launches": None,
+            "e2e": {"value": round(world * rows * cols / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": rows * cols * 4,
+                    "d2h_bytes_per_step": porr * poc * 3, "ms_per_step": round(e2e_ms, 3), "input": "pinned host u16 DN bands", "steps": 2},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "kernel": "k_read_average<u16> (one launch per band: the raster read once, f64 accumulation in GDAL's order)",
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(k_ms, 4), "peak_source": peak_src},
+        }
+        # the oracle of the same chain on a crop (serial, like GDAL's RasterIO resampling and the reference's raster path)
+        from oracle import pyoracle as O
+        cr, cc = 4000, 6250
+        a = vv[:cr, :cc].cpu().numpy().view(np.uint16)
+        b = vh[:cr, :cc].cpu().numpy().view(np.uint16)
+        coc, corr, calg = O.read_dims_for_target(cc, cr, 512)
+        t0 = time.perf_counter()
+        r1 = O.read_band_resampled(a, coc, corr, calg)
+        r2 = O.read_band_resampled(b, coc, corr, calg)
+        O.pipeline_synrgb_jpeg(r1, r2, O.CLAHE, 512, True)
+        dt = time.perf_counter() - t0
+        import os
+        line["cpu_baseline"] = {"value": round(cr * cc / dt / 1e6, 3), "unit": "Mpixel/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"{cr}x{cc} crop per band, Average to 512px on read (OpenMP over output rows) then synRGB+CLAHE + pad, {dt:.2f} s"}
+        # launches of one step, counted on a separate step: one resampling kernel per band + the pipeline's
+        per_step = 0
+        for k, band in enumerate((vv, vh)):
+            ctx.read_band_resampled(band, oc, orr, alg, out=small[k])
+            per_step += ctx.timing().kernel_launches
+        ctx.process_synrgb_jpeg(small[0], small[1], S.CLAHE, target, True, out=out_dev)
+        per_step += ctx.timing().kernel_launches
+        line["gpu_launches"] = per_step * args.steps
+    return line, clocks

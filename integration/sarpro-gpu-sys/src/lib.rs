@@ -109,6 +109,13 @@ pub const SARPRO_DT_F32: i32 = 0;
 pub const SARPRO_DT_U16: i32 = 1;
 pub const SARPRO_LOC_HOST: i32 = 0;
 pub const SARPRO_LOC_DEVICE: i32 = 1;
+pub const SARPRO_LOC_NONE: i32 = 2;
+pub const SARPRO_U8: c_int = 0;
+pub const SARPRO_U16: c_int = 1;
+pub const SARPRO_FORMAT_TIFF: c_int = 0;
+pub const SARPRO_FORMAT_JPEG: c_int = 1;
+pub const SARPRO_RESAMPLE_AVERAGE: c_int = 0;
+pub const SARPRO_RESAMPLE_LANCZOS: c_int = 1;
 pub const SARPRO_OP_NONE: c_int = -1;
 pub const SARPRO_OK: c_int = 0;
 pub const SARPRO_ERR_NO_DEVICE: c_int = -2;

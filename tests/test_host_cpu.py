@@ -200,3 +200,28 @@ def test_f32_guard_bound_holds_under_worst_case_log2_error(lib_built, low, rng, 
         assert np.array_equal(idx[dec], exact[dec]), int((idx[dec] != exact[dec]).sum())
         accepted = int(dec[:400_000].sum())
     assert accepted > 0.5 * 400_000
+
+
+def test_rust_wrapper_covers_the_c_abi():
+    """integration/gpu.rs (the safe wrapper the patches call) may only name entry points the header declares, and names every
+    pipeline-level one; the patches only call wrapper methods that exist."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "sarpro_gpu.h")).read()
+    declared = set(re.findall(r"\b(sarpro_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(ROOT, "integration", "gpu.rs")).read()
+    used = set(re.findall(r"sys::(sarpro_[a-z0-9_]+)\s*\(", rs))
+    assert used <= declared, used - declared
+    for must in ("sarpro_pipeline_single", "sarpro_pipeline_multiband_tiff", "sarpro_pipeline_synrgb", "sarpro_pipeline_polops",
+                 "sarpro_pipeline_batch", "sarpro_read_band_resampled", "sarpro_encode_last_jpeg", "sarpro_process_scalar_data_pipeline",
+                 "sarpro_resize_image_data_with_meta", "sarpro_add_padding_to_square", "sarpro_create_synthetic_rgb_by_mode_and_strategy",
+                 "sarpro_pol_op", "sarpro_autoscale_tamed_synrgb_u8", "sarpro_process_scalar_data_inplace"):
+        assert must in used, must
+    methods = set(re.findall(r"pub fn ([a-z0-9_]+)\s*\(", rs))
+    pdir = os.path.join(ROOT, "integration", "patches")
+    called = set()
+    for name in sorted(os.listdir(pdir)):
+        for line in open(os.path.join(pdir, name)):
+            if line.startswith("+"):
+                called |= set(re.findall(r"\|g\| g\.([a-z0-9_]+)\(", line))
+                called |= set(re.findall(r"^\+\s+g\.([a-z0-9_]+)\(", line))
+    assert called and called <= methods, called - methods
