@@ -365,61 +365,11 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         jobs[b].bit_depth = SARPRO_U8;
         jobs[b].kind = kinds[b];
     }
-    for (int b = 0; b < 2; ++b) RC(dn_pass_a_launch_sharded(ctx, b, jobs[b].dn, rows, cols, clahe, sg, 1));
-    for (int b = 0; b < 2; ++b) RC(dn_pass_a_launch_sharded(ctx, b, jobs[b].dn, rows, cols, clahe, sg, 2));
-    // ---- 1. DN histograms of both bands: one fused all-reduce (a group of two) ---------------------------------------------
-    {
-        COMM_BEGIN();
-        NC(api.GroupStart());
-        for (int b = 0; b < 2; ++b)
-            NC(api.AllReduce(ctx->band[b].total.p, ctx->band[b].total.p, kDnBins, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
-        NC(api.GroupEnd());
-        COMM_END();
-    }
-    // ---- plans: on the device for the gamma == 1 strategies (no host round trip; every rank plans redundantly from the
-    // merged histogram, bit-identically), else on the host from the merged dense totals
-    const int both[2] = {0, 1};
-    if (plans_on_device(ctx, jobs[0]) && plans_on_device(ctx, jobs[1])) {
-        RC(plan_bands_on_device(ctx, both, jobs, 2)); // one launch, one CTA per band
-    } else {
-        for (int b = 0; b < 2; ++b) {
-            BandWs& w = ctx->band[b];
-            if (plans_on_device(ctx, jobs[b])) {
-                RC(plan_band_on_device(ctx, b, jobs[b]));
-                continue;
-            }
-            CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            ctx->timing.host_syncs++;
-            plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
-            std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
-            w.hot = w.plan.any_valid ? hmma_hot_from_plan(w.plan, &w.hot_top) : 0;
-            CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
-            RC(upload_plan_dev(ctx, b));
-            w.dev_planned = false;
-            w.hist_auto_pending = true;
-        }
-    }
-    // ---- 2. CLAHE tile histograms of both bands: one launch, one fused all-reduce, then every rank builds all 64 CDFs -------
-    if (clahe) {
-        struct Hook {
-            static int reduce(sarpro_ctx* ctx, void*) {
-                NcclApi& api = nccl();
-                CommState* cs = ctx->comm;
-                COMM_BEGIN();
-                NC(api.GroupStart());
-                for (int b = 0; b < 2; ++b)
-                    NC(api.AllReduce(ctx->band[b].tile256.p, ctx->band[b].tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum, cs->comm,
-                                     ctx->stream));
-                NC(api.GroupEnd());
-                COMM_END();
-                return 0;
-            }
-        };
-        RC(run_clahe_stats_bands(ctx, both, 2, &Hook::reduce, nullptr));
-    }
-    // ---- pass B: horizontal pass over the held rows; band 0 on the side stream so that band 1's persistent CTAs fill the
-    // SMs band 0's leave early
+    // ---- per band: pass A -> DN-histogram all-reduce -> plan -> CLAHE tile statistics (+ all-reduce) -> pass B. Band 0's chain
+    // (everything after its pass A) runs on the side stream, so its two collectives, its planner and its CLAHE statistics
+    // overlap band 1's pass A, and its pass B starts while band 1's chain is still at its collectives; band 1's persistent
+    // pass-B CTAs then fill the SMs band 0's leave. The collectives are issued in the same order on every rank (program
+    // order: band 0's two, then band 1's two), which is what NCCL needs of one communicator used from two streams.
     const size_t esz = 1;
     const size_t n_out = g.oc * g.orr;
     HResizeArgs args[2];
@@ -427,15 +377,55 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     ctx->pair_spare = 0;
     cudaStream_t main_stream = ctx->stream;
     const bool two = ctx->two_stream && ctx->stream2;
-    if (two) {
-        CU(cudaEventRecord(ctx->ev[4], main_stream));
-        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev[4], 0));
-    }
+    for (int b = 0; b < 2; ++b) RC(dn_pass_a_launch_sharded(ctx, b, jobs[b].dn, rows, cols, clahe, sg, 1));
+    RC(dn_pass_a_launch_sharded(ctx, 0, jobs[0].dn, rows, cols, clahe, sg, 2));
+    if (two) CU(cudaEventRecord(ctx->ev[4], main_stream));
+    RC(dn_pass_a_launch_sharded(ctx, 1, jobs[1].dn, rows, cols, clahe, sg, 2));
+    if (two) CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev[4], 0));
+    struct Hook { // all-reduce of one band's CLAHE tile histograms: every rank then builds all 64 CDFs of that band
+        static int reduce(sarpro_ctx* ctx, void* arg) {
+            const int b = *(const int*)arg;
+            NcclApi& api = nccl();
+            CommState* cs = ctx->comm;
+            COMM_BEGIN();
+            NC(api.AllReduce(ctx->band[b].tile256.p, ctx->band[b].tile256.p, (size_t)ctx->n_tiles * 256, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
+            COMM_END();
+            return 0;
+        }
+    };
     int rc_b = 0;
     for (int b = 0; b < 2 && !rc_b; ++b) {
         BandWs& w = ctx->band[b];
         ctx->stream = (two && b == 0) ? ctx->stream2 : main_stream;
         auto body = [&]() -> int {
+            // 1. the band's DN histogram over all ranks
+            {
+                COMM_BEGIN();
+                NC(api.AllReduce(w.total.p, w.total.p, kDnBins, kNcclUint32, kNcclSum, cs->comm, ctx->stream));
+                COMM_END();
+            }
+            // plan: on the device for the gamma == 1 strategies (no host round trip; every rank plans redundantly from the
+            // merged histogram, bit-identically), else on the host from the merged dense totals
+            if (plans_on_device(ctx, jobs[b])) {
+                RC(plan_band_on_device(ctx, b, jobs[b]));
+            } else {
+                CU(cudaMemcpyAsync(ctx->h_hist + (size_t)b * kDnBins, w.total.p, kDnBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                ctx->timing.host_syncs++;
+                plan_from_dn_histogram32(ctx->h_hist + (size_t)b * kDnBins, SARPRO_U8, strategy, kinds[b], &w.plan);
+                std::memcpy(ctx->h_lut + (size_t)b * kDnBins, w.plan.lut.data(), kDnBins * 2);
+                w.hot = w.plan.any_valid ? hmma_hot_from_plan(w.plan, &w.hot_top) : 0;
+                CU(cudaMemcpyAsync(w.lut.p, ctx->h_lut + (size_t)b * kDnBins, kDnBins * 2, cudaMemcpyHostToDevice, ctx->stream));
+                RC(upload_plan_dev(ctx, b));
+                w.dev_planned = false;
+                w.hist_auto_pending = true;
+            }
+            // 2. CLAHE tile histograms through the table, merged over the ranks, then the 64 CDFs
+            if (clahe) {
+                int slot = b;
+                RC(run_clahe_stats_bands(ctx, &slot, 1, &Hook::reduce, &slot));
+            }
+            // pass B: horizontal pass over the held rows
             RC(reserve(ctx, w.temp, std::max<size_t>((size_t)rows * g.rc * esz, 16)));
             RC(reserve(ctx, w.small, std::max<size_t>(n_out * esz, 16)));
             CU(cudaMemsetAsync(w.small.p, 0, std::max<size_t>(n_out * esz, 1), ctx->stream));

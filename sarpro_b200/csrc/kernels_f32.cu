@@ -78,10 +78,36 @@ struct F32Src {
         f32_load8(a, a_u16, i, cnt, vec != 0, x);
         const bool need_b = op[0] >= 0 || (NOPS == 2);
         if (need_b) f32_load8(b, b_u16, i, cnt, vec != 0, y);
+        // the operation is warp-uniform: one switch per vector and operation, straight-line arithmetic inside
 #pragma unroll
-        for (int o = 0; o < NOPS; ++o)
+        for (int o = 0; o < NOPS; ++o) {
+            switch (op[o]) {
+            case 0:
 #pragma unroll
-            for (int k = 0; k < 8; ++k) out[o][k] = op[o] < 0 ? x[k] : f32_pol(op[o], x[k], y[k]);
+                for (int k = 0; k < 8; ++k) out[o][k] = __fadd_rn(x[k], y[k]);
+                break;
+            case 1:
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out[o][k] = __fsub_rn(x[k], y[k]);
+                break;
+            case 2:
+            case 4: // log-ratio == ratio (ops.rs:35-44)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out[o][k] = fabsf(y[k]) > 1e-10f ? __fdiv_rn(x[k], y[k]) : 0.0f;
+                break;
+            case 3:
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float denom = __fadd_rn(x[k], y[k]);
+                    out[o][k] = fabsf(denom) > 1e-10f ? __fdiv_rn(__fsub_rn(x[k], y[k]), denom) : 0.0f;
+                }
+                break;
+            default:
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out[o][k] = x[k];
+                break;
+            }
+        }
         return cnt;
     }
 };
@@ -166,11 +192,12 @@ __device__ __forceinline__ bool f32_guarded_index(const F32Guard& gd, int e, flo
     const float d = __fadd_rn((float)(e - gd.e0), __fsub_rn(lg, gd.f0));
     const float t = __fmul_rn(d, gd.scale);
     const float nf = (float)n;
-    if (t < -gd.guard) { *idx = 0; return true; }
-    if (t > nf + gd.guard) { *idx = top; return true; }
     const float fl = floorf(t), fr = t - fl; // exact
-    if (fr >= gd.guard && fr <= 1.0f - gd.guard && fl >= 0.0f && fl < nf) { *idx = (uint32_t)fl; return true; }
-    return false;
+    // branch-free: below the range / above it / inside with the fraction clear of both integers
+    const bool lo = t < -gd.guard, hi = t > nf + gd.guard;
+    const bool in = (fr >= gd.guard) & (fr <= 1.0f - gd.guard) & (t >= 0.0f) & (fl < nf);
+    *idx = lo ? 0u : (hi ? top : (uint32_t)(int)fl);
+    return lo | hi | in;
 }
 
 // ---- pass 2: 4096-bin histogram over [min_db, max_db] + mean / M2 accumulators -----------------------
@@ -205,6 +232,7 @@ __global__ void __launch_bounds__(256) k_f32_hist4096(F32Src src, uint64_t n, F3
 #pragma unroll
         for (int o = 0; o < NOPS; ++o) {
             float r1 = 0.f, r2 = 0.f; // per-vector partial sums in fp32 (8 terms), then f64
+            uint32_t todo = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float x = s[o][k];
@@ -213,12 +241,23 @@ __global__ void __launch_bounds__(256) k_f32_hist4096(F32Src src, uint64_t n, F3
                     const float lg = f32_split_log2(x, &e);
                     const float rel = __fsub_rn(3.0102999566f * __fadd_rn((float)e, lg), h.min_db[o]);
                     uint32_t idx;
-                    if (!f32_guarded_index(h.guard[o], e, lg, 4096u, 4095u, &idx))
-                        idx = edge_index(s_edges + o * 4096, 4095, x, (int)(rel * h.inv_span4096[o]));
-                    atomicAdd(&s_hist[o * 4096 + idx], 1u);
+                    if (f32_guarded_index(h.guard[o], e, lg, 4096u, 4095u, &idx)) atomicAdd(&s_hist[o * 4096 + idx], 1u);
+                    else todo |= 1u << k;
                     r1 += rel;
                     r2 += rel * rel;
                 }
+            }
+            while (todo) { // the few samples the guard did not decide: exact threshold comparison, one per iteration
+                const int k = __ffs((int)todo) - 1;
+                todo &= todo - 1;
+                float x = s[o][0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) x = k == j ? s[o][j] : x;
+                int e;
+                const float lg = f32_split_log2(x, &e);
+                const float rel = __fsub_rn(3.0102999566f * __fadd_rn((float)e, lg), h.min_db[o]);
+                const uint32_t idx = edge_index(s_edges + o * 4096, 4095, x, (int)(rel * h.inv_span4096[o]));
+                atomicAdd(&s_hist[o * 4096 + idx], 1u);
             }
             s1[o] += (double)r1;
             s2[o] += (double)r2;
@@ -301,26 +340,42 @@ __global__ void __launch_bounds__(256) k_f32_quantize(F32Src src, uint64_t n, F3
         for (int o = 0; o < NOPS; ++o) {
             const float* edges = small ? s_edges[o] : qa.edges[o];
             uint32_t q[8];
+            // first the guarded direct levels of all 8 samples (straight-line code), then the threshold comparisons of the few
+            // samples the guard did not decide, one per iteration: the slow path is issued once per vector, not once per sample
+            uint32_t todo = 0, valid = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float x0 = s[o][k];
-                uint32_t r = 0;
+                q[k] = 0;
                 if ((uint32_t)k < c && x0 >= qa.valid_thresh) {
+                    valid |= 1u << k;
                     int e;
                     const float lg = f32_split_log2(x0, &e);
-                    uint32_t lvl;
-                    if (!f32_guarded_index(qa.guard[o], e, lg, qa.n_levels, qa.n_levels, &lvl)) {
-                        float x = 3.0102999566f * __fadd_rn((float)e, lg);
-                        x = fminf(fmaxf(x, qa.low_db[o]), qa.high_db[o]);
-                        x = (x - qa.low_db[o]) * qa.inv_range[o];
-                        if (qa.gamma[o] != 1.0f) x = __powf(fmaxf(x, 0.0f), qa.gamma[o]);
-                        lvl = edge_index(edges, qa.n_levels, x0, (int)(x * fl));
-                    }
-                    r = qa.key_plane ? lvl + 1 : (sizeof(OutT) == 1 ? (uint32_t)s_remap[o][lvl & 255u] : lvl);
-                } else if (!qa.key_plane && sizeof(OutT) == 1) {
-                    r = s_remap[o][0]; // invalid samples are 0 before scale_u16_to_u8 (autoscale.rs:444, 669-670)
+                    if (!f32_guarded_index(qa.guard[o], e, lg, qa.n_levels, qa.n_levels, &q[k])) todo |= 1u << k;
                 }
-                q[k] = r;
+            }
+            while (todo) {
+                const int k = __ffs((int)todo) - 1;
+                todo &= todo - 1;
+                float x0 = s[o][0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) x0 = k == j ? s[o][j] : x0;
+                int e;
+                const float lg = f32_split_log2(x0, &e);
+                float x = 3.0102999566f * __fadd_rn((float)e, lg);
+                x = fminf(fmaxf(x, qa.low_db[o]), qa.high_db[o]);
+                x = (x - qa.low_db[o]) * qa.inv_range[o];
+                if (qa.gamma[o] != 1.0f) x = __powf(fmaxf(x, 0.0f), qa.gamma[o]);
+                const uint32_t lvl = edge_index(edges, qa.n_levels, x0, (int)(x * fl));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q[j] = k == j ? lvl : q[j];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool v = (valid >> k) & 1u;
+                if (qa.key_plane) q[k] = v ? q[k] + 1u : 0u;
+                else if (sizeof(OutT) == 1) q[k] = s_remap[o][v ? (q[k] & 255u) : 0u]; // invalid samples are 0 before scale_u16_to_u8 (autoscale.rs:444, 669-670)
+                else q[k] = v ? q[k] : 0u;
             }
             OutT* out = reinterpret_cast<OutT*>(qa.out[o]) + v * 8;
             if (c == 8 && qa.out_vec) {

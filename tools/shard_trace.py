@@ -6,6 +6,7 @@ import torch
 import torch.distributed as dist
 import sarpro_b200 as S
 from sarpro_b200.synth import SEED_VH, SEED_VV, synth_band_torch
+os.environ.setdefault("SARPRO_STAGE_TIMING", "all")  # every launch gets an event pair (the context reads this when it is created)
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
