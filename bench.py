@@ -169,7 +169,7 @@ def run_reference(args, rank, world):
                          "note": "reference path is serial (SURVEY F1); only the Lanczos stage uses the threads"},
         "e2e": {"value": round(mpx, 3), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=globals().get('_REAL_STDOUT', sys.stdout), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -188,6 +188,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    # ONE JSON line on stdout, whatever the libraries print there (NCCL writes its version banner to stdout): everything else
+    # goes to stderr, the line is written to the original stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    globals()["_REAL_STDOUT"] = real_stdout
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -465,13 +471,13 @@ def main():
                 crop_r, crop_c = 4000, 6250
                 vvc, vhc = synth_pair(crop_r, crop_c)  # same recipe as the device generator (numpy RNG)
             if vvc is None:
-                print(json.dumps(line), flush=True)
+                print(json.dumps(line), file=globals().get('_REAL_STDOUT', sys.stdout), flush=True)
                 ctx.close()
                 return
             v, dt, note = cpu_sample(cfg, vvc, vhc, 1, full_cols)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": "Mpixel/s", "cores": 1, "kind": "port",
                                     "sample": f"{crop_r}x{crop_c} crop per band of the same scene, {note}, {dt:.1f} s, serial like the reference (SURVEY F1)"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=globals().get('_REAL_STDOUT', sys.stdout), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

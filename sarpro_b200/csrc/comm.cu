@@ -30,6 +30,7 @@ struct NcclApi {
     void* handle = nullptr;
     int (*GetUniqueId)(nccl_unique_id*) = nullptr;
     int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
+    int (*CommInitRankConfig)(nccl_comm_t*, int, nccl_unique_id, int, void*) = nullptr; // optional (NCCL >= 2.14)
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
@@ -63,6 +64,7 @@ static NcclApi& nccl() {
     if (!api.field) { api.error = std::string("missing NCCL symbol ") + name; return api; }
     SARPRO_SYM(GetUniqueId, "ncclGetUniqueId")
     SARPRO_SYM(CommInitRank, "ncclCommInitRank")
+    *(void**)(&api.CommInitRankConfig) = dlsym(api.handle, "ncclCommInitRankConfig");
     SARPRO_SYM(CommDestroy, "ncclCommDestroy")
     SARPRO_SYM(AllReduce, "ncclAllReduce")
     SARPRO_SYM(Broadcast, "ncclBroadcast")
@@ -74,6 +76,8 @@ static NcclApi& nccl() {
     api.ok = true;
     return api;
 }
+
+constexpr int kCommSpareSms = 8; // SMs the big kernels of a sharded call leave to the collectives and the small kernels
 
 struct CommState {
     nccl_comm_t comm = nullptr;
@@ -283,7 +287,20 @@ int sarpro_comm_init(sarpro_ctx* ctx, const void* unique_id128, int rank, int wo
     CommState* cs = new CommState();
     cs->rank = rank;
     cs->world = world;
-    int r = api.CommInitRank(&cs->comm, world, id, rank);
+    // The collectives of a sharded scene are small and run BESIDE the persistent histogram / pass-B kernels, on the few SMs
+    // those leave free (kCommSpareSms): the communicator is capped at that many CTAs, or its kernels would wait for the big
+    // kernels to drain (measured on 2 GPUs: a 256 KB all-reduce took 0.09 ms instead of 0.03 ms).
+    struct NcclConfigV22700 { // ncclConfig_t as of NCCL 2.27 (newer libraries accept older layouts by size / version)
+        size_t size; unsigned int magic, version;
+        int blocking, cgaClusterSize, minCTAs, maxCTAs; const char* netName; int splitShare, trafficClass; const char* commName;
+        int collnetEnable, CTAPolicy, shrinkShare, nvlsCTAs;
+    };
+    constexpr int kUndef = (int)0x80000000; // NCCL_CONFIG_UNDEF_INT
+    NcclConfigV22700 cfg = {sizeof(NcclConfigV22700), 0xcafebeefu, 22700u, kUndef, kUndef, 1, kCommSpareSms, nullptr, kUndef, kUndef, nullptr,
+                            kUndef, kUndef, kUndef, kUndef};
+    int r = -1;
+    if (api.CommInitRankConfig && !getenv("SARPRO_NCCL_NO_CONFIG")) r = api.CommInitRankConfig(&cs->comm, world, id, rank, &cfg);
+    if (r != 0) r = api.CommInitRank(&cs->comm, world, id, rank);
     if (r != 0) {
         delete cs;
         return fail(ctx, SARPRO_ERR_COMM, "ncclCommInitRank failed: %s", api.GetErrorString(r));
@@ -374,7 +391,10 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     const size_t n_out = g.oc * g.orr;
     HResizeArgs args[2];
     bool gates[2] = {false, false};
-    ctx->pair_spare = 0;
+    // SMs that band 1's pass A and band 0's pass B leave free: band 0's collectives (NCCL kernels need an SM slot each), planner
+    // and CLAHE statistics run beside band 1's pass A, band 1's beside band 0's pass B (measured without: band 0's all-reduce
+    // waited 0.06 ms for pass A's persistent CTAs to drain; the communicator is capped at the same number of CTAs)
+    ctx->pair_spare = std::max(ctx->spare_sms, kCommSpareSms);
     cudaStream_t main_stream = ctx->stream;
     const bool two = ctx->two_stream && ctx->stream2;
     for (int b = 0; b < 2; ++b) RC(dn_pass_a_launch_sharded(ctx, b, jobs[b].dn, rows, cols, clahe, sg, 1));
@@ -478,7 +498,7 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     unsigned char* const my_slot = (unsigned char*)ctx->gather.p + (size_t)cs->rank * gg.slot_bytes;
     CU(cudaMemsetAsync(my_slot, 0, gg.slot_bytes, ctx->stream)); // pad columns of the rows
     // vertical pass for the owned output rows, straight into the slot (first run: assumes the tensor-core kernel took the band
-    // and the CLAHE re-stretch is the identity; the gated re-runs below and the repair path further down cover the rest)
+    // and the CLAHE re-stretch is the identity; the checks after the exchange cover the rest)
     auto vpass = [&](int b, int stage, const uint32_t* skip, const uint32_t* run_if) -> int {
         BandWs& w = ctx->band[b];
         if (oy1 <= oy0) return 0;
@@ -490,13 +510,6 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         return 0;
     };
     for (int b = 0; b < 2; ++b) RC(vpass(b, SARPRO_STAGE_VRESIZE, nullptr, nullptr));
-    for (int b = 0; b < 2; ++b)
-        if (gates[b]) {
-            HResizeArgs ag = args[b];
-            ag.run_if = &args[b].plan->use_generic;
-            RC(run_hpass_generic(ctx, ag, src_kind, 0, ah));
-            RC(vpass(b, SARPRO_STAGE_OTHER, nullptr, &args[b].plan->use_generic));
-        }
     RC(reserve(ctx, ctx->rgbsel, 64));
     uint32_t* const nonident = (uint32_t*)ctx->rgbsel.p + 4; // set by the unpack kernel: some band's re-stretch is not the identity
     auto exchange = [&]() -> int {
@@ -521,21 +534,44 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
         return 0;
     };
     if (n_out) RC(exchange());
-    // ---- scale_u16_to_u8 after CLAHE (autoscale.rs:348-364) needs the sample extrema of the WHOLE scene. The result above
-    // assumed the re-stretch is the identity (extrema 0 / 255: any scene with an invalid pixel and a saturated one); the merged
-    // extrema arrive with the rows, and in the rare other case every rank (they all see the same merged values) repairs its
-    // rows with the remap table and the exchange runs once more.
-    if (clahe && n_out) {
-        CU(cudaMemcpyAsync(ctx->h_scalars + 7, nonident, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream)); // (the sync every call ends with; end_call's then returns at once)
-        if (ctx->h_scalars[7]) {
+    // ---- what the first pass speculated, checked once the result is there (one small read-back in front of the sync every
+    // call ends with; every rank sees the same values, so all of them take the same path):
+    //  * a device-planned band whose DN table does not fit the tensor-core kernel (plan->use_generic: more than 2000 hot DNs)
+    //    was skipped by it: the generic exact kernel takes the band and the exchange runs again;
+    //  * scale_u16_to_u8 after CLAHE (autoscale.rs:348-364) needs the sample extrema of the WHOLE scene. The first pass assumed
+    //    the identity (extrema 0 / 255: any scene with an invalid pixel and a saturated one); the merged extrema arrive with the
+    //    rows, and otherwise every rank re-runs its rows through the remap table and the exchange runs once more.
+    if (n_out) {
+        auto read_flags = [&]() -> int {
+            ctx->h_scalars[7] = 0;
+            ctx->h_scalars[5] = ctx->h_scalars[8 + 5] = 0;
+            if (clahe) CU(cudaMemcpyAsync(ctx->h_scalars + 7, nonident, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            for (int b = 0; b < 2; ++b)
+                if (gates[b]) CU(cudaMemcpyAsync(ctx->h_scalars + 8 * b + 5, &args[b].plan->use_generic, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream)); // (the sync every call ends with; end_call's then returns at once)
+            return 0;
+        };
+        RC(read_flags());
+        bool redo = false;
+        for (int b = 0; b < 2; ++b)
+            if (gates[b] && ctx->h_scalars[8 * b + 5]) {
+                RC(run_hpass_generic(ctx, args[b], src_kind, 0, ah));
+                RC(vpass(b, SARPRO_STAGE_OTHER, nullptr, nullptr));
+                gates[b] = false;
+                redo = true;
+            }
+        if (redo) {
+            ctx->timing.host_syncs++;
+            RC(exchange());
+            RC(read_flags());
+        }
+        if (clahe && ctx->h_scalars[7]) {
             ctx->timing.host_syncs++;
             for (int b = 0; b < 2; ++b) {
                 BandWs& w = ctx->band[b];
                 RC(reserve(ctx, w.remap, 256 + 16));
                 uint32_t* flag = reinterpret_cast<uint32_t*>((unsigned char*)w.remap.p + 256);
-                KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream,
-                                                                gates[b] ? args[b].plan : nullptr));
+                KS(SARPRO_STAGE_PLAN, launch_clahe_remap_decide((const uint32_t*)w.scalars.p, (uint8_t*)w.remap.p, flag, ctx->stream, nullptr));
                 HResizeArgs ar = args[b];
                 ar.remap = (const uint8_t*)w.remap.p;
                 ar.minmax = nullptr;

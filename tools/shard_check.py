@@ -63,7 +63,10 @@ for rows, cols, target in shapes:
         two = np.where((np.arange(rows)[:, None] // 97 + np.arange(cols)[None, :] // 131) % 2 == 0, 300, 900).astype(np.uint16)
         tri = np.asarray(vv).copy()
         tri[tri == 0] = 1                                                               # no invalid pixel: the minimum sample may exceed 0
-        for name, a, b in (("flat", flat, two), ("two", two, tri)):
+        # a raster whose DN -> bin table does not fit the tensor-core kernel (> 2000 distinct hot DNs): the device planner sets
+        # plan->use_generic, the sharded pipeline notices after the exchange and re-runs the band with the generic exact kernel
+        wide = np.random.default_rng(rows + cols).integers(1, 40000, (rows, cols)).astype(np.uint16)
+        for name, a, b in (("flat", flat, two), ("two", two, tri), ("wide", wide, tri)):
             h0, h1 = S.shard_halo_rows(rows, cols, target, world, rank, True)
             img = ctx.process_synrgb_sharded(a[h0:h1], b[h0:h1], rows, S.CLAHE, target, True)
             t = ctx.timing()
