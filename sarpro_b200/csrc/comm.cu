@@ -77,7 +77,7 @@ static NcclApi& nccl() {
     return api;
 }
 
-constexpr int kCommSpareSms = 8; // SMs the big kernels of a sharded call leave to the collectives and the small kernels
+constexpr int kCommSpareSms = 16; // SMs the big kernels of a sharded call leave to the collectives and the small kernels
 
 struct CommState {
     nccl_comm_t comm = nullptr;
@@ -287,19 +287,21 @@ int sarpro_comm_init(sarpro_ctx* ctx, const void* unique_id128, int rank, int wo
     CommState* cs = new CommState();
     cs->rank = rank;
     cs->world = world;
-    // The collectives of a sharded scene are small and run BESIDE the persistent histogram / pass-B kernels, on the few SMs
-    // those leave free (kCommSpareSms): the communicator is capped at that many CTAs, or its kernels would wait for the big
-    // kernels to drain (measured on 2 GPUs: a 256 KB all-reduce took 0.09 ms instead of 0.03 ms).
+    // The collectives of a sharded scene are small and run BESIDE the persistent histogram / pass-B kernels, on the SMs those
+    // leave free (kCommSpareSms = 16: with 4 a 256 KB all-reduce waited for the big kernel to drain, 0.09 ms instead of 0.03 ms).
+    // SARPRO_NCCL_MAX_CTAS caps the communicator's CTAs instead (measurement: a cap of 8 made the early all-reduces fast on 8
+    // spare SMs but tripled the final all-gather, 0.114 ms instead of 0.042 ms on 4 GPUs, so it is off by default).
     struct NcclConfigV22700 { // ncclConfig_t as of NCCL 2.27 (newer libraries accept older layouts by size / version)
         size_t size; unsigned int magic, version;
         int blocking, cgaClusterSize, minCTAs, maxCTAs; const char* netName; int splitShare, trafficClass; const char* commName;
         int collnetEnable, CTAPolicy, shrinkShare, nvlsCTAs;
     };
     constexpr int kUndef = (int)0x80000000; // NCCL_CONFIG_UNDEF_INT
-    NcclConfigV22700 cfg = {sizeof(NcclConfigV22700), 0xcafebeefu, 22700u, kUndef, kUndef, 1, kCommSpareSms, nullptr, kUndef, kUndef, nullptr,
+    const int max_ctas = getenv("SARPRO_NCCL_MAX_CTAS") ? atoi(getenv("SARPRO_NCCL_MAX_CTAS")) : 0;
+    NcclConfigV22700 cfg = {sizeof(NcclConfigV22700), 0xcafebeefu, 22700u, kUndef, kUndef, 1, max_ctas, nullptr, kUndef, kUndef, nullptr,
                             kUndef, kUndef, kUndef, kUndef};
     int r = -1;
-    if (api.CommInitRankConfig && !getenv("SARPRO_NCCL_NO_CONFIG")) r = api.CommInitRankConfig(&cs->comm, world, id, rank, &cfg);
+    if (api.CommInitRankConfig && max_ctas > 0) r = api.CommInitRankConfig(&cs->comm, world, id, rank, &cfg);
     if (r != 0) r = api.CommInitRank(&cs->comm, world, id, rank);
     if (r != 0) {
         delete cs;
@@ -393,7 +395,7 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     bool gates[2] = {false, false};
     // SMs that band 1's pass A and band 0's pass B leave free: band 0's collectives (NCCL kernels need an SM slot each), planner
     // and CLAHE statistics run beside band 1's pass A, band 1's beside band 0's pass B (measured without: band 0's all-reduce
-    // waited 0.06 ms for pass A's persistent CTAs to drain; the communicator is capped at the same number of CTAs)
+    // waited 0.06 ms for pass A's persistent CTAs to drain)
     ctx->pair_spare = std::max(ctx->spare_sms, kCommSpareSms);
     cudaStream_t main_stream = ctx->stream;
     const bool two = ctx->two_stream && ctx->stream2;
