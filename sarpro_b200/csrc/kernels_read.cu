@@ -25,26 +25,36 @@ __device__ __forceinline__ double rd_to_double(float v) { return (double)v; }
 template <typename T>
 __global__ void __launch_bounds__(rd::kWarps * 32) k_read_average(const T* __restrict__ src, uint32_t rows, uint32_t cols, ReadAvgAxis ax,
                                                                  ReadAvgAxis ay, float* __restrict__ out, uint32_t out_rows, uint32_t out_cols) {
-    __shared__ T s_row[rd::kWarps][rd::kSpanMax];
+    __shared__ __align__(16) T s_row[rd::kWarps][rd::kSpanMax];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t oy = blockIdx.y * rd::kWarps + warp;
     if (oy >= out_rows) return;
     const uint32_t ox0 = blockIdx.x * 32u, ox = ox0 + lane;
     const bool live = ox < out_cols;
     const uint32_t oxl = min(ox0 + 31u, out_cols - 1u);
-    const int seg0 = ax.start[ox0], seg1 = ax.end[oxl];
+    // the segment starts on a 16-byte boundary of the row when the raster allows 128-bit loads (rows 16-byte aligned)
+    constexpr int kVec = 16 / (int)sizeof(T);
+    const bool vec = (cols % kVec) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const int seg0 = vec ? (ax.start[ox0] & ~(kVec - 1)) : ax.start[ox0], seg1 = ax.end[oxl];
     const int xs = live ? ax.start[ox] : seg0, xe = live ? ax.end[ox] : seg0;
     const double wxf = live ? ax.w_first[ox] : 1.0, wxl = live ? ax.w_last[ox] : 1.0;
     const int ys = ay.start[oy], ye = ay.end[oy];
     const double wyf = ay.w_first[oy], wyl = ay.w_last[oy];
-    const bool staged = (uint32_t)(seg1 - seg0) <= rd::kSpanMax;
+    const bool staged = (uint32_t)(seg1 - seg0) + (uint32_t)kVec <= rd::kSpanMax;
     double total = 0.0, wsum = 0.0;
     T* const s = s_row[warp];
     for (int y = ys; y < ye; ++y) {
         const double wy = y == ys ? wyf : (y + 1 == ye ? wyl : 1.0);
         const T* row = src + (size_t)y * cols;
         if (staged) {
-            for (int x = seg0 + (int)lane; x < seg1; x += 32) s[x - seg0] = row[x];
+            if (vec) { // whole 16-byte vectors (the row length is a multiple of kVec, so the last one stays inside the row)
+                const uint4* rv = reinterpret_cast<const uint4*>(row + seg0);
+                uint4* sv = reinterpret_cast<uint4*>(s);
+                const int nv = (seg1 - seg0 + kVec - 1) / kVec;
+                for (int i = (int)lane; i < nv; i += 32) sv[i] = __ldg(rv + i);
+            } else {
+                for (int x = seg0 + (int)lane; x < seg1; x += 32) s[x - seg0] = row[x];
+            }
             __syncwarp();
         }
         // Same operations in the same order as the reference loop (w = wy * wx; total += v * w; wsum += w), with the factors
