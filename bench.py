@@ -370,7 +370,7 @@ def main():
             full = (rows, cols) == (ROWS, COLS) and world == 1
             kname = "k_hmma<CLAHE>" if cfg == "c3" else "k_hmma<LUT>"
             roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                        "traffic": (871_000_000 if cfg == "c3" else None) if full else None,  # profiles/r02_ncu_full_hmma.md
+                        "traffic": (872_000_000 if cfg == "c3" else None) if full else None,  # profiles/r02p_ncu_full_hmma.md: 861.3 MB read + 10.7 MB written per launch
                         "kernel": f"{kname} (pass B: per-pixel stage fused with the horizontal Lanczos pass on IMMA.16832), one launch per band",
                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(apply_ms, 4), "peak_source": peak_src,
                         "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 4) for i in range(8) if stage_n[i]}}
