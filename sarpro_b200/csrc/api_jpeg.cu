@@ -103,9 +103,13 @@ static int jpeg_state(sarpro_ctx* ctx, JpegState** out) {
     if (!ctx->jpeg) {
         JpegState* js = new JpegState();
         ctx->jpeg = js;
-        NJ(api.CreateSimple(&js->handle));
-        NJ(api.EncoderStateCreate(js->handle, &js->state, ctx->stream));
-        NJ(api.EncoderParamsCreate(js->handle, &js->params, ctx->stream));
+        nvjpegStatus_t st = api.CreateSimple(&js->handle);
+        if (st == NVJPEG_STATUS_SUCCESS) st = api.EncoderStateCreate(js->handle, &js->state, ctx->stream);
+        if (st == NVJPEG_STATUS_SUCCESS) st = api.EncoderParamsCreate(js->handle, &js->params, ctx->stream);
+        if (st != NVJPEG_STATUS_SUCCESS) {
+            jpeg_state_destroy(ctx); // never leave a half-built encoder behind
+            return fail(ctx, SARPRO_ERR_INTERNAL, "nvJPEG encoder setup failed with status %d", (int)st);
+        }
     }
     *out = ctx->jpeg;
     return 0;
