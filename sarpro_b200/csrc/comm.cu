@@ -415,11 +415,15 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
             return 0;
         }
     };
+    // Two phases, each issued for band 0 (side stream) and then band 1 (main stream): NCCL runs a communicator's collectives
+    // in issue order, so band 1's first all-reduce is queued before band 0's second one and does not wait behind it.
     int rc_b = 0;
+    for (int phase = 0; phase < 2 && !rc_b; ++phase)
     for (int b = 0; b < 2 && !rc_b; ++b) {
         BandWs& w = ctx->band[b];
         ctx->stream = (two && b == 0) ? ctx->stream2 : main_stream;
         auto body = [&]() -> int {
+            if (phase == 0) {
             // 1. the band's DN histogram over all ranks
             {
                 COMM_BEGIN();
@@ -442,6 +446,8 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
                 w.dev_planned = false;
                 w.hist_auto_pending = true;
             }
+            return 0;
+            } // phase 0
             // 2. CLAHE tile histograms through the table, merged over the ranks, then the 64 CDFs
             if (clahe) {
                 int slot = b;
