@@ -103,7 +103,9 @@ int upload_rgb_luts(sarpro_ctx* ctx) {
 // local rows [0, rows) are scene rows [row_off, row_off+rows); tiles follow the scene geometry.
 // own0/own1: local rows that are counted (a sharded rank also holds halo rows it must not count).
 int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uint64_t scene_rows, uint64_t row_off,
-                  uint64_t own0, uint64_t own1) {
+                  uint64_t own0, uint64_t own1, uint64_t pitch) {
+    // pitch >= cols: the per-column CLAHE tables cover the padding columns of a re-pitched raster as well (geometry from cols)
+    const uint64_t tcols = std::max(cols, pitch);
     std::vector<HistUnit> units;
     const uint64_t target_px = 192 * 1024;
     if (!clahe) {
@@ -163,17 +165,17 @@ int prepare_units(sarpro_ctx* ctx, uint64_t rows, uint64_t cols, bool clahe, uin
         CU(cudaMemcpyAsync(ctx->tile_px.p, px, sizeof(px), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         // bilinear geometry per column / row
-        RC(reserve(ctx, ctx->col_dx, cols * 8));
-        RC(reserve(ctx, ctx->col_omdx, cols * 8));
-        RC(reserve(ctx, ctx->col_t, cols * 2));
+        RC(reserve(ctx, ctx->col_dx, tcols * 8));
+        RC(reserve(ctx, ctx->col_omdx, tcols * 8));
+        RC(reserve(ctx, ctx->col_t, tcols * 2));
         RC(reserve(ctx, ctx->row_dy, rows * 8));
         RC(reserve(ctx, ctx->row_omdy, rows * 8));
         RC(reserve(ctx, ctx->row_t, rows * 2));
-        RC(reserve(ctx, ctx->col_m, cols * 4));
+        RC(reserve(ctx, ctx->col_m, tcols * 4));
         RC(reserve(ctx, ctx->row_sat, rows * 4)); // sat, then sat1
         ctx->clahe_tile_w = g.tile_w;
         ctx->clahe_tile_h = g.tile_h;
-        KL(launch_clahe_axis((uint32_t)cols, 0, (uint32_t)g.tile_w, kClaheTiles, (double*)ctx->col_dx.p,
+        KL(launch_clahe_axis((uint32_t)tcols, 0, (uint32_t)g.tile_w, kClaheTiles, (double*)ctx->col_dx.p,
                              (double*)ctx->col_omdx.p, (uint16_t*)ctx->col_t.p, (int32_t*)ctx->col_m.p, nullptr, ctx->stream));
         KL(launch_clahe_axis((uint32_t)rows, (uint32_t)row_off, (uint32_t)g.tile_h, kClaheTiles, (double*)ctx->row_dy.p,
                              (double*)ctx->row_omdy.p, (uint16_t*)ctx->row_t.p, nullptr, (uint16_t*)ctx->row_sat.p, ctx->stream,
@@ -217,8 +219,10 @@ static void drop_axis_plans(sarpro_ctx* ctx) {
     for (auto& w : ctx->band) { w.pc_axis_id = 0; w.pc_n_ctas = 0; }
 }
 
-int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res, uint32_t strip_nt) {
-    const AxisKey key{in, out, wide ? 1 : 0, horiz ? 1 : 0, horiz ? src_kind : 0, horiz ? strip_nt : 0u};
+int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res, uint32_t strip_nt,
+             uint32_t hmma_in) {
+    if (!hmma_in || !horiz) hmma_in = in;
+    const AxisKey key{in, out, wide ? 1 : 0, horiz ? 1 : 0, horiz ? src_kind : 0, horiz ? strip_nt : 0u, horiz ? hmma_in : 0u};
     auto it = ctx->axes.find(key);
     if (it != ctx->axes.end()) { *res = it->second; return 0; }
     AxisPlan* ap = new AxisPlan();
@@ -255,7 +259,8 @@ int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, 
         }
         if (!rc && !wide && src_kind != HSRC_IMAGE) {
             const uint32_t tile_w = (in + kClaheTiles - 1) / kClaheTiles;
-            if (hmma_build_plan(h.start.data(), h.size.data(), h.coef.data(), h.window, out, in,
+            // (taps come from the true width `in`; the walk covers hmma_in >= in columns, the extra ones carry no tap)
+            if (hmma_build_plan(h.start.data(), h.size.data(), h.coef.data(), h.window, out, hmma_in,
                                 src_kind == HSRC_DN_CLAHE ? tile_w : 0u, &mp, strip_nt)) {
                 rc = upload_vec(ctx, ap->m_btab, mp.btab.data(), mp.btab.size() * sizeof(uint4));
                 if (!rc) rc = upload_vec(ctx, ap->m_ntile, mp.ntile.data(), mp.ntile.size() * sizeof(int4));
@@ -428,10 +433,12 @@ int dn_pass_a_launch(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, 
 
 int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_t rows, uint64_t cols, bool clahe_units,
                              const ShardGeom& sg, int phase) {
+    const uint64_t pitch = ctx->band[b].pitch ? ctx->band[b].pitch : cols; // row pitch of `dn` (a re-pitched raster: > cols)
     if (ctx->units_rows != rows || ctx->units_cols != cols || ctx->units_clahe != (int)clahe_units ||
         ctx->units_scene_rows != sg.scene_rows || ctx->units_row_off != sg.row_off || ctx->units_own0 != sg.own0 ||
-        ctx->units_own1 != sg.own1) {
-        RC(prepare_units(ctx, rows, cols, clahe_units, sg.scene_rows, sg.row_off, sg.own0, sg.own1));
+        ctx->units_own1 != sg.own1 || ctx->units_pitch != pitch) {
+        RC(prepare_units(ctx, rows, cols, clahe_units, sg.scene_rows, sg.row_off, sg.own0, sg.own1, pitch));
+        ctx->units_pitch = pitch;
         ctx->units_rows = rows;
         ctx->units_cols = cols;
         ctx->units_clahe = clahe_units;
@@ -466,12 +473,12 @@ int dn_pass_a_launch_sharded(sarpro_ctx* ctx, int b, const uint16_t* dn, uint64_
             CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[sb.ev0 + c], 0));
             if (upto == done) continue;
             if (done) CU(cudaMemsetAsync((uint32_t*)w.scalars.p + 4, 0, 4, ctx->stream)); // the kernels' work-unit counter
-            KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units_by_row.p + done, upto - done, (uint32_t*)w.tile_hist.p,
+            KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, pitch, (const HistUnit*)ctx->units_by_row.p + done, upto - done, (uint32_t*)w.tile_hist.p,
                                                  grid_sms, variant, ctx->stream, (uint32_t*)w.scalars.p + 4));
             done = upto;
         }
     } else {
-        KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, cols, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p, grid_sms, variant,
+        KS(SARPRO_STAGE_HIST, launch_dn_hist(dn, pitch, (const HistUnit*)ctx->units.p, ctx->n_units, (uint32_t*)w.tile_hist.p, grid_sms, variant,
                                              ctx->stream, (uint32_t*)w.scalars.p + 4));
     }
     KS(SARPRO_STAGE_PLAN, launch_hist_total((const uint32_t*)w.tile_hist.p, ctx->n_tiles, (uint32_t*)w.total.p,
@@ -728,14 +735,16 @@ int run_pass_b_resized(sarpro_ctx* ctx, int b, const BandJob& j, const OutGeom& 
     const bool clahe = uses_clahe(j);
     const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
     AxisPlan *ah, *av;
-    RC(get_axis(ctx, (uint32_t)j.cols, (uint32_t)g.rc, pix16, true, src_kind, &ah, choose_strip_nt(ctx, j.rows, g.rc, clahe)));
+    // (a re-pitched raster, produce_bands: j.dn has rows w.pitch samples apart; taps and geometry stay those of j.cols)
+    RC(get_axis(ctx, (uint32_t)j.cols, (uint32_t)g.rc, pix16, true, src_kind, &ah, choose_strip_nt(ctx, j.rows, g.rc, clahe), (uint32_t)w.pitch));
     RC(get_axis(ctx, (uint32_t)j.rows, (uint32_t)g.rr, pix16, false, 0, &av));
     RC(reserve(ctx, w.temp, (size_t)j.rows * g.rc * esz));
     if (clahe) RC(run_clahe_stats(ctx, b));
     HResizeArgs a{};
     a.src = j.dn;
     a.src_rows = (uint32_t)j.rows;
-    a.src_cols = (uint32_t)j.cols;
+    a.src_cols = (uint32_t)(w.pitch ? w.pitch : j.cols);
+    a.src_width = (uint32_t)j.cols;
     a.lut = (const uint16_t*)w.lut.p;
     a.plan = (const PlanDev*)w.plan_dev.p;
     a.remap = nullptr;
@@ -948,6 +957,7 @@ int begin_call(sarpro_ctx* ctx) {
     std::memset(&ctx->timing, 0, sizeof(ctx->timing));
     ctx->pending_stats[0] = ctx->pending_stats[1] = nullptr;
     ctx->streamed[0].n_chunks = ctx->streamed[1].n_chunks = 0;
+    ctx->band[0].pitch = ctx->band[1].pitch = 0;
     if (ctx->upload_in_flight && ctx->stream_up) { cudaStreamSynchronize(ctx->stream_up); ctx->upload_in_flight = false; }
     if (!ctx->keep_last)
         for (auto& l : ctx->last) l = sarpro_ctx::LastResult{}; // the buffers are about to be reused
@@ -1068,7 +1078,34 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
         }
         return 0;
     }
-    for (int b = 0; b < nb; ++b) RC(stage_band(ctx, b, ins[b], ins2[b], ops[b], &jobs[b].dn, &integral[b]));
+    // A resized output of a DN raster whose width is not a multiple of 8 would miss the tensor-core pass B, the third-generation
+    // histogram kernel and the 128-bit loads of the generic kernel (all need 16-byte aligned rows): such rasters are re-pitched
+    // to the next multiple of 8 columns, the edge sample replicated into the 1..7 padding columns (which carry no tap and are
+    // kept out of every statistic). A host raster is re-pitched by its upload (a 2-D copy, no extra pass), a device raster by
+    // one kernel (4 B per sample).
+    bool want_pad[2] = {false, false};
+    for (int b = 0; b < nb; ++b)
+        want_pad[b] = geom->resize && (cols % 8) != 0 && cols >= 512 && ops[b] < 0 && ctx->repitch && !ctx->force_exact;
+    const uint64_t pitch = (cols + 7) & ~uint64_t(7);
+    for (int b = 0; b < nb; ++b) {
+        BandWs& w = ctx->band[b];
+        if (want_pad[b] && ins[b]->dtype == SARPRO_DT_U16 && ins[b]->location == SARPRO_LOC_HOST) {
+            RC(reserve(ctx, w.dn_pad, rows * pitch * 2));
+            CU(cudaMemcpy2DAsync(w.dn_pad.p, pitch * 2, ins[b]->data, cols * 2, cols * 2, rows, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->timing.h2d_bytes += rows * cols * 2;
+            KL(launch_pad_cols((uint16_t*)w.dn_pad.p, (uint32_t)rows, (uint32_t)cols, (uint32_t)pitch, ctx->stream));
+            jobs[b].dn = (const uint16_t*)w.dn_pad.p;
+            w.pitch = pitch;
+            continue;
+        }
+        RC(stage_band(ctx, b, ins[b], ins2[b], ops[b], &jobs[b].dn, &integral[b]));
+        if (want_pad[b] && integral[b]) {
+            RC(reserve(ctx, w.dn_pad, rows * pitch * 2));
+            KL(launch_repitch(jobs[b].dn, (uint16_t*)w.dn_pad.p, (uint32_t)rows, (uint32_t)cols, (uint32_t)pitch, ctx->sm_count, ctx->stream));
+            jobs[b].dn = (const uint16_t*)w.dn_pad.p;
+            w.pitch = pitch;
+        }
+    }
     // u16-valued rasters share one pass A + planner round trip
     BandJob dnjobs[2];
     int dnidx[2], ndn = 0;
@@ -1194,6 +1231,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if (const char* v = getenv("SARPRO_HOST_PLAN")) ctx->host_plan = atoi(v);
     if (const char* v = getenv("SARPRO_F32_NO_GUARD")) ctx->f32_no_guard = atoi(v);
     if (const char* v = getenv("SARPRO_STREAM_UPLOAD")) ctx->stream_upload = atoi(v);
+    if (const char* v = getenv("SARPRO_REPITCH")) ctx->repitch = atoi(v);
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
     if (const char* v = getenv("SARPRO_HMMA")) ctx->use_hmma = atoi(v);
@@ -1218,7 +1256,7 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     sarpro_comm_destroy(ctx); // NCCL communicator + CommState
     jpeg_state_destroy(ctx);
     for (auto& w : ctx->band)
-        for (DevBuf* b : {&w.dn, &w.f32a, &w.f32b, &w.tile_hist, &w.total, &w.lut, &w.tile256, &w.cdf, &w.cdf32, &w.remap,
+        for (DevBuf* b : {&w.dn, &w.dn_pad, &w.f32a, &w.f32b, &w.tile_hist, &w.total, &w.lut, &w.tile256, &w.cdf, &w.cdf32, &w.remap,
                           &w.temp, &w.small, &w.full, &w.scalars, &w.present, &w.edges, &w.hist4096, &w.f32scan, &w.pieces,
                           &w.cta_first, &w.plan_dev, &w.plan_scratch})
             release(*b);

@@ -59,13 +59,17 @@ struct AxisKey {
     uint32_t in, out;
     int wide, horiz, src_kind;
     uint32_t strip_nt; // n-tiles per strip of the tensor-core plan (horizontal axes only)
+    uint32_t hmma_in;  // width the tensor-core plan walks (the pitch of a re-pitched raster; = in otherwise)
     bool operator<(const AxisKey& o) const {
-        return std::tie(in, out, wide, horiz, src_kind, strip_nt) < std::tie(o.in, o.out, o.wide, o.horiz, o.src_kind, o.strip_nt);
+        return std::tie(in, out, wide, horiz, src_kind, strip_nt, hmma_in) <
+               std::tie(o.in, o.out, o.wide, o.horiz, o.src_kind, o.strip_nt, o.hmma_in);
     }
 };
 
 struct BandWs {
     DevBuf dn;         // uploaded / converted raster
+    DevBuf dn_pad;     // the raster re-pitched to a multiple of 8 columns (resized u8 outputs of rasters of other widths)
+    uint64_t pitch = 0; // row pitch of dn_pad in samples while the call uses it, else 0
     DevBuf f32a, f32b; // f32 staging
     DevBuf tile_hist, total, lut, tile256, cdf, cdf32, remap;
     DevBuf temp, small, full;
@@ -141,6 +145,7 @@ struct sarpro_ctx {
     int use_hmma = 1;    // SARPRO_HMMA=0: the generic exact kernel (kernels_resize.cu) instead of kernels_hmma.cu (validation)
     int force_exact = 0; // SARPRO_FORCE_EXACT=1: generic kernels + exact f64 CLAHE everywhere (validation)
     // geometry caches
+    uint64_t units_pitch = 0; // columns the CLAHE per-column tables were built for (the pitch of a re-pitched raster)
     uint64_t units_rows = 0, units_cols = 0, units_scene_rows = 0, units_row_off = 0, units_own0 = 0, units_own1 = 0;
     int units_clahe = -1;
     uint32_t n_units = 0, n_tiles = 0;
@@ -186,6 +191,7 @@ struct sarpro_ctx {
     struct StreamedBand { int n_chunks = 0, ev0 = 0; uint32_t row_end[kUploadChunks] = {}; }; // ev0: first of its events in ev_chunk
     StreamedBand streamed[2];
     bool upload_in_flight = false;              // chunks were queued in a call that has not completed (error path): drain first
+    int repitch = 1;                            // SARPRO_REPITCH=0: rasters of odd widths stay on the generic kernels (measurement)
     int stream_upload = 1;                      // SARPRO_STREAM_UPLOAD=0: one copy on the main stream (measurement)
     sarpro::DevBuf units_by_row;                // the work units of pass A ordered by last row
     std::vector<uint32_t> units_r1;             // their last rows (ascending), host copy
@@ -206,7 +212,9 @@ int reserve(sarpro_ctx* ctx, DevBuf& b, size_t bytes);
 uint32_t hmma_hot(const uint16_t* lut_host, const uint32_t* hist_host, uint32_t max_present_dn, uint32_t* top_out);
 uint32_t hmma_hot_from_plan(const BandPlan& plan, uint32_t* top_out);
 // strip_nt: n-tiles (8 output columns) per strip of the tensor-core pass B; shorter strips = finer work units for short rasters
-int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res, uint32_t strip_nt = 32);
+// hmma_in: width the tensor-core plan walks when the raster was re-pitched to a multiple of 8 columns (0 = in)
+int get_axis(sarpro_ctx* ctx, uint32_t in, uint32_t out, bool wide, bool horiz, int src_kind, AxisPlan** res, uint32_t strip_nt = 32,
+             uint32_t hmma_in = 0);
 uint32_t choose_strip_nt(const sarpro_ctx* ctx, uint64_t rows, uint64_t out_cols, bool clahe);
 int begin_call(sarpro_ctx* ctx);
 int ensure_upload_stream(sarpro_ctx* ctx); // api_batch.cu

@@ -124,6 +124,11 @@ cudaError_t launch_apply_clahe(const uint16_t* dn, uint32_t rows, uint32_t cols,
                                int max_val, uint8_t* out_u8, uint16_t* out_u16, uint32_t* minmax, int sm_count,
                                cudaStream_t stream);
 // packs (unpack = 0) / unpacks (1) {max, ~min} of two bands' {min, max} words into / from a 4-word vector
+// columns [width, pitch) of every row <- the row's last real sample (re-pitched rasters, see HResizeArgs::src_width)
+cudaError_t launch_pad_cols(uint16_t* dn, uint32_t rows, uint32_t width, uint32_t pitch, cudaStream_t stream);
+// the whole re-pitch of a device raster in one pass (edge replication included)
+cudaError_t launch_repitch(const uint16_t* src, uint16_t* dst, uint32_t rows, uint32_t width, uint32_t pitch, int sm_count,
+                           cudaStream_t stream);
 cudaError_t launch_minmax_pack(uint32_t* scalars0, uint32_t* scalars1, uint32_t* packed4, int unpack, cudaStream_t stream);
 // Sharded scene, last exchange (comm.cu): every rank's slot of the all-gathered buffer holds its own output rows of both bands
 // (max_rows x out_pitch bytes per band, row oy of rank r at local row oy - oy0[r]) and a 16-byte tail {min0, max0, min1, max1}
@@ -174,6 +179,9 @@ struct HResizeArgs {
     uint32_t row0, n_rows;
     void* temp;            // [n_rows][out_cols] same pixel type
     AxisDev ax;
+    // Re-pitched raster (source width not a multiple of 8: the rows were copied to a pitch of src_cols = the next multiple of 8
+    // and the last 1..7 columns replicate the edge pixel, so that every row starts 16-byte aligned): the true width. 0 = src_cols.
+    uint32_t src_width;
 };
 // One CTA of the horizontal pass owns a strip of output columns; the strip's source span is staged per row.
 struct HStrip {

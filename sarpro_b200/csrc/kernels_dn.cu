@@ -635,6 +635,43 @@ cudaError_t launch_minmax_pack(uint32_t* scalars0, uint32_t* scalars1, uint32_t*
     return cudaGetLastError();
 }
 
+// ---- re-pitched rasters: replicate the edge sample into the padding columns -------------------------------------------------
+__global__ void __launch_bounds__(256) k_pad_cols(uint16_t* __restrict__ dn, uint32_t rows, uint32_t width, uint32_t pitch) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    uint16_t* row = dn + (size_t)r * pitch;
+    const uint16_t v = row[width - 1];
+    for (uint32_t c = width; c < pitch; ++c) row[c] = v;
+}
+// dst[r][c] = src[r][min(c, width - 1)], dst rows `pitch` samples apart (a multiple of 8, 16-byte aligned), src rows `width`
+// apart at whatever alignment: a thread writes one 128-bit vector from eight 2-byte loads (consecutive lanes read consecutive
+// 16-byte pieces, L1 merges the 2-byte accesses of a line)
+__global__ void __launch_bounds__(256) k_repitch(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, uint32_t rows,
+                                                 uint32_t width, uint32_t pitch) {
+    const uint32_t vpr = pitch / 8u; // vectors per row
+    const uint64_t nvec = (uint64_t)rows * vpr, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint32_t r = (uint32_t)(v / vpr), c = (uint32_t)(v % vpr) * 8u;
+        const uint16_t* s = src + (size_t)r * width;
+        uint32_t x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = s[min(c + (uint32_t)k, width - 1u)];
+        *reinterpret_cast<uint4*>(dst + (size_t)r * pitch + c) =
+            make_uint4(x[0] | (x[1] << 16), x[2] | (x[3] << 16), x[4] | (x[5] << 16), x[6] | (x[7] << 16));
+    }
+}
+cudaError_t launch_repitch(const uint16_t* src, uint16_t* dst, uint32_t rows, uint32_t width, uint32_t pitch, int sm_count,
+                           cudaStream_t stream) {
+    if (rows == 0 || width == 0) return cudaSuccess;
+    k_repitch<<<sm_count * 8, 256, 0, stream>>>(src, dst, rows, width, pitch);
+    return cudaGetLastError();
+}
+cudaError_t launch_pad_cols(uint16_t* dn, uint32_t rows, uint32_t width, uint32_t pitch, cudaStream_t stream) {
+    if (rows == 0 || pitch <= width || width == 0) return cudaSuccess;
+    k_pad_cols<<<(rows + 255) / 256, 256, 0, stream>>>(dn, rows, width, pitch);
+    return cudaGetLastError();
+}
+
 // ---- sharded scene: rows + extrema out of the all-gathered slots (see GatherGeom in kernels.h) ----------------------------
 __global__ void k_gather_tail(const uint32_t* __restrict__ s0, const uint32_t* __restrict__ s1, uint32_t* __restrict__ tail) {
     const uint32_t* s = threadIdx.x < 2 ? s0 : s1;

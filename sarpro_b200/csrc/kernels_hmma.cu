@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t lut_shift = hmma_lut_shift(hot); // table word of DN idx, replica r: byte (idx << lut_shift) + 4r
     const HMmaSmem L = hmma_layout(CLAHE, hot << lut_shift, pp.b_bytes);
-    const uint32_t cols = a.src_cols;
+    const uint32_t cols = a.src_cols;                          // row pitch and width the kernel walks (a multiple of 8)
+    const uint32_t width = a.src_width ? a.src_width : cols;  // true raster width (re-pitched rasters: cols - width < 8)
     const uint32_t tid = threadIdx.x, lane = hm_keep(tid & 31u), g = hm_keep(lane >> 2), q = hm_keep(lane & 3u);
     if (sbase + (hot << lut_shift) > 65536u) __trap(); // 16-bit table addresses (dynamic smem starts low on sm_100)
     uint32_t* const s_ctrl = reinterpret_cast<uint32_t*>(smem + L.ctrl);
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
 
         // exact u8 sample of pixel (r, c) (local row, column) with the reference's f64 operation order
         auto exact_px = [&](uint32_t r, uint32_t c) -> uint32_t {
+            if (c >= width) return 0u; // padding column of a re-pitched raster: zero taps, and it must not enter the min / max
             const uint32_t d = src[(size_t)r * cols + c];
             const uint32_t di = min(d, hot - 1u);
             const uint32_t word = reinterpret_cast<const uint32_t*>(smem + L.lut)[(size_t)di << (lut_shift - 2)];
@@ -547,7 +549,9 @@ __global__ void __launch_bounds__(CLAHE ? hm::kThreadsClahe : hm::kThreadsLut, 1
                         for (int rw = 0; rw < 2; ++rw) {
                             const int v = rw * 2 + h;
                             const uint32_t (&pr)[4] = prr[rw];
-                            bool risky = racc[rw] > fmask;
+                            // (the one vector per row that holds padding columns of a re-pitched raster: their position-dependent
+                            // samples exist in no real pixel, so the vector takes the exact path, which skips them)
+                            bool risky = racc[rw] > fmask || c0 + 8u > width;
                             const uint32_t k0 = __viaddmin_s16x2_relu(pr[0], relu_c, 0x00FF00FFu);
                             const uint32_t k1 = __viaddmin_s16x2_relu(pr[1], relu_c, 0x00FF00FFu);
                             const uint32_t k2 = __viaddmin_s16x2_relu(pr[2], relu_c, 0x00FF00FFu);

@@ -54,6 +54,8 @@ struct Loader {
             for (int k = 0; k < 8; ++k) d[k] = (c + k < a.src_cols) ? (uint32_t)p[k] : 0u;
         }
     }
+    // true raster width: src_cols is the row pitch, which exceeds it by 1..7 padding columns on a re-pitched raster
+    __device__ __forceinline__ uint32_t width() const { return a.src_width ? a.src_width : a.src_cols; }
 
     __device__ __forceinline__ void get(uint32_t r, uint32_t c, uint32_t o[8]) {
         if (SRC == HSRC_IMAGE) {
@@ -88,7 +90,7 @@ struct Loader {
             for (int k = 0; k < 8; ++k) {
                 uint32_t v = 0;
                 const uint32_t cc = c + k;
-                if (cc < a.src_cols) {
+                if (cc < width()) { // (padding columns carry no tap and must not enter the min / max)
                     if (d[k] != 0) {
                         const uint32_t bin = look(d[k]) & 255u;
                         const uint32_t tx = cl.col_t[cc];

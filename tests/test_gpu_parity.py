@@ -658,3 +658,29 @@ def test_streamed_upload_gives_the_same_bytes(strategy, monkeypatch):
         dvv, dvh = torch.from_numpy(vv.view(np.int16)).cuda(), torch.from_numpy(vh.view(np.int16)).cuda()
         dev = c.process_synrgb_jpeg(dvv, dvh, strategy, 1024, True)
     assert np.array_equal(dev.rgb, outs[0])
+
+
+# ---- rasters whose width is not a multiple of 8 (re-pitched for the aligned kernels) ----------------------------------
+@pytest.mark.parametrize("cols", [4097, 4103, 5001])
+def test_repitched_raster_matches_oracle(ctx, cols, monkeypatch):
+    """A raster whose width is not a multiple of 8 is re-pitched (host rasters by their upload, device rasters by one kernel; the
+    1..7 padding columns replicate the edge sample, carry no tap and stay out of every statistic) so that the tensor-core pass B
+    and the aligned loads apply. Host and device inputs, CLAHE (position-dependent samples: the padding must not leak into the
+    re-stretch extrema) and a LUT strategy, u8 synRGB and U16 bands: all equal to the oracle, and to SARPRO_REPITCH=0."""
+    import torch
+    from sarpro_b200.synth import synth_pair
+    vv, vh = synth_pair(1300, cols, point_targets=1e-4)
+    vv[vv == 0] = 1   # no invalid pixel in band 1: its minimum sample is not 0, the re-stretch decision depends on real pixels only
+    dvv, dvh = torch.from_numpy(vv.view(np.int16)).cuda(), torch.from_numpy(vh.view(np.int16)).cuda()
+    for strategy in (S.CLAHE, S.ROBUST):
+        ref, _ = O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), strategy, 512, True)
+        for a, b in ((vv, vh), (dvv, dvh)):
+            img = ctx.process_synrgb_jpeg(a, b, strategy, 512, True)
+            assert np.array_equal(img.rgb, ref), (strategy, type(a).__name__, int((img.rgb != ref).sum()))
+        r1, r2, _ = O.pipeline_multiband_tiff(vv.astype(np.float32), vh.astype(np.float32), S.U16, strategy, 400, False)
+        mb = ctx.process_multiband_tiff(dvv, dvh, S.U16, strategy, 400, False)
+        assert np.array_equal(mb.gray16, r1) and np.array_equal(mb.gray16_band2, r2), strategy
+    monkeypatch.setenv("SARPRO_REPITCH", "0")
+    with S.Context(0) as c:
+        plain = c.process_synrgb_jpeg(vv, vh, S.CLAHE, 512, True)
+    assert np.array_equal(plain.rgb, O.pipeline_synrgb_jpeg(vv.astype(np.float32), vh.astype(np.float32), S.CLAHE, 512, True)[0])
