@@ -347,7 +347,8 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     const int src_kind = clahe ? HSRC_DN_CLAHE : HSRC_DN_LUT;
     if (g.rc == 0 || g.rr == 0) return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "resize target yields an empty image");
     // (the strip length follows the rows this rank holds, b1->rows: see choose_strip_nt)
-    RC(get_axis(ctx, (uint32_t)cols, (uint32_t)g.rc, false, true, src_kind, &ah, choose_strip_nt(ctx, b1->rows, g.rc, clahe)));
+    const uint32_t hmma_in = ((cols % 8) != 0 && cols >= 512 && ctx->repitch && !ctx->force_exact) ? (uint32_t)((cols + 7) & ~(size_t)7) : 0u;
+    RC(get_axis(ctx, (uint32_t)cols, (uint32_t)g.rc, false, true, src_kind, &ah, choose_strip_nt(ctx, b1->rows, g.rc, clahe), hmma_in));
     RC(get_axis(ctx, (uint32_t)scene_rows, (uint32_t)g.rr, false, false, 0, &av));
     RC(shard_geometry(scene_rows, cols, true, target, pad != 0, cs->world, cs->rank, clahe, &r0, &r1, &h0, &h1, &oy0, &oy1, &g,
                       &av->h));
@@ -368,10 +369,24 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     sg.row_off = h0;
     sg.own0 = r0 - h0;
     sg.own1 = r1 - h0;
+    // (a width that is not a multiple of 8: the rank's rows are re-pitched like a whole scene's, see produce_bands in api.cu)
+    const bool repitch = (cols % 8) != 0 && cols >= 512 && ctx->repitch && !ctx->force_exact;
+    const uint64_t pitch = repitch ? ((cols + 7) & ~uint64_t(7)) : 0;
     for (int b = 0; b < 2; ++b) {
         BandWs& w = ctx->band[b];
         const uint16_t* dn = (const uint16_t*)ins[b]->data;
-        if (ins[b]->location == SARPRO_LOC_HOST) {
+        if (repitch) {
+            RC(reserve(ctx, w.dn_pad, std::max<size_t>(rows * pitch * 2, 16)));
+            if (ins[b]->location == SARPRO_LOC_HOST) {
+                CU(cudaMemcpy2DAsync(w.dn_pad.p, pitch * 2, ins[b]->data, cols * 2, cols * 2, rows, cudaMemcpyHostToDevice, ctx->stream));
+                ctx->timing.h2d_bytes += rows * cols * 2;
+                KL(launch_pad_cols((uint16_t*)w.dn_pad.p, (uint32_t)rows, (uint32_t)cols, (uint32_t)pitch, ctx->stream));
+            } else {
+                KL(launch_repitch(dn, (uint16_t*)w.dn_pad.p, (uint32_t)rows, (uint32_t)cols, (uint32_t)pitch, ctx->sm_count, ctx->stream));
+            }
+            dn = (const uint16_t*)w.dn_pad.p;
+            w.pitch = pitch;
+        } else if (ins[b]->location == SARPRO_LOC_HOST) {
             RC(reserve(ctx, w.dn, rows * cols * 2));
             CU(cudaMemcpyAsync(w.dn.p, ins[b]->data, rows * cols * 2, cudaMemcpyHostToDevice, ctx->stream));
             ctx->timing.h2d_bytes += rows * cols * 2;
@@ -460,7 +475,8 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
             HResizeArgs a{};
             a.src = jobs[b].dn;
             a.src_rows = (uint32_t)rows;
-            a.src_cols = (uint32_t)cols;
+            a.src_cols = (uint32_t)(w.pitch ? w.pitch : cols);
+            a.src_width = (uint32_t)cols;
             a.lut = (const uint16_t*)w.lut.p;
             a.plan = (const PlanDev*)w.plan_dev.p;
             a.remap = nullptr;
