@@ -187,17 +187,15 @@ __device__ __forceinline__ float f32_split_log2(float x, int* e) {
     *e = (int)(b >> 23) - 127;
     return __log2f(__uint_as_float((b & 0x7fffffu) | 0x3f800000u));
 }
-// returns true and the index when the shortcut decides; n = number of edges (indices 0..n)
-__device__ __forceinline__ bool f32_guarded_index(const F32Guard& gd, int e, float lg, uint32_t n, uint32_t top, uint32_t* idx) {
+// Returns true and the index when the shortcut decides. The reference's index is clamp(floor(t*), 0, top) for the exact
+// position t* (stat bins: top = 4095 with n = 4096; levels: top = n). With |t - t*| <= E < guard, a fraction of t that keeps
+// `guard` away from both integers puts t* strictly inside (floor(t), floor(t) + 1): floor(t*) == floor(t), in range or not.
+__device__ __forceinline__ bool f32_guarded_index(const F32Guard& gd, int e, float lg, uint32_t top, uint32_t* idx) {
     const float d = __fadd_rn((float)(e - gd.e0), __fsub_rn(lg, gd.f0));
     const float t = __fmul_rn(d, gd.scale);
-    const float nf = (float)n;
     const float fl = floorf(t), fr = t - fl; // exact
-    // branch-free: below the range / above it / inside with the fraction clear of both integers
-    const bool lo = t < -gd.guard, hi = t > nf + gd.guard;
-    const bool in = (fr >= gd.guard) & (fr <= 1.0f - gd.guard) & (t >= 0.0f) & (fl < nf);
-    *idx = lo ? 0u : (hi ? top : (uint32_t)(int)fl);
-    return lo | hi | in;
+    *idx = (uint32_t)min(max((int)fl, 0), (int)top); // (the conversion saturates)
+    return fabsf(fr - 0.5f) <= 0.5f - gd.guard;      // false for NaN and for |t| >= 2^23 (fr == 0)
 }
 
 // ---- pass 2: 4096-bin histogram over [min_db, max_db] + mean / M2 accumulators -----------------------
@@ -241,7 +239,7 @@ __global__ void __launch_bounds__(256) k_f32_hist4096(F32Src src, uint64_t n, F3
                     const float lg = f32_split_log2(x, &e);
                     const float rel = __fsub_rn(3.0102999566f * __fadd_rn((float)e, lg), h.min_db[o]);
                     uint32_t idx;
-                    if (f32_guarded_index(h.guard[o], e, lg, 4096u, 4095u, &idx)) atomicAdd(&s_hist[o * 4096 + idx], 1u);
+                    if (f32_guarded_index(h.guard[o], e, lg, 4095u, &idx)) atomicAdd(&s_hist[o * 4096 + idx], 1u);
                     else todo |= 1u << k;
                     r1 += rel;
                     r2 += rel * rel;
@@ -344,15 +342,14 @@ __global__ void __launch_bounds__(256) k_f32_quantize(F32Src src, uint64_t n, F3
             // samples the guard did not decide, one per iteration: the slow path is issued once per vector, not once per sample
             uint32_t todo = 0, valid = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 8; ++k) { // branch-free: every lane evaluates, invalid samples are masked afterwards
                 const float x0 = s[o][k];
-                q[k] = 0;
-                if ((uint32_t)k < c && x0 >= qa.valid_thresh) {
-                    valid |= 1u << k;
-                    int e;
-                    const float lg = f32_split_log2(x0, &e);
-                    if (!f32_guarded_index(qa.guard[o], e, lg, qa.n_levels, qa.n_levels, &q[k])) todo |= 1u << k;
-                }
+                const bool ok = (uint32_t)k < c && x0 >= qa.valid_thresh;
+                int e;
+                const float lg = f32_split_log2(x0, &e);
+                const bool decided = f32_guarded_index(qa.guard[o], e, lg, qa.n_levels, &q[k]);
+                valid |= (ok ? 1u : 0u) << k;
+                todo |= ((ok && !decided) ? 1u : 0u) << k;
             }
             while (todo) {
                 const int k = __ffs((int)todo) - 1;

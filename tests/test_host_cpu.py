@@ -191,12 +191,8 @@ def test_f32_guard_bound_holds_under_worst_case_log2_error(lib_built, low, rng, 
         t = (d * np.float32(sc.value)).astype(np.float32)
         fl = np.floor(t)
         fr = (t - fl).astype(np.float32)
-        idx = np.full(v.shape, -1, np.int64)
-        idx[t < -g] = 0
-        idx[t > np.float32(n) + g] = n
-        ok = (fr >= g) & (fr <= np.float32(1) - g) & (fl >= 0) & (fl < n) & (idx < 0)
-        idx[ok] = fl[ok].astype(np.int64)
-        dec = idx >= 0
+        dec = np.abs(fr - np.float32(0.5)) <= np.float32(0.5) - g   # the device's test: the fraction is clear of both integers
+        idx = np.clip(fl.astype(np.int64), 0, n)                   # ... and then clamp(floor(t), 0, top) is the index
         assert np.array_equal(idx[dec], exact[dec]), int((idx[dec] != exact[dec]).sum())
         accepted = int(dec[:400_000].sum())
     assert accepted > 0.5 * 400_000
