@@ -262,3 +262,45 @@ def test_read_lanczos_is_a_normalised_low_pass():
     assert float(out.std()) < float(a.std())
     ident = O.read_band_resampled(a, 420, 300, O.RESAMPLE_LANCZOS)     # same shape: the kernel collapses to the sample itself
     assert np.allclose(ident, a, rtol=1e-5, atol=1e-3)
+
+
+# ---- adversarial inputs for the restated fast_image_resize Lanczos (parity unpinned: these are the properties any faithful
+#      implementation of the crate's fixed-point scheme must have, plus two independent opinions: the numpy re-derivation and Pillow)
+@pytest.mark.parametrize("in_w,out_w", [(16, 3), (97, 96), (1000, 7), (2048, 300), (25000, 2048), (4099, 512), (9, 8)])
+def test_lanczos_adversarial_rows(in_w, out_w):
+    from PIL import Image
+    rows = 6
+
+    def both(img, dtype):
+        fn = O.resize_u8_image if dtype == np.uint8 else O.resize_u16_image
+        got = fn(img.astype(dtype), out_w, rows)
+        assert np.array_equal(got, R.resize_lanczos3(img.astype(dtype), out_w, rows)), "oracle != numpy re-derivation"
+        return got
+
+    for dtype, top in ((np.uint8, 255), (np.uint16, 65535)):
+        # constants survive exactly (the quantised taps of every window sum close enough to 2^p), including the clamp ends
+        for c in (0, 1, top // 2, top - 1, top):
+            got = both(np.full((rows, in_w), c, np.int64), dtype)
+            assert (got == c).all(), (dtype.__name__, c, np.unique(got))
+        # impulses (negative lobes must clamp at 0, never wrap), at the edges and in the middle
+        for pos in (0, 1, in_w // 2, in_w - 2, in_w - 1):
+            img = np.zeros((rows, in_w), np.int64)
+            img[:, pos] = top
+            got = both(img, dtype)
+            assert got.max() <= top and got.min() >= 0
+            assert got[0].sum() > 0 or in_w > 40 * out_w   # the impulse shows up unless its tap weight rounds to nothing
+            assert (got == got[0]).all()                   # rows are independent and identical
+        # alternating columns / a step: the worst case for overshoot; the clamp must hold both ends
+        alt = np.tile(np.array([0, top], np.int64), in_w // 2 + 1)[:in_w][None, :].repeat(rows, 0)
+        step = np.where(np.arange(in_w) < in_w // 2, 0, top)[None, :].repeat(rows, 0)
+        for img in (alt, step):
+            got = both(img, dtype)
+            assert got.min() >= 0 and got.max() <= top
+        got = both(step, dtype)[0]
+        assert got[0] == 0 and got[-1] == top                # far from the edge the step is flat
+        if dtype == np.uint8:
+            # third opinion on the same inputs: Pillow (same windows and weights, fixed 22-bit precision)
+            for img in (alt, step):
+                a = O.resize_u8_image(img.astype(np.uint8), out_w, rows)
+                p = np.asarray(Image.fromarray(img.astype(np.uint8), "L").resize((out_w, rows), Image.LANCZOS))
+                assert np.abs(a.astype(int) - p.astype(int)).max() <= 2
