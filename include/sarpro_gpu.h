@@ -333,6 +333,11 @@ int sarpro_plan_kind_from_dn_histogram(const uint64_t* hist65536, int bit_depth,
 int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t out_size, size_t max_span, size_t strip_ntiles,
                                   uint8_t* out_direct, uint8_t* out_replay);
 
+/* Test hook (host only): one row of u16 samples through the downsample-on-read tables the kernels use (plan_read.cpp: spans and
+ * weights of GDAL's Average / Lanczos resampling, see sarpro_read_band_resampled), accumulated in f64 in the kernels' order.
+ * out has out_size f32 samples. No GPU needed: the CPU tests compare it with the oracle's restatement. */
+int sarpro_read_row_plan_check(const uint16_t* samples, size_t in_size, size_t out_size, int alg, float* out);
+
 /* Test hook (host only): parameters and error bound of the guarded direct index the general f32 kernels use for the indices
  * that are linear in dB, trunc((10 log10 v - low_db) / range_db * n) (stat bins autoscale.rs:113-116; quantised levels with
  * gamma == 1, :440-442 / :649-651 / :732-734). The device evaluates t = ((e - e0) + (lg2(m) - f0)) * scale in fp32 (v = m 2^e,

@@ -136,6 +136,7 @@ SYMBOLS = {
     "sarpro_plan_from_present_list": (_I, [_P, _P, C.c_uint32, _I, _I, C.POINTER(Stats), _P]),
     "sarpro_plan_on_device": (_I, [_P, _P, _I, _I, _I, C.POINTER(Stats), _P, _P]),
     "sarpro_plan_kind_from_dn_histogram": (_I, [_P, _I, _I, _I, C.POINTER(Stats), _P, _P]),
+    "sarpro_read_row_plan_check": (_I, [_P, _SZ, _SZ, _I, _P]),
     "sarpro_f32_guard_params": (_I, [C.c_double, C.c_double, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "sarpro_lanczos_row_plan_check": (_I, [_P, _SZ, _SZ, _SZ, _SZ, _P, _P]),

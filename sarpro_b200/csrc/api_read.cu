@@ -21,6 +21,35 @@ int sarpro_read_dims_for_target(size_t cols, size_t rows, size_t target, size_t*
     return SARPRO_OK;
 }
 
+int sarpro_read_row_plan_check(const uint16_t* samples, size_t in_size, size_t out_size, int alg, float* out) {
+    if (!samples || !out || in_size == 0 || out_size == 0 || out_size > in_size) return SARPRO_ERR_INVALID_ARGUMENT;
+    if (alg == SARPRO_RESAMPLE_AVERAGE) {
+        ReadAverageAxisHost ax;
+        build_read_average_axis(in_size, out_size, &ax);
+        for (size_t d = 0; d < out_size; ++d) { // k_read_average with one source row (wy == 1)
+            double total = 0.0, wsum = 0.0;
+            for (int x = ax.start[d]; x < ax.end[d]; ++x) {
+                const double w = x == ax.start[d] ? ax.w_first[d] : (x + 1 == ax.end[d] ? ax.w_last[d] : 1.0);
+                total += (double)samples[x] * w;
+                wsum += w;
+            }
+            out[d] = (float)(total / wsum);
+        }
+        return SARPRO_OK;
+    }
+    if (alg == SARPRO_RESAMPLE_LANCZOS) {
+        ReadLanczosAxisHost ax;
+        build_read_lanczos_axis(in_size, out_size, &ax);
+        for (size_t d = 0; d < out_size; ++d) { // k_read_conv_h, then the identity vertical pass of a one-row raster
+            double v = 0.0;
+            for (int k = 0; k < ax.count[d]; ++k) v += (double)samples[ax.start[d] + k] * ax.w[d * (size_t)ax.window + k];
+            out[d] = (float)v;
+        }
+        return SARPRO_OK;
+    }
+    return SARPRO_ERR_INVALID_ARGUMENT;
+}
+
 int sarpro_read_band_resampled(sarpro_ctx* ctx, const sarpro_band* in, size_t out_cols, size_t out_rows, int alg, float* out,
                                int out_location) {
     RC(begin_call(ctx));

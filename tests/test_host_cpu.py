@@ -221,3 +221,19 @@ def test_rust_wrapper_covers_the_c_abi():
                 called |= set(re.findall(r"\|g\| g\.([a-z0-9_]+)\(", line))
                 called |= set(re.findall(r"^\+\s+g\.([a-z0-9_]+)\(", line))
     assert called and called <= methods, called - methods
+
+
+@pytest.mark.parametrize("in_size,out_size", [(25000, 2048), (16000, 1311), (1000, 1000), (1000, 999), (4097, 512), (77, 3), (8192, 2048)])
+@pytest.mark.parametrize("alg", [0, 1])
+def test_read_resample_tables_replay_the_oracle(lib_built, in_size, out_size, alg):
+    """Host logic of downsample-on-read (plan_read.cpp: the spans and weights the kernels read): one row through the product's
+    tables, accumulated like the kernels do, equals the oracle's restatement of GDAL's resampling bit for bit."""
+    if alg == 1 and in_size > 6 * out_size:
+        pytest.skip("the reader only picks Lanczos below a reduction of 4")
+    rng = np.random.default_rng(in_size + out_size)
+    row = rng.integers(0, 65536, in_size).astype(np.uint16)
+    row[: in_size // 7] = 65535
+    got = np.zeros(out_size, np.float32)
+    assert _ffi.lib().sarpro_read_row_plan_check(row.ctypes.data, in_size, out_size, alg, got.ctypes.data) == 0
+    ref = O.read_band_resampled(row[None, :], out_size, 1, alg)[0]
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), int((got != ref).sum())
