@@ -403,7 +403,7 @@ int sarpro_pipeline_synrgb_sharded(sarpro_ctx* ctx, const sarpro_band* b1, const
     // (everything after its pass A) runs on the side stream, so its two collectives, its planner and its CLAHE statistics
     // overlap band 1's pass A, and its pass B starts while band 1's chain is still at its collectives; band 1's persistent
     // pass-B CTAs then fill the SMs band 0's leave. The collectives are issued in the same order on every rank (program
-    // order: band 0's two, then band 1's two), which is what NCCL needs of one communicator used from two streams.
+    // order: both bands' first one, then both bands' second one), which is what NCCL needs of one communicator used from two streams.
     const size_t esz = 1;
     const size_t n_out = g.oc * g.orr;
     HResizeArgs args[2];
