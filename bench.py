@@ -395,7 +395,7 @@ def main():
                 line["parity_ok"] = parity_ok
                 line["batch_mode"] = batch
         if not sharded and rank == 0 and (rows, cols) == (ROWS, COLS) and not args.no_cpu_baseline:
-            # the real drop-in boundary of the Rust caller: host Array2<f32> bands (gdal.rs:123) -> 2x the upload + the f32 -> DN bridge
+            # the real drop-in boundary of the Rust caller: host Array2<f32> bands (gdal.rs:123); h2d_bytes is what crossed PCIe
             vv_f = torch.empty((rows, cols), dtype=torch.float32).pin_memory()
             vh_f = torch.empty((rows, cols), dtype=torch.float32).pin_memory()
             vv_f.copy_(vv.to(torch.int32).bitwise_and_(0xffff))
@@ -403,7 +403,9 @@ def main():
             f_ms, f_h2d, f_d2h = timed_e2e(lambda: ctx.process_synrgb_jpeg(vv_f.numpy(), vh_f.numpy(), strategy, target, True, out=out_h), 2)
             line["e2e_f32_boundary"] = {"value": round(rows * cols / (f_ms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "ms_per_step": round(f_ms, 3),
                                         "h2d_bytes_per_step": f_h2d, "d2h_bytes_per_step": f_d2h,
-                                        "input": "pinned host f32 bands (the reference's Array2<f32> boundary, gdal.rs:123)"}
+                                        "input": "pinned host f32 bands (the reference's Array2<f32> boundary, gdal.rs:123)" +
+                                                 ("; narrowed to u16 DNs by the library's host threads chunk by chunk while the previous chunk uploads"
+                                                  if f_h2d < rows * cols * 8 else "; uploaded as f32 (host narrowing off or slower than PCIe on this host)")}
             del vv_f, vh_f
 
     # ====================================================================================================================

@@ -346,6 +346,22 @@ int sarpro_read_row_plan_check(const uint16_t* samples, size_t in_size, size_t o
 int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float min_v, float max_v, int* e0, float* f0, float* scale,
                             float* guard);
 
+/* Test hook (host only, not thread-safe against concurrent calls of the library): the threshold tables of the general f32 path
+ * (smallest f32 reaching each stat bin, kind = -1, autoscale.rs:113-116; or each quantised level: kind 0 = autoscale.rs:440-442,
+ * 1 = the Tamed u8 levels :732-734, 2 = the CLAHE bins :585-587), built twice: the way the pipelines build them (boundaries
+ * placed analytically where the f64 expression provably cannot disagree, plan_f32.cpp) and by bracketing every boundary with
+ * the reference's own f64 expression. Returns the table length (4096 or n_levels + 1); n_analytic = entries placed
+ * analytically, n_mismatch = entries whose bit patterns differ (must be 0); edges_out (optional) receives the table. */
+int sarpro_f32_edges_check(int kind, double low_db, double high_db, double gamma, uint32_t n_levels, float min_v, float max_v,
+                           uint32_t* n_analytic, uint32_t* n_mismatch, float* edges_out);
+
+/* Test hook (host only): the host-side narrowing the pipelines apply to large f32 HOST rasters on their way to the device
+ * (the reference's boundary is the f32 raster GDAL made of a u16 band, gdal.rs:123; narrowing halves the PCIe bytes). dst[i]
+ * = the DN of src[i]: 0 for samples that are not valid (negative, NaN, <= -50 dB: pipeline.rs:19-22), the sample itself
+ * otherwise. u16_valued = 0 when some valid sample is not a whole number <= 65535: such rasters are uploaded as f32 and take
+ * the general path (dst is then unspecified). Same rule as the device kernel that narrows f32 DEVICE rasters. */
+int sarpro_narrow_f32_check(const float* src, size_t n, uint16_t* dst, int* u16_valued);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,4 +165,6 @@ extern "C" {
     pub fn sarpro_lanczos_row_plan_check(samples: *const u8, in_size: usize, out_size: usize, max_span: usize, strip_ntiles: usize, out_direct: *mut u8, out_replay: *mut u8) -> c_int;
     pub fn sarpro_read_row_plan_check(samples: *const u16, in_size: usize, out_size: usize, alg: c_int, out: *mut f32) -> c_int;
     pub fn sarpro_f32_guard_params(low_db: f64, range_db: f64, n: u32, min_v: f32, max_v: f32, e0: *mut c_int, f0: *mut f32, scale: *mut f32, guard: *mut f32) -> c_int;
+    pub fn sarpro_f32_edges_check(kind: c_int, low_db: f64, high_db: f64, gamma: f64, n_levels: u32, min_v: f32, max_v: f32, n_analytic: *mut u32, n_mismatch: *mut u32, edges_out: *mut f32) -> c_int;
+    pub fn sarpro_narrow_f32_check(src: *const f32, n: usize, dst: *mut u16, u16_valued: *mut c_int) -> c_int;
 }

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsarpro_gpu.so")
-SOURCES = ["api.cu", "api_f32.cu", "api_batch.cu", "api_jpeg.cu", "api_read.cu", "kernels_read.cu", "plan_read.cpp", "comm.cu", "kernels_dn.cu", "kernels_resize.cu", "kernels_hmma.cu", "kernels_plan.cu", "kernels_small.cu", "kernels_f32.cu", "plan.cpp", "plan_f32.cpp"]
-HEADERS = ["ctx.h", "kernels.h", "plan.h", "common.cuh", "clahe_exact.cuh", os.path.join("..", "..", "include", "sarpro_gpu.h")]
+SOURCES = ["api.cu", "api_f32.cu", "api_batch.cu", "api_jpeg.cu", "api_read.cu", "kernels_read.cu", "plan_read.cpp", "comm.cu", "kernels_dn.cu", "kernels_resize.cu", "kernels_hmma.cu", "kernels_plan.cu", "kernels_small.cu", "kernels_f32.cu", "plan.cpp", "plan_f32.cpp", "narrow.cpp"]
+HEADERS = ["ctx.h", "kernels.h", "plan.h", "host_pool.h", "common.cuh", "clahe_exact.cuh", os.path.join("..", "..", "include", "sarpro_gpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

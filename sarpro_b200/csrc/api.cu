@@ -848,8 +848,65 @@ int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint
 // ---- inputs ----------------------------------------------------------------------------------------
 // Brings band `in` (optionally op(in, in2)) to a u16 DN raster on the device. Returns SARPRO_ERR_INTERNAL + flag
 // when the samples are not u16-valued (general f32 path).
+// Narrowing upload of a large f32 host raster (see stage_band). Returns 0 when every chunk is queued on the copy stream,
+// 1 when the raster is not u16-valued (copy stream drained, nothing of this band left in flight), < 0 on errors.
+static int narrow_and_stream(sarpro_ctx* ctx, int b, const sarpro_band* in, const uint16_t** dn_out) {
+    BandWs& w = ctx->band[b];
+    const uint64_t n = in->rows * in->cols;
+    RC(ensure_upload_stream(ctx));
+    const uint64_t per = ((in->rows + sarpro_ctx::kUploadChunks - 1) / sarpro_ctx::kUploadChunks + 127) & ~uint64_t(127);
+    const size_t slot_bytes = per * in->cols * 2;
+    if (ctx->narrow_ring_bytes < slot_bytes) {
+        CU(cudaStreamSynchronize(ctx->stream_up));
+        for (int s = 0; s < 2; ++s) {
+            if (ctx->narrow_ring[s]) { cudaFreeHost(ctx->narrow_ring[s]); ctx->narrow_ring[s] = nullptr; }
+            ctx->ring_busy[s] = false;
+        }
+        ctx->narrow_ring_bytes = 0;
+        for (int s = 0; s < 2; ++s) {
+            CU(cudaHostAlloc(&ctx->narrow_ring[s], slot_bytes, cudaHostAllocDefault));
+            if (!ctx->ev_ring[s]) CU(cudaEventCreateWithFlags(&ctx->ev_ring[s], cudaEventDisableTiming));
+        }
+        ctx->narrow_ring_bytes = slot_bytes;
+    }
+    RC(reserve(ctx, w.dn, n * 2));
+    sarpro_ctx::StreamedBand& sb = ctx->streamed[b];
+    sb.n_chunks = 0;
+    sb.ev0 = b * sarpro_ctx::kUploadChunks;
+    ctx->upload_in_flight = true;
+    const float* src = (const float*)in->data;
+    int slot = 0;
+    double conv_s = 0.0;
+    for (uint64_t r = 0; r < in->rows; r += per, slot ^= 1) {
+        const uint64_t r1 = std::min<uint64_t>(in->rows, r + per), cnt = (r1 - r) * in->cols;
+        if (ctx->ring_busy[slot]) { CU(cudaEventSynchronize(ctx->ev_ring[slot])); ctx->ring_busy[slot] = false; }
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool dn_valued = narrow_f32_to_dn(src + r * in->cols, (uint16_t*)ctx->narrow_ring[slot], cnt, ctx->valid_thresh);
+        conv_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (!dn_valued) {
+            CU(cudaStreamSynchronize(ctx->stream_up)); // the chunks already queued must not land behind the f32 path's writes
+            ctx->ring_busy[0] = ctx->ring_busy[1] = false;
+            return 1;
+        }
+        CU(cudaMemcpyAsync((char*)w.dn.p + r * in->cols * 2, ctx->narrow_ring[slot], cnt * 2, cudaMemcpyHostToDevice, ctx->stream_up));
+        CU(cudaEventRecord(ctx->ev_chunk[sb.ev0 + sb.n_chunks], ctx->stream_up));
+        CU(cudaEventRecord(ctx->ev_ring[slot], ctx->stream_up));
+        ctx->ring_busy[slot] = true;
+        sb.row_end[sb.n_chunks++] = (uint32_t)r1;
+    }
+    ctx->timing.h2d_bytes += n * 2;
+    ctx->narrowed_bands++;
+    // Narrowing only pays while the host threads read the f32 raster faster than PCIe would have carried it (~55 GB/s of pinned
+    // host-to-device bandwidth on this platform, profiles/r02w_h2d_probe.log): a host that cannot keep that up goes back to
+    // the f32 upload for the following calls of this context.
+    ctx->narrow_gbs = conv_s > 0.0 ? (double)n * 4.0 / conv_s * 1e-9 : 0.0;
+    if (ctx->narrow_upload == 1 && ctx->narrow_gbs < 60.0) ctx->narrow_upload = 0;
+    *dn_out = (const uint16_t*)w.dn.p;
+    return 0;
+}
+
 int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band* in2, int op, const uint16_t** dn_out,
-               bool* integral) {
+               bool* integral, bool may_stream) {
     BandWs& w = ctx->band[b];
     const uint64_t n = in->rows * in->cols;
     *integral = true;
@@ -858,7 +915,7 @@ int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band*
         RC(reserve(ctx, w.dn, n * 2));
         ctx->timing.h2d_bytes += n * 2;
         *dn_out = (const uint16_t*)w.dn.p;
-        if (ctx->stream_upload && b < 2 && n * 2 >= (64u << 20) && in->rows >= 1024) {
+        if (may_stream && ctx->stream_upload && b < 2 && n * 2 >= (64u << 20) && in->rows >= 1024) {
             // Streamed upload: row chunks on the copy stream, an event per chunk. Pass A consumes the chunks as they land and
             // the other band's plan / pass B run beside this band's upload (PCIe is the bottleneck of a call with host
             // rasters: 29 of 31 ms at C3). The previous call on this context ended with its streams drained, so nothing still
@@ -898,6 +955,16 @@ int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band*
     }
     if (in->dtype != SARPRO_DT_F32 || (op >= 0 && in2->dtype != SARPRO_DT_F32))
         return fail(ctx, SARPRO_ERR_INVALID_ARGUMENT, "polarization ops take two f32 bands or two u16 DN bands (ops.rs:4-44)");
+    if (may_stream && op < 0 && in->location == SARPRO_LOC_HOST && ctx->narrow_upload && ctx->stream_upload && b < 2 && n * 2 >= (64u << 20) &&
+        in->rows >= 1024) {
+        // The reference's boundary: the f32 raster GDAL made of a u16 band (gdal.rs:123). PCIe is the whole end-to-end time of
+        // such a call, so the host threads narrow each row chunk to DNs (narrow.cpp, the rule of k_f32_to_dn) into one of two
+        // pinned slots while the previous chunk is on the wire, and the chunks then take the streamed path of a u16 raster: half
+        // the bytes, pass A per chunk. A chunk with a sample that is not a DN ends the attempt: the raster goes up as f32 below.
+        int rc = narrow_and_stream(ctx, b, in, dn_out);
+        if (rc <= 0) return rc;          // 0: queued; < 0: error
+        ctx->streamed[b].n_chunks = 0;   // 1: not u16-valued
+    }
     const float* fa = (const float*)in->data;
     const float* fb = op >= 0 ? (const float*)in2->data : nullptr;
     if (in->location == SARPRO_LOC_HOST) {
@@ -1098,7 +1165,8 @@ int produce_bands(sarpro_ctx* ctx, const sarpro_band* const* ins, const sarpro_b
             w.pitch = pitch;
             continue;
         }
-        RC(stage_band(ctx, b, ins[b], ins2[b], ops[b], &jobs[b].dn, &integral[b]));
+        // (a raster that still has to be re-pitched on the device is read by that kernel at once: no streamed chunks)
+        RC(stage_band(ctx, b, ins[b], ins2[b], ops[b], &jobs[b].dn, &integral[b], !want_pad[b]));
         if (want_pad[b] && integral[b]) {
             RC(reserve(ctx, w.dn_pad, rows * pitch * 2));
             KL(launch_repitch(jobs[b].dn, (uint16_t*)w.dn_pad.p, (uint32_t)rows, (uint32_t)cols, (uint32_t)pitch, ctx->sm_count, ctx->stream));
@@ -1231,6 +1299,7 @@ int sarpro_ctx_create(sarpro_ctx** out, int device_id) {
     if (const char* v = getenv("SARPRO_HOST_PLAN")) ctx->host_plan = atoi(v);
     if (const char* v = getenv("SARPRO_F32_NO_GUARD")) ctx->f32_no_guard = atoi(v);
     if (const char* v = getenv("SARPRO_STREAM_UPLOAD")) ctx->stream_upload = atoi(v);
+    if (const char* v = getenv("SARPRO_NARROW_UPLOAD")) ctx->narrow_upload = atoi(v);
     if (const char* v = getenv("SARPRO_REPITCH")) ctx->repitch = atoi(v);
     if (const char* v = getenv("SARPRO_HIST_VARIANT")) ctx->hist_variant = atoi(v);
     if (const char* v = getenv("SARPRO_FORCE_EXACT")) ctx->force_exact = atoi(v);
@@ -1268,6 +1337,10 @@ void sarpro_ctx_destroy(sarpro_ctx* ctx) {
     release(ctx->gather);
     release(ctx->units_by_row);
     if (ctx->stream_up) { cudaStreamSynchronize(ctx->stream_up); cudaStreamDestroy(ctx->stream_up); }
+    for (int s = 0; s < 2; ++s) {
+        if (ctx->narrow_ring[s]) cudaFreeHost(ctx->narrow_ring[s]);
+        if (ctx->ev_ring[s]) cudaEventDestroy(ctx->ev_ring[s]);
+    }
     for (auto& ev : ctx->ev_up)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_chunk)
@@ -1349,6 +1422,34 @@ int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float mi
     if (!e0 || !f0 || !scale || !guard) return SARPRO_ERR_INVALID_ARGUMENT;
     f32_guard(true, low_db, range_db, n, min_v, max_v, e0, f0, scale, guard);
     return SARPRO_OK;
+}
+
+int sarpro_narrow_f32_check(const float* src, size_t n, uint16_t* dst, int* u16_valued) {
+    if ((n && (!src || !dst)) || !u16_valued) return SARPRO_ERR_INVALID_ARGUMENT;
+    *u16_valued = narrow_f32_to_dn(src, dst, n, valid_threshold()) ? 1 : 0;
+    return SARPRO_OK;
+}
+
+int sarpro_f32_edges_check(int kind, double low_db, double high_db, double gamma, uint32_t n_levels, float min_v, float max_v,
+                           uint32_t* n_analytic, uint32_t* n_mismatch, float* edges_out) {
+    if (!n_analytic || !n_mismatch || !(min_v > 0.f) || !(max_v >= min_v) || kind < -1 || kind > 2) return SARPRO_ERR_INVALID_ARGUMENT;
+    if (kind >= 0 && (n_levels == 0 || n_levels > 65535u)) return SARPRO_ERR_INVALID_ARGUMENT;
+    std::vector<float> fast, slow;
+    auto build = [&](std::vector<float>* e) {
+        if (kind < 0) build_stat_edges(min_v, max_v, e);
+        else build_level_edges((LevelKind)kind, low_db, high_db, gamma, n_levels, min_v, max_v, e, nullptr, nullptr);
+    };
+    const uint64_t h0 = f32_edges_analytic_hits();
+    build(&fast);
+    *n_analytic = (uint32_t)(f32_edges_analytic_hits() - h0);
+    f32_edges_set_analytic(false);
+    build(&slow);
+    f32_edges_set_analytic(true);
+    uint32_t bad = fast.size() != slow.size();
+    for (size_t i = 0; i < fast.size() && i < slow.size(); ++i) bad += std::memcmp(&fast[i], &slow[i], 4) != 0;
+    *n_mismatch = bad;
+    if (edges_out) std::memcpy(edges_out, fast.data(), fast.size() * 4);
+    return (int)fast.size();
 }
 
 int sarpro_plan_from_present_list(const uint32_t* blocks, const uint32_t* pairs, uint32_t cap, int bit_depth, int strategy,

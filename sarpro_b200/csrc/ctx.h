@@ -193,6 +193,16 @@ struct sarpro_ctx {
     bool upload_in_flight = false;              // chunks were queued in a call that has not completed (error path): drain first
     int repitch = 1;                            // SARPRO_REPITCH=0: rasters of odd widths stay on the generic kernels (measurement)
     int stream_upload = 1;                      // SARPRO_STREAM_UPLOAD=0: one copy on the main stream (measurement)
+    // Host-side narrowing of large f32 host rasters (narrow.cpp): two pinned staging slots of one row chunk of DNs each; the
+    // host threads fill one while the other is on the wire. ev_ring[s]: the copy out of slot s has completed.
+    int narrow_upload = 1;                      // SARPRO_NARROW_UPLOAD=0: f32 rasters are uploaded as f32 and narrowed by k_f32_to_dn;
+                                                // =2: always narrow; 1 (default): until the host proves slower than the f32 upload
+    double narrow_gbs = 0.0;                    // f32 source bytes the host threads narrowed per second, last band (GB/s)
+    void* narrow_ring[2] = {nullptr, nullptr};
+    size_t narrow_ring_bytes = 0;
+    cudaEvent_t ev_ring[2] = {nullptr, nullptr};
+    bool ring_busy[2] = {false, false};
+    uint64_t narrowed_bands = 0;                // bands that took the narrowing path (tests)
     sarpro::DevBuf units_by_row;                // the work units of pass A ordered by last row
     std::vector<uint32_t> units_r1;             // their last rows (ascending), host copy
     // u8 results of the last pipeline call that are still in the context's device buffers: [0] interleaved RGB, [1] / [2] the

@@ -149,4 +149,11 @@ void f32_guard(bool on, double low_db, double range_db, uint32_t n, float min_v,
 //   ClaheBin      : round(clamp((clip(db)-low)/range, 0, 1) * 255)                            autoscale.rs:585-587, 263
 void build_level_edges(LevelKind kind, double low, double high, double gamma, uint32_t n_levels, float min_v, float max_v,
                        std::vector<float>* edges, uint32_t* level_of_min, uint32_t* level_of_max);
+// Both builders place most boundaries analytically (one pow, plan_f32.cpp: analytic_threshold) and search only the rest.
+// Test hook: on == false builds every entry by search; hits = entries placed analytically since process start.
+void f32_edges_set_analytic(bool on);
+uint64_t f32_edges_analytic_hits();
+// narrow.cpp: f32 samples of a u16-valued raster -> their DN with the rule of k_f32_to_dn (not >= valid_thresh -> 0), on the
+// library's host threads. false: some valid sample is not a whole number <= 65535 (dst is then unspecified).
+bool narrow_f32_to_dn(const float* src, uint16_t* dst, size_t n, float valid_thresh);
 } // namespace sarpro

@@ -2,12 +2,12 @@
 // Every index the reference computes from a sample is monotone in the sample value; the boundaries are
 // located here by evaluating the reference's own f64 expression (same libm) on f32 bit patterns.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
-#include <functional>
 #include <limits>
-#include <thread>
 
+#include "host_pool.h"
 #include "plan.h"
 
 namespace sarpro {
@@ -57,17 +57,33 @@ uint32_t first_reaching(F&& level, uint32_t k, uint32_t lo, uint32_t hi, uint32_
     return hi;
 }
 
-template <typename F>
-void parallel_for(uint32_t n, F&& f) {
-    const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    if (n < 2048 || nt == 1) { f(0, n); return; }
-    std::vector<std::thread> th;
-    const uint32_t chunk = (n + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; ++t) {
-        const uint32_t a = t * chunk, b = std::min(n, a + chunk);
-        if (a < b) th.emplace_back([&, a, b] { f(a, b); });
-    }
-    for (auto& x : th) x.join();
+// ---- analytic thresholds ------------------------------------------------------------------------
+// For an index that is LINEAR in dB, idx(v) = trunc(q(v)), q(v) = (10 log10 v - low) / range * n, the real-valued position
+// of boundary k is v* = 10^((low + range k/n) / 10), and the threshold is the smallest f32 >= v* -- provided the reference's
+// f64 evaluation of q cannot land on the other side of k for the two f32 neighbours of v*. Its error against the real q is
+//   |q_f64(v) - q(v)| <= n/range * 2.4e-13 + n * 3.3e-16     (glibc log10 < 2 ulp, |dB| <= 400, one rounding each for the
+//                                                             product by 10, the subtraction, the quotient, the product by n)
+// while moving v by a relative m moves q by n/range * 10/ln 10 * m = n/range * 4.34 m. With m = 1e-9 (and range <= 1e4 dB)
+// the second exceeds the first by four orders of magnitude, and v* itself (exp(dB ln10/10): the rounded argument, |arg| < 90,
+// contributes 2e-14 relative, exp < 1 ulp) is known to ~3e-14: if both f32 neighbours of v* are at least m v* away from it, the f64 expression reaches k at
+// the upper one and not at the lower one, which is the definition of the threshold. f32 spacing is 6e-8..1.2e-7 relative, so
+// ~2 % of the boundaries fall within m of an f32 and take the search below instead. One exp replaces pow + two log10 + the
+// clamp arithmetic; tests/test_host_cpu.py compares whole tables of both methods.
+constexpr double kAnalyticMargin = 1e-9;
+constexpr double kLn10Over10 = 0.23025850929940457;
+constexpr double kAnalyticDbMargin = 1e-6;   // the boundary's f32 neighbours (<= 5.2e-7 dB away) must stay clear of the clip ends
+std::atomic<bool> g_analytic{true};          // test hook: tables by search only
+std::atomic<uint64_t> g_analytic_hits{0};
+inline bool analytic_threshold(double vstar, uint32_t lo, uint32_t hi, uint32_t* out) {
+    if (!(vstar > 0.0) || !(vstar < 3.0e38)) return false;
+    if (!(vstar > 1e-30)) return false;           // normal f32 only: neighbours are bit pattern +- 1
+    uint32_t b = bits_of((float)vstar);           // nearest f32
+    if ((double)float_of(b) < vstar) ++b;         // smallest f32 >= v* (positive floats are ordered like their bit patterns)
+    const double m = kAnalyticMargin * vstar;
+    if (!((double)float_of(b) - vstar >= m) || !(vstar - (double)float_of(b - 1) >= m)) return false;
+    if (b <= lo || b > hi) return false;          // outside the data range: let the search apply its own end rules
+    *out = b;
+    return true;
 }
 
 } // namespace
@@ -96,13 +112,20 @@ void build_stat_edges(float min_v, float max_v, std::vector<float>* edges) {
     };
     const uint32_t lo = bits_of(min_v), hi = bits_of(max_v);
     const uint32_t l_lo = level(lo), l_hi = level(hi);
+    // analytic boundaries (see analytic_threshold): the index is linear in dB over [min_db, max_db]
+    const bool analytic = g_analytic.load(std::memory_order_relaxed) && std::isfinite(span) && span >= kStatBins * kAnalyticDbMargin &&
+                          span <= 1e4 && std::fabs(min_db) <= 400.0 && std::fabs(max_db) <= 400.0;
     parallel_for(kStatBins - 1, [&](uint32_t a, uint32_t b) {
+        uint64_t hits = 0;
         for (uint32_t i = a; i < b; ++i) {
             const uint32_t k = i + 1;
             const double db = min_db + span * ((double)k / (double)kStatBins);
-            const uint32_t guess = bits_of((float)std::pow(10.0, db / 10.0));
-            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, guess, l_lo, l_hi));
+            const double vstar = std::exp(db * kLn10Over10);
+            uint32_t bits;
+            if (analytic && l_lo < k && k <= l_hi && analytic_threshold(vstar, lo, hi, &bits)) { (*edges)[k] = float_of(bits); ++hits; continue; }
+            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, bits_of((float)vstar), l_lo, l_hi));
         }
+        if (hits) g_analytic_hits.fetch_add(hits, std::memory_order_relaxed);
     });
 }
 
@@ -130,17 +153,35 @@ void build_level_edges(LevelKind kind, double low, double high, double gamma, ui
     const uint32_t l_lo = level(lo), l_hi = level(hi);
     if (level_of_min) *level_of_min = l_lo;
     if (level_of_max) *level_of_max = l_hi;
+    // analytic boundaries (see analytic_threshold) where the level is trunc of a quantity linear in dB: gamma == 1, not the
+    // CLAHE bins (a round), boundaries strictly inside the clip window (the top level of a window narrower than 1 dB, whose
+    // range was raised, and the level at high_clip itself go through the search)
+    const bool analytic = g_analytic.load(std::memory_order_relaxed) && kind != LevelKind::ClaheBin && gamma == 1.0 && std::isfinite(low) &&
+                          std::isfinite(high) && range <= 1e4 && std::fabs(low) <= 400.0 && std::fabs(high) <= 400.0 &&
+                          (kind != LevelKind::TamedLinearU8 || n_levels == 255);
     parallel_for(n_levels, [&](uint32_t a, uint32_t b) {
+        uint64_t hits = 0;
         for (uint32_t i = a; i < b; ++i) {
             const uint32_t k = i + 1;
             double frac = (kind == LevelKind::ClaheBin) ? ((double)k - 0.5) / 255.0 : (double)k / max_val;
             if (kind == LevelKind::Quantize && gamma != 1.0) frac = std::pow(frac, 1.0 / gamma);
             const double db = low + range * frac;
-            const uint32_t guess = bits_of((float)std::pow(10.0, db / 10.0));
-            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, guess, l_lo, l_hi));
+            const double vstar = std::exp(db * kLn10Over10);
+            uint32_t bits;
+            if (analytic && l_lo < k && k <= l_hi && db - kAnalyticDbMargin >= low && db + kAnalyticDbMargin <= high &&
+                analytic_threshold(vstar, lo, hi, &bits)) {
+                (*edges)[k] = float_of(bits);
+                ++hits;
+                continue;
+            }
+            (*edges)[k] = float_of(first_reaching(level, k, lo, hi, bits_of((float)vstar), l_lo, l_hi));
         }
+        if (hits) g_analytic_hits.fetch_add(hits, std::memory_order_relaxed);
     });
 }
+
+void f32_edges_set_analytic(bool on) { g_analytic.store(on); }
+uint64_t f32_edges_analytic_hits() { return g_analytic_hits.load(); }
 
 void f32_guard(bool on, double low_db, double range_db, uint32_t n, float min_v, float max_v, int* e0, float* f0, float* scale,
                float* guard) {

@@ -660,6 +660,57 @@ def test_streamed_upload_gives_the_same_bytes(strategy, monkeypatch):
     assert np.array_equal(dev.rgb, outs[0])
 
 
+def test_large_f32_host_rasters_are_narrowed_on_the_host(monkeypatch):
+    """The reference's own boundary: host f32 rasters GDAL made of u16 bands (gdal.rs:123). Rasters of 64 MB of DNs and more
+    are narrowed to u16 by the library's host threads, chunk by chunk into pinned staging while the previous chunk uploads, and
+    then take the streamed path (half the PCIe bytes). The result must equal the oracle on the same f32 rasters, the u16-host
+    path and the f32 upload with the device-side bridge (SARPRO_NARROW_UPLOAD=0) byte for byte, with invalid samples (NaN,
+    negatives, zeros) mixed in; a raster that is NOT u16-valued must be noticed wherever the odd sample sits and give the
+    bytes of the general path."""
+    from sarpro_b200.synth import synth_pair
+    rows, cols = 4200, 8192
+    vv, vh = synth_pair(rows, cols, point_targets=1e-4)
+    vv_f, vh_f = vv.astype(np.float32), vh.astype(np.float32)
+    vv_f[100:140, 3000:3300] = np.nan          # no-data block
+    vv_f[4100:, :50] = -7.0
+    vh_f[::977, ::13] = 0.0
+    vv_u = np.where(np.isfinite(vv_f) & (vv_f > 0), vv_f, 0).astype(np.uint16)
+    vh_u = vh_f.astype(np.uint16)
+    n = rows * cols
+    monkeypatch.setenv("SARPRO_NARROW_UPLOAD", "2")   # narrow whatever the host's speed (the default gives up on a slow host)
+    with S.Context(0) as c:
+        img = c.process_synrgb_jpeg(vv_f, vh_f, S.CLAHE, 1024, True)
+        assert c.timing().h2d_bytes == 2 * n * 2, c.timing().h2d_bytes     # both bands crossed PCIe as u16
+        rgb = img.rgb.copy()
+        again = c.process_synrgb_jpeg(vv_f, vh_f, S.CLAHE, 1024, True)     # the staging slots are reused
+        assert np.array_equal(again.rgb, rgb)
+        from_u16 = c.process_synrgb_jpeg(vv_u, vh_u, S.CLAHE, 1024, True).rgb.copy()
+        mb = c.process_multiband_tiff(vv_f, vh_f, S.U16, S.ROBUST, 900, False)
+        mb_n = np.stack([mb.gray, mb.gray_band2]).copy()
+        # not u16-valued: one half-integer sample in the last chunk of the second band, then in the very first sample
+        odd = []
+        for pos in ((rows - 3, cols - 5), (0, 0)):
+            w = vh_f.copy()
+            w[pos] = 1234.5
+            odd.append(c.process_synrgb_jpeg(vv_f, w, S.ROBUST, 1024, True).rgb.copy())
+            assert c.timing().h2d_bytes == n * 2 + n * 4                   # VV as DNs, VH as f32 after the refused attempt
+    monkeypatch.setenv("SARPRO_NARROW_UPLOAD", "0")
+    with S.Context(0) as c:
+        plain = c.process_synrgb_jpeg(vv_f, vh_f, S.CLAHE, 1024, True)
+        assert c.timing().h2d_bytes == 2 * n * 4
+        assert np.array_equal(plain.rgb, rgb)
+        mb = c.process_multiband_tiff(vv_f, vh_f, S.U16, S.ROBUST, 900, False)
+        assert np.array_equal(np.stack([mb.gray, mb.gray_band2]), mb_n)
+        for k, pos in enumerate(((rows - 3, cols - 5), (0, 0))):
+            w = vh_f.copy()
+            w[pos] = 1234.5
+            assert np.array_equal(c.process_synrgb_jpeg(vv_f, w, S.ROBUST, 1024, True).rgb, odd[k])
+    assert np.array_equal(from_u16, rgb)
+    O.set_resize_threads(os.cpu_count() or 1)
+    ref, _ = O.pipeline_synrgb_jpeg(vv_f, vh_f, S.CLAHE, 1024, True)
+    assert np.array_equal(rgb, ref), int((rgb != ref).sum())
+
+
 # ---- rasters whose width is not a multiple of 8 (re-pitched for the aligned kernels) ----------------------------------
 @pytest.mark.parametrize("cols", [4097, 4103, 5001])
 def test_repitched_raster_matches_oracle(ctx, cols, monkeypatch):

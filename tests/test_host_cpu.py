@@ -237,3 +237,133 @@ def test_read_resample_tables_replay_the_oracle(lib_built, in_size, out_size, al
     assert _ffi.lib().sarpro_read_row_plan_check(row.ctypes.data, in_size, out_size, alg, got.ctypes.data) == 0
     ref = O.read_band_resampled(row[None, :], out_size, 1, alg)[0]
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), int((got != ref).sum())
+
+
+_EDGE_CASES = [
+    # kind, low, high, gamma, n_levels, vmin, vmax
+    (0, -12.3, 14.7, 1.0, 65535, 1.0 / 1800.0, 1500.0),      # config 4: Equalized window of a VV/VH ratio, u16 levels
+    (0, -21.4, 3.9, 1.0, 65535, 1.6e-5, 0.999),              # normalised difference, u16
+    (0, -12.3, 14.7, 1.0, 255, 2e-3, 80.0),                  # u8 levels
+    (0, -0.7, -0.2, 1.0, 65535, 0.7, 1.2),                   # window narrower than 1 dB: range raised to 1, top levels unreachable
+    (0, -60.0, 90.0, 1.0, 65535, 1.1e-5, 3.0e8),             # window wider than the data
+    (0, 3.0, 9.0, 1.0, 65535, 2.5, 2.6),                     # data inside a sliver of the window
+    (0, -12.3, 14.7, 0.8, 65535, 2e-3, 80.0),                # gamma != 1: every entry by search
+    (0, -12.3, 14.7, 1.6, 255, 2e-3, 80.0),
+    (1, -18.0, 6.5, 1.0, 255, 1e-3, 40.0),                   # Tamed u8 levels
+    (2, -18.0, 6.5, 1.0, 255, 1e-3, 40.0),                   # CLAHE bins (a round): every entry by search
+    (-1, 0.0, 0.0, 1.0, 0, 1.0 / 1800.0, 1500.0),            # stat bins over the data range
+    (-1, 0.0, 0.0, 1.0, 0, 1.6e-5, 3.0e8),
+    (-1, 0.0, 0.0, 1.0, 0, 0.9991, 1.0007),                  # span of 7e-3 dB: bins 1.7e-6 dB wide
+    (-1, 0.0, 0.0, 1.0, 0, 1.0, 1.0000002),                  # two adjacent f32 values
+]
+
+
+@pytest.mark.parametrize("kind,low,high,gamma,n_levels,vmin,vmax", _EDGE_CASES)
+def test_f32_threshold_tables_analytic_equals_search(lib_built, kind, low, high, gamma, n_levels, vmin, vmax):
+    """The general f32 path's threshold tables (plan_f32.cpp) place most boundaries analytically (one exp per boundary, with
+    a margin argument) and search only the rest. The analytic table must equal, bit for bit, the table found by bracketing
+    every boundary with the reference's own f64 expression; and that table must have the threshold property under an
+    independent numpy evaluation of the expression (level(edge) >= k > level(previous f32))."""
+    import ctypes as C
+    na, bad = C.c_uint32(), C.c_uint32()
+    size = 4096 if kind < 0 else n_levels + 1
+    edges = np.zeros(size, np.float32)
+    rc = _ffi.lib().sarpro_f32_edges_check(kind, low, high, gamma, n_levels, vmin, vmax, C.byref(na), C.byref(bad),
+                                           edges.ctypes.data_as(C.c_void_p))
+    assert rc == size
+    assert bad.value == 0
+    vmin32, vmax32 = np.float32(vmin), np.float32(vmax)
+
+    def level(v):
+        db = 10.0 * np.log10(np.maximum(v.astype(np.float64), 1e-10))
+        if kind < 0:
+            lo_db, hi_db = 10.0 * np.log10(np.float64(vmin32)), 10.0 * np.log10(np.float64(vmax32))
+            t = np.clip((db - lo_db) * (1.0 / (hi_db - lo_db)), 0.0, 1.0)
+            return np.minimum((t * 4096.0).astype(np.int64), 4095)
+        rng = max(high - low, 1.0)
+        n = (np.clip(db, low, high) - low) / rng
+        if kind == 2:
+            return np.clip(np.floor(np.clip(n, 0.0, 1.0) * 255.0 + 0.5), 0, 255).astype(np.int64)   # f64::round, positive arguments
+        q = np.clip((n if gamma == 1.0 else np.power(n, gamma)) * float(n_levels), 0.0, float(n_levels))
+        return np.where(q >= n_levels, n_levels, q.astype(np.int64))
+
+    k = np.arange(1, size)
+    e = edges[1:]
+    finite = np.isfinite(e)
+    top = int(level(np.array([vmax32]))[0])
+    bottom = int(level(np.array([vmin32]))[0])
+    # unreachable levels are +inf, reachable ones lie in [vmin, vmax]
+    assert np.array_equal(finite, k <= top)
+    ef, kf = e[finite], k[finite]
+    assert np.all((ef >= vmin32) & (ef <= vmax32))
+    assert np.all(level(ef) >= kf)
+    inner = ef > vmin32                       # levels the smallest sample already reaches sit at vmin
+    assert np.all(kf[~inner] <= bottom)
+    assert np.all(level(np.nextafter(ef[inner], np.float32(0))) < kf[inner])
+    analytic_expected = gamma == 1.0 and kind != 2 and size > 2 and top - bottom > 8 and not (kind < 0 and vmax / vmin < 1.0001)
+    if analytic_expected:
+        assert na.value > 0.9 * (top - bottom - 1), (na.value, top, bottom)
+    if gamma != 1.0 or kind == 2:
+        assert na.value == 0
+
+
+def test_f32_threshold_tables_random_windows(lib_built):
+    """Same comparison over random windows, ranges and level counts (analytic == search on every entry)."""
+    import ctypes as C
+    r = np.random.default_rng(20251018)
+    na, bad = C.c_uint32(), C.c_uint32()
+    placed = 0
+    for i in range(40):
+        vmin = float(np.exp(r.uniform(np.log(1.1e-5), np.log(50.0))))
+        vmax = vmin * float(np.exp(r.uniform(0.0, 12.0)))
+        low = 10 * np.log10(vmin) + r.uniform(-3, 8)
+        high = low + r.uniform(0.2, 60.0)
+        kind = int(r.integers(-1, 2))
+        n_levels = 255 if kind == 1 else int(r.choice([255, 4095, 65535]))
+        rc = _ffi.lib().sarpro_f32_edges_check(kind, low, high, 1.0, n_levels, vmin, vmax, C.byref(na), C.byref(bad), None)
+        assert rc > 0 and bad.value == 0, (i, kind, low, high, n_levels, vmin, vmax, bad.value)
+        placed += na.value
+    assert placed > 100_000
+
+
+def test_host_narrowing_of_f32_rasters(lib_built):
+    """Large f32 host rasters are narrowed to their DN by the host threads before they cross PCIe (narrow.cpp). The rule is
+    the one of the reference's validity test (pipeline.rs:19-22: 10 log10(max(v, 1e-10)) > -50) plus 'is a u16': checked here
+    against numpy on u16-valued data with invalid samples mixed in, on every alignment of the vector loop, and on rasters that
+    are not u16-valued (which must be refused, wherever the offending sample sits)."""
+    import ctypes as C
+    lib = _ffi.lib()
+    r = np.random.default_rng(7)
+
+    def run(a):
+        out = np.zeros(a.size, np.uint16)
+        flag = C.c_int(-1)
+        assert lib.sarpro_narrow_f32_check(a.ctypes.data_as(C.c_void_p), a.size, out.ctypes.data_as(C.c_void_p), C.byref(flag)) == 0
+        return out, flag.value
+
+    for n in (0, 1, 7, 15, 16, 17, 31, 33, 1000, 256 * 1024 + 5, 3 * 256 * 1024 + 123):
+        dn = r.integers(0, 65536, n).astype(np.uint16)
+        a = dn.astype(np.float32)
+        special = r.random(n)
+        a[special < 0.02] = np.nan
+        a[(special >= 0.02) & (special < 0.04)] = -3.0
+        a[(special >= 0.04) & (special < 0.06)] = 0.0
+        a[(special >= 0.06) & (special < 0.08)] = 9.9e-6          # below -50 dB
+        a[(special >= 0.08) & (special < 0.09)] = -np.inf
+        a[(special >= 0.09) & (special < 0.10)] = -0.5             # not a whole number, but not valid either
+        with np.errstate(invalid="ignore", divide="ignore"):
+            valid = 10.0 * np.log10(np.maximum(a.astype(np.float64), 1e-10)) > -50.0
+        want = np.where(valid, np.nan_to_num(a, nan=0.0, posinf=0.0, neginf=0.0), 0).astype(np.uint16)
+        for off in (0, 1, 3):                                     # unaligned starts of the source
+            got, ok = run(np.ascontiguousarray(a[off:]))
+            assert ok == 1
+            assert np.array_equal(got, want[off:])
+    # not u16-valued: a fraction, a value above 65535, +inf, 1e-5 (valid: -50 dB + a hair, and not a whole number)
+    base = r.integers(1, 2000, 3 * 256 * 1024).astype(np.float32)
+    for bad in (0.5, 1234.25, 65536.0, 1e9, np.inf, 1.0001e-5):
+        for pos in (0, 5, 16, base.size // 2 + 3, base.size - 1):
+            a = base.copy()
+            a[pos] = bad
+            assert run(a)[1] == 0, (bad, pos)
+    assert run(base)[1] == 1
+    assert run(np.full(40, 65535.0, np.float32)) [1] == 1
