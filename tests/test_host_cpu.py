@@ -335,11 +335,14 @@ def test_host_narrowing_of_f32_rasters(lib_built):
     lib = _ffi.lib()
     r = np.random.default_rng(7)
 
-    def run(a):
-        out = np.zeros(a.size, np.uint16)
+    def run(a, dst_off=0):
+        # dst_off shifts the destination: 32-byte aligned destinations take the non-temporal stores of the staging path
+        buf = np.zeros(a.size + 64, np.uint16)
+        base = (-buf.ctypes.data // 2) % 16          # elements up to the next 32-byte boundary
+        out = buf[base + dst_off: base + dst_off + a.size]
         flag = C.c_int(-1)
         assert lib.sarpro_narrow_f32_check(a.ctypes.data_as(C.c_void_p), a.size, out.ctypes.data_as(C.c_void_p), C.byref(flag)) == 0
-        return out, flag.value
+        return out.copy(), flag.value
 
     for n in (0, 1, 7, 15, 16, 17, 31, 33, 1000, 256 * 1024 + 5, 3 * 256 * 1024 + 123):
         dn = r.integers(0, 65536, n).astype(np.uint16)
@@ -355,9 +358,10 @@ def test_host_narrowing_of_f32_rasters(lib_built):
             valid = 10.0 * np.log10(np.maximum(a.astype(np.float64), 1e-10)) > -50.0
         want = np.where(valid, np.nan_to_num(a, nan=0.0, posinf=0.0, neginf=0.0), 0).astype(np.uint16)
         for off in (0, 1, 3):                                     # unaligned starts of the source
-            got, ok = run(np.ascontiguousarray(a[off:]))
-            assert ok == 1
-            assert np.array_equal(got, want[off:])
+            for dst_off in (0, 1, 8):
+                got, ok = run(np.ascontiguousarray(a[off:]), dst_off)
+                assert ok == 1
+                assert np.array_equal(got, want[off:])
     # not u16-valued: a fraction, a value above 65535, +inf, 1e-5 (valid: -50 dB + a hair, and not a whole number)
     base = r.integers(1, 2000, 3 * 256 * 1024).astype(np.float32)
     for bad in (0.5, 1234.25, 65536.0, 1e9, np.inf, 1.0001e-5):
