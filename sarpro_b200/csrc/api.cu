@@ -846,10 +846,9 @@ int dn_band_with_preset_lut(sarpro_ctx* ctx, int b, const BandJob& j, const uint
 }
 
 // ---- inputs ----------------------------------------------------------------------------------------
-// Brings band `in` (optionally op(in, in2)) to a u16 DN raster on the device. Returns SARPRO_ERR_INTERNAL + flag
-// when the samples are not u16-valued (general f32 path).
 // Narrowing upload of a large f32 host raster (see stage_band). Returns 0 when every chunk is queued on the copy stream,
-// 1 when the raster is not u16-valued (copy stream drained, nothing of this band left in flight), < 0 on errors.
+// 1 when the raster has to go up as f32 (it is not u16-valued, or there is no pinned memory for the staging slots; the copy
+// stream is drained, nothing of this band is left in flight), < 0 on errors.
 static int narrow_and_stream(sarpro_ctx* ctx, int b, const sarpro_band* in, const uint16_t** dn_out) {
     BandWs& w = ctx->band[b];
     const uint64_t n = in->rows * in->cols;
@@ -864,7 +863,14 @@ static int narrow_and_stream(sarpro_ctx* ctx, int b, const sarpro_band* in, cons
         }
         ctx->narrow_ring_bytes = 0;
         for (int s = 0; s < 2; ++s) {
-            CU(cudaHostAlloc(&ctx->narrow_ring[s], slot_bytes, cudaHostAllocDefault));
+            if (cudaHostAlloc(&ctx->narrow_ring[s], slot_bytes, cudaHostAllocDefault) != cudaSuccess) {
+                // no pinned memory to spare (locked-memory limit): not an error of the call, the raster goes up as f32
+                cudaGetLastError();
+                ctx->narrow_ring[s] = nullptr;
+                if (s == 1) { cudaFreeHost(ctx->narrow_ring[0]); ctx->narrow_ring[0] = nullptr; }
+                ctx->narrow_upload = 0;
+                return 1;
+            }
             if (!ctx->ev_ring[s]) CU(cudaEventCreateWithFlags(&ctx->ev_ring[s], cudaEventDisableTiming));
         }
         ctx->narrow_ring_bytes = slot_bytes;
@@ -905,6 +911,9 @@ static int narrow_and_stream(sarpro_ctx* ctx, int b, const sarpro_band* in, cons
     return 0;
 }
 
+// Brings band `in` (optionally op(in, in2)) to a u16 DN raster on the device; *integral = false when the samples are not
+// u16-valued (general f32 path). may_stream: large host rasters may arrive in row chunks on the copy stream (the caller's next
+// consumer of the raster is pass A, which waits per chunk).
 int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band* in2, int op, const uint16_t** dn_out,
                bool* integral, bool may_stream) {
     BandWs& w = ctx->band[b];
@@ -963,7 +972,7 @@ int stage_band(sarpro_ctx* ctx, int b, const sarpro_band* in, const sarpro_band*
         // the bytes, pass A per chunk. A chunk with a sample that is not a DN ends the attempt: the raster goes up as f32 below.
         int rc = narrow_and_stream(ctx, b, in, dn_out);
         if (rc <= 0) return rc;          // 0: queued; < 0: error
-        ctx->streamed[b].n_chunks = 0;   // 1: not u16-valued
+        ctx->streamed[b].n_chunks = 0;   // 1: goes up as f32
     }
     const float* fa = (const float*)in->data;
     const float* fb = op >= 0 ? (const float*)in2->data : nullptr;

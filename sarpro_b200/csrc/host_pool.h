@@ -2,6 +2,7 @@
 // rasters on their way to the device). Header-only; one pool per process.
 #pragma once
 #include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -14,10 +15,10 @@
 namespace sarpro {
 
 // ---- worker pool ------------------------------------------------------------------------------
-// The threshold tables of a two-operation call are 2 x (4,095 + 65,535) independent searches of ~0.1 us each: a few ms of
-// serial work that sits on the critical path between two kernels. Spawning 16 threads per table cost more than the
-// searches themselves; the workers are therefore created once per process and woken per table. Chunks are pulled from an
-// atomic counter, the calling thread works too. One job at a time (contexts on other threads queue on `gate`).
+// The host work of a call sits on its critical path between two kernels or ahead of an upload (threshold tables: 2 x (4,095 +
+// 65,535) independent boundaries per two-operation call; narrowing: 100 MB row chunks). Spawning 16 threads per table cost
+// more than the table itself; the workers are therefore created once per process and woken per job. Chunks are pulled from
+// an atomic counter, the calling thread works too. One job at a time (contexts on other threads queue on `gate`).
 class WorkerPool {
 public:
     static WorkerPool& get() {
@@ -53,7 +54,10 @@ public:
 
 private:
     WorkerPool() {
-        const unsigned hw = std::thread::hardware_concurrency();
+        // the CPUs this process may run on (a rank of a multi-process job is often confined to a subset), at most 16
+        unsigned hw = std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = (unsigned)CPU_COUNT(&set);
         n_workers_ = hw > 1 ? std::min(16u, hw) - 1 : 0;
         for (unsigned i = 0; i < n_workers_; ++i) std::thread([this] { loop(); }).detach();
     }
