@@ -371,3 +371,69 @@ def test_host_narrowing_of_f32_rasters(lib_built):
             assert run(a)[1] == 0, (bad, pos)
     assert run(base)[1] == 1
     assert run(np.full(40, 65535.0, np.float32)) [1] == 1
+
+
+def test_planner_matches_oracle_on_random_distributions(lib_built):
+    """Randomised version of test_planner_matches_oracle: uniform, speckle at five brightness levels, constant, half-invalid,
+    three-valued, near-constant Gaussian, almost-empty and log-uniform rasters of random small shapes; every strategy and bit
+    depth. Statistics bit-exact, LUT applied to the DNs == the oracle's samples."""
+    rng = np.random.default_rng(2026)
+    for it in range(24):
+        rows, cols = int(rng.integers(3, 120)), int(rng.integers(3, 160))
+        kind = it % 8
+        if kind == 0:
+            dn = rng.integers(0, 65536, (rows, cols))
+        elif kind == 1:
+            dn = np.rint(np.sqrt(rng.gamma(4.4, 1 / 4.4, (rows, cols))) * rng.choice([3, 30, 150, 900, 5000])).clip(0, 65535)
+        elif kind == 2:
+            dn = np.full((rows, cols), int(rng.integers(0, 65536)))
+        elif kind == 3:
+            dn = np.rint(np.sqrt(rng.gamma(1.0, 1.0, (rows, cols))) * 100).clip(0, 65535)
+            dn[rng.random((rows, cols)) < 0.4] = 0
+        elif kind == 4:
+            dn = rng.choice([1, 2, 65535], (rows, cols), p=[.5, .49, .01])
+        elif kind == 5:
+            dn = np.rint(rng.normal(1000, rng.choice([0.5, 3, 30]), (rows, cols))).clip(0, 65535)
+        elif kind == 6:
+            dn = np.zeros((rows, cols))
+            dn.ravel()[:int(rng.integers(0, 4))] = rng.integers(1, 65536)
+        else:
+            dn = np.rint(np.exp(rng.uniform(0, np.log(65535), (rows, cols))))
+        dn = dn.astype(np.uint16)
+        hist = np.bincount(dn.ravel(), minlength=65536).astype(np.uint64)
+        v = dn.astype(np.float32)
+        for strategy in range(7):
+            for bit_depth in (S.U8, S.U16):
+                st, lut = S.plan_from_dn_histogram(hist, bit_depth, strategy)
+                po = O.process_scalar_data_pipeline(v, bit_depth, strategy)
+                for k in EXACT:
+                    a, b = getattr(st, k), getattr(po.stats, k)
+                    assert a == b or (a != a and b != b), (it, strategy, bit_depth, k, a, b)
+                if strategy != S.CLAHE:
+                    ref = po.u8 if bit_depth == S.U8 else po.u16
+                    assert np.array_equal(lut[dn].astype(ref.dtype), ref), (it, strategy, bit_depth)
+
+
+def test_tensor_core_tap_plan_on_random_axes(lib_built):
+    """Randomised version of test_tensor_core_tap_plan_replays_the_horizontal_pass: random widths (mostly multiples of 8),
+    scale factors 1..40, strip lengths and CLAHE spans; wherever a plan exists its replay equals the direct pass."""
+    rng = np.random.default_rng(12345)
+    plans = 0
+    for _ in range(150):
+        in_size = int(rng.integers(64, 30000))
+        if rng.random() < 0.8:
+            in_size = (in_size + 7) // 8 * 8
+        out_size = max(1, int(in_size / float(np.exp(rng.uniform(0.0, np.log(40.0))))))
+        max_span = int(rng.choice([0, (in_size + 7) // 8, 512]))
+        strip_nt = int(rng.choice([0, 32, 16, 8, 4, 2, 1]))
+        row = rng.integers(0, 256, in_size).astype(np.uint8)
+        if rng.random() < 0.3:
+            row[: in_size // 5] = 255
+        direct = np.zeros(out_size, np.uint8)
+        replay = np.full(out_size, 7, np.uint8)
+        rc = _ffi.lib().sarpro_lanczos_row_plan_check(row.ctypes.data, in_size, out_size, max_span, strip_nt, direct.ctypes.data, replay.ctypes.data)
+        assert rc in (0, 1), (rc, in_size, out_size, max_span, strip_nt)
+        if rc == 1:
+            plans += 1
+            assert np.array_equal(direct, replay), (in_size, out_size, max_span, strip_nt)
+    assert plans > 40
