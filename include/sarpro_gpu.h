@@ -355,6 +355,14 @@ int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float mi
 int sarpro_f32_edges_check(int kind, double low_db, double high_db, double gamma, uint32_t n_levels, float min_v, float max_v,
                            uint32_t* n_analytic, uint32_t* n_mismatch, float* edges_out);
 
+/* Test hook (host only): the host step of the general f32 path between its histogram pass and its quantisation pass (api_f32.cu):
+ * percentiles from the 4096-bin stat histogram over [dB(min_v), dB(max_v)] (autoscale.rs:103-160) and the strategy's window
+ * (autoscale.rs:404-428, 492-562; tamed_synrgb_kind 1 / 2 = the co- / cross-pol windows of :719-728, 0 = the strategy's).
+ * Together with sarpro_f32_edges_check the CPU tests replay the whole path (numpy stands in for the comparing kernels) against
+ * the oracle. */
+int sarpro_plan_from_stat_histogram(const uint64_t* hist4096, uint64_t valid_count, float min_v, float max_v, double mean_db, double std_db,
+                                    int strategy, int tamed_synrgb_kind, sarpro_stats* stats);
+
 /* Test hook (host only): the host-side narrowing the pipelines apply to large f32 HOST rasters on their way to the device
  * (the reference's boundary is the f32 raster GDAL made of a u16 band, gdal.rs:123; narrowing halves the PCIe bytes). dst[i]
  * = the DN of src[i]: 0 for samples that are not valid (negative, NaN, <= -50 dB: pipeline.rs:19-22), the sample itself

@@ -1433,6 +1433,20 @@ int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float mi
     return SARPRO_OK;
 }
 
+int sarpro_plan_from_stat_histogram(const uint64_t* hist4096, uint64_t valid_count, float min_v, float max_v, double mean_db, double std_db,
+                                    int strategy, int tamed_synrgb_kind, sarpro_stats* stats) {
+    if (!hist4096 || !stats || strategy < SARPRO_STRATEGY_STANDARD || strategy > SARPRO_STRATEGY_DEFAULT || tamed_synrgb_kind < 0 ||
+        tamed_synrgb_kind > 2)
+        return SARPRO_ERR_INVALID_ARGUMENT;
+    std::memset(stats, 0, sizeof(*stats));
+    if (valid_count == 0) return SARPRO_OK;
+    // the sequence of api_f32.cu after its second pass
+    stats_from_stat_histogram(hist4096, valid_count, db_of_sample(min_v), db_of_sample(max_v), mean_db, std_db, stats);
+    choose_window(strategy, tamed_synrgb_kind == 0 ? PlanKind::Autoscale : (tamed_synrgb_kind == 1 ? PlanKind::TamedSynRgbCopol : PlanKind::TamedSynRgbCross),
+                  stats);
+    return SARPRO_OK;
+}
+
 int sarpro_narrow_f32_check(const float* src, size_t n, uint16_t* dst, int* u16_valued) {
     if ((n && (!src || !dst)) || !u16_valued) return SARPRO_ERR_INVALID_ARGUMENT;
     *u16_valued = narrow_f32_to_dn(src, dst, n, valid_threshold()) ? 1 : 0;

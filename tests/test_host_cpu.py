@@ -437,3 +437,83 @@ def test_tensor_core_tap_plan_on_random_axes(lib_built):
             plans += 1
             assert np.array_equal(direct, replay), (in_size, out_size, max_span, strip_nt)
     assert plans > 40
+
+
+def _valid_threshold_f32():
+    """Smallest f32 whose dB (pipeline.rs:19-20) exceeds -50 (pipeline.rs:22)."""
+    lo, hi = np.float32(0.0).view(np.uint32), np.float32(1.0).view(np.uint32)
+    while hi - lo > 1:
+        mid = np.uint32((int(lo) + int(hi)) // 2)
+        if 10.0 * np.log10(max(float(mid.view(np.float32)), 1e-10)) > -50.0:
+            hi = mid
+        else:
+            lo = mid
+    return hi.view(np.float32)
+
+
+def _f32_edges(kind, low, high, gamma, n_levels, vmin, vmax):
+    import ctypes as C
+    size = 4096 if kind < 0 else n_levels + 1
+    edges = np.zeros(size, np.float32)
+    na, bad = C.c_uint32(), C.c_uint32()
+    assert _ffi.lib().sarpro_f32_edges_check(kind, low, high, gamma, n_levels, vmin, vmax, C.byref(na), C.byref(bad),
+                                             edges.ctypes.data_as(C.c_void_p)) == size
+    assert bad.value == 0
+    return edges
+
+
+@pytest.mark.parametrize("make", ["ratio", "ndiff", "scaled", "narrow"])
+@pytest.mark.parametrize("strategy", range(7))
+def test_general_f32_path_host_logic_replays_the_oracle(lib_built, make, strategy):
+    """The general f32 path (rasters that are not u16-valued: polarization products, calibrated inputs) on the CPU: the device
+    kernels only COMPARE samples with host-built threshold tables, so numpy's searchsorted stands in for them and the product's
+    own host steps do the rest - stat-bin thresholds, percentiles and window from the 4096-bin histogram, level thresholds.
+    The replay must give the oracle's statistics bit for bit and its u16 / u8 samples (CLAHE: its bins) for every strategy."""
+    import ctypes as C
+    rng = np.random.default_rng(strategy * 10 + len(make))
+    a = np.rint(np.sqrt(rng.gamma(4.4, 1 / 4.4, (97, 131))) * 150).astype(np.float32)
+    b = np.rint(np.sqrt(rng.gamma(4.4, 1 / 4.4, (97, 131))) * 50).astype(np.float32)
+    a[:, :5] = 0
+    b[40:44, :] = 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if make == "ratio":
+            v = np.where(np.abs(b) > 1e-10, a / b, np.float32(0)).astype(np.float32)            # ops.rs:9-19
+        elif make == "ndiff":
+            v = np.where(np.abs(a + b) > 1e-10, (a - b) / (a + b), np.float32(0)).astype(np.float32)  # ops.rs:22-33 (half of it negative: invalid)
+        elif make == "scaled":
+            v = (a * np.float32(0.0371)).astype(np.float32)                                       # a calibrated-looking raster
+        else:
+            v = (np.float32(2.5) + rng.random((97, 131)).astype(np.float32) * np.float32(0.3)).astype(np.float32)  # < 1 dB of range
+    thr = _valid_threshold_f32()
+    valid = v >= thr
+    assert valid.any()
+    vmin, vmax = float(v[valid].min()), float(v[valid].max())
+    # pass 2 of the device: stat-bin index = number of thresholds <= sample
+    se = _f32_edges(-1, 0.0, 0.0, 1.0, 0, vmin, vmax)
+    idx = np.searchsorted(se[1:], v[valid], side="right")
+    hist = np.bincount(idx, minlength=4096).astype(np.uint64)
+    db = 10.0 * np.log10(v[valid].astype(np.float64))
+    for bit_depth in (S.U8, S.U16):
+        po = O.process_scalar_data_pipeline(v, bit_depth, strategy)
+        st = _ffi.Stats()
+        assert _ffi.lib().sarpro_plan_from_stat_histogram(hist.ctypes.data_as(C.c_void_p), int(valid.sum()), vmin, vmax, float(db.mean()),
+                                                          float(db.std()), strategy, 0, C.byref(st)) == 0
+        for k in EXACT:
+            x, y = getattr(st, k), getattr(po.stats, k)
+            assert x == y or (x != x and y != y), (k, x, y)
+        if strategy == S.CLAHE:
+            le = _f32_edges(2, st.low_clip, st.high_clip, 1.0, 255, vmin, vmax)
+            bins = np.searchsorted(le[1:], v[valid], side="right")
+            rng_db = max(st.high_clip - st.low_clip, 1.0)
+            want = np.floor(np.clip((np.clip(db, st.low_clip, st.high_clip) - st.low_clip) / rng_db, 0, 1) * 255.0 + 0.5).astype(np.int64)
+            assert np.array_equal(bins, want)   # autoscale.rs:585-587, 263 (the rest of CLAHE runs on the DN machinery, tested elsewhere)
+            continue
+        # pass 3: level = number of level thresholds <= sample; invalid samples are written as 0 (autoscale.rs:437-447)
+        n_levels = 255 if bit_depth == S.U8 else 65535
+        le = _f32_edges(0, st.low_clip, st.high_clip, st.gamma, n_levels, vmin, vmax)
+        q = np.zeros(v.shape, np.uint16)
+        q[valid] = np.searchsorted(le[1:], v[valid], side="right")
+        if bit_depth == S.U16:
+            assert np.array_equal(q, po.u16), int((q != po.u16).sum())
+        else:
+            assert np.array_equal(O.scale_u16_to_u8(q), po.u8)   # autoscale.rs:669-670
