@@ -355,6 +355,14 @@ int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float mi
 int sarpro_f32_edges_check(int kind, double low_db, double high_db, double gamma, uint32_t n_levels, float min_v, float max_v,
                            uint32_t* n_analytic, uint32_t* n_mismatch, float* edges_out);
 
+/* Test hook (host only): one of the 42 channel-LUT sets the synthetic-RGB kernels read (set 0..40: the suppressed variant for that
+ * floor_with_cushion, synthetic_rgb.rs:115-154; 41: the default variant, :10-50; -1: the suppressed set chosen from the combined
+ * 256-bin histogram of both u8 bands, :92-113, the rule k_synrgb_floor applies on the device). lut_r / lut_g: 256 entries,
+ * lut_b: 65536 entries indexed (band1 << 8) | band2. The CPU tests compose every (band1, band2) pair through them and
+ * compare with the oracle. */
+int sarpro_synrgb_lut_check(int set, const uint32_t* hist256, uint64_t n_per_band, int* floor_with_cushion, uint8_t* lut_r, uint8_t* lut_g,
+                            uint8_t* lut_b);
+
 /* Test hook (host only): the host step of the general f32 path between its histogram pass and its quantisation pass (api_f32.cu):
  * percentiles from the 4096-bin stat histogram over [dB(min_v), dB(max_v)] (autoscale.rs:103-160) and the strategy's window
  * (autoscale.rs:404-428, 492-562; tamed_synrgb_kind 1 / 2 = the co- / cross-pol windows of :719-728, 0 = the strategy's).

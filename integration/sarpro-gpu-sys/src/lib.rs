@@ -166,6 +166,7 @@ extern "C" {
     pub fn sarpro_read_row_plan_check(samples: *const u16, in_size: usize, out_size: usize, alg: c_int, out: *mut f32) -> c_int;
     pub fn sarpro_f32_guard_params(low_db: f64, range_db: f64, n: u32, min_v: f32, max_v: f32, e0: *mut c_int, f0: *mut f32, scale: *mut f32, guard: *mut f32) -> c_int;
     pub fn sarpro_f32_edges_check(kind: c_int, low_db: f64, high_db: f64, gamma: f64, n_levels: u32, min_v: f32, max_v: f32, n_analytic: *mut u32, n_mismatch: *mut u32, edges_out: *mut f32) -> c_int;
+    pub fn sarpro_synrgb_lut_check(set: c_int, hist256: *const u32, n_per_band: u64, floor_with_cushion: *mut c_int, lut_r: *mut u8, lut_g: *mut u8, lut_b: *mut u8) -> c_int;
     pub fn sarpro_plan_from_stat_histogram(hist4096: *const u64, valid_count: u64, min_v: f32, max_v: f32, mean_db: f64, std_db: f64, strategy: c_int, tamed_synrgb_kind: c_int, stats: *mut sarpro_stats) -> c_int;
     pub fn sarpro_narrow_f32_check(src: *const f32, n: usize, dst: *mut u16, u16_valued: *mut c_int) -> c_int;
 }

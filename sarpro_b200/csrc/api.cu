@@ -1433,6 +1433,20 @@ int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float mi
     return SARPRO_OK;
 }
 
+int sarpro_synrgb_lut_check(int set, const uint32_t* hist256, uint64_t n_per_band, int* floor_with_cushion, uint8_t* lut_r, uint8_t* lut_g,
+                            uint8_t* lut_b) {
+    if (set < -1 || set > (int)kSynRgbDefaultSet || !lut_r || !lut_g || !lut_b || (set < 0 && !hist256)) return SARPRO_ERR_INVALID_ARGUMENT;
+    if (set < 0) set = synrgb_floor_from_histogram(hist256, n_per_band); // the host mirror of k_synrgb_floor
+    if (floor_with_cushion) *floor_with_cushion = set == (int)kSynRgbDefaultSet ? -1 : set;
+    SynRgbLut l; // built exactly like the sets load_rgb_luts uploads
+    if (set == (int)kSynRgbDefaultSet) build_synrgb_default_lut(&l);
+    else build_synrgb_suppressed_lut(set, &l);
+    std::memcpy(lut_r, l.r, 256);
+    std::memcpy(lut_g, l.g, 256);
+    std::memcpy(lut_b, l.b.data(), 65536);
+    return SARPRO_OK;
+}
+
 int sarpro_plan_from_stat_histogram(const uint64_t* hist4096, uint64_t valid_count, float min_v, float max_v, double mean_db, double std_db,
                                     int strategy, int tamed_synrgb_kind, sarpro_stats* stats) {
     if (!hist4096 || !stats || strategy < SARPRO_STRATEGY_STANDARD || strategy > SARPRO_STRATEGY_DEFAULT || tamed_synrgb_kind < 0 ||

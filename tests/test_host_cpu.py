@@ -517,3 +517,44 @@ def test_general_f32_path_host_logic_replays_the_oracle(lib_built, make, strateg
             assert np.array_equal(q, po.u16), int((q != po.u16).sum())
         else:
             assert np.array_equal(O.scale_u16_to_u8(q), po.u8)   # autoscale.rs:669-670
+
+
+def _synrgb_through_product_luts(b1, b2, suppressed):
+    """Composes RGB the way k_synrgb does, from the product's host-built LUT set (and, for the suppressed variant, the host
+    mirror of the device's floor rule on the combined histogram)."""
+    import ctypes as C
+    r, g, b = np.zeros(256, np.uint8), np.zeros(256, np.uint8), np.zeros(65536, np.uint8)
+    fwc = C.c_int(-7)
+    hist = (np.bincount(b1.ravel(), minlength=256) + np.bincount(b2.ravel(), minlength=256)).astype(np.uint32)
+    rc = _ffi.lib().sarpro_synrgb_lut_check(-1 if suppressed else 41, hist.ctypes.data_as(C.c_void_p), b1.size, C.byref(fwc),
+                                            r.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    v1, v2 = b1.astype(np.int64), b2.astype(np.int64)
+    rgb = np.stack([r[v1], g[v2], b[(v1 << 8) | v2]], axis=-1)
+    if suppressed:
+        rgb[(v1 <= fwc.value) & (v2 <= fwc.value)] = 0   # water short-circuit, synthetic_rgb.rs:160-166
+    return rgb, fwc.value
+
+
+def test_synrgb_lut_sets_match_the_oracle_on_every_pair(lib_built):
+    """Every (band1, band2) pair of u8 samples through the product's channel LUTs == the oracle's create_synthetic_rgb /
+    _suppressed (synthetic_rgb.rs:10-67, 88-178). The suppressed variant depends on the data through floor_with_cushion (p05 of
+    the combined histogram + 3, capped at 40): the 65,536-pair grid is extended with a run of one dark value so that the
+    floor sweeps its whole range 3..40, and with bright pixels so that it stays at the bottom."""
+    g1, g2 = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    g1, g2 = g1.ravel(), g2.ravel()
+    got, _ = _synrgb_through_product_luts(g1[None, :], g2[None, :], False)
+    assert np.array_equal(got, O.create_synthetic_rgb(g1[None, :], g2[None, :]))
+    floors = set()
+    for p in list(range(0, 45)) + [60, 200]:
+        # p05 of the grid alone is 12; a run of value p long enough pulls it to p (below 12) or pushes it up to p (above)
+        extra = int((6553.6 - 512 * (p + 1)) / 0.95) + 50 if p <= 12 else 10240 * p - 131072 + 3000
+        for fill in (p, 255):
+            run = np.full(max(extra, 0) // 2 + 1, fill, np.uint8)
+            b1 = np.concatenate([g1, run])[None, :]
+            b2 = np.concatenate([g2, run])[None, :]
+            got, fwc = _synrgb_through_product_luts(b1, b2, True)
+            floors.add(fwc)
+            ref = O.create_synthetic_rgb_suppressed(b1, b2)
+            assert np.array_equal(got, ref), (p, fill, fwc, int((got != ref).any(axis=-1).sum()))
+    assert floors == set(range(3, 41)), sorted(floors)   # every suppressed set the device holds except 0..2 (unreachable: +3)
