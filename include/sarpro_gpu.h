@@ -333,6 +333,10 @@ int sarpro_plan_kind_from_dn_histogram(const uint64_t* hist65536, int bit_depth,
 int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t out_size, size_t max_span, size_t strip_ntiles,
                                   uint8_t* out_direct, uint8_t* out_replay);
 
+/* Test hook (host only): one row of u16 samples through the Lanczos3 table of the u16 kernels (i32 taps, i64 accumulate: the
+ * crate's U16 convolution, resize.rs:62-81) in the kernels' arithmetic. The CPU tests compare it with the oracle. */
+int sarpro_lanczos_row_check_u16(const uint16_t* samples, size_t in_size, size_t out_size, uint16_t* out);
+
 /* Test hook (host only): one row of u16 samples through the downsample-on-read tables the kernels use (plan_read.cpp: spans and
  * weights of GDAL's Average / Lanczos resampling, see sarpro_read_band_resampled), accumulated in f64 in the kernels' order.
  * out has out_size f32 samples. No GPU needed: the CPU tests compare it with the oracle's restatement. */

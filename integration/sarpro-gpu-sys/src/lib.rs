@@ -163,6 +163,7 @@ extern "C" {
     pub fn sarpro_plan_on_device(ctx: *mut sarpro_ctx, hist65536: *const u32, bit_depth: c_int, strategy: c_int, plan_kind: c_int, stats: *mut sarpro_stats, lut16: *mut u16, hot2: *mut u32) -> c_int;
     pub fn sarpro_plan_kind_from_dn_histogram(hist65536: *const u64, bit_depth: c_int, strategy: c_int, plan_kind: c_int, stats: *mut sarpro_stats, lut16: *mut u16, hot2: *mut u32) -> c_int;
     pub fn sarpro_lanczos_row_plan_check(samples: *const u8, in_size: usize, out_size: usize, max_span: usize, strip_ntiles: usize, out_direct: *mut u8, out_replay: *mut u8) -> c_int;
+    pub fn sarpro_lanczos_row_check_u16(samples: *const u16, in_size: usize, out_size: usize, out: *mut u16) -> c_int;
     pub fn sarpro_read_row_plan_check(samples: *const u16, in_size: usize, out_size: usize, alg: c_int, out: *mut f32) -> c_int;
     pub fn sarpro_f32_guard_params(low_db: f64, range_db: f64, n: u32, min_v: f32, max_v: f32, e0: *mut c_int, f0: *mut f32, scale: *mut f32, guard: *mut f32) -> c_int;
     pub fn sarpro_f32_edges_check(kind: c_int, low_db: f64, high_db: f64, gamma: f64, n_levels: u32, min_v: f32, max_v: f32, n_analytic: *mut u32, n_mismatch: *mut u32, edges_out: *mut f32) -> c_int;

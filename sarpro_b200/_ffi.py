@@ -140,6 +140,7 @@ SYMBOLS = {
     "sarpro_f32_guard_params": (_I, [C.c_double, C.c_double, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "sarpro_lanczos_row_plan_check": (_I, [_P, _SZ, _SZ, _SZ, _SZ, _P, _P]),
+    "sarpro_lanczos_row_check_u16": (_I, [_P, _SZ, _SZ, _P]),
     "sarpro_synrgb_lut_check": (_I, [_I, _P, C.c_uint64, C.POINTER(C.c_int), _P, _P, _P]),
     "sarpro_plan_from_stat_histogram": (_I, [_P, C.c_uint64, C.c_float, C.c_float, C.c_double, C.c_double, _I, _I, C.POINTER(Stats)]),
     "sarpro_narrow_f32_check": (_I, [_P, _SZ, _P, C.POINTER(C.c_int)]),

@@ -1426,6 +1426,19 @@ int sarpro_lanczos_row_plan_check(const uint8_t* samples, size_t in_size, size_t
     return 1;
 }
 
+int sarpro_lanczos_row_check_u16(const uint16_t* samples, size_t in_size, size_t out_size, uint16_t* out) {
+    if (!samples || !out || in_size == 0 || out_size == 0) return SARPRO_ERR_INVALID_ARGUMENT;
+    ResampleAxis ax;
+    build_lanczos3_axis((uint32_t)in_size, (uint32_t)out_size, true, &ax); // the table k_hresize<., PIX16> / k_vresize read
+    for (uint32_t ox = 0; ox < out_size; ++ox) { // fast_image_resize u16 pass: i32 taps, i64 accumulate from 1 << (p - 1), >> p, clamp
+        long long acc = ax.precision > 0 ? (1ll << (ax.precision - 1)) : 0ll;
+        for (uint32_t k = 0; k < ax.size[ox]; ++k) acc += (long long)ax.coef[(size_t)ox * ax.window + k] * (long long)samples[ax.start[ox] + k];
+        const long long v = acc >> ax.precision;
+        out[ox] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+    }
+    return SARPRO_OK;
+}
+
 int sarpro_f32_guard_params(double low_db, double range_db, uint32_t n, float min_v, float max_v, int* e0, float* f0, float* scale,
                             float* guard) {
     if (!e0 || !f0 || !scale || !guard) return SARPRO_ERR_INVALID_ARGUMENT;

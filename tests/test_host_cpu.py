@@ -558,3 +558,20 @@ def test_synrgb_lut_sets_match_the_oracle_on_every_pair(lib_built):
             ref = O.create_synthetic_rgb_suppressed(b1, b2)
             assert np.array_equal(got, ref), (p, fill, fwc, int((got != ref).any(axis=-1).sum()))
     assert floors == set(range(3, 41)), sorted(floors)   # every suppressed set the device holds except 0..2 (unreachable: +3)
+
+
+def test_u16_lanczos_table_replays_the_oracle(lib_built):
+    """The u16 Lanczos3 table of the product (i32 taps, i64 accumulate; the vertical pass and the generic horizontal kernel read
+    it) on single rows == the oracle's resize_u16_image: fixed shapes around the reference's sizes and random ones, with
+    saturated runs at both ends of the range (the negative lobes must clamp identically)."""
+    rng = np.random.default_rng(5)
+    shapes = [(25000, 2048), (16000, 1311), (4096, 2048), (1000, 999), (1000, 1000), (77, 3), (8, 1), (5003, 512)]
+    shapes += [(int(n), max(1, int(n / float(np.exp(rng.uniform(0, np.log(30))))))) for n in rng.integers(8, 20000, 40)]
+    for in_size, out_size in shapes:
+        row = rng.integers(0, 65536, in_size).astype(np.uint16)
+        row[: in_size // 6] = 65535
+        row[-(in_size // 9) - 1:] = 0
+        got = np.zeros(out_size, np.uint16)
+        assert _ffi.lib().sarpro_lanczos_row_check_u16(row.ctypes.data, in_size, out_size, got.ctypes.data) == 0
+        ref = np.asarray(O.resize_u16_image(row[None, :], out_size, 1)).reshape(-1)
+        assert np.array_equal(got, ref), (in_size, out_size, int((got != ref).sum()))
